@@ -1,0 +1,341 @@
+/*
+ * nbvh_b200.h -- C ABI of libnbvh_b200.so: the B200-native (sm_100a) neural ray-query hot path of N-BVH.
+ *
+ * This is the drop-in boundary for the reference's `NeuralBVHModule` / `NeuralPathModule`
+ * (/root/reference/include/cuda/neural/neural_bvh_module.h:144-241,
+ *  /root/reference/include/cuda/neural/path/path_module.h:256-345) and for the tiny-cuda-nn surface the
+ * renderer touches through it (`network->inference`, `trainer->training_step`, `serialize/deserialize`,
+ * `n_params`; /root/reference/src/cuda/neural/path/path_module.cu:92,
+ * /root/reference/src/cuda/neural/neural_bvh_renderer.cu:172-175,
+ * /root/reference/src/cuda/neural/neural_bvh_renderer_init.cu:385-404).
+ *
+ * Conventions: opaque context; every call returns 0 on success or a negative nbvh_status, and
+ * nbvh_last_error() gives the text (no C++ exception crosses the boundary -- the reference throws
+ * std::runtime_error from CUDA_CHECK, include/ntwr.h:30-54).  Pointers are DEVICE pointers unless the
+ * parameter name ends in `_host`.  `stream` is a cudaStream_t passed as void* (0 = default stream).
+ * There is no CPU fallback: every compute entry point fails with NBVH_ERR_CUDA when no sm_100 device
+ * is usable.
+ *
+ * The POD constant blocks below are layout-identical to the reference's __constant__ structs so the
+ * renderer can hand over the very bytes it uploads today with cudaMemcpyToSymbol
+ * (neural_bvh_renderer_init.cu:93-103).
+ */
+#ifndef NBVH_B200_H
+#define NBVH_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBVH_ABI_VERSION 1
+
+typedef enum {
+    NBVH_OK              = 0,
+    NBVH_ERR_INVALID_ARG = -1,
+    NBVH_ERR_CUDA        = -2,
+    NBVH_ERR_IO          = -3,
+    NBVH_ERR_PARSE       = -4,
+    NBVH_ERR_UNSUPPORTED = -5,
+    NBVH_ERR_STATE       = -6
+} nbvh_status;
+
+typedef struct nbvh_ctx nbvh_ctx;
+
+/* ---- POD constant blocks (layout == reference) ------------------------------------------------ */
+
+/* NeuralBVHRendererConstants, include/cuda/neural/neural_bvh_renderer_constants.cuh:13-47 */
+typedef struct __attribute__((aligned(8))) {
+    uint32_t neural_bvh_idx;
+    int32_t num_lods_learned;
+    int32_t current_learned_lod;
+    int32_t rendered_lod;
+    bool ignore_neural_blas;
+    bool path_lod_switch;
+    int32_t lod_switch;
+    float leaf_boundary_sampling_ratio;
+    float inference_mint_epsilon;
+    float inference_maxt_epsilon;
+    float learning_mint_epsilon;
+    float learning_maxt_epsilon;
+    float sampling_bbox_scaling;
+    float fixed_node_dilation;
+    float node_extent_dilation;
+    float loss_exposure;
+    bool show_loss_heuristic;
+    bool ellipsoidal_bvh;
+    bool rescale_ellipsoid;
+    int32_t log2_bvh_max_traversals;
+    bool sample_cosine_weighted;
+    bool backface_bounce_training;
+    int32_t max_training_bounces;
+    bool training_node_survival;
+    float survival_probability_scale;
+    float min_rr_survival_prob;
+    bool view_dependent_sampling;
+    float view_dependent_ratio;
+} nbvh_renderer_constants;
+
+/* NeuralBVHModuleConstants, include/cuda/neural/neural_bvh_module.h:79-94 */
+typedef struct __attribute__((aligned(8))) {
+    uint32_t input_segment_point_dim;
+    uint32_t input_segment_points;
+    uint32_t input_segment_points_dim;
+    uint32_t input_segment_direction_dim;
+    uint32_t input_network_dims;
+    int32_t segment_distribution; /* 0 EquidistantInterior, 1 EquidistantExterior, 2 Uniform */
+    bool antialias_direction;
+    bool merge_operator;
+    bool apply_encoding_trafo;
+} nbvh_module_constants;
+
+/* PathTracingOutputConstants, include/cuda/neural/neural_bvh_module.h:243-274 */
+typedef struct __attribute__((aligned(8))) {
+    uint32_t output_visibility_dim;
+    uint32_t output_depth_dim;
+    uint32_t output_normal_dim;
+    uint32_t output_albedo_dim;
+    uint32_t output_network_dims;
+    uint8_t visibility_loss; /* LossType, include/cuda/neural/utils/tcnn_config.h:26-35 */
+    float visibility_loss_scale;
+    uint8_t depth_loss;
+    float depth_loss_scale;
+    uint8_t normal_loss;
+    float normal_loss_scale;
+    uint8_t albedo_loss;
+    float albedo_loss_scale;
+    uint8_t depth_learning_mode; /* 0 LocalT, 1 WorldT, 2 Position, 3 LocalPosition */
+    bool output_normal_linear_activation;
+    bool output_depth_linear_activation;
+    bool output_albedo_linear_activation;
+    bool visibility_masking_loss;
+    float primary_visibility_threshold;
+    float secondary_visibility_threshold;
+    float depth_epsilon;
+    float fixed_depth_epsilon;
+    bool interpolate_depth;
+    float depth_interpolation_eps;
+} nbvh_pt_output_constants;
+
+/* NeuralPathModuleConstants, include/cuda/neural/path/path_module.h:217-254 */
+typedef struct __attribute__((aligned(8))) {
+    uint8_t output_mode; /* 0 NeuralPathTracing */
+    float normal_epsilon_offset;
+    bool apply_russian_roulette;
+    int32_t rr_start_depth;
+    float neural_roughness;
+    float neural_specular;
+    float neural_metallic;
+} nbvh_path_constants;
+
+/* CudaSceneConstants, include/cuda/cuda_backend.h:58-72 */
+typedef struct __attribute__((aligned(8))) {
+    float constant_roughness;
+    float constant_specular;
+    float constant_metallic;
+    float envmap_strength;
+    float envmap_rotation;
+    bool envmap_eval;
+    bool emission_eval;
+    bool skylike_background;
+    bool sample_light;
+    float ema_weight;
+    bool ema_accumulate;
+    bool force_constant_material;
+} nbvh_scene_constants;
+
+/* CameraParams (origin, du, dv, dir_top_left as 4 packed vec3), src/cuda/cuda_backend.cpp:595-611 */
+typedef struct {
+    float origin[3];
+    float du[3];
+    float dv[3];
+    float dir_top_left[3];
+} nbvh_camera_params;
+
+/* Bbox3f neural_scene_bbox, include/base/bbox.h:8-11 */
+typedef struct {
+    float min[3];
+    float max[3];
+} nbvh_bbox3f;
+
+/* HashGridOptions / NetworkOptions / OptimizerOptions, include/cuda/neural/utils/tcnn_config.h:69-77,153-166,228-233 */
+typedef struct {
+    int32_t n_levels;
+    int32_t n_features_per_level;
+    int32_t log2_hashmap_size;
+    int32_t base_resolution;
+    float per_level_scale;
+    int32_t n_neurons;
+    int32_t n_hidden_layers;
+} nbvh_network_desc;
+
+typedef struct {
+    float learning_rate;
+    int32_t decay_start;
+    int32_t decay_interval;
+    float decay_base;
+    float beta1, beta2, epsilon, l2_reg;
+} nbvh_optimizer_desc;
+
+typedef enum {
+    NBVH_CONST_RENDERER   = 0, /* nbvh_renderer_constants   (symbol bvh_const)         */
+    NBVH_CONST_MODULE     = 1, /* nbvh_module_constants     (symbol bvh_module_const)  */
+    NBVH_CONST_PT_OUTPUT  = 2, /* nbvh_pt_output_constants  (symbol pt_target_const)   */
+    NBVH_CONST_PATH       = 3, /* nbvh_path_constants       (symbol path_module_const) */
+    NBVH_CONST_SCENE      = 4, /* nbvh_scene_constants      (symbol scene_constants)   */
+    NBVH_CONST_CAMERA     = 5, /* nbvh_camera_params        (symbol camera_params)     */
+    NBVH_CONST_SCENE_BBOX = 6, /* nbvh_bbox3f               (symbol neural_scene_bbox) */
+    NBVH_CONST_NETWORK    = 7, /* nbvh_network_desc  (rebuilds the parameter layout)   */
+    NBVH_CONST_OPTIMIZER  = 8  /* nbvh_optimizer_desc                                  */
+} nbvh_constant_block;
+
+/* ---- scene structs (layout == reference; device pointers inside) ------------------------------- */
+
+/* 32-byte node: BVH2Node / NeuralBVH2Node (include/base/accel/bvh.h:66-71) and TLASNode (tlas.cuh:64-68) */
+typedef struct {
+    float aabb_min[3];
+    uint32_t prim_count_or_left; /* BVH2: prim_count (N-BVH: LoD tag); TLAS: left_or_blas_offset */
+    float aabb_max[3];
+    uint32_t left_or_prim_offset; /* BVH2: left child / first prim; TLAS: leaf_type (0 interior, 1 leaf, 2 neural) */
+} nbvh_node32;
+
+/* CudaBVH2 : BaseCudaBLAS (include/cuda/accel/bvh.cuh:11-23, bvh2.cuh:9-10) */
+typedef struct {
+    uint32_t num_nodes;
+    const uint64_t *prim_indices; /* size_t* in the reference */
+    uint32_t num_prim_indices;
+    const float *vertices;   /* vec3 */
+    const uint32_t *indices; /* uvec3 */
+    const float *normals;    /* vec3 or NULL */
+    const float *texcoords;  /* vec2 or NULL */
+    const int32_t *material_ids;
+    const uint32_t *material_map;
+    uint32_t num_materials;
+    const nbvh_node32 *nodes;
+} nbvh_cuda_blas;
+
+/* CudaSceneData { CudaTLAS, PackedMaterial*, cudaTextureObject_t* } (include/cuda/cuda_backend.h:109-113,
+ * include/cuda/accel/tlas.cuh:124-131) */
+typedef struct {
+    const nbvh_node32 *tlas_nodes;
+    uint32_t num_tlas_nodes;
+    const uint32_t *blas_indices;
+    const nbvh_cuda_blas *mesh_bvhs; /* DEVICE array of num_meshes descriptors */
+    uint32_t num_meshes;
+    const void *materials; /* PackedMaterial* (unused until the shading row) */
+    const void *textures;  /* cudaTextureObject_t* */
+} nbvh_scene_data;
+
+/* Primary-hit record written per pixel by nbvh_render when a hit buffer is attached:
+ * the content of NeuralTraversalResult / HybridIntersectionResult for the first bounce
+ * (include/cuda/neural/path/path_module.h:19-45). */
+typedef struct {
+    float t;                /* FLT_MAX = miss */
+    uint32_t valid_hit;     /* 0 none, 1 NEURAL_TRAVERSAL_HIT, 2 NORMAL_TRAVERSAL_HIT */
+    float normal_or_uv[3];  /* neural: unit normal; normal: (u, v, 0) */
+    float albedo_or_ids[3]; /* neural: albedo; normal: (mesh_idx, prim_idx, 0) bit-cast */
+} nbvh_hit_record;
+
+/* Counter slots of nbvh_get_counters */
+enum {
+    NBVH_CNT_RAYS = 0,          /* rays generated                            */
+    NBVH_CNT_QUERIES,           /* network queries (ray x leaf)              */
+    NBVH_CNT_NBVH_STEPS,        /* N-BVH interior steps (child pairs tested) */
+    NBVH_CNT_BLAS_STEPS,        /* classical BLAS interior steps             */
+    NBVH_CNT_TRI_TESTS,         /* triangle tests                            */
+    NBVH_CNT_TILE_ITERATIONS,   /* 128-row MLP tiles executed                */
+    NBVH_CNT_COUNT
+};
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+uint32_t nbvh_abi_version(void);
+/* Creates a context on CUDA device `device`.  config_json may be NULL (reference defaults). */
+int nbvh_create(int device, const char *config_json, nbvh_ctx **out);
+void nbvh_destroy(nbvh_ctx *ctx);
+const char *nbvh_last_error(const nbvh_ctx *ctx);
+
+/* ---- configuration: replaces load_config_from_json + setup_constants --------------------------- */
+/* (neural_bvh_renderer_init.cu:566-749,93-103).  Partial configs are legal; missing keys take the
+ * reference defaults; unknown enum strings are an error (the reference silently stores -1). */
+int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text);
+int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t bytes);
+int nbvh_get_constants(const nbvh_ctx *ctx, int which, void *pod_host, size_t bytes);
+/* camera.cpp:39-82 + cuda_backend.cpp:595-611: 4x4 column-major camera matrix + yfov (radians) -> camera_params */
+int nbvh_set_camera(nbvh_ctx *ctx, const float matrix16_host[16], float yfov_rad);
+int nbvh_get_max_depth(const nbvh_ctx *ctx);
+int nbvh_set_max_depth(nbvh_ctx *ctx, int max_depth);
+
+/* ---- scene, tree-cut, weights ------------------------------------------------------------------ */
+int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *scene_host);
+/* replaces build_and_upload_neural_bvh's upload / load_neural_bvh (neural_bvh_renderer_accel.cpp:208-254).
+ * set_neural_bvh copies n 32-byte nodes from DEVICE memory; the root box becomes neural_scene_bbox
+ * unless NBVH_CONST_SCENE_BBOX is set afterwards. */
+int nbvh_set_neural_bvh(nbvh_ctx *ctx, const nbvh_node32 *nodes, uint32_t n);
+int nbvh_load_neural_bvh_file(nbvh_ctx *ctx, const char *path_host);
+int nbvh_save_neural_bvh_file(nbvh_ctx *ctx, const char *path_host);
+uint32_t nbvh_neural_bvh_num_nodes(const nbvh_ctx *ctx);
+int nbvh_get_neural_bvh_host(const nbvh_ctx *ctx, nbvh_node32 *nodes_host, uint32_t n);
+/* replaces load_network_model / save_network_model (neural_bvh_renderer_init.cu:385-404) */
+int nbvh_load_network_file(nbvh_ctx *ctx, const char *path_host);
+int nbvh_save_network_file(nbvh_ctx *ctx, const char *path_host);
+uint64_t nbvh_n_params(const nbvh_ctx *ctx); /* == network->n_params() */
+int nbvh_load_params_host(nbvh_ctx *ctx, const uint16_t *fp16_host, uint64_t n);
+int nbvh_get_params_host(const nbvh_ctx *ctx, uint16_t *fp16_host, uint64_t n);
+/* tcnn initialisation ranges (grid U(-1e-4,1e-4), MLP Xavier uniform), own counter-based RNG */
+int nbvh_init_params(nbvh_ctx *ctx, uint64_t seed);
+
+/* ---- inference --------------------------------------------------------------------------------- */
+/* reinitialise_inference_data (neural_bvh_module.cu:12-116) + GL surfaces replaced by linear memory:
+ * accum = float4[w*h], ldr = uchar4[w*h] (either may be NULL -> owned internally). */
+int nbvh_set_framebuffer(nbvh_ctx *ctx, float *accum_rgba32f, uint8_t *ldr_rgba8, uint32_t w, uint32_t h);
+int nbvh_set_hit_buffer(nbvh_ctx *ctx, nbvh_hit_record *hits /* w*h, or NULL to detach */);
+/* == network->inference(stream, in 9xN col-major f32, out 8xN col-major f32) (path_module.cu:92) */
+int nbvh_query(nbvh_ctx *ctx, const float *in, float *out, uint32_t n, void *stream);
+/* parity hook: unconditional ordered leaf-interval list of each ray (NeuralBVH2::intersect driven with
+ * maxt = FLT_MAX, neural_bvh2.cuh:170-292).  o,d: n x 3; outputs n x max_intervals (+ counts[n]). */
+int nbvh_trace_intervals(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
+                         uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt, void *stream);
+/* parity hook: CudaBVH2::intersect<false> on BLAS `blas_idx` (bvh2.cuh:13-88); maxt may be NULL */
+int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const float *d, const float *maxt,
+                        uint32_t n, float *t, float *u, float *v, uint32_t *prim, void *stream);
+/* parity hook: camera_raygen for pixels [first, first+n) (neural_bvh_module_common.cuh:440-446) */
+int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx, int sample_offset, float *o,
+                float *d, void *stream);
+/* == neural_render(accumulated_spp, sample_offset, neural_bvh) (path_module.cu:139-245): one sample per
+ * pixel of the attached framebuffer.  pixel range [first, first+count) restricts the launch to a
+ * shard of the image (count = 0 -> whole frame). */
+int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel,
+                uint32_t pixel_count, void *stream);
+/* End-to-end variant with HOST buffers: uploads `camera_host` (may be NULL), renders, copies the
+ * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
+int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
+                     const nbvh_camera_params *camera_host, uint8_t *ldr_rgba8_host, nbvh_hit_record *hits_host);
+int nbvh_get_counters(nbvh_ctx *ctx, uint64_t *out_host, uint32_t n);
+int nbvh_reset_counters(nbvh_ctx *ctx);
+/* average duration (ms) and launch count of the dominant kernel since the last reset, measured with
+ * CUDA events on the launching stream */
+int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches);
+int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable);
+
+/* ---- online optimisation ------------------------------------------------------------------------ */
+/* == trainer->training_step(stream, in 9xB, target 8xB) -> ctx.L (16xB) + trainer->loss()
+ * (ext/tiny-cuda-nn trainer.h:163-190; loss: include/cuda/neural/utils/pt_composite_loss.cuh:19-123).
+ * per_sample_loss (16 x B floats, may be NULL); loss_host receives the mean loss if non-NULL. */
+int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch, float *per_sample_loss,
+                       float *loss_host, void *stream);
+/* Split form for data-parallel training: backward leaves fp32 gradients in the context's gradient
+ * buffer (nbvh_gradients() -> device pointer, n_params floats) for an external allreduce (NCCL over
+ * NVLink, driven by the host process), then optimizer_step applies Adam with the given gradient scale. */
+int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch,
+                                   uint32_t global_batch, float *per_sample_loss, float *loss_sum_dev, void *stream);
+float *nbvh_gradients(nbvh_ctx *ctx);
+int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
+uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBVH_B200_H */

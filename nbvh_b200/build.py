@@ -1,0 +1,39 @@
+"""Builds libnbvh_b200.so (hand-written CUDA for sm_100a + the C-ABI host side) in-tree with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libnbvh_b200.so")
+SOURCES = ["context.cu", "kernels.cu"]
+HEADERS = ["device_core.cuh", "mlp_tile.cuh", "kernels.cuh", "json_min.hpp", "../../include/nbvh_b200.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # bit-exact traversal contract: only the explicit __fmaf_rn calls may fuse (see device_core.cuh)
+    "-fmad=false",
+    "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)

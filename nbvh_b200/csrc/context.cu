@@ -1,0 +1,1303 @@
+// context.cu -- host side of libnbvh_b200.so: context object, the reference's on-disk formats
+// (config JSON, .nbvh, network_models JSON), constant blocks, parameter layout, and the C ABI glue.
+// Mirrors what NeuralBVHRenderer / NeuralBVHModule do on the host around the hot path
+// (/root/reference/src/cuda/neural/neural_bvh_renderer_init.cu:385-404,566-749,
+//  /root/reference/src/cuda/neural/neural_bvh_renderer_accel.cpp:170-254,
+//  /root/reference/src/cuda/neural/neural_bvh_module.cu:12-263).
+#include "json_min.hpp"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+using namespace nbvh;
+
+#define CU_TRY(ctx, expr)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                              \
+            return NBVH_ERR_CUDA;                                                                           \
+        }                                                                                                   \
+    } while (0)
+
+namespace {
+
+const char *const kLossTypes[] = {"RelativeL2", "L2", "RelativeL1", "L1", "RelativeL2Luminance", "BinaryCrossEntropy",
+                                  "LogL2", "LHalf"};
+const char *const kDepthModes[]           = {"LocalT", "WorldT", "Position", "LocalPosition"};
+const char *const kSegmentDistributions[] = {"EquidistantInterior", "EquidistantExterior", "Uniform"};
+const char *const kOutputModes[]          = {"NeuralPathTracing"};
+
+template <size_t N>
+int find_index(const std::string &s, const char *const (&table)[N])
+{
+    for (size_t i = 0; i < N; i++)
+        if (s == table[i])
+            return (int)i;
+    return -1;
+}
+
+// ---- defaults of the reference structs ---------------------------------------------------------
+nbvh_renderer_constants default_renderer_constants()
+{
+    nbvh_renderer_constants c;
+    memset(&c, 0, sizeof(c));
+    c.neural_bvh_idx = 0, c.num_lods_learned = 1, c.current_learned_lod = 0, c.rendered_lod = 0;
+    c.ignore_neural_blas = false, c.path_lod_switch = false, c.lod_switch = 0;
+    c.leaf_boundary_sampling_ratio = 0.f;
+    c.inference_mint_epsilon = 1e-4f, c.inference_maxt_epsilon = 1e-3f;
+    c.learning_mint_epsilon = 1e-3f, c.learning_maxt_epsilon = 1e-3f;
+    c.sampling_bbox_scaling = 1.5f, c.fixed_node_dilation = 1e-5f, c.node_extent_dilation = 1e-4f;
+    c.loss_exposure = 2e-7f, c.show_loss_heuristic = false, c.ellipsoidal_bvh = false, c.rescale_ellipsoid = false;
+    c.log2_bvh_max_traversals = 0, c.sample_cosine_weighted = true, c.backface_bounce_training = false;
+    c.max_training_bounces = 1, c.training_node_survival = true, c.survival_probability_scale = 1.f;
+    c.min_rr_survival_prob = 0.005f, c.view_dependent_sampling = false, c.view_dependent_ratio = 0.f;
+    return c;
+}
+
+nbvh_module_constants default_module_constants()
+{
+    nbvh_module_constants c;
+    memset(&c, 0, sizeof(c));
+    c.input_segment_point_dim = 3, c.input_segment_points = 3, c.input_segment_points_dim = 9;
+    c.input_segment_direction_dim = 0, c.input_network_dims = 9;
+    c.segment_distribution = 0; // EquidistantInterior
+    return c;
+}
+
+nbvh_pt_output_constants default_pt_constants()
+{
+    nbvh_pt_output_constants c;
+    memset(&c, 0, sizeof(c));
+    c.output_visibility_dim = 1, c.output_depth_dim = 1, c.output_normal_dim = 0, c.output_albedo_dim = 0;
+    c.output_network_dims = 2;
+    c.visibility_loss = 5, c.visibility_loss_scale = 1.f, c.depth_loss = 3, c.depth_loss_scale = 1.f;
+    c.normal_loss = 3, c.normal_loss_scale = 1.f, c.albedo_loss = 0, c.albedo_loss_scale = 1.f;
+    c.depth_learning_mode = 0;
+    c.output_normal_linear_activation = true, c.output_depth_linear_activation = false;
+    c.output_albedo_linear_activation = false, c.visibility_masking_loss = true;
+    c.primary_visibility_threshold = 0.5f, c.secondary_visibility_threshold = 0.5f;
+    c.depth_epsilon = 0.2f, c.fixed_depth_epsilon = 1e-5f, c.interpolate_depth = false, c.depth_interpolation_eps = 1e-3f;
+    return c;
+}
+
+nbvh_path_constants default_path_constants()
+{
+    nbvh_path_constants c;
+    memset(&c, 0, sizeof(c));
+    c.output_mode = 0, c.normal_epsilon_offset = 1e-4f, c.apply_russian_roulette = true, c.rr_start_depth = 2;
+    c.neural_roughness = 1.f, c.neural_specular = 0.f, c.neural_metallic = 0.f;
+    return c;
+}
+
+nbvh_scene_constants default_scene_constants()
+{
+    nbvh_scene_constants c;
+    memset(&c, 0, sizeof(c));
+    c.constant_roughness = 1.f, c.constant_specular = 0.f, c.constant_metallic = 0.f;
+    c.envmap_strength = 1.f, c.envmap_rotation = 0.f, c.envmap_eval = true, c.emission_eval = true;
+    c.skylike_background = false, c.sample_light = false, c.ema_weight = 0.05f, c.ema_accumulate = true;
+    c.force_constant_material = false;
+    return c;
+}
+
+// ---- camera (host float arithmetic, no contraction: compiled with -fmad=false, and x86 baseline has no FMA)
+// glm::inverse cofactor expansion + Camera::origin/dir/up + CudaBackend::update_camera
+// (/root/reference/src/base/camera/camera.cpp:39-82, /root/reference/src/cuda/cuda_backend.cpp:595-611)
+void invert4(const float *a, float *out)
+{
+    auto M = [&](int c, int r) { return a[c * 4 + r]; };
+    const float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3), c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+    const float c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3), c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+    const float c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3), c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+    const float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2), c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+    const float c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2), c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+    const float c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3), c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+    const float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2), c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+    const float c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2), c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+    const float c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1), c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+    const float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    const float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    const float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+    const float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, v3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+    float inv[16];
+    for (int i = 0; i < 4; i++) {
+        const float sa = (i & 1) ? -1.f : 1.f, sb = -sa;
+        inv[0 + i]  = (v1[i] * f0[i] - v2[i] * f1[i] + v3[i] * f2[i]) * sa;
+        inv[4 + i]  = (v0[i] * f0[i] - v2[i] * f3[i] + v3[i] * f4[i]) * sb;
+        inv[8 + i]  = (v0[i] * f1[i] - v1[i] * f3[i] + v3[i] * f5[i]) * sa;
+        inv[12 + i] = (v0[i] * f2[i] - v1[i] * f4[i] + v2[i] * f5[i]) * sb;
+    }
+    const float det = (M(0, 0) * inv[0] + M(0, 1) * inv[4]) + (M(0, 2) * inv[8] + M(0, 3) * inv[12]);
+    const float ood = 1.f / det;
+    for (int i = 0; i < 16; i++)
+        out[i] = inv[i] * ood;
+}
+
+void normalize3(const float *v, float *o)
+{
+    const float dot = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const float inv = 1.f / sqrtf(dot);
+    o[0] = v[0] * inv, o[1] = v[1] * inv, o[2] = v[2] * inv;
+}
+
+void cross3(const float *x, const float *y, float *o)
+{
+    o[0] = x[1] * y[2] - y[1] * x[2];
+    o[1] = x[2] * y[0] - y[2] * x[0];
+    o[2] = x[0] * y[1] - y[0] * x[1];
+}
+
+nbvh_camera_params camera_from_matrix(const float *m, float yfov_rad, uint32_t w, uint32_t h)
+{
+    float inv[16];
+    invert4(m, inv);
+    nbvh_camera_params cp;
+    float dir_raw[3], up_raw[3], dir[3], up[3];
+    for (int r = 0; r < 3; r++) {
+        cp.origin[r] = (inv[0 + r] * 0.f + inv[4 + r] * 0.f) + (inv[8 + r] * 0.f + inv[12 + r] * 1.f);
+        dir_raw[r]   = (inv[0 + r] * 0.f + inv[4 + r] * 0.f) + (inv[8 + r] * -1.f + inv[12 + r] * 0.f);
+        up_raw[r]    = (inv[0 + r] * 0.f + inv[4 + r] * 1.f) + (inv[8 + r] * 0.f + inv[12 + r] * 0.f);
+    }
+    normalize3(dir_raw, dir);
+    normalize3(up_raw, up);
+    const float fovy_deg = yfov_rad * 57.295779513082320876798154814105f;        // glm::degrees
+    const float half_rad = (0.5f * fovy_deg) * 0.01745329251994329576923690768489f; // glm::radians
+    const float plane_y  = 2.f * tanf(half_rad);
+    const float aspect   = (float)w / (float)h;
+    const float plane_x  = plane_y * aspect;
+    float c1[3], c1n[3], c2[3], c2n[3];
+    cross3(dir, up, c1);
+    normalize3(c1, c1n);
+    for (int i = 0; i < 3; i++)
+        cp.du[i] = c1n[i] * plane_x;
+    cross3(cp.du, dir, c2);
+    normalize3(c2, c2n);
+    for (int i = 0; i < 3; i++)
+        cp.dv[i] = -c2n[i] * plane_y;
+    for (int i = 0; i < 3; i++)
+        cp.dir_top_left[i] = dir[i] - 0.5f * cp.du[i] - 0.5f * cp.dv[i];
+    return cp;
+}
+
+bool read_file(const std::string &path, std::string &out)
+{
+    std::ifstream f(path, std::ios::binary);
+    if (!f)
+        return false;
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+uint16_t f32_to_f16_host(float f) { return __half_as_ushort(__float2half_rn(f)); }
+
+} // namespace
+
+// ================================================================================================ context
+struct nbvh_ctx {
+    int device = 0;
+    int num_sms = 148;
+    std::string error;
+
+    nbvh_renderer_constants bvh_const = default_renderer_constants();
+    nbvh_module_constants module_const = default_module_constants();
+    nbvh_pt_output_constants pt_const = default_pt_constants();
+    nbvh_path_constants path_const = default_path_constants();
+    nbvh_scene_constants scene_const = default_scene_constants();
+    nbvh_camera_params camera{};
+    nbvh_bbox3f scene_bbox{};
+    bool scene_bbox_set = false;
+    nbvh_network_desc net_desc{8, 4, 18, 8, 2.0f, 64, 4};
+    nbvh_optimizer_desc opt_desc{1e-2f, 10000, 2000, 0.33f, 0.9f, 0.999f, 1e-8f, 1e-8f};
+    int max_depth = 2; // NeuralPathModule::m_max_depth default (path_module.h:313)
+    uint32_t fb_w = 0, fb_h = 0;
+    uint32_t training_step = 0;
+
+    // network parameter layout
+    uint64_t n_params = 0, n_mlp_params = 0;
+    std::vector<uint32_t> level_offsets; // entries
+    uint32_t in_k = 0, n_layers = 0;
+    uint16_t *d_params = nullptr; // fp16: MLP then grid
+    uint8_t *d_wimg    = nullptr;
+    uint32_t wimg_bytes = 0;
+    std::vector<uint32_t> layer_off;
+    bool params_loaded = false;
+
+    // tree-cut
+    float4 *d_nbvh = nullptr, *d_nbvh_dilated = nullptr;
+    uint32_t nbvh_nodes = 0;
+    float dilated_with  = -1.f;
+
+    // scene
+    SceneConst scene{};
+    bool scene_set = false;
+
+    // framebuffer
+    float4 *accum = nullptr;
+    uchar4 *ldr   = nullptr;
+    bool own_accum = false, own_ldr = false;
+    nbvh_hit_record *hits = nullptr;
+    nbvh_hit_record *own_hits = nullptr;
+
+    uint32_t *d_next_chunk = nullptr;
+    unsigned long long *d_counters = nullptr;
+
+    // kernel timing
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float total_ms = 0.f;
+    uint32_t launches = 0;
+
+    // training buffers (allocated lazily)
+    float *d_grads = nullptr;
+};
+
+namespace {
+
+int fail(nbvh_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx)
+        ctx->error = msg;
+    return code;
+}
+
+uint32_t grid_resolution(float scale) { return (uint32_t)ceilf(scale) + 1u; }
+float grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f((float)level * log2_pls) * (float)base - 1.0f; }
+
+// Parameter layout: FullyFusedMLP matrices (row-major W[out][in]) then the grid levels
+// (network_with_input_encoding.h:115-122, fully_fused_mlp.cu:636-678, grid.h:692-723)
+int rebuild_layout(nbvh_ctx *ctx)
+{
+    const nbvh_network_desc &d = ctx->net_desc;
+    if (d.n_features_per_level != 4)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only n_features_per_level == 4 is implemented");
+    if (d.n_neurons != kNeurons)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only n_neurons == 64 is implemented");
+    if (d.n_levels < 1 || d.n_levels > kMaxLevels || d.n_hidden_layers < 1 || d.n_hidden_layers + 1 > kMaxLayers)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "n_levels / n_hidden_layers out of range");
+    if (ctx->module_const.input_segment_direction_dim != 0)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "direction encoding input is not implemented");
+    const uint32_t n_points = ctx->module_const.input_segment_points;
+    if (n_points < 1 || n_points > 4)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "1..4 segment points supported");
+    ctx->in_k = n_points * d.n_levels * d.n_features_per_level;
+    if (ctx->in_k % 16u != 0u || ctx->in_k > kMaxInputK)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "encoded input width must be a multiple of 16 and <= 128");
+    if (ctx->pt_const.output_network_dims > 8)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "output_network_dims > 8");
+    ctx->n_layers = (uint32_t)d.n_hidden_layers + 1u;
+
+    ctx->level_offsets.assign(d.n_levels + 1, 0);
+    uint32_t offset    = 0;
+    const float l2     = log2f(d.per_level_scale);
+    for (int l = 0; l < d.n_levels; l++) {
+        const uint32_t res = grid_resolution(grid_scale(l, l2, d.base_resolution));
+        const uint32_t max_params = 0xFFFFFFFFu / 2u;
+        uint32_t in_level = powf((float)res, 3.f) > (float)max_params ? max_params : res * res * res;
+        in_level          = (in_level + 7u) / 8u * 8u;
+        const uint32_t hs = 1u << d.log2_hashmap_size;
+        if (in_level > hs)
+            in_level = hs;
+        ctx->level_offsets[l] = offset;
+        offset += in_level;
+    }
+    ctx->level_offsets[d.n_levels] = offset;
+    ctx->n_mlp_params = (uint64_t)kNeurons * ctx->in_k + (uint64_t)(d.n_hidden_layers - 1) * kNeurons * kNeurons +
+                        (uint64_t)kOutPadded * kNeurons;
+    ctx->n_params = ctx->n_mlp_params + (uint64_t)offset * d.n_features_per_level;
+
+    // weights image: one canonical K-major operand block per layer
+    ctx->layer_off.assign(ctx->n_layers, 0);
+    uint32_t bytes = 0;
+    for (uint32_t l = 0; l < ctx->n_layers; l++) {
+        const uint32_t k = l == 0 ? ctx->in_k : (uint32_t)kNeurons;
+        const uint32_t n = l + 1 == ctx->n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+        ctx->layer_off[l] = bytes;
+        bytes += n * k * 2u;
+    }
+    ctx->wimg_bytes = bytes;
+    if (ctx->d_params)
+        cudaFree(ctx->d_params);
+    if (ctx->d_wimg)
+        cudaFree(ctx->d_wimg);
+    ctx->d_params = nullptr, ctx->d_wimg = nullptr;
+    ctx->params_loaded = false;
+    CU_TRY(ctx, cudaMalloc(&ctx->d_params, ctx->n_params * sizeof(uint16_t)));
+    CU_TRY(ctx, cudaMemset(ctx->d_params, 0, ctx->n_params * sizeof(uint16_t)));
+    CU_TRY(ctx, cudaMalloc(&ctx->d_wimg, ctx->wimg_bytes));
+    CU_TRY(ctx, configure_kernels(ctx->wimg_bytes, ctx->in_k));
+    return NBVH_OK;
+}
+
+// Re-packs the MLP matrices into the UMMA canonical layout and uploads them
+int upload_weight_image(nbvh_ctx *ctx, const uint16_t *mlp_host)
+{
+    std::vector<uint8_t> img(ctx->wimg_bytes, 0);
+    const uint16_t *w = mlp_host;
+    for (uint32_t l = 0; l < ctx->n_layers; l++) {
+        const uint32_t k = l == 0 ? ctx->in_k : (uint32_t)kNeurons;
+        const uint32_t n = l + 1 == ctx->n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+        uint8_t *dst     = img.data() + ctx->layer_off[l];
+        for (uint32_t r = 0; r < n; r++)
+            for (uint32_t c = 0; c < k; c++) {
+                const uint32_t off = (r >> 3) * ((k >> 3) * 128u) + (c >> 3) * 128u + (r & 7u) * 16u + (c & 7u) * 2u;
+                memcpy(dst + off, &w[(size_t)r * k + c], 2);
+            }
+        w += (size_t)n * k;
+    }
+    CU_TRY(ctx, cudaMemcpy(ctx->d_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    return NBVH_OK;
+}
+
+NetConst make_net_const(const nbvh_ctx *ctx)
+{
+    NetConst nc;
+    memset(&nc, 0, sizeof(nc));
+    const nbvh_network_desc &d = ctx->net_desc;
+    nc.grid     = reinterpret_cast<const uint2 *>(ctx->d_params + ctx->n_mlp_params);
+    nc.n_levels = d.n_levels;
+    nc.n_points = ctx->module_const.input_segment_points;
+    nc.in_k     = ctx->in_k;
+    nc.n_layers = ctx->n_layers;
+    nc.n_out    = ctx->pt_const.output_network_dims;
+    nc.wimg     = ctx->d_wimg;
+    nc.wimg_bytes = ctx->wimg_bytes;
+    for (uint32_t l = 0; l < ctx->n_layers; l++)
+        nc.layer_off[l] = ctx->layer_off[l];
+    const float l2 = log2f(d.per_level_scale);
+    for (int l = 0; l < d.n_levels; l++) {
+        GridLevel &L = nc.lv[l];
+        L.offset     = ctx->level_offsets[l];
+        L.size       = ctx->level_offsets[l + 1] - ctx->level_offsets[l];
+        L.mask       = (L.size > 1u && (L.size & (L.size - 1u)) == 0u) ? L.size - 1u : 0u;
+        L.scale      = grid_scale(l, l2, d.base_resolution);
+        L.res        = grid_resolution(L.scale);
+        // tcnn grid_index: dense indexing unless the dense stride product exceeds the level size
+        const uint64_t r = L.res;
+        L.dense          = (r <= L.size && r * r <= L.size && r * r * r <= (uint64_t)L.size) ? 1u : 0u;
+    }
+    return nc;
+}
+
+NbvhConst make_nbvh_const(const nbvh_ctx *ctx, bool inference)
+{
+    NbvhConst bc;
+    bc.nodes        = ctx->d_nbvh_dilated;
+    bc.num_nodes    = ctx->nbvh_nodes;
+    bc.leaf_lod_max = 2u + (uint32_t)ctx->bvh_const.rendered_lod;
+    bc.mint_eps     = inference ? ctx->bvh_const.inference_mint_epsilon : ctx->bvh_const.learning_mint_epsilon;
+    bc.maxt_eps     = inference ? ctx->bvh_const.inference_maxt_epsilon : ctx->bvh_const.learning_maxt_epsilon;
+    bc.dilation     = ctx->bvh_const.fixed_node_dilation;
+    bc.predilated   = 1u;
+    return bc;
+}
+
+// keep the pre-dilated node copy in sync with fixed_node_dilation
+int refresh_dilated(nbvh_ctx *ctx)
+{
+    if (!ctx->d_nbvh)
+        return fail(ctx, NBVH_ERR_STATE, "no neural BVH set");
+    if (ctx->bvh_const.ellipsoidal_bvh)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "ellipsoidal_bvh is not implemented");
+    if (ctx->dilated_with == ctx->bvh_const.fixed_node_dilation)
+        return NBVH_OK;
+    if (ctx->bvh_const.fixed_node_dilation == 0.f) {
+        CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh_dilated, ctx->d_nbvh, (size_t)ctx->nbvh_nodes * 32, cudaMemcpyDeviceToDevice));
+    } else {
+        CU_TRY(ctx, launch_predilate(ctx->d_nbvh, ctx->d_nbvh_dilated, ctx->nbvh_nodes, ctx->bvh_const.fixed_node_dilation, 0));
+        CU_TRY(ctx, cudaDeviceSynchronize());
+    }
+    ctx->dilated_with = ctx->bvh_const.fixed_node_dilation;
+    return NBVH_OK;
+}
+
+EncodeConst make_encode_const(const nbvh_ctx *ctx)
+{
+    EncodeConst ec;
+    memset(&ec, 0, sizeof(ec));
+    // neural_bvh_module_kernels.cu:39-43 (host evaluation of the same float expressions, no contraction)
+    const float dilation = (ctx->bvh_const.node_extent_dilation + 1.f) + ctx->bvh_const.fixed_node_dilation;
+    for (int i = 0; i < 3; i++) {
+        ec.extent[i] = dilation * (ctx->scene_bbox.max[i] - ctx->scene_bbox.min[i]);
+        ec.center[i] = (ctx->scene_bbox.max[i] + ctx->scene_bbox.min[i]) * 0.5f;
+    }
+    const uint32_t n = ctx->module_const.input_segment_points;
+    ec.n_points      = n;
+    float delta, offset;
+    if (ctx->module_const.segment_distribution == 1) { // EquidistantExterior
+        delta  = n == 1 ? 1.f : 1.f / (float)(n - 1);
+        offset = 0.f;
+    } else {
+        delta  = 1.f / (float)n;
+        offset = 0.5f;
+    }
+    for (uint32_t k = 0; k < n && k < 4; k++)
+        ec.point_s[k] = delta * ((float)k + offset);
+    return ec;
+}
+
+int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params)
+{
+    if (need_params && !ctx->params_loaded)
+        return fail(ctx, NBVH_ERR_STATE, "network parameters not loaded");
+    if (need_nbvh && !ctx->d_nbvh)
+        return fail(ctx, NBVH_ERR_STATE, "neural BVH not set");
+    if (need_scene && !ctx->scene_set)
+        return fail(ctx, NBVH_ERR_STATE, "scene not set");
+    if (ctx->module_const.segment_distribution == 2)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "Uniform segment distribution is not implemented");
+    if (ctx->pt_const.depth_learning_mode != 0)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only depth_learning_mode LocalT is implemented");
+    return NBVH_OK;
+}
+
+struct KernelTimer {
+    nbvh_ctx *ctx;
+    cudaStream_t st;
+    KernelTimer(nbvh_ctx *c, cudaStream_t s) : ctx(c), st(s)
+    {
+        if (ctx->timing)
+            cudaEventRecord(ctx->ev0, st);
+    }
+    void stop()
+    {
+        if (!ctx->timing)
+            return;
+        cudaEventRecord(ctx->ev1, st);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->total_ms += ms;
+        ctx->launches++;
+    }
+};
+
+} // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+uint32_t nbvh_abi_version(void) { return NBVH_ABI_VERSION; }
+
+const char *nbvh_last_error(const nbvh_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
+{
+    if (!out)
+        return NBVH_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+        return NBVH_ERR_CUDA; // no CPU fallback
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return NBVH_ERR_CUDA;
+    if (prop.major != 10)
+        return NBVH_ERR_CUDA; // the kernels exist for sm_100a only
+    nbvh_ctx *ctx = new nbvh_ctx();
+    ctx->device   = device;
+    ctx->num_sms  = prop.multiProcessorCount;
+    if (cudaMalloc(&ctx->d_next_chunk, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * CNT_COUNT) != cudaSuccess) {
+        delete ctx;
+        return NBVH_ERR_CUDA;
+    }
+    cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT);
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    int rc = config_json ? nbvh_load_config_json(ctx, config_json) : rebuild_layout(ctx);
+    *out   = ctx; // returned even on a config error so the caller can read nbvh_last_error
+    return rc;
+}
+
+void nbvh_destroy(nbvh_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_params);
+    cudaFree(ctx->d_wimg);
+    cudaFree(ctx->d_nbvh);
+    cudaFree(ctx->d_nbvh_dilated);
+    if (ctx->own_accum)
+        cudaFree(ctx->accum);
+    if (ctx->own_ldr)
+        cudaFree(ctx->ldr);
+    cudaFree(ctx->own_hits);
+    cudaFree(ctx->d_next_chunk);
+    cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_grads);
+    if (ctx->ev0)
+        cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1)
+        cudaEventDestroy(ctx->ev1);
+    delete ctx;
+}
+
+// ---- configuration ---------------------------------------------------------------------------------
+int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
+{
+    if (!ctx || !json_text)
+        return NBVH_ERR_INVALID_ARG;
+    Json root;
+    try {
+        root = json_parse(json_text);
+    } catch (const std::exception &e) {
+        return fail(ctx, NBVH_ERR_PARSE, e.what());
+    }
+    const Json &scene = root.object("cuda_scene");
+    const Json &rend  = root.object("neural_bvh_renderer");
+    const Json &mod   = rend.object("neural_module");
+
+    // scene constants (cuda_backend.h:93-107)
+    {
+        const Json &j           = scene.object("scene_constants");
+        nbvh_scene_constants d  = default_scene_constants(), &c = ctx->scene_const;
+        c.force_constant_material = j.value("force_constant_material", d.force_constant_material);
+        c.constant_roughness    = (float)j.value("constant_roughness", (double)d.constant_roughness);
+        c.constant_specular     = (float)j.value("constant_specular", (double)d.constant_specular);
+        c.constant_metallic     = (float)j.value("constant_metallic", (double)d.constant_metallic);
+        c.envmap_rotation       = (float)j.value("envmap_rotation", (double)d.envmap_rotation);
+        c.envmap_strength       = (float)j.value("envmap_strength", (double)d.envmap_strength);
+        c.ema_accumulate        = j.value("ema_accumulate", d.ema_accumulate);
+        c.ema_weight            = (float)j.value("ema_weight", (double)d.ema_weight);
+        c.envmap_eval           = j.value("envmap_eval", d.envmap_eval);
+        c.emission_eval         = j.value("emission_eval", d.emission_eval);
+        c.skylike_background    = j.value("skylike_background", d.skylike_background);
+    }
+    // bvh constants (neural_bvh_renderer_constants.cuh:77-106)
+    {
+        const Json &j = rend.object("bvh_constants");
+        nbvh_renderer_constants d = default_renderer_constants(), &c = ctx->bvh_const;
+#define GETI(name) c.name = (int32_t)j.value(#name, (double)d.name)
+#define GETF(name) c.name = (float)j.value(#name, (double)d.name)
+#define GETB(name) c.name = j.value(#name, (bool)d.name)
+        GETI(num_lods_learned);
+        GETI(current_learned_lod);
+        GETI(rendered_lod);
+        GETB(ignore_neural_blas);
+        GETF(leaf_boundary_sampling_ratio);
+        GETF(inference_mint_epsilon);
+        GETF(inference_maxt_epsilon);
+        GETF(learning_mint_epsilon);
+        GETF(learning_maxt_epsilon);
+        GETF(sampling_bbox_scaling);
+        GETF(fixed_node_dilation);
+        GETF(node_extent_dilation);
+        GETF(loss_exposure);
+        GETB(show_loss_heuristic);
+        GETB(ellipsoidal_bvh);
+        GETB(rescale_ellipsoid);
+        GETI(log2_bvh_max_traversals);
+        GETB(sample_cosine_weighted);
+        GETB(backface_bounce_training);
+        GETI(max_training_bounces);
+        GETB(training_node_survival);
+        GETF(survival_probability_scale);
+        GETF(min_rr_survival_prob);
+#undef GETI
+#undef GETF
+#undef GETB
+    }
+    // module constants (neural_bvh_module.h:112-130)
+    {
+        const Json &j = mod.object("bvh_module_constants");
+        nbvh_module_constants d = default_module_constants(), &c = ctx->module_const;
+        c.input_segment_point_dim     = (uint32_t)j.value("input_segment_point_dim", (double)d.input_segment_point_dim);
+        c.input_segment_points        = (uint32_t)j.value("input_segment_points", (double)d.input_segment_points);
+        c.input_segment_points_dim    = (uint32_t)j.value("input_segment_points_dim", (double)d.input_segment_points_dim);
+        c.input_segment_direction_dim = (uint32_t)j.value("input_segment_direction_dim", (double)d.input_segment_direction_dim);
+        c.input_network_dims          = (uint32_t)j.value("input_network_dims", (double)d.input_network_dims);
+        const int sd = find_index(j.value("segment_distribution", std::string(kSegmentDistributions[d.segment_distribution])),
+                                  kSegmentDistributions);
+        if (sd < 0)
+            return fail(ctx, NBVH_ERR_PARSE, "unknown segment_distribution");
+        c.segment_distribution = sd;
+        c.antialias_direction  = j.value("antialias_direction", d.antialias_direction);
+        c.merge_operator       = j.value("merge_operator", d.merge_operator);
+        c.apply_encoding_trafo = j.value("apply_encoding_trafo", d.apply_encoding_trafo);
+        if (c.apply_encoding_trafo)
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "apply_encoding_trafo (asserted off in the reference) is not implemented");
+    }
+    // path-tracing output constants (neural_bvh_module.h:305-351)
+    {
+        const Json &j = mod.object("pt_output_constants");
+        nbvh_pt_output_constants d = default_pt_constants(), &c = ctx->pt_const;
+        c.output_visibility_dim = (uint32_t)j.value("output_visibility_dim", (double)d.output_visibility_dim);
+        c.output_depth_dim      = (uint32_t)j.value("output_depth_dim", (double)d.output_depth_dim);
+        c.output_normal_dim     = (uint32_t)j.value("output_normal_dim", (double)d.output_normal_dim);
+        c.output_albedo_dim     = (uint32_t)j.value("output_albedo_dim", (double)d.output_albedo_dim);
+        c.output_network_dims   = (uint32_t)j.value("output_network_dims", (double)d.output_network_dims);
+        struct {
+            const char *key;
+            uint8_t *dst;
+            uint8_t def;
+        } losses[] = {{"visibility_loss", &c.visibility_loss, d.visibility_loss},
+                      {"depth_loss", &c.depth_loss, d.depth_loss},
+                      {"normal_loss", &c.normal_loss, d.normal_loss},
+                      {"albedo_loss", &c.albedo_loss, d.albedo_loss}};
+        for (auto &l : losses) {
+            const int idx = find_index(j.value(l.key, std::string(kLossTypes[l.def])), kLossTypes);
+            if (idx < 0)
+                return fail(ctx, NBVH_ERR_PARSE, std::string("unknown loss type for ") + l.key);
+            *l.dst = (uint8_t)idx;
+        }
+        c.visibility_loss_scale = (float)j.value("visibility_loss_scale", (double)d.visibility_loss_scale);
+        c.depth_loss_scale      = (float)j.value("depth_loss_scale", (double)d.depth_loss_scale);
+        c.normal_loss_scale     = (float)j.value("normal_loss_scale", (double)d.normal_loss_scale);
+        c.albedo_loss_scale     = (float)j.value("albedo_loss_scale", (double)d.albedo_loss_scale);
+        const int dm = find_index(j.value("depth_learning_mode", std::string(kDepthModes[d.depth_learning_mode])), kDepthModes);
+        if (dm < 0)
+            return fail(ctx, NBVH_ERR_PARSE, "unknown depth_learning_mode");
+        c.depth_learning_mode             = (uint8_t)dm;
+        c.output_normal_linear_activation = j.value("output_normal_linear_activation", d.output_normal_linear_activation);
+        c.output_depth_linear_activation  = j.value("output_depth_linear_activation", d.output_depth_linear_activation);
+        c.output_albedo_linear_activation = j.value("output_albedo_linear_activation", d.output_albedo_linear_activation);
+        c.visibility_masking_loss         = j.value("visibility_masking_loss", d.visibility_masking_loss);
+        c.primary_visibility_threshold    = (float)j.value("primary_visibility_threshold", (double)d.primary_visibility_threshold);
+        c.secondary_visibility_threshold  = (float)j.value("secondary_visibility_threshold", (double)d.secondary_visibility_threshold);
+        c.depth_epsilon                   = (float)j.value("depth_epsilon", (double)d.depth_epsilon);
+        c.fixed_depth_epsilon             = (float)j.value("fixed_depth_epsilon", (double)d.fixed_depth_epsilon);
+    }
+    // path module constants (path_module.h:242-253)
+    {
+        const Json &j = mod.object("path_module_constants");
+        nbvh_path_constants d = default_path_constants(), &c = ctx->path_const;
+        const int om = find_index(j.value("output_mode", std::string(kOutputModes[d.output_mode])), kOutputModes);
+        if (om < 0)
+            return fail(ctx, NBVH_ERR_PARSE, "unknown output_mode");
+        c.output_mode            = (uint8_t)om;
+        c.normal_epsilon_offset  = (float)j.value("normal_epsilon_offset", (double)d.normal_epsilon_offset);
+        c.apply_russian_roulette = j.value("apply_russian_roulette", d.apply_russian_roulette);
+        c.rr_start_depth         = (int32_t)j.value("rr_start_depth", (double)d.rr_start_depth);
+        c.neural_roughness       = (float)j.value("neural_roughness", (double)d.neural_roughness);
+        c.neural_specular        = (float)j.value("neural_specular", (double)d.neural_specular);
+        c.neural_metallic        = (float)j.value("neural_metallic", (double)d.neural_metallic);
+    }
+    ctx->max_depth = (int)mod.value("max_depth", (double)ctx->max_depth);
+    // network + encoding + optimizer (tcnn_config.h)
+    {
+        const Json &nw = mod.object("network");
+        const Json &hg = mod.object("segment_encoding").object("hashgrid_options");
+        nbvh_network_desc &d = ctx->net_desc;
+        const std::string net_type = nw.value("network", std::string("FullyFusedMLP"));
+        if (net_type != "FullyFusedMLP" && net_type != "CutlassMLP")
+            return fail(ctx, NBVH_ERR_PARSE, "unknown network type");
+        if (nw.value("activation", std::string("ReLU")) != "ReLU" ||
+            nw.value("output_activation", std::string("Sigmoid")) != "Sigmoid")
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "only ReLU hidden / Sigmoid output activations are implemented");
+        const std::string enc_type = mod.object("segment_encoding").value("type", std::string("HashGrid"));
+        if (enc_type != "HashGrid")
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "only the HashGrid segment encoding is implemented");
+        if (mod.object("segment_encoding").value("reduction", std::string("Concatenation")) != "Concatenation")
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "only the Concatenation reduction is implemented");
+        if (hg.value("hash", std::string("CoherentPrime")) != "CoherentPrime" ||
+            hg.value("interpolation", std::string("Linear")) != "Linear" || hg.value("stochastic_interpolation", false))
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "only CoherentPrime hash with Linear interpolation is implemented");
+        d.n_neurons            = (int32_t)nw.value("n_neurons", 64.0);
+        d.n_hidden_layers      = (int32_t)nw.value("n_hidden_layers", 4.0);
+        d.n_levels             = (int32_t)hg.value("n_levels", 8.0);
+        d.n_features_per_level = (int32_t)hg.value("n_features_per_level", 4.0);
+        d.log2_hashmap_size    = (int32_t)hg.value("log2_hashmap_size", 18.0);
+        d.base_resolution      = (int32_t)hg.value("base_resolution", 8.0);
+        d.per_level_scale      = (float)hg.value("per_level_scale", 2.0);
+        const Json &op         = mod.object("optimizer");
+        nbvh_optimizer_desc &o = ctx->opt_desc;
+        if (op.value("type", std::string("Adam")) != "Adam")
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, "only the Adam optimizer is implemented");
+        o.learning_rate  = (float)op.value("learning_rate", 1e-2);
+        o.decay_start    = (int32_t)op.value("decay_start", 10000.0);
+        o.decay_interval = (int32_t)op.value("decay_interval", 2000.0);
+        o.decay_base     = (float)op.value("decay_base", (double)0.33f);
+        o.beta1          = (float)op.value("beta1", (double)0.9f);
+        o.beta2          = (float)op.value("beta2", (double)0.999f);
+        o.epsilon        = (float)op.value("epsilon", (double)1e-8f);
+        o.l2_reg         = (float)op.value("l2_reg", (double)1e-8f);
+    }
+    ctx->training_step = (uint32_t)rend.value("training_step", 0.0);
+    // framebuffer size + camera
+    if (const Json *fb = scene.find("fb_size")) {
+        if (fb->size() == 2) {
+            int rc = nbvh_set_framebuffer(ctx, nullptr, nullptr, (uint32_t)fb->at_num(0), (uint32_t)fb->at_num(1));
+            if (rc != NBVH_OK)
+                return rc;
+        }
+    }
+    const Json &cam = scene.object("camera");
+    if (const Json *m = cam.find("matrix")) {
+        if (m->size() != 16)
+            return fail(ctx, NBVH_ERR_PARSE, "camera.matrix must have 16 entries");
+        float mtx[16];
+        for (int i = 0; i < 16; i++)
+            mtx[i] = (float)m->at_num(i);
+        const float yfov = (float)cam.value("yfov", (double)(45.0f * 0.01745329251994329576923690768489f));
+        int rc           = nbvh_set_camera(ctx, mtx, yfov);
+        if (rc != NBVH_OK)
+            return rc;
+    }
+    ctx->dilated_with = -1.f;
+    return rebuild_layout(ctx);
+}
+
+static void *block_ptr(nbvh_ctx *ctx, int which, size_t &bytes)
+{
+    switch (which) {
+    case NBVH_CONST_RENDERER: bytes = sizeof(ctx->bvh_const); return &ctx->bvh_const;
+    case NBVH_CONST_MODULE: bytes = sizeof(ctx->module_const); return &ctx->module_const;
+    case NBVH_CONST_PT_OUTPUT: bytes = sizeof(ctx->pt_const); return &ctx->pt_const;
+    case NBVH_CONST_PATH: bytes = sizeof(ctx->path_const); return &ctx->path_const;
+    case NBVH_CONST_SCENE: bytes = sizeof(ctx->scene_const); return &ctx->scene_const;
+    case NBVH_CONST_CAMERA: bytes = sizeof(ctx->camera); return &ctx->camera;
+    case NBVH_CONST_SCENE_BBOX: bytes = sizeof(ctx->scene_bbox); return &ctx->scene_bbox;
+    case NBVH_CONST_NETWORK: bytes = sizeof(ctx->net_desc); return &ctx->net_desc;
+    case NBVH_CONST_OPTIMIZER: bytes = sizeof(ctx->opt_desc); return &ctx->opt_desc;
+    default: bytes = 0; return nullptr;
+    }
+}
+
+int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t bytes)
+{
+    if (!ctx || !pod_host)
+        return NBVH_ERR_INVALID_ARG;
+    size_t want = 0;
+    void *dst   = block_ptr(ctx, which, want);
+    if (!dst || bytes != want)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_set_constants: unknown block or size mismatch");
+    if (which == NBVH_CONST_NETWORK || which == NBVH_CONST_MODULE) {
+        // these change the parameter layout: compare first so per-frame re-uploads stay cheap
+        if (memcmp(dst, pod_host, bytes) == 0)
+            return NBVH_OK;
+        memcpy(dst, pod_host, bytes);
+        return rebuild_layout(ctx);
+    }
+    memcpy(dst, pod_host, bytes);
+    if (which == NBVH_CONST_SCENE_BBOX)
+        ctx->scene_bbox_set = true;
+    return NBVH_OK;
+}
+
+int nbvh_get_constants(const nbvh_ctx *ctx, int which, void *pod_host, size_t bytes)
+{
+    if (!ctx || !pod_host)
+        return NBVH_ERR_INVALID_ARG;
+    size_t want     = 0;
+    const void *src = block_ptr(const_cast<nbvh_ctx *>(ctx), which, want);
+    if (!src || bytes != want)
+        return NBVH_ERR_INVALID_ARG;
+    memcpy(pod_host, src, bytes);
+    return NBVH_OK;
+}
+
+int nbvh_set_camera(nbvh_ctx *ctx, const float matrix16_host[16], float yfov_rad)
+{
+    if (!ctx || !matrix16_host)
+        return NBVH_ERR_INVALID_ARG;
+    if (ctx->fb_w == 0 || ctx->fb_h == 0)
+        return fail(ctx, NBVH_ERR_STATE, "set the framebuffer size before the camera (aspect ratio)");
+    ctx->camera = camera_from_matrix(matrix16_host, yfov_rad, ctx->fb_w, ctx->fb_h);
+    return NBVH_OK;
+}
+
+int nbvh_get_max_depth(const nbvh_ctx *ctx) { return ctx ? ctx->max_depth : NBVH_ERR_INVALID_ARG; }
+int nbvh_set_max_depth(nbvh_ctx *ctx, int max_depth)
+{
+    if (!ctx || max_depth < 1)
+        return NBVH_ERR_INVALID_ARG;
+    ctx->max_depth = max_depth;
+    return NBVH_OK;
+}
+
+// ---- scene, tree-cut, weights --------------------------------------------------------------------------
+int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
+{
+    if (!ctx || !s)
+        return NBVH_ERR_INVALID_ARG;
+    if (s->num_meshes > (uint32_t)kMaxBlas)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "more than 16 BLAS");
+    std::vector<nbvh_cuda_blas> blas(s->num_meshes);
+    if (s->num_meshes)
+        CU_TRY(ctx, cudaMemcpy(blas.data(), s->mesh_bvhs, sizeof(nbvh_cuda_blas) * s->num_meshes, cudaMemcpyDeviceToHost));
+    memset(&ctx->scene, 0, sizeof(ctx->scene));
+    ctx->scene.tlas.nodes        = reinterpret_cast<const float4 *>(s->tlas_nodes);
+    ctx->scene.tlas.blas_indices = s->blas_indices;
+    ctx->scene.tlas.num_meshes   = s->num_meshes;
+    ctx->scene.n_blas            = s->num_meshes;
+    for (uint32_t i = 0; i < s->num_meshes; i++) {
+        ctx->scene.blas[i].nodes        = reinterpret_cast<const float4 *>(blas[i].nodes);
+        ctx->scene.blas[i].prim_indices = reinterpret_cast<const unsigned long long *>(blas[i].prim_indices);
+        ctx->scene.blas[i].vertices     = blas[i].vertices;
+        ctx->scene.blas[i].indices      = blas[i].indices;
+    }
+    ctx->scene_set = true;
+    return NBVH_OK;
+}
+
+static int adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKind kind)
+{
+    if (n == 0)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "empty neural BVH");
+    if (ctx->nbvh_nodes != n) {
+        cudaFree(ctx->d_nbvh);
+        cudaFree(ctx->d_nbvh_dilated);
+        ctx->d_nbvh = ctx->d_nbvh_dilated = nullptr;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_nbvh, (size_t)n * 32));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_nbvh_dilated, (size_t)n * 32));
+        ctx->nbvh_nodes = n;
+    }
+    CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes, (size_t)n * 32, kind));
+    ctx->dilated_with = -1.f;
+    if (!ctx->scene_bbox_set) {
+        // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
+        // (neural_bvh_renderer_accel.cpp:40,248-251)
+        nbvh_node32 root;
+        CU_TRY(ctx, cudaMemcpy(&root, ctx->d_nbvh, 32, cudaMemcpyDeviceToHost));
+        memcpy(ctx->scene_bbox.min, root.aabb_min, 12);
+        memcpy(ctx->scene_bbox.max, root.aabb_max, 12);
+    }
+    return refresh_dilated(ctx);
+}
+
+int nbvh_set_neural_bvh(nbvh_ctx *ctx, const nbvh_node32 *nodes, uint32_t n)
+{
+    if (!ctx || !nodes)
+        return NBVH_ERR_INVALID_ARG;
+    return adopt_nbvh(ctx, nodes, n, cudaMemcpyDeviceToDevice);
+}
+
+// .nbvh = bvh::v2::Bvh<Node<float,3,64,32>>::serialize: u64 n_nodes, u64 n_prim_ids, n_nodes x {6 f32 bounds
+// (minx,maxx,miny,maxy,minz,maxz), u64 first_id, u64 prim_count}, n_prim_ids x u64
+// (/root/reference/ext/bvh/src/bvh/v2/bvh.h:133-153, node.h:119-133)
+int nbvh_load_neural_bvh_file(nbvh_ctx *ctx, const char *path)
+{
+    if (!ctx || !path)
+        return NBVH_ERR_INVALID_ARG;
+    std::string data;
+    if (!read_file(path, data))
+        return fail(ctx, NBVH_ERR_IO, std::string("cannot read ") + path);
+    if (data.size() < 16)
+        return fail(ctx, NBVH_ERR_PARSE, ".nbvh too short");
+    uint64_t n_nodes, n_prims;
+    memcpy(&n_nodes, data.data(), 8);
+    memcpy(&n_prims, data.data() + 8, 8);
+    if (n_nodes == 0 || n_nodes > 0x7FFFFFFFull || data.size() != 16 + n_nodes * 40 + n_prims * 8)
+        return fail(ctx, NBVH_ERR_PARSE, ".nbvh size does not match its header");
+    std::vector<nbvh_node32> nodes(n_nodes);
+    const char *p = data.data() + 16;
+    for (uint64_t i = 0; i < n_nodes; i++, p += 40) {
+        float b[6];
+        uint64_t first, count;
+        memcpy(b, p, 24);
+        memcpy(&first, p + 24, 8);
+        memcpy(&count, p + 32, 8);
+        nodes[i].aabb_min[0] = b[0], nodes[i].aabb_max[0] = b[1];
+        nodes[i].aabb_min[1] = b[2], nodes[i].aabb_max[1] = b[3];
+        nodes[i].aabb_min[2] = b[4], nodes[i].aabb_max[2] = b[5];
+        nodes[i].prim_count_or_left  = (uint32_t)count;
+        nodes[i].left_or_prim_offset = (uint32_t)first;
+    }
+    return adopt_nbvh(ctx, nodes.data(), (uint32_t)n_nodes, cudaMemcpyHostToDevice);
+}
+
+int nbvh_save_neural_bvh_file(nbvh_ctx *ctx, const char *path)
+{
+    if (!ctx || !path)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->d_nbvh)
+        return fail(ctx, NBVH_ERR_STATE, "no neural BVH set");
+    std::vector<nbvh_node32> nodes(ctx->nbvh_nodes);
+    CU_TRY(ctx, cudaMemcpy(nodes.data(), ctx->d_nbvh, (size_t)ctx->nbvh_nodes * 32, cudaMemcpyDeviceToHost));
+    std::ofstream f(path, std::ios::binary);
+    if (!f)
+        return fail(ctx, NBVH_ERR_IO, std::string("cannot write ") + path);
+    const uint64_t n = nodes.size(), one = 1, zero = 0;
+    f.write((const char *)&n, 8);
+    f.write((const char *)&one, 8); // one dummy prim id (neural_bvh_renderer_accel.cpp:186-187)
+    for (auto &nd : nodes) {
+        const float b[6] = {nd.aabb_min[0], nd.aabb_max[0], nd.aabb_min[1], nd.aabb_max[1], nd.aabb_min[2], nd.aabb_max[2]};
+        const uint64_t first = nd.left_or_prim_offset, count = nd.prim_count_or_left;
+        f.write((const char *)b, 24);
+        f.write((const char *)&first, 8);
+        f.write((const char *)&count, 8);
+    }
+    f.write((const char *)&zero, 8);
+    return f ? NBVH_OK : fail(ctx, NBVH_ERR_IO, "write failed");
+}
+
+uint32_t nbvh_neural_bvh_num_nodes(const nbvh_ctx *ctx) { return ctx ? ctx->nbvh_nodes : 0; }
+
+int nbvh_get_neural_bvh_host(const nbvh_ctx *ctx, nbvh_node32 *nodes_host, uint32_t n)
+{
+    if (!ctx || !nodes_host || n != ctx->nbvh_nodes || !ctx->d_nbvh)
+        return NBVH_ERR_INVALID_ARG;
+    return cudaMemcpy(nodes_host, ctx->d_nbvh, (size_t)n * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? NBVH_OK : NBVH_ERR_CUDA;
+}
+
+uint64_t nbvh_n_params(const nbvh_ctx *ctx) { return ctx ? ctx->n_params : 0; }
+
+int nbvh_load_params_host(nbvh_ctx *ctx, const uint16_t *fp16, uint64_t n)
+{
+    if (!ctx || !fp16)
+        return NBVH_ERR_INVALID_ARG;
+    if (n != ctx->n_params)
+        return fail(ctx, NBVH_ERR_INVALID_ARG,
+                    "parameter count mismatch: file has " + std::to_string(n) + ", network needs " +
+                        std::to_string(ctx->n_params));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_params, fp16, n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    int rc = upload_weight_image(ctx, fp16);
+    if (rc != NBVH_OK)
+        return rc;
+    ctx->params_loaded = true;
+    return NBVH_OK;
+}
+
+int nbvh_get_params_host(const nbvh_ctx *ctx, uint16_t *fp16, uint64_t n)
+{
+    if (!ctx || !fp16 || n != ctx->n_params)
+        return NBVH_ERR_INVALID_ARG;
+    return cudaMemcpy(fp16, ctx->d_params, n * sizeof(uint16_t), cudaMemcpyDeviceToHost) == cudaSuccess ? NBVH_OK : NBVH_ERR_CUDA;
+}
+
+// network_models/*_network.json: {"n_params":N,"params_binary":{"bytes":[...],"subtype":null},"params_type":"__half"}
+// (ext/tiny-cuda-nn trainer.h:275-320, gpu_memory_json.h:36-60); "float" payloads are accepted too (trainer.h:292-295)
+int nbvh_load_network_file(nbvh_ctx *ctx, const char *path)
+{
+    if (!ctx || !path)
+        return NBVH_ERR_INVALID_ARG;
+    std::string text;
+    if (!read_file(path, text))
+        return fail(ctx, NBVH_ERR_IO, std::string("cannot read ") + path);
+    Json root;
+    try {
+        root = json_parse(text);
+    } catch (const std::exception &e) {
+        return fail(ctx, NBVH_ERR_PARSE, e.what());
+    }
+    const Json *bin = root.find("params_binary");
+    const Json *bytes = bin ? bin->find("bytes") : nullptr;
+    if (!bytes || (bytes->type != Json::NumArray && bytes->type != Json::Array))
+        return fail(ctx, NBVH_ERR_PARSE, "params_binary.bytes missing");
+    const uint64_t n         = (uint64_t)root.value("n_params", 0.0);
+    const std::string type   = root.value("params_type", std::string("__half"));
+    const size_t elem        = type == "float" ? 4 : 2;
+    if (type != "float" && type != "__half")
+        return fail(ctx, NBVH_ERR_PARSE, "unknown params_type " + type);
+    if (bytes->size() != n * elem)
+        return fail(ctx, NBVH_ERR_PARSE, "params_binary.bytes length does not match n_params");
+    std::vector<uint8_t> raw(bytes->size());
+    for (size_t i = 0; i < raw.size(); i++)
+        raw[i] = (uint8_t)bytes->at_num(i);
+    std::vector<uint16_t> half(n);
+    if (elem == 2) {
+        memcpy(half.data(), raw.data(), raw.size());
+    } else {
+        for (uint64_t i = 0; i < n; i++) {
+            float f;
+            memcpy(&f, raw.data() + 4 * i, 4);
+            half[i] = f32_to_f16_host(f);
+        }
+    }
+    return nbvh_load_params_host(ctx, half.data(), n);
+}
+
+int nbvh_save_network_file(nbvh_ctx *ctx, const char *path)
+{
+    if (!ctx || !path)
+        return NBVH_ERR_INVALID_ARG;
+    std::vector<uint16_t> half(ctx->n_params);
+    CU_TRY(ctx, cudaMemcpy(half.data(), ctx->d_params, half.size() * 2, cudaMemcpyDeviceToHost));
+    FILE *f = fopen(path, "wb");
+    if (!f)
+        return fail(ctx, NBVH_ERR_IO, std::string("cannot write ") + path);
+    fprintf(f, "{\"n_params\":%llu,\"params_binary\":{\"bytes\":[", (unsigned long long)ctx->n_params);
+    const uint8_t *b = reinterpret_cast<const uint8_t *>(half.data());
+    std::string buf;
+    buf.reserve(1 << 20);
+    for (size_t i = 0; i < half.size() * 2; i++) {
+        if (i)
+            buf += ',';
+        buf += std::to_string((unsigned)b[i]);
+        if (buf.size() > (1 << 20) - 8) {
+            fwrite(buf.data(), 1, buf.size(), f);
+            buf.clear();
+        }
+    }
+    fwrite(buf.data(), 1, buf.size(), f);
+    fprintf(f, "],\"subtype\":null},\"params_type\":\"__half\"}");
+    fclose(f);
+    return NBVH_OK;
+}
+
+// tcnn initial values: grid U(-1e-4, 1e-4) (grid.h:1059-1062), MLP Xavier uniform (fully_fused_mlp.cu:866-891).
+// Own splitmix64 stream (tcnn uses pcg32 seed 1337; initial weights are statistically, not bitwise, equivalent).
+int nbvh_init_params(nbvh_ctx *ctx, uint64_t seed)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    std::vector<uint16_t> p(ctx->n_params);
+    uint64_t s = seed;
+    auto next  = [&]() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (float)((z >> 40) * (1.0 / 16777216.0)); // [0,1)
+    };
+    size_t idx = 0;
+    for (uint32_t l = 0; l < ctx->n_layers; l++) {
+        const uint32_t k = l == 0 ? ctx->in_k : (uint32_t)kNeurons;
+        const uint32_t n = l + 1 == ctx->n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+        const float sc   = sqrtf(6.f / (float)(k + n));
+        for (uint32_t i = 0; i < n * k; i++)
+            p[idx++] = f32_to_f16_host((next() * 2.f - 1.f) * sc);
+    }
+    for (; idx < p.size(); idx++)
+        p[idx] = f32_to_f16_host((next() * 2.f - 1.f) * 1e-4f);
+    return nbvh_load_params_host(ctx, p.data(), p.size());
+}
+
+// ---- inference ------------------------------------------------------------------------------------------
+int nbvh_set_framebuffer(nbvh_ctx *ctx, float *accum, uint8_t *ldr, uint32_t w, uint32_t h)
+{
+    if (!ctx || w == 0 || h == 0)
+        return NBVH_ERR_INVALID_ARG;
+    if (ctx->own_accum)
+        cudaFree(ctx->accum);
+    if (ctx->own_ldr)
+        cudaFree(ctx->ldr);
+    ctx->accum = nullptr, ctx->ldr = nullptr, ctx->own_accum = ctx->own_ldr = false;
+    ctx->fb_w = w, ctx->fb_h = h;
+    const size_t n = (size_t)w * h;
+    if (accum) {
+        ctx->accum = reinterpret_cast<float4 *>(accum);
+    } else {
+        CU_TRY(ctx, cudaMalloc(&ctx->accum, n * sizeof(float4)));
+        CU_TRY(ctx, cudaMemset(ctx->accum, 0, n * sizeof(float4)));
+        ctx->own_accum = true;
+    }
+    if (ldr) {
+        ctx->ldr = reinterpret_cast<uchar4 *>(ldr);
+    } else {
+        CU_TRY(ctx, cudaMalloc(&ctx->ldr, n * sizeof(uchar4)));
+        CU_TRY(ctx, cudaMemset(ctx->ldr, 0, n * sizeof(uchar4)));
+        ctx->own_ldr = true;
+    }
+    cudaFree(ctx->own_hits);
+    ctx->own_hits = nullptr;
+    ctx->hits     = nullptr;
+    return NBVH_OK;
+}
+
+int nbvh_set_hit_buffer(nbvh_ctx *ctx, nbvh_hit_record *hits)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    ctx->hits = hits;
+    return NBVH_OK;
+}
+
+int nbvh_query(nbvh_ctx *ctx, const float *in, float *out, uint32_t n, void *stream)
+{
+    if (!ctx || (n && (!in || !out)))
+        return NBVH_ERR_INVALID_ARG;
+    int rc = check_ready(ctx, false, false, true);
+    if (rc != NBVH_OK)
+        return rc;
+    const NetConst nc = make_net_const(ctx);
+    KernelTimer kt(ctx, (cudaStream_t)stream);
+    CU_TRY(ctx, launch_query(nc, in, out, n, ctx->module_const.input_network_dims, ctx->d_counters, ctx->num_sms,
+                             (cudaStream_t)stream));
+    kt.stop();
+    return NBVH_OK;
+}
+
+int nbvh_trace_intervals(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t max_intervals, uint32_t *counts,
+                         uint32_t *node_idx, float *mint, float *maxt, void *stream)
+{
+    if (!ctx || (n && (!o || !d || !counts || !node_idx || !mint || !maxt)))
+        return NBVH_ERR_INVALID_ARG;
+    int rc = check_ready(ctx, false, true, false);
+    if (rc == NBVH_OK)
+        rc = refresh_dilated(ctx);
+    if (rc != NBVH_OK)
+        return rc;
+    KernelTimer kt(ctx, (cudaStream_t)stream);
+    CU_TRY(ctx, launch_trace_intervals(make_nbvh_const(ctx, true), o, d, n, max_intervals, counts, node_idx, mint, maxt,
+                                       ctx->d_counters, (cudaStream_t)stream));
+    kt.stop();
+    return NBVH_OK;
+}
+
+int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const float *d, const float *maxt, uint32_t n,
+                        float *t, float *u, float *v, uint32_t *prim, void *stream)
+{
+    if (!ctx || (n && (!o || !d || !t || !u || !v || !prim)))
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->scene_set || blas_idx >= ctx->scene.n_blas)
+        return fail(ctx, NBVH_ERR_STATE, "scene not set or BLAS index out of range");
+    KernelTimer kt(ctx, (cudaStream_t)stream);
+    CU_TRY(ctx, launch_blas_intersect(ctx->scene.blas[blas_idx], o, d, maxt, n, t, u, v, prim, ctx->d_counters,
+                                      (cudaStream_t)stream));
+    kt.stop();
+    return NBVH_OK;
+}
+
+static CameraConst make_camera_const(const nbvh_ctx *ctx)
+{
+    CameraConst cc;
+    memcpy(cc.origin, ctx->camera.origin, 12);
+    memcpy(cc.du, ctx->camera.du, 12);
+    memcpy(cc.dv, ctx->camera.dv, 12);
+    memcpy(cc.top_left, ctx->camera.dir_top_left, 12);
+    cc.fb_w = ctx->fb_w, cc.fb_h = ctx->fb_h;
+    return cc;
+}
+
+int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx, int sample_offset, float *o, float *d,
+                void *stream)
+{
+    if (!ctx || (n && (!o || !d)))
+        return NBVH_ERR_INVALID_ARG;
+    if (ctx->fb_w == 0)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    CU_TRY(ctx, launch_raygen(make_camera_const(ctx), first_pixel, n, sample_idx, sample_offset, o, d, (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
+int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
+                void *stream)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    int rc = check_ready(ctx, true, true, true);
+    if (rc == NBVH_OK)
+        rc = refresh_dilated(ctx);
+    if (rc != NBVH_OK)
+        return rc;
+    if (!ctx->accum)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    if (ctx->max_depth != 1)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED,
+                    "max_depth > 1 needs the shading row (Disney BSDF sampling, SURVEY 8 f1); set max_depth to 1");
+    const uint32_t total = ctx->fb_w * ctx->fb_h;
+    if (pixel_count == 0) {
+        first_pixel = 0;
+        pixel_count = total;
+    }
+    if (first_pixel >= total || pixel_count > total - first_pixel)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "pixel range outside the framebuffer");
+    if ((first_pixel & 31u) != 0u)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "first_pixel must be a multiple of 32");
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.cam   = make_camera_const(ctx);
+    rp.nbvh  = make_nbvh_const(ctx, true);
+    rp.scene = ctx->scene;
+    rp.enc   = make_encode_const(ctx);
+    rp.dec.primary_thr         = ctx->pt_const.primary_visibility_threshold;
+    rp.dec.secondary_thr       = ctx->pt_const.secondary_visibility_threshold;
+    rp.dec.depth_epsilon       = ctx->pt_const.depth_epsilon;
+    rp.dec.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
+    rp.ignore_neural_blas      = ctx->bvh_const.ignore_neural_blas;
+    rp.max_depth               = (uint32_t)ctx->max_depth;
+    rp.envmap_eval             = ctx->scene_const.envmap_eval;
+    rp.skylike_background      = ctx->scene_const.skylike_background;
+    rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
+    rp.next_chunk    = ctx->d_next_chunk;
+    rp.sample_idx    = (int)accumulated_spp;
+    rp.sample_offset = (int)sample_offset;
+    rp.accum = ctx->accum, rp.ldr = ctx->ldr, rp.hits = ctx->hits;
+    rp.ema_accumulate = ctx->scene_const.ema_accumulate;
+    rp.ema_weight     = ctx->scene_const.ema_weight;
+    rp.counters       = ctx->d_counters;
+    const NetConst nc = make_net_const(ctx);
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, sizeof(uint32_t), st));
+    KernelTimer kt(ctx, st);
+    CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
+    kt.stop();
+    return NBVH_OK;
+}
+
+int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
+                     uint8_t *ldr_host, nbvh_hit_record *hits_host)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    if (camera_host)
+        ctx->camera = *camera_host; // the per-frame constant upload of the reference (setup_constants)
+    const size_t n = (size_t)ctx->fb_w * ctx->fb_h;
+    if (hits_host && !ctx->hits) {
+        if (!ctx->own_hits)
+            CU_TRY(ctx, cudaMalloc(&ctx->own_hits, n * sizeof(nbvh_hit_record)));
+        ctx->hits = ctx->own_hits;
+    }
+    int rc = nbvh_render(ctx, accumulated_spp, sample_offset, 0, 0, nullptr);
+    if (rc != NBVH_OK)
+        return rc;
+    if (ldr_host)
+        CU_TRY(ctx, cudaMemcpyAsync(ldr_host, ctx->ldr, n * sizeof(uchar4), cudaMemcpyDeviceToHost, 0));
+    if (hits_host)
+        CU_TRY(ctx, cudaMemcpyAsync(hits_host, ctx->hits, n * sizeof(nbvh_hit_record), cudaMemcpyDeviceToHost, 0));
+    CU_TRY(ctx, cudaStreamSynchronize(0));
+    return NBVH_OK;
+}
+
+int nbvh_get_counters(nbvh_ctx *ctx, uint64_t *out_host, uint32_t n)
+{
+    if (!ctx || !out_host || n > CNT_COUNT)
+        return NBVH_ERR_INVALID_ARG;
+    CU_TRY(ctx, cudaMemcpy(out_host, ctx->d_counters, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+    return NBVH_OK;
+}
+
+int nbvh_reset_counters(nbvh_ctx *ctx)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    CU_TRY(ctx, cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT));
+    ctx->total_ms = 0.f, ctx->launches = 0;
+    return NBVH_OK;
+}
+
+int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    ctx->timing = enable != 0;
+    return NBVH_OK;
+}
+
+int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    if (total_ms)
+        *total_ms = ctx->total_ms;
+    if (launches)
+        *launches = ctx->launches;
+    return NBVH_OK;
+}
+
+// ---- online optimisation (implemented in training.cu once the row lands) --------------------------------------
+int nbvh_training_step(nbvh_ctx *ctx, const float *, const float *, uint32_t, float *, float *, void *)
+{
+    return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet");
+}
+int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *, const float *, uint32_t, uint32_t, float *, float *, void *)
+{
+    return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet");
+}
+float *nbvh_gradients(nbvh_ctx *ctx) { return ctx ? ctx->d_grads : nullptr; }
+int nbvh_optimizer_step(nbvh_ctx *ctx, void *) { return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet"); }
+uint32_t nbvh_training_step_count(const nbvh_ctx *ctx) { return ctx ? ctx->training_step : 0; }
+
+} // extern "C"

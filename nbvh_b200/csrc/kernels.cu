@@ -1,0 +1,562 @@
+// kernels.cu -- CUDA kernels of the neural ray-query hot path for sm_100a.
+//
+//   k_render          persistent wavefront-free megakernel: ray generation, TLAS + N-BVH walk with the
+//                     stack in thread-private storage, 3-point segment encoding, hash-grid gather, the
+//                     64-wide MLP on tcgen05/TMEM, depth decode, closest-hit bookkeeping, classical BLAS
+//                     closest hit and the final splat -- replaces K1,K2,K3x3,K4,K5,K6,K7,K8 and the
+//                     max_depth = 1 part of K9 and the host loops of
+//                     /root/reference/src/cuda/neural/path/path_module.cu:54-245.
+//   k_query           == tcnn::NetworkWithInputEncoding::inference (path_module.cu:92)
+//   k_trace_intervals / k_blas_intersect / k_raygen   parity hooks on the traversal building blocks
+//
+// Compiled with -fmad=false: see device_core.cuh for the arithmetic contract.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace nbvh {
+
+constexpr int kTilesPerCta   = 2;
+constexpr int kCtaThreads    = kTilesPerCta * kTileRows;
+constexpr int kRefillRounds  = 6;
+
+// ------------------------------------------------------------------------------------------------ CTA setup
+struct CtaShared {
+    uint8_t *base;
+    SmemLayout lay;
+};
+
+// Loads the packed weights with one TMA bulk copy, allocates TMEM, initialises the per-tile mbarriers.
+// Returns the TMEM base address.  Must be called by all threads of the CTA.
+__device__ __forceinline__ uint32_t cta_setup(const NetConst &nc, uint8_t *smem, const SmemLayout &lay)
+{
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t bar_base = smem_u32(smem + lay.bar_off);
+    const uint32_t w_bar    = bar_base + 8u * kTilesPerCta;
+    if (tid == 0) {
+        for (int t = 0; t < kTilesPerCta; ++t)
+            mbar_init(bar_base + 8u * t, 1u);
+        mbar_init(w_bar, 1u);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(w_bar, nc.wimg_bytes);
+        tma_bulk_g2s(smem_u32(smem + lay.w_off), nc.wimg, nc.wimg_bytes, w_bar);
+    }
+    if (tid < 32) {
+        tmem_alloc(smem_u32(smem + lay.tmem_off), 64u * kTilesPerCta); // 64 fp32 accumulator columns per tile
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
+    mbar_wait(w_bar, 0u); // weights landed (async proxy writes are visible after the mbarrier completes)
+    return tmem_base;
+}
+
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base)
+{
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 64u * kTilesPerCta);
+    }
+}
+
+__device__ __forceinline__ TileCtx make_tile(uint8_t *smem, const SmemLayout &lay, const NetConst &nc, uint32_t tile,
+                                             uint32_t tmem_base)
+{
+    const uint32_t a_bytes = kTileRows * (nc.in_k > (uint32_t)kNeurons ? nc.in_k : (uint32_t)kNeurons) * 2u;
+    TileCtx t;
+    t.a_tile   = smem + lay.a_off + tile * a_bytes;
+    t.w_smem   = smem_u32(smem + lay.w_off);
+    t.mma_bar  = smem_u32(smem + lay.bar_off) + 8u * tile;
+    t.tmem_acc = tmem_base + 64u * tile;
+    t.bar_id   = 1u + tile;
+    t.phase    = 0u;
+    return t;
+}
+
+__device__ __forceinline__ void warp_add_counter(unsigned long long *counters, int slot, uint32_t v)
+{
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0u && v != 0u && counters)
+        atomicAdd(counters + slot, (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------------------ k_query
+__global__ void __launch_bounds__(kCtaThreads, 2)
+k_query(const __grid_constant__ NetConst nc, const float *__restrict__ in, float *__restrict__ out, uint32_t n,
+        uint32_t n_in_dims, unsigned long long *counters)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
+    const uint32_t tmem_base = cta_setup(nc, smem, lay);
+    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t row       = threadIdx.x % kTileRows;
+    TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
+
+    const uint32_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    uint32_t iters         = 0;
+    for (uint32_t tt = blockIdx.x * kTilesPerCta + tile; tt < n_tiles; tt += gridDim.x * kTilesPerCta) {
+        const uint32_t i = tt * kTileRows + row;
+        const bool valid = i < n;
+        float pts[12];
+        if (valid) {
+#pragma unroll
+            for (uint32_t j = 0; j < 12; ++j)
+                pts[j] = j < n_in_dims ? __ldg(in + (size_t)i * n_in_dims + j) : 0.f;
+        }
+        encode_row_to_tile(nc, t.a_tile, row, pts, valid);
+        fence_proxy_async_smem();
+        float y[8];
+        mlp_tile_forward(nc, t, row, y);
+        if (valid) {
+            for (uint32_t j = 0; j < nc.n_out; ++j)
+                out[(size_t)i * nc.n_out + j] = y[j];
+        }
+        ++iters;
+    }
+    if (row == 0 && counters && iters)
+        atomicAdd(counters + CNT_TILE_ITERS, (unsigned long long)iters);
+    cta_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ parity hooks
+__global__ void k_trace_intervals(NbvhConst bc, const float *__restrict__ o, const float *__restrict__ d, uint32_t n,
+                                  uint32_t max_intervals, uint32_t *__restrict__ counts, uint32_t *__restrict__ node_idx,
+                                  float *__restrict__ mint, float *__restrict__ maxt, unsigned long long *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps   = 0;
+    if (i < n) {
+        Ray r;
+        r.ox = o[3 * i], r.oy = o[3 * i + 1], r.oz = o[3 * i + 2];
+        r.dx = d[3 * i], r.dy = d[3 * i + 1], r.dz = d[3 * i + 2];
+        uint32_t stack[kNeuralStackSize];
+        int ss    = 1;
+        stack[0]  = 0;
+        uint32_t k = 0;
+        while (ss > 0) {
+            float a, b;
+            uint32_t ni;
+            if (!nbvh_next_interval(bc, r, stack, ss, FLT_MAX, a, b, ni, steps))
+                break;
+            if (k < max_intervals) {
+                node_idx[(size_t)i * max_intervals + k] = ni;
+                mint[(size_t)i * max_intervals + k]     = a;
+                maxt[(size_t)i * max_intervals + k]     = b;
+            }
+            ++k;
+        }
+        counts[i] = k;
+    }
+    warp_add_counter(counters, CNT_NBVH_STEPS, steps);
+}
+
+__global__ void k_blas_intersect(BlasConst b, const float *__restrict__ o, const float *__restrict__ d,
+                                 const float *__restrict__ maxt, uint32_t n, float *__restrict__ t, float *__restrict__ u,
+                                 float *__restrict__ v, uint32_t *__restrict__ prim, unsigned long long *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps = 0, tests = 0;
+    if (i < n) {
+        Ray r;
+        r.ox = o[3 * i], r.oy = o[3 * i + 1], r.oz = o[3 * i + 2];
+        r.dx = d[3 * i], r.dy = d[3 * i + 1], r.dz = d[3 * i + 2];
+        const TriHit h = blas_closest_hit(b, r, 1e-4f, maxt ? maxt[i] : FLT_MAX, steps, tests);
+        t[i] = h.t, u[i] = h.u, v[i] = h.v, prim[i] = h.prim;
+    }
+    warp_add_counter(counters, CNT_BLAS_STEPS, steps);
+    warp_add_counter(counters, CNT_TRI_TESTS, tests);
+}
+
+__global__ void k_raygen(CameraConst cam, uint32_t first, uint32_t n, int sample_idx, int sample_offset,
+                         float *__restrict__ o, float *__restrict__ d)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t rng;
+    const Ray r = camera_ray(cam, first + i, sample_idx, sample_offset, rng);
+    o[3 * i] = r.ox, o[3 * i + 1] = r.oy, o[3 * i + 2] = r.oz;
+    d[3 * i] = r.dx, d[3 * i + 1] = r.dy, d[3 * i + 2] = r.dz;
+}
+
+// Stores a copy of the N-BVH whose boxes are already dilated by fixed_node_dilation (same operations as
+// the on-the-fly dilation -> same bits), so the inference walk does no per-visit dilation arithmetic.
+__global__ void k_predilate(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t n, float dilation)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    Node nd = load_node(src, i);
+    dilate_node(nd, dilation);
+    dst[2 * i]     = make_float4(nd.mnx, nd.mny, nd.mnz, __uint_as_float(nd.a));
+    dst[2 * i + 1] = make_float4(nd.mxx, nd.mxy, nd.mxz, __uint_as_float(nd.b));
+}
+
+// ------------------------------------------------------------------------------------------------ k_render
+struct LaneState {
+    Ray ray;
+    uint32_t pixel;
+    uint32_t rng;
+    // closest hit so far (NeuralTraversalResult / HybridIntersectionResult)
+    float best_t;
+    uint32_t valid_hit;
+    float n_or_uv[3];
+    float alb_or_ids[3];
+    // pending query
+    float seg_mint, seg_maxt;
+    int tss, nss;
+    bool have_ray, have_query, neural_active;
+};
+
+// accumulate_pixel_value (include/cuda/neural/neural_bvh_renderer_kernels.cuh:81-127) on linear memory
+__device__ __forceinline__ float linear_to_srgb(float x)
+{
+    return (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(x, 0.f), 1.f / 2.4f) - 0.055f;
+}
+
+__device__ __forceinline__ void splat(const RenderParams &p, uint32_t pixel, float r, float g, float b, float alpha)
+{
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.sample_idx > 0)
+        acc = p.accum[pixel];
+    if (p.ema_accumulate) {
+        if (alpha == 0.f && p.sample_idx > 0)
+            return;
+        if (p.sample_idx > 0) {
+            const float w = p.ema_weight, iw = 1.f - p.ema_weight;
+            acc = make_float4(r * w + acc.x * iw, g * w + acc.y * iw, b * w + acc.z * iw, alpha * w + acc.w * iw);
+        } else {
+            acc = make_float4(r, g, b, alpha);
+        }
+        p.accum[pixel] = acc;
+    } else {
+        acc            = make_float4(acc.x + r, acc.y + g, acc.z + b, acc.w + alpha);
+        p.accum[pixel] = acc;
+        const float inv = 1.f / float(p.sample_idx + 1);
+        acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+    if (p.ldr) {
+        uchar4 px;
+        px.x = (unsigned char)min(max(int(linear_to_srgb(acc.x) * 256.0f), 0), 255);
+        px.y = (unsigned char)min(max(int(linear_to_srgb(acc.y) * 256.0f), 0), 255);
+        px.z = (unsigned char)min(max(int(linear_to_srgb(acc.z) * 256.0f), 0), 255);
+        px.w = 255;
+        p.ldr[pixel] = px;
+    }
+}
+
+// background_hit_eval (path_inference_kernels.cu:37-59); the HDR environment texture belongs to the shading
+// row and evaluates to black here.
+__device__ __forceinline__ void background(const RenderParams &p, const Ray &ray, float bg[3])
+{
+    bg[0] = bg[1] = bg[2] = 0.f;
+    if (!p.envmap_eval)
+        return;
+    if (p.skylike_background) {
+        const float a = 0.5f * (ray.dy + 1.f);
+        bg[0] = (1.f - a) * 1.f + a * 0.5f;
+        bg[1] = (1.f - a) * 1.f + a * 0.7f;
+        bg[2] = (1.f - a) * 1.f + a * 1.f;
+    }
+}
+
+// The ray reached the end of its TLAS walk: hybrid_scatter_and_get_next_tlas_traversal_step with
+// ray_depth == max_depth (path_inference_kernels.cu:306-321): add the background when nothing was hit, splat.
+__device__ __forceinline__ void finish_ray(const RenderParams &p, LaneState &s)
+{
+    float illum[3] = {0.f, 0.f, 0.f};
+    if (s.valid_hit == 0u)
+        background(p, s.ray, illum);
+    splat(p, s.pixel, illum[0], illum[1], illum[2], 1.0f);
+    if (p.hits) {
+        nbvh_hit_record h;
+        h.t = s.best_t, h.valid_hit = s.valid_hit;
+        h.normal_or_uv[0] = s.n_or_uv[0], h.normal_or_uv[1] = s.n_or_uv[1], h.normal_or_uv[2] = s.n_or_uv[2];
+        h.albedo_or_ids[0] = s.alb_or_ids[0], h.albedo_or_ids[1] = s.alb_or_ids[1], h.albedo_or_ids[2] = s.alb_or_ids[2];
+        p.hits[s.pixel] = h;
+    }
+    s.have_ray = false;
+}
+
+// 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1)
+__device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_t s)
+{
+    const uint32_t w = p.cam.fb_w, h = p.cam.fb_h;
+    if ((w & 7u) || (h & 3u))
+        return s;
+    const uint32_t chunk = s >> 5, k = s & 31u;
+    const uint32_t bpr = w >> 3;
+    const uint32_t bx = chunk % bpr, by = chunk / bpr;
+    return (by * 4u + (k >> 3)) * w + bx * 8u + (k & 7u);
+}
+
+// Advances the lane's ray until it has a network query pending or the ray is finished
+// (tlas_traversal_and_fill_next_hybrid_traversal, neural_bvh_module_common.cuh:291-420;
+//  process_bvh_network_output_and_intersect_neural_bvh :497-550; non_neural_bvh_intersection,
+//  path_inference_kernels.cu:195-222).
+__device__ __forceinline__ void advance_ray(const RenderParams &p, LaneState &s, uint32_t *nstack, uint32_t *tstack,
+                                            uint32_t &cnt_nbvh, uint32_t &cnt_blas, uint32_t &cnt_tri)
+{
+    for (;;) {
+        if (s.neural_active) {
+            // resume the N-BVH walk with ray.maxt = current closest t
+            uint32_t node;
+            if (s.nss > 0 &&
+                nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
+                s.have_query = true;
+                return;
+            }
+            s.neural_active = false;
+        }
+        uint32_t blas_idx;
+        bool is_neural;
+        if (s.tss == 0 || !tlas_next_blas(p.scene.tlas, s.ray, tstack, s.tss, blas_idx, is_neural)) {
+            finish_ray(p, s);
+            return;
+        }
+        if (is_neural && !p.ignore_neural_blas) {
+            nstack[0] = 0u;
+            s.nss     = 1;
+            uint32_t node;
+            // first interval of this BLAS: maxt = FLT_MAX (common.cuh:338-348)
+            if (nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, FLT_MAX, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
+                s.neural_active = true;
+                s.have_query    = true;
+                return;
+            }
+        } else if (blas_idx < p.scene.n_blas) {
+            const TriHit h = blas_closest_hit(p.scene.blas[blas_idx], s.ray, 1e-4f, s.best_t, cnt_blas, cnt_tri);
+            if (h.t < s.best_t) { // set_or_update_with_preliminary_its_data (path_module.h:150-175)
+                s.best_t        = h.t;
+                s.valid_hit     = 2u;
+                s.n_or_uv[0]    = h.u, s.n_or_uv[1] = h.v, s.n_or_uv[2] = 0.f;
+                s.alb_or_ids[0] = __uint_as_float(blas_idx), s.alb_or_ids[1] = __uint_as_float(h.prim);
+                s.alb_or_ids[2] = 0.f;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kCtaThreads, 2)
+k_render(const __grid_constant__ RenderParams p, const __grid_constant__ NetConst nc)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_flags[kCtaThreads / 32];
+    const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
+    const uint32_t tmem_base = cta_setup(nc, smem, lay);
+    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t row       = threadIdx.x % kTileRows;
+    const uint32_t lane      = threadIdx.x & 31u;
+    const uint32_t warp      = threadIdx.x >> 5;
+    TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
+
+    uint32_t nstack[kNeuralStackSize];
+    uint32_t tstack[kTlasStackSize];
+    LaneState s;
+    s.have_ray = s.have_query = s.neural_active = false;
+    s.tss = s.nss = 0;
+    s.best_t      = FLT_MAX;
+    s.valid_hit   = 0u;
+    s.pixel       = 0u;
+
+    // per-warp work chunk (32 pixels of the swizzled order)
+    const uint32_t n_chunks = (p.pixel_count + 31u) >> 5;
+    uint32_t chunk_base = 0u, chunk_used = 32u;
+    bool exhausted = false;
+
+    uint32_t cnt_rays = 0, cnt_q = 0, cnt_nbvh = 0, cnt_blas = 0, cnt_tri = 0, cnt_iters = 0;
+
+    for (;;) {
+        // ---------------- phase A: every lane works until it owns a pending query (or the frame is exhausted)
+        for (int round = 0; round < kRefillRounds; ++round) {
+            // refill idle lanes from the warp's chunk (warp-converged)
+            uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, !s.have_ray);
+            while (need_mask && !exhausted) {
+                if (chunk_used == 32u) {
+                    uint32_t c = 0;
+                    if (lane == 0)
+                        c = atomicAdd(p.next_chunk, 1u);
+                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                    if (c >= n_chunks) {
+                        exhausted = true;
+                        break;
+                    }
+                    chunk_base = c << 5, chunk_used = 0u;
+                }
+                const uint32_t avail = 32u - chunk_used;
+                const uint32_t rank  = __popc(need_mask & ((1u << lane) - 1u));
+                const bool mine      = !s.have_ray && rank < avail;
+                if (mine) {
+                    const uint32_t sidx = chunk_base + chunk_used + rank;
+                    if (sidx < p.pixel_count) {
+                        s.pixel = swizzle_pixel(p, p.first_pixel + sidx);
+                        s.ray   = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, s.rng);
+                        s.have_ray = true, s.have_query = false, s.neural_active = false;
+                        s.best_t = FLT_MAX, s.valid_hit = 0u;
+                        s.n_or_uv[0] = s.n_or_uv[1] = s.n_or_uv[2] = 0.f;
+                        s.alb_or_ids[0] = s.alb_or_ids[1] = s.alb_or_ids[2] = 0.f;
+                        tstack[0] = 0u, s.tss = 1, s.nss = 0;
+                        ++cnt_rays;
+                    }
+                }
+                const uint32_t want = __popc(need_mask);
+                chunk_used += want < avail ? want : avail;
+                // lanes that were served (with or without a valid pixel) leave the mask
+                need_mask = __ballot_sync(0xFFFFFFFFu, !s.have_ray && !(rank < avail));
+            }
+            const bool work = s.have_ray && !s.have_query;
+            if (!__any_sync(0xFFFFFFFFu, work))
+                break;
+            if (work)
+                advance_ray(p, s, nstack, tstack, cnt_nbvh, cnt_blas, cnt_tri);
+            __syncwarp();
+            if (__all_sync(0xFFFFFFFFu, s.have_query))
+                break;
+            if (exhausted && !__any_sync(0xFFFFFFFFu, s.have_ray && !s.have_query))
+                break;
+        }
+        // ---------------- tile-wide agreement: anything to infer?  anything left at all?
+        {
+            const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
+            const uint32_t live = (__any_sync(0xFFFFFFFFu, s.have_ray) || !exhausted) ? 2u : 0u;
+            if (lane == 0)
+                s_flags[warp] = q | live;
+            named_bar_sync(t.bar_id, kTileRows);
+            uint32_t f = 0;
+#pragma unroll
+            for (int w = 0; w < kTileRows / 32; ++w)
+                f |= s_flags[tile * (kTileRows / 32) + w];
+            named_bar_sync(t.bar_id, kTileRows); // flags may be rewritten next iteration
+            if (f == 0u)
+                break;
+            if (!(f & 1u))
+                continue;
+        }
+        // ---------------- phase B: segment encoding + hash grid -> A tile (a8, a9)
+        float pts[12];
+        if (s.have_query) {
+            float eo[3], ei[3];
+            encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                if (k < p.enc.n_points) {
+                    pts[3 * k]     = lerp_point(eo[0], ei[0], p.enc.point_s[k]);
+                    pts[3 * k + 1] = lerp_point(eo[1], ei[1], p.enc.point_s[k]);
+                    pts[3 * k + 2] = lerp_point(eo[2], ei[2], p.enc.point_s[k]);
+                }
+            }
+        }
+        encode_row_to_tile(nc, t.a_tile, row, pts, s.have_query);
+        fence_proxy_async_smem();
+        // ---------------- phase C: MLP on tensor cores (a10)
+        float y[8];
+        mlp_tile_forward(nc, t, row, y);
+        ++cnt_iters;
+        // ---------------- phase D: decode + closest-hit update (a11); the walk resumes in phase A (a12)
+        if (s.have_query) {
+            ++cnt_q;
+            float t_hit;
+            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, 1u, t_hit) && t_hit < s.best_t) {
+                s.best_t    = t_hit;
+                s.valid_hit = 1u;
+                decode_normal(y[2], y[3], y[4], s.n_or_uv);
+                s.alb_or_ids[0] = y[5], s.alb_or_ids[1] = y[6], s.alb_or_ids[2] = y[7];
+            }
+            s.have_query = false;
+            if (s.nss == 0)
+                s.neural_active = false;
+        }
+    }
+    warp_add_counter(p.counters, CNT_RAYS, cnt_rays);
+    warp_add_counter(p.counters, CNT_QUERIES, cnt_q);
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
+    warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
+    if (row == 0 && p.counters && cnt_iters)
+        atomicAdd(p.counters + CNT_TILE_ITERS, (unsigned long long)cnt_iters);
+    cta_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static uint32_t g_smem_bytes = 0;
+
+cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k)
+{
+    const SmemLayout lay = smem_layout(wimg_bytes, in_k, kTilesPerCta);
+    g_smem_bytes         = lay.total;
+    cudaError_t e = cudaFuncSetAttribute(k_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    if (e != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+}
+
+cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32_t n, uint32_t n_in_dims,
+                         unsigned long long *counters, int num_sms, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    const uint32_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    uint32_t grid          = (n_tiles + kTilesPerCta - 1) / kTilesPerCta;
+    const uint32_t cap     = (uint32_t)num_sms * 2u;
+    if (grid > cap)
+        grid = cap;
+    k_query<<<grid, kCtaThreads, g_smem_bytes, stream>>>(nc, in, out, n, n_in_dims, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_intervals(const NbvhConst &bc, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
+                                   uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt,
+                                   unsigned long long *counters, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_trace_intervals<<<(n + 127) / 128, 128, 0, stream>>>(bc, o, d, n, max_intervals, counts, node_idx, mint, maxt, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_blas_intersect(const BlasConst &b, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
+                                  float *u, float *v, uint32_t *prim, unsigned long long *counters, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_blas_intersect<<<(n + 127) / 128, 128, 0, stream>>>(b, o, d, maxt, n, t, u, v, prim, counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_raygen(const CameraConst &cam, uint32_t first, uint32_t n, int sample_idx, int sample_offset, float *o,
+                          float *d, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_raygen<<<(n + 127) / 128, 128, 0, stream>>>(cam, first, n, sample_idx, sample_offset, o, d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_predilate<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n, dilation);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream)
+{
+    if (rp.pixel_count == 0)
+        return cudaSuccess;
+    const uint32_t n_chunks = (rp.pixel_count + 31u) >> 5;
+    uint32_t grid           = (uint32_t)num_sms * 2u; // 2 resident CTAs per SM (launch bounds), persistent
+    const uint32_t needed   = (n_chunks + (kCtaThreads / 32) - 1) / (kCtaThreads / 32);
+    if (grid > needed)
+        grid = needed;
+    k_render<<<grid, kCtaThreads, g_smem_bytes, stream>>>(rp, nc);
+    return cudaGetLastError();
+}
+
+} // namespace nbvh

@@ -1,0 +1,80 @@
+// kernels.cuh -- kernel parameter blocks shared between kernels.cu (device) and context.cu (host)
+#pragma once
+#include "device_core.cuh"
+#include "mlp_tile.cuh"
+#include "../../include/nbvh_b200.h"
+
+namespace nbvh {
+
+constexpr int kMaxBlas = 16;
+
+enum Counter {
+    CNT_RAYS = 0,
+    CNT_QUERIES,
+    CNT_NBVH_STEPS,
+    CNT_BLAS_STEPS,
+    CNT_TRI_TESTS,
+    CNT_TILE_ITERS,
+    CNT_COUNT
+};
+
+struct SceneConst {
+    TlasConst tlas;
+    BlasConst blas[kMaxBlas];
+    uint32_t n_blas;
+};
+
+struct RenderParams {
+    CameraConst cam;
+    NbvhConst nbvh;
+    SceneConst scene;
+    EncodeConst enc;
+    DecodeConst dec;
+    uint32_t ignore_neural_blas;
+    uint32_t max_depth;
+    // background for rays that escape (scene_constants: envmap_eval off or skylike_background)
+    uint32_t envmap_eval, skylike_background;
+    // work distribution
+    uint32_t first_pixel, pixel_count; // shard of the frame rendered by this launch
+    uint32_t *next_chunk;               // global work counter (32-pixel chunks)
+    int sample_idx, sample_offset;
+    // outputs
+    float4 *accum;          // RGBA32F accumulation buffer (linear memory replaces the GL surface)
+    uchar4 *ldr;            // sRGB8 framebuffer
+    nbvh_hit_record *hits;  // optional per-pixel primary-hit records
+    uint32_t ema_accumulate;
+    float ema_weight;
+    unsigned long long *counters;
+};
+
+// smem carve-up of the tile kernels
+struct SmemLayout {
+    uint32_t w_off, a_off, bar_off, tmem_off, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(uint32_t wimg_bytes, uint32_t in_k, uint32_t tiles)
+{
+    SmemLayout s;
+    s.w_off    = 0;
+    s.a_off    = (wimg_bytes + 127u) & ~127u;
+    const uint32_t a_bytes = kTileRows * (in_k > (uint32_t)kNeurons ? in_k : (uint32_t)kNeurons) * 2u;
+    s.bar_off  = s.a_off + tiles * a_bytes;
+    s.tmem_off = s.bar_off + 8u * (tiles + 1u);
+    s.total    = s.tmem_off + 16u;
+    return s;
+}
+
+cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32_t n, uint32_t n_in_dims,
+                         unsigned long long *counters, int num_sms, cudaStream_t stream);
+cudaError_t launch_trace_intervals(const NbvhConst &bc, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
+                                   uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt,
+                                   unsigned long long *counters, cudaStream_t stream);
+cudaError_t launch_blas_intersect(const BlasConst &b, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
+                                  float *u, float *v, uint32_t *prim, unsigned long long *counters, cudaStream_t stream);
+cudaError_t launch_raygen(const CameraConst &cam, uint32_t first, uint32_t n, int sample_idx, int sample_offset, float *o,
+                          float *d, cudaStream_t stream);
+cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream);
+cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
+cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);
+
+} // namespace nbvh

@@ -1,0 +1,273 @@
+"""Host-side mirror of the reference's module interface for the neural ray-query path.
+
+`NeuralPathModule` follows `ntwr::neural::path::NeuralPathModule : NeuralBVHModule`
+(/root/reference/include/cuda/neural/neural_bvh_module.h:144-241,
+ /root/reference/include/cuda/neural/path/path_module.h:256-345): same method names, argument meaning
+and error behaviour (the reference throws std::runtime_error; here `NbvhError`).  Every method is a thin
+call into the C ABI of libnbvh_b200.so -- PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import (CONST_CAMERA, CONST_MODULE, CONST_NETWORK, CONST_OPTIMIZER, CONST_PATH, CONST_PT_OUTPUT,
+                    CONST_RENDERER, CONST_SCENE, CONST_SCENE_BBOX, CONST_TYPES, COUNTER_NAMES)
+
+NODE_DTYPE = np.dtype([("mn", "<f4", 3), ("a", "<u4"), ("mx", "<f4", 3), ("b", "<u4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("valid_hit", "<u4"), ("normal_or_uv", "<f4", 3), ("albedo_or_ids", "<f4", 3)])
+
+
+class NbvhError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("nbvh_b200 error %s (%d): %s" % (_capi.ERR_NAMES.get(code, "?"), code, msg))
+        self.code = code
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class NeuralPathModule:
+    """One instance per process per device, like the reference (its __constant__ symbols are process-global)."""
+
+    def __init__(self, config=None, device=0):
+        self._lib = _capi.load_library()
+        self._h = C.c_void_p()
+        self.device = device
+        if isinstance(config, dict):
+            config = json.dumps(config)
+        cfg = config.encode() if isinstance(config, str) else config
+        rc = self._lib.nbvh_create(int(device), cfg, C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.nbvh_last_error(self._h).decode() if self._h else "no usable sm_100 CUDA device"
+            if self._h:
+                self._lib.nbvh_destroy(self._h)
+                self._h = C.c_void_p()
+            raise NbvhError(rc, msg)
+        self._keep = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise NbvhError(rc, self._lib.nbvh_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nbvh_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def name(self):
+        return "Path Tracing Module"
+
+    # ------------------------------------------------------------------ configuration
+    def load_config_from_json(self, config):
+        """== NeuralBVHRenderer::load_config_from_json (neural_bvh_renderer_init.cu:566-749)."""
+        if isinstance(config, dict):
+            config = json.dumps(config)
+        self._check(self._lib.nbvh_load_config_json(self._h, config.encode()))
+
+    def get_constants(self, which):
+        pod = CONST_TYPES[which]()
+        self._check(self._lib.nbvh_get_constants(self._h, which, C.byref(pod), C.sizeof(pod)))
+        return pod
+
+    def set_constants(self, which, pod):
+        self._check(self._lib.nbvh_set_constants(self._h, which, C.byref(pod), C.sizeof(pod)))
+
+    def setup_neural_module_constants(self, **blocks):
+        """== setup_neural_module_constants(): pushes constant blocks (keyword = block id name)."""
+        for which, pod in blocks.items():
+            self.set_constants(which, pod)
+
+    def set_camera(self, matrix16, yfov_rad):
+        m = (C.c_float * 16)(*[float(x) for x in matrix16])
+        self._check(self._lib.nbvh_set_camera(self._h, m, C.c_float(yfov_rad)))
+
+    @property
+    def max_depth(self):
+        return self._lib.nbvh_get_max_depth(self._h)
+
+    @max_depth.setter
+    def max_depth(self, v):
+        self._check(self._lib.nbvh_set_max_depth(self._h, int(v)))
+
+    def network_output_dims(self):
+        return self.get_constants(CONST_PT_OUTPUT).output_network_dims
+
+    # ------------------------------------------------------------------ scene / tree-cut / weights
+    def set_scene(self, tlas_nodes, tlas_indices, blas_list):
+        """Uploads a scene description (numpy arrays) and hands the device pointers over, standing in for
+        CudaBackend's buffers (cuda_backend.cpp:186-385).  blas_list: dicts with nodes, prim_ids, vertices,
+        indices (prim ids are widened to 64 bit: the reference stores size_t)."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+
+        def up(a, dtype):
+            a = np.ascontiguousarray(a)
+            return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
+
+        keep = []
+        t_nodes = up(np.ascontiguousarray(tlas_nodes, dtype=NODE_DTYPE), None)
+        t_idx = up(np.ascontiguousarray(tlas_indices, dtype=np.uint32), None)
+        keep += [t_nodes, t_idx]
+        descs = (_capi.CudaBlas * len(blas_list))()
+        for i, b in enumerate(blas_list):
+            nodes = up(np.ascontiguousarray(b["nodes"], dtype=NODE_DTYPE), None)
+            prim = up(np.ascontiguousarray(b["prim_ids"]).astype(np.uint64), None)
+            verts = up(np.ascontiguousarray(b["vertices"], dtype=np.float32), None)
+            idx = up(np.ascontiguousarray(b["indices"], dtype=np.uint32), None)
+            keep += [nodes, prim, verts, idx]
+            descs[i].num_nodes = len(b["nodes"])
+            descs[i].prim_indices = prim.data_ptr()
+            descs[i].num_prim_indices = len(b["prim_ids"])
+            descs[i].vertices = verts.data_ptr()
+            descs[i].indices = idx.data_ptr()
+            descs[i].nodes = nodes.data_ptr()
+        d_descs = torch.from_numpy(np.frombuffer(bytes(descs), dtype=np.uint8).copy()).to(dev)
+        keep.append(d_descs)
+        sd = _capi.SceneData()
+        sd.tlas_nodes = t_nodes.data_ptr()
+        sd.num_tlas_nodes = len(tlas_nodes)
+        sd.blas_indices = t_idx.data_ptr()
+        sd.mesh_bvhs = d_descs.data_ptr()
+        sd.num_meshes = len(blas_list)
+        self._check(self._lib.nbvh_set_scene(self._h, C.byref(sd)))
+        self._keep["scene"] = keep
+
+    def set_neural_bvh(self, nodes):
+        torch = _torch()
+        nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+        d = torch.from_numpy(nodes.view(np.uint8).reshape(-1).copy()).to(torch.device("cuda", self.device))
+        self._check(self._lib.nbvh_set_neural_bvh(self._h, _ptr(d), len(nodes)))
+
+    def load_neural_bvh(self, path):
+        """== NeuralBVHRenderer::load_neural_bvh (neural_bvh_renderer_accel.cpp:208-254)."""
+        self._check(self._lib.nbvh_load_neural_bvh_file(self._h, os.fsencode(path)))
+
+    def save_neural_bvh(self, path):
+        self._check(self._lib.nbvh_save_neural_bvh_file(self._h, os.fsencode(path)))
+
+    def neural_bvh_nodes(self):
+        n = self._lib.nbvh_neural_bvh_num_nodes(self._h)
+        out = np.zeros(n, dtype=NODE_DTYPE)
+        self._check(self._lib.nbvh_get_neural_bvh_host(self._h, out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def load_network_model(self, path):
+        """== NeuralBVHRenderer::load_network_model -> trainer->deserialize (neural_bvh_renderer_init.cu:394-404)."""
+        self._check(self._lib.nbvh_load_network_file(self._h, os.fsencode(path)))
+
+    def save_network_model(self, path):
+        self._check(self._lib.nbvh_save_network_file(self._h, os.fsencode(path)))
+
+    def n_params(self):
+        return int(self._lib.nbvh_n_params(self._h))
+
+    def load_params(self, fp16_bits):
+        a = np.ascontiguousarray(fp16_bits, dtype=np.uint16)
+        self._check(self._lib.nbvh_load_params_host(self._h, a.ctypes.data_as(C.c_void_p), a.size))
+
+    def get_params(self):
+        out = np.zeros(self.n_params(), dtype=np.uint16)
+        self._check(self._lib.nbvh_get_params_host(self._h, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    def init_params(self, seed=1337):
+        self._check(self._lib.nbvh_init_params(self._h, int(seed)))
+
+    # ------------------------------------------------------------------ inference
+    def reinitialise_inference_data(self, fb_size):
+        """== reinitialise_inference_data(fb_size): (re)allocates the frame buffers."""
+        self._check(self._lib.nbvh_set_framebuffer(self._h, None, None, int(fb_size[0]), int(fb_size[1])))
+
+    def attach_hit_buffer(self, n_pixels):
+        torch = _torch()
+        buf = torch.zeros(n_pixels * HIT_DTYPE.itemsize, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        self._check(self._lib.nbvh_set_hit_buffer(self._h, _ptr(buf)))
+        self._keep["hits"] = buf
+        return buf
+
+    def inference(self, inputs, outputs=None, stream=None):
+        """== network->inference(stream, in 9xN, out 8xN): torch CUDA tensors, row i = query i."""
+        torch = _torch()
+        n = inputs.shape[0]
+        if outputs is None:
+            outputs = torch.empty((n, self.network_output_dims()), dtype=torch.float32, device=inputs.device)
+        assert inputs.is_cuda and inputs.is_contiguous() and inputs.dtype == torch.float32
+        self._check(self._lib.nbvh_query(self._h, _ptr(inputs), _ptr(outputs), n, stream))
+        return outputs
+
+    def trace_intervals(self, o, d, max_intervals, stream=None):
+        torch = _torch()
+        n = o.shape[0]
+        dev = o.device
+        counts = torch.zeros(n, dtype=torch.int32, device=dev)
+        node = torch.zeros((n, max_intervals), dtype=torch.int32, device=dev)
+        mint = torch.zeros((n, max_intervals), dtype=torch.float32, device=dev)
+        maxt = torch.zeros((n, max_intervals), dtype=torch.float32, device=dev)
+        self._check(self._lib.nbvh_trace_intervals(self._h, _ptr(o), _ptr(d), n, max_intervals, _ptr(counts), _ptr(node),
+                                                   _ptr(mint), _ptr(maxt), stream))
+        return counts, node, mint, maxt
+
+    def blas_intersect(self, blas_idx, o, d, maxt=None, stream=None):
+        torch = _torch()
+        n = o.shape[0]
+        dev = o.device
+        t = torch.zeros(n, dtype=torch.float32, device=dev)
+        u = torch.zeros(n, dtype=torch.float32, device=dev)
+        v = torch.zeros(n, dtype=torch.float32, device=dev)
+        prim = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._check(self._lib.nbvh_blas_intersect(self._h, blas_idx, _ptr(o), _ptr(d), _ptr(maxt), n, _ptr(t), _ptr(u),
+                                                  _ptr(v), _ptr(prim), stream))
+        return t, u, v, prim
+
+    def raygen(self, first_pixel, n, sample_idx=0, sample_offset=0, stream=None):
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        o = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        d = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        self._check(self._lib.nbvh_raygen(self._h, first_pixel, n, sample_idx, sample_offset, _ptr(o), _ptr(d), stream))
+        return o, d
+
+    def neural_render(self, accumulated_spp, sample_offset, first_pixel=0, pixel_count=0, stream=None):
+        """== neural_render(accumulated_spp, sample_offset, neural_bvh) (path_module.cu:139-245)."""
+        self._check(self._lib.nbvh_render(self._h, int(accumulated_spp), int(sample_offset), int(first_pixel),
+                                          int(pixel_count), stream))
+
+    def neural_render_host(self, accumulated_spp, sample_offset, ldr_host=None, hits_host=None, camera=None):
+        """End-to-end call with HOST buffers (numpy arrays, ideally pinned)."""
+        cam = C.byref(camera) if camera is not None else None
+        lp = ldr_host.ctypes.data_as(C.c_void_p) if ldr_host is not None else None
+        hp = hits_host.ctypes.data_as(C.c_void_p) if hits_host is not None else None
+        self._check(self._lib.nbvh_render_host(self._h, int(accumulated_spp), int(sample_offset), cam, lp, hp))
+
+    # ------------------------------------------------------------------ counters / timing
+    def counters(self):
+        out = (C.c_uint64 * len(COUNTER_NAMES))()
+        self._check(self._lib.nbvh_get_counters(self._h, out, len(COUNTER_NAMES)))
+        return dict(zip(COUNTER_NAMES, [int(x) for x in out]))
+
+    def reset_counters(self):
+        self._check(self._lib.nbvh_reset_counters(self._h))
+
+    def enable_kernel_timing(self, on=True):
+        self._check(self._lib.nbvh_enable_kernel_timing(self._h, int(on)))
+
+    def kernel_time(self):
+        ms, n = C.c_float(0), C.c_uint32(0)
+        self._check(self._lib.nbvh_get_kernel_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,190 @@
+"""Harness-side scene loading: stands in for the reference's CudaBackend (scene upload) when driving the module.
+
+  * load_scene_arrays / load_chess_module: the Chess fixture written by tools/make_fixtures.py
+    (baseline/_ref/chess: BLAS/TLAS built by the reference's own ext/bvh settings, shipped config / .nbvh / weights)
+  * synthetic_scene: procedural scene + tree-cut + random weights of the shipped network shape, for boxes
+    without the fixture and for the synthetic configuration of BASELINE.json.
+"""
+import json
+import os
+
+import numpy as np
+
+from .module import NODE_DTYPE, NeuralPathModule
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHESS_BASE = "nodes_32940_hash_18_lvl_8_tsteps_10000"
+
+
+def chess_fixture_dir():
+    d = os.path.join(REPO, "baseline", "_ref", "chess")
+    return d if os.path.exists(os.path.join(d, "manifest.json")) else None
+
+
+def load_scene_arrays(root, with_neural_mesh=False):
+    man = json.load(open(os.path.join(root, "manifest.json")))
+    blas = []
+    for i, m in enumerate(man["meshes"]):
+        p = os.path.join(root, "mesh%d" % i)
+        if i == man["neural_mesh"] and not with_neural_mesh:
+            # placeholder BLAS: never traversed while ignore_neural_blas is false
+            blas.append(dict(nodes=np.zeros(1, NODE_DTYPE), prim_ids=np.zeros(1, np.uint32),
+                             vertices=np.zeros(9, np.float32), indices=np.zeros(3, np.uint32)))
+            continue
+        blas.append(dict(nodes=np.fromfile(p + "_bvh_nodes.bin", dtype=NODE_DTYPE),
+                         prim_ids=np.fromfile(p + "_prim_ids.u32", dtype="<u4"),
+                         vertices=np.fromfile(p + "_vertices.f32", dtype="<f4"),
+                         indices=np.fromfile(p + "_indices.u32", dtype="<u4")))
+    tlas_nodes = np.fromfile(os.path.join(root, "tlas_nodes.bin"), dtype=NODE_DTYPE)
+    tlas_idx = np.fromfile(os.path.join(root, "tlas_indices.u32"), dtype="<u4")
+    return tlas_nodes, tlas_idx, blas, man
+
+
+def load_chess_module(device=0, max_depth=1, envmap_eval=False, with_neural_mesh=False, root=None):
+    """Shipped Chess configuration: config JSON, .nbvh and network_models JSON load unchanged through the C ABI."""
+    root = root or chess_fixture_dir()
+    if root is None:
+        raise FileNotFoundError("Chess fixture missing (baseline/_ref/chess); run tools/make_fixtures.py")
+    cfg_text = open(os.path.join(root, CHESS_BASE + "_neural.json")).read()
+    mod = NeuralPathModule(cfg_text, device=device)
+    mod.load_neural_bvh(os.path.join(root, CHESS_BASE + ".nbvh"))
+    mod.load_network_model(os.path.join(root, CHESS_BASE + "_network.json"))
+    tlas_nodes, tlas_idx, blas, _ = load_scene_arrays(root, with_neural_mesh)
+    mod.set_scene(tlas_nodes, tlas_idx, blas)
+    mod.max_depth = max_depth
+    from ._capi import CONST_SCENE
+    sc = mod.get_constants(CONST_SCENE)
+    sc.envmap_eval = envmap_eval
+    mod.set_constants(CONST_SCENE, sc)
+    return mod
+
+
+# ------------------------------------------------------------------------------------------------ synthetic
+def _build_median_bvh(centers, bmin, bmax, leaf_size):
+    """Simple median-split BVH2 in the reference's 32-byte node layout (children adjacent: left, left+1)."""
+    n = centers.shape[0]
+    order = np.arange(n, dtype=np.uint32)
+    nodes = [None]
+    prim_ids = []
+
+    def bounds(ids):
+        return bmin[ids].min(axis=0), bmax[ids].max(axis=0)
+
+    stack = [(0, order)]
+    while stack:
+        ni, ids = stack.pop()
+        lo, hi = bounds(ids)
+        if len(ids) <= leaf_size:
+            nodes[ni] = (lo, len(ids), hi, len(prim_ids))
+            prim_ids.extend(ids.tolist())
+            continue
+        axis = int(np.argmax(hi - lo))
+        srt = ids[np.argsort(centers[ids, axis], kind="stable")]
+        half = len(srt) // 2
+        left = len(nodes)
+        nodes.append(None)
+        nodes.append(None)
+        nodes[ni] = (lo, 0, hi, left)
+        stack.append((left, srt[:half]))
+        stack.append((left + 1, srt[half:]))
+    out = np.zeros(len(nodes), dtype=NODE_DTYPE)
+    for i, (lo, a, hi, b) in enumerate(nodes):
+        out[i] = (lo, a, hi, b)
+    return out, np.asarray(prim_ids, dtype=np.uint32)
+
+
+def synthetic_scene(seed=1234, n_spheres=24, subdiv=12, cut_depth=9, fb=(256, 192), log2_hashmap=14):
+    """Procedural stand-in: jittered lattice of tessellated spheres (neural mesh, used only to derive the tree-cut),
+    a ground quad grid as the classical BLAS, a fixed-depth N-BVH cut and the shipped network shape.
+    Returns (config dict, nbvh nodes, tlas_nodes, tlas_indices, blas_list)."""
+    rng = np.random.default_rng(seed)
+    # neural mesh: spheres
+    verts, tris = [], []
+    for s in range(n_spheres):
+        c = rng.uniform(-0.4, 0.4, 3) * np.array([1.0, 0.3, 1.0]) + np.array([0, 0.25, 0])
+        r = rng.uniform(0.03, 0.08)
+        base = len(verts)
+        for i in range(subdiv + 1):
+            th = np.pi * i / subdiv
+            for j in range(2 * subdiv):
+                ph = np.pi * j / subdiv
+                verts.append(c + r * np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)]))
+        w = 2 * subdiv
+        for i in range(subdiv):
+            for j in range(w):
+                a = base + i * w + j
+                b = base + i * w + (j + 1) % w
+                tris.append((a, b, a + w))
+                tris.append((b, b + w, a + w))
+    verts = np.asarray(verts, dtype=np.float32)
+    tris = np.asarray(tris, dtype=np.uint32)
+    tv = verts[tris]
+    n_nodes, n_prims = _build_median_bvh(tv.mean(axis=1), tv.min(axis=1), tv.max(axis=1), 2)
+    # tree-cut at fixed depth: traverse_and_build_neural_bvh (neural_bvh_renderer_accel.cpp:24-74)
+    cut = [None]
+    work = [(0, 0, 0)]
+    while work:
+        bi, ci, depth = work.pop()
+        nd = n_nodes[bi]
+        if nd["a"] > 0 or depth == cut_depth:
+            cut[ci] = (nd["mn"], 1 if nd["a"] > 0 else 8, nd["mx"], 0xFFFFFFFF)
+            continue
+        left = len(cut)
+        cut.append(None)
+        cut.append(None)
+        cut[ci] = (nd["mn"], 0, nd["mx"], left)
+        work.append((int(nd["b"]), left, depth + 1))
+        work.append((int(nd["b"]) + 1, left + 1, depth + 1))
+    nbvh = np.zeros(len(cut), dtype=NODE_DTYPE)
+    for i, c in enumerate(cut):
+        nbvh[i] = c
+    # classical BLAS: ground grid
+    g = 24
+    gx, gz = np.meshgrid(np.linspace(-0.6, 0.6, g + 1), np.linspace(-0.6, 0.6, g + 1))
+    gverts = np.stack([gx.ravel(), 0.02 * np.sin(7 * gx.ravel()) * np.cos(5 * gz.ravel()), gz.ravel()], axis=1).astype(np.float32)
+    gtris = []
+    for i in range(g):
+        for j in range(g):
+            a = i * (g + 1) + j
+            gtris.append((a, a + 1, a + g + 1))
+            gtris.append((a + 1, a + g + 2, a + g + 1))
+    gtris = np.asarray(gtris, dtype=np.uint32)
+    gv = gverts[gtris]
+    gmin, gmax = gv.min(axis=1), gv.max(axis=1)
+    flat = (gmax - gmin) <= 1e-4
+    gmin = gmin - flat * 5e-5
+    gmax = gmax + flat * 5e-5
+    g_nodes, g_prims = _build_median_bvh(gv.mean(axis=1), gmin, gmax, 2)
+    blas = [dict(nodes=n_nodes, prim_ids=n_prims, vertices=verts.ravel(), indices=tris.ravel()),
+            dict(nodes=g_nodes, prim_ids=g_prims, vertices=gverts.ravel(), indices=gtris.ravel())]
+    # TLAS: root + 2 leaves (neural first)
+    tlas = np.zeros(3, dtype=NODE_DTYPE)
+    tlas[0] = (np.minimum(n_nodes[0]["mn"], g_nodes[0]["mn"]), 1, np.maximum(n_nodes[0]["mx"], g_nodes[0]["mx"]), 0)
+    tlas[1] = (n_nodes[0]["mn"], 0, n_nodes[0]["mx"], 2)
+    tlas[2] = (g_nodes[0]["mn"], 1, g_nodes[0]["mx"], 1)
+    tlas_idx = np.array([0, 1], dtype=np.uint32)
+    # camera looking at the origin from above
+    eye = np.array([0.9, 0.7, 0.8], dtype=np.float64)
+    fwd = -eye / np.linalg.norm(eye)
+    right = np.cross(fwd, [0, 1, 0])
+    right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    view = np.eye(4)
+    view[0, :3], view[1, :3], view[2, :3] = right, up, -fwd
+    view[:3, 3] = -view[:3, :3] @ eye
+    cfg = {
+        "cuda_scene": {"fb_size": list(fb), "camera": {"yfov": 0.7, "matrix": [float(x) for x in view.T.ravel()]},
+                       "scene_constants": {"envmap_eval": False, "ema_accumulate": False}},
+        "neural_bvh_renderer": {
+            "neural_module": {
+                "max_depth": 1,
+                "pt_output_constants": {"output_albedo_dim": 3, "output_depth_dim": 1, "output_network_dims": 8,
+                                        "output_normal_dim": 3, "output_visibility_dim": 1},
+                "bvh_module_constants": {"input_network_dims": 9, "input_segment_points": 3,
+                                         "input_segment_points_dim": 9, "segment_distribution": "EquidistantExterior"},
+                "segment_encoding": {"type": "HashGrid", "hashgrid_options": {"log2_hashmap_size": log2_hashmap}},
+            },
+            "bvh_constants": {"rendered_lod": 0, "current_learned_lod": 6},
+        },
+    }
+    return cfg, nbvh, tlas, tlas_idx, blas

@@ -1,0 +1,880 @@
+/*
+ * nbvh_oracle.c -- TEST INFRASTRUCTURE ONLY (see nbvh_oracle.h for the rules and the parity status).
+ *
+ * Scalar CPU restatement of the reference's neural ray-query path.  Compile with
+ *   gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC
+ * so that the only fused multiply-adds are the explicit fmaf()/fma() calls below, each of which
+ * mirrors an fma.rn the reference's own kernels contain when built by nvcc 12.9 for sm_100
+ * (PTX of src/cuda/neural/path/path_inference_kernels.cu and src/cuda/neural/neural_bvh_module_kernels.cu).
+ * All file:line citations are into /root/reference.
+ */
+#include "nbvh_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NEURAL_STACK_SIZE 24 /* include/cuda/neural/accel/neural_bvh.cuh:22 */
+#define TLAS_STACK_SIZE 10   /* include/cuda/accel/tlas.cuh:16 */
+#define BLAS_STACK_SIZE 32   /* include/cuda/accel/bvh2.cuh:24 */
+
+/* glm::min / glm::max operand order (ext/glm/glm/detail/func_common.inl:17-30) */
+static inline float gmin(float x, float y) { return (y < x) ? y : x; }
+static inline float gmax(float x, float y) { return (x < y) ? y : x; }
+
+/* ------------------------------------------------------------------ fp16 */
+float onbvh_h2f(uint16_t h)
+{
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp  = (h >> 10) & 0x1Fu;
+    uint32_t man  = h & 0x3FFu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { /* subnormal */
+            int e = -1;
+            do {
+                man <<= 1;
+                e++;
+            } while (!(man & 0x400u));
+            man &= 0x3FFu;
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | (man << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7F800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+/* double -> half, round to nearest even (one rounding) */
+static uint16_t d2h(double d)
+{
+    uint16_t sign = 0;
+    if (d != d)
+        return 0x7FFF;
+    if (signbit(d)) {
+        sign = 0x8000u;
+        d    = -d;
+    }
+    if (d == 0.0)
+        return sign;
+    if (d >= 65520.0) /* rounds to inf */
+        return sign | 0x7C00u;
+    int e;
+    double m = frexp(d, &e); /* d = m * 2^e, m in [0.5,1) */
+    /* half normal range: 2^-14 .. ; unit in last place is 2^(E-10) with E = e-1 */
+    int E = e - 1;
+    if (E < -14)
+        E = -14; /* subnormal: fixed ulp 2^-24 */
+    double scaled = ldexp(d, 10 - E); /* value in units of ulp */
+    double r      = nearbyint(scaled); /* default rounding mode = RNE */
+    uint32_t q    = (uint32_t)r;
+    (void)m;
+    if (E == -14 && q < 1024u)
+        return sign | (uint16_t)q; /* subnormal or zero */
+    if (q == 2048u) {               /* mantissa overflow */
+        q = 1024u;
+        E++;
+    }
+    if (E > 15)
+        return sign | 0x7C00u;
+    return sign | (uint16_t)(((uint32_t)(E + 15) << 10) | (q - 1024u));
+}
+
+uint16_t onbvh_f2h(float f) { return d2h((double)f); }
+
+/* __hfma: one rounding of a*b+c to half (tcnn vec.h:210-212,370) */
+static inline uint16_t hfma(uint16_t a, uint16_t b, uint16_t c)
+{
+    return d2h((double)onbvh_h2f(a) * (double)onbvh_h2f(b) + (double)onbvh_h2f(c));
+}
+
+/* ------------------------------------------------------------------ RNG (include/cuda/utils/lcg_rng.cuh:12-72) */
+static uint32_t murmur_mix(uint32_t hash, uint32_t k)
+{
+    k *= 0xcc9e2d51u;
+    k = (k << 15) | (k >> 17);
+    k *= 0x1b873593u;
+    hash ^= k;
+    hash = ((hash << 13) | (hash >> 19)) * 5u + 0xe6546b64u;
+    return hash;
+}
+
+uint32_t onbvh_lcg_rng_init(uint32_t index, uint32_t frame, uint32_t linear)
+{
+    uint32_t h = murmur_mix(0u, linear);
+    h          = murmur_mix(h, 512u * frame + index);
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+float onbvh_lcg_randomf(uint32_t *state)
+{
+    *state = *state * 1664525u + 1013904223u;
+    /* ldexp((float)u, -32): cvt.rn.f32.u32 then an exact scale by 2^-32 (can return 1.0f) */
+    return (float)(*state) * 0x1p-32f;
+}
+
+/* ------------------------------------------------------------------ camera */
+/* glm::inverse(mat4) cofactor formulation (ext/glm/glm/detail/func_matrix.inl compute_inverse<4,4>),
+ * host code: no contraction.  m is column-major m[col][row]. */
+static void mat4_inverse(const float a[16], float out[16])
+{
+#define M(c, r) a[(c)*4 + (r)]
+    float c00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+    float c02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+    float c03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+    float c04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+    float c06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3);
+    float c07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+    float c08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+    float c10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+    float c11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+    float c12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+    float c14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3);
+    float c15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+    float c16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+    float c18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+    float c19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+    float c20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+    float c22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1);
+    float c23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+    float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    float v0[4] = {M(1, 0), M(0, 0), M(0, 0), M(0, 0)}, v1[4] = {M(1, 1), M(0, 1), M(0, 1), M(0, 1)};
+    float v2[4] = {M(1, 2), M(0, 2), M(0, 2), M(0, 2)}, v3[4] = {M(1, 3), M(0, 3), M(0, 3), M(0, 3)};
+    float sa[4] = {1.f, -1.f, 1.f, -1.f}, sb[4] = {-1.f, 1.f, -1.f, 1.f};
+    float inv[16];
+    for (int i = 0; i < 4; i++) {
+        float i0 = v1[i] * f0[i] - v2[i] * f1[i] + v3[i] * f2[i];
+        float i1 = v0[i] * f0[i] - v2[i] * f3[i] + v3[i] * f4[i];
+        float i2 = v0[i] * f1[i] - v1[i] * f3[i] + v3[i] * f5[i];
+        float i3 = v0[i] * f2[i] - v1[i] * f4[i] + v2[i] * f5[i];
+        inv[0 * 4 + i] = i0 * sa[i];
+        inv[1 * 4 + i] = i1 * sb[i];
+        inv[2 * 4 + i] = i2 * sa[i];
+        inv[3 * 4 + i] = i3 * sb[i];
+    }
+    float d0 = M(0, 0) * inv[0], d1 = M(0, 1) * inv[4], d2 = M(0, 2) * inv[8], d3 = M(0, 3) * inv[12];
+    float det = (d0 + d1) + (d2 + d3);
+    float ood = 1.f / det;
+    for (int i = 0; i < 16; i++)
+        out[i] = inv[i] * ood;
+#undef M
+}
+
+static void host_normalize(const float v[3], float out[3])
+{
+    /* glm::normalize = v * inversesqrt(dot(v,v)), inversesqrt = 1/sqrt (host: no fma) */
+    float dot = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    float inv = 1.f / sqrtf(dot);
+    out[0] = v[0] * inv, out[1] = v[1] * inv, out[2] = v[2] * inv;
+}
+
+static void host_cross(const float x[3], const float y[3], float out[3])
+{
+    out[0] = x[1] * y[2] - y[1] * x[2];
+    out[1] = x[2] * y[0] - y[2] * x[0];
+    out[2] = x[0] * y[1] - y[0] * x[1];
+}
+
+/* src/base/camera/camera.cpp:39-82 + src/cuda/cuda_backend.cpp:595-611 */
+void onbvh_camera_params(const float matrix[16], float yfov_rad, uint32_t w, uint32_t h, float origin[3], float du[3],
+                         float dv[3], float top_left[3])
+{
+    float inv[16];
+    mat4_inverse(matrix, inv);
+    /* inv * (0,0,0,1), inv*(0,0,-1,0), inv*(0,1,0,0): glm mat*vec = (c0*x + c1*y) + (c2*z + c3*w) */
+    float dir_raw[3], up_raw[3], dir[3], up[3];
+    for (int r = 0; r < 3; r++) {
+        origin[r]  = (inv[0 + r] * 0.f + inv[4 + r] * 0.f) + (inv[8 + r] * 0.f + inv[12 + r] * 1.f);
+        dir_raw[r] = (inv[0 + r] * 0.f + inv[4 + r] * 0.f) + (inv[8 + r] * -1.f + inv[12 + r] * 0.f);
+        up_raw[r]  = (inv[0 + r] * 0.f + inv[4 + r] * 1.f) + (inv[8 + r] * 0.f + inv[12 + r] * 0.f);
+    }
+    host_normalize(dir_raw, dir);
+    host_normalize(up_raw, up);
+    /* set_fovy_from_radian stores degrees (glm::degrees = x * 57.29577951308232), update_camera goes back */
+    float fovy_deg = yfov_rad * 57.295779513082320876798154814105f;
+    float half_rad = (0.5f * fovy_deg) * 0.01745329251994329576923690768489f;
+    float plane_y  = 2.f * tanf(half_rad);
+    float aspect   = (float)w / (float)h;
+    float plane_x  = plane_y * aspect;
+    float c1[3], c1n[3], c2[3], c2n[3];
+    host_cross(dir, up, c1);
+    host_normalize(c1, c1n);
+    for (int i = 0; i < 3; i++)
+        du[i] = c1n[i] * plane_x;
+    host_cross(du, dir, c2);
+    host_normalize(c2, c2n);
+    for (int i = 0; i < 3; i++)
+        dv[i] = -c2n[i] * plane_y;
+    for (int i = 0; i < 3; i++)
+        top_left[i] = dir[i] - 0.5f * du[i] - 0.5f * dv[i];
+}
+
+/* a6: neural_bvh_module_common.cuh:440-446 + neural_bvh_renderer_kernels.cuh:74-79.
+ * PTX: dir = fma(xf,du, yf*dv) + top_left;  len2 = fma(z,z, fma(x,x, y*y));  d = dir * rcp(sqrt(len2)) */
+void onbvh_raygen(const oconst_t *c, uint32_t pixel, int sample_idx, int rnd_offset, float o[3], float d[3],
+                  uint32_t *rng_state)
+{
+    uint32_t px = pixel % c->fb_w, py = pixel / c->fb_w;
+    uint32_t rng = onbvh_lcg_rng_init((uint32_t)sample_idx, (uint32_t)rnd_offset, pixel);
+    float r0     = onbvh_lcg_randomf(&rng);
+    float xf     = (r0 + (float)px) / (float)c->fb_w;
+    float r1     = onbvh_lcg_randomf(&rng);
+    float yf     = (r1 + (float)py) / (float)c->fb_h;
+    float v[3];
+    for (int i = 0; i < 3; i++)
+        v[i] = fmaf(xf, c->cam_du[i], yf * c->cam_dv[i]) + c->cam_top_left[i];
+    float len2 = fmaf(v[2], v[2], fmaf(v[0], v[0], v[1] * v[1]));
+    float inv  = 1.f / sqrtf(len2);
+    for (int i = 0; i < 3; i++) {
+        d[i] = v[i] * inv;
+        o[i] = c->cam_origin[i];
+    }
+    if (rng_state)
+        *rng_state = rng;
+}
+
+/* ------------------------------------------------------------------ slab test (a1) */
+/* include/cuda/base/ray.cuh:116-132, include/base/accel/bvh.h:123-154 */
+int onbvh_slab(const float mn[3], const float mx[3], const float o[3], const float d[3], float ray_mint,
+               float ray_maxt, int check, float *mint, float *maxt)
+{
+    float sm[3], bg[3];
+    for (int i = 0; i < 3; i++) {
+        float t0 = (mn[i] - o[i]) / d[i];
+        float t1 = (mx[i] - o[i]) / d[i];
+        sm[i]    = gmin(t0, t1);
+        bg[i]    = gmax(t0, t1);
+    }
+    float cmax = gmax(gmax(sm[0], sm[1]), sm[2]);
+    float cmin = gmin(gmin(bg[0], bg[1]), bg[2]);
+    *mint      = check ? gmax(ray_mint, cmax) : cmax;
+    *maxt      = check ? gmin(ray_maxt, cmin) : cmin;
+    return *mint <= *maxt;
+}
+
+/* dilated box about the centre (neural_bvh2.cuh:85-91,105-112; bvh.h:223-232) */
+static void dilate(const onode_t *n, float dilation, float mn[3], float mx[3])
+{
+    const float scale = 1.f + dilation;
+    for (int i = 0; i < 3; i++) {
+        float ext    = n->mx[i] - n->mn[i];
+        float center = n->mn[i] + ext * 0.5f;
+        float e2     = ext * scale;
+        mn[i]        = center - e2 * 0.5f;
+        mx[i]        = center + e2 * 0.5f;
+    }
+}
+
+static int node_primitive_min_max(const onode_t *n, const float o[3], const float d[3], float ray_mint,
+                                  float ray_maxt, int check, float dilation, float *mint, float *maxt)
+{
+    if (dilation != 0.f) {
+        float mn[3], mx[3];
+        dilate(n, dilation, mn, mx);
+        return onbvh_slab(mn, mx, o, d, ray_mint, ray_maxt, check, mint, maxt);
+    }
+    return onbvh_slab(n->mn, n->mx, o, d, ray_mint, ray_maxt, check, mint, maxt);
+}
+
+/* ------------------------------------------------------------------ N-BVH walk (a2, a3) */
+/* include/cuda/neural/accel/neural_bvh2.cuh:170-292.  LoD predicates :119-149. */
+int onbvh_neural_intersect(const onode_t *nodes, const oconst_t *c, uint32_t lod, const float o[3],
+                           const float d[3], uint32_t *stack, int *stack_size, int inference, float current_maxt,
+                           float dilation, float *out_mint, float *out_maxt, uint32_t *out_node,
+                           uint64_t *interior_steps)
+{
+    const float ray_mint = -FLT_MAX, ray_maxt = current_maxt;
+    const uint32_t leaf_lod = 2u + lod; /* LEAF_LOD(lod) = HIGHEST_BVH_LOD + lod */
+    uint32_t node_idx       = stack[--(*stack_size)];
+    for (;;) {
+        const onode_t *node = &nodes[node_idx];
+        const int is_leaf   = (node->a > 0u && node->a <= leaf_lod);
+        if (is_leaf || node->b == 0xFFFFFFFFu) {
+            float mint, maxt;
+            if (node_primitive_min_max(node, o, d, ray_mint, ray_maxt, 0, dilation, &mint, &maxt)) {
+                float maxt_eps = inference ? c->inference_maxt_epsilon : c->learning_maxt_epsilon;
+                float mint_eps = inference ? c->inference_mint_epsilon : c->learning_mint_epsilon;
+                int valid      = mint < ray_maxt;
+                if (mint < 0.f)
+                    valid &= maxt > maxt_eps;
+                else
+                    valid &= mint > mint_eps;
+                if (valid) {
+                    *out_mint = mint;
+                    *out_maxt = maxt;
+                    if (out_node)
+                        *out_node = node_idx;
+                    return 1;
+                }
+            }
+            if (*stack_size == 0)
+                return 0;
+            node_idx = stack[--(*stack_size)];
+            continue;
+        }
+        if (interior_steps)
+            (*interior_steps)++;
+        uint32_t c1 = node->b, c2 = node->b + 1u;
+        float m1, m2, tmp;
+        /* intersect_traversal_bbox: check_ray_bounds = true, returns mint or FLT_MAX */
+        m1 = node_primitive_min_max(&nodes[c1], o, d, ray_mint, ray_maxt, 1, dilation, &m1, &tmp) ? m1 : FLT_MAX;
+        m2 = node_primitive_min_max(&nodes[c2], o, d, ray_mint, ray_maxt, 1, dilation, &m2, &tmp) ? m2 : FLT_MAX;
+        if (m1 > m2) {
+            float t = m1;
+            m1      = m2;
+            m2      = t;
+            uint32_t ti = c1;
+            c1          = c2;
+            c2          = ti;
+        }
+        if (m1 == FLT_MAX) {
+            if (*stack_size == 0)
+                return 0;
+            node_idx = stack[--(*stack_size)];
+        } else {
+            node_idx = c1;
+            if (m2 != FLT_MAX) {
+                stack[(*stack_size)++] = c2;
+                if (*stack_size >= NEURAL_STACK_SIZE)
+                    return 0; /* "Out of bound stack!" -> ray dropped */
+            }
+        }
+    }
+}
+
+void onbvh_trace_intervals(const onode_t *nodes, const oconst_t *c, uint32_t n_rays, const float *o, const float *d,
+                           uint32_t max_intervals, uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt,
+                           uint64_t *interior_steps)
+{
+    uint64_t steps = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : steps)
+    for (int64_t r = 0; r < (int64_t)n_rays; r++) {
+        uint32_t stack[NEURAL_STACK_SIZE];
+        int ss   = 1;
+        stack[0] = 0;
+        uint32_t n = 0;
+        uint64_t local = 0;
+        while (ss > 0) {
+            float a, b;
+            uint32_t ni = 0;
+            if (!onbvh_neural_intersect(nodes, c, c->rendered_lod, o + 3 * r, d + 3 * r, stack, &ss, 1, FLT_MAX,
+                                        c->fixed_node_dilation, &a, &b, &ni, &local))
+                break;
+            if (n < max_intervals) {
+                node_idx[(size_t)r * max_intervals + n] = ni;
+                mint[(size_t)r * max_intervals + n]     = a;
+                maxt[(size_t)r * max_intervals + n]     = b;
+            }
+            n++;
+        }
+        counts[r] = n;
+        steps += local;
+    }
+    if (interior_steps)
+        *interior_steps = steps;
+}
+
+/* ------------------------------------------------------------------ BVH2 closest hit (a14) */
+/* include/base/accel/bvh.h:123-137 (BVH2Node::intersect, honours ray bounds) */
+static float node_intersect(const onode_t *n, const float o[3], const float d[3], float ray_mint, float ray_maxt)
+{
+    float mint, maxt;
+    return onbvh_slab(n->mn, n->mx, o, d, ray_mint, ray_maxt, 1, &mint, &maxt) ? mint : FLT_MAX;
+}
+
+/* include/cuda/accel/bvh.cuh:98-136.  PTX: cross = mul,mul,sub (not fused);
+ * dot(a,b) = fma(a.z,b.z, fma(a.x,b.x, a.y*b.y)); inv_det = rcp.rn(det). */
+static inline float dot_ptx(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[0], b[0], a[1] * b[1])); }
+static inline void cross_ptx(const float x[3], const float y[3], float out[3])
+{
+    out[0] = x[1] * y[2] - y[1] * x[2];
+    out[1] = x[2] * y[0] - y[2] * x[0];
+    out[2] = x[0] * y[1] - y[0] * x[1];
+}
+
+static float tri_intersect(const oblas_t *b, uint32_t prim, const float o[3], const float d[3], float ray_mint,
+                           float ray_maxt, float *u_out, float *v_out)
+{
+    const uint32_t *id = b->indices + 3 * (size_t)prim;
+    const float *v0 = b->vertices + 3 * (size_t)id[0], *v1 = b->vertices + 3 * (size_t)id[1],
+                *v2 = b->vertices + 3 * (size_t)id[2];
+    float e1[3], e2[3], pvec[3], tvec[3], qvec[3];
+    for (int i = 0; i < 3; i++) {
+        e1[i] = v1[i] - v0[i];
+        e2[i] = v2[i] - v0[i];
+    }
+    cross_ptx(d, e2, pvec);
+    float det = dot_ptx(e1, pvec);
+    if (det > -1e-8f && det < 1e-8f)
+        return FLT_MAX;
+    float inv_det = 1.f / det;
+    for (int i = 0; i < 3; i++)
+        tvec[i] = o[i] - v0[i];
+    float u = dot_ptx(tvec, pvec) * inv_det;
+    if (u < 0.f || u > 1.f)
+        return FLT_MAX;
+    cross_ptx(tvec, e1, qvec);
+    /* dot(ray.d, qvec) and dot(e2, qvec): PTX multiplies the .y pair first, then fuses .x and .z */
+    float v = fmaf(qvec[2], d[2], fmaf(qvec[0], d[0], qvec[1] * d[1])) * inv_det;
+    if (v < 0.f || (u + v) > 1.f)
+        return FLT_MAX;
+    float t = fmaf(qvec[2], e2[2], fmaf(e2[0], qvec[0], qvec[1] * e2[1])) * inv_det;
+    if (t < ray_mint || t >= ray_maxt)
+        return FLT_MAX;
+    *u_out = u;
+    *v_out = v;
+    return t;
+}
+
+/* include/cuda/accel/bvh2.cuh:13-88 */
+float onbvh_blas_intersect(const oblas_t *blas, const float o[3], const float d[3], float ray_mint, float ray_maxt,
+                           float *u, float *v, uint32_t *prim_idx, uint64_t *interior_steps, uint64_t *tri_tests)
+{
+    uint32_t stack[BLAS_STACK_SIZE];
+    int ss        = 0;
+    uint32_t ni   = 0;
+    float best_t  = FLT_MAX;
+    for (;;) {
+        const onode_t *node = &blas->nodes[ni];
+        if (node->a > 0u) {
+            for (uint32_t p = node->b; p < node->b + node->a; p++) {
+                uint32_t prim = blas->prim_ids[p];
+                float uu = 0.f, vv = 0.f;
+                if (tri_tests)
+                    (*tri_tests)++;
+                float t = tri_intersect(blas, prim, o, d, ray_mint, ray_maxt, &uu, &vv);
+                if (t < ray_maxt) {
+                    best_t   = t;
+                    *u       = uu;
+                    *v       = vv;
+                    *prim_idx = prim;
+                    ray_maxt = t;
+                }
+            }
+            if (ss == 0)
+                return best_t;
+            ni = stack[--ss];
+            continue;
+        }
+        if (interior_steps)
+            (*interior_steps)++;
+        uint32_t c1 = node->b, c2 = node->b + 1u;
+        float m1 = node_intersect(&blas->nodes[c1], o, d, ray_mint, ray_maxt);
+        float m2 = node_intersect(&blas->nodes[c2], o, d, ray_mint, ray_maxt);
+        if (m1 > m2) {
+            float t = m1;
+            m1      = m2;
+            m2      = t;
+            uint32_t ti = c1;
+            c1          = c2;
+            c2          = ti;
+        }
+        if (m1 == FLT_MAX) {
+            if (ss == 0)
+                return best_t;
+            ni = stack[--ss];
+        } else {
+            ni = c1;
+            if (m2 != FLT_MAX)
+                stack[ss++] = c2;
+        }
+    }
+}
+
+void onbvh_blas_intersect_batch(const oblas_t *blas, uint32_t n, const float *o, const float *d, const float *maxt,
+                                float *t, float *u, float *v, uint32_t *prim, uint64_t *counters)
+{
+    uint64_t steps = 0, tests = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : steps, tests)
+    for (int64_t r = 0; r < (int64_t)n; r++) {
+        uint64_t a = 0, b = 0;
+        float uu = 0.f, vv = 0.f;
+        uint32_t pp = 0xFFFFFFFFu;
+        t[r]    = onbvh_blas_intersect(blas, o + 3 * r, d + 3 * r, 1e-4f, maxt ? maxt[r] : FLT_MAX, &uu, &vv, &pp, &a, &b);
+        u[r]    = uu;
+        v[r]    = vv;
+        prim[r] = pp;
+        steps += a;
+        tests += b;
+    }
+    if (counters) {
+        counters[0] = steps;
+        counters[1] = tests;
+    }
+}
+
+/* ------------------------------------------------------------------ TLAS (a4) */
+/* include/cuda/accel/tlas.cuh:220-325 (local stack variant); the ray keeps [1e-4, FLT_MAX]. */
+int onbvh_tlas_intersect_only(const oscene_t *s, const float o[3], const float d[3], uint32_t *stack,
+                              int *stack_size, uint32_t *blas_idx, int *is_neural)
+{
+    *is_neural  = 0;
+    uint32_t ni = stack[--(*stack_size)];
+    for (;;) {
+        const onode_t *node = &s->tlas_nodes[ni];
+        if (node->b >= 1u) { /* leaf_type >= TLAS_LEAF */
+            if (s->n_blas == 1 && node_intersect(node, o, d, 1e-4f, FLT_MAX) == FLT_MAX)
+                return 0;
+            *is_neural = node->b == 2u;
+            *blas_idx  = s->blas_indices[node->a];
+            return 1;
+        }
+        uint32_t c1 = node->a, c2 = node->a + 1u;
+        float m1 = node_intersect(&s->tlas_nodes[c1], o, d, 1e-4f, FLT_MAX);
+        float m2 = node_intersect(&s->tlas_nodes[c2], o, d, 1e-4f, FLT_MAX);
+        if (m1 > m2) {
+            float t = m1;
+            m1      = m2;
+            m2      = t;
+            uint32_t ti = c1;
+            c1          = c2;
+            c2          = ti;
+        }
+        if (m1 == FLT_MAX) {
+            if (*stack_size == 0)
+                return 0;
+            ni = stack[--(*stack_size)];
+        } else {
+            ni = c1;
+            if (m2 != FLT_MAX) {
+                stack[(*stack_size)++] = c2;
+                if (*stack_size >= TLAS_STACK_SIZE)
+                    return 0;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ segment encoding (a8) */
+/* src/cuda/neural/neural_bvh_module_kernels.cu:10-97,266-303.
+ * PTX: world = fma(t, d, o); dilation = (extent_dil + 1) + fixed_dil; centre = (max+min)*0.5;
+ *      enc = (world - centre) / (dilation*(max-min)) + 0.5; p = fma(enc_i, s, enc_o*(1-s)),
+ *      s = rcp(float(n-1)) * (float(k) + offset). */
+void onbvh_encode_segment(const oconst_t *c, const float o[3], const float d[3], float mint, float maxt, float *out)
+{
+    if (mint < 0.f) {
+        float t = mint;
+        mint    = maxt;
+        maxt    = t;
+    }
+    const float dilation = (c->node_extent_dilation + 1.f) + c->fixed_node_dilation;
+    float eo[3], ei[3];
+    for (int i = 0; i < 3; i++) {
+        float wo     = fmaf(mint, d[i], o[i]);
+        float wi     = fmaf(maxt, d[i], o[i]);
+        float extent = dilation * (c->bbox_max[i] - c->bbox_min[i]);
+        float center = (c->bbox_max[i] + c->bbox_min[i]) * 0.5f;
+        eo[i]        = (wo - center) / extent + 0.5f;
+        ei[i]        = (wi - center) / extent + 0.5f;
+    }
+    const uint32_t n = c->n_segment_points;
+    float delta, offset;
+    if (c->segment_distribution == 1u) { /* EquidistantExterior */
+        delta  = (n == 1u) ? 1.f : 1.f / (float)(n - 1u);
+        offset = 0.f;
+    } else { /* EquidistantInterior */
+        delta  = 1.f / (float)n;
+        offset = 0.5f;
+    }
+    for (uint32_t k = 0; k < n; k++) {
+        float s = delta * ((float)k + offset);
+        for (int i = 0; i < 3; i++)
+            out[3 * k + i] = fmaf(ei[i], s, eo[i] * (1.0f - s));
+    }
+}
+
+/* ------------------------------------------------------------------ hash grid (a9) */
+/* ext/tiny-cuda-nn/include/tiny-cuda-nn/common_device.h:709-718 */
+static float grid_scale(uint32_t level, float log2_pls, uint32_t base_res)
+{
+    return exp2f((float)level * log2_pls) * (float)base_res - 1.0f;
+}
+static uint32_t grid_resolution(float scale) { return (uint32_t)ceilf(scale) + 1u; }
+
+/* ext/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:692-723 */
+uint64_t onbvh_grid_n_params(const onet_t *net, uint32_t *offsets)
+{
+    uint32_t offset = 0;
+    const float l2  = log2f(net->per_level_scale);
+    for (uint32_t l = 0; l < net->n_levels; l++) {
+        uint32_t res       = grid_resolution(grid_scale(l, l2, net->base_resolution));
+        uint32_t max_p     = 0xFFFFFFFFu / 2u;
+        uint32_t in_level  = powf((float)res, 3.f) > (float)max_p ? max_p : res * res * res;
+        in_level           = (in_level + 7u) / 8u * 8u;
+        uint32_t hash_size = 1u << net->log2_hashmap_size;
+        if (in_level > hash_size)
+            in_level = hash_size;
+        if (offsets)
+            offsets[l] = offset;
+        offset += in_level;
+    }
+    if (offsets)
+        offsets[net->n_levels] = offset;
+    return (uint64_t)offset * net->n_features;
+}
+
+static uint64_t mlp_n_params(const onet_t *net)
+{
+    return (uint64_t)net->n_neurons * net->n_input + (uint64_t)(net->n_hidden_layers - 1) * net->n_neurons * net->n_neurons +
+           (uint64_t)net->n_output_padded * net->n_neurons;
+}
+
+/* grid.h:49-169 (Linear interpolation, Hash grid type, CoherentPrime hash: common_device.h:652-655,691-707) */
+void onbvh_grid_encode(const onet_t *net, const float *points, uint32_t n_points, uint16_t *features)
+{
+    uint32_t offsets[64];
+    onbvh_grid_n_params(net, offsets);
+    const uint16_t *grid_base = net->params + mlp_n_params(net);
+    const float l2            = log2f(net->per_level_scale);
+    const uint32_t F          = net->n_features;
+    for (uint32_t p = 0; p < n_points; p++) {
+        for (uint32_t l = 0; l < net->n_levels; l++) {
+            const uint16_t *grid   = grid_base + (size_t)offsets[l] * F;
+            const uint32_t hsize   = offsets[l + 1] - offsets[l];
+            const float scale      = grid_scale(l, l2, net->base_resolution);
+            const uint32_t res     = grid_resolution(scale);
+            float pos[3];
+            uint32_t pg[3];
+            for (int dim = 0; dim < 3; dim++) { /* pos_fract, common_device.h:857-868 */
+                float x   = fmaf(scale, points[3 * p + dim], 0.5f);
+                float fl  = floorf(x);
+                pg[dim]   = (uint32_t)(int)fl;
+                pos[dim]  = x - fl;
+            }
+            uint16_t result[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t idx = 0; idx < 8; idx++) {
+                float w = 1.f;
+                uint32_t q[3];
+                for (int dim = 0; dim < 3; dim++) {
+                    if ((idx & (1u << dim)) == 0) {
+                        w *= 1.f - pos[dim];
+                        q[dim] = pg[dim];
+                    } else {
+                        w *= pos[dim];
+                        q[dim] = pg[dim] + 1u;
+                    }
+                }
+                /* grid_index */
+                uint32_t stride = 1, index = 0;
+                for (int dim = 0; dim < 3 && stride <= hsize; dim++) {
+                    index += q[dim] * stride;
+                    stride *= res;
+                }
+                if (hsize < stride)
+                    index = (q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u);
+                index %= hsize;
+                uint16_t wh = onbvh_f2h(w);
+                for (uint32_t f = 0; f < F; f++)
+                    result[f] = hfma(wh, grid[(size_t)index * F + f], result[f]);
+            }
+            for (uint32_t f = 0; f < F; f++)
+                features[(size_t)p * net->n_levels * F + l * F + f] = result[f];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ MLP (a10) */
+static inline float logistic(float x) { return 1.0f / (1.0f + expf(-x)); } /* common_device.h:129-133 */
+
+/* Weight layout: row-major W[out][in], matrices back to back (fully_fused_mlp.cu:855-863). */
+void onbvh_mlp_forward(const onet_t *net, const uint16_t *features, int mode, float *out, float *hidden)
+{
+    float act[256], next[256];
+    uint32_t in_w = net->n_input;
+    for (uint32_t i = 0; i < in_w; i++)
+        act[i] = onbvh_h2f(features[i]);
+    const uint16_t *W = net->params;
+    const uint32_t n_mats = net->n_hidden_layers + 1;
+    for (uint32_t m = 0; m < n_mats; m++) {
+        const int last       = (m == n_mats - 1);
+        const uint32_t out_w = last ? net->n_output_padded : net->n_neurons;
+        for (uint32_t r = 0; r < out_w; r++) {
+            const uint16_t *row = W + (size_t)r * in_w;
+            float acc;
+            if (mode == 1) { /* fp16 accumulator, rounded after every 16-wide K chunk (wmma m16n16k16) */
+                uint16_t acc_h = 0;
+                for (uint32_t k0 = 0; k0 < in_w; k0 += 16) {
+                    float part = onbvh_h2f(acc_h);
+                    for (uint32_t k = k0; k < k0 + 16 && k < in_w; k++)
+                        part += onbvh_h2f(row[k]) * act[k];
+                    acc_h = onbvh_f2h(part);
+                }
+                acc = onbvh_h2f(acc_h);
+            } else { /* fp32 accumulate, sequential in K like one MMA lane would sum exact products */
+                double a = 0.0;
+                for (uint32_t k = 0; k < in_w; k++)
+                    a += (double)onbvh_h2f(row[k]) * (double)act[k];
+                acc = (float)a;
+            }
+            if (!last) {
+                float v = acc > 0.f ? acc : 0.f;
+                next[r] = (mode == 2) ? v : onbvh_h2f(onbvh_f2h(v)); /* activations travel as fp16 */
+            } else {
+                float s = logistic(acc);
+                next[r] = (mode == 1) ? onbvh_h2f(onbvh_f2h(s)) : s;
+            }
+        }
+        W += (size_t)out_w * in_w;
+        if (!last && hidden)
+            memcpy(hidden + (size_t)m * net->n_neurons, next, sizeof(float) * net->n_neurons);
+        memcpy(act, next, sizeof(float) * out_w);
+        in_w = out_w;
+    }
+    for (uint32_t i = 0; i < net->n_output; i++)
+        out[i] = act[i];
+}
+
+static void query_one(const onet_t *net, const float *pts, uint32_t n_points, int mode, float *out)
+{
+    uint16_t feat[256];
+    onbvh_grid_encode(net, pts, n_points, feat);
+    if (mode == 2) { /* keep fp16-valued features; fp32 everywhere else */
+    }
+    onbvh_mlp_forward(net, feat, mode, out, NULL);
+}
+
+void onbvh_query(const onet_t *net, const float *in, uint32_t n, int mode, float *out)
+{
+    const uint32_t n_points = net->n_input / (net->n_levels * net->n_features);
+    const uint32_t in_dims  = 3 * n_points;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++)
+        query_one(net, in + (size_t)i * in_dims, n_points, mode, out + (size_t)i * net->n_output);
+}
+
+/* ------------------------------------------------------------------ decode (a11) */
+/* neural_bvh_module_common.cuh:23-57,160-209 (LocalT).  PTX: the literal 1e-3 is a double:
+ *   outside: t = (float)fma((double)len + 1e-3, (double)u, (double)mint)
+ *   inside : e = (float)(((double)len + 1e-3) * (double)u);  accept iff e < (maxt - len*eps) - fixed_eps */
+int onbvh_decode(const oconst_t *c, const float *y, float seg_mint, float seg_maxt, uint32_t depth, float *t_out)
+{
+    float thr = depth == 1u ? c->primary_visibility_threshold : c->secondary_visibility_threshold;
+    if (!(y[0] > thr)) {
+        *t_out = FLT_MAX;
+        return 0;
+    }
+    float len  = seg_maxt - seg_mint;
+    float unit = y[1];
+    unit       = gmin(gmax(unit, 0.f), 1.f); /* glm::clamp = min(max(x,lo),hi) */
+    float t    = FLT_MAX;
+    if (seg_mint < 0.f) {
+        if (c->depth_epsilon != 1.f) {
+            float inward = (float)(((double)len + 1e-3) * (double)unit);
+            float lim    = (seg_maxt - len * c->depth_epsilon) - c->fixed_depth_epsilon;
+            if (inward < lim)
+                t = seg_maxt - inward;
+        }
+    } else {
+        t = (float)fma((double)len + 1e-3, (double)unit, (double)seg_mint);
+    }
+    *t_out = t;
+    return t != FLT_MAX;
+}
+
+/* ------------------------------------------------------------------ primary-ray pipeline */
+static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t pixel,
+                       int sample_idx, int rnd_offset, int mlp_mode, ohit_t *hit, uint64_t *cnt)
+{
+    float o[3], d[3];
+    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, NULL);
+    memset(hit, 0, sizeof(*hit));
+    hit->t = FLT_MAX;
+    uint32_t tstack[TLAS_STACK_SIZE];
+    int tss   = 1;
+    tstack[0] = 0;
+    const uint32_t n_points = c->n_segment_points;
+    while (tss > 0) {
+        uint32_t blas_idx;
+        int is_neural;
+        if (!onbvh_tlas_intersect_only(s, o, d, tstack, &tss, &blas_idx, &is_neural))
+            break;
+        if (is_neural && !c->ignore_neural_blas) {
+            /* tlas_traversal_and_fill_next_hybrid_traversal (common.cuh:323-380): first interval with FLT_MAX */
+            uint32_t stack[NEURAL_STACK_SIZE];
+            int ss      = 1;
+            stack[0]    = 0;
+            float maxt_ray = FLT_MAX;
+            for (;;) {
+                float mint, maxt;
+                uint32_t node;
+                if (!onbvh_neural_intersect(nbvh, c, c->rendered_lod, o, d, stack, &ss, 1, maxt_ray,
+                                            c->fixed_node_dilation, &mint, &maxt, &node, &cnt[1]))
+                    break;
+                float pts[64], y[16];
+                onbvh_encode_segment(c, o, d, mint, maxt, pts);
+                query_one(net, pts, n_points, mlp_mode, y);
+                cnt[0]++;
+                float t;
+                /* process_neural_bvh_traversal_step (path_inference_kernels.cu:61-131) */
+                if (onbvh_decode(c, y, mint, maxt, 1u, &t) && t < hit->t) {
+                    hit->valid_hit = 1;
+                    hit->t         = t;
+                    float n[3]     = {y[2] * 2.f - 1.f, y[3] * 2.f - 1.f, y[4] * 2.f - 1.f};
+                    float len2     = fmaf(n[2], n[2], fmaf(n[0], n[0], n[1] * n[1]));
+                    float inv      = 1.f / sqrtf(len2);
+                    for (int i = 0; i < 3; i++) {
+                        hit->normal_or_uv[i]  = n[i] * inv;
+                        hit->albedo_or_ids[i] = y[5 + i];
+                    }
+                }
+                /* resume with ray.maxt = current best t (common.cuh:529-545) */
+                maxt_ray = hit->t;
+                if (ss == 0)
+                    break;
+            }
+        } else {
+            /* non_neural_bvh_intersection (path_inference_kernels.cu:195-222): ray.maxt = last_tlas_t */
+            float u = 0.f, v = 0.f;
+            uint32_t prim = 0;
+            float t = onbvh_blas_intersect(&s->blas[blas_idx], o, d, 1e-4f, hit->t, &u, &v, &prim, &cnt[2], &cnt[3]);
+            if (t < hit->t) {
+                hit->valid_hit       = 2;
+                hit->t               = t;
+                hit->normal_or_uv[0] = u;
+                hit->normal_or_uv[1] = v;
+                memcpy(&hit->albedo_or_ids[0], &blas_idx, 4);
+                memcpy(&hit->albedo_or_ids[1], &prim, 4);
+            }
+        }
+    }
+}
+
+void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net,
+                          uint32_t pixel_begin, uint32_t pixel_end, uint32_t pixel_stride, int sample_idx,
+                          int rnd_offset, int mlp_mode, ohit_t *hits, uint64_t *counters, int n_threads)
+{
+    uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    if (pixel_stride == 0)
+        pixel_stride = 1;
+    const int64_t n = ((int64_t)pixel_end - (int64_t)pixel_begin + pixel_stride - 1) / pixel_stride;
+#ifdef _OPENMP
+    if (n_threads > 0)
+        omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : c0, c1, c2, c3)
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t cnt[4] = {0, 0, 0, 0};
+        render_one(s, nbvh, c, net, pixel_begin + (uint32_t)i * pixel_stride, sample_idx, rnd_offset, mlp_mode,
+                   &hits[i], cnt);
+        c0 += cnt[0], c1 += cnt[1], c2 += cnt[2], c3 += cnt[3];
+    }
+    if (counters) {
+        counters[0] = c0, counters[1] = c1, counters[2] = c2, counters[3] = c3;
+    }
+}

@@ -1,0 +1,310 @@
+"""ctypes front-end of the CPU oracle (oracle/libnbvh_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (nbvh_b200) never imports this module.
+
+Also holds independent numpy readers for the reference's on-disk formats (config JSON, .nbvh,
+network_models JSON) so the C++ loaders of the product can be checked against a second implementation.
+"""
+import ctypes as C
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnbvh_oracle.so")
+
+NODE_DTYPE = np.dtype([("mn", "<f4", 3), ("a", "<u4"), ("mx", "<f4", 3), ("b", "<u4")])
+HIT_DTYPE = np.dtype([("valid_hit", "u1"), ("t", "<f4"), ("normal_or_uv", "<f4", 3), ("albedo_or_ids", "<f4", 3)],
+                     align=True)
+
+
+class ONode(C.Structure):
+    _fields_ = [("mn", C.c_float * 3), ("a", C.c_uint32), ("mx", C.c_float * 3), ("b", C.c_uint32)]
+
+
+class OBlas(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("n_nodes", C.c_uint32), ("prim_ids", C.c_void_p), ("vertices", C.c_void_p),
+                ("indices", C.c_void_p)]
+
+
+class OScene(C.Structure):
+    _fields_ = [("tlas_nodes", C.c_void_p), ("n_tlas_nodes", C.c_uint32), ("blas_indices", C.c_void_p),
+                ("blas", C.POINTER(OBlas)), ("n_blas", C.c_uint32)]
+
+
+class OConst(C.Structure):
+    _fields_ = [("rendered_lod", C.c_uint32), ("fixed_node_dilation", C.c_float), ("node_extent_dilation", C.c_float),
+                ("inference_mint_epsilon", C.c_float), ("inference_maxt_epsilon", C.c_float),
+                ("learning_mint_epsilon", C.c_float), ("learning_maxt_epsilon", C.c_float),
+                ("primary_visibility_threshold", C.c_float), ("secondary_visibility_threshold", C.c_float),
+                ("depth_epsilon", C.c_float), ("fixed_depth_epsilon", C.c_float), ("ignore_neural_blas", C.c_uint32),
+                ("n_segment_points", C.c_uint32), ("segment_distribution", C.c_uint32), ("bbox_min", C.c_float * 3),
+                ("bbox_max", C.c_float * 3), ("cam_origin", C.c_float * 3), ("cam_du", C.c_float * 3),
+                ("cam_dv", C.c_float * 3), ("cam_top_left", C.c_float * 3), ("fb_w", C.c_uint32), ("fb_h", C.c_uint32)]
+
+
+class ONet(C.Structure):
+    _fields_ = [("n_levels", C.c_uint32), ("n_features", C.c_uint32), ("base_resolution", C.c_uint32),
+                ("log2_hashmap_size", C.c_uint32), ("per_level_scale", C.c_float), ("n_hidden_layers", C.c_uint32),
+                ("n_neurons", C.c_uint32), ("n_input", C.c_uint32), ("n_output_padded", C.c_uint32),
+                ("n_output", C.c_uint32), ("params", C.c_void_p), ("n_params", C.c_uint64)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-C", HERE, "-s"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.onbvh_h2f.restype = C.c_float
+        _lib.onbvh_h2f.argtypes = [C.c_uint16]
+        _lib.onbvh_f2h.restype = C.c_uint16
+        _lib.onbvh_f2h.argtypes = [C.c_float]
+        _lib.onbvh_lcg_rng_init.restype = C.c_uint32
+        _lib.onbvh_lcg_randomf.restype = C.c_float
+        _lib.onbvh_blas_intersect.restype = C.c_float
+        _lib.onbvh_grid_n_params.restype = C.c_uint64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- file formats (independent readers)
+def read_nbvh(path):
+    """.nbvh = bvh::v2::Bvh<Node<float,3,64,32>>::serialize (ext/bvh/src/bvh/v2/bvh.h:133-153, node.h:119-133).
+    Returns 32-byte device nodes laid out like neural_bvh_renderer_accel.cpp:229-238 does."""
+    d = open(path, "rb").read()
+    n_nodes, n_prims = struct.unpack("<QQ", d[:16])
+    rec = np.dtype([("b", "<f4", 6), ("first", "<u8"), ("cnt", "<u8")])
+    assert len(d) == 16 + n_nodes * rec.itemsize + 8 * n_prims, "unexpected .nbvh size"
+    raw = np.frombuffer(d, dtype=rec, count=n_nodes, offset=16)
+    out = np.zeros(n_nodes, dtype=NODE_DTYPE)
+    out["mn"] = raw["b"][:, 0::2]
+    out["mx"] = raw["b"][:, 1::2]
+    out["a"] = raw["cnt"].astype(np.uint32)      # prim_count (LoD tag)
+    out["b"] = raw["first"].astype(np.uint32)    # left child / NO_NEURAL_CHILD
+    return out
+
+
+def read_network_json(path):
+    """network_models/*_network.json (trainer.h:275-320, gpu_memory_json.h:36-60): returns fp16 bit patterns."""
+    j = json.load(open(path))
+    n = int(j["n_params"])
+    raw = np.asarray(j["params_binary"]["bytes"], dtype=np.uint8)
+    if j["params_type"] == "__half":
+        bits = raw.view("<u2").copy()
+    elif j["params_type"] == "float":
+        bits = raw.view("<f4").astype(np.float16).view("<u2").copy()
+    else:
+        raise ValueError("unknown params_type " + str(j["params_type"]))
+    assert bits.size == n
+    return bits
+
+
+SEGMENT_DISTRIBUTIONS = ["EquidistantInterior", "EquidistantExterior", "Uniform"]
+
+
+def config_constants(cfg, nbvh_nodes=None):
+    """Config JSON -> OConst + network description, with the reference's defaults
+    (neural_bvh_renderer_constants.cuh:13-47, neural_bvh_module.h:79-94,243-274, tcnn_config.h)."""
+    scene = cfg.get("cuda_scene", {})
+    r = cfg.get("neural_bvh_renderer", {})
+    m = r.get("neural_module", {})
+    bc = r.get("bvh_constants", {})
+    pt = m.get("pt_output_constants", {})
+    mc = m.get("bvh_module_constants", {})
+    c = OConst()
+    c.rendered_lod = bc.get("rendered_lod", 0)
+    c.fixed_node_dilation = bc.get("fixed_node_dilation", 1e-5)
+    c.node_extent_dilation = bc.get("node_extent_dilation", 1e-4)
+    c.inference_mint_epsilon = bc.get("inference_mint_epsilon", 1e-4)
+    c.inference_maxt_epsilon = bc.get("inference_maxt_epsilon", 1e-3)
+    c.learning_mint_epsilon = bc.get("learning_mint_epsilon", 1e-3)
+    c.learning_maxt_epsilon = bc.get("learning_maxt_epsilon", 1e-3)
+    c.primary_visibility_threshold = pt.get("primary_visibility_threshold", 0.5)
+    c.secondary_visibility_threshold = pt.get("secondary_visibility_threshold", 0.5)
+    c.depth_epsilon = pt.get("depth_epsilon", 0.2)
+    c.fixed_depth_epsilon = pt.get("fixed_depth_epsilon", 1e-5)
+    c.ignore_neural_blas = int(bc.get("ignore_neural_blas", False))
+    c.n_segment_points = mc.get("input_segment_points", 3)
+    c.segment_distribution = SEGMENT_DISTRIBUTIONS.index(mc.get("segment_distribution", "EquidistantInterior"))
+    fb = scene.get("fb_size", [1920, 1080])
+    c.fb_w, c.fb_h = fb
+    cam = scene.get("camera", {})
+    if "matrix" in cam:
+        mtx = (C.c_float * 16)(*[float(x) for x in cam["matrix"]])
+        o, du, dv, tl = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        lib().onbvh_camera_params(mtx, C.c_float(cam.get("yfov", np.radians(45.0))), C.c_uint32(c.fb_w),
+                                  C.c_uint32(c.fb_h), o, du, dv, tl)
+        c.cam_origin, c.cam_du, c.cam_dv, c.cam_top_left = o, du, dv, tl
+    if nbvh_nodes is not None:
+        c.bbox_min = (C.c_float * 3)(*nbvh_nodes["mn"][0])
+        c.bbox_max = (C.c_float * 3)(*nbvh_nodes["mx"][0])
+    return c
+
+
+def make_net(cfg, params_bits):
+    m = cfg.get("neural_bvh_renderer", {}).get("neural_module", {})
+    hg = m.get("segment_encoding", {}).get("hashgrid_options", {})
+    nw = m.get("network", {})
+    pt = m.get("pt_output_constants", {})
+    mc = m.get("bvh_module_constants", {})
+    net = ONet()
+    net.n_levels = hg.get("n_levels", 8)
+    net.n_features = hg.get("n_features_per_level", 4)
+    net.base_resolution = hg.get("base_resolution", 8)
+    net.log2_hashmap_size = hg.get("log2_hashmap_size", 18)
+    net.per_level_scale = hg.get("per_level_scale", 2.0)
+    net.n_hidden_layers = nw.get("n_hidden_layers", 4)
+    net.n_neurons = nw.get("n_neurons", 64)
+    n_points = mc.get("input_segment_points", 3)
+    net.n_input = n_points * net.n_levels * net.n_features
+    net.n_output = pt.get("output_network_dims", 8)
+    net.n_output_padded = (net.n_output + 15) // 16 * 16
+    params_bits = np.ascontiguousarray(params_bits, dtype=np.uint16)
+    net.params = params_bits.ctypes.data
+    net.n_params = params_bits.size
+    net._keep = params_bits
+    return net
+
+
+def expected_n_params(net):
+    offs = (C.c_uint32 * 65)()
+    grid = lib().onbvh_grid_n_params(C.byref(net), offs)
+    mlp = net.n_neurons * net.n_input + (net.n_hidden_layers - 1) * net.n_neurons ** 2 + net.n_output_padded * net.n_neurons
+    return mlp + grid, list(offs[: net.n_levels + 1])
+
+
+# ----------------------------------------------------------------------------- scene assembly
+class Scene:
+    """Keeps numpy arrays alive and exposes an OScene."""
+
+    def __init__(self, tlas_nodes, tlas_indices, blas_list):
+        self.tlas_nodes = np.ascontiguousarray(tlas_nodes, dtype=NODE_DTYPE)
+        self.tlas_indices = np.ascontiguousarray(tlas_indices, dtype=np.uint32)
+        self.blas_arrays = []
+        self.blas = (OBlas * len(blas_list))()
+        for i, b in enumerate(blas_list):
+            nodes = np.ascontiguousarray(b["nodes"], dtype=NODE_DTYPE)
+            prim = np.ascontiguousarray(b["prim_ids"], dtype=np.uint32)
+            verts = np.ascontiguousarray(b["vertices"], dtype=np.float32)
+            idx = np.ascontiguousarray(b["indices"], dtype=np.uint32)
+            self.blas_arrays.append((nodes, prim, verts, idx))
+            self.blas[i] = OBlas(_p(nodes), nodes.size, _p(prim), _p(verts), _p(idx))
+        self.c = OScene(_p(self.tlas_nodes), self.tlas_nodes.size, _p(self.tlas_indices), self.blas, len(blas_list))
+
+
+def load_chess_fixture(root, with_neural_mesh=False):
+    """Loads baseline/_ref/chess (written by tools/make_fixtures.py).  The neural mesh's triangle BLAS
+    (1.4 M triangles) is only needed for training targets / the non-neural CPU baseline."""
+    man = json.load(open(os.path.join(root, "manifest.json")))
+    blas = []
+    for i, m in enumerate(man["meshes"]):
+        p = os.path.join(root, "mesh%d" % i)
+        if i == man["neural_mesh"] and not with_neural_mesh:
+            # a stub: never traversed while ignore_neural_blas == false
+            blas.append(dict(nodes=np.zeros(1, NODE_DTYPE), prim_ids=np.zeros(1, np.uint32),
+                             vertices=np.zeros(9, np.float32), indices=np.zeros(3, np.uint32)))
+            continue
+        blas.append(dict(nodes=np.fromfile(p + "_bvh_nodes.bin", dtype=NODE_DTYPE),
+                         prim_ids=np.fromfile(p + "_prim_ids.u32", dtype="<u4"),
+                         vertices=np.fromfile(p + "_vertices.f32", dtype="<f4"),
+                         indices=np.fromfile(p + "_indices.u32", dtype="<u4")))
+    tlas_nodes = np.fromfile(os.path.join(root, "tlas_nodes.bin"), dtype=NODE_DTYPE)
+    tlas_idx = np.fromfile(os.path.join(root, "tlas_indices.u32"), dtype="<u4")
+    return Scene(tlas_nodes, tlas_idx, blas), man
+
+
+# ----------------------------------------------------------------------------- wrappers
+def trace_intervals(nodes, const, o, d, max_intervals):
+    nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
+    o = np.ascontiguousarray(o, dtype=np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    n = o.shape[0]
+    counts = np.zeros(n, np.uint32)
+    node_idx = np.zeros((n, max_intervals), np.uint32)
+    mint = np.zeros((n, max_intervals), np.float32)
+    maxt = np.zeros((n, max_intervals), np.float32)
+    steps = C.c_uint64(0)
+    lib().onbvh_trace_intervals(_p(nodes), C.byref(const), C.c_uint32(n), _p(o), _p(d), C.c_uint32(max_intervals),
+                                _p(counts), _p(node_idx), _p(mint), _p(maxt), C.byref(steps))
+    return counts, node_idx, mint, maxt, steps.value
+
+
+def raygen(const, pixels, sample_idx=0, rnd_offset=0):
+    pixels = np.asarray(pixels, dtype=np.uint32)
+    o = np.zeros((pixels.size, 3), np.float32)
+    d = np.zeros((pixels.size, 3), np.float32)
+    oo, dd = (C.c_float * 3)(), (C.c_float * 3)()
+    f = lib().onbvh_raygen
+    for i, p in enumerate(pixels):
+        f(C.byref(const), C.c_uint32(int(p)), C.c_int(sample_idx), C.c_int(rnd_offset), oo, dd, None)
+        o[i] = oo[:]
+        d[i] = dd[:]
+    return o, d
+
+
+def blas_intersect(scene, blas_idx, o, d, maxt=None):
+    o = np.ascontiguousarray(o, dtype=np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    n = o.shape[0]
+    t = np.zeros(n, np.float32)
+    u = np.zeros(n, np.float32)
+    v = np.zeros(n, np.float32)
+    prim = np.zeros(n, np.uint32)
+    cnt = (C.c_uint64 * 2)()
+    mt = None if maxt is None else _p(np.ascontiguousarray(maxt, dtype=np.float32))
+    lib().onbvh_blas_intersect_batch(C.byref(scene.blas[blas_idx]), C.c_uint32(n), _p(o), _p(d), mt, _p(t), _p(u),
+                                     _p(v), _p(prim), cnt)
+    return t, u, v, prim, (cnt[0], cnt[1])
+
+
+def encode_segments(const, o, d, mint, maxt):
+    n = o.shape[0]
+    out = np.zeros((n, 3 * const.n_segment_points), np.float32)
+    f = lib().onbvh_encode_segment
+    for i in range(n):
+        oo = (C.c_float * 3)(*o[i])
+        dd = (C.c_float * 3)(*d[i])
+        f(C.byref(const), oo, dd, C.c_float(mint[i]), C.c_float(maxt[i]), _p(out[i]))
+    return out
+
+
+def query(net, inputs, mode=0):
+    """inputs: (N, 9) float32 rows (== the reference's column-major 9xN matrix in memory)."""
+    x = np.ascontiguousarray(inputs, dtype=np.float32)
+    out = np.zeros((x.shape[0], net.n_output), np.float32)
+    lib().onbvh_query(C.byref(net), _p(x), C.c_uint32(x.shape[0]), C.c_int(mode), _p(out))
+    return out
+
+
+def grid_encode(net, points):
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    feats = np.zeros(pts.shape[0] * net.n_levels * net.n_features, np.uint16)
+    lib().onbvh_grid_encode(C.byref(net), _p(pts), C.c_uint32(pts.shape[0]), _p(feats))
+    return feats
+
+
+def render_primary(scene, nbvh_nodes, const, net, pixel_begin, pixel_end, stride=1, sample_idx=0, rnd_offset=0,
+                   mlp_mode=0, n_threads=0):
+    nbvh_nodes = np.ascontiguousarray(nbvh_nodes, dtype=NODE_DTYPE)
+    n = (pixel_end - pixel_begin + stride - 1) // stride
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    cnt = (C.c_uint64 * 4)()
+    lib().onbvh_render_primary(C.byref(scene.c), _p(nbvh_nodes), C.byref(const), C.byref(net), C.c_uint32(pixel_begin),
+                               C.c_uint32(pixel_end), C.c_uint32(stride), C.c_int(sample_idx), C.c_int(rnd_offset),
+                               C.c_int(mlp_mode), _p(hits), cnt, C.c_int(n_threads))
+    return hits, [cnt[i] for i in range(4)]
