@@ -1,0 +1,261 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the N-BVH neural ray-query hot path on B200 ("Measurement").
+
+A step = one 1-spp pass of the hot path over one frame of primary rays of the shipped Chess configuration
+(1920x1080, shipped camera / .nbvh / weights): ray generation, TLAS + N-BVH walk, hash-grid encoding, 64-wide MLP,
+decode, closest-hit bookkeeping, classical BLAS closest hit, splat -- all inside ONE persistent kernel (k_render).
+  value  = rays / device time of the kernel region (inputs resident in HBM, CUDA events, max over ranks)
+  e2e    = same metric through the C-ABI host call nbvh_render_host: camera constants H2D, 8-bit frame D2H
+  N > 1  = every rank renders its own sample of the frame (spp sharding, no data-path collective): weak scaling
+--impl reference times the reference's CPU path (ext/bvh closest-hit traversal of the same primary rays, the neural
+mesh traced as triangles) on the host cores through oracle/_ref/cpu_bvh_trace (or the oracle port when absent).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "neural ray queries/sec (Mrays/s, 1080p Chess)"
+UNIT = "Mrays/s"
+CPU_TOOL = os.path.join(REPO, "oracle", "_ref", "cpu_bvh_trace")
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nme, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(repeats, root, w, h):
+    """The reference's CPU path on the host cores.  Returns (Mrays/s, cores, kind, sample description)."""
+    import numpy as np
+    if os.path.exists(CPU_TOOL) and root is not None:
+        out = subprocess.run([CPU_TOOL, root, str(w), str(h), "0", "0", str(repeats)], capture_output=True, text=True,
+                             check=True).stdout.strip().splitlines()[-1]
+        j = json.loads(out)
+        return j["mrays_s"], j["threads"], "reference", ("full %dx%d frame of primary rays, closest hit through ext/bvh "
+                                                         "Bvh::intersect (all meshes as triangles), best of %d, BVH build %.2f s "
+                                                         "excluded" % (w, h, repeats, j["build_s"])), j["best_s"] * 1e3
+    # oracle port: neural primary pipeline of the oracle on a pixel sample (OpenMP)
+    from oracle import oracle as O
+    import nbvh_b200
+    cfg, nbvh, tlas, tlas_idx, blas = nbvh_b200.synthetic_scene(fb=(w, h))
+    const = O.config_constants(cfg, nbvh)
+    rng = np.random.default_rng(1337)
+    net0 = O.make_net(cfg, np.zeros(16, np.uint16))
+    total, _ = O.expected_n_params(net0)
+    net = O.make_net(cfg, (rng.standard_normal(total) * 0.05).astype(np.float16).view(np.uint16))
+    sc = O.Scene(tlas, tlas_idx, blas)
+    stride = max(1, (w * h) // 200000)
+    best = 1e30
+    for _ in range(max(1, repeats)):
+        t0 = time.time()
+        hits, _ = O.render_primary(sc, nbvh, const, net, 0, w * h, stride=stride)
+        best = min(best, time.time() - t0)
+    return len(hits) / best / 1e6, os.cpu_count(), "port", "every %d-th pixel of a %dx%d synthetic frame, oracle neural pipeline" % (
+        stride, w, h), best * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import nbvh_b200
+    root = nbvh_b200.chess_fixture_dir()
+    W, H = 1920, 1080
+    workload = ("Chess N-BVH inference, shipped config nodes_32940_hash_18_lvl_8 (hash grid 8x4 2^18 + 64-wide MLP), "
+                "visibility/distance/normal/albedo queries, 1920x1080 1spp primary rays (max_depth 1)")
+    if root is None:
+        workload = "SYNTHETIC stand-in (Chess fixture absent): procedural scene, shipped network shape, 1920x1080 1spp primary rays"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vals = []
+        info = None
+        for i in range(args.warmup + args.steps):
+            info = cpu_reference_run(1, root, W, H)
+            if i >= args.warmup:
+                vals.append(info[4])
+        ms = sum(vals) / max(1, len(vals))
+        v = W * H / (ms * 1e-3) / 1e6 if info[2] == "reference" else info[0]
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "shipped Chess scene" if root else "synthetic",
+                "config": {"workload": workload + " -- reference arm: CPU closest-hit traversal of the non-neural BLAS (BASELINE config 1)"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3]},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nbvh_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    if root is not None:
+        mod = nbvh_b200.load_chess_module(device=local_rank, max_depth=1, envmap_eval=False)
+    else:
+        cfg, nbvh, tlas, tlas_idx, blas = nbvh_b200.synthetic_scene(fb=(W, H), cut_depth=9)
+        mod = nbvh_b200.NeuralPathModule(cfg, device=local_rank)
+        mod.set_neural_bvh(nbvh)
+        mod.set_scene(tlas, tlas_idx, blas)
+        mod.init_params(1337)
+    n_rays = W * H
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing: K launches of k_render, CUDA events on the launching stream
+    stream = torch.cuda.current_stream()
+    for i in range(args.warmup):
+        flush.fill_(i & 0xFF)
+        mod.neural_render(i * world + rank, 0, stream=stream.cuda_stream)
+    barrier()
+    mod.reset_counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event interval)
+        evs[i][0].record(stream)
+        mod.neural_render((args.warmup + i) * world + rank, 0, stream=stream.cuda_stream)
+        evs[i][1].record(stream)
+    barrier()
+    t_wall = time.time() - t_wall0
+    sampler.stop_flag = True
+    sampler.join()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    counters = mod.counters()
+
+    # ---------------- end to end through the C-ABI host call (pinned host buffers, copies inside the timed region)
+    ldr_host = torch.empty(n_rays * 4, dtype=torch.uint8, pin_memory=True).numpy()
+    cam = mod.get_constants(nbvh_b200.CONST_CAMERA)
+    for i in range(2):
+        mod.neural_render_host(i, 0, ldr_host=ldr_host, camera=cam)
+    barrier()
+    t0 = time.time()
+    for i in range(args.steps):
+        mod.neural_render_host(args.warmup + i, 0, ldr_host=ldr_host, camera=cam)
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * n_rays * args.steps / (total_ms * 1e-3) / 1e6
+        e2e_value = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
+        peak, peak_src = measured_peaks()
+        K = args.steps
+        per = {k: v / K for k, v in counters.items()}
+        # algorithmic bytes per launch: 64 B per interior step (child pair), 56 B per triangle test,
+        # 48 B per ray (ray in + hit out), 1600 B per network query (1536 B table gathers + 64 B state)
+        alg_bytes = 64.0 * (per["nbvh_steps"] + per["blas_steps"]) + 56.0 * per["tri_tests"] + 48.0 * per["rays"] + 1600.0 * per["queries"]
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "k_render_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 traversal + f16 hash grid/MLP operands with f32 accumulate",
+            "data": "shipped Chess scene + shipped pre-trained weights" if root else "synthetic",
+            "config": {"workload": workload, "rays_per_step_per_gpu": n_rays,
+                       "sharding": "one full-frame sample per rank per step (spp sharding), scene and weights replicated",
+                       "l2": "256 MiB buffer written between timed steps (outside the event intervals)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n_rays * 4,
+                    "api": "nbvh_render_host (C ABI): camera constants in, sRGB8 frame out, pinned host memory"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "nbvh::k_render", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "scene, tree-cut and hash table are L2-resident by design; the bytes are L2-level algorithmic traffic"},
+            "counters_per_step": per,
+            "neural_queries_per_s": per["queries"] / (ms_per_step * 1e-3),
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, kind, sample, _ = cpu_reference_run(5, root, W, H)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    mod.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
