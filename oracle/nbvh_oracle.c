@@ -878,3 +878,265 @@ void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t
         counters[0] = c0, counters[1] = c1, counters[2] = c2, counters[3] = c3;
     }
 }
+
+/* ================================================================== online optimisation (a18-a21) */
+/* include/cuda/neural/utils/loss_gradient.cuh:24-95 */
+static void loss_and_gradient(float target, float prediction, uint32_t type, float *loss, float *grad)
+{
+    float diff = prediction - target;
+    switch (type) {
+    case 0: { /* RelativeL2 */
+        float denom = prediction * prediction + 1e-2f;
+        *loss = diff * diff / denom, *grad = 2.0f * diff / denom;
+        break;
+    }
+    case 3: /* L1 */
+        *loss = fabsf(diff), *grad = copysignf(1.0f, diff);
+        break;
+    case 2: { /* RelativeL1 */
+        float scale = 1.0f / (fabsf(prediction) + 1e-2f);
+        *loss = fabsf(diff) * scale, *grad = copysignf(scale, diff);
+        break;
+    }
+    case 5: { /* BinaryCrossEntropy */
+        const float eps = 1e-5f;
+        float pred      = fminf(fmaxf(prediction, eps), 1.f - eps);
+        *loss = -(target * logf(pred) + (1.f - target) * logf(1.f - pred));
+        *grad = -(target - pred) / (pred - (pred * pred));
+        break;
+    }
+    case 6: { /* LogL2 */
+        float d = logf(1 + prediction) - logf(1 + target);
+        *loss = d * d, *grad = 2.0f * d / (prediction + 1);
+        break;
+    }
+    case 7: { /* LHalf */
+        float s = sqrtf(fabsf(diff));
+        *loss = s, *grad = 1.f / (2.f * s + 1e-5f);
+        break;
+    }
+    default: /* L2 (and RelativeL2Luminance, which the reference's switch sends to L2) */
+        *loss = diff * diff, *grad = 2.0f * diff;
+        break;
+    }
+}
+
+/* pt_composite_loss.cuh:19-123 */
+float onbvh_loss_element(const oloss_t *lc, const float *target8, float prediction, uint32_t elem, uint32_t n_total,
+                         float loss_scale, float *grad_out)
+{
+    const uint32_t depth0 = lc->vis_dim, normal0 = depth0 + lc->depth_dim, albedo0 = normal0 + lc->normal_dim,
+                   end = albedo0 + lc->albedo_dim;
+    float loss = 0.f, grad = 0.f;
+    if (elem < end) {
+        const float target = target8[elem];
+        const int ignore   = lc->vis_masking ? (target8[0] < 0.5f) : 0;
+        if (lc->vis_dim > 0 && elem == 0) {
+            loss_and_gradient(target, prediction, lc->vis_loss, &loss, &grad);
+            loss *= lc->vis_scale, grad *= lc->vis_scale;
+        } else if (!ignore && elem >= depth0 && elem < normal0) {
+            loss_and_gradient(target, prediction, lc->depth_loss, &loss, &grad);
+            if (lc->depth_linear)
+                grad *= (lc->depth_loss == 1 || lc->depth_loss == 0) ? 100.f : 10.f;
+            loss *= lc->depth_scale, grad *= lc->depth_scale;
+        } else if (!ignore && elem >= normal0 && elem < albedo0) {
+            if (lc->normal_linear) {
+                float n_length = 0.1f;
+                float n_axis   = (prediction * 2.f - 1.f) / n_length;
+                float lin      = n_axis * 0.5f + 0.5f;
+                loss_and_gradient(target, lin, lc->normal_loss, &loss, &grad);
+                grad *= 1.f / n_length;
+            } else {
+                loss_and_gradient(target, prediction, lc->normal_loss, &loss, &grad);
+            }
+            loss *= lc->normal_scale, grad *= lc->normal_scale;
+        } else if (!ignore && elem >= albedo0 && elem < end) {
+            if (lc->albedo_linear) {
+                float n_length = 0.1f;
+                float lin      = prediction / n_length;
+                loss_and_gradient(target, lin, lc->albedo_loss, &loss, &grad);
+                grad *= 1.f / n_length;
+            } else {
+                loss_and_gradient(target, prediction, lc->albedo_loss, &loss, &grad);
+            }
+            loss *= lc->albedo_scale, grad *= lc->albedo_scale;
+        }
+    }
+    *grad_out = loss_scale * grad / (float)n_total;
+    return loss / (float)n_total;
+}
+
+static inline float round_h(float x) { return onbvh_h2f(onbvh_f2h(x)); }
+
+/* Scatter of one point's feature gradient into the grid (kernel_grid_backward, grid.h:215-320): same positions,
+ * weights and indices as the forward pass; gradient += weight * dL/dfeature per corner. */
+static void grid_backward_point(const onet_t *net, const uint32_t *offsets, const float *pt, const float *dfeat /* levels*F */,
+                                float *grid_grads)
+{
+    const float l2   = log2f(net->per_level_scale);
+    const uint32_t F = net->n_features;
+    for (uint32_t l = 0; l < net->n_levels; l++) {
+        const uint32_t hsize = offsets[l + 1] - offsets[l];
+        const float scale    = grid_scale(l, l2, net->base_resolution);
+        const uint32_t res   = grid_resolution(scale);
+        float pos[3];
+        uint32_t pg[3];
+        for (int dim = 0; dim < 3; dim++) {
+            float x  = fmaf(scale, pt[dim], 0.5f);
+            float fl = floorf(x);
+            pg[dim]  = (uint32_t)(int)fl;
+            pos[dim] = x - fl;
+        }
+        for (uint32_t idx = 0; idx < 8; idx++) {
+            float w = 1.f;
+            uint32_t q[3];
+            for (int dim = 0; dim < 3; dim++) {
+                if ((idx & (1u << dim)) == 0) {
+                    w *= 1.f - pos[dim];
+                    q[dim] = pg[dim];
+                } else {
+                    w *= pos[dim];
+                    q[dim] = pg[dim] + 1u;
+                }
+            }
+            uint32_t stride = 1, index = 0;
+            for (int dim = 0; dim < 3 && stride <= hsize; dim++) {
+                index += q[dim] * stride;
+                stride *= res;
+            }
+            if (hsize < stride)
+                index = (q[0] * 1u) ^ (q[1] * 2654435761u) ^ (q[2] * 805459861u);
+            index %= hsize;
+            float *g = grid_grads + ((size_t)offsets[l] + index) * F;
+            for (uint32_t f = 0; f < F; f++)
+                g[f] += w * dfeat[l * F + f];
+        }
+    }
+}
+
+void onbvh_train_forward_backward(const onet_t *net, const oloss_t *lc, const float *in, const float *target,
+                                  uint32_t batch, uint32_t global_batch, float loss_scale, float *L, float *grads,
+                                  double *loss_sum)
+{
+    uint32_t offsets[64];
+    onbvh_grid_n_params(net, offsets);
+    const uint64_t n_mlp    = mlp_n_params(net);
+    const uint32_t n_points = net->n_input / (net->n_levels * net->n_features);
+    const uint32_t in_dims  = 3 * n_points;
+    const uint32_t n_mats   = net->n_hidden_layers + 1;
+    const uint32_t W        = net->n_neurons, K0 = net->n_input, NO = net->n_output_padded;
+    const uint32_t n_total  = global_batch * net->n_output;
+    const uint32_t ppf      = net->n_levels * net->n_features; /* features per point */
+    memset(grads, 0, sizeof(float) * net->n_params);
+    double lsum = 0.0;
+    /* fp32 copies of the fp16 weights */
+    float *Wf = (float *)malloc(sizeof(float) * n_mlp);
+    for (uint64_t i = 0; i < n_mlp; i++)
+        Wf[i] = onbvh_h2f(net->params[i]);
+    double *wg = (double *)calloc(n_mlp, sizeof(double)); /* weight gradients accumulate in high precision */
+    float *gg  = grads + n_mlp;
+    for (uint32_t s = 0; s < batch; s++) {
+        uint16_t feat[256];
+        float act[9][256]; /* act[0] = features, act[l] = hidden l (post ReLU, fp16 valued) */
+        float y[64], dz[256], dprev[256];
+        onbvh_grid_encode(net, in + (size_t)s * in_dims, n_points, feat);
+        for (uint32_t i = 0; i < K0; i++)
+            act[0][i] = onbvh_h2f(feat[i]);
+        const float *Wl = Wf;
+        uint32_t in_w   = K0;
+        for (uint32_t m = 0; m < n_mats; m++) {
+            const int last       = m == n_mats - 1;
+            const uint32_t out_w = last ? NO : W;
+            for (uint32_t r = 0; r < out_w; r++) {
+                double a = 0.0;
+                for (uint32_t k = 0; k < in_w; k++)
+                    a += (double)Wl[(size_t)r * in_w + k] * (double)act[m][k];
+                float acc = (float)a;
+                if (!last)
+                    act[m + 1][r] = round_h(acc > 0.f ? acc : 0.f);
+                else
+                    y[r] = round_h(logistic(acc)); /* the training forward hands fp16 predictions to the loss */
+            }
+            Wl += (size_t)out_w * in_w;
+            in_w = out_w;
+        }
+        /* loss + output-activation backward: dz = dL/dy * y(1-y), operands fp16-rounded */
+        for (uint32_t r = 0; r < NO; r++) {
+            float g = 0.f, lv = 0.f;
+            if (r < net->n_output)
+                lv = onbvh_loss_element(lc, target + (size_t)s * net->n_output, y[r], r, n_total, loss_scale, &g);
+            if (L)
+                L[(size_t)s * NO + r] = lv;
+            lsum += lv;
+            g     = round_h(g);
+            dz[r] = round_h(g * (y[r] * (1.f - y[r])));
+        }
+        /* backward through the matrices, last to first */
+        const float *Wend = Wf + n_mlp;
+        uint32_t out_w    = NO;
+        for (int m = (int)n_mats - 1; m >= 0; m--) {
+            const uint32_t k_w = m == 0 ? K0 : W;
+            Wend -= (size_t)out_w * k_w;
+            double *wgm = wg + (Wend - Wf);
+            for (uint32_t r = 0; r < out_w; r++)
+                if (dz[r] != 0.f)
+                    for (uint32_t k = 0; k < k_w; k++)
+                        wgm[(size_t)r * k_w + k] += (double)dz[r] * (double)act[m][k];
+            for (uint32_t k = 0; k < k_w; k++) {
+                double a = 0.0;
+                for (uint32_t r = 0; r < out_w; r++)
+                    a += (double)Wend[(size_t)r * k_w + k] * (double)dz[r];
+                float d = (float)a;
+                if (m > 0)
+                    d = act[m][k] > 0.f ? d : 0.f; /* ReLU' from the stored activation */
+                dprev[k] = round_h(d);
+            }
+            memcpy(dz, dprev, sizeof(float) * k_w);
+            out_w = k_w;
+        }
+        /* dz now holds dL/dfeatures (K0 values): scatter into the grid, point by point */
+        for (uint32_t p = 0; p < n_points; p++)
+            grid_backward_point(net, offsets, in + (size_t)s * in_dims + 3 * p, dz + p * ppf, gg);
+    }
+    for (uint64_t i = 0; i < n_mlp; i++)
+        grads[i] = (float)wg[i];
+    free(Wf);
+    free(wg);
+    if (loss_sum)
+        *loss_sum = lsum;
+}
+
+/* exponential_decay.h:60-71: the factor is multiplied BEFORE the nested step when step >= decay_start and
+ * (step - decay_start) % decay_interval == 0 */
+float onbvh_learning_rate(const oopt_t *oc, uint32_t step)
+{
+    float factor = 1.f;
+    for (uint32_t s = 0; s <= step; s++)
+        if ((int64_t)s >= oc->decay_start && oc->decay_interval > 0 && ((int64_t)s - oc->decay_start) % oc->decay_interval == 0)
+            factor *= oc->decay_base;
+    return oc->learning_rate * factor;
+}
+
+/* optimizers/adam.h:48-123 with relative/absolute decay 0, no weight clipping, AdaBound off */
+void onbvh_adam_step(const oopt_t *oc, uint32_t step, uint64_t n_params, uint64_t n_matrix, float loss_scale,
+                     const float *grads, float *master, uint16_t *params, float *m, float *v, uint32_t *param_steps)
+{
+    const float base_lr = onbvh_learning_rate(oc, step);
+    for (uint64_t i = 0; i < n_params; i++) {
+        float gradient = round_h(grads[i]) / loss_scale;
+        if (i >= n_matrix && gradient == 0.f)
+            continue;
+        const float w = master[i];
+        if (i < n_matrix)
+            gradient += oc->l2_reg * w;
+        const float g2 = gradient * gradient;
+        const float fm = m[i] = oc->beta1 * m[i] + (1.f - oc->beta1) * gradient;
+        const float sm = v[i] = oc->beta2 * v[i] + (1.f - oc->beta2) * g2;
+        const uint32_t t = ++param_steps[i];
+        float lr = base_lr * (sqrtf(1.f - powf(oc->beta2, (float)t)) / (1.f - powf(oc->beta1, (float)t)));
+        const float eff = lr / (sqrtf(sm) + oc->epsilon);
+        const float nw  = w - eff * fm;
+        master[i] = nw;
+        params[i] = onbvh_f2h(nw);
+    }
+}

@@ -129,6 +129,43 @@ void onbvh_query(const onet_t *net, const float *in, uint32_t n, int mode, float
 /* a11 */
 int onbvh_decode(const oconst_t *c, const float *y, float seg_mint, float seg_maxt, uint32_t depth, float *t_out);
 
+
+/* --- online optimisation (a18-a21) --- */
+/* PathTracingOutputConstants subset driving the composite loss (neural_bvh_module.h:243-274). Loss types:
+ * 0 RelativeL2, 1 L2, 2 RelativeL1, 3 L1, 4 RelativeL2Luminance, 5 BinaryCrossEntropy, 6 LogL2, 7 LHalf */
+typedef struct {
+    uint32_t vis_dim, depth_dim, normal_dim, albedo_dim; /* 1,1,3,3 */
+    uint32_t vis_loss, depth_loss, normal_loss, albedo_loss;
+    float vis_scale, depth_scale, normal_scale, albedo_scale;
+    uint32_t normal_linear, depth_linear, albedo_linear, vis_masking;
+} oloss_t;
+
+typedef struct {
+    float learning_rate;
+    int32_t decay_start, decay_interval;
+    float decay_base, beta1, beta2, epsilon, l2_reg;
+} oopt_t;
+
+/* a18: composite_pt_loss (pt_composite_loss.cuh:19-123) for one output element.  Returns the loss value (already
+ * divided by n_total) and writes the loss-scaled gradient (128 * g / n_total), before any fp16 rounding. */
+float onbvh_loss_element(const oloss_t *lc, const float *target8, float prediction, uint32_t elem, uint32_t n_total,
+                         float loss_scale, float *grad);
+/* a9/a10 forward with stored activations + a18 + a19 + a20: gradients of the loss-scaled objective.
+ * in: B x 9, target: B x 8 (row per sample).  L: B x 16 per-output loss values (may be NULL).
+ * grads: n_params floats, OVERWRITTEN (MLP matrices then grid, same order as the parameters).
+ * Rounding points follow the B200 kernels (fp16 operands, fp32 accumulation): features, hidden activations,
+ * network output, dL/dy, every dZ tile and dL/dfeatures are rounded to fp16; sums are fp32/double.
+ * n_total = global_batch * n_output (data-parallel shards pass the global batch). */
+void onbvh_train_forward_backward(const onet_t *net, const oloss_t *lc, const float *in, const float *target,
+                                  uint32_t batch, uint32_t global_batch, float loss_scale, float *L, float *grads,
+                                  double *loss_sum);
+/* a21: adam_step (optimizers/adam.h:48-123) under ExponentialDecay (exponential_decay.h:60-71).  `step` is the
+ * number of optimiser steps already taken.  Gradients are first rounded to fp16 (tcnn's gradient type) so that the
+ * "gradient == 0 -> skip" rule sees the same underflow. */
+void onbvh_adam_step(const oopt_t *oc, uint32_t step, uint64_t n_params, uint64_t n_matrix, float loss_scale,
+                     const float *grads, float *master, uint16_t *params, float *m, float *v, uint32_t *param_steps);
+float onbvh_learning_rate(const oopt_t *oc, uint32_t step);
+
 /* --- whole primary-ray pipeline (section 9 of SURVEY.md), max_depth = 1 --- */
 typedef struct {
     uint8_t valid_hit; /* 0 none, 1 neural, 2 normal */

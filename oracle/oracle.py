@@ -308,3 +308,96 @@ def render_primary(scene, nbvh_nodes, const, net, pixel_begin, pixel_end, stride
                                C.c_uint32(pixel_end), C.c_uint32(stride), C.c_int(sample_idx), C.c_int(rnd_offset),
                                C.c_int(mlp_mode), _p(hits), cnt, C.c_int(n_threads))
     return hits, [cnt[i] for i in range(4)]
+
+
+# ----------------------------------------------------------------------------- online optimisation
+LOSS_TYPES = ["RelativeL2", "L2", "RelativeL1", "L1", "RelativeL2Luminance", "BinaryCrossEntropy", "LogL2", "LHalf"]
+
+
+class OLoss(C.Structure):
+    _fields_ = [("vis_dim", C.c_uint32), ("depth_dim", C.c_uint32), ("normal_dim", C.c_uint32), ("albedo_dim", C.c_uint32),
+                ("vis_loss", C.c_uint32), ("depth_loss", C.c_uint32), ("normal_loss", C.c_uint32), ("albedo_loss", C.c_uint32),
+                ("vis_scale", C.c_float), ("depth_scale", C.c_float), ("normal_scale", C.c_float), ("albedo_scale", C.c_float),
+                ("normal_linear", C.c_uint32), ("depth_linear", C.c_uint32), ("albedo_linear", C.c_uint32),
+                ("vis_masking", C.c_uint32)]
+
+
+class OOpt(C.Structure):
+    _fields_ = [("learning_rate", C.c_float), ("decay_start", C.c_int32), ("decay_interval", C.c_int32),
+                ("decay_base", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+                ("l2_reg", C.c_float)]
+
+
+def make_loss(cfg):
+    """PathTracingOutputConstants defaults: neural_bvh_module.h:243-274."""
+    pt = cfg.get("neural_bvh_renderer", {}).get("neural_module", {}).get("pt_output_constants", {})
+    lc = OLoss()
+    lc.vis_dim = pt.get("output_visibility_dim", 1)
+    lc.depth_dim = pt.get("output_depth_dim", 1)
+    lc.normal_dim = pt.get("output_normal_dim", 0)
+    lc.albedo_dim = pt.get("output_albedo_dim", 0)
+    lc.vis_loss = LOSS_TYPES.index(pt.get("visibility_loss", "BinaryCrossEntropy"))
+    lc.depth_loss = LOSS_TYPES.index(pt.get("depth_loss", "L1"))
+    lc.normal_loss = LOSS_TYPES.index(pt.get("normal_loss", "L1"))
+    lc.albedo_loss = LOSS_TYPES.index(pt.get("albedo_loss", "RelativeL2"))
+    lc.vis_scale = pt.get("visibility_loss_scale", 1.0)
+    lc.depth_scale = pt.get("depth_loss_scale", 1.0)
+    lc.normal_scale = pt.get("normal_loss_scale", 1.0)
+    lc.albedo_scale = pt.get("albedo_loss_scale", 1.0)
+    lc.normal_linear = int(pt.get("output_normal_linear_activation", True))
+    lc.depth_linear = int(pt.get("output_depth_linear_activation", False))
+    lc.albedo_linear = int(pt.get("output_albedo_linear_activation", False))
+    lc.vis_masking = int(pt.get("visibility_masking_loss", True))
+    return lc
+
+
+def make_opt(cfg):
+    op = cfg.get("neural_bvh_renderer", {}).get("neural_module", {}).get("optimizer", {})
+    return OOpt(op.get("learning_rate", 1e-2), op.get("decay_start", 10000), op.get("decay_interval", 2000),
+                op.get("decay_base", 0.33), op.get("beta1", 0.9), op.get("beta2", 0.999), op.get("epsilon", 1e-8),
+                op.get("l2_reg", 1e-8))
+
+
+class Trainer:
+    """CPU restatement of tcnn::Trainer + Adam/ExponentialDecay around the oracle network (fp32 master weights,
+    fp16 parameters, per-parameter step counters; trainer.h:68-87, optimizers/adam.h:48-123)."""
+
+    def __init__(self, cfg, params_bits):
+        self.cfg = cfg
+        self.params = np.ascontiguousarray(params_bits, dtype=np.uint16).copy()
+        self.net = make_net(cfg, self.params)
+        self.params = self.net._keep  # the array the C side reads
+        self.loss_c = make_loss(cfg)
+        self.opt_c = make_opt(cfg)
+        n = self.params.size
+        self.master = self.params.view(np.float16).astype(np.float32)
+        self.m = np.zeros(n, np.float32)
+        self.v = np.zeros(n, np.float32)
+        self.param_steps = np.zeros(n, np.uint32)
+        self.grads = np.zeros(n, np.float32)
+        self.step = 0
+        self.n_matrix = (self.net.n_neurons * self.net.n_input + (self.net.n_hidden_layers - 1) * self.net.n_neurons ** 2 +
+                         self.net.n_output_padded * self.net.n_neurons)
+        self.loss_scale = 128.0
+
+    def forward_backward(self, x, target, global_batch=None):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        target = np.ascontiguousarray(target, dtype=np.float32)
+        b = x.shape[0]
+        L = np.zeros((b, self.net.n_output_padded), np.float32)
+        s = C.c_double(0)
+        lib().onbvh_train_forward_backward(C.byref(self.net), C.byref(self.loss_c), _p(x), _p(target), C.c_uint32(b),
+                                           C.c_uint32(global_batch or b), C.c_float(self.loss_scale), _p(L), _p(self.grads),
+                                           C.byref(s))
+        return L, s.value
+
+    def optimizer_step(self):
+        lib().onbvh_adam_step(C.byref(self.opt_c), C.c_uint32(self.step), C.c_uint64(self.params.size),
+                              C.c_uint64(self.n_matrix), C.c_float(self.loss_scale), _p(self.grads), _p(self.master),
+                              _p(self.params), _p(self.m), _p(self.v), _p(self.param_steps))
+        self.step += 1
+
+    def training_step(self, x, target):
+        L, loss = self.forward_backward(x, target)
+        self.optimizer_step()
+        return L, loss
