@@ -332,6 +332,9 @@ int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint
 int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch,
                                    uint32_t global_batch, float *per_sample_loss, float *loss_sum_dev, void *stream);
 float *nbvh_gradients(nbvh_ctx *ctx);
+/* Lets the host own the fp32 gradient vector (n_params floats of device memory; NULL -> back to the internal buffer), so
+ * the process that drives NCCL can allreduce it in place without a copy. */
+int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);
 

@@ -142,6 +142,7 @@ SYMBOLS = {
     "nbvh_training_step": (_i, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_f), _vp]),
     "nbvh_training_forward_backward": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_gradients": (_vp, [_vp]),
+    "nbvh_set_gradient_buffer": (_i, [_vp, _vp]),
     "nbvh_optimizer_step": (_i, [_vp, _vp]),
     "nbvh_training_step_count": (_u32, [_vp]),
 }

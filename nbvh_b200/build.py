@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnbvh_b200.so")
-SOURCES = ["context.cu", "kernels.cu"]
+SOURCES = ["context.cu", "kernels.cu", "training.cu"]
 HEADERS = ["device_core.cuh", "mlp_tile.cuh", "kernels.cuh", "json_min.hpp", "../../include/nbvh_b200.h"]
 
 NVCC_FLAGS = [

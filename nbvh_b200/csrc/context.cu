@@ -256,8 +256,16 @@ struct nbvh_ctx {
     float total_ms = 0.f;
     uint32_t launches = 0;
 
-    // training buffers (allocated lazily)
-    float *d_grads = nullptr;
+    // training state (allocated lazily): tcnn::Trainer's buffers (trainer.h:68-87) + Adam moments and step counters
+    float *d_grads = nullptr, *d_master = nullptr, *d_m = nullptr, *d_v = nullptr;
+    uint32_t *d_steps = nullptr;
+    uint8_t *d_feat = nullptr, *d_dfeat = nullptr;
+    uint32_t feat_capacity = 0; // samples
+    float *d_loss = nullptr;
+    float *own_grads = nullptr; // internal gradient buffer (d_grads may point at a host-owned one instead)
+    bool train_state_valid = false;
+    uint32_t opt_step = 0;    // optimiser steps since the state was (re)initialised (tcnn: optimizer->step())
+    float lr_factor   = 1.f;  // ExponentialDecay's running factor
 };
 
 namespace {
@@ -330,10 +338,15 @@ int rebuild_layout(nbvh_ctx *ctx)
         cudaFree(ctx->d_wimg);
     ctx->d_params = nullptr, ctx->d_wimg = nullptr;
     ctx->params_loaded = false;
+    cudaFree(ctx->own_grads), cudaFree(ctx->d_master), cudaFree(ctx->d_m), cudaFree(ctx->d_v), cudaFree(ctx->d_steps);
+    ctx->d_grads = ctx->own_grads = ctx->d_master = ctx->d_m = ctx->d_v = nullptr;
+    ctx->d_steps = nullptr;
+    ctx->train_state_valid = false;
     CU_TRY(ctx, cudaMalloc(&ctx->d_params, ctx->n_params * sizeof(uint16_t)));
     CU_TRY(ctx, cudaMemset(ctx->d_params, 0, ctx->n_params * sizeof(uint16_t)));
     CU_TRY(ctx, cudaMalloc(&ctx->d_wimg, ctx->wimg_bytes));
     CU_TRY(ctx, configure_kernels(ctx->wimg_bytes, ctx->in_k));
+    CU_TRY(ctx, configure_training(ctx->wimg_bytes, ctx->in_k, ctx->n_layers));
     return NBVH_OK;
 }
 
@@ -534,7 +547,14 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_grads);
+    cudaFree(ctx->own_grads);
+    cudaFree(ctx->d_master);
+    cudaFree(ctx->d_m);
+    cudaFree(ctx->d_v);
+    cudaFree(ctx->d_steps);
+    cudaFree(ctx->d_feat);
+    cudaFree(ctx->d_dfeat);
+    cudaFree(ctx->d_loss);
     if (ctx->ev0)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
@@ -955,6 +975,7 @@ int nbvh_load_params_host(nbvh_ctx *ctx, const uint16_t *fp16, uint64_t n)
     if (rc != NBVH_OK)
         return rc;
     ctx->params_loaded = true;
+    ctx->train_state_valid = false; // fp32 master copy, Adam moments and step counters restart from these parameters
     return NBVH_OK;
 }
 
@@ -1287,17 +1308,152 @@ int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
     return NBVH_OK;
 }
 
-// ---- online optimisation (implemented in training.cu once the row lands) --------------------------------------
-int nbvh_training_step(nbvh_ctx *ctx, const float *, const float *, uint32_t, float *, float *, void *)
+// ---- online optimisation -------------------------------------------------------------------------------------
+static int ensure_training_state(nbvh_ctx *ctx, uint32_t batch, cudaStream_t st)
 {
-    return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet");
+    if (!ctx->params_loaded)
+        return fail(ctx, NBVH_ERR_STATE, "network parameters not loaded (nbvh_init_params / nbvh_load_network_file)");
+    // TMEM budget of k_train_mlp: working accumulators + one fp32 accumulator per weight matrix
+    if (192u + ctx->in_k + (ctx->n_layers - 2u) * kNeurons + kOutPadded > 512u)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "network too deep/wide for the TMEM-resident weight-gradient accumulators");
+    const size_t n = ctx->n_params;
+    if (!ctx->d_grads) {
+        CU_TRY(ctx, cudaMalloc(&ctx->own_grads, n * sizeof(float)));
+        ctx->d_grads = ctx->own_grads;
+    }
+    if (!ctx->d_master) {
+        CU_TRY(ctx, cudaMalloc(&ctx->d_master, n * sizeof(float)));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_m, n * sizeof(float)));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_v, n * sizeof(float)));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_steps, n * sizeof(uint32_t)));
+        ctx->train_state_valid = false;
+    }
+    if (!ctx->d_loss)
+        CU_TRY(ctx, cudaMalloc(&ctx->d_loss, sizeof(float)));
+    if (!ctx->train_state_valid) {
+        CU_TRY(ctx, launch_half_to_float(ctx->d_params, ctx->d_master, n, st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_m, 0, n * sizeof(float), st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_v, 0, n * sizeof(float), st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_steps, 0, n * sizeof(uint32_t), st));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_grads, 0, n * sizeof(float), st));
+        ctx->opt_step = 0, ctx->lr_factor = 1.f;
+        ctx->train_state_valid = true;
+    }
+    const uint32_t padded = (batch + kTileRows - 1u) / kTileRows * kTileRows;
+    if (padded > ctx->feat_capacity) {
+        cudaFree(ctx->d_feat), cudaFree(ctx->d_dfeat);
+        ctx->d_feat = ctx->d_dfeat = nullptr, ctx->feat_capacity = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_feat, (size_t)padded * ctx->in_k * 2u));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_dfeat, (size_t)padded * ctx->in_k * 2u));
+        ctx->feat_capacity = padded;
+    }
+    return NBVH_OK;
 }
-int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *, const float *, uint32_t, uint32_t, float *, float *, void *)
+
+int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch, uint32_t global_batch,
+                                   float *per_sample_loss, float *loss_sum_dev, void *stream)
 {
-    return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet");
+    if (!ctx || !in || !target || batch == 0)
+        return ctx ? fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_training_forward_backward: null input or empty batch") : NBVH_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_ready(ctx, false, false, true);
+    if (rc == NBVH_OK)
+        rc = ensure_training_state(ctx, batch, st);
+    if (rc != NBVH_OK)
+        return rc;
+    if (global_batch < batch)
+        global_batch = batch;
+    const NetConst nc = make_net_const(ctx);
+    float *loss_dev   = loss_sum_dev ? loss_sum_dev : ctx->d_loss;
+    // GradientMode::Overwrite (trainer.h:171): every call starts from zero gradients
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_grads, 0, ctx->n_params * sizeof(float), st));
+    CU_TRY(ctx, cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
+    KernelTimer kt(ctx, st);
+    CU_TRY(ctx, launch_encode_features(nc, in, batch, ctx->module_const.input_network_dims, ctx->d_feat, ctx->num_sms, st));
+    TrainParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.feat = ctx->d_feat, tp.dfeat = ctx->d_dfeat, tp.target = target, tp.per_sample_loss = per_sample_loss;
+    tp.wgrad = ctx->d_grads, tp.loss_sum = loss_dev, tp.batch = batch;
+    tp.n_total    = global_batch * ctx->pt_const.output_network_dims;
+    tp.loss_scale = 128.f; // default_loss_scale<__half>() (ext/tiny-cuda-nn common.h:232)
+    const nbvh_pt_output_constants &pc = ctx->pt_const;
+    tp.loss.vis_dim = pc.output_visibility_dim, tp.loss.depth_dim = pc.output_depth_dim;
+    tp.loss.normal_dim = pc.output_normal_dim, tp.loss.albedo_dim = pc.output_albedo_dim;
+    tp.loss.vis_loss = pc.visibility_loss, tp.loss.depth_loss = pc.depth_loss;
+    tp.loss.normal_loss = pc.normal_loss, tp.loss.albedo_loss = pc.albedo_loss;
+    tp.loss.vis_scale = pc.visibility_loss_scale, tp.loss.depth_scale = pc.depth_loss_scale;
+    tp.loss.normal_scale = pc.normal_loss_scale, tp.loss.albedo_scale = pc.albedo_loss_scale;
+    tp.loss.normal_linear = pc.output_normal_linear_activation, tp.loss.depth_linear = pc.output_depth_linear_activation;
+    tp.loss.albedo_linear = pc.output_albedo_linear_activation, tp.loss.vis_masking = pc.visibility_masking_loss;
+    CU_TRY(ctx, launch_train_mlp(nc, tp, ctx->num_sms, st));
+    CU_TRY(ctx, launch_grid_backward(nc, in, ctx->d_dfeat, batch, ctx->module_const.input_network_dims, ctx->d_grads + ctx->n_mlp_params,
+                                     ctx->num_sms, st));
+    kt.stop();
+    return NBVH_OK;
 }
+
 float *nbvh_gradients(nbvh_ctx *ctx) { return ctx ? ctx->d_grads : nullptr; }
-int nbvh_optimizer_step(nbvh_ctx *ctx, void *) { return fail(ctx, NBVH_ERR_UNSUPPORTED, "training step not built yet"); }
+
+int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    if (grads) {
+        ctx->d_grads = grads;
+    } else {
+        if (!ctx->own_grads)
+            CU_TRY(ctx, cudaMalloc(&ctx->own_grads, ctx->n_params * sizeof(float)));
+        ctx->d_grads = ctx->own_grads;
+    }
+    return NBVH_OK;
+}
+
+int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->train_state_valid || !ctx->d_grads)
+        return fail(ctx, NBVH_ERR_STATE, "nbvh_optimizer_step before nbvh_training_forward_backward");
+    cudaStream_t st = (cudaStream_t)stream;
+    // ExponentialDecayOptimizer::step (exponential_decay.h:60-71)
+    const nbvh_optimizer_desc &o = ctx->opt_desc;
+    if (ctx->opt_step == 0)
+        ctx->lr_factor = 1.f;
+    if ((int64_t)ctx->opt_step >= o.decay_start && o.decay_interval > 0 &&
+        ((int64_t)ctx->opt_step - o.decay_start) % o.decay_interval == 0)
+        ctx->lr_factor *= o.decay_base;
+    AdamParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.n_params = ctx->n_params, ap.n_matrix = ctx->n_mlp_params;
+    ap.loss_scale = 128.f, ap.lr = o.learning_rate * ctx->lr_factor;
+    ap.beta1 = o.beta1, ap.beta2 = o.beta2, ap.epsilon = o.epsilon, ap.l2_reg = o.l2_reg;
+    ap.grads = ctx->d_grads, ap.master = ctx->d_master, ap.m = ctx->d_m, ap.v = ctx->d_v, ap.steps = ctx->d_steps;
+    ap.params = reinterpret_cast<__half *>(ctx->d_params), ap.wimg = ctx->d_wimg;
+    ap.in_k = ctx->in_k, ap.n_layers = ctx->n_layers;
+    for (uint32_t l = 0; l < ctx->n_layers; l++)
+        ap.layer_off[l] = ctx->layer_off[l];
+    CU_TRY(ctx, launch_adam(ap, st));
+    ctx->opt_step++;
+    ctx->training_step++;
+    return NBVH_OK;
+}
+
+int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch, float *per_sample_loss, float *loss_host,
+                       void *stream)
+{
+    int rc = nbvh_training_forward_backward(ctx, in, target, batch, batch, per_sample_loss, nullptr, stream);
+    if (rc != NBVH_OK)
+        return rc;
+    rc = nbvh_optimizer_step(ctx, stream);
+    if (rc != NBVH_OK)
+        return rc;
+    if (loss_host) { // == trainer->loss(stream, *ctx): one scalar back to the host
+        CU_TRY(ctx, cudaMemcpyAsync(loss_host, ctx->d_loss, sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    return NBVH_OK;
+}
+
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx) { return ctx ? ctx->training_step : 0; }
 
 } // extern "C"

@@ -64,6 +64,47 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t wimg_bytes, uint32_t 
     return s;
 }
 
+// ---- online optimisation (training.cu)
+struct LossConst { // PathTracingOutputConstants subset read by the composite loss
+    uint32_t vis_dim, depth_dim, normal_dim, albedo_dim;
+    uint32_t vis_loss, depth_loss, normal_loss, albedo_loss;
+    float vis_scale, depth_scale, normal_scale, albedo_scale;
+    uint32_t normal_linear, depth_linear, albedo_linear, vis_masking;
+};
+
+struct TrainParams {
+    const uint8_t *feat;    // fp16 feature tiles, tile-canonical layout (one 128 x in_k K-major operand block per tile)
+    uint8_t *dfeat;         // fp16 dL/dfeatures, same layout
+    const float *target;    // batch x n_out
+    float *per_sample_loss; // batch x 16 (ctx.L of tcnn) or nullptr
+    float *wgrad;           // fp32 gradients of the MLP matrices (accumulated with atomics)
+    float *loss_sum;        // device accumulator of the batch loss
+    uint32_t batch, n_total;
+    float loss_scale;
+    LossConst loss;
+};
+
+struct AdamParams {
+    uint64_t n_params, n_matrix;
+    float loss_scale, lr, beta1, beta2, epsilon, l2_reg;
+    const float *grads;
+    float *master, *m, *v;
+    uint32_t *steps;
+    __half *params;
+    uint8_t *wimg;
+    uint32_t in_k, n_layers;
+    uint32_t layer_off[kMaxLayers];
+};
+
+cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_layers);
+cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t batch, uint32_t n_in_dims, uint8_t *feat, int num_sms,
+                                   cudaStream_t stream);
+cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_sms, cudaStream_t stream);
+cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint8_t *dfeat, uint32_t batch, uint32_t n_in_dims,
+                                 float *grid_grads, int num_sms, cudaStream_t stream);
+cudaError_t launch_adam(const AdamParams &ap, cudaStream_t stream);
+cudaError_t launch_half_to_float(const void *src, float *dst, uint64_t n, cudaStream_t stream);
+
 cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32_t n, uint32_t n_in_dims,
                          unsigned long long *counters, int num_sms, cudaStream_t stream);
 cudaError_t launch_trace_intervals(const NbvhConst &bc, const float *o, const float *d, uint32_t n, uint32_t max_intervals,

@@ -1,0 +1,689 @@
+// training.cu -- the online-optimisation step of the neural ray-query path for sm_100a.
+//
+// Replaces tcnn::Trainer::training_step on the reference's model (ext/tiny-cuda-nn trainer.h:163-190):
+//   k_encode_features  grid forward for a training batch: 9 x B inputs -> 96-wide fp16 feature tiles          (K3 x3)
+//   k_train_mlp        per 128-sample tile, on tcgen05/TMEM: forward with the hidden activations kept in shared
+//                      memory, composite loss + gradient, dgrad chain, and the five weight-gradient GEMMs whose fp32
+//                      accumulators stay resident in TMEM across all tiles of the CTA                     (K11,K12,K13)
+//   k_grid_backward    scatter of dL/dfeatures into the fp32 grid-gradient table: shared-memory privatised for the
+//                      small dense levels, vector reductions (REDG.E.ADD.F32x4) for the rest                  (K14 x3)
+//   k_adam             Adam under ExponentialDecay with tcnn's per-parameter step counters and zero-gradient skip;
+//                      also refreshes the fp16 parameters and the packed tensor-core weight image            (K15)
+// (kernel numbers: SURVEY.md section 2.4; /root/reference/ext/tiny-cuda-nn/include/tiny-cuda-nn/encodings/grid.h:49-320,
+//  src/fully_fused_mlp.cu:151-259,736-836, include/tiny-cuda-nn/optimizers/adam.h:48-123,
+//  /root/reference/include/cuda/neural/utils/pt_composite_loss.cuh:19-123.)
+//
+// Numerics: fp16 operands, fp32 accumulation everywhere (tcnn accumulates in fp16); gradients carry tcnn's loss scale
+// of 128 and are rounded to fp16 only at the point where tcnn stores them, so Adam's "gradient == 0 -> skip" rule sees
+// the same underflow.
+#include "kernels.cuh"
+
+#include <cuda_fp16.h>
+
+namespace nbvh {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float h2f_round(float x) { return __half2float(__float2half_rn(x)); }
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Positions, weights and entry indices of one (point, level): identical arithmetic to grid_level_features
+struct GridCorner {
+    uint32_t index[8];
+    float weight[8];
+};
+
+__device__ __forceinline__ void grid_corners(const GridLevel &L, float x, float y, float z, GridCorner &gc)
+{
+    float px = __fmaf_rn(L.scale, x, 0.5f), py = __fmaf_rn(L.scale, y, 0.5f), pz = __fmaf_rn(L.scale, z, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    px = __fsub_rn(px, fx), py = __fsub_rn(py, fy), pz = __fsub_rn(pz, fz);
+    const float qx = __fsub_rn(1.f, px), qy = __fsub_rn(1.f, py), qz = __fsub_rn(1.f, pz);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t cx = gx + (c & 1), cy = gy + ((c >> 1) & 1), cz = gz + ((c >> 2) & 1);
+        uint32_t index;
+        if (L.dense)
+            index = cx + cy * L.res + cz * L.res * L.res;
+        else
+            index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+        gc.index[c] = L.mask ? (index & L.mask) : (index % L.size);
+        float w     = (c & 1) ? px : qx;
+        w           = __fmul_rn(w, (c & 2) ? py : qy);
+        gc.weight[c] = __fmul_rn(w, (c & 4) ? pz : qz);
+    }
+}
+
+// byte offset of the 8-byte (point, level) slot j of sample s in the tile-canonical feature layout
+__device__ __forceinline__ size_t feat_slot_offset(uint32_t s, uint32_t j, uint32_t in_k)
+{
+    const uint32_t tile = s >> 7, row = s & 127u;
+    return (size_t)tile * (kTileRows * in_k * 2u) + tile_chunk_off(row, j >> 1, in_k) + (j & 1u) * 8u;
+}
+
+// ------------------------------------------------------------------------------------------------ k_encode_features
+// One thread per (sample, point, level).  Lanes are ordered so that 16 consecutive lanes write one 128-byte core
+// matrix of the tile (8 rows x {even, odd} slot): coalesced stores, 8 independent 8-byte gathers in flight per thread.
+__global__ void __launch_bounds__(256)
+k_encode_features(const __grid_constant__ NetConst nc, const float *__restrict__ in, uint32_t batch, uint32_t padded_batch,
+                  uint32_t n_in_dims, uint8_t *__restrict__ feat)
+{
+    const uint32_t slots = nc.in_k >> 2; // (point, level) slots per sample
+    const uint64_t total = (uint64_t)padded_batch * slots;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        // i -> (row group of 8 samples, slot pair, row in group, slot parity)
+        const uint32_t pairs = slots >> 1;
+        const uint32_t lo    = (uint32_t)(i & 15u);
+        const uint64_t hi    = i >> 4;
+        const uint32_t pair  = (uint32_t)(hi % pairs);
+        const uint32_t rgrp  = (uint32_t)(hi / pairs);
+        const uint32_t s     = rgrp * 8u + (lo >> 1);
+        const uint32_t j     = pair * 2u + (lo & 1u);
+        uint2 f              = make_uint2(0u, 0u);
+        if (s < batch) {
+            const uint32_t p = j / nc.n_levels, l = j % nc.n_levels;
+            const float *x   = in + (size_t)s * n_in_dims + 3u * p;
+            f                = grid_level_features(nc.grid, nc.lv[l], __ldg(x), __ldg(x + 1), __ldg(x + 2));
+        }
+        *reinterpret_cast<uint2 *>(feat + feat_slot_offset(s, j, nc.in_k)) = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ composite loss (a18)
+__device__ __forceinline__ void loss_and_gradient(float target, float prediction, uint32_t type, float &loss, float &grad)
+{
+    const float diff = prediction - target;
+    switch (type) {
+    case 0: { // RelativeL2
+        const float denom = prediction * prediction + 1e-2f;
+        loss = diff * diff / denom, grad = 2.0f * diff / denom;
+        break;
+    }
+    case 3: // L1
+        loss = fabsf(diff), grad = copysignf(1.0f, diff);
+        break;
+    case 2: { // RelativeL1
+        const float scale = 1.0f / (fabsf(prediction) + 1e-2f);
+        loss = fabsf(diff) * scale, grad = copysignf(scale, diff);
+        break;
+    }
+    case 5: { // BinaryCrossEntropy
+        const float eps  = 1e-5f;
+        const float pred = fminf(fmaxf(prediction, eps), 1.f - eps);
+        loss = -(target * logf(pred) + (1.f - target) * logf(1.f - pred));
+        grad = -(target - pred) / (pred - (pred * pred));
+        break;
+    }
+    case 6: { // LogL2
+        const float d = logf(1.f + prediction) - logf(1.f + target);
+        loss = d * d, grad = 2.0f * d / (prediction + 1.f);
+        break;
+    }
+    case 7: { // LHalf
+        const float s = sqrtf(fabsf(diff));
+        loss = s, grad = 1.f / (2.f * s + 1e-5f);
+        break;
+    }
+    default: // L2
+        loss = diff * diff, grad = 2.0f * diff;
+        break;
+    }
+}
+
+// pt_composite_loss.cuh:19-123 for output element `e` of one sample; returns loss / n_total, grad = scale*g/n_total
+__device__ __forceinline__ float loss_element(const LossConst &lc, const float *tgt, float prediction, uint32_t e, float n_total,
+                                              float loss_scale, float &grad_out)
+{
+    const uint32_t depth0 = lc.vis_dim, normal0 = depth0 + lc.depth_dim, albedo0 = normal0 + lc.normal_dim,
+                   end = albedo0 + lc.albedo_dim;
+    float loss = 0.f, grad = 0.f;
+    if (e < end) {
+        const float target = tgt[e];
+        const bool ignore  = lc.vis_masking ? (tgt[0] < 0.5f) : false;
+        if (lc.vis_dim > 0 && e == 0) {
+            loss_and_gradient(target, prediction, lc.vis_loss, loss, grad);
+            loss *= lc.vis_scale, grad *= lc.vis_scale;
+        } else if (!ignore && e >= depth0 && e < normal0) {
+            loss_and_gradient(target, prediction, lc.depth_loss, loss, grad);
+            if (lc.depth_linear)
+                grad *= (lc.depth_loss == 1u || lc.depth_loss == 0u) ? 100.f : 10.f;
+            loss *= lc.depth_scale, grad *= lc.depth_scale;
+        } else if (!ignore && e >= normal0 && e < albedo0) {
+            if (lc.normal_linear) {
+                const float n_length = 0.1f;
+                const float lin      = ((prediction * 2.f - 1.f) / n_length) * 0.5f + 0.5f;
+                loss_and_gradient(target, lin, lc.normal_loss, loss, grad);
+                grad *= 1.f / n_length;
+            } else {
+                loss_and_gradient(target, prediction, lc.normal_loss, loss, grad);
+            }
+            loss *= lc.normal_scale, grad *= lc.normal_scale;
+        } else if (!ignore && e >= albedo0 && e < end) {
+            if (lc.albedo_linear) {
+                const float n_length = 0.1f;
+                loss_and_gradient(target, prediction / n_length, lc.albedo_loss, loss, grad);
+                grad *= 1.f / n_length;
+            } else {
+                loss_and_gradient(target, prediction, lc.albedo_loss, loss, grad);
+            }
+            loss *= lc.albedo_scale, grad *= lc.albedo_scale;
+        }
+    }
+    grad_out = loss_scale * grad / n_total;
+    return loss / n_total;
+}
+
+// ------------------------------------------------------------------------------------------------ k_train_mlp
+// UMMA descriptor of an MN-major no-swizzle operand: 16-byte rows hold 8 MN-contiguous elements, a core matrix is 8
+// such rows along K; SBO = byte stride between 8-element groups along MN, LBO = byte stride between 8-row groups along K.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t k_group_stride, uint32_t mn_group_stride)
+{
+    return umma_desc(smem_addr, k_group_stride, mn_group_stride);
+}
+
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t m, uint32_t n, uint32_t a_mn, uint32_t b_mn)
+{
+    return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// TMEM column map of the training kernel (512 columns allocated, fp32)
+constexpr uint32_t kColZ   = 0;   // 128 x 64 working accumulator (forward pre-activations / dgrad)
+constexpr uint32_t kColDA0 = 64;  // 128 x in_k (<= 128) dL/dfeatures
+constexpr uint32_t kColDW  = 192; // weight-gradient accumulators: layer 0 (64 x in_k), hidden (64 x 64 each), last (64 x 16, transposed)
+
+struct TrainSmem {
+    uint32_t w_off, a0_off, h_off, dz_off, dzo_off, bar_off, tmem_off, total;
+};
+
+__host__ __device__ inline TrainSmem train_smem_layout(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_hidden)
+{
+    TrainSmem s;
+    s.w_off    = 0;
+    s.a0_off   = (wimg_bytes + 127u) & ~127u;
+    s.h_off    = s.a0_off + kTileRows * in_k * 2u;
+    s.dz_off   = s.h_off + n_hidden * kTileRows * kNeurons * 2u;
+    s.dzo_off  = s.dz_off + kTileRows * kNeurons * 2u;
+    s.bar_off  = s.dzo_off + kTileRows * kOutPadded * 2u;
+    s.tmem_off = s.bar_off + 32u;
+    s.total    = s.tmem_off + 16u;
+    return s;
+}
+
+__global__ void __launch_bounds__(kTileRows, 1)
+k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainParams tp)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t n_hidden = nc.n_layers - 1u;
+    const TrainSmem lay     = train_smem_layout(nc.wimg_bytes, nc.in_k, n_hidden);
+    const uint32_t row      = threadIdx.x;
+    const uint32_t warp     = row >> 5, lane = row & 31u;
+    const uint32_t bar_mma  = smem_u32(smem + lay.bar_off);
+    const uint32_t bar_w    = bar_mma + 8u;
+    const uint32_t bar_feat = bar_mma + 16u;
+
+    if (row == 0) {
+        mbar_init(bar_mma, 1u);
+        mbar_init(bar_w, 1u);
+        mbar_init(bar_feat, 1u);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (row == 0) {
+        mbar_expect_tx(bar_w, nc.wimg_bytes);
+        tma_bulk_g2s(smem_u32(smem + lay.w_off), nc.wimg, nc.wimg_bytes, bar_w);
+    }
+    if (warp == 0)
+        tmem_alloc(smem_u32(smem + lay.tmem_off), 512u);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem      = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
+    const uint32_t lane_base = (row & ~31u) << 16;
+    mbar_wait(bar_w, 0u);
+
+    const uint32_t w_smem   = smem_u32(smem + lay.w_off);
+    uint8_t *a0_tile        = smem + lay.a0_off;
+    const uint32_t a0_addr  = smem_u32(a0_tile);
+    uint8_t *dz_tile        = smem + lay.dz_off;
+    const uint32_t dz_addr  = smem_u32(dz_tile);
+    uint8_t *dzo_tile       = smem + lay.dzo_off;
+    const uint32_t dzo_addr = smem_u32(dzo_tile);
+    const uint32_t tile_bytes = kTileRows * nc.in_k * 2u;
+    const uint32_t rg_a0    = (nc.in_k >> 3) * 128u;            // row-group stride of the feature tile
+    const uint32_t rg_h     = (uint32_t)(kNeurons >> 3) * 128u; // ... of the 64-wide tiles
+    const uint32_t rg_o     = (uint32_t)(kOutPadded >> 3) * 128u;
+    const float n_total_f   = (float)tp.n_total;
+
+    uint32_t mma_phase = 0u, feat_phase = 0u;
+    uint32_t first_tile = 1u;
+    float loss_acc      = 0.f;
+
+    const uint32_t n_tiles = (tp.batch + kTileRows - 1u) / kTileRows;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- feature tile: one TMA bulk copy (the previous tile's MMAs that read a0 have completed: their commit was waited on)
+        if (row == 0) {
+            mbar_expect_tx(bar_feat, tile_bytes);
+            tma_bulk_g2s(a0_addr, tp.feat + (size_t)tile * tile_bytes, tile_bytes, bar_feat);
+        }
+        const uint32_t s  = tile * kTileRows + row;
+        const bool valid  = s < tp.batch;
+        float tgt[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j)
+            tgt[j] = (valid && j < nc.n_out) ? __ldg(tp.target + (size_t)s * nc.n_out + j) : 0.f;
+        mbar_wait(bar_feat, feat_phase);
+        feat_phase ^= 1u;
+
+        // ================= forward: activations of every layer stay in shared memory
+        uint32_t k_in = nc.in_k, a_addr = a0_addr;
+        float y[8];
+        for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
+            const bool last      = layer + 1u == nc.n_layers;
+            const uint32_t n_out = last ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+            tc_fence_before_sync();
+            __syncthreads();
+            if (row == 0) {
+                tc_fence_after_sync();
+                const uint32_t sbo   = (k_in >> 3) * 128u;
+                const uint32_t idesc = umma_idesc(128u, n_out, 0u, 0u);
+                const uint32_t w_l   = w_smem + nc.layer_off[layer];
+                for (uint32_t k = 0; k < k_in; k += 16u)
+                    umma_f16(tmem + kColZ, umma_desc(a_addr + (k >> 3) * 128u, kLBO, sbo), umma_desc(w_l + (k >> 3) * 128u, kLBO, sbo),
+                             idesc, k > 0u ? 1u : 0u);
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after_sync();
+            if (!last) {
+                uint8_t *h_tile = smem + lay.h_off + layer * (kTileRows * kNeurons * 2u);
+#pragma unroll
+                for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + kColZ + lane_base + c0, v);
+                    tmem_ld_wait();
+                    uint32_t h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __half2 p = __floats2half2_rn(fmaxf(__uint_as_float(v[2 * i]), 0.f), fmaxf(__uint_as_float(v[2 * i + 1]), 0.f));
+                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                    }
+                    *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
+                }
+                fence_proxy_async_smem();
+                a_addr = smem_u32(h_tile);
+                k_in   = kNeurons;
+            } else {
+                uint32_t v[16];
+                tmem_ld16(tmem + kColZ + lane_base, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) // the training forward hands fp16 predictions to the loss (trainer.h:108-131)
+                    y[i] = h2f_round(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[i]))));
+            }
+        }
+        // ================= loss + output-activation backward -> dZ_out tile (128 x 16 fp16, loss-scaled)
+        {
+            float dz[8];
+            float lrow = 0.f;
+#pragma unroll
+            for (uint32_t e = 0; e < 8; ++e) {
+                float g       = 0.f;
+                const float l = (valid && e < nc.n_out) ? loss_element(tp.loss, tgt, y[e], e, n_total_f, tp.loss_scale, g) : 0.f;
+                if (tp.per_sample_loss && valid)
+                    tp.per_sample_loss[(size_t)s * kOutPadded + e] = l;
+                lrow += l;
+                g     = valid ? h2f_round(g) : 0.f;
+                dz[e] = g * (y[e] * (1.f - y[e])); // sigmoid' from the output value
+            }
+            if (tp.per_sample_loss && valid) {
+#pragma unroll
+                for (uint32_t e = 8; e < (uint32_t)kOutPadded; ++e)
+                    tp.per_sample_loss[(size_t)s * kOutPadded + e] = 0.f;
+            }
+            loss_acc += lrow;
+            uint32_t h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __half2 p = __floats2half2_rn(dz[2 * i], dz[2 * i + 1]);
+                h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+            }
+            *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 0u, kOutPadded)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 1u, kOutPadded)) = make_uint4(0u, 0u, 0u, 0u);
+            fence_proxy_async_smem();
+        }
+        // ================= backward: for layer = last .. 0:  dW_layer += dZ^T A_{layer-1};  dA_{layer-1} = dZ W_layer
+        uint32_t cur_dz_addr = dzo_addr, cur_rg = rg_o, cur_n = kOutPadded; // dZ of the layer being processed
+        uint32_t dw_col      = kColDW + nc.in_k + (n_hidden - 1u) * kNeurons; // accumulator of the last layer
+        for (int layer = (int)nc.n_layers - 1; layer >= 0; --layer) {
+            const bool last        = layer + 1 == (int)nc.n_layers;
+            const uint32_t kin     = layer == 0 ? nc.in_k : (uint32_t)kNeurons;
+            const uint32_t in_addr = layer == 0 ? a0_addr : smem_u32(smem + lay.h_off + (uint32_t)(layer - 1) * (kTileRows * kNeurons * 2u));
+            const uint32_t in_rg   = layer == 0 ? rg_a0 : rg_h;
+            tc_fence_before_sync();
+            __syncthreads();
+            if (row == 0) {
+                tc_fence_after_sync();
+                // ---- weight gradient, K = the 128 samples of the tile (8 steps of 16), both operands MN-major
+                if (last) {
+                    // transposed: D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
+                    const uint32_t idesc = umma_idesc(64u, kOutPadded, 1u, 1u);
+                    for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
+                        umma_f16(tmem + dw_col, umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u),
+                                 umma_desc_mn(cur_dz_addr + ks * 2u * cur_rg, cur_rg, 128u), idesc, (first_tile && ks == 0u) ? 0u : 1u);
+                } else {
+                    // D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
+                    const uint32_t idesc = umma_idesc(64u, kin, 1u, 1u);
+                    for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
+                        umma_f16(tmem + dw_col, umma_desc_mn(cur_dz_addr + ks * 2u * cur_rg, cur_rg, 128u),
+                                 umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u), idesc, (first_tile && ks == 0u) ? 0u : 1u);
+                }
+                // ---- data gradient: D[128 x kin] = dZ (K-major, K = cur_n) . W_layer viewed MN-major (N = kin, K = out)
+                {
+                    const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
+                    const uint32_t w_l   = w_smem + nc.layer_off[layer];
+                    const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
+                    const uint32_t dcol  = layer == 0 ? kColDA0 : kColZ;
+                    for (uint32_t k = 0; k < cur_n; k += 16u)
+                        umma_f16(tmem + dcol, umma_desc(cur_dz_addr + (k >> 3) * 128u, kLBO, cur_rg),
+                                 umma_desc_mn(w_l + (k >> 3) * w_rg, w_rg, 128u), idesc, k > 0u ? 1u : 0u);
+                }
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after_sync();
+            if (layer > 0) {
+                // dZ_{layer-1} = dA ⊙ ReLU'(H_{layer-1}) -> fp16 -> dz tile (both MMAs that read the old dZ have completed)
+                const uint8_t *h_tile = smem + lay.h_off + (uint32_t)(layer - 1) * (kTileRows * kNeurons * 2u);
+#pragma unroll
+                for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + kColZ + lane_base + c0, v);
+                    tmem_ld_wait();
+                    const uint4 m0 = *reinterpret_cast<const uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons));
+                    const uint4 m1 = *reinterpret_cast<const uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons));
+                    const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                    uint32_t h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a   = (mk[i] & 0x00007FFFu) ? __uint_as_float(v[2 * i]) : 0.f; // stored activation > 0 (fp16 bits)
+                        const float b   = (mk[i] & 0x7FFF0000u) ? __uint_as_float(v[2 * i + 1]) : 0.f;
+                        const __half2 p = __floats2half2_rn(a, b);
+                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                    }
+                    *reinterpret_cast<uint4 *>(dz_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(dz_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
+                }
+                fence_proxy_async_smem();
+                cur_dz_addr = dz_addr, cur_rg = rg_h, cur_n = kNeurons;
+                dw_col -= (layer == 1) ? nc.in_k : (uint32_t)kNeurons;
+            } else {
+                // dL/dfeatures -> fp16 -> global, same tile-canonical layout as the features
+                uint8_t *dst = tp.dfeat + (size_t)tile * tile_bytes;
+                for (uint32_t c0 = 0; c0 < nc.in_k; c0 += 16u) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + kColDA0 + lane_base + c0, v);
+                    tmem_ld_wait();
+                    uint32_t h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const __half2 p = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                    }
+                    *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, c0 >> 3, nc.in_k))        = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, (c0 >> 3) + 1u, nc.in_k)) = make_uint4(h[4], h[5], h[6], h[7]);
+                }
+            }
+        }
+        first_tile = 0u;
+        // all threads finished reading TMEM / smem of this tile before the next tile's TMA and MMAs overwrite them
+        tc_fence_before_sync();
+        __syncthreads();
+    }
+
+    // ================= flush: loss and the TMEM-resident weight gradients
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0 && tp.loss_sum)
+        atomicAdd(tp.loss_sum, loss_acc);
+    if (!first_tile) {
+        tc_fence_after_sync();
+        // M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  ->  warp w, lanes 0..15 hold rows 16 w .. 16 w + 15
+        const uint32_t r = 16u * warp + lane;
+        uint32_t col     = kColDW;
+        size_t goff      = 0;
+        for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
+            const bool last    = layer + 1u == nc.n_layers;
+            const uint32_t kin = layer == 0 ? nc.in_k : (uint32_t)kNeurons;
+            const uint32_t nn  = last ? (uint32_t)kOutPadded : kin; // accumulator columns
+            for (uint32_t c0 = 0; c0 < nn; c0 += 16u) {
+                uint32_t v[16];
+                tmem_ld16(tmem + col + lane_base + c0, v);
+                tmem_ld_wait();
+                if (lane < 16u) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float g = __uint_as_float(v[i]);
+                        if (g != 0.f) {
+                            // hidden/first: D[out = r][in = c0 + i]; last (transposed): D[in = r][out = c0 + i]
+                            const size_t idx = last ? goff + (size_t)(c0 + i) * kNeurons + r : goff + (size_t)r * kin + c0 + i;
+                            atomicAdd(tp.wgrad + idx, g);
+                        }
+                    }
+                }
+            }
+            col += nn;
+            goff += (size_t)(last ? kOutPadded : kNeurons) * kin;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem, 512u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_grid_backward
+// One thread per (sample, point) of ONE level (blockIdx.y), so a block's scatter targets one level's table.
+// use_smem: the level's gradient table (size x 4 floats) is privatised in shared memory and flushed once per block.
+__global__ void __launch_bounds__(256)
+k_grid_backward(const __grid_constant__ NetConst nc, const float *__restrict__ in, const uint8_t *__restrict__ dfeat, uint32_t batch,
+                uint32_t n_in_dims, uint32_t first_level, uint32_t use_smem, float *__restrict__ grid_grads)
+{
+    extern __shared__ float sg[];
+    const uint32_t level = first_level + blockIdx.y;
+    const GridLevel &L   = nc.lv[level];
+    if (use_smem) {
+        for (uint32_t i = threadIdx.x; i < L.size * 4u; i += blockDim.x)
+            sg[i] = 0.f;
+        __syncthreads();
+    }
+    const uint64_t total = (uint64_t)batch * nc.n_points;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(i / batch), s = (uint32_t)(i % batch); // consecutive threads -> consecutive samples
+        const uint32_t j = p * nc.n_levels + level;
+        const uint2 raw  = __ldg(reinterpret_cast<const uint2 *>(dfeat + feat_slot_offset(s, j, nc.in_k)));
+        if ((raw.x | raw.y) == 0u)
+            continue; // masked sample (target not visible) or dead ReLU path: nothing to scatter
+        const float2 g01 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 g23 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        const float *x   = in + (size_t)s * n_in_dims + 3u * p;
+        GridCorner gc;
+        grid_corners(L, __ldg(x), __ldg(x + 1), __ldg(x + 2), gc);
+        if (use_smem) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float *dst = sg + 4u * gc.index[c];
+                atomicAdd(dst + 0, gc.weight[c] * g01.x);
+                atomicAdd(dst + 1, gc.weight[c] * g01.y);
+                atomicAdd(dst + 2, gc.weight[c] * g23.x);
+                atomicAdd(dst + 3, gc.weight[c] * g23.y);
+            }
+        } else {
+            float *base = grid_grads + 4u * (size_t)L.offset;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                red_add_v4(base + 4u * (size_t)gc.index[c], gc.weight[c] * g01.x, gc.weight[c] * g01.y, gc.weight[c] * g23.x,
+                           gc.weight[c] * g23.y);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        float *base = grid_grads + 4u * (size_t)L.offset;
+        for (uint32_t e = threadIdx.x; e < L.size; e += blockDim.x) {
+            const float4 v = *reinterpret_cast<const float4 *>(sg + 4u * e);
+            if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                red_add_v4(base + 4u * (size_t)e, v.x, v.y, v.z, v.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_adam
+// optimizers/adam.h:48-123 (relative/absolute decay 0, no clipping, AdaBound off).  lr already carries the
+// ExponentialDecay factor.  Also writes the fp16 parameter and, for matrix weights, its slot in the packed weight image.
+__global__ void __launch_bounds__(256)
+k_adam(const __grid_constant__ AdamParams ap)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ap.n_params)
+        return;
+    // tcnn keeps gradients in fp16: round here so underflow-to-zero (and hence the skip below) is reproduced
+    float gradient = __half2float(__float2half_rn(ap.grads[i])) / ap.loss_scale;
+    const bool matrix = i < ap.n_matrix;
+    if (!matrix && gradient == 0.f)
+        return;
+    const float w = ap.master[i];
+    if (matrix)
+        gradient += ap.l2_reg * w;
+    const float g2 = gradient * gradient;
+    const float m  = ap.m[i] = ap.beta1 * ap.m[i] + (1.f - ap.beta1) * gradient;
+    const float v  = ap.v[i] = ap.beta2 * ap.v[i] + (1.f - ap.beta2) * g2;
+    const uint32_t t = ++ap.steps[i];
+    const float lr   = ap.lr * (sqrtf(1.f - powf(ap.beta2, (float)t)) / (1.f - powf(ap.beta1, (float)t)));
+    const float nw   = w - (lr / (sqrtf(v) + ap.epsilon)) * m;
+    ap.master[i]     = nw;
+    const __half hw  = __float2half_rn(nw);
+    ap.params[i]     = hw;
+    if (matrix) {
+        // (layer, r, c) of matrix weight i -> canonical K-major slot of the tensor-core weight image
+        uint32_t rem = (uint32_t)i, layer = 0, k = ap.in_k, n = kNeurons;
+        for (;; ++layer) {
+            k = layer == 0 ? ap.in_k : (uint32_t)kNeurons;
+            n = layer + 1u == ap.n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+            if (rem < n * k)
+                break;
+            rem -= n * k;
+        }
+        const uint32_t r = rem / k, c = rem % k;
+        const uint32_t off = ap.layer_off[layer] + (r >> 3) * ((k >> 3) * 128u) + (c >> 3) * 128u + (r & 7u) * 16u + (c & 7u) * 2u;
+        *reinterpret_cast<__half *>(ap.wimg + off) = hw;
+    }
+}
+
+__global__ void k_half_to_float(const __half *__restrict__ src, float *__restrict__ dst, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __half2float(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static uint32_t g_train_smem = 0;
+
+cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_layers)
+{
+    const TrainSmem lay = train_smem_layout(wimg_bytes, in_k, n_layers - 1u);
+    g_train_smem        = lay.total;
+    cudaError_t e = cudaFuncSetAttribute(k_train_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    if (e != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_grid_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+}
+
+cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t batch, uint32_t n_in_dims, uint8_t *feat, int num_sms,
+                                   cudaStream_t stream)
+{
+    if (batch == 0)
+        return cudaSuccess;
+    const uint32_t padded = (batch + kTileRows - 1u) / kTileRows * kTileRows;
+    const uint64_t total  = (uint64_t)padded * (nc.in_k >> 2);
+    uint64_t blocks       = (total + 255u) / 256u;
+    const uint64_t cap    = (uint64_t)num_sms * 32u;
+    if (blocks > cap)
+        blocks = cap;
+    k_encode_features<<<(uint32_t)blocks, 256, 0, stream>>>(nc, in, batch, padded, n_in_dims, feat);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_sms, cudaStream_t stream)
+{
+    if (tp.batch == 0)
+        return cudaSuccess;
+    const uint32_t n_tiles = (tp.batch + kTileRows - 1u) / kTileRows;
+    const uint32_t grid    = n_tiles < (uint32_t)num_sms ? n_tiles : (uint32_t)num_sms;
+    k_train_mlp<<<grid, kTileRows, g_train_smem, stream>>>(nc, tp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint8_t *dfeat, uint32_t batch, uint32_t n_in_dims,
+                                 float *grid_grads, int num_sms, cudaStream_t stream)
+{
+    if (batch == 0)
+        return cudaSuccess;
+    // leading levels small enough for a 64 KB shared-memory table
+    uint32_t n_small = 0;
+    while (n_small < nc.n_levels && nc.lv[n_small].size * 16u <= 64u * 1024u)
+        ++n_small;
+    const uint64_t total = (uint64_t)batch * nc.n_points;
+    if (n_small) {
+        uint32_t bx = (uint32_t)((total + 255u) / 256u);
+        const uint32_t cap = (uint32_t)num_sms; // few, long-lived blocks: one flush of the table per block
+        if (bx > cap)
+            bx = cap;
+        k_grid_backward<<<dim3(bx, n_small), 256, 64 * 1024, stream>>>(nc, in, dfeat, batch, n_in_dims, 0u, 1u, grid_grads);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+    }
+    if (n_small < nc.n_levels) {
+        uint32_t bx = (uint32_t)((total + 255u) / 256u);
+        const uint32_t cap = (uint32_t)num_sms * 8u;
+        if (bx > cap)
+            bx = cap;
+        k_grid_backward<<<dim3(bx, nc.n_levels - n_small), 256, 0, stream>>>(nc, in, dfeat, batch, n_in_dims, n_small, 0u, grid_grads);
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_adam(const AdamParams &ap, cudaStream_t stream)
+{
+    if (ap.n_params == 0)
+        return cudaSuccess;
+    k_adam<<<(uint32_t)((ap.n_params + 255u) / 256u), 256, 0, stream>>>(ap);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_half_to_float(const void *src, float *dst, uint64_t n, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_half_to_float<<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(reinterpret_cast<const __half *>(src), dst, n);
+    return cudaGetLastError();
+}
+
+} // namespace nbvh

@@ -255,6 +255,37 @@ class NeuralPathModule:
         hp = hits_host.ctypes.data_as(C.c_void_p) if hits_host is not None else None
         self._check(self._lib.nbvh_render_host(self._h, int(accumulated_spp), int(sample_offset), cam, lp, hp))
 
+    # ------------------------------------------------------------------ online optimisation
+    def gradient_buffer(self):
+        """fp32 gradient vector (n_params) owned by torch and registered with the library: NCCL allreduces it in place."""
+        torch = _torch()
+        if "grads" not in self._keep or self._keep["grads"].numel() != self.n_params():
+            g = torch.zeros(self.n_params(), dtype=torch.float32, device=torch.device("cuda", self.device))
+            self._check(self._lib.nbvh_set_gradient_buffer(self._h, _ptr(g)))
+            self._keep["grads"] = g
+        return self._keep["grads"]
+
+    def training_forward_backward(self, inputs, targets, global_batch=None, per_sample_loss=None, loss_sum=None, stream=None):
+        """Forward + composite loss + backward; leaves loss-scaled (x128) fp32 gradients in the gradient buffer."""
+        n = inputs.shape[0]
+        assert inputs.is_cuda and inputs.is_contiguous() and targets.is_contiguous() and targets.shape[0] == n
+        self._check(self._lib.nbvh_training_forward_backward(self._h, _ptr(inputs), _ptr(targets), n, int(global_batch or n),
+                                                             _ptr(per_sample_loss), _ptr(loss_sum), stream))
+
+    def optimizer_step(self, stream=None):
+        self._check(self._lib.nbvh_optimizer_step(self._h, stream))
+
+    def training_step(self, inputs, targets, per_sample_loss=None, want_loss=True, stream=None):
+        """== trainer->training_step(stream, in 9xB, target 8xB) (+ trainer->loss when want_loss): returns the batch loss."""
+        n = inputs.shape[0]
+        loss = C.c_float(0)
+        self._check(self._lib.nbvh_training_step(self._h, _ptr(inputs), _ptr(targets), n, _ptr(per_sample_loss),
+                                                 C.byref(loss) if want_loss else None, stream))
+        return loss.value if want_loss else None
+
+    def training_step_count(self):
+        return int(self._lib.nbvh_training_step_count(self._h))
+
     # ------------------------------------------------------------------ counters / timing
     def counters(self):
         out = (C.c_uint64 * len(COUNTER_NAMES))()
