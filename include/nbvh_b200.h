@@ -313,6 +313,9 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
                      const nbvh_camera_params *camera_host, uint8_t *ldr_rgba8_host, nbvh_hit_record *hits_host);
+/* device self-test of the hoisted IEEE division used by the slab tests (csrc/device_core.cuh): compares n_trials random
+ * quotients inside the documented operand range against div.rn and returns the number of differing bit patterns */
+int nbvh_selftest_division(nbvh_ctx *ctx, uint64_t seed, uint64_t n_trials, uint64_t *mismatches_host);
 int nbvh_get_counters(nbvh_ctx *ctx, uint64_t *out_host, uint32_t n);
 int nbvh_reset_counters(nbvh_ctx *ctx);
 /* average duration (ms) and launch count of the dominant kernel since the last reset, measured with

@@ -135,6 +135,7 @@ SYMBOLS = {
     "nbvh_raygen": (_i, [_vp, _u32, _u32, _i, _i, _vp, _vp, _vp]),
     "nbvh_render": (_i, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_render_host": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
+    "nbvh_selftest_division": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),
     "nbvh_get_counters": (_i, [_vp, _vp, _u32]),
     "nbvh_reset_counters": (_i, [_vp]),
     "nbvh_get_kernel_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_u32)]),

@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -235,6 +236,9 @@ struct nbvh_ctx {
     float4 *d_nbvh = nullptr, *d_nbvh_dilated = nullptr;
     uint32_t nbvh_nodes = 0;
     float dilated_with  = -1.f;
+    bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
+    bool blas_safe[kMaxBlas] = {};
+    bool tlas_safe = false;
 
     // scene
     SceneConst scene{};
@@ -247,7 +251,10 @@ struct nbvh_ctx {
     nbvh_hit_record *hits = nullptr;
     nbvh_hit_record *own_hits = nullptr;
 
-    uint32_t *d_next_chunk = nullptr;
+    uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor
+    NeuralQueueEntry *d_queue = nullptr;
+    size_t queue_capacity = 0;
+    bool mega_kernel = false; // NBVH_RENDER_MODE=mega: the single persistent kernel of the first design (kept for A/B timing)
     unsigned long long *d_counters = nullptr;
 
     // kernel timing
@@ -346,6 +353,7 @@ int rebuild_layout(nbvh_ctx *ctx)
     CU_TRY(ctx, cudaMemset(ctx->d_params, 0, ctx->n_params * sizeof(uint16_t)));
     CU_TRY(ctx, cudaMalloc(&ctx->d_wimg, ctx->wimg_bytes));
     CU_TRY(ctx, configure_kernels(ctx->wimg_bytes, ctx->in_k));
+    CU_TRY(ctx, configure_render(ctx->wimg_bytes, ctx->in_k));
     CU_TRY(ctx, configure_training(ctx->wimg_bytes, ctx->in_k, ctx->n_layers));
     return NBVH_OK;
 }
@@ -413,6 +421,18 @@ NbvhConst make_nbvh_const(const nbvh_ctx *ctx, bool inference)
     return bc;
 }
 
+// hoisted-division precondition on a node array (device_core.cuh): synchronous, setup time only
+int check_nodes(nbvh_ctx *ctx, const float4 *nodes, uint32_t n, bool &ok)
+{
+    uint32_t one = 1u, result = 0u;
+    uint32_t *flag = ctx->d_next_chunk + 3;
+    CU_TRY(ctx, cudaMemcpy(flag, &one, 4, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, launch_check_nodes(nodes, n, flag, 0));
+    CU_TRY(ctx, cudaMemcpy(&result, flag, 4, cudaMemcpyDeviceToHost));
+    ok = result != 0u;
+    return NBVH_OK;
+}
+
 // keep the pre-dilated node copy in sync with fixed_node_dilation
 int refresh_dilated(nbvh_ctx *ctx)
 {
@@ -429,7 +449,7 @@ int refresh_dilated(nbvh_ctx *ctx)
         CU_TRY(ctx, cudaDeviceSynchronize());
     }
     ctx->dilated_with = ctx->bvh_const.fixed_node_dilation;
-    return NBVH_OK;
+    return check_nodes(ctx, ctx->d_nbvh_dilated, ctx->nbvh_nodes, ctx->nbvh_safe);
 }
 
 EncodeConst make_encode_const(const nbvh_ctx *ctx)
@@ -518,8 +538,10 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
     nbvh_ctx *ctx = new nbvh_ctx();
     ctx->device   = device;
     ctx->num_sms  = prop.multiProcessorCount;
-    if (cudaMalloc(&ctx->d_next_chunk, sizeof(uint32_t)) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * CNT_COUNT) != cudaSuccess) {
+    if (const char *m = getenv("NBVH_RENDER_MODE"))
+        ctx->mega_kernel = std::string(m) == "mega";
+    if (cudaMalloc(&ctx->d_next_chunk, 4 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
         return NBVH_ERR_CUDA;
     }
@@ -546,6 +568,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaFree(ctx->ldr);
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
+    cudaFree(ctx->d_queue);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->own_grads);
     cudaFree(ctx->d_master);
@@ -855,6 +878,14 @@ int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
         ctx->scene.blas[i].prim_indices = reinterpret_cast<const unsigned long long *>(blas[i].prim_indices);
         ctx->scene.blas[i].vertices     = blas[i].vertices;
         ctx->scene.blas[i].indices      = blas[i].indices;
+        int rc = check_nodes(ctx, ctx->scene.blas[i].nodes, blas[i].num_nodes, ctx->blas_safe[i]);
+        if (rc != NBVH_OK)
+            return rc;
+    }
+    {
+        int rc = check_nodes(ctx, ctx->scene.tlas.nodes, s->num_tlas_nodes, ctx->tlas_safe);
+        if (rc != NBVH_OK)
+            return rc;
     }
     ctx->scene_set = true;
     return NBVH_OK;
@@ -1151,7 +1182,7 @@ int nbvh_trace_intervals(nbvh_ctx *ctx, const float *o, const float *d, uint32_t
     if (rc != NBVH_OK)
         return rc;
     KernelTimer kt(ctx, (cudaStream_t)stream);
-    CU_TRY(ctx, launch_trace_intervals(make_nbvh_const(ctx, true), o, d, n, max_intervals, counts, node_idx, mint, maxt,
+    CU_TRY(ctx, launch_trace_intervals(make_nbvh_const(ctx, true), ctx->nbvh_safe ? 1u : 0u, o, d, n, max_intervals, counts, node_idx, mint, maxt,
                                        ctx->d_counters, (cudaStream_t)stream));
     kt.stop();
     return NBVH_OK;
@@ -1165,7 +1196,7 @@ int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const 
     if (!ctx->scene_set || blas_idx >= ctx->scene.n_blas)
         return fail(ctx, NBVH_ERR_STATE, "scene not set or BLAS index out of range");
     KernelTimer kt(ctx, (cudaStream_t)stream);
-    CU_TRY(ctx, launch_blas_intersect(ctx->scene.blas[blas_idx], o, d, maxt, n, t, u, v, prim, ctx->d_counters,
+    CU_TRY(ctx, launch_blas_intersect(ctx->scene.blas[blas_idx], ctx->blas_safe[blas_idx] ? 1u : 0u, o, d, maxt, n, t, u, v, prim, ctx->d_counters,
                                       (cudaStream_t)stream));
     kt.stop();
     return NBVH_OK;
@@ -1179,6 +1210,10 @@ static CameraConst make_camera_const(const nbvh_ctx *ctx)
     memcpy(cc.dv, ctx->camera.dv, 12);
     memcpy(cc.top_left, ctx->camera.dir_top_left, 12);
     cc.fb_w = ctx->fb_w, cc.fb_h = ctx->fb_h;
+    bool safe = ctx->nbvh_safe && ctx->tlas_safe;
+    for (uint32_t i = 0; i < ctx->scene.n_blas; i++)
+        safe = safe && ctx->blas_safe[i];
+    cc.nodes_safe = safe ? 1u : 0u;
     return cc;
 }
 
@@ -1234,6 +1269,13 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     rp.skylike_background      = ctx->scene_const.skylike_background;
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
     rp.next_chunk    = ctx->d_next_chunk;
+    if (ctx->queue_capacity < (size_t)total) {
+        cudaFree(ctx->d_queue);
+        ctx->d_queue = nullptr, ctx->queue_capacity = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_queue, (size_t)total * sizeof(NeuralQueueEntry)));
+        ctx->queue_capacity = total;
+    }
+    rp.queue = ctx->d_queue, rp.queue_count = ctx->d_next_chunk + 1, rp.queue_cursor = ctx->d_next_chunk + 2;
     rp.sample_idx    = (int)accumulated_spp;
     rp.sample_offset = (int)sample_offset;
     rp.accum = ctx->accum, rp.ldr = ctx->ldr, rp.hits = ctx->hits;
@@ -1241,9 +1283,12 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     rp.ema_weight     = ctx->scene_const.ema_weight;
     rp.counters       = ctx->d_counters;
     const NetConst nc = make_net_const(ctx);
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, sizeof(uint32_t), st));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, 4 * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
-    CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
+    if (ctx->mega_kernel)
+        CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
+    else
+        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st));
     kt.stop();
     return NBVH_OK;
 }
@@ -1269,6 +1314,19 @@ int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_of
     if (hits_host)
         CU_TRY(ctx, cudaMemcpyAsync(hits_host, ctx->hits, n * sizeof(nbvh_hit_record), cudaMemcpyDeviceToHost, 0));
     CU_TRY(ctx, cudaStreamSynchronize(0));
+    return NBVH_OK;
+}
+
+int nbvh_selftest_division(nbvh_ctx *ctx, uint64_t seed, uint64_t n_trials, uint64_t *mismatches_host)
+{
+    if (!ctx || !mismatches_host)
+        return NBVH_ERR_INVALID_ARG;
+    unsigned long long *d = ctx->d_counters + CNT_COUNT; // spare slot
+    CU_TRY(ctx, cudaMemset(d, 0, sizeof(unsigned long long)));
+    const uint32_t iters  = 1024u;
+    const uint32_t blocks = (uint32_t)((n_trials + 256ull * iters - 1) / (256ull * iters));
+    CU_TRY(ctx, launch_selftest_division(seed, blocks ? blocks : 1u, iters, d, 0));
+    CU_TRY(ctx, cudaMemcpy(mismatches_host, d, sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return NBVH_OK;
 }
 

@@ -10,7 +10,7 @@
 //   k_trace_intervals / k_blas_intersect / k_raygen   parity hooks on the traversal building blocks
 //
 // Compiled with -fmad=false: see device_core.cuh for the arithmetic contract.
-#include "kernels.cuh"
+#include "render_common.cuh"
 
 #include <cstdio>
 
@@ -20,72 +20,6 @@ constexpr int kTilesPerCta   = 2;
 constexpr int kCtaThreads    = kTilesPerCta * kTileRows;
 constexpr int kRefillRounds  = 6;
 
-// ------------------------------------------------------------------------------------------------ CTA setup
-struct CtaShared {
-    uint8_t *base;
-    SmemLayout lay;
-};
-
-// Loads the packed weights with one TMA bulk copy, allocates TMEM, initialises the per-tile mbarriers.
-// Returns the TMEM base address.  Must be called by all threads of the CTA.
-__device__ __forceinline__ uint32_t cta_setup(const NetConst &nc, uint8_t *smem, const SmemLayout &lay)
-{
-    const uint32_t tid      = threadIdx.x;
-    const uint32_t bar_base = smem_u32(smem + lay.bar_off);
-    const uint32_t w_bar    = bar_base + 8u * kTilesPerCta;
-    if (tid == 0) {
-        for (int t = 0; t < kTilesPerCta; ++t)
-            mbar_init(bar_base + 8u * t, 1u);
-        mbar_init(w_bar, 1u);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(w_bar, nc.wimg_bytes);
-        tma_bulk_g2s(smem_u32(smem + lay.w_off), nc.wimg, nc.wimg_bytes, w_bar);
-    }
-    if (tid < 32) {
-        tmem_alloc(smem_u32(smem + lay.tmem_off), 64u * kTilesPerCta); // 64 fp32 accumulator columns per tile
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
-    mbar_wait(w_bar, 0u); // weights landed (async proxy writes are visible after the mbarrier completes)
-    return tmem_base;
-}
-
-__device__ __forceinline__ void cta_teardown(uint32_t tmem_base)
-{
-    tc_fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        tc_fence_after_sync();
-        tmem_dealloc(tmem_base, 64u * kTilesPerCta);
-    }
-}
-
-__device__ __forceinline__ TileCtx make_tile(uint8_t *smem, const SmemLayout &lay, const NetConst &nc, uint32_t tile,
-                                             uint32_t tmem_base)
-{
-    const uint32_t a_bytes = kTileRows * (nc.in_k > (uint32_t)kNeurons ? nc.in_k : (uint32_t)kNeurons) * 2u;
-    TileCtx t;
-    t.a_tile   = smem + lay.a_off + tile * a_bytes;
-    t.w_smem   = smem_u32(smem + lay.w_off);
-    t.mma_bar  = smem_u32(smem + lay.bar_off) + 8u * tile;
-    t.tmem_acc = tmem_base + 64u * tile;
-    t.bar_id   = 1u + tile;
-    t.phase    = 0u;
-    return t;
-}
-
-__device__ __forceinline__ void warp_add_counter(unsigned long long *counters, int slot, uint32_t v)
-{
-    v = __reduce_add_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31u) == 0u && v != 0u && counters)
-        atomicAdd(counters + slot, (unsigned long long)v);
-}
-
 // ------------------------------------------------------------------------------------------------ k_query
 __global__ void __launch_bounds__(kCtaThreads, 2)
 k_query(const __grid_constant__ NetConst nc, const float *__restrict__ in, float *__restrict__ out, uint32_t n,
@@ -93,7 +27,7 @@ k_query(const __grid_constant__ NetConst nc, const float *__restrict__ in, float
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
-    const uint32_t tmem_base = cta_setup(nc, smem, lay);
+    const uint32_t tmem_base = cta_setup<kTilesPerCta>(nc, smem, lay);
     const uint32_t tile      = threadIdx.x / kTileRows;
     const uint32_t row       = threadIdx.x % kTileRows;
     TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
@@ -121,11 +55,11 @@ k_query(const __grid_constant__ NetConst nc, const float *__restrict__ in, float
     }
     if (row == 0 && counters && iters)
         atomicAdd(counters + CNT_TILE_ITERS, (unsigned long long)iters);
-    cta_teardown(tmem_base);
+    cta_teardown<kTilesPerCta>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ parity hooks
-__global__ void k_trace_intervals(NbvhConst bc, const float *__restrict__ o, const float *__restrict__ d, uint32_t n,
+__global__ void k_trace_intervals(NbvhConst bc, uint32_t nodes_safe, const float *__restrict__ o, const float *__restrict__ d, uint32_t n,
                                   uint32_t max_intervals, uint32_t *__restrict__ counts, uint32_t *__restrict__ node_idx,
                                   float *__restrict__ mint, float *__restrict__ maxt, unsigned long long *counters)
 {
@@ -135,6 +69,7 @@ __global__ void k_trace_intervals(NbvhConst bc, const float *__restrict__ o, con
         Ray r;
         r.ox = o[3 * i], r.oy = o[3 * i + 1], r.oz = o[3 * i + 2];
         r.dx = d[3 * i], r.dy = d[3 * i + 1], r.dz = d[3 * i + 2];
+        ray_prepare(r, nodes_safe != 0u);
         uint32_t stack[kNeuralStackSize];
         int ss    = 1;
         stack[0]  = 0;
@@ -156,7 +91,7 @@ __global__ void k_trace_intervals(NbvhConst bc, const float *__restrict__ o, con
     warp_add_counter(counters, CNT_NBVH_STEPS, steps);
 }
 
-__global__ void k_blas_intersect(BlasConst b, const float *__restrict__ o, const float *__restrict__ d,
+__global__ void k_blas_intersect(BlasConst b, uint32_t nodes_safe, const float *__restrict__ o, const float *__restrict__ d,
                                  const float *__restrict__ maxt, uint32_t n, float *__restrict__ t, float *__restrict__ u,
                                  float *__restrict__ v, uint32_t *__restrict__ prim, unsigned long long *counters)
 {
@@ -166,6 +101,7 @@ __global__ void k_blas_intersect(BlasConst b, const float *__restrict__ o, const
         Ray r;
         r.ox = o[3 * i], r.oy = o[3 * i + 1], r.oz = o[3 * i + 2];
         r.dx = d[3 * i], r.dy = d[3 * i + 1], r.dz = d[3 * i + 2];
+        ray_prepare(r, nodes_safe != 0u);
         const TriHit h = blas_closest_hit(b, r, 1e-4f, maxt ? maxt[i] : FLT_MAX, steps, tests);
         t[i] = h.t, u[i] = h.u, v[i] = h.v, prim[i] = h.prim;
     }
@@ -214,58 +150,6 @@ struct LaneState {
     bool have_ray, have_query, neural_active;
 };
 
-// accumulate_pixel_value (include/cuda/neural/neural_bvh_renderer_kernels.cuh:81-127) on linear memory
-__device__ __forceinline__ float linear_to_srgb(float x)
-{
-    return (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(x, 0.f), 1.f / 2.4f) - 0.055f;
-}
-
-__device__ __forceinline__ void splat(const RenderParams &p, uint32_t pixel, float r, float g, float b, float alpha)
-{
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.sample_idx > 0)
-        acc = p.accum[pixel];
-    if (p.ema_accumulate) {
-        if (alpha == 0.f && p.sample_idx > 0)
-            return;
-        if (p.sample_idx > 0) {
-            const float w = p.ema_weight, iw = 1.f - p.ema_weight;
-            acc = make_float4(r * w + acc.x * iw, g * w + acc.y * iw, b * w + acc.z * iw, alpha * w + acc.w * iw);
-        } else {
-            acc = make_float4(r, g, b, alpha);
-        }
-        p.accum[pixel] = acc;
-    } else {
-        acc            = make_float4(acc.x + r, acc.y + g, acc.z + b, acc.w + alpha);
-        p.accum[pixel] = acc;
-        const float inv = 1.f / float(p.sample_idx + 1);
-        acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    }
-    if (p.ldr) {
-        uchar4 px;
-        px.x = (unsigned char)min(max(int(linear_to_srgb(acc.x) * 256.0f), 0), 255);
-        px.y = (unsigned char)min(max(int(linear_to_srgb(acc.y) * 256.0f), 0), 255);
-        px.z = (unsigned char)min(max(int(linear_to_srgb(acc.z) * 256.0f), 0), 255);
-        px.w = 255;
-        p.ldr[pixel] = px;
-    }
-}
-
-// background_hit_eval (path_inference_kernels.cu:37-59); the HDR environment texture belongs to the shading
-// row and evaluates to black here.
-__device__ __forceinline__ void background(const RenderParams &p, const Ray &ray, float bg[3])
-{
-    bg[0] = bg[1] = bg[2] = 0.f;
-    if (!p.envmap_eval)
-        return;
-    if (p.skylike_background) {
-        const float a = 0.5f * (ray.dy + 1.f);
-        bg[0] = (1.f - a) * 1.f + a * 0.5f;
-        bg[1] = (1.f - a) * 1.f + a * 0.7f;
-        bg[2] = (1.f - a) * 1.f + a * 1.f;
-    }
-}
-
 // The ray reached the end of its TLAS walk: hybrid_scatter_and_get_next_tlas_traversal_step with
 // ray_depth == max_depth (path_inference_kernels.cu:306-321): add the background when nothing was hit, splat.
 __device__ __forceinline__ void finish_ray(const RenderParams &p, LaneState &s)
@@ -282,18 +166,6 @@ __device__ __forceinline__ void finish_ray(const RenderParams &p, LaneState &s)
         p.hits[s.pixel] = h;
     }
     s.have_ray = false;
-}
-
-// 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1)
-__device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_t s)
-{
-    const uint32_t w = p.cam.fb_w, h = p.cam.fb_h;
-    if ((w & 7u) || (h & 3u))
-        return s;
-    const uint32_t chunk = s >> 5, k = s & 31u;
-    const uint32_t bpr = w >> 3;
-    const uint32_t bx = chunk % bpr, by = chunk / bpr;
-    return (by * 4u + (k >> 3)) * w + bx * 8u + (k & 7u);
 }
 
 // Advances the lane's ray until it has a network query pending or the ray is finished
@@ -349,7 +221,7 @@ k_render(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kCtaThreads / 32];
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
-    const uint32_t tmem_base = cta_setup(nc, smem, lay);
+    const uint32_t tmem_base = cta_setup<kTilesPerCta>(nc, smem, lay);
     const uint32_t tile      = threadIdx.x / kTileRows;
     const uint32_t row       = threadIdx.x % kTileRows;
     const uint32_t lane      = threadIdx.x & 31u;
@@ -480,11 +352,71 @@ k_render(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
     if (row == 0 && p.counters && cnt_iters)
         atomicAdd(p.counters + CNT_TILE_ITERS, (unsigned long long)cnt_iters);
-    cta_teardown(tmem_base);
+    cta_teardown<kTilesPerCta>(tmem_base);
+}
+
+// Range check of a node array for the hoisted division (device_core.cuh): clears *ok when a coordinate is not in {0} u [2^-60, 2^40]
+__global__ void k_check_nodes(const float4 *__restrict__ nodes, uint32_t n, uint32_t *ok)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * n)
+        return;
+    const float4 v = nodes[i];
+    const float lo = 8.673617379884035e-19f, hi = 1099511627776.0f;
+    if (!(in_range_or_zero(v.x, lo, hi) && in_range_or_zero(v.y, lo, hi) && in_range_or_zero(v.z, lo, hi)))
+        *ok = 0u;
+}
+
+// Device self-test of hoisted_div against __fdiv_rn over random operands inside the documented precondition
+__global__ void k_selftest_division(uint64_t seed, uint32_t iters, unsigned long long *mismatches)
+{
+    uint64_t s = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x + 1u);
+    auto next = [&]() {
+        s += 0x9E3779B97F4A7C15ull;
+        uint64_t z = s;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return (uint32_t)((z ^ (z >> 31)) >> 16);
+    };
+    uint32_t bad = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        // b: random sign/mantissa, exponent in [-30, 30];  a: exponent in [-84, 41] or exactly zero; every 16th pair uses
+        // boundary mantissas (all ones / all zeros / one-off), the classic hard cases for correctly rounded division
+        uint32_t rb = next(), ra = next(), sel = next();
+        uint32_t mb = rb & 0x7FFFFFu, ma = ra & 0x7FFFFFu;
+        if ((sel & 15u) == 0u) {
+            const uint32_t special[4] = {0x7FFFFFu, 0u, 1u, 0x7FFFFEu};
+            mb = special[(sel >> 4) & 3u], ma = special[(sel >> 6) & 3u];
+        }
+        const uint32_t eb = 127u - 30u + (rb >> 23) % 61u, ea = 127u - 84u + (ra >> 23) % 126u;
+        const float b = __uint_as_float((rb & 0x80000000u) | (eb << 23) | mb);
+        float a       = __uint_as_float((ra & 0x80000000u) | (ea << 23) | ma);
+        if ((sel & 0xFF00u) == 0x1100u)
+            a = 0.f;
+        const float want = __fdiv_rn(a, b);
+        const float got  = hoisted_div(a, b, refined_rcp(b));
+        bad += __float_as_uint(want) != __float_as_uint(got);
+    }
+    if (bad)
+        atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
 static uint32_t g_smem_bytes = 0;
+
+cudaError_t launch_check_nodes(const float4 *nodes, uint32_t n, uint32_t *ok_dev, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_check_nodes<<<(2u * n + 255u) / 256u, 256, 0, stream>>>(nodes, n, ok_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_selftest_division(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long *mismatches, cudaStream_t stream)
+{
+    k_selftest_division<<<blocks, 256, 0, stream>>>(seed, iters, mismatches);
+    return cudaGetLastError();
+}
 
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k)
 {
@@ -510,22 +442,22 @@ cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace_intervals(const NbvhConst &bc, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
+cudaError_t launch_trace_intervals(const NbvhConst &bc, uint32_t nodes_safe, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
                                    uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt,
                                    unsigned long long *counters, cudaStream_t stream)
 {
     if (n == 0)
         return cudaSuccess;
-    k_trace_intervals<<<(n + 127) / 128, 128, 0, stream>>>(bc, o, d, n, max_intervals, counts, node_idx, mint, maxt, counters);
+    k_trace_intervals<<<(n + 127) / 128, 128, 0, stream>>>(bc, nodes_safe, o, d, n, max_intervals, counts, node_idx, mint, maxt, counters);
     return cudaGetLastError();
 }
 
-cudaError_t launch_blas_intersect(const BlasConst &b, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
+cudaError_t launch_blas_intersect(const BlasConst &b, uint32_t nodes_safe, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
                                   float *u, float *v, uint32_t *prim, unsigned long long *counters, cudaStream_t stream)
 {
     if (n == 0)
         return cudaSuccess;
-    k_blas_intersect<<<(n + 127) / 128, 128, 0, stream>>>(b, o, d, maxt, n, t, u, v, prim, counters);
+    k_blas_intersect<<<(n + 127) / 128, 128, 0, stream>>>(b, nodes_safe, o, d, maxt, n, t, u, v, prim, counters);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,10 @@ struct SceneConst {
     uint32_t n_blas;
 };
 
+struct NeuralQueueEntry { // a ray that reached the neural BLAS: pixel id + closest classical hit so far (32 B)
+    uint4 a, b;
+};
+
 struct RenderParams {
     CameraConst cam;
     NbvhConst nbvh;
@@ -37,6 +41,8 @@ struct RenderParams {
     // work distribution
     uint32_t first_pixel, pixel_count; // shard of the frame rendered by this launch
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
+    NeuralQueueEntry *queue;            // neural ray queue filled by k_primary, drained by k_neural
+    uint32_t *queue_count, *queue_cursor;
     int sample_idx, sample_offset;
     // outputs
     float4 *accum;          // RGBA32F accumulation buffer (linear memory replaces the GL surface)
@@ -107,15 +113,19 @@ cudaError_t launch_half_to_float(const void *src, float *dst, uint64_t n, cudaSt
 
 cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32_t n, uint32_t n_in_dims,
                          unsigned long long *counters, int num_sms, cudaStream_t stream);
-cudaError_t launch_trace_intervals(const NbvhConst &bc, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
+cudaError_t launch_trace_intervals(const NbvhConst &bc, uint32_t nodes_safe, const float *o, const float *d, uint32_t n, uint32_t max_intervals,
                                    uint32_t *counts, uint32_t *node_idx, float *mint, float *maxt,
                                    unsigned long long *counters, cudaStream_t stream);
-cudaError_t launch_blas_intersect(const BlasConst &b, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
+cudaError_t launch_blas_intersect(const BlasConst &b, uint32_t nodes_safe, const float *o, const float *d, const float *maxt, uint32_t n, float *t,
                                   float *u, float *v, uint32_t *prim, unsigned long long *counters, cudaStream_t stream);
 cudaError_t launch_raygen(const CameraConst &cam, uint32_t first, uint32_t n, int sample_idx, int sample_offset, float *o,
                           float *d, cudaStream_t stream);
+cudaError_t launch_check_nodes(const float4 *nodes, uint32_t n, uint32_t *ok_dev, cudaStream_t stream);
+cudaError_t launch_selftest_division(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long *mismatches, cudaStream_t stream);
 cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
+cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
+cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k);
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);
 
 } // namespace nbvh

@@ -147,6 +147,16 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 }
 
 // ------------------------------------------------------------------------------------------------ hash grid (a9)
+// index % size: every hashed level has a power-of-two table (mask); dense levels only wrap when a coordinate sits on the
+// upper face of the unit cube, so the true modulo is a rare out-of-line call instead of ~25 instructions per corner
+static __device__ __noinline__ uint32_t grid_wrap_slow(uint32_t index, uint32_t size) { return index % size; }
+__device__ __forceinline__ uint32_t grid_wrap(uint32_t index, uint32_t mask, uint32_t size)
+{
+    if (mask)
+        return index & mask;
+    return index < size ? index : grid_wrap_slow(index, size);
+}
+
 // One level of tcnn's kernel_grid for one point, arithmetic identical to the reference: positions through
 // fma(scale,x,0.5), weights as products in fp32 rounded to fp16, accumulation with __hfma2 in corner order
 // 0..7 (grid.h:94-169; pos_fract common_device.h:857-868; grid_index :691-707; coherent prime hash :652-655).
@@ -168,7 +178,7 @@ __device__ __forceinline__ uint2 grid_level_features(const uint2 *__restrict__ g
             index = cx + cy * L.res + cz * L.res * L.res;
         else
             index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
-        index = L.mask ? (index & L.mask) : (index % L.size);
+        index = grid_wrap(index, L.mask, L.size);
         g[c]  = __ldg(grid + L.offset + index);
     }
     __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);

@@ -1,0 +1,283 @@
+// render.cu -- the frame pipeline of the neural ray-query path as two kernels (replaces the host loops of
+// /root/reference/src/cuda/neural/path/path_module.cu:54-245 and kernels K1-K9 at max_depth 1):
+//
+//   k_primary   one thread per pixel, no tensor-core state, full occupancy: camera ray (a6), complete TLAS walk (a4) with the
+//               classical BLAS closest hits (a14) taken on the way; rays whose TLAS walk reaches the neural BLAS are appended
+//               to the neural ray queue with a warp ballot/prefix-sum compaction (one atomic per warp), all others are
+//               finished (background, splat, hit record).
+//   k_neural    persistent tile kernel (tcgen05/TMEM): lanes pull queue entries, regenerate their ray from the pixel id
+//               (same arithmetic -> same bits), walk the N-BVH tree-cut from the root to the next leaf interval (a3), and
+//               every 128-lane tile runs hash-grid encode + MLP + decode (a8-a11) on the pending intervals; the walk resumes
+//               with ray.maxt = current closest t (a12); finished lanes splat and refill from the queue (a13).
+//
+// Order of BLAS visits: the reference visits the BLAS of a ray in TLAS front-to-back order; here every classical BLAS is
+// intersected before the neural walk starts, which only *prunes* neural leaves behind the classical hit.  The final closest
+// hit is the minimum over the same candidate set, so hit records are identical; the number of network queries can only shrink.
+//
+// Compiled with -fmad=false: see device_core.cuh for the arithmetic contract.
+#include "render_common.cuh"
+
+namespace nbvh {
+
+constexpr int kNeuralTiles   = 2;                        // 128-lane tiles per CTA
+constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
+constexpr int kWalkRounds    = 4;                        // refill/advance rounds before a tile runs the network
+
+// ------------------------------------------------------------------------------------------------ shared helpers
+struct HitState {
+    float best_t;
+    uint32_t valid_hit;
+    float n_or_uv[3];
+    float alb_or_ids[3];
+};
+
+// hybrid_scatter_and_get_next_tlas_traversal_step at ray_depth == max_depth (path_inference_kernels.cu:306-321)
+__device__ __forceinline__ void finish_pixel(const RenderParams &p, uint32_t pixel, const Ray &ray, const HitState &h)
+{
+    float illum[3] = {0.f, 0.f, 0.f};
+    if (h.valid_hit == 0u)
+        background(p, ray, illum);
+    splat(p, pixel, illum[0], illum[1], illum[2], 1.0f);
+    if (p.hits) {
+        nbvh_hit_record r;
+        r.t = h.best_t, r.valid_hit = h.valid_hit;
+        r.normal_or_uv[0] = h.n_or_uv[0], r.normal_or_uv[1] = h.n_or_uv[1], r.normal_or_uv[2] = h.n_or_uv[2];
+        r.albedo_or_ids[0] = h.alb_or_ids[0], r.albedo_or_ids[1] = h.alb_or_ids[1], r.albedo_or_ids[2] = h.alb_or_ids[2];
+        p.hits[pixel] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_primary
+__global__ void __launch_bounds__(256)
+k_primary(const __grid_constant__ RenderParams p)
+{
+    const uint32_t lane  = threadIdx.x & 31u;
+    const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t sidx  = chunk * 32u + lane;
+    const bool active    = sidx < p.pixel_count;
+    uint32_t cnt_blas = 0, cnt_tri = 0;
+    bool neural       = false;
+    uint32_t pixel    = 0;
+    Ray ray;
+    HitState h;
+    h.best_t = FLT_MAX, h.valid_hit = 0u;
+    h.n_or_uv[0] = h.n_or_uv[1] = h.n_or_uv[2] = 0.f;
+    h.alb_or_ids[0] = h.alb_or_ids[1] = h.alb_or_ids[2] = 0.f;
+    if (active) {
+        uint32_t rng;
+        pixel = swizzle_pixel(p, p.first_pixel + sidx);
+        ray   = camera_ray(p.cam, pixel, p.sample_idx, p.sample_offset, rng);
+        uint32_t tstack[kTlasStackSize];
+        int tss   = 1;
+        tstack[0] = 0u;
+        while (tss > 0) {
+            uint32_t blas_idx;
+            bool is_neural;
+            if (!tlas_next_blas(p.scene.tlas, ray, tstack, tss, blas_idx, is_neural))
+                break;
+            if (is_neural && !p.ignore_neural_blas) {
+                neural = true;
+            } else if (blas_idx < p.scene.n_blas) {
+                // non_neural_bvh_intersection (path_inference_kernels.cu:195-222): ray.maxt = closest t so far
+                const TriHit th = blas_closest_hit(p.scene.blas[blas_idx], ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
+                if (th.t < h.best_t) { // set_or_update_with_preliminary_its_data (path_module.h:150-175)
+                    h.best_t        = th.t;
+                    h.valid_hit     = 2u;
+                    h.n_or_uv[0]    = th.u, h.n_or_uv[1] = th.v, h.n_or_uv[2] = 0.f;
+                    h.alb_or_ids[0] = __uint_as_float(blas_idx), h.alb_or_ids[1] = __uint_as_float(th.prim);
+                    h.alb_or_ids[2] = 0.f;
+                }
+            }
+        }
+    }
+    // ---- queue compaction: one atomic per warp
+    const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
+    if (qmask) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(qmask) - 1))
+            base = atomicAdd(p.queue_count, (uint32_t)__popc(qmask));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(qmask) - 1);
+        if (active && neural) {
+            const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
+            uint4 *q            = reinterpret_cast<uint4 *>(p.queue + slot);
+            q[0] = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
+            q[1] = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), 0u);
+        }
+    }
+    if (active && !neural)
+        finish_pixel(p, pixel, ray, h);
+    warp_add_counter(p.counters, CNT_RAYS, active ? 1u : 0u);
+    warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
+    warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
+}
+
+// ------------------------------------------------------------------------------------------------ k_neural
+struct NeuralLane {
+    Ray ray;
+    uint32_t pixel;
+    HitState h;
+    float seg_mint, seg_maxt;
+    int nss;
+    bool have_ray, have_query;
+};
+
+__global__ void __launch_bounds__(kNeuralThreads, 2)
+k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetConst nc)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t s_flags[kNeuralThreads / 32];
+    const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles);
+    const uint32_t tmem_base = cta_setup<kNeuralTiles>(nc, smem, lay);
+    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t row       = threadIdx.x % kTileRows;
+    const uint32_t lane      = threadIdx.x & 31u;
+    const uint32_t warp      = threadIdx.x >> 5;
+    TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
+
+    const uint32_t n_queued = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
+    uint32_t nstack[kNeuralStackSize];
+    NeuralLane s;
+    s.have_ray = s.have_query = false;
+    s.nss = 0, s.pixel = 0u;
+
+    uint32_t chunk_base = 0u, chunk_used = 32u;
+    bool exhausted = false;
+    uint32_t cnt_q = 0, cnt_nbvh = 0, cnt_iters = 0;
+
+    for (;;) {
+        // ---------------- walk phase: every lane works until it owns a pending interval (or the queue is drained)
+        for (int round = 0; round < kWalkRounds; ++round) {
+            uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, !s.have_ray);
+            while (need_mask && !exhausted) {
+                if (chunk_used == 32u) {
+                    uint32_t c = 0;
+                    if (lane == 0)
+                        c = atomicAdd(p.queue_cursor, 32u);
+                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                    if (c >= n_queued) {
+                        exhausted = true;
+                        break;
+                    }
+                    chunk_base = c, chunk_used = 0u;
+                }
+                const uint32_t avail = 32u - chunk_used;
+                const uint32_t rank  = __popc(need_mask & ((1u << lane) - 1u));
+                if (!s.have_ray && rank < avail) {
+                    const uint32_t qi = chunk_base + chunk_used + rank;
+                    if (qi < n_queued) {
+                        const uint4 *q = reinterpret_cast<const uint4 *>(p.queue + qi);
+                        const uint4 a = q[0], b = q[1];
+                        uint32_t rng;
+                        s.pixel       = a.x;
+                        s.ray         = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, rng);
+                        s.h.best_t    = __uint_as_float(a.y);
+                        s.h.valid_hit = a.z;
+                        s.h.n_or_uv[0] = __uint_as_float(a.w), s.h.n_or_uv[1] = __uint_as_float(b.x), s.h.n_or_uv[2] = 0.f;
+                        s.h.alb_or_ids[0] = __uint_as_float(b.y), s.h.alb_or_ids[1] = __uint_as_float(b.z), s.h.alb_or_ids[2] = 0.f;
+                        nstack[0]    = 0u;
+                        s.nss        = 1;
+                        s.have_ray   = true;
+                        s.have_query = false;
+                    }
+                }
+                const uint32_t want = __popc(need_mask);
+                chunk_used += want < avail ? want : avail;
+                need_mask = __ballot_sync(0xFFFFFFFFu, !s.have_ray && !(rank < avail));
+            }
+            const bool work = s.have_ray && !s.have_query;
+            if (!__any_sync(0xFFFFFFFFu, work))
+                break;
+            if (work) {
+                // NeuralBVH2::intersect resumed with ray.maxt = closest t so far (neural_bvh_module_common.cuh:529-545)
+                uint32_t node;
+                if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
+                    s.have_query = true;
+                } else {
+                    finish_pixel(p, s.pixel, s.ray, s.h);
+                    s.have_ray = false;
+                }
+            }
+            __syncwarp();
+            if (exhausted && !__any_sync(0xFFFFFFFFu, s.have_ray && !s.have_query))
+                break;
+        }
+        // ---------------- tile-wide agreement: anything to infer?  anything left at all?
+        {
+            const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
+            const uint32_t live = (__any_sync(0xFFFFFFFFu, s.have_ray) || !exhausted) ? 2u : 0u;
+            if (lane == 0)
+                s_flags[warp] = q | live;
+            named_bar_sync(t.bar_id, kTileRows);
+            uint32_t f = 0;
+#pragma unroll
+            for (int w = 0; w < kTileRows / 32; ++w)
+                f |= s_flags[tile * (kTileRows / 32) + w];
+            named_bar_sync(t.bar_id, kTileRows);
+            if (f == 0u)
+                break;
+            if (!(f & 1u))
+                continue;
+        }
+        // ---------------- segment encoding + hash grid -> A tile (a8, a9)
+        float pts[12];
+        if (s.have_query) {
+            float eo[3], ei[3];
+            encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                if (k < p.enc.n_points) {
+                    pts[3 * k]     = lerp_point(eo[0], ei[0], p.enc.point_s[k]);
+                    pts[3 * k + 1] = lerp_point(eo[1], ei[1], p.enc.point_s[k]);
+                    pts[3 * k + 2] = lerp_point(eo[2], ei[2], p.enc.point_s[k]);
+                }
+            }
+        }
+        encode_row_to_tile(nc, t.a_tile, row, pts, s.have_query);
+        fence_proxy_async_smem();
+        // ---------------- MLP on tensor cores (a10), decode + closest-hit update (a11)
+        float y[8];
+        mlp_tile_forward(nc, t, row, y);
+        ++cnt_iters;
+        if (s.have_query) {
+            ++cnt_q;
+            float t_hit;
+            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, 1u, t_hit) && t_hit < s.h.best_t) {
+                s.h.best_t    = t_hit;
+                s.h.valid_hit = 1u;
+                decode_normal(y[2], y[3], y[4], s.h.n_or_uv);
+                s.h.alb_or_ids[0] = y[5], s.h.alb_or_ids[1] = y[6], s.h.alb_or_ids[2] = y[7];
+            }
+            s.have_query = false;
+        }
+    }
+    warp_add_counter(p.counters, CNT_QUERIES, cnt_q);
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    if (row == 0 && p.counters && cnt_iters)
+        atomicAdd(p.counters + CNT_TILE_ITERS, (unsigned long long)cnt_iters);
+    cta_teardown<kNeuralTiles>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static uint32_t g_neural_smem = 0;
+
+cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
+{
+    const SmemLayout lay = smem_layout(wimg_bytes, in_k, kNeuralTiles);
+    g_neural_smem        = lay.total;
+    return cudaFuncSetAttribute(k_neural, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+}
+
+cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream)
+{
+    if (rp.pixel_count == 0)
+        return cudaSuccess;
+    const uint32_t n_chunks = (rp.pixel_count + 31u) >> 5;
+    k_primary<<<(n_chunks + 7u) / 8u, 256, 0, stream>>>(rp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return e;
+    k_neural<<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+    return cudaGetLastError();
+}
+
+} // namespace nbvh

@@ -1,0 +1,136 @@
+// render_common.cuh -- device helpers shared by the tile kernels (k_query, k_render, k_neural) and the primary pass.
+#pragma once
+#include "kernels.cuh"
+
+namespace nbvh {
+
+// ------------------------------------------------------------------------------------------------ CTA setup
+__host__ __device__ constexpr uint32_t tmem_cols(int tiles) { return tiles <= 1 ? 64u : tiles <= 2 ? 128u : tiles <= 4 ? 256u : 512u; }
+
+// Loads the packed weights with one TMA bulk copy, allocates TMEM, initialises the per-tile mbarriers.
+// Returns the TMEM base address.  Must be called by all threads of the CTA.
+template <int kTilesPerCta>
+__device__ __forceinline__ uint32_t cta_setup(const NetConst &nc, uint8_t *smem, const SmemLayout &lay)
+{
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t bar_base = smem_u32(smem + lay.bar_off);
+    const uint32_t w_bar    = bar_base + 8u * kTilesPerCta;
+    if (tid == 0) {
+        for (int t = 0; t < kTilesPerCta; ++t)
+            mbar_init(bar_base + 8u * t, 1u);
+        mbar_init(w_bar, 1u);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(w_bar, nc.wimg_bytes);
+        tma_bulk_g2s(smem_u32(smem + lay.w_off), nc.wimg, nc.wimg_bytes, w_bar);
+    }
+    if (tid < 32) {
+        tmem_alloc(smem_u32(smem + lay.tmem_off), tmem_cols(kTilesPerCta)); // 64 fp32 accumulator columns per tile
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
+    mbar_wait(w_bar, 0u); // weights landed (async proxy writes are visible after the mbarrier completes)
+    return tmem_base;
+}
+
+template <int kTilesPerCta>
+__device__ __forceinline__ void cta_teardown(uint32_t tmem_base)
+{
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, tmem_cols(kTilesPerCta));
+    }
+}
+
+__device__ __forceinline__ TileCtx make_tile(uint8_t *smem, const SmemLayout &lay, const NetConst &nc, uint32_t tile,
+                                             uint32_t tmem_base)
+{
+    const uint32_t a_bytes = kTileRows * (nc.in_k > (uint32_t)kNeurons ? nc.in_k : (uint32_t)kNeurons) * 2u;
+    TileCtx t;
+    t.a_tile   = smem + lay.a_off + tile * a_bytes;
+    t.w_smem   = smem_u32(smem + lay.w_off);
+    t.mma_bar  = smem_u32(smem + lay.bar_off) + 8u * tile;
+    t.tmem_acc = tmem_base + 64u * tile;
+    t.bar_id   = 1u + tile;
+    t.phase    = 0u;
+    return t;
+}
+
+__device__ __forceinline__ void warp_add_counter(unsigned long long *counters, int slot, uint32_t v)
+{
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31u) == 0u && v != 0u && counters)
+        atomicAdd(counters + slot, (unsigned long long)v);
+}
+
+// accumulate_pixel_value (include/cuda/neural/neural_bvh_renderer_kernels.cuh:81-127) on linear memory
+__device__ __forceinline__ float linear_to_srgb(float x)
+{
+    return (x <= 0.0031308f) ? 12.92f * x : 1.055f * powf(fmaxf(x, 0.f), 1.f / 2.4f) - 0.055f;
+}
+
+__device__ __forceinline__ void splat(const RenderParams &p, uint32_t pixel, float r, float g, float b, float alpha)
+{
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.sample_idx > 0)
+        acc = p.accum[pixel];
+    if (p.ema_accumulate) {
+        if (alpha == 0.f && p.sample_idx > 0)
+            return;
+        if (p.sample_idx > 0) {
+            const float w = p.ema_weight, iw = 1.f - p.ema_weight;
+            acc = make_float4(r * w + acc.x * iw, g * w + acc.y * iw, b * w + acc.z * iw, alpha * w + acc.w * iw);
+        } else {
+            acc = make_float4(r, g, b, alpha);
+        }
+        p.accum[pixel] = acc;
+    } else {
+        acc            = make_float4(acc.x + r, acc.y + g, acc.z + b, acc.w + alpha);
+        p.accum[pixel] = acc;
+        const float inv = 1.f / float(p.sample_idx + 1);
+        acc = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+    if (p.ldr) {
+        uchar4 px;
+        px.x = (unsigned char)min(max(int(linear_to_srgb(acc.x) * 256.0f), 0), 255);
+        px.y = (unsigned char)min(max(int(linear_to_srgb(acc.y) * 256.0f), 0), 255);
+        px.z = (unsigned char)min(max(int(linear_to_srgb(acc.z) * 256.0f), 0), 255);
+        px.w = 255;
+        p.ldr[pixel] = px;
+    }
+}
+
+// background_hit_eval (path_inference_kernels.cu:37-59); the HDR environment texture belongs to the shading
+// row and evaluates to black here.
+__device__ __forceinline__ void background(const RenderParams &p, const Ray &ray, float bg[3])
+{
+    bg[0] = bg[1] = bg[2] = 0.f;
+    if (!p.envmap_eval)
+        return;
+    if (p.skylike_background) {
+        const float a = 0.5f * (ray.dy + 1.f);
+        bg[0] = (1.f - a) * 1.f + a * 0.5f;
+        bg[1] = (1.f - a) * 1.f + a * 0.7f;
+        bg[2] = (1.f - a) * 1.f + a * 1.f;
+    }
+}
+
+// 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1)
+__device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_t s)
+{
+    const uint32_t w = p.cam.fb_w, h = p.cam.fb_h;
+    if ((w & 7u) || (h & 3u))
+        return s;
+    const uint32_t chunk = s >> 5, k = s & 31u;
+    const uint32_t bpr = w >> 3;
+    const uint32_t bx = chunk % bpr, by = chunk / bpr;
+    return (by * 4u + (k >> 3)) * w + bx * 8u + (k & 7u);
+}
+
+} // namespace nbvh

@@ -59,7 +59,7 @@ __device__ __forceinline__ void grid_corners(const GridLevel &L, float x, float 
             index = cx + cy * L.res + cz * L.res * L.res;
         else
             index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
-        gc.index[c] = L.mask ? (index & L.mask) : (index % L.size);
+        gc.index[c] = grid_wrap(index, L.mask, L.size);
         float w     = (c & 1) ? px : qx;
         w           = __fmul_rn(w, (c & 2) ? py : qy);
         gc.weight[c] = __fmul_rn(w, (c & 4) ? pz : qz);

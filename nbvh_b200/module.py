@@ -286,6 +286,11 @@ class NeuralPathModule:
     def training_step_count(self):
         return int(self._lib.nbvh_training_step_count(self._h))
 
+    def selftest_division(self, n_trials, seed=1):
+        bad = C.c_uint64(0)
+        self._check(self._lib.nbvh_selftest_division(self._h, int(seed), int(n_trials), C.byref(bad)))
+        return bad.value
+
     # ------------------------------------------------------------------ counters / timing
     def counters(self):
         out = (C.c_uint64 * len(COUNTER_NAMES))()

@@ -256,3 +256,10 @@ def test_chess_query_within_tolerance(chess, oracle, torch_cuda):
 def test_chess_render_1080p_matches_oracle(chess, oracle, torch_cuda):
     cnt = check_render(chess, oracle, torch_cuda, stride=51)
     assert cnt["queries"] > 100000
+
+
+def test_hoisted_division_is_ieee(syn):
+    """The slab tests divide by a per-ray hoisted reciprocal (csrc/device_core.cuh: hoisted_div).  Inside its documented
+    operand range every quotient must carry the same bits as div.rn: 2^28 random + boundary-mantissa pairs on the device."""
+    assert syn["mod"].selftest_division(1 << 28, seed=12345) == 0
+    assert syn["mod"].selftest_division(1 << 24, seed=777) == 0
