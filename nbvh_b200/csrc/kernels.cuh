@@ -24,8 +24,11 @@ struct SceneConst {
     uint32_t n_blas;
 };
 
-struct NeuralQueueEntry { // a ray that reached the neural BLAS: pixel id + closest classical hit so far (32 B)
-    uint4 a, b;
+// A ray with a pending neural leaf interval: pixel id, closest classical hit so far, the interval and the N-BVH stack
+// (a: pixel, best_t, valid_hit, u | b: v, blas_idx, prim, stack size | c: seg_mint, seg_maxt, -, - | st: 24 stack entries)
+struct NeuralQueueEntry {
+    uint4 a, b, c;
+    uint4 st[kNeuralStackSize / 4];
 };
 
 struct RenderParams {

@@ -2,13 +2,15 @@
 // /root/reference/src/cuda/neural/path/path_module.cu:54-245 and kernels K1-K9 at max_depth 1):
 //
 //   k_primary   one thread per pixel, no tensor-core state, full occupancy: camera ray (a6), complete TLAS walk (a4) with the
-//               classical BLAS closest hits (a14) taken on the way; rays whose TLAS walk reaches the neural BLAS are appended
-//               to the neural ray queue with a warp ballot/prefix-sum compaction (one atomic per warp), all others are
-//               finished (background, splat, hit record).
-//   k_neural    persistent tile kernel (tcgen05/TMEM): lanes pull queue entries, regenerate their ray from the pixel id
-//               (same arithmetic -> same bits), walk the N-BVH tree-cut from the root to the next leaf interval (a3), and
-//               every 128-lane tile runs hash-grid encode + MLP + decode (a8-a11) on the pending intervals; the walk resumes
-//               with ray.maxt = current closest t (a12); finished lanes splat and refill from the queue (a13).
+//               classical BLAS closest hits (a14) taken on the way, then -- for rays whose TLAS walk reached the neural BLAS --
+//               the N-BVH walk from the root to the FIRST leaf interval (a3; coherent primary rays, so the long root walk
+//               runs at high SIMT efficiency here).  Rays with a pending interval are appended, stack included, to the
+//               neural ray queue with a warp ballot/prefix-sum compaction (one atomic per warp); all others are finished
+//               (background, splat, hit record).
+//   k_neural    persistent tile kernel (tcgen05/TMEM): lanes pull queue entries (ray regenerated from the pixel id: same
+//               arithmetic -> same bits), every 128-lane tile runs hash-grid encode + MLP + decode (a8-a11) on the pending
+//               intervals, then each lane resumes its walk with ray.maxt = current closest t (a12) -- a short pop/descend --
+//               and finished lanes splat and refill from the queue (a13).
 //
 // Order of BLAS visits: the reference visits the BLAS of a ray in TLAS front-to-back order; here every classical BLAS is
 // intersected before the neural walk starts, which only *prunes* neural leaves behind the classical hit.  The final closest
@@ -55,9 +57,12 @@ k_primary(const __grid_constant__ RenderParams p)
     const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t sidx  = chunk * 32u + lane;
     const bool active    = sidx < p.pixel_count;
-    uint32_t cnt_blas = 0, cnt_tri = 0;
+    uint32_t cnt_blas = 0, cnt_tri = 0, cnt_nbvh = 0;
     bool neural       = false;
     uint32_t pixel    = 0;
+    uint32_t nstack[kNeuralStackSize];
+    int nss        = 0;
+    float seg_mint = 0.f, seg_maxt = 0.f;
     Ray ray;
     HitState h;
     h.best_t = FLT_MAX, h.valid_hit = 0u;
@@ -89,6 +94,12 @@ k_primary(const __grid_constant__ RenderParams p)
                 }
             }
         }
+        if (neural) {
+            // first leaf interval of the tree-cut, ray.maxt = closest classical hit (only prunes: see the header)
+            uint32_t node;
+            nstack[0] = 0u, nss = 1;
+            neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
+        }
     }
     // ---- queue compaction: one atomic per warp
     const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
@@ -99,9 +110,12 @@ k_primary(const __grid_constant__ RenderParams p)
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(qmask) - 1);
         if (active && neural) {
             const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
-            uint4 *q            = reinterpret_cast<uint4 *>(p.queue + slot);
-            q[0] = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
-            q[1] = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), 0u);
+            NeuralQueueEntry *q = p.queue + slot;
+            q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
+            q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
+            q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), 0u, 0u);
+            for (int i = 0; i < nss; i += 4)
+                q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
         }
     }
     if (active && !neural)
@@ -109,6 +123,7 @@ k_primary(const __grid_constant__ RenderParams p)
     warp_add_counter(p.counters, CNT_RAYS, active ? 1u : 0u);
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
     warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
 }
 
 // ------------------------------------------------------------------------------------------------ k_neural
@@ -165,8 +180,8 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 if (!s.have_ray && rank < avail) {
                     const uint32_t qi = chunk_base + chunk_used + rank;
                     if (qi < n_queued) {
-                        const uint4 *q = reinterpret_cast<const uint4 *>(p.queue + qi);
-                        const uint4 a = q[0], b = q[1];
+                        const NeuralQueueEntry *q = p.queue + qi;
+                        const uint4 a = q->a, b = q->b, c = q->c;
                         uint32_t rng;
                         s.pixel       = a.x;
                         s.ray         = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, rng);
@@ -174,10 +189,14 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                         s.h.valid_hit = a.z;
                         s.h.n_or_uv[0] = __uint_as_float(a.w), s.h.n_or_uv[1] = __uint_as_float(b.x), s.h.n_or_uv[2] = 0.f;
                         s.h.alb_or_ids[0] = __uint_as_float(b.y), s.h.alb_or_ids[1] = __uint_as_float(b.z), s.h.alb_or_ids[2] = 0.f;
-                        nstack[0]    = 0u;
-                        s.nss        = 1;
+                        s.nss      = (int)b.w;
+                        s.seg_mint = __uint_as_float(c.x), s.seg_maxt = __uint_as_float(c.y);
+                        for (int i = 0; i < s.nss; i += 4) {
+                            const uint4 v = q->st[i >> 2];
+                            nstack[i] = v.x, nstack[i + 1] = v.y, nstack[i + 2] = v.z, nstack[i + 3] = v.w;
+                        }
                         s.have_ray   = true;
-                        s.have_query = false;
+                        s.have_query = true;
                     }
                 }
                 const uint32_t want = __popc(need_mask);
