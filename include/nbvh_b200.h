@@ -247,6 +247,8 @@ enum {
     NBVH_CNT_BLAS_STEPS,        /* classical BLAS interior steps             */
     NBVH_CNT_TRI_TESTS,         /* triangle tests                            */
     NBVH_CNT_TILE_ITERATIONS,   /* 128-row MLP tiles executed                */
+    NBVH_CNT_QUEUED_RAYS,       /* rays handed from k_primary to k_neural    */
+    NBVH_CNT_NBVH_STEPS_NEURAL, /* the part of NBVH_STEPS taken in k_neural  */
     NBVH_CNT_COUNT
 };
 
@@ -322,6 +324,11 @@ int nbvh_reset_counters(nbvh_ctx *ctx);
  * CUDA events on the launching stream */
 int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches);
 int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable);
+/* per-kernel timing of the frame pipeline without host synchronisation: after enabling, each of the next `max_frames`
+ * nbvh_render calls records CUDA events before k_primary, between k_primary and k_neural, and after k_neural on the
+ * launching stream; nbvh_get_stage_times synchronises on them, returns the two summed durations and re-arms. */
+int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames);
+int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_ms_total, uint32_t *frames);
 
 /* ---- online optimisation ------------------------------------------------------------------------ */
 /* == trainer->training_step(stream, in 9xB, target 8xB) -> ctx.L (16xB) + trainer->loss()

@@ -11,7 +11,8 @@ ERR_NAMES = {0: "OK", -1: "INVALID_ARG", -2: "CUDA", -3: "IO", -4: "PARSE", -5: 
 CONST_RENDERER, CONST_MODULE, CONST_PT_OUTPUT, CONST_PATH, CONST_SCENE, CONST_CAMERA, CONST_SCENE_BBOX, \
     CONST_NETWORK, CONST_OPTIMIZER = range(9)
 
-COUNTER_NAMES = ["rays", "queries", "nbvh_steps", "blas_steps", "tri_tests", "tile_iterations"]
+COUNTER_NAMES = ["rays", "queries", "nbvh_steps", "blas_steps", "tri_tests", "tile_iterations", "queued_rays",
+                 "nbvh_steps_neural"]
 
 
 class RendererConstants(C.Structure):
@@ -140,6 +141,8 @@ SYMBOLS = {
     "nbvh_reset_counters": (_i, [_vp]),
     "nbvh_get_kernel_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_enable_kernel_timing": (_i, [_vp, _i]),
+    "nbvh_enable_stage_timing": (_i, [_vp, _u32]),
+    "nbvh_get_stage_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_training_step": (_i, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_f), _vp]),
     "nbvh_training_forward_backward": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_gradients": (_vp, [_vp]),

@@ -262,6 +262,10 @@ struct nbvh_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float total_ms = 0.f;
     uint32_t launches = 0;
+    // stage timing of the split frame pipeline: event triples (start, between k_primary and k_neural, end) recorded
+    // without host synchronisation; read back by nbvh_get_stage_times
+    std::vector<cudaEvent_t> stage_ev;
+    uint32_t stage_used = 0; // frames recorded
 
     // training state (allocated lazily): tcnn::Trainer's buffers (trainer.h:68-87) + Adam moments and step counters
     float *d_grads = nullptr, *d_master = nullptr, *d_m = nullptr, *d_v = nullptr;
@@ -582,6 +586,8 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaEventDestroy(ctx->ev0);
     if (ctx->ev1)
         cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->stage_ev)
+        cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -1285,10 +1291,17 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     const NetConst nc = make_net_const(ctx);
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, 4 * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
-    if (ctx->mega_kernel)
+    if (ctx->mega_kernel) {
         CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
-    else
-        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st));
+    } else if (3u * (ctx->stage_used + 1u) <= ctx->stage_ev.size()) {
+        cudaEvent_t *e = ctx->stage_ev.data() + 3u * ctx->stage_used;
+        CU_TRY(ctx, cudaEventRecord(e[0], st));
+        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st, e[1]));
+        CU_TRY(ctx, cudaEventRecord(e[2], st));
+        ctx->stage_used++;
+    } else {
+        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st, nullptr));
+    }
     kt.stop();
     return NBVH_OK;
 }
@@ -1363,6 +1376,45 @@ int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
         *total_ms = ctx->total_ms;
     if (launches)
         *launches = ctx->launches;
+    return NBVH_OK;
+}
+
+int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    for (cudaEvent_t e : ctx->stage_ev)
+        cudaEventDestroy(e);
+    ctx->stage_ev.clear();
+    ctx->stage_used = 0;
+    for (uint32_t i = 0; i < 3u * max_frames; i++) {
+        cudaEvent_t e;
+        CU_TRY(ctx, cudaEventCreate(&e));
+        ctx->stage_ev.push_back(e);
+    }
+    return NBVH_OK;
+}
+
+int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_ms_total, uint32_t *frames)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    float a = 0.f, b = 0.f;
+    for (uint32_t i = 0; i < ctx->stage_used; i++) {
+        cudaEvent_t *e = ctx->stage_ev.data() + 3u * i;
+        CU_TRY(ctx, cudaEventSynchronize(e[2]));
+        float m0 = 0.f, m1 = 0.f;
+        CU_TRY(ctx, cudaEventElapsedTime(&m0, e[0], e[1]));
+        CU_TRY(ctx, cudaEventElapsedTime(&m1, e[1], e[2]));
+        a += m0, b += m1;
+    }
+    if (primary_ms_total)
+        *primary_ms_total = a;
+    if (neural_ms_total)
+        *neural_ms_total = b;
+    if (frames)
+        *frames = ctx->stage_used;
+    ctx->stage_used = 0;
     return NBVH_OK;
 }
 

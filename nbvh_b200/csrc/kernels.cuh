@@ -15,6 +15,8 @@ enum Counter {
     CNT_BLAS_STEPS,
     CNT_TRI_TESTS,
     CNT_TILE_ITERS,
+    CNT_QUEUED,
+    CNT_NBVH_STEPS_NEURAL,
     CNT_COUNT
 };
 
@@ -127,7 +129,7 @@ cudaError_t launch_check_nodes(const float4 *nodes, uint32_t n, uint32_t *ok_dev
 cudaError_t launch_selftest_division(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long *mismatches, cudaStream_t stream);
 cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
-cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
+cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream, cudaEvent_t between);
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k);
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);
 

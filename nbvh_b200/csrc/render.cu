@@ -124,6 +124,7 @@ k_primary(const __grid_constant__ RenderParams p)
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
     warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
     warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    warp_add_counter(p.counters, CNT_QUEUED, active && neural ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ k_neural
@@ -271,6 +272,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     }
     warp_add_counter(p.counters, CNT_QUERIES, cnt_q);
     warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    warp_add_counter(p.counters, CNT_NBVH_STEPS_NEURAL, cnt_nbvh);
     if (row == 0 && p.counters && cnt_iters)
         atomicAdd(p.counters + CNT_TILE_ITERS, (unsigned long long)cnt_iters);
     cta_teardown<kNeuralTiles>(tmem_base);
@@ -286,7 +288,7 @@ cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
     return cudaFuncSetAttribute(k_neural, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
 }
 
-cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream)
+cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream, cudaEvent_t between)
 {
     if (rp.pixel_count == 0)
         return cudaSuccess;
@@ -294,6 +296,8 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
     k_primary<<<(n_chunks + 7u) / 8u, 256, 0, stream>>>(rp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
+        return e;
+    if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess)
         return e;
     k_neural<<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
     return cudaGetLastError();

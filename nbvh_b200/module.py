@@ -307,3 +307,13 @@ class NeuralPathModule:
         ms, n = C.c_float(0), C.c_uint32(0)
         self._check(self._lib.nbvh_get_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def enable_stage_timing(self, max_frames):
+        """Event triples around k_primary / k_neural for the next `max_frames` frames (no host synchronisation)."""
+        self._check(self._lib.nbvh_enable_stage_timing(self._h, int(max_frames)))
+
+    def stage_times(self):
+        """-> (k_primary total ms, k_neural total ms, frames) since the last call; synchronises on the events."""
+        a, b, n = C.c_float(0), C.c_float(0), C.c_uint32(0)
+        self._check(self._lib.nbvh_get_stage_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value

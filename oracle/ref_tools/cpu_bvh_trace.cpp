@@ -141,6 +141,7 @@ int main(int argc, char **argv)
     std::vector<float> out_t(n);
     std::vector<uint32_t> out_prim(n);
     double best = 1e30;
+    std::vector<double> rep_s;
     for (int rep = 0; rep < repeats; rep++) {
         const auto t0 = std::chrono::steady_clock::now();
         executor.for_each(0, n, [&](size_t b, size_t e) {
@@ -179,6 +180,7 @@ int main(int argc, char **argv)
         const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (s < best)
             best = s;
+        rep_s.push_back(s);
     }
     size_t hits = 0;
     for (uint32_t i = 0; i < n; i++)
@@ -188,7 +190,10 @@ int main(int argc, char **argv)
         f.write(reinterpret_cast<const char *>(out_t.data()), sizeof(float) * n);
         f.write(reinterpret_cast<const char *>(out_prim.data()), sizeof(uint32_t) * n);
     }
-    printf("{\"mrays_s\": %.4f, \"best_s\": %.6f, \"threads\": %u, \"build_s\": %.3f, \"hits\": %zu, \"n_rays\": %u}\n",
+    printf("{\"mrays_s\": %.4f, \"best_s\": %.6f, \"threads\": %u, \"build_s\": %.3f, \"hits\": %zu, \"n_rays\": %u, \"rep_s\": [",
            n / best / 1e6, best, threads, build_s, hits, n);
+    for (size_t i = 0; i < rep_s.size(); i++)
+        printf("%s%.6f", i ? ", " : "", rep_s[i]);
+    printf("]}\n");
     return 0;
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU session: tests, bench, ncu launch list and one full capture of the dominant kernel.
+# One GPU session: tests, bench (both arms), ncu launch list and full captures of the two frame kernels.
 # usage (under gpurun): bash tools/gpu_round.sh <tag>
 TAG=${1:-r01}
 OUT=gpurun_out
@@ -7,12 +7,14 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt
 timeout 900 python -m pytest tests -x -q -m gpu > $OUT/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
 tail -5 $OUT/${TAG}_pytest.log
-timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
-cat $OUT/${TAG}_bench.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
 cat $OUT/${TAG}_bench_ref.json
+timeout 600 python bench.py --steps 200 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
+cat $OUT/${TAG}_bench.json
+timeout 300 python tools/gpu_perf.py > $OUT/${TAG}_perf.json 2>> $OUT/${TAG}_bench.err
+cat $OUT/${TAG}_perf.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render -s 3 -c 2 -f -o $OUT/${TAG}_k_render \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_neural|k_primary' -s 6 -c 4 -f -o $OUT/${TAG}_frame \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT
