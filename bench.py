@@ -289,134 +289,6 @@ def main():
         tp = os.path.join(REPO, "profiles", "k_neural_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "shipped Chess scene" if root else "synthetic",
-                "config": {"workload": workload + " -- reference arm: CPU closest-hit traversal of the non-neural BLAS (BASELINE config 1)"},
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3]},
-                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: nbvh_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    if root is not None:
-        mod = nbvh_b200.load_chess_module(device=local_rank, max_depth=1, envmap_eval=False)
-    else:
-        cfg, nbvh, tlas, tlas_idx, blas = nbvh_b200.synthetic_scene(fb=(W, H), cut_depth=9)
-        mod = nbvh_b200.NeuralPathModule(cfg, device=local_rank)
-        mod.set_neural_bvh(nbvh)
-        mod.set_scene(tlas, tlas_idx, blas)
-        mod.init_params(1337)
-    n_rays = W * H
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident timing: K launches of k_render, CUDA events on the launching stream
-    stream = torch.cuda.current_stream()
-    for i in range(args.warmup):
-        flush.fill_(i & 0xFF)
-        mod.neural_render(i * world + rank, 0, stream=stream.cuda_stream)
-    barrier()
-    mod.reset_counters()
-    mod.enable_stage_timing(args.steps)  # event triples around k_primary / k_neural inside the timed region, no host sync
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.time()
-    for i in range(args.steps):
-        flush.fill_(i & 0xFF)  # L2 flush between timed iterations (outside the event interval)
-        evs[i][0].record(stream)
-        mod.neural_render((args.warmup + i) * world + rank, 0, stream=stream.cuda_stream)
-        evs[i][1].record(stream)
-    barrier()
-    t_wall = time.time() - t_wall0
-    sampler.stop_flag = True
-    sampler.join()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(sum(step_ms))
-    counters = mod.counters()
-    prim_ms_total, neur_ms_total, stage_frames = mod.stage_times()
-    mod.enable_stage_timing(0)
-
-    # ---------------- end to end through the C-ABI host call (pinned host buffers, copies inside the timed region)
-    ldr_host = torch.empty(n_rays * 4, dtype=torch.uint8, pin_memory=True).numpy()
-    cam = mod.get_constants(nbvh_b200.CONST_CAMERA)
-    for i in range(2):
-        mod.neural_render_host(i, 0, ldr_host=ldr_host, camera=cam)
-    barrier()
-    t0 = time.time()
-    for i in range(args.steps):
-        mod.neural_render_host(args.warmup + i, 0, ldr_host=ldr_host, camera=cam)
-    torch.cuda.synchronize()
-    e2e_s = time.time() - t0
-
-    # ---------------- online optimisation (second half of BASELINE's metric: train samples/s), data parallel:
-    # every rank owns 2^18 slots, gradients (fp32, 21.6 MB) are allreduced by NCCL, Adam is replicated
-    train_B = 1 << 18
-    rng = np.random.default_rng(1234 + rank)
-    tx = torch.from_numpy(rng.uniform(0, 1, size=(train_B, 9)).astype(np.float32)).to(dev)
-    tg = rng.uniform(0, 1, size=(train_B, 8)).astype(np.float32)
-    vis = rng.uniform(0, 1, size=train_B) < 0.5
-    tg[:, 0] = vis
-    tg[~vis, 1:] = 0
-    tt = torch.from_numpy(tg).to(dev)
-    grads = mod.gradient_buffer()
-    train_steps = max(5, min(args.steps, 50))
-
-    def train_step():
-        mod.training_forward_backward(tx, tt, global_batch=train_B * world, stream=stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(grads)
-        mod.optimizer_step(stream=stream.cuda_stream)
-
-    for _ in range(3):
-        train_step()
-    barrier()
-    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    te0.record(stream)
-    for _ in range(train_steps):
-        train_step()
-    te1.record(stream)
-    barrier()
-    train_ms = te0.elapsed_time(te1) / train_steps
-
-    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
-
-    if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = world * n_rays * args.steps / (total_ms * 1e-3) / 1e6
-        e2e_value = world * n_rays * args.steps / (e2e_ms * 1e-3) / 1e6
-        peak, peak_src = measured_peaks()
-        K = args.steps
-        per = {k: v / K for k, v in counters.items()}
-        # algorithmic bytes per launch: 64 B per interior step (child pair), 56 B per triangle test,
-        # 48 B per ray (ray in + hit out), 1600 B per network query (1536 B table gathers + 64 B state)
-        alg_bytes = 64.0 * (per["nbvh_steps"] + per["blas_steps"]) + 56.0 * per["tri_tests"] + 48.0 * per["rays"] + 1600.0 * per["queries"]
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(REPO, "profiles", "k_render_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -435,8 +307,7 @@ def main():
                                  "L2-level gathers, compared with the measured HBM copy bandwidth as SURVEY 8(d) prescribes"},
             "roofline_tensor": {"bound": "tensor", "achieved": tensor_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                                 "frac": (tensor_tflops / tensor_peak) if tensor_peak else None, "kernel": "nbvh::k_neural",
-                                "flop_per_query": 37888, "note": "the MLP is 2.4% of a B200's tensor pipe at this query rate; "
-                                "the kernel is bound by the table gathers and the walk, not by the tensor cores"},
+                                "flop_per_query": 37888},
             "roofline_primary": {"bound": "hbm", "kernel": "nbvh::k_primary", "kernel_ms": primary_ms,
                                  "algorithmic_bytes_per_launch": primary_bytes,
                                  "achieved": primary_bytes / (primary_ms * 1e-3) / 1e9 if primary_ms else None, "peak": peak,
