@@ -306,6 +306,10 @@ int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const 
 /* parity hook: camera_raygen for pixels [first, first+n) (neural_bvh_module_common.cuh:440-446) */
 int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx, int sample_offset, float *o,
                 float *d, void *stream);
+/* parity hook: encode_bvh_network_input_data (neural_bvh_module_kernels.cu:266-303) for n segments
+ * (o,d: n x 3; mint,maxt: n) -> out: n x input_network_dims (the column-major 9xN matrix of the reference) */
+int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const float *mint, const float *maxt,
+                         uint32_t n, float *out, void *stream);
 /* == neural_render(accumulated_spp, sample_offset, neural_bvh) (path_module.cu:139-245): one sample per
  * pixel of the attached framebuffer.  pixel range [first, first+count) restricts the launch to a
  * shard of the image (count = 0 -> whole frame). */

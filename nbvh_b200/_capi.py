@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnbvh_b200.so")
+LIB_PATH = os.environ.get("NBVH_B200_LIB") or os.path.join(HERE, "libnbvh_b200.so")  # override: A/B builds (build.build_variant)
 
 NBVH_OK = 0
 ERR_NAMES = {0: "OK", -1: "INVALID_ARG", -2: "CUDA", -3: "IO", -4: "PARSE", -5: "UNSUPPORTED", -6: "STATE"}
@@ -134,6 +134,7 @@ SYMBOLS = {
     "nbvh_trace_intervals": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "nbvh_blas_intersect": (_i, [_vp, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "nbvh_raygen": (_i, [_vp, _u32, _u32, _i, _i, _vp, _vp, _vp]),
+    "nbvh_encode_segments": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "nbvh_render": (_i, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_render_host": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_selftest_division": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),

@@ -35,5 +35,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A/B experiments on the GPU box: the same sources with extra -D switches -> libnbvh_b200_<name>.so, selected at
+    load time with NBVH_B200_LIB=<path> (development only; the product library is libnbvh_b200.so)."""
+    out = os.path.join(HERE, "libnbvh_b200_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build_variant(sys.argv[i + 1], sys.argv[i + 2:])
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1234,6 +1234,17 @@ int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx,
     return NBVH_OK;
 }
 
+int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n, float *out,
+                         void *stream)
+{
+    if (!ctx || (n && (!o || !d || !mint || !maxt || !out)))
+        return NBVH_ERR_INVALID_ARG;
+    if (ctx->module_const.input_network_dims != 3u * ctx->module_const.input_segment_points)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "encode_segments: directional inputs are not supported");
+    CU_TRY(ctx, launch_encode_segments(make_encode_const(ctx), o, d, mint, maxt, n, out, (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
                 void *stream)
 {

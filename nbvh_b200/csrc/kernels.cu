@@ -121,6 +121,23 @@ __global__ void k_raygen(CameraConst cam, uint32_t first, uint32_t n, int sample
     d[3 * i] = r.dx, d[3 * i + 1] = r.dy, d[3 * i + 2] = r.dz;
 }
 
+// parity hook for a8: the segment points exactly as the frame kernels feed them to the hash grid
+__global__ void k_encode_segments(EncodeConst ec, const float *__restrict__ o, const float *__restrict__ d,
+                                  const float *__restrict__ mint, const float *__restrict__ maxt, uint32_t n, float *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    Ray r;
+    r.ox = o[3 * i], r.oy = o[3 * i + 1], r.oz = o[3 * i + 2];
+    r.dx = d[3 * i], r.dy = d[3 * i + 1], r.dz = d[3 * i + 2];
+    float eo[3], ei[3];
+    encode_endpoints(ec, r, mint[i], maxt[i], eo, ei);
+    for (uint32_t k = 0; k < ec.n_points; ++k)
+        for (int c = 0; c < 3; ++c)
+            out[(size_t)i * 3 * ec.n_points + 3 * k + c] = lerp_point(eo[c], ei[c], ec.point_s[k]);
+}
+
 // Stores a copy of the N-BVH whose boxes are already dilated by fixed_node_dilation (same operations as
 // the on-the-fly dilation -> same bits), so the inference walk does no per-visit dilation arithmetic.
 __global__ void k_predilate(const float4 *__restrict__ src, float4 *__restrict__ dst, uint32_t n, float dilation)
@@ -467,6 +484,15 @@ cudaError_t launch_raygen(const CameraConst &cam, uint32_t first, uint32_t n, in
     if (n == 0)
         return cudaSuccess;
     k_raygen<<<(n + 127) / 128, 128, 0, stream>>>(cam, first, n, sample_idx, sample_offset, o, d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode_segments(const EncodeConst &ec, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n,
+                                   float *out, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_encode_segments<<<(n + 255) / 256, 256, 0, stream>>>(ec, o, d, mint, maxt, n, out);
     return cudaGetLastError();
 }
 

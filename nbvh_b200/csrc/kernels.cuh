@@ -125,6 +125,8 @@ cudaError_t launch_blas_intersect(const BlasConst &b, uint32_t nodes_safe, const
                                   float *u, float *v, uint32_t *prim, unsigned long long *counters, cudaStream_t stream);
 cudaError_t launch_raygen(const CameraConst &cam, uint32_t first, uint32_t n, int sample_idx, int sample_offset, float *o,
                           float *d, cudaStream_t stream);
+cudaError_t launch_encode_segments(const EncodeConst &ec, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n,
+                                   float *out, cudaStream_t stream);
 cudaError_t launch_check_nodes(const float4 *nodes, uint32_t n, uint32_t *ok_dev, cudaStream_t stream);
 cudaError_t launch_selftest_division(uint64_t seed, uint32_t blocks, uint32_t iters, unsigned long long *mismatches, cudaStream_t stream);
 cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream);

@@ -170,6 +170,32 @@ __device__ __forceinline__ uint2 grid_level_features(const uint2 *__restrict__ g
     const float qx = __fsub_rn(1.f, px), qy = __fsub_rn(1.f, py), qz = __fsub_rn(1.f, pz);
 
     uint2 g[8];
+#ifdef NBVH_GRID_PAIRED
+    // The two x-neighbours of a (y,z) corner pair are adjacent table entries on dense levels (index+1) and, when gx is
+    // even, on hashed levels too ((gx^h) and (gx^h)^1): fetch the aligned 16-byte entry pair with one LDG.128 and only
+    // issue the second gather when the neighbour lives elsewhere -> ~25 % fewer L1 lookups per query.
+    const uint4 *__restrict__ pairs = reinterpret_cast<const uint4 *>(grid + L.offset); // level offsets are multiples of 8 entries
+#pragma unroll
+    for (int c2 = 0; c2 < 4; ++c2) {
+        const uint32_t cy = gy + (c2 & 1), cz = gz + (c2 >> 1);
+        uint32_t i0, i1;
+        if (L.dense) {
+            i0 = gx + cy * L.res + cz * L.res * L.res;
+            i1 = i0 + 1u;
+        } else {
+            const uint32_t h = (cy * 2654435761u) ^ (cz * 805459861u);
+            i0 = gx ^ h, i1 = (gx + 1u) ^ h;
+        }
+        i0 = grid_wrap(i0, L.mask, L.size), i1 = grid_wrap(i1, L.mask, L.size);
+        const uint4 pr  = __ldg(pairs + (i0 >> 1));
+        const bool odd  = i0 & 1u;
+        g[2 * c2]       = odd ? make_uint2(pr.z, pr.w) : make_uint2(pr.x, pr.y);
+        if ((i0 ^ i1) == 1u)
+            g[2 * c2 + 1] = odd ? make_uint2(pr.x, pr.y) : make_uint2(pr.z, pr.w);
+        else
+            g[2 * c2 + 1] = __ldg(grid + L.offset + i1);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         const uint32_t cx = gx + (c & 1), cy = gy + ((c >> 1) & 1), cz = gz + ((c >> 2) & 1);
@@ -181,6 +207,7 @@ __device__ __forceinline__ uint2 grid_level_features(const uint2 *__restrict__ g
         index = grid_wrap(index, L.mask, L.size);
         g[c]  = __ldg(grid + L.offset + index);
     }
+#endif
     __half2 r01 = __float2half2_rn(0.f), r23 = __float2half2_rn(0.f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {

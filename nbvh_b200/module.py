@@ -243,6 +243,14 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_raygen(self._h, first_pixel, n, sample_idx, sample_offset, _ptr(o), _ptr(d), stream))
         return o, d
 
+    def encode_segments(self, o, d, mint, maxt, stream=None):
+        """== encode_bvh_network_input_data (neural_bvh_module_kernels.cu:266-303): -> (n, input_network_dims) float32."""
+        torch = _torch()
+        n = o.shape[0]
+        out = torch.zeros((n, self.get_constants(CONST_MODULE).input_network_dims), dtype=torch.float32, device=o.device)
+        self._check(self._lib.nbvh_encode_segments(self._h, _ptr(o), _ptr(d), _ptr(mint), _ptr(maxt), n, _ptr(out), stream))
+        return out
+
     def neural_render(self, accumulated_spp, sample_offset, first_pixel=0, pixel_count=0, stream=None):
         """== neural_render(accumulated_spp, sample_offset, neural_bvh) (path_module.cu:139-245)."""
         self._check(self._lib.nbvh_render(self._h, int(accumulated_spp), int(sample_offset), int(first_pixel),

@@ -398,14 +398,17 @@ static float node_intersect(const onode_t *n, const float o[3], const float d[3]
     return onbvh_slab(n->mn, n->mx, o, d, ray_mint, ray_maxt, 1, &mint, &maxt) ? mint : FLT_MAX;
 }
 
-/* include/cuda/accel/bvh.cuh:98-136.  PTX: cross = mul,mul,sub (not fused);
- * dot(a,b) = fma(a.z,b.z, fma(a.x,b.x, a.y*b.y)); inv_det = rcp.rn(det). */
+/* include/cuda/accel/bvh.cuh:98-136.  dot(a,b) = fma(a.z,b.z, fma(a.x,b.x, a.y*b.y)); inv_det = rcp.rn(det).
+ * cross: the PTX shows mul,mul,sub WITHOUT .rn, and ptxas fuses the minuend product into the subtraction
+ * (SASS of non_neural_bvh_intersection: FMUL r = x2*y2; FFMA out = x1*y1 - r).  Pinned by the reference's own
+ * kernel run on a B200 (tests/golden/ref_chess_256x144.npz): the unfused form differs in 1-2 ulp of t on ~14 % of
+ * the chessboard hits (needle triangles, det ~ 1e-6). */
 static inline float dot_ptx(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[0], b[0], a[1] * b[1])); }
 static inline void cross_ptx(const float x[3], const float y[3], float out[3])
 {
-    out[0] = x[1] * y[2] - y[1] * x[2];
-    out[1] = x[2] * y[0] - y[2] * x[0];
-    out[2] = x[0] * y[1] - y[0] * x[1];
+    out[0] = fmaf(x[1], y[2], -(y[1] * x[2]));
+    out[1] = fmaf(x[2], y[0], -(y[2] * x[0]));
+    out[2] = fmaf(x[0], y[1], -(y[0] * x[1]));
 }
 
 static float tri_intersect(const oblas_t *b, uint32_t prim, const float o[3], const float d[3], float ray_mint,
