@@ -239,6 +239,15 @@ typedef struct {
     float albedo_or_ids[3]; /* neural: albedo; normal: (mesh_idx, prim_idx, 0) bit-cast */
 } nbvh_hit_record;
 
+/* NeuralTreeCutData (include/cuda/neural/neural_bvh_renderer.h:36-47): per tree-cut node loss statistics, owned by
+ * the renderer, read by the sample generator's node-survival roulette */
+typedef struct {
+    float loss;
+    uint32_t iter_alive;
+    uint32_t depth;
+    uint32_t samples;
+} nbvh_tree_cut_data;
+
 /* Counter slots of nbvh_get_counters */
 enum {
     NBVH_CNT_RAYS = 0,          /* rays generated                            */
@@ -348,6 +357,20 @@ int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *
 float *nbvh_gradients(nbvh_ctx *ctx);
 /* Lets the host own the fp32 gradient vector (n_params floats of device memory; NULL -> back to the internal buffer), so
  * the process that drives NCCL can allreduce it in place without a copy. */
+/* == NeuralBVHModule::optimisation_data_generation -> generate_and_fill_bvh_output_reference (path_module.cu:20-52,
+ * kernel granular_sample_bvh_network_input_data, neural_bvh_module_kernels.cu:119-264): fills `inputs`
+ * (batch x input_network_dims) and `targets` (batch x output_network_dims) and the sampled node index of every slot.
+ * The scene set with nbvh_set_scene must carry the neural mesh's classical BLAS (mesh bvh_const.neural_bvh_idx) with its
+ * shading attributes, plus materials / textures when targets need them.  All pointers are device pointers;
+ * batch_size must be a power of two >= 2^log2_bvh_max_traversals. */
+int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uint32_t batch_size,
+                                      uint32_t log2_bvh_max_traversals, uint32_t *sampled_node_indices,
+                                      float current_max_loss, const nbvh_tree_cut_data *tree_cut_data, float *inputs,
+                                      float *targets, void *stream);
+/* harness helper mirroring CudaBackend::create_cuda_textures_buffer (cuda_backend.cpp:387-441): RGBA8 array texture,
+ * wrap addressing, linear filtering, normalized float reads.  Returns a cudaTextureObject_t in *tex_out. */
+int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out);
+int nbvh_destroy_textures(nbvh_ctx *ctx);
 int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);

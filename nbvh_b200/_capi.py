@@ -146,6 +146,9 @@ SYMBOLS = {
     "nbvh_get_stage_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_training_step": (_i, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_f), _vp]),
     "nbvh_training_forward_backward": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
+    "nbvh_optimisation_data_generation": (_i, [_vp, _u32, _u32, _u32, _vp, _f, _vp, _vp, _vp, _vp]),
+    "nbvh_create_texture_rgba8": (_i, [_vp, _vp, _u32, _u32, C.POINTER(_u64)]),
+    "nbvh_destroy_textures": (_i, [_vp]),
     "nbvh_gradients": (_vp, [_vp]),
     "nbvh_set_gradient_buffer": (_i, [_vp, _vp]),
     "nbvh_optimizer_step": (_i, [_vp, _vp]),

@@ -6,6 +6,7 @@
 //  /root/reference/src/cuda/neural/neural_bvh_module.cu:12-263).
 #include "json_min.hpp"
 #include "kernels.cuh"
+#include "sampler.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -243,6 +244,9 @@ struct nbvh_ctx {
     // scene
     SceneConst scene{};
     bool scene_set = false;
+    std::vector<nbvh_cuda_blas> blas_desc; // host copy of the caller's descriptors (shading attributes for the sampler)
+    const void *materials = nullptr, *textures = nullptr;
+    std::vector<std::pair<cudaTextureObject_t, cudaArray_t>> own_textures; // nbvh_create_texture_rgba8
 
     // framebuffer
     float4 *accum = nullptr;
@@ -562,6 +566,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     if (!ctx)
         return;
     cudaSetDevice(ctx->device);
+    nbvh_destroy_textures(ctx);
     cudaFree(ctx->d_params);
     cudaFree(ctx->d_wimg);
     cudaFree(ctx->d_nbvh);
@@ -893,6 +898,9 @@ int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
         if (rc != NBVH_OK)
             return rc;
     }
+    ctx->blas_desc = blas;
+    ctx->materials = s->materials;
+    ctx->textures  = s->textures;
     ctx->scene_set = true;
     return NBVH_OK;
 }
@@ -1242,6 +1250,127 @@ int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const fl
     if (ctx->module_const.input_network_dims != 3u * ctx->module_const.input_segment_points)
         return fail(ctx, NBVH_ERR_UNSUPPORTED, "encode_segments: directional inputs are not supported");
     CU_TRY(ctx, launch_encode_segments(make_encode_const(ctx), o, d, mint, maxt, n, out, (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
+int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uint32_t batch_size, uint32_t log2_bvh_max_traversals,
+                                      uint32_t *sampled_node_indices, float current_max_loss, const nbvh_tree_cut_data *tree_cut_data,
+                                      float *inputs, float *targets, void *stream)
+{
+    if (!ctx || !sampled_node_indices || !inputs || !targets)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->d_nbvh || !ctx->scene_set)
+        return fail(ctx, NBVH_ERR_STATE, "optimisation_data_generation: neural BVH and scene must be set");
+    const nbvh_renderer_constants &bc = ctx->bvh_const;
+    if (batch_size == 0 || (batch_size & (batch_size - 1)) || log2_bvh_max_traversals > 31 || (batch_size >> log2_bvh_max_traversals) == 0)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "batch_size must be a power of two >= 2^log2_bvh_max_traversals");
+    if (bc.ellipsoidal_bvh || bc.view_dependent_sampling || bc.leaf_boundary_sampling_ratio != 0.f)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: ellipsoidal_bvh / view_dependent_sampling / leaf_boundary_sampling_ratio are not implemented");
+    if (ctx->pt_const.depth_learning_mode != 0 /* LocalT */ || ctx->module_const.input_segment_direction_dim != 0 ||
+        ctx->module_const.segment_distribution == 2 /* Uniform */ || ctx->module_const.apply_encoding_trafo)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: only LocalT depth targets and equidistant segment points are implemented");
+    if (bc.training_node_survival && !tree_cut_data)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "training_node_survival needs tree_cut_data");
+    if (bc.neural_bvh_idx >= ctx->blas_desc.size() || ctx->blas_desc[bc.neural_bvh_idx].num_nodes < 1 || !ctx->blas_desc[bc.neural_bvh_idx].nodes)
+        return fail(ctx, NBVH_ERR_STATE, "sampler: the scene has no classical BLAS for the neural mesh");
+    if ((uint32_t)bc.current_learned_lod >= 7u)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "current_learned_lod out of range");
+    const nbvh_cuda_blas &nb = ctx->blas_desc[bc.neural_bvh_idx];
+    SamplerParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.nbvh.nodes      = ctx->d_nbvh;
+    sp.nbvh.num_nodes  = ctx->nbvh_nodes;
+    sp.nbvh.mint_eps   = bc.learning_mint_epsilon;
+    sp.nbvh.maxt_eps   = bc.learning_maxt_epsilon;
+    sp.nbvh.predilated = 0u;
+    sp.blas            = ctx->scene.blas[bc.neural_bvh_idx];
+    sp.attr.normals       = nb.normals;
+    sp.attr.texcoords     = nb.texcoords;
+    sp.attr.material_ids  = nb.material_ids;
+    sp.attr.material_map  = nb.material_map;
+    sp.attr.num_materials = nb.num_materials;
+    if (!nb.material_map || nb.num_materials == 0)
+        sp.attr.material_ids = nullptr; // no material table: every hit takes the default material
+    sp.nodes_safe = 0u; // the raw tree-cut is dilated per sample: every quotient goes through div.rn
+    sp.materials  = reinterpret_cast<const MaterialPod *>(ctx->materials);
+    sp.textures   = reinterpret_cast<const cudaTextureObject_t *>(ctx->textures);
+    sp.enc        = make_encode_const(ctx);
+    for (int i = 0; i < 3; i++) {
+        sp.bbox_min[i] = ctx->scene_bbox.min[i];
+        sp.bbox_ext[i] = ctx->scene_bbox.max[i] - ctx->scene_bbox.min[i];
+    }
+    sp.sampling_bbox_scaling      = bc.sampling_bbox_scaling;
+    sp.fixed_node_dilation        = bc.fixed_node_dilation;
+    sp.node_extent_dilation       = bc.node_extent_dilation;
+    sp.current_learned_lod        = (uint32_t)bc.current_learned_lod;
+    sp.num_bvh_lods               = 7u; // NUM_BVH_LODS, neural_bvh2.cuh:14
+    sp.training_node_survival     = bc.training_node_survival ? 1u : 0u;
+    sp.survival_probability_scale = bc.survival_probability_scale;
+    sp.min_rr_survival_prob       = bc.min_rr_survival_prob;
+    sp.max_training_bounces       = bc.max_training_bounces;
+    sp.backface_bounce_training   = bc.backface_bounce_training ? 1u : 0u;
+    sp.sample_cosine_weighted     = bc.sample_cosine_weighted ? 1u : 0u;
+    sp.n_in        = ctx->module_const.input_network_dims;
+    sp.n_out       = ctx->pt_const.output_network_dims;
+    sp.vis_dim     = ctx->pt_const.output_visibility_dim;
+    sp.depth_dim   = ctx->pt_const.output_depth_dim;
+    sp.normal_dim  = ctx->pt_const.output_normal_dim;
+    sp.albedo_dim  = ctx->pt_const.output_albedo_dim;
+    sp.depth_linear = ctx->pt_const.output_depth_linear_activation ? 1u : 0u;
+    if (sp.depth_dim > 1u || (sp.normal_dim != 0u && sp.normal_dim != 3u) || (sp.albedo_dim != 0u && sp.albedo_dim != 3u) ||
+        sp.vis_dim + sp.depth_dim + sp.normal_dim + sp.albedo_dim != sp.n_out)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: unsupported output layout");
+    sp.sub_batch_size = (int)(batch_size >> log2_bvh_max_traversals);
+    sp.n_sub_batch    = (int)(1u << log2_bvh_max_traversals);
+    sp.rng_index      = training_step * batch_size;
+    sp.sampled_node_indices = sampled_node_indices;
+    sp.inputs           = inputs;
+    sp.targets          = targets;
+    sp.current_max_loss = current_max_loss;
+    sp.tree_cut         = tree_cut_data;
+    sp.counters         = ctx->d_counters;
+    CU_TRY(ctx, launch_generate_batch(sp, (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
+int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out)
+{
+    if (!ctx || !pixels_host || !tex_out || w == 0 || h == 0)
+        return NBVH_ERR_INVALID_ARG;
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    CU_TRY(ctx, cudaMallocArray(&arr, &cd, w, h));
+    CU_TRY(ctx, cudaMemcpy2DToArray(arr, 0, 0, pixels_host, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd = {};
+    rd.resType          = cudaResourceTypeArray;
+    rd.res.array.array  = arr;
+    cudaTextureDesc td  = {};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode          = cudaFilterModeLinear;
+    td.readMode            = cudaReadModeNormalizedFloat;
+    td.normalizedCoords    = 1;
+    td.maxAnisotropy       = 1;
+    td.maxMipmapLevelClamp = 99;
+    td.minMipmapLevelClamp = 0;
+    td.mipmapFilterMode    = cudaFilterModePoint;
+    td.borderColor[0]      = 1.0f;
+    td.sRGB                = 0;
+    cudaTextureObject_t tex = 0;
+    CU_TRY(ctx, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    ctx->own_textures.emplace_back(tex, arr);
+    *tex_out = (uint64_t)tex;
+    return NBVH_OK;
+}
+
+int nbvh_destroy_textures(nbvh_ctx *ctx)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    for (auto &t : ctx->own_textures) {
+        cudaDestroyTextureObject(t.first);
+        cudaFreeArray(t.second);
+    }
+    ctx->own_textures.clear();
     return NBVH_OK;
 }
 

@@ -1,0 +1,339 @@
+// sampler.cu -- online-optimisation sample generator (kernel K10): replaces
+// granular_sample_bvh_network_input_data (/root/reference/src/cuda/neural/neural_bvh_module_kernels.cu:119-264) and the
+// device functions it calls: stack_based_sample_uniform_bvh_density, generate_single_bvh_network_output_reference,
+// compute_depth_or_position_output (include/cuda/neural/neural_bvh_module_common.cuh:586-861), BaseCudaBLAS::compute_its_data
+// (include/cuda/accel/bvh.cuh:53-96), unpack_albedo / unpack_normal (include/cuda/base/material.cuh:66-89),
+// shading_frame / ortho_basis / sample_lambertian_dir / square_to_uniform_sphere.
+//
+// One thread owns n_sub_batch consecutive batch slots (exactly like the reference: a ray that misses the mesh inside a
+// leaf CONTINUES through the tree-cut and its next leaf fills the thread's next slot).  Per slot: sample (or continue) a ray,
+// walk the tree-cut at a random LoD with a random node dilation (learning epsilons), node-survival roulette, encode the leaf
+// segment, trace the leaf segment against the neural mesh's classical BLAS for the targets
+// [hit, local depth, (n+1)/2, albedo].  Slots rejected by the roulette keep their previous contents (the reference's
+// `continue` also skips the slot increment; replicated).
+//
+// Arithmetic: same contract as device_core.cuh (-fmad=false, explicit fma where the reference's SASS fuses).  The
+// traversal, segment encoding and triangle test are the bit-exact building blocks pinned against the reference kernels;
+// the sampling arithmetic (sphere sampling, barycentric interpolation, normal mapping) follows the source expression by
+// expression with the contraction that reproduces the reference kernel's outputs BIT FOR BIT on the shipped Chess scene
+// (node ids, inputs and all 8 targets of every slot; tests/test_sampler.py).  The optional training bounce
+// (max_training_bounces > 1, off in every shipped config) is checked against the oracle with a tolerance only.
+#include "render_common.cuh"
+#include "sampler.cuh"
+
+namespace nbvh {
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 ld3(const float *p, uint32_t i) { return V3{__ldg(p + 3u * i), __ldg(p + 3u * i + 1u), __ldg(p + 3u * i + 2u)}; }
+__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return V3{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b)
+{
+    return V3{__fmaf_rn(a.y, b.z, -__fmul_rn(b.y, a.z)), __fmaf_rn(a.z, b.x, -__fmul_rn(b.z, a.x)), __fmaf_rn(a.x, b.y, -__fmul_rn(b.x, a.y))};
+}
+// glm::normalize: v * inversesqrt(dot(v, v)), inversesqrt = rcp(sqrt) on the device (same pattern as camera_ray)
+__device__ __forceinline__ V3 normalize3(V3 a)
+{
+    const float inv = __frcp_rn(__fsqrt_rn(dot3(a, a)));
+    return V3{__fmul_rn(a.x, inv), __fmul_rn(a.y, inv), __fmul_rn(a.z, inv)};
+}
+// w*a + u*b + v*c per component: the reference's SASS evaluates fma(v,c, fma(w,a, u*b)) (found by matching the reference
+// kernel's outputs bit for bit, tests/golden/ref_chess_sampler.npz)
+__device__ __forceinline__ float bary(float w, float a, float u, float b, float v, float c)
+{
+    return __fmaf_rn(v, c, __fmaf_rn(w, a, __fmul_rn(u, b)));
+}
+
+// include/cuda/utils/common.cuh:21-36
+__device__ __forceinline__ void ortho_basis(V3 &tangent, V3 &bitangent, V3 n)
+{
+    bitangent = v3(0.f, 0.f, 0.f);
+    if (n.x < 0.6f && n.x > -0.6f)
+        bitangent.x = 1.f;
+    else if (n.y < 0.6f && n.y > -0.6f)
+        bitangent.y = 1.f;
+    else if (n.z < 0.6f && n.z > -0.6f)
+        bitangent.z = 1.f;
+    else
+        bitangent.x = 1.f;
+    tangent   = normalize3(cross3(bitangent, n));
+    bitangent = normalize3(cross3(n, tangent));
+}
+
+// include/cuda/utils/sampling.cuh:8-14
+__device__ __forceinline__ V3 square_to_uniform_sphere(float sx, float sy)
+{
+    const float phi       = __fmul_rn(6.2831854820251465f, sx); // 2.0f * PI folded at compile time
+    const float cos_theta = __fmaf_rn(sy, 2.0f, -1.0f);
+    const float sin_theta = __fsqrt_rn(__fmaf_rn(-cos_theta, cos_theta, 1.0f));
+    return V3{__fmul_rn(sin_theta, cosf(phi)), __fmul_rn(sin_theta, sinf(phi)), cos_theta};
+}
+
+// include/cuda/base/material.cuh:101-120,193-200
+__device__ __forceinline__ V3 sample_lambertian_dir(V3 n, V3 tangent, V3 bitangent, float ux, float uy)
+{
+    const float sx = __fmaf_rn(2.f, ux, -1.f), sy = __fmaf_rn(2.f, uy, -1.f);
+    float dx = sx, dy = sy;
+    if (!(sx == 0.f && sy == 0.f)) {
+        float radius, theta;
+        if (fabsf(sx) > fabsf(sy)) {
+            radius = sx;
+            theta  = __fmul_rn(0.78539818525314331f, __fdiv_rn(sy, sx));
+        } else {
+            radius = sy;
+            theta  = __fsub_rn(1.5707963705062866f, __fmul_rn(0.78539818525314331f, __fdiv_rn(sx, sy)));
+        }
+        dx = __fmul_rn(radius, cosf(theta)), dy = __fmul_rn(radius, sinf(theta));
+    }
+    const float dz = __fsqrt_rn(fmaxf(0.f, __fsub_rn(__fsub_rn(1.f, __fmul_rn(dx, dx)), __fmul_rn(dy, dy))));
+    const V3 h = normalize3(v3(dx, dy, dz));
+    return V3{bary(h.x, tangent.x, h.y, bitangent.x, h.z, n.x), bary(h.x, tangent.y, h.y, bitangent.y, h.z, n.y),
+              bary(h.x, tangent.z, h.y, bitangent.z, h.z, n.z)};
+}
+
+struct ItsData {
+    V3 position, sh_normal;
+    float u, v; // texture coordinates
+    int material_id;
+};
+
+__device__ __forceinline__ float4 tex_fetch(const cudaTextureObject_t *textures, uint32_t id, float u, float v)
+{
+    return tex2D<float4>(textures[id], u, v);
+}
+
+// BaseCudaBLAS::compute_its_data (bvh.cuh:53-96)
+__device__ __forceinline__ ItsData compute_its_data(const SamplerParams &p, const TriHit &h)
+{
+    ItsData its;
+    const uint32_t i0 = __ldg(p.blas.indices + 3u * h.prim), i1 = __ldg(p.blas.indices + 3u * h.prim + 1u),
+                   i2 = __ldg(p.blas.indices + 3u * h.prim + 2u);
+    // upper_bound(material_map, num_materials, prim) - 1
+    uint32_t left = 0, right = p.attr.num_materials;
+    while (left < right) {
+        const uint32_t mid = left + (right - left) / 2u;
+        if (__ldg(p.attr.material_map + mid) <= h.prim)
+            left = mid + 1u;
+        else
+            right = mid;
+    }
+    its.material_id = p.attr.material_ids ? __ldg(p.attr.material_ids + (left - 1u)) : -1;
+    const V3 v0 = ld3(p.blas.vertices, i0), v1 = ld3(p.blas.vertices, i1), v2 = ld3(p.blas.vertices, i2);
+    const float w = __fsub_rn(__fsub_rn(1.f, h.u), h.v);
+    if (p.attr.normals) {
+        const V3 n0 = ld3(p.attr.normals, i0), n1 = ld3(p.attr.normals, i1), n2 = ld3(p.attr.normals, i2);
+        its.sh_normal = normalize3(v3(bary(w, n0.x, h.u, n1.x, h.v, n2.x), bary(w, n0.y, h.u, n1.y, h.v, n2.y), bary(w, n0.z, h.u, n1.z, h.v, n2.z)));
+    } else {
+        its.sh_normal = normalize3(cross3(sub3(v1, v0), sub3(v2, v0)));
+    }
+    its.position = v3(bary(w, v0.x, h.u, v1.x, h.v, v2.x), bary(w, v0.y, h.u, v1.y, h.v, v2.y), bary(w, v0.z, h.u, v1.z, h.v, v2.z));
+    if (p.attr.texcoords) {
+        const float *t = p.attr.texcoords;
+        its.u = bary(w, __ldg(t + 2u * i0), h.u, __ldg(t + 2u * i1), h.v, __ldg(t + 2u * i2));
+        its.v = bary(w, __ldg(t + 2u * i0 + 1u), h.u, __ldg(t + 2u * i1 + 1u), h.v, __ldg(t + 2u * i2 + 1u));
+    } else {
+        its.u = h.u, its.v = h.v;
+    }
+    if (its.material_id != -1 && p.materials) {
+        // unpack_normal (material.cuh:66-75): tangent-space normal map -> world
+        const uint32_t mask = __float_as_uint(p.materials[its.material_id].normal[0]);
+        if (mask & 0x80000000u) {
+            const float4 tx = tex_fetch(p.textures, mask & 0x1fffffffu, its.u, its.v);
+            if (!(tx.x == -1.f && tx.y == -1.f && tx.z == -1.f)) {
+                const V3 tsn = normalize3(v3(__fsub_rn(tx.x, 0.5f), __fsub_rn(tx.y, 0.5f), __fsub_rn(tx.z, 0.5f)));
+                V3 tw, bw;
+                ortho_basis(tw, bw, its.sh_normal);
+                const V3 n = its.sh_normal; // mat3(tw, bw, n) * tsn = tw*x + bw*y + n*z
+                its.sh_normal = v3(bary(tw.x, tsn.x, bw.x, tsn.y, n.x, tsn.z), bary(tw.y, tsn.x, bw.y, tsn.y, n.y, tsn.z),
+                                   bary(tw.z, tsn.x, bw.z, tsn.y, n.z, tsn.z));
+            }
+        }
+    }
+    return its;
+}
+
+__global__ void __launch_bounds__(128)
+k_generate_batch(const __grid_constant__ SamplerParams p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.sub_batch_size)
+        return;
+    NbvhConst bc = p.nbvh;
+    uint32_t nstack[kNeuralStackSize];
+    int nss = 0;
+    float leaf_mint = 0.f, leaf_maxt = 0.f;
+    Ray ray;
+    ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
+    ray_prepare(ray, false);
+    bool continue_traversal = false, swap_dir = false;
+    int training_bounce = 0;
+    uint32_t cnt_nbvh = 0, cnt_blas = 0, cnt_tri = 0, cnt_written = 0;
+
+    uint32_t slot = (uint32_t)i * (uint32_t)p.n_sub_batch;
+    for (int inner = 0; inner < p.n_sub_batch; ++inner) {
+        uint32_t rng = lcg_rng_init(p.rng_index, 0u, slot);
+        // ---------------- stack_based_sample_uniform_bvh_density (neural_bvh_module_common.cuh:703-781)
+        const float s0 = lcg_randomf(rng), s1 = lcg_randomf(rng);
+        const V3 dir   = square_to_uniform_sphere(s0, s1);
+        bool valid     = continue_traversal && nss != 0;
+        bool restarted = false;
+        const uint32_t n_lods = p.num_bvh_lods - p.current_learned_lod;
+        const uint32_t lod    = p.current_learned_lod + min((uint32_t)__fmul_rn(lcg_randomf(rng), __uint2float_rn(n_lods)), n_lods - 1u);
+        bc.leaf_lod_max       = 2u + lod;
+        bc.dilation           = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
+        uint32_t node_idx     = 0u;
+        do {
+            if (!valid) {
+                nstack[0] = 0u, nss = 1;
+                const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
+                const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
+                const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
+                            lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
+                ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
+                ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
+                ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
+                ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+                ray_prepare(ray, p.nodes_safe != 0u);
+                restarted = true;
+            }
+            valid = nbvh_next_interval(bc, ray, nstack, nss, FLT_MAX, leaf_mint, leaf_maxt, node_idx, cnt_nbvh);
+        } while (!valid);
+        p.sampled_node_indices[slot] = node_idx;
+        if (restarted) {
+            training_bounce = 0;
+            swap_dir        = false;
+        }
+        if (swap_dir && leaf_mint >= 0.f)
+            swap_dir = false;
+        // ---------------- node survival roulette (neural_bvh_module_kernels.cu:181-198)
+        if (p.training_node_survival) {
+            const nbvh_tree_cut_data nd = p.tree_cut[node_idx];
+            float est = -FLT_MAX;
+            if (nd.samples != 0u) {
+                const float ia = __uint2float_rn(nd.iter_alive);
+                est = __fdiv_rn(nd.loss, __fmul_rn(ia, __fsqrt_rn(__fdiv_rn(__uint2float_rn(nd.samples), ia))));
+            }
+            float keep = fmaxf(p.min_rr_survival_prob, __fdiv_rn(est, p.current_max_loss));
+            if (!(est <= p.current_max_loss))
+                keep = 1.f;
+            if (__fmul_rn(p.survival_probability_scale, keep) < lcg_randomf(rng))
+                continue; // the slot is NOT advanced and keeps its previous contents (reference quirk)
+        }
+        // ---------------- inputs: encode_segment_from_world_po_pi (neural_bvh_module_kernels.cu:10-97)
+        {
+            const float t_o = swap_dir ? leaf_maxt : leaf_mint, t_i = swap_dir ? leaf_mint : leaf_maxt;
+            float eo[3], ei[3];
+            encode_endpoints_raw(p.enc, ray, t_o, t_i, eo, ei);
+            float *in = p.inputs + (size_t)slot * p.n_in;
+            for (uint32_t k = 0; k < p.enc.n_points; ++k) {
+                in[3u * k]      = lerp_point(eo[0], ei[0], p.enc.point_s[k]);
+                in[3u * k + 1u] = lerp_point(eo[1], ei[1], p.enc.point_s[k]);
+                in[3u * k + 2u] = lerp_point(eo[2], ei[2], p.enc.point_s[k]);
+            }
+        }
+        // ---------------- targets: generate_single_bvh_network_output_reference (neural_bvh_module_common.cuh:783-861)
+        Ray tr = ray;
+        float seg_mint = leaf_mint, seg_maxt = leaf_maxt;
+        if (swap_dir) {
+            tr.dx = -ray.dx, tr.dy = -ray.dy, tr.dz = -ray.dz;
+            ray_prepare(tr, p.nodes_safe != 0u);
+            seg_mint = -leaf_maxt, seg_maxt = -leaf_mint;
+        }
+        const TriHit hit = blas_closest_hit(p.blas, tr, seg_mint, seg_maxt, cnt_blas, cnt_tri);
+        const bool is_hit = hit.prim != 0xFFFFFFFFu;
+        float *tg = p.targets + (size_t)slot * p.n_out;
+        uint32_t o = 0;
+        tg[o] = is_hit ? 1.f : 0.f;
+        o += p.vis_dim;
+        ItsData its;
+        if (is_hit && (p.normal_dim || p.albedo_dim || p.max_training_bounces > 0))
+            its = compute_its_data(p, hit);
+        if (p.depth_dim) { // LocalT: (t - mint) / ((double)len + 1e-3), evaluated in double like the reference's literal
+            float depth = 0.f;
+            if (is_hit) {
+                const float len = __fsub_rn(seg_maxt, seg_mint);
+                depth = __double2float_rn(__ddiv_rn((double)__fsub_rn(hit.t, seg_mint), __dadd_rn((double)len, 1e-3)));
+                if (p.depth_linear)
+                    depth = __fmaf_rn(depth, 0.1f, 0.45f);
+            }
+            tg[o] = depth;
+            o += p.depth_dim;
+        }
+        if (p.normal_dim) {
+            tg[o]      = is_hit ? __fmul_rn(__fadd_rn(its.sh_normal.x, 1.f), 0.5f) : 0.f;
+            tg[o + 1u] = is_hit ? __fmul_rn(__fadd_rn(its.sh_normal.y, 1.f), 0.5f) : 0.f;
+            tg[o + 2u] = is_hit ? __fmul_rn(__fadd_rn(its.sh_normal.z, 1.f), 0.5f) : 0.f;
+            o += p.normal_dim;
+        }
+        if (p.albedo_dim) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if (is_hit) {
+                a0 = a1 = a2 = 0.9f; // CudaMaterial{}.base_color
+                if (its.material_id != -1 && p.materials) { // unpack_albedo (material.cuh:80-89)
+                    const MaterialPod &m = p.materials[its.material_id];
+                    const uint32_t mask  = __float_as_uint(m.base_color[0]);
+                    if (mask & 0x80000000u) {
+                        const float4 tx = tex_fetch(p.textures, mask & 0x1fffffffu, its.u, its.v);
+                        a0 = tx.x, a1 = tx.y, a2 = tx.z;
+                    } else {
+                        a0 = m.base_color[0], a1 = m.base_color[1], a2 = m.base_color[2];
+                    }
+                }
+            }
+            tg[o] = a0, tg[o + 1u] = a1, tg[o + 2u] = a2;
+            o += p.albedo_dim;
+        }
+        ++cnt_written;
+        swap_dir           = false;
+        continue_traversal = !is_hit;
+        // ---------------- optional training bounce (neural_bvh_module_kernels.cu:223-259)
+        if (is_hit && p.max_training_bounces > 0) {
+            ++training_bounce;
+            V3 wo = v3(-ray.dx, -ray.dy, -ray.dz), shn = its.sh_normal, tangent, bitangent;
+            bool backface = false;
+            if (dot3(wo, shn) < 0.f) { // shading_frame (rendering.cuh:11-22)
+                shn      = v3(-shn.x, -shn.y, -shn.z);
+                backface = true;
+            }
+            ortho_basis(tangent, bitangent, shn);
+            if ((backface && !p.backface_bounce_training) || training_bounce >= p.max_training_bounces) {
+                training_bounce    = 0;
+                continue_traversal = false;
+            } else {
+                const float u0 = lcg_randomf(rng), u1 = lcg_randomf(rng);
+                V3 d;
+                if (p.sample_cosine_weighted) {
+                    d = sample_lambertian_dir(shn, tangent, bitangent, u0, u1);
+                } else {
+                    d = square_to_uniform_sphere(u0, u1);
+                    if (!(__fmul_rn(dot3(wo, shn), dot3(d, shn)) > 0.f))
+                        d = v3(-d.x, -d.y, -d.z);
+                }
+                ray.ox = its.position.x, ray.oy = its.position.y, ray.oz = its.position.z;
+                ray.dx = d.x, ray.dy = d.y, ray.dz = d.z;
+                ray_prepare(ray, p.nodes_safe != 0u);
+                continue_traversal = true;
+                swap_dir           = true;
+                nstack[0] = 0u, nss = 1;
+            }
+        }
+        ++slot;
+    }
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
+    warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
+    warp_add_counter(p.counters, CNT_RAYS, cnt_written);
+}
+
+cudaError_t launch_generate_batch(const SamplerParams &p, cudaStream_t stream)
+{
+    if (p.sub_batch_size <= 0)
+        return cudaSuccess;
+    k_generate_batch<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace nbvh

@@ -1,0 +1,53 @@
+// sampler.cuh -- parameter block of the online-optimisation sample generator (sampler.cu), shared with context.cu
+#pragma once
+#include "kernels.cuh"
+
+namespace nbvh {
+
+// PackedMaterial == Material + vtable pointer (include/base/material.h:52-87): 96 bytes
+struct MaterialPod {
+    unsigned long long vptr;
+    float base_color[3], metallic;
+    float specular, roughness, specular_tint, anisotropy;
+    float sheen, sheen_tint, clearcoat, clearcoat_gloss;
+    float base_emission[3], emission_scale;
+    float normal[3], ior;
+    float specular_transmission, pad;
+};
+static_assert(sizeof(MaterialPod) == 96, "PackedMaterial layout");
+
+struct BlasAttr { // BaseCudaBLAS shading attributes (include/cuda/accel/bvh.cuh:11-23)
+    const float *normals, *texcoords;
+    const int *material_ids;
+    const uint32_t *material_map;
+    uint32_t num_materials;
+};
+
+struct SamplerParams {
+    NbvhConst nbvh; // raw (undilated) node array, learning epsilons; leaf_lod_max / dilation are set per slot
+    BlasConst blas; // the neural mesh's classical BLAS (bvh_const.neural_bvh_idx)
+    BlasAttr attr;
+    uint32_t nodes_safe;
+    const MaterialPod *materials;
+    const cudaTextureObject_t *textures;
+    EncodeConst enc;
+    float bbox_min[3], bbox_ext[3];
+    float sampling_bbox_scaling, fixed_node_dilation, node_extent_dilation;
+    uint32_t current_learned_lod, num_bvh_lods;
+    uint32_t training_node_survival;
+    float survival_probability_scale, min_rr_survival_prob;
+    int max_training_bounces;
+    uint32_t backface_bounce_training, sample_cosine_weighted;
+    uint32_t n_in, n_out, vis_dim, depth_dim, normal_dim, albedo_dim, depth_linear;
+    int sub_batch_size, n_sub_batch;
+    uint32_t rng_index; // training_step * batch_size
+    uint32_t *sampled_node_indices;
+    float *inputs, *targets;
+    float current_max_loss;
+    const nbvh_tree_cut_data *tree_cut;
+    unsigned long long *counters;
+};
+
+cudaError_t launch_generate_batch(const SamplerParams &p, cudaStream_t stream);
+
+} // namespace nbvh

@@ -17,6 +17,12 @@ from ._capi import (CONST_CAMERA, CONST_MODULE, CONST_NETWORK, CONST_OPTIMIZER, 
                     CONST_RENDERER, CONST_SCENE, CONST_SCENE_BBOX, CONST_TYPES, COUNTER_NAMES)
 
 NODE_DTYPE = np.dtype([("mn", "<f4", 3), ("a", "<u4"), ("mx", "<f4", 3), ("b", "<u4")])
+# PackedMaterial (include/base/material.h:52-87): vtable pointer + Disney parameters; a negative float encodes a texture handle
+MATERIAL_DTYPE = np.dtype([("vptr", "<u8"), ("base_color", "<f4", 3), ("metallic", "<f4"), ("specular", "<f4"), ("roughness", "<f4"),
+                           ("specular_tint", "<f4"), ("anisotropy", "<f4"), ("sheen", "<f4"), ("sheen_tint", "<f4"),
+                           ("clearcoat", "<f4"), ("clearcoat_gloss", "<f4"), ("base_emission", "<f4", 3), ("emission_scale", "<f4"),
+                           ("normal", "<f4", 3), ("ior", "<f4"), ("specular_transmission", "<f4"), ("pad", "<f4")])
+TREE_CUT_DTYPE = np.dtype([("loss", "<f4"), ("iter_alive", "<u4"), ("depth", "<u4"), ("samples", "<u4")])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("valid_hit", "<u4"), ("normal_or_uv", "<f4", 3), ("albedo_or_ids", "<f4", 3)])
 
 
@@ -109,10 +115,12 @@ class NeuralPathModule:
         return self.get_constants(CONST_PT_OUTPUT).output_network_dims
 
     # ------------------------------------------------------------------ scene / tree-cut / weights
-    def set_scene(self, tlas_nodes, tlas_indices, blas_list):
+    def set_scene(self, tlas_nodes, tlas_indices, blas_list, materials=None, textures=None):
         """Uploads a scene description (numpy arrays) and hands the device pointers over, standing in for
-        CudaBackend's buffers (cuda_backend.cpp:186-385).  blas_list: dicts with nodes, prim_ids, vertices,
-        indices (prim ids are widened to 64 bit: the reference stores size_t)."""
+        CudaBackend's buffers (cuda_backend.cpp:186-441).  blas_list: dicts with nodes, prim_ids, vertices,
+        indices (prim ids are widened to 64 bit: the reference stores size_t) and, for the training sampler, the optional
+        shading attributes normals, texcoords, material_ids, material_map.  materials: MATERIAL_DTYPE array
+        (PackedMaterial); textures: list of (H, W, 4) uint8 images (RGBA8, wrap + linear like the reference's)."""
         torch = _torch()
         dev = torch.device("cuda", self.device)
 
@@ -137,6 +145,13 @@ class NeuralPathModule:
             descs[i].vertices = verts.data_ptr()
             descs[i].indices = idx.data_ptr()
             descs[i].nodes = nodes.data_ptr()
+            for key, dt in (("normals", np.float32), ("texcoords", np.float32), ("material_ids", np.int32), ("material_map", np.uint32)):
+                if b.get(key) is not None:
+                    t = up(np.ascontiguousarray(b[key], dtype=dt), None)
+                    keep.append(t)
+                    setattr(descs[i], key, t.data_ptr())
+            if b.get("material_map") is not None:
+                descs[i].num_materials = len(b["material_map"])
         d_descs = torch.from_numpy(np.frombuffer(bytes(descs), dtype=np.uint8).copy()).to(dev)
         keep.append(d_descs)
         sd = _capi.SceneData()
@@ -145,6 +160,22 @@ class NeuralPathModule:
         sd.blas_indices = t_idx.data_ptr()
         sd.mesh_bvhs = d_descs.data_ptr()
         sd.num_meshes = len(blas_list)
+        if materials is not None:
+            m = up(np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE), None)
+            keep.append(m)
+            sd.materials = m.data_ptr()
+        if textures:
+            self._check(self._lib.nbvh_destroy_textures(self._h))
+            handles = np.zeros(len(textures), np.uint64)
+            for k, img in enumerate(textures):
+                img = np.ascontiguousarray(img, dtype=np.uint8)
+                assert img.ndim == 3 and img.shape[2] == 4
+                h = C.c_uint64(0)
+                self._check(self._lib.nbvh_create_texture_rgba8(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], C.byref(h)))
+                handles[k] = h.value
+            t = up(handles, None)
+            keep.append(t)
+            sd.textures = t.data_ptr()
         self._check(self._lib.nbvh_set_scene(self._h, C.byref(sd)))
         self._keep["scene"] = keep
 
@@ -272,6 +303,15 @@ class NeuralPathModule:
             self._check(self._lib.nbvh_set_gradient_buffer(self._h, _ptr(g)))
             self._keep["grads"] = g
         return self._keep["grads"]
+
+    def optimisation_data_generation(self, training_step, batch_size, log2_bvh_max_traversals, sampled_node_indices, current_max_loss,
+                                     tree_cut_data, inputs, targets, stream=None):
+        """== NeuralBVHModule::optimisation_data_generation (neural_bvh_module.h:172-180, path_module.cu:20-52): torch CUDA
+        tensors; sampled_node_indices int32/uint32 [B], tree_cut_data uint8 view of TREE_CUT_DTYPE[num_nodes] (or None),
+        inputs float32 [B, in_dims], targets float32 [B, out_dims] -- all updated in place."""
+        self._check(self._lib.nbvh_optimisation_data_generation(self._h, int(training_step), int(batch_size), int(log2_bvh_max_traversals),
+                                                                _ptr(sampled_node_indices), C.c_float(current_max_loss),
+                                                                _ptr(tree_cut_data), _ptr(inputs), _ptr(targets), stream))
 
     def training_forward_backward(self, inputs, targets, global_batch=None, per_sample_loss=None, loss_sum=None, stream=None):
         """Forward + composite loss + backward; leaves loss-scaled (x128) fp32 gradients in the gradient buffer."""

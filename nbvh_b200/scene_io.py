@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .module import NODE_DTYPE, NeuralPathModule
+from .module import MATERIAL_DTYPE, NODE_DTYPE, TREE_CUT_DTYPE, NeuralPathModule
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHESS_BASE = "nodes_32940_hash_18_lvl_8_tsteps_10000"
@@ -21,7 +21,57 @@ def chess_fixture_dir():
     return d if os.path.exists(os.path.join(d, "manifest.json")) else None
 
 
-def load_scene_arrays(root, with_neural_mesh=False):
+def texture_handle(tex_id, channel=0):
+    """A material parameter that refers to a texture: sign bit set, channel in bits 29-30, id below
+    (include/base/material.h:8-28), as the float32 whose bit pattern it is."""
+    return np.array([0x80000000 | ((channel & 3) << 29) | (tex_id & 0x1FFFFFFF)], dtype=np.uint32).view(np.float32)[0]
+
+
+def procedural_materials(n_materials, tex_size=64, seed=7):
+    """Deterministic stand-in for the glTF materials (JPEG decoding belongs to the host application): every second
+    material has a base-colour texture, every third a tangent-space normal map; smooth RGBA8 patterns.
+    Returns (MATERIAL_DTYPE array, list of (H, W, 4) uint8 textures)."""
+    rng = np.random.default_rng(seed)
+    mats = np.zeros(n_materials, dtype=MATERIAL_DTYPE)
+    mats["base_color"] = 0.9
+    mats["roughness"] = 1.0
+    mats["emission_scale"] = 1.0
+    mats["ior"] = 1.5
+    yy, xx = np.meshgrid(np.arange(tex_size) / tex_size, np.arange(tex_size) / tex_size, indexing="ij")
+    textures = []
+    for m in range(n_materials):
+        if m % 2 == 0:
+            img = np.zeros((tex_size, tex_size, 4), np.float64)
+            for ch in range(3):
+                kx, ky = rng.integers(1, 4, 2)
+                img[..., ch] = 0.5 + 0.4 * np.sin(2 * np.pi * (kx * xx + ky * yy + rng.uniform()))
+            img[..., 3] = 1.0
+            mats["base_color"][m, 0] = texture_handle(len(textures))
+            textures.append(np.clip(np.rint(img * 255), 0, 255).astype(np.uint8))
+        else:
+            mats["base_color"][m] = rng.uniform(0.1, 0.9, 3).astype(np.float32)
+        if m % 3 == 0:
+            kx, ky = rng.integers(1, 3, 2)
+            nx = 0.25 * np.sin(2 * np.pi * (kx * xx + rng.uniform()))
+            ny = 0.25 * np.cos(2 * np.pi * (ky * yy + rng.uniform()))
+            img = np.stack([0.5 + 0.5 * nx, 0.5 + 0.5 * ny, np.full_like(nx, 1.0), np.ones_like(nx)], axis=-1)
+            mats["normal"][m, 0] = texture_handle(len(textures))
+            textures.append(np.clip(np.rint(img * 255), 0, 255).astype(np.uint8))
+    return mats, textures
+
+
+def procedural_tree_cut(n_nodes, seed=11):
+    """Deterministic NeuralTreeCutData stand-in (the renderer owns the real statistics): ~10 % of the nodes unsampled."""
+    rng = np.random.default_rng(seed)
+    cut = np.zeros(n_nodes, dtype=TREE_CUT_DTYPE)
+    cut["loss"] = rng.uniform(0.0, 400.0, n_nodes).astype(np.float32)
+    cut["iter_alive"] = rng.integers(1, 100, n_nodes)
+    cut["depth"] = rng.integers(0, 20, n_nodes)
+    cut["samples"] = rng.integers(1, 5000, n_nodes) * (rng.uniform(size=n_nodes) > 0.1)
+    return cut
+
+
+def load_scene_arrays(root, with_neural_mesh=False, with_attributes=False):
     man = json.load(open(os.path.join(root, "manifest.json")))
     blas = []
     for i, m in enumerate(man["meshes"]):
@@ -35,6 +85,10 @@ def load_scene_arrays(root, with_neural_mesh=False):
                          prim_ids=np.fromfile(p + "_prim_ids.u32", dtype="<u4"),
                          vertices=np.fromfile(p + "_vertices.f32", dtype="<f4"),
                          indices=np.fromfile(p + "_indices.u32", dtype="<u4")))
+        if with_attributes:
+            blas[-1].update(normals=np.fromfile(p + "_normals.f32", dtype="<f4"), texcoords=np.fromfile(p + "_texcoords.f32", dtype="<f4"),
+                            material_ids=np.fromfile(p + "_material_ids.i32", dtype="<i4"),
+                            material_map=np.fromfile(p + "_material_map.u32", dtype="<u4"))
     tlas_nodes = np.fromfile(os.path.join(root, "tlas_nodes.bin"), dtype=NODE_DTYPE)
     tlas_idx = np.fromfile(os.path.join(root, "tlas_indices.u32"), dtype="<u4")
     return tlas_nodes, tlas_idx, blas, man

@@ -790,6 +790,299 @@ int onbvh_decode(const oconst_t *c, const float *y, float seg_mint, float seg_ma
     return t != FLT_MAX;
 }
 
+
+/* ------------------------------------------------------------------ training-sample generator (a17, K10) */
+/* CUDA texture unit, cudaFilterModeLinear + cudaAddressModeWrap + normalized coordinates + cudaReadModeNormalizedFloat
+ * (CUDA programming guide, "Texture fetching": x = frac(u)*N - 0.5, weights in 1.8 fixed point). */
+void onbvh_tex2d(const otexture_t *t, float u, float v, float out[4])
+{
+    float x = (u - floorf(u)) * (float)t->w - 0.5f, y = (v - floorf(v)) * (float)t->h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = floorf((x - fx) * 256.f + 0.5f) / 256.f, b = floorf((y - fy) * 256.f + 0.5f) / 256.f;
+    int i0 = (int)fx, j0 = (int)fy;
+    int i1 = i0 + 1, j1 = j0 + 1;
+    i0 = ((i0 % (int)t->w) + (int)t->w) % (int)t->w, i1 = ((i1 % (int)t->w) + (int)t->w) % (int)t->w;
+    j0 = ((j0 % (int)t->h) + (int)t->h) % (int)t->h, j1 = ((j1 % (int)t->h) + (int)t->h) % (int)t->h;
+    for (int ch = 0; ch < 4; ch++) {
+        float t00 = t->rgba[4 * ((size_t)j0 * t->w + i0) + ch] / 255.f, t10 = t->rgba[4 * ((size_t)j0 * t->w + i1) + ch] / 255.f;
+        float t01 = t->rgba[4 * ((size_t)j1 * t->w + i0) + ch] / 255.f, t11 = t->rgba[4 * ((size_t)j1 * t->w + i1) + ch] / 255.f;
+        out[ch]   = (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+    }
+}
+
+static inline void s_normalize(const float v[3], float out[3])
+{
+    float inv = 1.f / sqrtf(dot_ptx(v, v)); /* glm::normalize on the device: v * rcp(sqrt(dot)) */
+    out[0] = v[0] * inv, out[1] = v[1] * inv, out[2] = v[2] * inv;
+}
+/* w*a + u*b + v*c as the reference's SASS evaluates it (pinned bit-exactly by tests/golden/ref_chess_sampler.npz) */
+static inline float s_bary(float w, float a, float u, float b, float v, float c) { return fmaf(v, c, fmaf(w, a, u * b)); }
+
+/* include/cuda/utils/common.cuh:21-36 */
+static void s_ortho_basis(float tangent[3], float bitangent[3], const float n[3])
+{
+    float b[3] = {0.f, 0.f, 0.f}, c[3];
+    if (n[0] < 0.6f && n[0] > -0.6f)
+        b[0] = 1.f;
+    else if (n[1] < 0.6f && n[1] > -0.6f)
+        b[1] = 1.f;
+    else if (n[2] < 0.6f && n[2] > -0.6f)
+        b[2] = 1.f;
+    else
+        b[0] = 1.f;
+    cross_ptx(b, n, c);
+    s_normalize(c, tangent);
+    cross_ptx(n, tangent, c);
+    s_normalize(c, bitangent);
+}
+
+/* include/cuda/utils/sampling.cuh:8-14 */
+static void s_uniform_sphere(float sx, float sy, float out[3])
+{
+    float phi       = 6.2831854820251465f * sx;
+    float cos_theta = fmaf(sy, 2.0f, -1.0f);
+    float sin_theta = sqrtf(fmaf(-cos_theta, cos_theta, 1.0f));
+    out[0] = sin_theta * cosf(phi), out[1] = sin_theta * sinf(phi), out[2] = cos_theta;
+}
+
+/* include/cuda/base/material.cuh:101-120,193-200 */
+static void s_lambertian_dir(const float n[3], const float tangent[3], const float bitangent[3], float ux, float uy, float out[3])
+{
+    float sx = fmaf(2.f, ux, -1.f), sy = fmaf(2.f, uy, -1.f), dx = sx, dy = sy;
+    if (!(sx == 0.f && sy == 0.f)) {
+        float radius, theta;
+        if (fabsf(sx) > fabsf(sy)) {
+            radius = sx;
+            theta  = 0.78539818525314331f * (sy / sx);
+        } else {
+            radius = sy;
+            theta  = 1.5707963705062866f - 0.78539818525314331f * (sx / sy);
+        }
+        dx = radius * cosf(theta), dy = radius * sinf(theta);
+    }
+    float h[3] = {dx, dy, sqrtf(fmaxf(0.f, (1.f - dx * dx) - dy * dy))}, hn[3];
+    s_normalize(h, hn);
+    for (int i = 0; i < 3; i++)
+        out[i] = s_bary(hn[0], tangent[i], hn[1], bitangent[i], hn[2], n[i]);
+}
+
+typedef struct {
+    float position[3], sh_normal[3], uv[2];
+    int32_t material_id;
+} oits_t;
+
+/* BaseCudaBLAS::compute_its_data (include/cuda/accel/bvh.cuh:53-96) */
+static void s_compute_its(const osampler_t *sp, uint32_t prim, float u, float v, oits_t *its)
+{
+    const uint32_t *id = sp->blas.indices + 3 * (size_t)prim;
+    uint32_t left = 0, right = sp->num_materials;
+    while (left < right) { /* upper_bound(material_map, prim) - 1 */
+        uint32_t mid = left + (right - left) / 2;
+        if (sp->material_map[mid] <= prim)
+            left = mid + 1;
+        else
+            right = mid;
+    }
+    its->material_id = (sp->material_ids && sp->num_materials) ? sp->material_ids[left - 1] : -1;
+    const float *v0 = sp->blas.vertices + 3 * (size_t)id[0], *v1 = sp->blas.vertices + 3 * (size_t)id[1],
+                *v2 = sp->blas.vertices + 3 * (size_t)id[2];
+    float w = (1.f - u) - v;
+    if (sp->normals) {
+        const float *n0 = sp->normals + 3 * (size_t)id[0], *n1 = sp->normals + 3 * (size_t)id[1], *n2 = sp->normals + 3 * (size_t)id[2];
+        float n[3];
+        for (int i = 0; i < 3; i++)
+            n[i] = s_bary(w, n0[i], u, n1[i], v, n2[i]);
+        s_normalize(n, its->sh_normal);
+    } else {
+        float e1[3], e2[3], g[3];
+        for (int i = 0; i < 3; i++)
+            e1[i] = v1[i] - v0[i], e2[i] = v2[i] - v0[i];
+        cross_ptx(e1, e2, g);
+        s_normalize(g, its->sh_normal);
+    }
+    for (int i = 0; i < 3; i++)
+        its->position[i] = s_bary(w, v0[i], u, v1[i], v, v2[i]);
+    if (sp->texcoords) {
+        const float *t0 = sp->texcoords + 2 * (size_t)id[0], *t1 = sp->texcoords + 2 * (size_t)id[1], *t2 = sp->texcoords + 2 * (size_t)id[2];
+        its->uv[0] = s_bary(w, t0[0], u, t1[0], v, t2[0]);
+        its->uv[1] = s_bary(w, t0[1], u, t1[1], v, t2[1]);
+    } else {
+        its->uv[0] = u, its->uv[1] = v;
+    }
+    if (its->material_id != -1 && sp->materials) { /* unpack_normal (material.cuh:66-75) */
+        uint32_t mask;
+        memcpy(&mask, &sp->materials[its->material_id].normal[0], 4);
+        if (mask & 0x80000000u) {
+            float tx[4];
+            onbvh_tex2d(&sp->textures[mask & 0x1fffffffu], its->uv[0], its->uv[1], tx);
+            if (!(tx[0] == -1.f && tx[1] == -1.f && tx[2] == -1.f)) {
+                float c[3] = {tx[0] - 0.5f, tx[1] - 0.5f, tx[2] - 0.5f}, tsn[3], tw[3], bw[3], n[3];
+                s_normalize(c, tsn);
+                s_ortho_basis(tw, bw, its->sh_normal);
+                memcpy(n, its->sh_normal, 12);
+                for (int i = 0; i < 3; i++)
+                    its->sh_normal[i] = s_bary(tw[i], tsn[0], bw[i], tsn[1], n[i], tsn[2]);
+            }
+        }
+    }
+}
+
+/* test hook: when set, receives (prim, u, v) of every written slot (3 floats per slot, prim bit-cast) */
+float *onbvh_sampler_debug = NULL;
+
+/* neural_bvh_module_kernels.cu:119-264 with stack_based_sample_uniform_bvh_density and
+ * generate_single_bvh_network_output_reference (neural_bvh_module_common.cuh:703-861); LocalT depth targets */
+void onbvh_generate_batch(const onode_t *nbvh, const oconst_t *c, const osampler_t *sp, uint32_t training_step,
+                          uint32_t batch_size, uint32_t log2_bvh_max_traversals, uint32_t *sampled_nodes,
+                          float current_max_loss, const otreecut_t *tree_cut, float *inputs, float *targets)
+{
+    const uint32_t sub_batch = batch_size >> log2_bvh_max_traversals, n_sub = 1u << log2_bvh_max_traversals;
+    const uint32_t n_in = 3u * c->n_segment_points, n_out = 8u;
+    const float dilation_enc = (c->node_extent_dilation + 1.f) + c->fixed_node_dilation;
+    const uint32_t n_lods    = 7u - sp->current_learned_lod; /* NUM_BVH_LODS = 7 */
+#pragma omp parallel for schedule(dynamic, 64)
+    for (uint32_t i = 0; i < sub_batch; i++) {
+        uint32_t stack[NEURAL_STACK_SIZE];
+        int ss = 0, cont = 0, swap_dir = 0, bounce = 0;
+        float leaf_mint = 0.f, leaf_maxt = 0.f, o[3] = {0, 0, 0}, d[3] = {1, 1, 1};
+        uint32_t slot = i * n_sub;
+        for (uint32_t inner = 0; inner < n_sub; inner++) {
+            uint32_t rng = onbvh_lcg_rng_init(training_step * batch_size, 0u, slot);
+            float s0 = onbvh_lcg_randomf(&rng), s1 = onbvh_lcg_randomf(&rng), dir[3];
+            s_uniform_sphere(s0, s1, dir);
+            int valid = cont && ss != 0, restarted = 0;
+            uint32_t lod = (uint32_t)(onbvh_lcg_randomf(&rng) * (float)n_lods);
+            lod          = sp->current_learned_lod + (lod < n_lods - 1u ? lod : n_lods - 1u);
+            float sampled_dilation = fmaf(onbvh_lcg_randomf(&rng), c->node_extent_dilation, c->fixed_node_dilation);
+            uint32_t node_idx      = 0;
+            do {
+                if (!valid) {
+                    stack[0] = 0, ss = 1;
+                    float off = (sp->sampling_bbox_scaling - 1.f) * 0.5f;
+                    for (int k = 0; k < 3; k++) {
+                        float l = fmaf(sp->sampling_bbox_scaling, onbvh_lcg_randomf(&rng), -off);
+                        o[k]    = fmaf(l, c->bbox_max[k] - c->bbox_min[k], c->bbox_min[k]);
+                        d[k]    = dir[k];
+                    }
+                    restarted = 1;
+                }
+                valid = onbvh_neural_intersect(nbvh, c, lod, o, d, stack, &ss, 0, FLT_MAX, sampled_dilation, &leaf_mint, &leaf_maxt,
+                                               &node_idx, NULL);
+            } while (!valid);
+            sampled_nodes[slot] = node_idx;
+            if (restarted)
+                bounce = 0, swap_dir = 0;
+            if (swap_dir && leaf_mint >= 0.f)
+                swap_dir = 0;
+            if (sp->training_node_survival) {
+                otreecut_t nd = tree_cut[node_idx];
+                float est     = -FLT_MAX;
+                if (nd.samples != 0u) {
+                    float ia = (float)nd.iter_alive;
+                    est      = nd.loss / (ia * sqrtf((float)nd.samples / ia));
+                }
+                float keep = fmaxf(sp->min_rr_survival_prob, est / current_max_loss);
+                if (!(est <= current_max_loss))
+                    keep = 1.f;
+                if (sp->survival_probability_scale * keep < onbvh_lcg_randomf(&rng))
+                    continue; /* slot not advanced, contents kept */
+            }
+            { /* encode_segment_from_world_po_pi, no negative-mint swap here */
+                float t_o = swap_dir ? leaf_maxt : leaf_mint, t_i = swap_dir ? leaf_mint : leaf_maxt, eo[3], ei[3];
+                for (int k = 0; k < 3; k++) {
+                    float extent = dilation_enc * (c->bbox_max[k] - c->bbox_min[k]);
+                    float center = (c->bbox_max[k] + c->bbox_min[k]) * 0.5f;
+                    eo[k]        = (fmaf(t_o, d[k], o[k]) - center) / extent + 0.5f;
+                    ei[k]        = (fmaf(t_i, d[k], o[k]) - center) / extent + 0.5f;
+                }
+                const uint32_t n = c->n_segment_points;
+                float delta = c->segment_distribution == 1u ? (n == 1u ? 1.f : 1.f / (float)(n - 1u)) : 1.f / (float)n;
+                float offs  = c->segment_distribution == 1u ? 0.f : 0.5f;
+                for (uint32_t k = 0; k < n; k++) {
+                    float s = delta * ((float)k + offs);
+                    for (int a = 0; a < 3; a++)
+                        inputs[(size_t)slot * n_in + 3 * k + a] = fmaf(ei[a], s, eo[a] * (1.0f - s));
+                }
+            }
+            float td[3] = {d[0], d[1], d[2]}, seg_mint = leaf_mint, seg_maxt = leaf_maxt;
+            if (swap_dir) {
+                td[0] = -d[0], td[1] = -d[1], td[2] = -d[2];
+                seg_mint = -leaf_maxt, seg_maxt = -leaf_mint;
+            }
+            float hu = 0.f, hv = 0.f;
+            uint32_t prim = 0xFFFFFFFFu;
+            float ht      = onbvh_blas_intersect(&sp->blas, o, td, seg_mint, seg_maxt, &hu, &hv, &prim, NULL, NULL);
+            int is_hit    = ht != FLT_MAX;
+            float *tg     = targets + (size_t)slot * n_out;
+            oits_t its;
+            memset(&its, 0, sizeof(its));
+            if (is_hit)
+                s_compute_its(sp, prim, hu, hv, &its);
+            if (onbvh_sampler_debug) {
+                memcpy(&onbvh_sampler_debug[3 * (size_t)slot], &prim, 4);
+                onbvh_sampler_debug[3 * (size_t)slot + 1] = hu, onbvh_sampler_debug[3 * (size_t)slot + 2] = hv;
+            }
+            tg[0] = is_hit ? 1.f : 0.f;
+            float depth = 0.f;
+            if (is_hit) {
+                depth = (float)((double)(ht - seg_mint) / ((double)(seg_maxt - seg_mint) + 1e-3));
+                if (sp->depth_linear_activation)
+                    depth = fmaf(depth, 0.1f, 0.45f);
+            }
+            tg[1] = depth;
+            for (int k = 0; k < 3; k++)
+                tg[2 + k] = is_hit ? (its.sh_normal[k] + 1.f) * 0.5f : 0.f;
+            float alb[3] = {0.f, 0.f, 0.f};
+            if (is_hit) {
+                alb[0] = alb[1] = alb[2] = 0.9f;
+                if (its.material_id != -1 && sp->materials) {
+                    const omaterial_t *m = &sp->materials[its.material_id];
+                    uint32_t mask;
+                    memcpy(&mask, &m->base_color[0], 4);
+                    if (mask & 0x80000000u) {
+                        float tx[4];
+                        onbvh_tex2d(&sp->textures[mask & 0x1fffffffu], its.uv[0], its.uv[1], tx);
+                        alb[0] = tx[0], alb[1] = tx[1], alb[2] = tx[2];
+                    } else {
+                        alb[0] = m->base_color[0], alb[1] = m->base_color[1], alb[2] = m->base_color[2];
+                    }
+                }
+            }
+            tg[5] = alb[0], tg[6] = alb[1], tg[7] = alb[2];
+            swap_dir = 0;
+            cont     = !is_hit;
+            if (is_hit && sp->max_training_bounces > 0) {
+                bounce++;
+                float wo[3] = {-d[0], -d[1], -d[2]}, shn[3] = {its.sh_normal[0], its.sh_normal[1], its.sh_normal[2]}, tangent[3], bitangent[3];
+                int backface = 0;
+                if (dot_ptx(wo, shn) < 0.f) {
+                    shn[0] = -shn[0], shn[1] = -shn[1], shn[2] = -shn[2];
+                    backface = 1;
+                }
+                s_ortho_basis(tangent, bitangent, shn);
+                if ((backface && !sp->backface_bounce_training) || bounce >= sp->max_training_bounces) {
+                    bounce = 0;
+                    cont   = 0;
+                } else {
+                    float u0 = onbvh_lcg_randomf(&rng), u1 = onbvh_lcg_randomf(&rng), nd[3];
+                    if (sp->sample_cosine_weighted) {
+                        s_lambertian_dir(shn, tangent, bitangent, u0, u1, nd);
+                    } else {
+                        s_uniform_sphere(u0, u1, nd);
+                        if (!(dot_ptx(wo, shn) * dot_ptx(nd, shn) > 0.f))
+                            nd[0] = -nd[0], nd[1] = -nd[1], nd[2] = -nd[2];
+                    }
+                    for (int k = 0; k < 3; k++)
+                        o[k] = its.position[k], d[k] = nd[k];
+                    cont = 1, swap_dir = 1;
+                    stack[0] = 0, ss = 1;
+                }
+            }
+            slot++;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ primary-ray pipeline */
 static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t pixel,
                        int sample_idx, int rnd_offset, int mlp_mode, ohit_t *hit, uint64_t *cnt)

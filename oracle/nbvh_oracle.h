@@ -166,6 +166,47 @@ void onbvh_adam_step(const oopt_t *oc, uint32_t step, uint64_t n_params, uint64_
                      const float *grads, float *master, uint16_t *params, float *m, float *v, uint32_t *param_steps);
 float onbvh_learning_rate(const oopt_t *oc, uint32_t step);
 
+/* --- online-optimisation sample generator (a17, K10) --- */
+/* PackedMaterial (include/base/material.h:52-87): vtable pointer + Disney parameters, 96 bytes */
+typedef struct {
+    uint64_t vptr;
+    float base_color[3], metallic, specular, roughness, specular_tint, anisotropy, sheen, sheen_tint, clearcoat,
+        clearcoat_gloss, base_emission[3], emission_scale, normal[3], ior, specular_transmission, pad;
+} omaterial_t;
+typedef struct {
+    const uint8_t *rgba; /* w*h*4, row-major */
+    uint32_t w, h;
+} otexture_t;
+typedef struct {
+    float loss;
+    uint32_t iter_alive, depth, samples;
+} otreecut_t;
+typedef struct {
+    oblas_t blas;                 /* classical BLAS of the neural mesh */
+    const float *normals;         /* vec3 per vertex or NULL */
+    const float *texcoords;       /* vec2 per vertex or NULL */
+    const int32_t *material_ids;  /* per material segment */
+    const uint32_t *material_map; /* first primitive of each segment */
+    uint32_t num_materials;
+    const omaterial_t *materials;
+    const otexture_t *textures;
+    /* bvh_const fields the sampler reads (neural_bvh_renderer_constants.cuh:13-47) */
+    float sampling_bbox_scaling;
+    uint32_t current_learned_lod;
+    uint32_t training_node_survival;
+    float survival_probability_scale, min_rr_survival_prob;
+    int32_t max_training_bounces;
+    uint32_t backface_bounce_training, sample_cosine_weighted;
+    uint32_t depth_linear_activation;
+} osampler_t;
+/* granular_sample_bvh_network_input_data (neural_bvh_module_kernels.cu:119-264) for the whole batch.  inputs: batch x 9,
+ * targets: batch x 8, sampled_nodes: batch -- all read-modify-write (rejected slots keep their contents). */
+void onbvh_generate_batch(const onode_t *nbvh, const oconst_t *c, const osampler_t *sp, uint32_t training_step,
+                          uint32_t batch_size, uint32_t log2_bvh_max_traversals, uint32_t *sampled_nodes,
+                          float current_max_loss, const otreecut_t *tree_cut, float *inputs, float *targets);
+/* CUDA bilinear fetch (wrap addressing, normalized coordinates, 8-bit fractional weights) of an RGBA8 texture */
+void onbvh_tex2d(const otexture_t *t, float u, float v, float out[4]);
+
 /* --- whole primary-ray pipeline (section 9 of SURVEY.md), max_depth = 1 --- */
 typedef struct {
     uint8_t valid_hit; /* 0 none, 1 neural, 2 normal */

@@ -310,6 +310,78 @@ def render_primary(scene, nbvh_nodes, const, net, pixel_begin, pixel_end, stride
     return hits, [cnt[i] for i in range(4)]
 
 
+# ----------------------------------------------------------------------------- sample generator (a17, K10)
+class OTexture(C.Structure):
+    _fields_ = [("rgba", C.c_void_p), ("w", C.c_uint32), ("h", C.c_uint32)]
+
+
+class OSampler(C.Structure):
+    _fields_ = [("blas", OBlas), ("normals", C.c_void_p), ("texcoords", C.c_void_p), ("material_ids", C.c_void_p),
+                ("material_map", C.c_void_p), ("num_materials", C.c_uint32), ("materials", C.c_void_p),
+                ("textures", C.POINTER(OTexture)), ("sampling_bbox_scaling", C.c_float), ("current_learned_lod", C.c_uint32),
+                ("training_node_survival", C.c_uint32), ("survival_probability_scale", C.c_float),
+                ("min_rr_survival_prob", C.c_float), ("max_training_bounces", C.c_int32),
+                ("backface_bounce_training", C.c_uint32), ("sample_cosine_weighted", C.c_uint32),
+                ("depth_linear_activation", C.c_uint32)]
+
+
+class Sampler:
+    """Keeps the arrays of the neural mesh (classical BLAS + shading attributes), materials and textures alive."""
+
+    def __init__(self, cfg, blas, materials=None, textures=None):
+        bc = cfg.get("neural_bvh_renderer", {}).get("bvh_constants", {})
+        pt = cfg.get("neural_bvh_renderer", {}).get("neural_module", {}).get("pt_output_constants", {})
+        self.keep = [np.ascontiguousarray(blas["nodes"], dtype=NODE_DTYPE), np.ascontiguousarray(blas["prim_ids"], dtype=np.uint32),
+                     np.ascontiguousarray(blas["vertices"], dtype=np.float32), np.ascontiguousarray(blas["indices"], dtype=np.uint32)]
+        s = OSampler()
+        s.blas = OBlas(_p(self.keep[0]), self.keep[0].size, _p(self.keep[1]), _p(self.keep[2]), _p(self.keep[3]))
+        for key, dt in (("normals", np.float32), ("texcoords", np.float32), ("material_ids", np.int32), ("material_map", np.uint32)):
+            if blas.get(key) is not None:
+                a = np.ascontiguousarray(blas[key], dtype=dt)
+                self.keep.append(a)
+                setattr(s, key, a.ctypes.data)
+        s.num_materials = len(blas["material_map"]) if blas.get("material_map") is not None else 0
+        if materials is not None:
+            m = np.ascontiguousarray(materials)
+            assert m.dtype.itemsize == 96
+            self.keep.append(m)
+            s.materials = m.ctypes.data
+        if textures:
+            self.tex = (OTexture * len(textures))()
+            for k, img in enumerate(textures):
+                img = np.ascontiguousarray(img, dtype=np.uint8)
+                self.keep.append(img)
+                self.tex[k] = OTexture(img.ctypes.data, img.shape[1], img.shape[0])
+            s.textures = self.tex
+        s.sampling_bbox_scaling = bc.get("sampling_bbox_scaling", 1.5)
+        s.current_learned_lod = bc.get("current_learned_lod", 0)
+        s.training_node_survival = int(bc.get("training_node_survival", True))
+        s.survival_probability_scale = bc.get("survival_probability_scale", 1.0)
+        s.min_rr_survival_prob = bc.get("min_rr_survival_prob", 0.005)
+        s.max_training_bounces = bc.get("max_training_bounces", 1)
+        s.backface_bounce_training = int(bc.get("backface_bounce_training", False))
+        s.sample_cosine_weighted = int(bc.get("sample_cosine_weighted", True))
+        s.depth_linear_activation = int(pt.get("output_depth_linear_activation", False))
+        self.c = s
+
+
+def generate_batch(nbvh_nodes, const, sampler, training_step, batch, log2_max_trav, sampled_nodes, max_loss, tree_cut, inputs, targets):
+    """In place on sampled_nodes (uint32 [B]), inputs (float32 [B, 9]), targets (float32 [B, 8])."""
+    nbvh_nodes = np.ascontiguousarray(nbvh_nodes, dtype=NODE_DTYPE)
+    tc = np.ascontiguousarray(tree_cut)
+    assert tc.dtype.itemsize == 16 and inputs.flags.c_contiguous and targets.flags.c_contiguous
+    lib().onbvh_generate_batch(_p(nbvh_nodes), C.byref(const), C.byref(sampler.c), C.c_uint32(training_step), C.c_uint32(batch),
+                               C.c_uint32(log2_max_trav), _p(sampled_nodes), C.c_float(max_loss), _p(tc), _p(inputs), _p(targets))
+
+
+def tex2d(img, u, v):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    t = OTexture(img.ctypes.data, img.shape[1], img.shape[0])
+    out = (C.c_float * 4)()
+    lib().onbvh_tex2d(C.byref(t), C.c_float(u), C.c_float(v), out)
+    return np.array(out[:], dtype=np.float32)
+
+
 # ----------------------------------------------------------------------------- online optimisation
 LOSS_TYPES = ["RelativeL2", "L2", "RelativeL1", "L1", "RelativeL2Luminance", "BinaryCrossEntropy", "LogL2", "LHalf"]
 

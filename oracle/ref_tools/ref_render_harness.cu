@@ -9,6 +9,9 @@
 // render_app.cpp:307-312) are replaced by plain cudaMalloc buffers and cudaArray surfaces.
 //
 // usage: ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames>
+//        ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> 0 sampler <batch> <log2_max_traversals> <steps> [max_loss]
+//          (K10: granular_sample_bvh_network_input_data; also reads mesh<i>_{normals.f32,texcoords.f32,material_ids.i32,
+//           material_map.u32}, materials.bin, tex<k>.rgba8 + tex<k>.dims, tree_cut.bin; writes sampler_{in.f32,tgt.f32,nodes.u32})
 //   reads  <workdir>/const_{renderer,scene_bbox,module,pt_output,path,camera,scene}.bin (POD blobs, sizes checked
 //          against the reference's own sizeof), nbvh_nodes.bin, tlas_nodes.bin, tlas_indices.u32,
 //          mesh<i>_{nodes.bin,prim_ids.u64,vertices.f32,indices.u32} (i = 0..n_meshes-1), params.u16
@@ -24,6 +27,7 @@
 #include "cuda/neural/neural_bvh_renderer_kernels.cuh"
 #include "cuda/neural/path/path_constants.cuh"
 #include "cuda/neural/path/path_inference_kernels.cuh"
+#include "cuda/neural/neural_bvh_renderer.h"
 
 #include <tiny-cuda-nn/common.h>
 #include <tiny-cuda-nn/gpu_matrix.h>
@@ -414,6 +418,18 @@ int main(int argc, char **argv)
         slurp(p + "_prim_ids.u64", prim), slurp(p + "_vertices.f32", verts), slurp(p + "_indices.u32", idx);
         CudaBLAS bl;
         memset((void *)&bl, 0, sizeof(bl));
+        std::vector<float> nrm, tc;
+        std::vector<int> mids;
+        std::vector<uint32_t> mmap;
+        if (slurp(p + "_normals.f32", nrm) && !nrm.empty())
+            bl.normals = (glm::vec3 *)upload(nrm);
+        if (slurp(p + "_texcoords.f32", tc) && !tc.empty())
+            bl.texcoords = (glm::vec2 *)upload(tc);
+        if (slurp(p + "_material_ids.i32", mids) && slurp(p + "_material_map.u32", mmap) && !mmap.empty()) {
+            bl.material_ids  = upload(mids);
+            bl.material_map  = upload(mmap);
+            bl.num_materials = (uint32_t)mmap.size();
+        }
         bl.num_nodes        = (uint32_t)nodes.size();
         bl.prim_indices     = upload(prim);
         bl.num_prim_indices = (uint32_t)prim.size();
@@ -434,6 +450,87 @@ int main(int argc, char **argv)
     nbvh.num_nodes = (uint32_t)nb_nodes.size();
     printf("[ref_render_harness] %ux%u, %zu tree-cut nodes, %zu meshes, neural_bvh_idx %u\n", W, H, nb_nodes.size(), meshes.size(),
            c_renderer.neural_bvh_idx);
+
+    // ---- sampler mode: the reference's training-sample generator (K10) for a few steps
+    if (argc >= 11 && std::string(argv[7]) == "sampler") {
+        const uint32_t batch = atoi(argv[8]), log2_trav = atoi(argv[9]), steps = atoi(argv[10]);
+        const float max_loss = argc >= 12 ? (float)atof(argv[11]) : 1.f;
+        // materials (raw PackedMaterial bytes; the vtable slot is never read on the device) and RGBA8 textures
+        std::vector<uint8_t> mats;
+        if (slurp(wd + "/materials.bin", mats) && !mats.empty()) {
+            if (mats.size() % sizeof(PackedMaterial)) {
+                fprintf(stderr, "materials.bin: %zu bytes is not a multiple of sizeof(PackedMaterial)=%zu\n", mats.size(), sizeof(PackedMaterial));
+                return 4;
+            }
+            scene.materials = (PackedMaterial *)upload(mats);
+        }
+        std::vector<cudaTextureObject_t> texs;
+        for (int k = 0;; k++) {
+            std::vector<uint8_t> px;
+            std::vector<uint32_t> dims;
+            if (!slurp(wd + "/tex" + std::to_string(k) + ".rgba8", px) || !slurp(wd + "/tex" + std::to_string(k) + ".dims", dims))
+                break;
+            const uint32_t tw = dims[0], th = dims[1];
+            cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+            cudaArray_t arr;
+            CK(cudaMallocArray(&arr, &cd, tw, th));
+            CK(cudaMemcpy2DToArray(arr, 0, 0, px.data(), tw * 4, tw * 4, th, cudaMemcpyHostToDevice));
+            cudaResourceDesc trd = {};
+            trd.resType          = cudaResourceTypeArray;
+            trd.res.array.array  = arr;
+            cudaTextureDesc td   = {}; // CudaBackend::create_cuda_textures_buffer (cuda_backend.cpp:421-432)
+            td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+            td.filterMode = cudaFilterModeLinear, td.readMode = cudaReadModeNormalizedFloat, td.normalizedCoords = 1;
+            td.maxAnisotropy = 1, td.maxMipmapLevelClamp = 99, td.minMipmapLevelClamp = 0, td.mipmapFilterMode = cudaFilterModePoint;
+            td.borderColor[0] = 1.0f, td.sRGB = 0;
+            cudaTextureObject_t t;
+            CK(cudaCreateTextureObject(&t, &trd, &td, nullptr));
+            texs.push_back(t);
+        }
+        if (!texs.empty())
+            scene.textures = upload(texs);
+        std::vector<NeuralTreeCutData> cut;
+        if (!slurp(wd + "/tree_cut.bin", cut) || cut.size() != nb_nodes.size()) {
+            fprintf(stderr, "tree_cut.bin: %zu entries, tree-cut has %zu nodes\n", cut.size(), nb_nodes.size());
+            return 4;
+        }
+        NeuralTreeCutData *d_cut = upload(cut);
+        const uint32_t in_d = c_module.input_network_dims, out_d = c_pt.output_network_dims;
+        uint32_t *d_nodes = dalloc<uint32_t>(batch);
+        float *d_in = dalloc<float>((size_t)batch * in_d), *d_tg = dalloc<float>((size_t)batch * out_d);
+        const uint32_t sub = batch >> log2_trav, nsub = 1u << log2_trav;
+        std::vector<float> all_in, all_tg;
+        std::vector<uint32_t> all_nodes;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        float ms_sum = 0.f;
+        for (uint32_t st = 0; st < steps; st++) {
+            cudaEventRecord(e0, 0);
+            LINEAR_KERNEL(granular_sample_bvh_network_input_data, 0, (int)sub, (int)nsub, (int)st, nbvh, scene, d_nodes, d_in, d_tg, max_loss, d_cut);
+            cudaEventRecord(e1, 0);
+            CK(cudaDeviceSynchronize());
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (st)
+                ms_sum += ms;
+            auto a = download(d_in, (size_t)batch * in_d);
+            auto b2 = download(d_tg, (size_t)batch * out_d);
+            auto c2 = download(d_nodes, batch);
+            all_in.insert(all_in.end(), a.begin(), a.end());
+            all_tg.insert(all_tg.end(), b2.begin(), b2.end());
+            all_nodes.insert(all_nodes.end(), c2.begin(), c2.end());
+        }
+        dump(wd + "/sampler_in.f32", all_in);
+        dump(wd + "/sampler_tgt.f32", all_tg);
+        dump(wd + "/sampler_nodes.u32", all_nodes);
+        FILE *fs = fopen((wd + "/sampler.json").c_str(), "w");
+        fprintf(fs, "{\"batch\": %u, \"log2_bvh_max_traversals\": %u, \"steps\": %u, \"ms_per_step\": %.5f, \"n_textures\": %zu}\n", batch,
+                log2_trav, steps, steps > 1 ? ms_sum / (steps - 1) : 0.f, texs.size());
+        fclose(fs);
+        printf("[ref_render_harness] sampler: batch %u, 2^%u traversals/thread, %u steps, %.4f ms/step\n", batch, log2_trav, steps,
+               steps > 1 ? ms_sum / (steps - 1) : 0.f);
+        return 0;
+    }
 
     // ---- network exactly as NeuralBVHModule::reinitialise_neural_model builds it (neural_bvh_module.cu:118-263) for the shipped config
     using json = nlohmann::json;

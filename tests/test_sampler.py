@@ -1,0 +1,153 @@
+"""Online-optimisation sample generator (kernel K10) against the reference's OWN kernel.
+
+tests/golden/ref_chess_sampler.npz holds the outputs of granular_sample_bvh_network_input_data
+(/root/reference/src/cuda/neural/neural_bvh_module_kernels.cu:119-264) compiled from the reference for sm_100 and run
+on a B200 (tools/make_ref_sampler_goldens.py) on the shipped Chess tree-cut + neural-mesh BLAS, with the deterministic
+procedural materials / tree-cut statistics of nbvh_b200.scene_io (rebuilt here from their seeds).
+
+  * CUDA path (`-m gpu`): sampled node ids, the 9 inputs and the 8 targets of every slot BIT-EXACT, for both the
+    one-slot-per-thread case and 4 slots per thread (rays continuing through the tree-cut), including slots the
+    node-survival roulette rejects (they keep their previous contents).
+  * CPU oracle (`-m "not gpu"`): node ids and hit flags exact; inputs within 1e-6 and targets within 2e-4 -- libm's
+    sinf/cosf differ from CUDA's in the last ulp and the texture unit's bilinear filter is emulated in software."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden", "ref_chess_sampler.npz")
+ORACLE_IN_TOL = 1e-6
+ORACLE_TGT_TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def gold():
+    if not os.path.exists(GOLD):
+        pytest.skip("sampler goldens not generated (tools/make_ref_sampler_goldens.py on a GPU box)")
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def chess_sampler_inputs(chess_root):
+    import nbvh_b200
+    from nbvh_b200.scene_io import CHESS_BASE
+    cfg = json.load(open(os.path.join(chess_root, CHESS_BASE + "_neural.json")))
+    tl, ti, bl, _ = nbvh_b200.load_scene_arrays(chess_root, with_neural_mesh=True, with_attributes=True)
+    n_mat = int(max(b["material_ids"].max() for b in bl)) + 1
+    mats, texs = nbvh_b200.procedural_materials(n_mat)
+    return dict(cfg=cfg, scene=(tl, ti, bl), mats=mats, texs=texs)
+
+
+def cases(gold):
+    for name in ("t0", "t2"):
+        batch, log2_trav, steps = [int(v) for v in gold[name + "_cfg"]]
+        yield name, batch, log2_trav, steps, gold[name + "_in"], gold[name + "_tgt"], gold[name + "_nodes"]
+
+
+# ------------------------------------------------------------------------------------------------ oracle (CPU)
+def test_oracle_texture_fetch_matches_bilinear_definition(oracle):
+    img = np.zeros((2, 2, 4), np.uint8)
+    img[0, 0] = 255
+    assert np.allclose(oracle.tex2d(img, 0.25, 0.25), 1.0)           # texel centre
+    assert np.allclose(oracle.tex2d(img, 0.5, 0.25), 0.5, atol=2e-3)  # halfway to the black neighbour
+    assert np.allclose(oracle.tex2d(img, 1.25, -0.75), 1.0)           # wrap addressing
+
+
+def test_oracle_sampler_matches_reference_kernel(gold, oracle, chess_root, chess_sampler_inputs):
+    import nbvh_b200
+    from nbvh_b200.scene_io import CHESS_BASE
+    env = chess_sampler_inputs
+    nbvh = oracle.read_nbvh(os.path.join(chess_root, CHESS_BASE + ".nbvh"))
+    const = oracle.config_constants(env["cfg"], nbvh)
+    sm = oracle.Sampler(env["cfg"], env["scene"][2][0], env["mats"], env["texs"])
+    cut = nbvh_b200.procedural_tree_cut(len(nbvh))
+    for name, batch, log2_trav, steps, gx, gt, gn in cases(gold):
+        nodes = np.zeros(batch, np.uint32)
+        x = np.zeros((batch, 9), np.float32)
+        t = np.zeros((batch, 8), np.float32)
+        for s in range(steps):
+            oracle.generate_batch(nbvh, const, sm, s, batch, log2_trav, nodes, float(gold["max_loss"]), cut, x, t)
+            assert (nodes == gn[s]).all(), name
+            assert (t[:, 0] == gt[s].view(np.float32)[:, 0]).all(), name
+            assert np.abs(x - gx[s].view(np.float32)).max() < ORACLE_IN_TOL, name
+            assert np.abs(t - gt[s].view(np.float32)).max() < ORACLE_TGT_TOL, name
+        written = np.abs(x).sum(axis=1) > 0
+        assert 0.2 < written.mean() < 1.0  # the roulette rejects some slots, and they stay untouched
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path (GPU)
+@pytest.fixture(scope="module")
+def gpu_mod(chess_sampler_inputs):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nbvh_b200
+    env = chess_sampler_inputs
+    mod = nbvh_b200.load_chess_module()
+    tl, ti, bl = env["scene"]
+    mod.set_scene(tl, ti, bl, materials=env["mats"], textures=env["texs"])
+    cut = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()))
+    cut_dev = torch.from_numpy(cut.view(np.uint8).reshape(-1).copy()).cuda()
+    yield mod, cut_dev, torch
+    mod.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_bit_exact_against_reference_kernel(gold, gpu_mod):
+    mod, cut_dev, torch = gpu_mod
+    for name, batch, log2_trav, steps, gx, gt, gn in cases(gold):
+        nodes = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        x = torch.zeros((batch, 9), dtype=torch.float32, device="cuda")
+        t = torch.zeros((batch, 8), dtype=torch.float32, device="cuda")
+        for s in range(steps):
+            mod.optimisation_data_generation(s, batch, log2_trav, nodes, float(gold["max_loss"]), cut_dev, x, t)
+            torch.cuda.synchronize()
+            assert (nodes.cpu().numpy().astype(np.uint32) == gn[s]).all(), name
+            assert (x.cpu().numpy().view(np.uint32) == gx[s]).all(), name
+            assert (t.cpu().numpy().view(np.uint32) == gt[s]).all(), name
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_feeds_training_step(gpu_mod):
+    """generate -> training_step, the loop of NeuralBVHRenderer::optimisation step (neural_bvh_renderer.cu:113-260):
+    the loss on freshly sampled Chess batches decreases from a fresh initialisation."""
+    mod, cut_dev, torch = gpu_mod
+    B = 1 << 16
+    params = mod.get_params()
+    try:
+        mod.init_params(1337)
+        nodes = torch.zeros(B, dtype=torch.int32, device="cuda")
+        x = torch.zeros((B, 9), dtype=torch.float32, device="cuda")
+        t = torch.zeros((B, 8), dtype=torch.float32, device="cuda")
+        losses = []
+        for s in range(60):
+            mod.optimisation_data_generation(s, B, 0, nodes, 1e30, cut_dev, x, t)  # max_loss huge -> min survival only
+            losses.append(mod.training_step(x, t))
+        assert np.isfinite(losses).all()
+        assert np.mean(losses[-10:]) < 0.8 * np.mean(losses[:5])
+    finally:
+        mod.load_params(params)
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_rejects_unsupported_modes(gpu_mod):
+    import nbvh_b200
+    mod, cut_dev, torch = gpu_mod
+    nodes = torch.zeros(64, dtype=torch.int32, device="cuda")
+    x = torch.zeros((64, 9), dtype=torch.float32, device="cuda")
+    t = torch.zeros((64, 8), dtype=torch.float32, device="cuda")
+    with pytest.raises(nbvh_b200.NbvhError):
+        mod.optimisation_data_generation(0, 48, 0, nodes, 1.0, cut_dev, x, t)       # not a power of two
+    with pytest.raises(nbvh_b200.NbvhError):
+        mod.optimisation_data_generation(0, 64, 0, nodes, 1.0, None, x, t)          # roulette needs the statistics
+    rc = mod.get_constants(nbvh_b200.CONST_RENDERER)
+    rc.ellipsoidal_bvh = True
+    saved = mod.get_constants(nbvh_b200.CONST_RENDERER)
+    try:
+        with pytest.raises(nbvh_b200.NbvhError):
+            mod.set_constants(nbvh_b200.CONST_RENDERER, rc)
+            mod.optimisation_data_generation(0, 64, 0, nodes, 1.0, cut_dev, x, t)
+    finally:
+        mod.set_constants(nbvh_b200.CONST_RENDERER, saved)
