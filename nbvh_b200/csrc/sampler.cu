@@ -185,22 +185,37 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
         bc.leaf_lod_max       = 2u + lod;
         bc.dilation           = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
         uint32_t node_idx     = 0u;
-        do {
-            if (!valid) {
-                nstack[0] = 0u, nss = 1;
-                const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
-                const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
-                const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
-                            lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
-                ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
-                ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
-                ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
-                ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
-                ray_prepare(ray, p.nodes_safe != 0u);
-                restarted = true;
+        // Phase-uniform retry loop: every iteration, lanes without a live walk draw a new origin (the direction is kept) and
+        // every lane then visits exactly one node.  Same draws, same visiting order as the reference's
+        // do { if (!valid) resample; valid = intersect(...) } while (!valid).
+        {
+            WalkState w;
+            bool walking = valid;
+            if (walking)
+                walk_pop(bc, w, nstack, nss);
+            for (;;) {
+                if (!walking) {
+                    nstack[0] = 0u, nss = 1;
+                    const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
+                    const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
+                    const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
+                                lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
+                    ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
+                    ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
+                    ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
+                    ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+                    ray_prepare(ray, p.nodes_safe != 0u);
+                    restarted = true;
+                    walk_pop(bc, w, nstack, nss);
+                    walking = true;
+                }
+                const WalkResult r = nbvh_walk_step(bc, ray, w, nstack, nss, FLT_MAX, leaf_mint, leaf_maxt, node_idx, cnt_nbvh);
+                if (r == WALK_FOUND)
+                    break;
+                if (r == WALK_EXHAUSTED)
+                    walking = false;
             }
-            valid = nbvh_next_interval(bc, ray, nstack, nss, FLT_MAX, leaf_mint, leaf_maxt, node_idx, cnt_nbvh);
-        } while (!valid);
+        }
         p.sampled_node_indices[slot] = node_idx;
         if (restarted) {
             training_bounce = 0;
