@@ -255,7 +255,7 @@ struct nbvh_ctx {
     nbvh_hit_record *hits = nullptr;
     nbvh_hit_record *own_hits = nullptr;
 
-    uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor
+    uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor, [3] node-check flag, [4] sampler slot counter
     NeuralQueueEntry *d_queue = nullptr;
     size_t queue_capacity = 0;
     bool mega_kernel = false; // NBVH_RENDER_MODE=mega: the single persistent kernel of the first design (kept for A/B timing)
@@ -548,7 +548,7 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
     ctx->num_sms  = prop.multiProcessorCount;
     if (const char *m = getenv("NBVH_RENDER_MODE"))
         ctx->mega_kernel = std::string(m) == "mega";
-    if (cudaMalloc(&ctx->d_next_chunk, 4 * sizeof(uint32_t)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
         return NBVH_ERR_CUDA;
@@ -1329,7 +1329,7 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.current_max_loss = current_max_loss;
     sp.tree_cut         = tree_cut_data;
     sp.counters         = ctx->d_counters;
-    CU_TRY(ctx, launch_generate_batch(sp, (cudaStream_t)stream));
+    CU_TRY(ctx, launch_generate_batch(sp, ctx->d_next_chunk ? ctx->d_next_chunk + 4 : nullptr, ctx->num_sms, (cudaStream_t)stream));
     return NBVH_OK;
 }
 

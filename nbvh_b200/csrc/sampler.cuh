@@ -48,6 +48,6 @@ struct SamplerParams {
     unsigned long long *counters;
 };
 
-cudaError_t launch_generate_batch(const SamplerParams &p, cudaStream_t stream);
+cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter, int num_sms, cudaStream_t stream);
 
 } // namespace nbvh
