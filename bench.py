@@ -229,19 +229,30 @@ def main():
     e2e_s = time.time() - t0
 
     # ---------------- online optimisation (second half of BASELINE's metric: train samples/s), data parallel:
-    # every rank owns 2^18 slots, gradients (fp32, 21.6 MB) are allreduced by NCCL, Adam is replicated
+    # every rank owns 2^18 batch slots; per step: sample generation (K10: tree-cut walk + neural-mesh BLAS trace +
+    # material lookups), hash-grid encode + fused MLP forward/loss/backward + grid backward, fp32 gradient allreduce
+    # (21.6 MB, NCCL) and the replicated Adam step
     train_B = 1 << 18
-    rng = np.random.default_rng(1234 + rank)
-    tx = torch.from_numpy(rng.uniform(0, 1, size=(train_B, 9)).astype(np.float32)).to(dev)
-    tg = rng.uniform(0, 1, size=(train_B, 8)).astype(np.float32)
-    vis = rng.uniform(0, 1, size=train_B) < 0.5
-    tg[:, 0] = vis
-    tg[~vis, 1:] = 0
-    tt = torch.from_numpy(tg).to(dev)
+    if root is not None:
+        tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root, with_neural_mesh=True, with_attributes=True)
+        mats, texs = nbvh_b200.procedural_materials(int(max(b["material_ids"].max() for b in bl)) + 1)
+        mod.set_scene(tl, ti, bl, materials=mats, textures=texs)
+    cut = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()), seed=11 + rank)
+    cut_dev = torch.from_numpy(cut.view(np.uint8).reshape(-1).copy()).to(dev)
+    nodes_dev = torch.zeros(train_B, dtype=torch.int32, device=dev)
+    tx = torch.zeros((train_B, 9), dtype=torch.float32, device=dev)
+    tt = torch.zeros((train_B, 8), dtype=torch.float32, device=dev)
     grads = mod.gradient_buffer()
     train_steps = max(5, min(args.steps, 50))
+    step_no = [0]
+
+    def generate():
+        # rank r samples the slots [r*B, (r+1)*B) of the global batch: the RNG is keyed by step * global batch + slot
+        mod.optimisation_data_generation(step_no[0] * world + rank, train_B, 0, nodes_dev, 1.0, cut_dev, tx, tt, stream=stream.cuda_stream)
+        step_no[0] += 1
 
     def train_step():
+        generate()
         mod.training_forward_backward(tx, tt, global_batch=train_B * world, stream=stream.cuda_stream)
         if world > 1:
             dist.all_reduce(grads)
@@ -257,6 +268,12 @@ def main():
     te1.record(stream)
     barrier()
     train_ms = te0.elapsed_time(te1) / train_steps
+    te0.record(stream)
+    for _ in range(train_steps):
+        generate()
+    te1.record(stream)
+    barrier()
+    gen_ms = te0.elapsed_time(te1) / train_steps
 
     t = torch.tensor([total_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -289,6 +306,20 @@ def main():
         tp = os.path.join(REPO, "profiles", "k_neural_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        ref_gpu, ref_train = None, None
+        gp = os.path.join(REPO, "tests", "golden")
+        try:  # the reference's own kernels + tcnn (sm_100 build) timed on a B200 by tools/make_ref_*_goldens.py
+            rg = json.load(open(os.path.join(gp, "ref_chess_timing.json")))
+            ref_gpu = {"ms_per_frame": rg["ms_best"], "Mrays_s": rg["mrays_s_best"], "queries": rg["queries"], "launches": rg["launches"],
+                       "host_syncs": rg["host_syncs"], "gpu": rg.get("gpu"), "what": rg.get("what")}
+            rs = json.load(open(os.path.join(gp, "ref_chess_sampler_timing.json")))
+            rt = json.load(open(os.path.join(gp, "tcnn_timings.json")))
+            tstep = rt["chess_1M_queries_2p18_batch"]["training_step_ms"]
+            ref_train = {"sample_generation_ms": rs["ms_per_step"], "training_step_ms": tstep,
+                         "samples_s": train_B / ((rs["ms_per_step"] + tstep) * 1e-3),
+                         "what": "reference granular_sample_bvh_network_input_data + tcnn training_step, batch 2^18, one B200"}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -313,12 +344,14 @@ def main():
                                  "achieved": primary_bytes / (primary_ms * 1e-3) / 1e9 if primary_ms else None, "peak": peak,
                                  "unit": "GB/s", "frac": primary_bytes / (primary_ms * 1e-3) / 1e9 / peak if primary_ms else None},
             "frame_alg_bytes": alg_bytes,
+            "reference_gpu_b200": ref_gpu,
             "train": {"metric": "train samples/s", "value": world * train_B / (train_ms * 1e-3), "unit": "samples/s",
                       "ms_per_step": train_ms, "batch_per_gpu": train_B, "steps": train_steps,
-                      "what": "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam on a resident "
-                              "synthetic batch (uniform inputs/targets; sample generation K10 not included)" +
+                      "sample_generation_ms": gen_ms,
+                      "what": "per step: sample generation on the Chess tree-cut + neural-mesh BLAS (K10, procedural materials), "
+                              "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam" +
                               ("; fp32 gradient allreduce (NCCL) per step" if world > 1 else ""),
-                      "reference_tcnn_ms_per_step_b200": 1.753},
+                      "reference_b200": ref_train},
             "counters_per_step": per,
             "neural_queries_per_s": per["queries"] / (ms_per_step * 1e-3),
             "clocks": sampler.summary(),
