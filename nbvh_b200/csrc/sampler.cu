@@ -17,7 +17,7 @@
 // the sampling arithmetic (sphere sampling, barycentric interpolation, normal mapping) follows the source expression by
 // expression with the contraction that reproduces the reference kernel's outputs BIT FOR BIT on the shipped Chess scene
 // (node ids, inputs and all 8 targets of every slot; tests/test_sampler.py).  The optional training bounce
-// (max_training_bounces > 1, off in every shipped config) is checked against the oracle with a tolerance only.
+// (max_training_bounces > 1, off in every shipped config) is checked against the CPU restatement with a tolerance only.
 #include "render_common.cuh"
 #include "sampler.cuh"
 
