@@ -371,6 +371,12 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
  * wrap addressing, linear filtering, normalized float reads.  Returns a cudaTextureObject_t in *tex_out. */
 int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out);
 int nbvh_destroy_textures(nbvh_ctx *ctx);
+/* Environment map == `envmap_texture` (include/cuda/cuda_backend_constants.cuh, CudaBackend::load_envmap
+ * src/cuda/cuda_backend.cpp:455-500): an RGBA32F lat-long cudaTextureObject_t (linear filter, normalized coordinates,
+ * clamp).  nbvh_set_envmap takes the caller's object (0 = the reference's white fallback image);
+ * nbvh_create_envmap_rgba32f builds one from host pixels (w*h*4 floats) for hosts without their own. */
+int nbvh_create_envmap_rgba32f(nbvh_ctx *ctx, const float *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out);
+int nbvh_set_envmap(nbvh_ctx *ctx, uint64_t envmap_texture);
 int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);

@@ -149,6 +149,8 @@ SYMBOLS = {
     "nbvh_optimisation_data_generation": (_i, [_vp, _u32, _u32, _u32, _vp, _f, _vp, _vp, _vp, _vp]),
     "nbvh_create_texture_rgba8": (_i, [_vp, _vp, _u32, _u32, C.POINTER(_u64)]),
     "nbvh_destroy_textures": (_i, [_vp]),
+    "nbvh_create_envmap_rgba32f": (_i, [_vp, _vp, _u32, _u32, C.POINTER(_u64)]),
+    "nbvh_set_envmap": (_i, [_vp, _u64]),
     "nbvh_gradients": (_vp, [_vp]),
     "nbvh_set_gradient_buffer": (_i, [_vp, _vp]),
     "nbvh_optimizer_step": (_i, [_vp, _vp]),

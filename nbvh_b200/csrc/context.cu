@@ -7,6 +7,7 @@
 #include "json_min.hpp"
 #include "kernels.cuh"
 #include "sampler.cuh"
+#include "path.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -246,7 +247,14 @@ struct nbvh_ctx {
     bool scene_set = false;
     std::vector<nbvh_cuda_blas> blas_desc; // host copy of the caller's descriptors (shading attributes for the sampler)
     const void *materials = nullptr, *textures = nullptr;
-    std::vector<std::pair<cudaTextureObject_t, cudaArray_t>> own_textures; // nbvh_create_texture_rgba8
+    std::vector<std::pair<cudaTextureObject_t, cudaArray_t>> own_textures; // nbvh_create_texture_rgba8 / nbvh_create_envmap_rgba32f
+    cudaTextureObject_t envmap = 0;                                        // envmap_texture (cuda_backend_constants.cuh); 0 = white
+
+    // multi-bounce path state (max_depth > 1): one PathState + PathHit per pixel, 2 queue counters per bounce
+    PathState *d_paths = nullptr;
+    PathHit *d_path_hits = nullptr;
+    size_t path_capacity = 0;
+    uint32_t *d_bounce_counters = nullptr;
 
     // framebuffer
     float4 *accum = nullptr;
@@ -578,6 +586,9 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     cudaFree(ctx->d_queue);
+    cudaFree(ctx->d_paths);
+    cudaFree(ctx->d_path_hits);
+    cudaFree(ctx->d_bounce_counters);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->own_grads);
     cudaFree(ctx->d_master);
@@ -1362,6 +1373,38 @@ int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_
     return NBVH_OK;
 }
 
+int nbvh_create_envmap_rgba32f(nbvh_ctx *ctx, const float *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out)
+{
+    if (!ctx || !pixels_host || !tex_out || w == 0 || h == 0)
+        return NBVH_ERR_INVALID_ARG;
+    // CudaBackend::load_envmap (cuda_backend.cpp:474-500): float4 array, linear filter, normalized coordinates, clamp
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+    cudaArray_t arr = nullptr;
+    CU_TRY(ctx, cudaMallocArray(&arr, &cd, w, h));
+    CU_TRY(ctx, cudaMemcpy2DToArray(arr, 0, 0, pixels_host, (size_t)w * 16, (size_t)w * 16, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd = {};
+    rd.resType          = cudaResourceTypeArray;
+    rd.res.array.array  = arr;
+    cudaTextureDesc td  = {};
+    td.filterMode       = cudaFilterModeLinear;
+    td.normalizedCoords = 1;
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    CU_TRY(ctx, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    ctx->own_textures.emplace_back(tex, arr);
+    *tex_out = (uint64_t)tex;
+    return NBVH_OK;
+}
+
+int nbvh_set_envmap(nbvh_ctx *ctx, uint64_t envmap_texture)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    ctx->envmap = (cudaTextureObject_t)envmap_texture;
+    return NBVH_OK;
+}
+
 int nbvh_destroy_textures(nbvh_ctx *ctx)
 {
     if (!ctx)
@@ -1371,6 +1414,7 @@ int nbvh_destroy_textures(nbvh_ctx *ctx)
         cudaFreeArray(t.second);
     }
     ctx->own_textures.clear();
+    ctx->envmap = 0;
     return NBVH_OK;
 }
 
@@ -1386,9 +1430,10 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
         return rc;
     if (!ctx->accum)
         return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
-    if (ctx->max_depth != 1)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED,
-                    "max_depth > 1 needs the shading row (Disney BSDF sampling, SURVEY 8 f1); set max_depth to 1");
+    if (ctx->max_depth > kMaxPathDepth)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "max_depth > 64");
+    if (ctx->path_const.output_mode != 0)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only OutputMode::NeuralPathTracing is implemented");
     const uint32_t total = ctx->fb_w * ctx->fb_h;
     if (pixel_count == 0) {
         first_pixel = 0;
@@ -1411,8 +1456,15 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     rp.dec.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
     rp.ignore_neural_blas      = ctx->bvh_const.ignore_neural_blas;
     rp.max_depth               = (uint32_t)ctx->max_depth;
-    rp.envmap_eval             = ctx->scene_const.envmap_eval;
-    rp.skylike_background      = ctx->scene_const.skylike_background;
+    rp.bg.envmap_eval          = ctx->scene_const.envmap_eval;
+    rp.bg.skylike_background   = ctx->scene_const.skylike_background;
+    {   // glm::rotate(mat4(1), radians(envmap_rotation), +Y) (path_inference_kernels.cu:45-47)
+        const float a  = ctx->scene_const.envmap_rotation * 0.01745329251994329576923690768489f;
+        rp.bg.rot_cos  = cosf(a);
+        rp.bg.rot_sin  = sinf(a);
+        rp.bg.strength = ctx->scene_const.envmap_strength;
+        rp.bg.envmap   = ctx->envmap;
+    }
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
     rp.next_chunk    = ctx->d_next_chunk;
     if (ctx->queue_capacity < (size_t)total) {
@@ -1431,7 +1483,48 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     const NetConst nc = make_net_const(ctx);
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, 4 * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
-    if (ctx->mega_kernel) {
+    if (ctx->max_depth > 1) {
+        // hybrid neural path tracing (path.cu): shading + re-queue per bounce, no host synchronisation
+        if (ctx->path_capacity < (size_t)total) {
+            cudaFree(ctx->d_paths), cudaFree(ctx->d_path_hits);
+            ctx->d_paths = nullptr, ctx->d_path_hits = nullptr, ctx->path_capacity = 0;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_paths, (size_t)total * sizeof(PathState)));
+            CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits, (size_t)total * sizeof(PathHit)));
+            ctx->path_capacity = total;
+        }
+        if (!ctx->d_bounce_counters)
+            CU_TRY(ctx, cudaMalloc(&ctx->d_bounce_counters, 2u * (kMaxPathDepth + 1) * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_bounce_counters, 0, 2u * (kMaxPathDepth + 1) * sizeof(uint32_t), st));
+        rp.paths = ctx->d_paths, rp.path_hits = ctx->d_path_hits;
+        PathConst pc;
+        memset(&pc, 0, sizeof(pc));
+        for (size_t i = 0; i < ctx->blas_desc.size() && i < (size_t)kMaxBlas; i++) {
+            const nbvh_cuda_blas &b = ctx->blas_desc[i];
+            pc.attr[i].normals       = b.normals;
+            pc.attr[i].texcoords     = b.texcoords;
+            pc.attr[i].material_ids  = (b.material_map && b.num_materials) ? b.material_ids : nullptr;
+            pc.attr[i].material_map  = b.material_map;
+            pc.attr[i].num_materials = b.material_map ? b.num_materials : 0u;
+        }
+        pc.materials = reinterpret_cast<const MaterialPod *>(ctx->materials);
+        pc.textures  = reinterpret_cast<const cudaTextureObject_t *>(ctx->textures);
+        pc.neural_bvh_idx          = ctx->bvh_const.neural_bvh_idx;
+        pc.normal_epsilon_offset   = ctx->path_const.normal_epsilon_offset;
+        pc.apply_russian_roulette  = ctx->path_const.apply_russian_roulette ? 1u : 0u;
+        pc.rr_start_depth          = (uint32_t)ctx->path_const.rr_start_depth;
+        pc.neural_roughness        = ctx->path_const.neural_roughness;
+        pc.neural_specular         = ctx->path_const.neural_specular;
+        pc.neural_metallic         = ctx->path_const.neural_metallic;
+        pc.force_constant_material = ctx->scene_const.force_constant_material ? 1u : 0u;
+        pc.emission_eval           = ctx->scene_const.emission_eval ? 1u : 0u;
+        pc.constant_roughness      = ctx->scene_const.constant_roughness;
+        pc.constant_specular       = ctx->scene_const.constant_specular;
+        pc.constant_metallic       = ctx->scene_const.constant_metallic;
+        NbvhConst nbvh_bounce = rp.nbvh;
+        if (ctx->bvh_const.path_lod_switch && ctx->bvh_const.num_lods_learned > 0)
+            nbvh_bounce.leaf_lod_max = 2u + (uint32_t)ctx->bvh_const.lod_switch;
+        CU_TRY(ctx, launch_render_path(rp, pc, nc, nbvh_bounce, ctx->d_bounce_counters, ctx->num_sms, st));
+    } else if (ctx->mega_kernel) {
         CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
     } else if (3u * (ctx->stage_used + 1u) <= ctx->stage_ev.size()) {
         cudaEvent_t *e = ctx->stage_ev.data() + 3u * ctx->stage_used;

@@ -7,6 +7,7 @@
 namespace nbvh {
 
 constexpr int kMaxBlas = 16;
+constexpr int kMaxPathDepth = 64; // max_depth bound of the multi-bounce path (queue counters per bounce)
 
 enum Counter {
     CNT_RAYS = 0,
@@ -33,6 +34,27 @@ struct NeuralQueueEntry {
     uint4 st[kNeuralStackSize / 4];
 };
 
+// Multi-bounce path state (max_depth > 1), one per pixel slot of the shard:
+//   s0 = (o.x, o.y, o.z, d.x)  s1 = (d.y, d.z, throughput.x, throughput.y)  s2 = (throughput.z, illumination.xyz)
+//   s3 = (rng state, ray depth -- 0 = path finished, pixel, -)
+struct PathState {
+    float4 s0, s1, s2;
+    uint4 s3;
+};
+// Closest hit of the path's current ray == HybridIntersectionResult (path_module.h:104-210):
+//   h0 = (t, valid_hit bits, normal_or_uv.xy)  h1 = (normal_or_uv.z, albedo_or_ids.xyz)
+struct PathHit {
+    float4 h0, h1;
+};
+
+// background_hit_eval constants (scene_constants + envmap_texture, path_inference_kernels.cu:37-59)
+struct BackgroundConst {
+    uint32_t envmap_eval, skylike_background;
+    float rot_cos, rot_sin; // glm::rotate(mat4(1), radians(envmap_rotation), +Y): x' = c x + s z, z' = -s x + c z
+    float strength;
+    cudaTextureObject_t envmap; // RGBA32F lat-long map, linear filter, clamp; 0 = white (the reference's fallback image)
+};
+
 struct RenderParams {
     CameraConst cam;
     NbvhConst nbvh;
@@ -41,8 +63,7 @@ struct RenderParams {
     DecodeConst dec;
     uint32_t ignore_neural_blas;
     uint32_t max_depth;
-    // background for rays that escape (scene_constants: envmap_eval off or skylike_background)
-    uint32_t envmap_eval, skylike_background;
+    BackgroundConst bg; // radiance of rays that escape
     // work distribution
     uint32_t first_pixel, pixel_count; // shard of the frame rendered by this launch
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
@@ -56,6 +77,10 @@ struct RenderParams {
     uint32_t ema_accumulate;
     float ema_weight;
     unsigned long long *counters;
+    // multi-bounce mode (path.cu): queue entries carry the path slot instead of the pixel, rays live in `paths`
+    PathState *paths;
+    PathHit *path_hits;
+    uint32_t ray_depth; // depth of the rays in flight (1 = camera rays): selects the visibility threshold
 };
 
 // smem carve-up of the tile kernels
@@ -133,6 +158,7 @@ cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float d
 cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
 cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream, cudaEvent_t between);
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k);
+cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream);
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);
 
 } // namespace nbvh

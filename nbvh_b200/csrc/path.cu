@@ -1,0 +1,245 @@
+// path.cu -- hybrid neural path tracing for max_depth > 1: replaces the host loop
+// NeuralPathModule::neural_path_tracing (/root/reference/src/cuda/neural/path/path_module.cu:139-245) and the kernels
+// hybrid_camera_raygen_and_hybrid_first_hit_and_traversal (K1), non_neural_bvh_intersection (K8) and
+// hybrid_scatter_and_get_next_tlas_traversal_step (K9: shading, BSDF sampling, Russian roulette, re-queue)
+// (/root/reference/src/cuda/neural/path/path_inference_kernels.cu:195-429).
+//
+// Per frame:   k_path_bounce<first>  ->  k_neural<path>  ->  k_path_bounce  ->  k_neural<path>  ->  ...  ->  k_path_bounce(last)
+//
+//   k_path_bounce   one thread per pixel slot.  Except in the first launch (camera rays) it first SHADES the closest hit that the
+//                   previous trace + k_neural left in path_hits[slot]: background for escaped rays, last-bounce splat,
+//                   intersection data and material of classical hits (texture fetches), the network's normal/albedo with the
+//                   module's constant metallic/roughness/specular for neural hits, emission, Disney BSDF sampling, throughput
+//                   update, Russian roulette, and the bounce ray.  It then TRACES the new ray exactly like k_primary does for
+//                   camera rays: whole TLAS walk with every classical BLAS closest hit, N-BVH walk to the first leaf interval,
+//                   ballot-compacted append to the neural ray queue.  Rays that need no network query leave their hit in
+//                   path_hits[slot] directly.
+//   k_neural<true>  the persistent tcgen05 tile kernel of render.cu; queue entries name path slots, rays come from the path
+//                   state, the closest hit goes to path_hits[slot].
+//
+// No host synchronisation and no ray-state ping-pong: 1 + 2 * max_depth launches per frame (the reference: ~125 launches and
+// ~22 host round trips per bounce).  The reference interleaves BLAS visits in TLAS order over several wavefront iterations;
+// the closest hit is the minimum over the same candidate set, so the paths are the same (see render.cu's header).
+// Random numbers are drawn in the reference's order (2 camera jitter, 3 per BSDF sample, 1 per roulette), so every pixel
+// follows the same path as in the reference up to floating-point rounding of the shading arithmetic.
+#include "render_common.cuh"
+#include "path.cuh"
+
+namespace nbvh {
+
+__device__ __forceinline__ void path_splat(const RenderParams &p, uint32_t pixel, V3 c) { splat(p, pixel, c.x, c.y, c.z, 1.0f); }
+
+// K9 after the TLAS walk of the current ray is complete (path_inference_kernels.cu:306-428).  Returns true when the path
+// continues with `ray` at depth + 1; otherwise the pixel has been splatted.
+__device__ __forceinline__ bool shade_and_scatter(const RenderParams &p, const PathConst &pc, uint32_t pixel, Ray &ray, uint32_t depth,
+                                                  const PathHit &ph, V3 &throughput, V3 &illumination, uint32_t &rng)
+{
+    const float best_t       = ph.h0.x;
+    const uint32_t valid_hit = __float_as_uint(ph.h0.y);
+    if (valid_hit == 0u || depth == p.max_depth) {
+        if (valid_hit == 0u)
+            illumination = add3(illumination, mul3(throughput, background_eval(p.bg, ray.dx, ray.dy, ray.dz)));
+        path_splat(p, pixel, illumination);
+        return false;
+    }
+    Bsdf bsdf   = default_bsdf();
+    const V3 wo = v3(-ray.dx, -ray.dy, -ray.dz);
+    V3 its_normal, hit_pos;
+    if (valid_hit == 1u) { // NEURAL_TRAVERSAL_HIT: the network's normal and albedo, constant specular parameters
+        bsdf.base_color = v3(ph.h1.y, ph.h1.z, ph.h1.w);
+        bsdf.metallic = pc.neural_metallic, bsdf.roughness = pc.neural_roughness, bsdf.specular = pc.neural_specular;
+        its_normal = v3(ph.h0.z, ph.h0.w, ph.h1.x);
+        hit_pos    = v3(ray.ox + best_t * ray.dx, ray.oy + best_t * ray.dy, ray.oz + best_t * ray.dz);
+    } else {
+        TriHit th;
+        th.t = best_t, th.u = ph.h0.z, th.v = ph.h0.w, th.prim = __float_as_uint(ph.h1.z);
+        const uint32_t mesh = __float_as_uint(ph.h1.y);
+        const ItsData its   = compute_its_data(p.scene.blas[mesh], pc.attr[mesh], pc.materials, pc.textures, th);
+        hit_pos = its.position, its_normal = its.sh_normal;
+        const bool has_material = its.material_id != -1 && pc.materials;
+        if (p.ignore_neural_blas && mesh == pc.neural_bvh_idx) {
+            if (has_material)
+                bsdf.base_color = color_param(pc.materials[its.material_id].base_color, its.u, its.v, pc.textures);
+            bsdf.metallic = pc.neural_metallic, bsdf.roughness = pc.neural_roughness, bsdf.specular = pc.neural_specular;
+        } else if (pc.force_constant_material) {
+            if (has_material)
+                bsdf.base_color = color_param(pc.materials[its.material_id].base_color, its.u, its.v, pc.textures);
+            bsdf.metallic = pc.constant_metallic, bsdf.roughness = pc.constant_roughness, bsdf.specular = pc.constant_specular;
+        } else if (has_material) {
+            bsdf = unpack_material(pc.materials[its.material_id], its.u, its.v, pc.textures);
+        }
+    }
+    V3 sh_normal, tangent, bitangent;
+    shading_frame(wo, its_normal, sh_normal, tangent, bitangent);
+    if ((depth == 1u || pc.emission_eval) && !is_zero3(bsdf.base_emission))
+        illumination = add3(illumination, mul3(throughput, scale3(bsdf.base_emission, bsdf.emission_scale)));
+    float pdf;
+    V3 wi;
+    const V3 f      = disney_sample_eval(bsdf, sh_normal, wo, tangent, bitangent, rng, wi, pdf);
+    const float cti = fabsf(dot3(wi, sh_normal));
+    throughput      = v3(throughput.x * (f.x * cti / pdf), throughput.y * (f.y * cti / pdf), throughput.z * (f.z * cti / pdf));
+    if (pdf == 0.f || is_zero3(f)) {
+        path_splat(p, pixel, illumination);
+        return false;
+    }
+    if (pc.apply_russian_roulette && rr_terminate(depth, throughput, pc.rr_start_depth, rng)) {
+        path_splat(p, pixel, illumination);
+        return false;
+    }
+    ray.ox = hit_pos.x + sh_normal.x * pc.normal_epsilon_offset;
+    ray.oy = hit_pos.y + sh_normal.y * pc.normal_epsilon_offset;
+    ray.oz = hit_pos.z + sh_normal.z * pc.normal_epsilon_offset;
+    ray.dx = wi.x, ray.dy = wi.y, ray.dz = wi.z;
+    ray_prepare(ray, p.cam.nodes_safe != 0u);
+    return true;
+}
+
+template <bool kFirst>
+__global__ void __launch_bounds__(256)
+k_path_bounce(const __grid_constant__ RenderParams p, const __grid_constant__ PathConst pc)
+{
+    const uint32_t lane  = threadIdx.x & 31u;
+    const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t sidx  = chunk * 32u + lane;
+    bool active          = sidx < p.pixel_count;
+    uint32_t cnt_blas = 0, cnt_tri = 0, cnt_nbvh = 0;
+    uint32_t pixel = 0, rng = 0, depth = 0;
+    Ray ray;
+    V3 throughput = splat3(1.f), illumination = splat3(0.f);
+    if (active) {
+        if constexpr (kFirst) {
+            pixel = swizzle_pixel(p, p.first_pixel + sidx);
+            ray   = camera_ray(p.cam, pixel, p.sample_idx, p.sample_offset, rng);
+            depth = 1u;
+        } else {
+            const PathState st = p.paths[sidx];
+            depth = st.s3.y;
+            if (depth == 0u) {
+                active = false;
+            } else {
+                rng = st.s3.x, pixel = st.s3.z;
+                ray.ox = st.s0.x, ray.oy = st.s0.y, ray.oz = st.s0.z, ray.dx = st.s0.w, ray.dy = st.s1.x, ray.dz = st.s1.y;
+                throughput   = v3(st.s1.z, st.s1.w, st.s2.x);
+                illumination = v3(st.s2.y, st.s2.z, st.s2.w);
+                const PathHit ph = p.path_hits[sidx];
+                if (shade_and_scatter(p, pc, pixel, ray, depth, ph, throughput, illumination, rng)) {
+                    ++depth;
+                } else {
+                    active            = false;
+                    p.paths[sidx].s3 = make_uint4(rng, 0u, pixel, 0u);
+                }
+            }
+        }
+    }
+    // ---- trace the ray: TLAS walk + classical BLAS closest hits + first N-BVH interval (same as k_primary)
+    bool neural = false;
+    uint32_t nstack[kNeuralStackSize];
+    int nss        = 0;
+    float seg_mint = 0.f, seg_maxt = 0.f;
+    HitState h;
+    h.best_t = FLT_MAX, h.valid_hit = 0u;
+    h.n_or_uv[0] = h.n_or_uv[1] = h.n_or_uv[2] = 0.f;
+    h.alb_or_ids[0] = h.alb_or_ids[1] = h.alb_or_ids[2] = 0.f;
+    if (active) {
+        uint32_t tstack[kTlasStackSize];
+        int tss   = 1;
+        tstack[0] = 0u;
+        while (tss > 0) {
+            uint32_t blas_idx;
+            bool is_neural;
+            if (!tlas_next_blas(p.scene.tlas, ray, tstack, tss, blas_idx, is_neural))
+                break;
+            if (is_neural && !p.ignore_neural_blas) {
+                neural = true;
+            } else if (blas_idx < p.scene.n_blas) {
+                const TriHit th = blas_closest_hit(p.scene.blas[blas_idx], ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
+                if (th.t < h.best_t) {
+                    h.best_t        = th.t;
+                    h.valid_hit     = 2u;
+                    h.n_or_uv[0]    = th.u, h.n_or_uv[1] = th.v, h.n_or_uv[2] = 0.f;
+                    h.alb_or_ids[0] = __uint_as_float(blas_idx), h.alb_or_ids[1] = __uint_as_float(th.prim);
+                    h.alb_or_ids[2] = 0.f;
+                }
+            }
+        }
+        if (neural) {
+            uint32_t node;
+            nstack[0] = 0u, nss = 1;
+            neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
+        }
+        PathState st;
+        st.s0 = make_float4(ray.ox, ray.oy, ray.oz, ray.dx);
+        st.s1 = make_float4(ray.dy, ray.dz, throughput.x, throughput.y);
+        st.s2 = make_float4(throughput.z, illumination.x, illumination.y, illumination.z);
+        st.s3 = make_uint4(rng, depth, pixel, 0u);
+        p.paths[sidx] = st;
+    }
+    const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
+    if (qmask) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(qmask) - 1))
+            base = atomicAdd(p.queue_count, (uint32_t)__popc(qmask));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(qmask) - 1);
+        if (active && neural) {
+            const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
+            NeuralQueueEntry *q = p.queue + slot;
+            q->a = make_uint4(sidx, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
+            q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
+            q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), 0u, 0u);
+            for (int i = 0; i < nss; i += 4)
+                q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
+        }
+    }
+    if (active && !neural) {
+        PathHit ph;
+        ph.h0 = make_float4(h.best_t, __uint_as_float(h.valid_hit), h.n_or_uv[0], h.n_or_uv[1]);
+        ph.h1 = make_float4(h.n_or_uv[2], h.alb_or_ids[0], h.alb_or_ids[1], h.alb_or_ids[2]);
+        p.path_hits[sidx] = ph;
+        if (kFirst && p.hits) { // primary-hit records of rays that never reach the network
+            nbvh_hit_record r;
+            r.t = h.best_t, r.valid_hit = h.valid_hit;
+            r.normal_or_uv[0] = h.n_or_uv[0], r.normal_or_uv[1] = h.n_or_uv[1], r.normal_or_uv[2] = h.n_or_uv[2];
+            r.albedo_or_ids[0] = h.alb_or_ids[0], r.albedo_or_ids[1] = h.alb_or_ids[1], r.albedo_or_ids[2] = h.alb_or_ids[2];
+            p.hits[pixel] = r;
+        }
+    }
+    warp_add_counter(p.counters, CNT_RAYS, active ? 1u : 0u);
+    warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
+    warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+    warp_add_counter(p.counters, CNT_QUEUED, active && neural ? 1u : 0u);
+}
+
+// One frame of NeuralPathModule::neural_path_tracing.  `counters` holds 2 zeroed words per bounce (queue count, cursor).
+cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
+                               uint32_t *bounce_counters, int num_sms, cudaStream_t stream)
+{
+    if (rp_in.pixel_count == 0)
+        return cudaSuccess;
+    RenderParams rp         = rp_in;
+    const uint32_t n_chunks = (rp.pixel_count + 31u) >> 5;
+    const uint32_t blocks   = (n_chunks + 7u) / 8u;
+    for (uint32_t depth = 1; depth <= rp.max_depth + 1u; ++depth) {
+        // launch `depth` shades the hits of the rays at depth-1 and traces the rays at `depth`
+        rp.queue_count  = bounce_counters + 2u * (depth - 1u);
+        rp.queue_cursor = rp.queue_count + 1;
+        rp.ray_depth    = depth;
+        if (depth > 1u)
+            rp.nbvh = nbvh_bounce; // path_lod_switch: bounce rays may walk a coarser LoD (neural_bvh_module_common.cuh:333-335)
+        if (depth == 1u)
+            k_path_bounce<true><<<blocks, 256, 0, stream>>>(rp, pc);
+        else
+            k_path_bounce<false><<<blocks, 256, 0, stream>>>(rp, pc);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+        if (depth == rp.max_depth + 1u)
+            break; // the last launch only shades (every path ends at max_depth)
+        e = launch_neural(rp, nc, num_sms, true, stream);
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
+
+} // namespace nbvh

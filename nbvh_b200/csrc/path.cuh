@@ -1,0 +1,24 @@
+// path.cuh -- parameter block of the multi-bounce path kernels (path.cu), shared with context.cu
+#pragma once
+#include "shading.cuh"
+
+namespace nbvh {
+
+struct PathConst {
+    BlasAttr attr[kMaxBlas];       // shading attributes of every BLAS (CudaSceneData.tlas.mesh_bvhs[i])
+    const MaterialPod *materials;  // CudaSceneData.materials
+    const cudaTextureObject_t *textures;
+    uint32_t neural_bvh_idx;       // bvh_const.neural_bvh_idx
+    // path_module_const (path_module.h:217-254)
+    float normal_epsilon_offset;
+    uint32_t apply_russian_roulette, rr_start_depth;
+    float neural_roughness, neural_specular, neural_metallic;
+    // scene_constants (cuda_backend.h:58-72)
+    uint32_t force_constant_material, emission_eval;
+    float constant_roughness, constant_specular, constant_metallic;
+};
+
+cudaError_t launch_render_path(const RenderParams &rp, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
+                               uint32_t *bounce_counters, int num_sms, cudaStream_t stream);
+
+} // namespace nbvh

@@ -26,13 +26,6 @@ constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
 constexpr int kWalkRounds    = 4;                        // refill/advance rounds before a tile runs the network
 
 // ------------------------------------------------------------------------------------------------ shared helpers
-struct HitState {
-    float best_t;
-    uint32_t valid_hit;
-    float n_or_uv[3];
-    float alb_or_ids[3];
-};
-
 // hybrid_scatter_and_get_next_tlas_traversal_step at ray_depth == max_depth (path_inference_kernels.cu:306-321)
 __device__ __forceinline__ void finish_pixel(const RenderParams &p, uint32_t pixel, const Ray &ray, const HitState &h)
 {
@@ -137,6 +130,29 @@ struct NeuralLane {
     bool have_ray, have_query;
 };
 
+// kPath: multi-bounce mode -- the queue entry names a path slot, the ray is read from the path state and the closest
+// hit goes to path_hits[slot] for the shading kernel (path.cu) instead of being splatted
+template <bool kPath>
+__device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, const Ray &ray, const HitState &h)
+{
+    if constexpr (kPath) {
+        PathHit ph;
+        ph.h0 = make_float4(h.best_t, __uint_as_float(h.valid_hit), h.n_or_uv[0], h.n_or_uv[1]);
+        ph.h1 = make_float4(h.n_or_uv[2], h.alb_or_ids[0], h.alb_or_ids[1], h.alb_or_ids[2]);
+        p.path_hits[id] = ph;
+        if (p.hits && p.ray_depth == 1u) { // primary-hit record (parity hook)
+            nbvh_hit_record r;
+            r.t = h.best_t, r.valid_hit = h.valid_hit;
+            r.normal_or_uv[0] = h.n_or_uv[0], r.normal_or_uv[1] = h.n_or_uv[1], r.normal_or_uv[2] = h.n_or_uv[2];
+            r.albedo_or_ids[0] = h.alb_or_ids[0], r.albedo_or_ids[1] = h.alb_or_ids[1], r.albedo_or_ids[2] = h.alb_or_ids[2];
+            p.hits[p.paths[id].s3.z] = r;
+        }
+    } else {
+        finish_pixel(p, id, ray, h);
+    }
+}
+
+template <bool kPath>
 __global__ void __launch_bounds__(kNeuralThreads, 2)
 k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetConst nc)
 {
@@ -185,7 +201,14 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                         const uint4 a = q->a, b = q->b, c = q->c;
                         uint32_t rng;
                         s.pixel       = a.x;
-                        s.ray         = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, rng);
+                        if constexpr (kPath) {
+                            const float4 s0 = p.paths[a.x].s0, s1 = p.paths[a.x].s1;
+                            s.ray.ox = s0.x, s.ray.oy = s0.y, s.ray.oz = s0.z;
+                            s.ray.dx = s0.w, s.ray.dy = s1.x, s.ray.dz = s1.y;
+                            ray_prepare(s.ray, p.cam.nodes_safe != 0u);
+                        } else {
+                            s.ray = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, rng);
+                        }
                         s.h.best_t    = __uint_as_float(a.y);
                         s.h.valid_hit = a.z;
                         s.h.n_or_uv[0] = __uint_as_float(a.w), s.h.n_or_uv[1] = __uint_as_float(b.x), s.h.n_or_uv[2] = 0.f;
@@ -213,7 +236,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
                     s.have_query = true;
                 } else {
-                    finish_pixel(p, s.pixel, s.ray, s.h);
+                    finish_lane<kPath>(p, s.pixel, s.ray, s.h);
                     s.have_ray = false;
                 }
             }
@@ -261,7 +284,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
-            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, 1u, t_hit) && t_hit < s.h.best_t) {
+            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, kPath ? p.ray_depth : 1u, t_hit) && t_hit < s.h.best_t) {
                 s.h.best_t    = t_hit;
                 s.h.valid_hit = 1u;
                 decode_normal(y[2], y[3], y[4], s.h.n_or_uv);
@@ -285,7 +308,19 @@ cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
 {
     const SmemLayout lay = smem_layout(wimg_bytes, in_k, kNeuralTiles);
     g_neural_smem        = lay.total;
-    return cudaFuncSetAttribute(k_neural, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    cudaError_t e = cudaFuncSetAttribute(k_neural<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    if (e != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_neural<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+}
+
+cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream)
+{
+    if (path_mode)
+        k_neural<true><<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+    else
+        k_neural<false><<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream, cudaEvent_t between)
@@ -299,8 +334,7 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
         return e;
     if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess)
         return e;
-    k_neural<<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
-    return cudaGetLastError();
+    return launch_neural(rp, nc, num_sms, false, stream);
 }
 
 } // namespace nbvh

@@ -1,8 +1,16 @@
 // render_common.cuh -- device helpers shared by the tile kernels (k_query, k_render, k_neural) and the primary pass.
 #pragma once
-#include "kernels.cuh"
+#include "shading.cuh"
 
 namespace nbvh {
+
+// closest hit of the ray in flight (NeuralTraversalResult / HybridIntersectionResult, path_module.h:19-45,104-210)
+struct HitState {
+    float best_t;
+    uint32_t valid_hit;
+    float n_or_uv[3];
+    float alb_or_ids[3];
+};
 
 // ------------------------------------------------------------------------------------------------ CTA setup
 __host__ __device__ constexpr uint32_t tmem_cols(int tiles) { return tiles <= 1 ? 64u : tiles <= 2 ? 128u : tiles <= 4 ? 256u : 512u; }
@@ -106,19 +114,11 @@ __device__ __forceinline__ void splat(const RenderParams &p, uint32_t pixel, flo
     }
 }
 
-// background_hit_eval (path_inference_kernels.cu:37-59); the HDR environment texture belongs to the shading
-// row and evaluates to black here.
+// background_hit_eval (path_inference_kernels.cu:37-59)
 __device__ __forceinline__ void background(const RenderParams &p, const Ray &ray, float bg[3])
 {
-    bg[0] = bg[1] = bg[2] = 0.f;
-    if (!p.envmap_eval)
-        return;
-    if (p.skylike_background) {
-        const float a = 0.5f * (ray.dy + 1.f);
-        bg[0] = (1.f - a) * 1.f + a * 0.5f;
-        bg[1] = (1.f - a) * 1.f + a * 0.7f;
-        bg[2] = (1.f - a) * 1.f + a * 1.f;
-    }
+    const V3 c = background_eval(p.bg, ray.dx, ray.dy, ray.dz);
+    bg[0] = c.x, bg[1] = c.y, bg[2] = c.z;
 }
 
 // 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1)

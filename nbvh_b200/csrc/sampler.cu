@@ -25,46 +25,6 @@
 
 namespace nbvh {
 
-struct V3 {
-    float x, y, z;
-};
-__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
-__device__ __forceinline__ V3 ld3(const float *p, uint32_t i) { return V3{__ldg(p + 3u * i), __ldg(p + 3u * i + 1u), __ldg(p + 3u * i + 2u)}; }
-__device__ __forceinline__ V3 sub3(V3 a, V3 b) { return V3{__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)}; }
-__device__ __forceinline__ float dot3(V3 a, V3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y))); }
-__device__ __forceinline__ V3 cross3(V3 a, V3 b)
-{
-    return V3{__fmaf_rn(a.y, b.z, -__fmul_rn(b.y, a.z)), __fmaf_rn(a.z, b.x, -__fmul_rn(b.z, a.x)), __fmaf_rn(a.x, b.y, -__fmul_rn(b.x, a.y))};
-}
-// glm::normalize: v * inversesqrt(dot(v, v)), inversesqrt = rcp(sqrt) on the device (same pattern as camera_ray)
-__device__ __forceinline__ V3 normalize3(V3 a)
-{
-    const float inv = __frcp_rn(__fsqrt_rn(dot3(a, a)));
-    return V3{__fmul_rn(a.x, inv), __fmul_rn(a.y, inv), __fmul_rn(a.z, inv)};
-}
-// w*a + u*b + v*c per component: the reference's SASS evaluates fma(v,c, fma(w,a, u*b)) (found by matching the reference
-// kernel's outputs bit for bit, tests/golden/ref_chess_sampler.npz)
-__device__ __forceinline__ float bary(float w, float a, float u, float b, float v, float c)
-{
-    return __fmaf_rn(v, c, __fmaf_rn(w, a, __fmul_rn(u, b)));
-}
-
-// include/cuda/utils/common.cuh:21-36
-__device__ __forceinline__ void ortho_basis(V3 &tangent, V3 &bitangent, V3 n)
-{
-    bitangent = v3(0.f, 0.f, 0.f);
-    if (n.x < 0.6f && n.x > -0.6f)
-        bitangent.x = 1.f;
-    else if (n.y < 0.6f && n.y > -0.6f)
-        bitangent.y = 1.f;
-    else if (n.z < 0.6f && n.z > -0.6f)
-        bitangent.z = 1.f;
-    else
-        bitangent.x = 1.f;
-    tangent   = normalize3(cross3(bitangent, n));
-    bitangent = normalize3(cross3(n, tangent));
-}
-
 // include/cuda/utils/sampling.cuh:8-14
 __device__ __forceinline__ V3 square_to_uniform_sphere(float sx, float sy)
 {
@@ -72,89 +32,6 @@ __device__ __forceinline__ V3 square_to_uniform_sphere(float sx, float sy)
     const float cos_theta = __fmaf_rn(sy, 2.0f, -1.0f);
     const float sin_theta = __fsqrt_rn(__fmaf_rn(-cos_theta, cos_theta, 1.0f));
     return V3{__fmul_rn(sin_theta, cosf(phi)), __fmul_rn(sin_theta, sinf(phi)), cos_theta};
-}
-
-// include/cuda/base/material.cuh:101-120,193-200
-__device__ __forceinline__ V3 sample_lambertian_dir(V3 n, V3 tangent, V3 bitangent, float ux, float uy)
-{
-    const float sx = __fmaf_rn(2.f, ux, -1.f), sy = __fmaf_rn(2.f, uy, -1.f);
-    float dx = sx, dy = sy;
-    if (!(sx == 0.f && sy == 0.f)) {
-        float radius, theta;
-        if (fabsf(sx) > fabsf(sy)) {
-            radius = sx;
-            theta  = __fmul_rn(0.78539818525314331f, __fdiv_rn(sy, sx));
-        } else {
-            radius = sy;
-            theta  = __fsub_rn(1.5707963705062866f, __fmul_rn(0.78539818525314331f, __fdiv_rn(sx, sy)));
-        }
-        dx = __fmul_rn(radius, cosf(theta)), dy = __fmul_rn(radius, sinf(theta));
-    }
-    const float dz = __fsqrt_rn(fmaxf(0.f, __fsub_rn(__fsub_rn(1.f, __fmul_rn(dx, dx)), __fmul_rn(dy, dy))));
-    const V3 h = normalize3(v3(dx, dy, dz));
-    return V3{bary(h.x, tangent.x, h.y, bitangent.x, h.z, n.x), bary(h.x, tangent.y, h.y, bitangent.y, h.z, n.y),
-              bary(h.x, tangent.z, h.y, bitangent.z, h.z, n.z)};
-}
-
-struct ItsData {
-    V3 position, sh_normal;
-    float u, v; // texture coordinates
-    int material_id;
-};
-
-__device__ __forceinline__ float4 tex_fetch(const cudaTextureObject_t *textures, uint32_t id, float u, float v)
-{
-    return tex2D<float4>(textures[id], u, v);
-}
-
-// BaseCudaBLAS::compute_its_data (bvh.cuh:53-96)
-__device__ __forceinline__ ItsData compute_its_data(const SamplerParams &p, const TriHit &h)
-{
-    ItsData its;
-    const uint32_t i0 = __ldg(p.blas.indices + 3u * h.prim), i1 = __ldg(p.blas.indices + 3u * h.prim + 1u),
-                   i2 = __ldg(p.blas.indices + 3u * h.prim + 2u);
-    // upper_bound(material_map, num_materials, prim) - 1
-    uint32_t left = 0, right = p.attr.num_materials;
-    while (left < right) {
-        const uint32_t mid = left + (right - left) / 2u;
-        if (__ldg(p.attr.material_map + mid) <= h.prim)
-            left = mid + 1u;
-        else
-            right = mid;
-    }
-    its.material_id = p.attr.material_ids ? __ldg(p.attr.material_ids + (left - 1u)) : -1;
-    const V3 v0 = ld3(p.blas.vertices, i0), v1 = ld3(p.blas.vertices, i1), v2 = ld3(p.blas.vertices, i2);
-    const float w = __fsub_rn(__fsub_rn(1.f, h.u), h.v);
-    if (p.attr.normals) {
-        const V3 n0 = ld3(p.attr.normals, i0), n1 = ld3(p.attr.normals, i1), n2 = ld3(p.attr.normals, i2);
-        its.sh_normal = normalize3(v3(bary(w, n0.x, h.u, n1.x, h.v, n2.x), bary(w, n0.y, h.u, n1.y, h.v, n2.y), bary(w, n0.z, h.u, n1.z, h.v, n2.z)));
-    } else {
-        its.sh_normal = normalize3(cross3(sub3(v1, v0), sub3(v2, v0)));
-    }
-    its.position = v3(bary(w, v0.x, h.u, v1.x, h.v, v2.x), bary(w, v0.y, h.u, v1.y, h.v, v2.y), bary(w, v0.z, h.u, v1.z, h.v, v2.z));
-    if (p.attr.texcoords) {
-        const float *t = p.attr.texcoords;
-        its.u = bary(w, __ldg(t + 2u * i0), h.u, __ldg(t + 2u * i1), h.v, __ldg(t + 2u * i2));
-        its.v = bary(w, __ldg(t + 2u * i0 + 1u), h.u, __ldg(t + 2u * i1 + 1u), h.v, __ldg(t + 2u * i2 + 1u));
-    } else {
-        its.u = h.u, its.v = h.v;
-    }
-    if (its.material_id != -1 && p.materials) {
-        // unpack_normal (material.cuh:66-75): tangent-space normal map -> world
-        const uint32_t mask = __float_as_uint(p.materials[its.material_id].normal[0]);
-        if (mask & 0x80000000u) {
-            const float4 tx = tex_fetch(p.textures, mask & 0x1fffffffu, its.u, its.v);
-            if (!(tx.x == -1.f && tx.y == -1.f && tx.z == -1.f)) {
-                const V3 tsn = normalize3(v3(__fsub_rn(tx.x, 0.5f), __fsub_rn(tx.y, 0.5f), __fsub_rn(tx.z, 0.5f)));
-                V3 tw, bw;
-                ortho_basis(tw, bw, its.sh_normal);
-                const V3 n = its.sh_normal; // mat3(tw, bw, n) * tsn = tw*x + bw*y + n*z
-                its.sh_normal = v3(bary(tw.x, tsn.x, bw.x, tsn.y, n.x, tsn.z), bary(tw.y, tsn.x, bw.y, tsn.y, n.y, tsn.z),
-                                   bary(tw.z, tsn.x, bw.z, tsn.y, n.z, tsn.z));
-            }
-        }
-    }
-    return its;
 }
 
 // node survival roulette (neural_bvh_module_kernels.cu:181-198); consumes one random number
@@ -202,7 +79,7 @@ __device__ __forceinline__ bool emit_slot(const SamplerParams &p, uint32_t slot,
     tg[o] = is_hit ? 1.f : 0.f;
     o += p.vis_dim;
     if (is_hit && (p.normal_dim || p.albedo_dim || p.max_training_bounces > 0))
-        its = compute_its_data(p, hit);
+        its = compute_its_data(p.blas, p.attr, p.materials, p.textures, hit);
     if (p.depth_dim) { // LocalT: (t - mint) / ((double)len + 1e-3), evaluated in double like the reference's literal
         float depth = 0.f;
         if (is_hit) {

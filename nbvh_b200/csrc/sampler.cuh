@@ -1,27 +1,8 @@
 // sampler.cuh -- parameter block of the online-optimisation sample generator (sampler.cu), shared with context.cu
 #pragma once
-#include "kernels.cuh"
+#include "shading.cuh"
 
 namespace nbvh {
-
-// PackedMaterial == Material + vtable pointer (include/base/material.h:52-87): 96 bytes
-struct MaterialPod {
-    unsigned long long vptr;
-    float base_color[3], metallic;
-    float specular, roughness, specular_tint, anisotropy;
-    float sheen, sheen_tint, clearcoat, clearcoat_gloss;
-    float base_emission[3], emission_scale;
-    float normal[3], ior;
-    float specular_transmission, pad;
-};
-static_assert(sizeof(MaterialPod) == 96, "PackedMaterial layout");
-
-struct BlasAttr { // BaseCudaBLAS shading attributes (include/cuda/accel/bvh.cuh:11-23)
-    const float *normals, *texcoords;
-    const int *material_ids;
-    const uint32_t *material_map;
-    uint32_t num_materials;
-};
 
 struct SamplerParams {
     NbvhConst nbvh; // raw (undilated) node array, learning epsilons; leaf_lod_max / dilation are set per slot

@@ -179,6 +179,18 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_set_scene(self._h, C.byref(sd)))
         self._keep["scene"] = keep
 
+    def set_envmap(self, pixels):
+        """== CudaBackend::load_envmap (cuda_backend.cpp:455-500): (H, W, 4) float32 lat-long radiance map, or None for the
+        reference's white fallback image.  Create it AFTER set_scene(textures=...) (which re-creates the texture set)."""
+        if pixels is None:
+            self._check(self._lib.nbvh_set_envmap(self._h, 0))
+            return
+        img = np.ascontiguousarray(pixels, dtype=np.float32)
+        assert img.ndim == 3 and img.shape[2] == 4
+        h = C.c_uint64(0)
+        self._check(self._lib.nbvh_create_envmap_rgba32f(self._h, img.ctypes.data_as(C.c_void_p), img.shape[1], img.shape[0], C.byref(h)))
+        self._check(self._lib.nbvh_set_envmap(self._h, h.value))
+
     def set_neural_bvh(self, nodes):
         torch = _torch()
         nodes = np.ascontiguousarray(nodes, dtype=NODE_DTYPE)
@@ -224,6 +236,17 @@ class NeuralPathModule:
     def reinitialise_inference_data(self, fb_size):
         """== reinitialise_inference_data(fb_size): (re)allocates the frame buffers."""
         self._check(self._lib.nbvh_set_framebuffer(self._h, None, None, int(fb_size[0]), int(fb_size[1])))
+
+    def attach_framebuffer(self, fb_size):
+        """Caller-owned frame buffers (the reference's GL surfaces): returns (accum RGBA32F [H, W, 4], ldr sRGB8 [H, W, 4])."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        w, h = int(fb_size[0]), int(fb_size[1])
+        accum = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+        ldr = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+        self._check(self._lib.nbvh_set_framebuffer(self._h, _ptr(accum), _ptr(ldr), w, h))
+        self._keep["fb"] = (accum, ldr)
+        return accum, ldr
 
     def attach_hit_buffer(self, n_pixels):
         torch = _torch()

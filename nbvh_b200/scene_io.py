@@ -94,8 +94,31 @@ def load_scene_arrays(root, with_neural_mesh=False, with_attributes=False):
     return tlas_nodes, tlas_idx, blas, man
 
 
-def load_chess_module(device=0, max_depth=1, envmap_eval=False, with_neural_mesh=False, root=None):
-    """Shipped Chess configuration: config JSON, .nbvh and network_models JSON load unchanged through the C ABI."""
+def load_shading_arrays(root, with_envmap=True):
+    """Materials (PackedMaterial records), RGBA8 textures and the RGBA32F environment map of the Chess fixture
+    (tools/make_fixtures.py: write_shading_fixture).  Returns (materials, textures, envmap or None)."""
+    mats = np.fromfile(os.path.join(root, "materials.bin"), dtype=MATERIAL_DTYPE)
+    textures = []
+    k = 0
+    while os.path.exists(os.path.join(root, "tex%d.rgba8" % k)):
+        w, h = np.fromfile(os.path.join(root, "tex%d.dims" % k), dtype="<u4")
+        textures.append(np.fromfile(os.path.join(root, "tex%d.rgba8" % k), dtype=np.uint8).reshape(int(h), int(w), 4))
+        k += 1
+    env = None
+    if with_envmap and os.path.exists(os.path.join(root, "envmap.f32")):
+        w, h = np.fromfile(os.path.join(root, "envmap.dims"), dtype="<u4")
+        env = np.fromfile(os.path.join(root, "envmap.f32"), dtype="<f4").reshape(int(h), int(w), 4)
+    return mats, textures, env
+
+
+def has_shading_fixture(root=None):
+    root = root or chess_fixture_dir()
+    return root is not None and os.path.exists(os.path.join(root, "materials.bin")) and os.path.exists(os.path.join(root, "envmap.f32"))
+
+
+def load_chess_module(device=0, max_depth=1, envmap_eval=False, with_neural_mesh=False, root=None, shading=False):
+    """Shipped Chess configuration: config JSON, .nbvh and network_models JSON load unchanged through the C ABI.
+    shading=True also uploads the shading attributes, materials, textures and the shipped environment map (max_depth > 1)."""
     root = root or chess_fixture_dir()
     if root is None:
         raise FileNotFoundError("Chess fixture missing (baseline/_ref/chess); run tools/make_fixtures.py")
@@ -103,8 +126,13 @@ def load_chess_module(device=0, max_depth=1, envmap_eval=False, with_neural_mesh
     mod = NeuralPathModule(cfg_text, device=device)
     mod.load_neural_bvh(os.path.join(root, CHESS_BASE + ".nbvh"))
     mod.load_network_model(os.path.join(root, CHESS_BASE + "_network.json"))
-    tlas_nodes, tlas_idx, blas, _ = load_scene_arrays(root, with_neural_mesh)
-    mod.set_scene(tlas_nodes, tlas_idx, blas)
+    tlas_nodes, tlas_idx, blas, man = load_scene_arrays(root, with_neural_mesh, with_attributes=shading)
+    if shading:
+        mats, textures, env = load_shading_arrays(root, with_envmap=envmap_eval)
+        mod.set_scene(tlas_nodes, tlas_idx, blas, materials=mats, textures=textures)
+        mod.set_envmap(env)
+    else:
+        mod.set_scene(tlas_nodes, tlas_idx, blas)
     mod.max_depth = max_depth
     from ._capi import CONST_SCENE
     sc = mod.get_constants(CONST_SCENE)

@@ -1084,11 +1084,10 @@ void onbvh_generate_batch(const onode_t *nbvh, const oconst_t *c, const osampler
 }
 
 /* ------------------------------------------------------------------ primary-ray pipeline */
-static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t pixel,
-                       int sample_idx, int rnd_offset, int mlp_mode, ohit_t *hit, uint64_t *cnt)
+/* closest hit of one ray over the whole TLAS: classical BLAS closest hits + neural leaf queries, in TLAS order */
+static void trace_ray(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const float o[3],
+                      const float d[3], uint32_t ray_depth, uint32_t lod, int mlp_mode, ohit_t *hit, uint64_t *cnt)
 {
-    float o[3], d[3];
-    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, NULL);
     memset(hit, 0, sizeof(*hit));
     hit->t = FLT_MAX;
     uint32_t tstack[TLAS_STACK_SIZE];
@@ -1109,7 +1108,7 @@ static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c
             for (;;) {
                 float mint, maxt;
                 uint32_t node;
-                if (!onbvh_neural_intersect(nbvh, c, c->rendered_lod, o, d, stack, &ss, 1, maxt_ray,
+                if (!onbvh_neural_intersect(nbvh, c, lod, o, d, stack, &ss, 1, maxt_ray,
                                             c->fixed_node_dilation, &mint, &maxt, &node, &cnt[1]))
                     break;
                 float pts[64], y[16];
@@ -1118,7 +1117,7 @@ static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c
                 cnt[0]++;
                 float t;
                 /* process_neural_bvh_traversal_step (path_inference_kernels.cu:61-131) */
-                if (onbvh_decode(c, y, mint, maxt, 1u, &t) && t < hit->t) {
+                if (onbvh_decode(c, y, mint, maxt, ray_depth, &t) && t < hit->t) {
                     hit->valid_hit = 1;
                     hit->t         = t;
                     float n[3]     = {y[2] * 2.f - 1.f, y[3] * 2.f - 1.f, y[4] * 2.f - 1.f};
@@ -1151,6 +1150,14 @@ static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c
     }
 }
 
+static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t pixel,
+                       int sample_idx, int rnd_offset, int mlp_mode, ohit_t *hit, uint64_t *cnt)
+{
+    float o[3], d[3];
+    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, NULL);
+    trace_ray(s, nbvh, c, net, o, d, 1u, c->rendered_lod, mlp_mode, hit, cnt);
+}
+
 void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net,
                           uint32_t pixel_begin, uint32_t pixel_end, uint32_t pixel_stride, int sample_idx,
                           int rnd_offset, int mlp_mode, ohit_t *hits, uint64_t *counters, int n_threads)
@@ -1172,6 +1179,460 @@ void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t
     }
     if (counters) {
         counters[0] = c0, counters[1] = c1, counters[2] = c2, counters[3] = c3;
+    }
+}
+
+/* ================================================================== hybrid neural path tracing (a15, f1) */
+/* Restates, in plain fp32 without contraction:
+ *   unpack_material / unpack_albedo           include/cuda/base/material.cuh:24-89
+ *   Disney BSDF sample / eval / pdf           include/cuda/base/material.cuh:91-592
+ *   Fr / Refract                              include/cuda/base/wip_disney.cuh:128-152
+ *   shading_frame / rr_terminate              include/cuda/utils/rendering.cuh:11-40
+ *   background_hit_eval                       src/cuda/neural/path/path_inference_kernels.cu:37-59
+ *   hybrid_scatter_and_get_next_tlas_traversal_step + neural_path_tracing
+ *                                             src/cuda/neural/path/path_inference_kernels.cu:224-429, path_module.cu:139-245 */
+#define O_PI 3.14159265358979323846f
+#define O_INV_PI 0.31830988618379067154f
+typedef struct {
+    float base_color[3], metallic, specular, roughness, specular_tint, anisotropy, sheen, sheen_tint, clearcoat,
+        clearcoat_gloss, base_emission[3], emission_scale, ior, specular_transmission;
+} obsdf_t;
+
+static float p_scalar(float x, const float uv[2], const otexture_t *tex)
+{
+    uint32_t mask;
+    memcpy(&mask, &x, 4);
+    if (mask & 0x80000000u) {
+        float t[4];
+        onbvh_tex2d(&tex[mask & 0x1fffffffu], uv[0], uv[1], t);
+        return t[(mask >> 29) & 3u];
+    }
+    return x;
+}
+static void p_color(const float p[3], const float uv[2], const otexture_t *tex, float out[3])
+{
+    uint32_t mask;
+    memcpy(&mask, &p[0], 4);
+    if (mask & 0x80000000u) {
+        float t[4];
+        onbvh_tex2d(&tex[mask & 0x1fffffffu], uv[0], uv[1], t);
+        out[0] = t[0], out[1] = t[1], out[2] = t[2];
+    } else {
+        out[0] = p[0], out[1] = p[1], out[2] = p[2];
+    }
+}
+static void p_default_bsdf(obsdf_t *b)
+{
+    memset(b, 0, sizeof(*b));
+    b->base_color[0] = b->base_color[1] = b->base_color[2] = 0.9f;
+    b->roughness = 1.f, b->emission_scale = 1.f, b->ior = 1.5f;
+}
+static void p_unpack_material(const omaterial_t *m, const float uv[2], const otexture_t *tex, obsdf_t *b)
+{
+    p_color(m->base_color, uv, tex, b->base_color);
+    b->metallic              = p_scalar(m->metallic, uv, tex);
+    b->specular              = p_scalar(m->specular, uv, tex);
+    b->roughness             = p_scalar(m->roughness, uv, tex);
+    b->specular_tint         = p_scalar(m->specular_tint, uv, tex);
+    b->anisotropy            = p_scalar(m->anisotropy, uv, tex);
+    b->sheen                 = p_scalar(m->sheen, uv, tex);
+    b->sheen_tint            = p_scalar(m->sheen_tint, uv, tex);
+    b->clearcoat             = p_scalar(m->clearcoat, uv, tex);
+    b->clearcoat_gloss       = p_scalar(m->clearcoat_gloss, uv, tex);
+    b->ior                   = p_scalar(m->ior, uv, tex);
+    b->specular_transmission = p_scalar(m->specular_transmission, uv, tex);
+    p_color(m->base_emission, uv, tex, b->base_emission);
+    b->emission_scale = m->emission_scale;
+}
+
+static inline float p_sqr(float x) { return x * x; }
+static inline float p_lerp(float a, float b, float t) { return a * (1.f - t) + b * t; } /* glm::mix */
+static inline float p_sat(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+static inline float p_schlick(float c) { return powf(p_sat(1.f - c), 5.f); }
+static inline float p_lum(const float c[3]) { return 0.2126f * c[0] + 0.7152f * c[1] + 0.0722f * c[2]; }
+static inline int p_same_hemi(const float wo[3], const float wi[3], const float n[3]) { return dot_ptx(wo, n) * dot_ptx(wi, n) > 0.f; }
+static void p_half(const float wi[3], const float wo[3], float h[3])
+{
+    float t[3] = {wi[0] + wo[0], wi[1] + wo[1], wi[2] + wo[2]};
+    s_normalize(t, h);
+}
+static void p_reflect(const float i[3], const float n[3], float out[3])
+{
+    float d = dot_ptx(i, n);
+    for (int k = 0; k < 3; k++)
+        out[k] = i[k] - 2.f * n[k] * d;
+}
+static void p_to_world(const float h[3], const float t[3], const float b[3], const float n[3], float out[3])
+{
+    for (int i = 0; i < 3; i++)
+        out[i] = s_bary(h[0], t[i], h[1], b[i], h[2], n[i]);
+}
+static float p_gtr1(float c, float alpha)
+{
+    if (alpha >= 1.f)
+        return O_INV_PI;
+    float a2 = alpha * alpha;
+    return O_INV_PI * (a2 - 1.f) / (logf(a2) * (1.f + (a2 - 1.f) * c * c));
+}
+static float p_gtr2(float c, float alpha)
+{
+    float a2 = alpha * alpha;
+    return O_INV_PI * a2 / p_sqr(1.f + (a2 - 1.f) * c * c);
+}
+static float p_gtr2_aniso(float hn, float hx, float hy, float ax, float ay)
+{
+    return O_INV_PI / (ax * ay * p_sqr(p_sqr(hx / ax) + p_sqr(hy / ay) + hn * hn));
+}
+static float p_smith(float n_dot_o, float alpha_g)
+{
+    float a = alpha_g * alpha_g, b = n_dot_o * n_dot_o;
+    return 1.f / (n_dot_o + sqrtf(a + b - a * b));
+}
+static float p_smith_aniso(float n_dot_o, float ox, float oy, float ax, float ay)
+{
+    return 1.f / (n_dot_o + sqrtf(p_sqr(ox * ax) + p_sqr(oy * ay) + p_sqr(n_dot_o)));
+}
+static void p_spec_colour(const obsdf_t *m, float out[3])
+{
+    float lum = p_lum(m->base_color);
+    for (int i = 0; i < 3; i++) {
+        float tint = lum > 0.f ? m->base_color[i] * (1.f / lum) : 1.f;
+        out[i]     = p_lerp(p_lerp(1.f, tint, m->specular_tint) * (m->specular * 0.08f), m->base_color[i], m->metallic);
+    }
+}
+static float p_fresnel_dielectric(float ci, float eta_i, float eta_t)
+{
+    float g = p_sqr(eta_t) / p_sqr(eta_i) - 1.f + p_sqr(ci);
+    if (g < 0.f)
+        return 1.f;
+    return 0.5f * p_sqr(g - ci) / p_sqr(g + ci) * (1.f + p_sqr(ci * (g + ci) - 1.f) / p_sqr(ci * (g - ci) + 1.f));
+}
+static void p_transmission_half(const float wo[3], const float wi[3], float eta_i, float eta_o, float h[3])
+{
+    float t[3];
+    for (int i = 0; i < 3; i++)
+        t[i] = wo[i] + wi[i] * eta_i * (1.f / eta_o);
+    s_normalize(t, h);
+}
+
+static void p_disney_eval(const obsdf_t *m, const float n[3], const float wo[3], const float wi[3], const float tg[3],
+                          const float bt[3], float out[3])
+{
+    out[0] = out[1] = out[2] = 0.f;
+    if (!p_same_hemi(wo, wi, n)) {
+        if (m->specular_transmission > 0.f) {
+            float on = dot_ptx(wo, n), in = dot_ptx(wi, n);
+            if (on == 0.f || in == 0.f)
+                return;
+            int entering = on > 0.f;
+            float eta_o = entering ? 1.f : m->ior, eta_i = entering ? m->ior : 1.f, h[3];
+            p_transmission_half(wo, wi, eta_i, eta_o, h);
+            float alpha = fmaxf(0.001f, m->roughness * m->roughness);
+            float d = p_gtr2(fabsf(dot_ptx(n, h)), alpha), f = p_fresnel_dielectric(fabsf(in), eta_o, eta_i);
+            float g = p_smith(fabsf(in), alpha) * p_smith(fabsf(on), alpha);
+            float ih = dot_ptx(wi, h), oh = dot_ptx(wo, h);
+            float c = fabsf(oh) / fabsf(on) * fabsf(ih) / fabsf(in) * p_sqr(eta_o) / p_sqr(eta_o * oh + eta_i * ih);
+            for (int i = 0; i < 3; i++)
+                out[i] = m->base_color[i] * (c * (1.f - f) * g * d) * ((1.f - m->metallic) * m->specular_transmission);
+        }
+        return;
+    }
+    float h[3], spec[3];
+    p_half(wi, wo, h);
+    p_spec_colour(m, spec);
+    /* clear coat */
+    float coat = 0.25f * m->clearcoat * p_gtr1(dot_ptx(n, h), p_lerp(0.1f, 0.001f, m->clearcoat_gloss)) *
+                 p_lerp(0.04f, 1.f, p_schlick(dot_ptx(wi, n))) * (p_smith(dot_ptx(n, wi), 0.25f) * p_smith(dot_ptx(n, wo), 0.25f));
+    /* sheen + diffuse */
+    float lum = p_lum(m->base_color), fh = p_schlick(dot_ptx(wi, h));
+    float n_dot_o = fabsf(dot_ptx(wo, n)), n_dot_i = fabsf(dot_ptx(wi, n)), ih = dot_ptx(wi, h);
+    float fd90 = 0.5f + 2.f * m->roughness * ih * ih;
+    float dif  = O_INV_PI * p_lerp(1.f, fd90, p_schlick(n_dot_i)) * p_lerp(1.f, fd90, p_schlick(n_dot_o));
+    /* gloss */
+    float dg;
+    if (m->anisotropy == 0.f) {
+        float alpha = fmaxf(0.001f, m->roughness * m->roughness);
+        dg = p_gtr2(dot_ptx(n, h), alpha) * (p_smith(dot_ptx(n, wi), alpha) * p_smith(dot_ptx(n, wo), alpha));
+    } else {
+        float aspect = sqrtf(1.f - m->anisotropy * 0.9f), a = m->roughness * m->roughness;
+        float ax = fmaxf(0.001f, a / aspect), ay = fmaxf(0.001f, a * aspect);
+        dg = p_gtr2_aniso(dot_ptx(n, h), fabsf(dot_ptx(h, tg)), fabsf(dot_ptx(h, bt)), ax, ay) *
+             (p_smith_aniso(dot_ptx(n, wi), fabsf(dot_ptx(wi, tg)), fabsf(dot_ptx(wi, bt)), ax, ay) *
+              p_smith_aniso(dot_ptx(n, wo), fabsf(dot_ptx(wo, tg)), fabsf(dot_ptx(wo, bt)), ax, ay));
+    }
+    float k = (1.f - m->metallic) * (1.f - m->specular_transmission);
+    for (int i = 0; i < 3; i++) {
+        float tint  = lum > 0.f ? m->base_color[i] * (1.f / lum) : 1.f;
+        float sheen = p_lerp(1.f, tint, m->sheen_tint) * (fh * m->sheen);
+        float gloss = p_lerp(spec[i], 1.f, fh) * dg;
+        out[i]      = (m->base_color[i] * dif + sheen) * k + gloss + coat;
+    }
+}
+
+static float p_disney_pdf(const obsdf_t *m, const float n[3], const float wo[3], const float wi[3], const float tg[3],
+                          const float bt[3])
+{
+    float alpha = fmaxf(0.001f, m->roughness * m->roughness), aspect = sqrtf(1.f - m->anisotropy * 0.9f);
+    float ax = fmaxf(0.001f, alpha / aspect), ay = fmaxf(0.001f, alpha * aspect);
+    float dn = dot_ptx(wi, n), diffuse = dn > 0.f ? dn * O_INV_PI : 0.f;
+    float coat = 0.f, micro = 0.f, trans = 0.f, n_comp = 3.f;
+    if (p_same_hemi(wo, wi, n)) {
+        float h[3];
+        p_half(wi, wo, h);
+        float c = dot_ptx(n, h), oh = dot_ptx(wo, h);
+        coat = p_gtr1(c, p_lerp(0.1f, 0.001f, m->clearcoat_gloss)) * c / (4.f * oh);
+        if (m->anisotropy == 0.f)
+            micro = p_gtr2(c, alpha) * c / (4.f * oh);
+        else
+            micro = p_gtr2_aniso(c, fabsf(dot_ptx(h, tg)), fabsf(dot_ptx(h, bt)), ax, ay) * c / (4.f * oh);
+    }
+    if (m->specular_transmission > 0.f) {
+        n_comp = 4.f;
+        if (!p_same_hemi(wo, wi, n)) {
+            int entering = dot_ptx(wo, n) > 0.f;
+            float eta_o = entering ? 1.f : m->ior, eta_i = entering ? m->ior : 1.f, h[3];
+            p_transmission_half(wo, wi, eta_i, eta_o, h);
+            float c = fabsf(dot_ptx(n, h)), ih = dot_ptx(wi, h), oh = dot_ptx(wo, h);
+            trans = p_gtr2(c, alpha) * c * fabsf(oh * p_sqr(eta_o) / p_sqr(eta_o * oh + eta_i * ih));
+        }
+    }
+    return (diffuse + micro + trans + coat) / n_comp;
+}
+
+static void p_spherical(float sin_t, float cos_t, float phi, float out[3])
+{
+    out[0] = sin_t * cosf(phi), out[1] = sin_t * sinf(phi), out[2] = cos_t;
+}
+
+/* disney_sample_eval (material.cuh:517-592) */
+static void p_disney_sample_eval(const obsdf_t *m, const float n[3], const float wo[3], const float tg[3], const float bt[3],
+                                 uint32_t *rng, float wi[3], float *pdf, float f[3])
+{
+    float sx = onbvh_lcg_randomf(rng), sy = onbvh_lcg_randomf(rng);
+    f[0] = f[1] = f[2] = 0.f;
+    if (!(m->specular_transmission < 1.f)) { /* dielectric_sample_eval (material.cuh:473-512) */
+        float eta = 1.f / m->ior, ci = dot_ptx(n, wo), F, bs = 0.f;
+        float s2t = p_sqr(eta) * (1.f - ci * ci);
+        if (s2t > 1.f) {
+            F = 1.f;
+        } else {
+            float ln = sqrtf(1.f - s2t), e = 1.f / eta;
+            float r1 = (ci - e * ln) / (ci + e * ln), r2 = (ln - e * ci) / (ln + e * ci);
+            F = 0.5f * (p_sqr(r1) + p_sqr(r2));
+        }
+        wi[0] = wi[1] = wi[2] = 0.f;
+        if (sy < F) {
+            float mwo[3] = {-wo[0], -wo[1], -wo[2]};
+            p_reflect(mwo, n, wi);
+            if (dot_ptx(wi, n) > 0.f)
+                bs = F;
+        } else {
+            float s2i = fmaxf(0.f, 1.f - ci * ci), s2 = eta * eta * s2i;
+            if (s2 < 1.f) {
+                float ct = sqrtf(1.f - s2), k = eta * ci - ct;
+                for (int i = 0; i < 3; i++)
+                    wi[i] = eta * -wo[i] + k * n[i];
+                bs = 1.f - F;
+            }
+        }
+        *pdf = 1.f;
+        float inv = 1.f / fabsf(dot_ptx(n, wi));
+        f[0] = f[1] = f[2] = bs * inv;
+        return;
+    }
+    int component = (int)(onbvh_lcg_randomf(rng) * 3.f);
+    component     = component < 0 ? 0 : component > 2 ? 2 : component;
+    if (component == 0) {
+        s_lambertian_dir(n, tg, bt, sx, sy, wi);
+    } else {
+        float hl[3], hn[3], h[3], mwo[3] = {-wo[0], -wo[1], -wo[2]};
+        if (component == 1) {
+            float alpha = fmaxf(0.001f, m->roughness * m->roughness);
+            if (m->anisotropy == 0.f) {
+                float c2 = (1.f - sy) / (1.f + (alpha * alpha - 1.f) * sy);
+                p_spherical(1.f - c2, sqrtf(c2), 2.f * O_PI * sx, hl);
+                s_normalize(hl, hn);
+                p_to_world(hn, tg, bt, n, h);
+            } else {
+                float aspect = sqrtf(1.f - m->anisotropy * 0.9f);
+                float ax = fmaxf(0.001f, alpha / aspect), ay = fmaxf(0.001f, alpha * aspect);
+                float x = 2.f * O_PI * sx, r = sqrtf(sy / (1.f - sy)), cx = ax * cosf(x), cy = ay * sinf(x);
+                for (int i = 0; i < 3; i++)
+                    hl[i] = r * (cx * tg[i] + cy * bt[i]) + n[i];
+                s_normalize(hl, h);
+            }
+        } else {
+            float alpha = p_lerp(0.1f, 0.001f, m->clearcoat_gloss), a2 = alpha * alpha;
+            float c2    = (1.f - powf(a2, 1.f - sy)) / (1.f - a2);
+            p_spherical(1.f - c2, sqrtf(c2), 2.f * O_PI * sx, hl);
+            s_normalize(hl, hn);
+            p_to_world(hn, tg, bt, n, h);
+        }
+        p_reflect(mwo, h, wi);
+        if (!p_same_hemi(wo, wi, n)) {
+            *pdf  = 0.f;
+            wi[0] = wi[1] = wi[2] = 0.f;
+            return;
+        }
+    }
+    *pdf = p_disney_pdf(m, n, wo, wi, tg, bt);
+    p_disney_eval(m, n, wo, wi, tg, bt, f);
+}
+
+/* float4 texture, cudaFilterModeLinear + cudaAddressModeClamp + normalized coordinates */
+static void p_tex2d_f32_clamp(const float *px, uint32_t w, uint32_t h, float u, float v, float out[4])
+{
+    float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float a = floorf((x - fx) * 256.f + 0.5f) / 256.f, b = floorf((y - fy) * 256.f + 0.5f) / 256.f;
+    int i0 = (int)fx, j0 = (int)fy, i1 = i0 + 1, j1 = j0 + 1;
+#define CLAMPI(i, n) ((i) < 0 ? 0 : (i) >= (int)(n) ? (int)(n) - 1 : (i))
+    i0 = CLAMPI(i0, w), i1 = CLAMPI(i1, w), j0 = CLAMPI(j0, h), j1 = CLAMPI(j1, h);
+#undef CLAMPI
+    for (int ch = 0; ch < 4; ch++) {
+        float t00 = px[4 * ((size_t)j0 * w + i0) + ch], t10 = px[4 * ((size_t)j0 * w + i1) + ch];
+        float t01 = px[4 * ((size_t)j1 * w + i0) + ch], t11 = px[4 * ((size_t)j1 * w + i1) + ch];
+        out[ch]   = (1.f - a) * (1.f - b) * t00 + a * (1.f - b) * t10 + (1.f - a) * b * t01 + a * b * t11;
+    }
+}
+
+static void p_background(const opath_t *pc, const float d[3], float out[3])
+{
+    out[0] = out[1] = out[2] = 0.f;
+    if (!pc->envmap_eval)
+        return;
+    if (pc->skylike_background) {
+        float a = 0.5f * (d[1] + 1.f);
+        out[0] = (1.f - a) * 1.f + a * 0.5f, out[1] = (1.f - a) * 1.f + a * 0.7f, out[2] = (1.f - a) * 1.f + a * 1.f;
+        return;
+    }
+    float ang = pc->envmap_rotation_deg * 0.01745329251994329576923690768489f, c = cosf(ang), s = sinf(ang);
+    float rx = c * d[0] + s * d[2], rz = c * d[2] - s * d[0];
+    float eu = atan2f(rx, -rz) * O_INV_PI * 0.5f + 0.5f, ev = acosf(fminf(fmaxf(d[1], -1.f), 1.f)) * O_INV_PI;
+    float val[4] = {1.f, 1.f, 1.f, 1.f};
+    if (pc->envmap)
+        p_tex2d_f32_clamp(pc->envmap, pc->env_w, pc->env_h, eu, ev, val);
+    for (int i = 0; i < 3; i++)
+        out[i] = fminf(100.f, val[i] * pc->envmap_strength);
+}
+
+static void path_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const opath_t *pc,
+                     uint32_t pixel, int sample_idx, int rnd_offset, int mlp_mode, float radiance[3], ohit_t *primary,
+                     uint64_t *cnt)
+{
+    float o[3], d[3], thr[3] = {1.f, 1.f, 1.f}, ill[3] = {0.f, 0.f, 0.f};
+    uint32_t rng;
+    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, &rng);
+    for (uint32_t depth = 1;; depth++) {
+        ohit_t hit;
+        uint32_t lod = (pc->path_lod_switch && pc->num_lods_learned > 0 && depth > 1) ? pc->lod_switch : c->rendered_lod;
+        trace_ray(s, nbvh, c, net, o, d, depth, lod, mlp_mode, &hit, cnt);
+        cnt[4]++;
+        if (depth == 1 && primary)
+            *primary = hit;
+        if (hit.valid_hit == 0 || depth == pc->max_depth) {
+            if (hit.valid_hit == 0) {
+                float bg[3];
+                p_background(pc, d, bg);
+                for (int i = 0; i < 3; i++)
+                    ill[i] += thr[i] * bg[i];
+            }
+            break;
+        }
+        obsdf_t bsdf;
+        p_default_bsdf(&bsdf);
+        float wo[3] = {-d[0], -d[1], -d[2]}, its_n[3], pos[3];
+        if (hit.valid_hit == 1) {
+            for (int i = 0; i < 3; i++) {
+                bsdf.base_color[i] = hit.albedo_or_ids[i];
+                its_n[i]           = hit.normal_or_uv[i];
+                pos[i]             = o[i] + hit.t * d[i];
+            }
+            bsdf.metallic = pc->neural_metallic, bsdf.roughness = pc->neural_roughness, bsdf.specular = pc->neural_specular;
+        } else {
+            uint32_t mesh, prim;
+            memcpy(&mesh, &hit.albedo_or_ids[0], 4);
+            memcpy(&prim, &hit.albedo_or_ids[1], 4);
+            osampler_t sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.blas          = s->blas[mesh];
+            sp.normals       = pc->attr[mesh].normals;
+            sp.texcoords     = pc->attr[mesh].texcoords;
+            sp.material_ids  = pc->attr[mesh].material_ids;
+            sp.material_map  = pc->attr[mesh].material_map;
+            sp.num_materials = pc->attr[mesh].material_map ? pc->attr[mesh].num_materials : 0;
+            sp.materials     = pc->materials;
+            sp.textures      = pc->textures;
+            oits_t its;
+            s_compute_its(&sp, prim, hit.normal_or_uv[0], hit.normal_or_uv[1], &its);
+            memcpy(pos, its.position, 12);
+            memcpy(its_n, its.sh_normal, 12);
+            int has_mat = its.material_id != -1 && pc->materials;
+            if (c->ignore_neural_blas && mesh == pc->neural_bvh_idx) {
+                if (has_mat)
+                    p_color(pc->materials[its.material_id].base_color, its.uv, pc->textures, bsdf.base_color);
+                bsdf.metallic = pc->neural_metallic, bsdf.roughness = pc->neural_roughness, bsdf.specular = pc->neural_specular;
+            } else if (pc->force_constant_material) {
+                if (has_mat)
+                    p_color(pc->materials[its.material_id].base_color, its.uv, pc->textures, bsdf.base_color);
+                bsdf.metallic = pc->constant_metallic, bsdf.roughness = pc->constant_roughness, bsdf.specular = pc->constant_specular;
+            } else if (has_mat) {
+                p_unpack_material(&pc->materials[its.material_id], its.uv, pc->textures, &bsdf);
+            }
+        }
+        float shn[3], tg[3], bt[3];
+        int flip = dot_ptx(wo, its_n) < 0.f; /* shading_frame */
+        for (int i = 0; i < 3; i++)
+            shn[i] = flip ? -its_n[i] : its_n[i];
+        s_ortho_basis(tg, bt, shn);
+        if ((depth == 1 || pc->emission_eval) && !(bsdf.base_emission[0] == 0.f && bsdf.base_emission[1] == 0.f && bsdf.base_emission[2] == 0.f))
+            for (int i = 0; i < 3; i++)
+                ill[i] += thr[i] * (bsdf.base_emission[i] * bsdf.emission_scale);
+        float wi[3], pdf, f[3];
+        p_disney_sample_eval(&bsdf, shn, wo, tg, bt, &rng, wi, &pdf, f);
+        float cti = fabsf(dot_ptx(wi, shn));
+        for (int i = 0; i < 3; i++)
+            thr[i] *= f[i] * cti / pdf;
+        if (pdf == 0.f || (f[0] == 0.f && f[1] == 0.f && f[2] == 0.f))
+            break;
+        if (pc->apply_russian_roulette && depth >= pc->rr_start_depth) { /* rr_terminate */
+            float survival = fminf(1.f, fmaxf(fmaxf(thr[0], thr[1]), thr[2]));
+            if (onbvh_lcg_randomf(&rng) < survival) {
+                for (int i = 0; i < 3; i++)
+                    thr[i] /= survival;
+            } else {
+                break;
+            }
+        }
+        for (int i = 0; i < 3; i++) {
+            o[i] = pos[i] + shn[i] * pc->normal_epsilon_offset;
+            d[i] = wi[i];
+        }
+    }
+    radiance[0] = ill[0], radiance[1] = ill[1], radiance[2] = ill[2];
+}
+
+void onbvh_render_path(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const opath_t *pc,
+                       uint32_t pixel_begin, uint32_t pixel_end, uint32_t pixel_stride, int sample_idx, int rnd_offset,
+                       int mlp_mode, float *radiance, ohit_t *primary_hits, uint64_t *counters, int n_threads)
+{
+    uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    if (pixel_stride == 0)
+        pixel_stride = 1;
+    const int64_t n = ((int64_t)pixel_end - (int64_t)pixel_begin + pixel_stride - 1) / pixel_stride;
+#ifdef _OPENMP
+    if (n_threads > 0)
+        omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : c0, c1, c2, c3, c4)
+    for (int64_t i = 0; i < n; i++) {
+        uint64_t cnt[5] = {0, 0, 0, 0, 0};
+        path_one(s, nbvh, c, net, pc, pixel_begin + (uint32_t)i * pixel_stride, sample_idx, rnd_offset, mlp_mode,
+                 radiance + 3 * i, primary_hits ? &primary_hits[i] : NULL, cnt);
+        c0 += cnt[0], c1 += cnt[1], c2 += cnt[2], c3 += cnt[3], c4 += cnt[4];
+    }
+    if (counters) {
+        counters[0] = c0, counters[1] = c1, counters[2] = c2, counters[3] = c3, counters[4] = c4;
     }
 }
 

@@ -220,6 +220,37 @@ void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t
                           uint64_t *counters /* [0]=queries [1]=nbvh interior steps [2]=blas interior [3]=tri tests */,
                           int n_threads);
 
+/* --- hybrid neural path tracing, max_depth >= 1 (a15 / f1: shading, BSDF sampling, Russian roulette, re-queue) --- */
+typedef struct {
+    const float *normals, *texcoords;
+    const int32_t *material_ids;
+    const uint32_t *material_map;
+    uint32_t num_materials;
+} oattr_t;
+typedef struct {
+    const oattr_t *attr; /* one per BLAS */
+    const omaterial_t *materials;
+    const otexture_t *textures;
+    uint32_t neural_bvh_idx, max_depth;
+    uint32_t path_lod_switch, lod_switch;
+    int32_t num_lods_learned;
+    /* path_module_const (path_module.h:217-254) */
+    float normal_epsilon_offset;
+    uint32_t apply_russian_roulette, rr_start_depth;
+    float neural_roughness, neural_specular, neural_metallic;
+    /* scene_constants (cuda_backend.h:58-72) */
+    uint32_t force_constant_material, emission_eval;
+    float constant_roughness, constant_specular, constant_metallic;
+    uint32_t envmap_eval, skylike_background;
+    float envmap_rotation_deg, envmap_strength;
+    const float *envmap; /* RGBA32F lat-long map or NULL (white) */
+    uint32_t env_w, env_h;
+} opath_t;
+/* radiance: 3 floats per pixel (the value accumulate_pixel_value receives); counters[4] = rays traced */
+void onbvh_render_path(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const opath_t *pc,
+                       uint32_t pixel_begin, uint32_t pixel_end, uint32_t pixel_stride, int sample_idx, int rnd_offset,
+                       int mlp_mode, float *radiance, ohit_t *primary_hits, uint64_t *counters, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

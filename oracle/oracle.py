@@ -382,6 +382,102 @@ def tex2d(img, u, v):
     return np.array(out[:], dtype=np.float32)
 
 
+# ----------------------------------------------------------------------------- hybrid neural path tracing (a15 / f1)
+class OAttr(C.Structure):
+    _fields_ = [("normals", C.c_void_p), ("texcoords", C.c_void_p), ("material_ids", C.c_void_p), ("material_map", C.c_void_p),
+                ("num_materials", C.c_uint32)]
+
+
+class OPath(C.Structure):
+    _fields_ = [("attr", C.POINTER(OAttr)), ("materials", C.c_void_p), ("textures", C.POINTER(OTexture)),
+                ("neural_bvh_idx", C.c_uint32), ("max_depth", C.c_uint32), ("path_lod_switch", C.c_uint32),
+                ("lod_switch", C.c_uint32), ("num_lods_learned", C.c_int32), ("normal_epsilon_offset", C.c_float),
+                ("apply_russian_roulette", C.c_uint32), ("rr_start_depth", C.c_uint32), ("neural_roughness", C.c_float),
+                ("neural_specular", C.c_float), ("neural_metallic", C.c_float), ("force_constant_material", C.c_uint32),
+                ("emission_eval", C.c_uint32), ("constant_roughness", C.c_float), ("constant_specular", C.c_float),
+                ("constant_metallic", C.c_float), ("envmap_eval", C.c_uint32), ("skylike_background", C.c_uint32),
+                ("envmap_rotation_deg", C.c_float), ("envmap_strength", C.c_float), ("envmap", C.c_void_p),
+                ("env_w", C.c_uint32), ("env_h", C.c_uint32)]
+
+
+class PathSetup:
+    """Shading inputs of the path tracer: per-BLAS attributes (dicts with optional normals / texcoords / material_ids /
+    material_map), PackedMaterial records (96-byte numpy records), RGBA8 textures, an RGBA32F environment map, and the
+    path / scene constants of the config JSON."""
+
+    def __init__(self, cfg, blas_list, materials=None, textures=None, envmap=None, max_depth=None, neural_bvh_idx=0):
+        r = cfg.get("neural_bvh_renderer", {})
+        nm = r.get("neural_module", {})
+        pmc = nm.get("path_module_constants", {})
+        bc = r.get("bvh_constants", {})
+        sc = cfg.get("cuda_scene", {}).get("scene_constants", {})
+        self.keep = []
+        self.attr = (OAttr * len(blas_list))()
+        for i, b in enumerate(blas_list):
+            a = OAttr()
+            for key, dt in (("normals", np.float32), ("texcoords", np.float32), ("material_ids", np.int32), ("material_map", np.uint32)):
+                if b.get(key) is not None and len(b[key]):
+                    arr = np.ascontiguousarray(b[key], dtype=dt)
+                    self.keep.append(arr)
+                    setattr(a, key, arr.ctypes.data)
+            a.num_materials = len(b["material_map"]) if b.get("material_map") is not None else 0
+            self.attr[i] = a
+        p = OPath()
+        p.attr = self.attr
+        if materials is not None and len(materials):
+            m = np.ascontiguousarray(materials)
+            assert m.dtype.itemsize == 96
+            self.keep.append(m)
+            p.materials = m.ctypes.data
+        if textures:
+            self.tex = (OTexture * len(textures))()
+            for k, img in enumerate(textures):
+                img = np.ascontiguousarray(img, dtype=np.uint8)
+                self.keep.append(img)
+                self.tex[k] = OTexture(img.ctypes.data, img.shape[1], img.shape[0])
+            p.textures = self.tex
+        if envmap is not None:
+            e = np.ascontiguousarray(envmap, dtype=np.float32)
+            assert e.ndim == 3 and e.shape[2] == 4
+            self.keep.append(e)
+            p.envmap, p.env_w, p.env_h = e.ctypes.data, e.shape[1], e.shape[0]
+        p.neural_bvh_idx = neural_bvh_idx
+        p.max_depth = int(max_depth if max_depth is not None else nm.get("max_depth", 2))
+        p.path_lod_switch = int(bc.get("path_lod_switch", False))
+        p.lod_switch = int(bc.get("lod_switch", 0))
+        p.num_lods_learned = int(bc.get("num_lods_learned", 0))
+        p.normal_epsilon_offset = pmc.get("normal_epsilon_offset", 1e-4)
+        p.apply_russian_roulette = int(pmc.get("apply_russian_roulette", True))
+        p.rr_start_depth = int(pmc.get("rr_start_depth", 2))
+        p.neural_roughness = pmc.get("neural_roughness", 0.2)
+        p.neural_specular = pmc.get("neural_specular", 0.2)
+        p.neural_metallic = pmc.get("neural_metallic", 0.1)
+        p.force_constant_material = int(sc.get("force_constant_material", False))
+        p.emission_eval = int(sc.get("emission_eval", True))
+        p.constant_roughness = sc.get("constant_roughness", 1.0)
+        p.constant_specular = sc.get("constant_specular", 0.0)
+        p.constant_metallic = sc.get("constant_metallic", 0.0)
+        p.envmap_eval = int(sc.get("envmap_eval", True))
+        p.skylike_background = int(sc.get("skylike_background", False))
+        p.envmap_rotation_deg = sc.get("envmap_rotation", 0.0)
+        p.envmap_strength = sc.get("envmap_strength", 1.0)
+        self.c = p
+
+
+def render_path(scene, nbvh_nodes, const, net, path, pixel_begin, pixel_end, stride=1, sample_idx=0, rnd_offset=0,
+                mlp_mode=0, n_threads=0):
+    """Radiance (n, 3) of one sample per pixel, the primary-hit records and [queries, nbvh steps, blas steps, tri tests, rays]."""
+    nbvh_nodes = np.ascontiguousarray(nbvh_nodes, dtype=NODE_DTYPE)
+    n = (pixel_end - pixel_begin + stride - 1) // stride
+    rad = np.zeros((n, 3), np.float32)
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    cnt = (C.c_uint64 * 5)()
+    lib().onbvh_render_path(C.byref(scene.c), _p(nbvh_nodes), C.byref(const), C.byref(net), C.byref(path.c),
+                            C.c_uint32(pixel_begin), C.c_uint32(pixel_end), C.c_uint32(stride), C.c_int(sample_idx),
+                            C.c_int(rnd_offset), C.c_int(mlp_mode), _p(rad), _p(hits), cnt, C.c_int(n_threads))
+    return rad, hits, [cnt[i] for i in range(5)]
+
+
 # ----------------------------------------------------------------------------- online optimisation
 LOSS_TYPES = ["RelativeL2", "L2", "RelativeL1", "L1", "RelativeL2Luminance", "BinaryCrossEntropy", "LogL2", "LHalf"]
 

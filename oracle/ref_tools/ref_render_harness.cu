@@ -9,6 +9,10 @@
 // render_app.cpp:307-312) are replaced by plain cudaMalloc buffers and cudaArray surfaces.
 //
 // usage: ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames>
+//        ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames> path <spp>
+//          (hybrid neural path tracing with shading: also reads materials.bin, tex<k>.rgba8 + tex<k>.dims, envmap.f32 + envmap.dims,
+//           mesh<i>_{normals.f32,texcoords.f32,material_ids.i32,material_map.u32}; writes path_accum_1spp.f32 / path_accum.f32 =
+//           the RGBA32F accumulation surface after 1 and after <spp> samples)
 //        ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> 0 sampler <batch> <log2_max_traversals> <steps> [max_loss]
 //          (K10: granular_sample_bvh_network_input_data; also reads mesh<i>_{normals.f32,texcoords.f32,material_ids.i32,
 //           material_map.u32}, materials.bin, tex<k>.rgba8 + tex<k>.dims, tree_cut.bin; writes sampler_{in.f32,tgt.f32,nodes.u32})
@@ -451,44 +455,71 @@ int main(int argc, char **argv)
     printf("[ref_render_harness] %ux%u, %zu tree-cut nodes, %zu meshes, neural_bvh_idx %u\n", W, H, nb_nodes.size(), meshes.size(),
            c_renderer.neural_bvh_idx);
 
+    // materials (raw PackedMaterial bytes; the vtable slot is never read on the device) and RGBA8 textures
+    std::vector<uint8_t> mats;
+    if (slurp(wd + "/materials.bin", mats) && !mats.empty()) {
+        if (mats.size() % sizeof(PackedMaterial)) {
+            fprintf(stderr, "materials.bin: %zu bytes is not a multiple of sizeof(PackedMaterial)=%zu\n", mats.size(), sizeof(PackedMaterial));
+            return 4;
+        }
+        scene.materials = (PackedMaterial *)upload(mats);
+    }
+    std::vector<cudaTextureObject_t> texs;
+    for (int k = 0;; k++) {
+        std::vector<uint8_t> px;
+        std::vector<uint32_t> dims;
+        if (!slurp(wd + "/tex" + std::to_string(k) + ".rgba8", px) || !slurp(wd + "/tex" + std::to_string(k) + ".dims", dims))
+            break;
+        const uint32_t tw = dims[0], th = dims[1];
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr;
+        CK(cudaMallocArray(&arr, &cd, tw, th));
+        CK(cudaMemcpy2DToArray(arr, 0, 0, px.data(), tw * 4, tw * 4, th, cudaMemcpyHostToDevice));
+        cudaResourceDesc trd = {};
+        trd.resType          = cudaResourceTypeArray;
+        trd.res.array.array  = arr;
+        cudaTextureDesc td   = {}; // CudaBackend::create_cuda_textures_buffer (cuda_backend.cpp:421-432)
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+        td.filterMode = cudaFilterModeLinear, td.readMode = cudaReadModeNormalizedFloat, td.normalizedCoords = 1;
+        td.maxAnisotropy = 1, td.maxMipmapLevelClamp = 99, td.minMipmapLevelClamp = 0, td.mipmapFilterMode = cudaFilterModePoint;
+        td.borderColor[0] = 1.0f, td.sRGB = 0;
+        cudaTextureObject_t t;
+        CK(cudaCreateTextureObject(&t, &trd, &td, nullptr));
+        texs.push_back(t);
+    }
+    if (!texs.empty())
+        scene.textures = upload(texs);
+
+    // ---- environment map == CudaBackend::load_envmap_texture (cuda_backend.cpp:444-500); absent file -> the reference's white image
+    {
+        std::vector<float> env;
+        std::vector<uint32_t> dims;
+        int ew = 1, eh = 1;
+        if (slurp(wd + "/envmap.f32", env) && slurp(wd + "/envmap.dims", dims) && dims.size() == 2 && env.size() == (size_t)dims[0] * dims[1] * 4) {
+            ew = (int)dims[0], eh = (int)dims[1];
+        } else {
+            env.assign(4, 1.f);
+        }
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc(32, 32, 32, 32, cudaChannelFormatKindFloat);
+        cudaArray_t arr;
+        CK(cudaMallocArray(&arr, &cd, ew, eh));
+        CK(cudaMemcpy2DToArray(arr, 0, 0, env.data(), (size_t)ew * 16, (size_t)ew * 16, eh, cudaMemcpyHostToDevice));
+        cudaResourceDesc erd = {};
+        erd.resType          = cudaResourceTypeArray;
+        erd.res.array.array  = arr;
+        cudaTextureDesc etd  = {};
+        etd.filterMode = cudaFilterModeLinear, etd.normalizedCoords = true;
+        etd.addressMode[0] = etd.addressMode[1] = cudaAddressModeClamp;
+        cudaTextureObject_t et;
+        CK(cudaCreateTextureObject(&et, &erd, &etd, nullptr));
+        CK(cudaMemcpyToSymbol(envmap_texture, &et, sizeof(et)));
+        printf("[ref_render_harness] envmap %dx%d\n", ew, eh);
+    }
+
     // ---- sampler mode: the reference's training-sample generator (K10) for a few steps
     if (argc >= 11 && std::string(argv[7]) == "sampler") {
         const uint32_t batch = atoi(argv[8]), log2_trav = atoi(argv[9]), steps = atoi(argv[10]);
         const float max_loss = argc >= 12 ? (float)atof(argv[11]) : 1.f;
-        // materials (raw PackedMaterial bytes; the vtable slot is never read on the device) and RGBA8 textures
-        std::vector<uint8_t> mats;
-        if (slurp(wd + "/materials.bin", mats) && !mats.empty()) {
-            if (mats.size() % sizeof(PackedMaterial)) {
-                fprintf(stderr, "materials.bin: %zu bytes is not a multiple of sizeof(PackedMaterial)=%zu\n", mats.size(), sizeof(PackedMaterial));
-                return 4;
-            }
-            scene.materials = (PackedMaterial *)upload(mats);
-        }
-        std::vector<cudaTextureObject_t> texs;
-        for (int k = 0;; k++) {
-            std::vector<uint8_t> px;
-            std::vector<uint32_t> dims;
-            if (!slurp(wd + "/tex" + std::to_string(k) + ".rgba8", px) || !slurp(wd + "/tex" + std::to_string(k) + ".dims", dims))
-                break;
-            const uint32_t tw = dims[0], th = dims[1];
-            cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
-            cudaArray_t arr;
-            CK(cudaMallocArray(&arr, &cd, tw, th));
-            CK(cudaMemcpy2DToArray(arr, 0, 0, px.data(), tw * 4, tw * 4, th, cudaMemcpyHostToDevice));
-            cudaResourceDesc trd = {};
-            trd.resType          = cudaResourceTypeArray;
-            trd.res.array.array  = arr;
-            cudaTextureDesc td   = {}; // CudaBackend::create_cuda_textures_buffer (cuda_backend.cpp:421-432)
-            td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
-            td.filterMode = cudaFilterModeLinear, td.readMode = cudaReadModeNormalizedFloat, td.normalizedCoords = 1;
-            td.maxAnisotropy = 1, td.maxMipmapLevelClamp = 99, td.minMipmapLevelClamp = 0, td.mipmapFilterMode = cudaFilterModePoint;
-            td.borderColor[0] = 1.0f, td.sRGB = 0;
-            cudaTextureObject_t t;
-            CK(cudaCreateTextureObject(&t, &trd, &td, nullptr));
-            texs.push_back(t);
-        }
-        if (!texs.empty())
-            scene.textures = upload(texs);
         std::vector<NeuralTreeCutData> cut;
         if (!slurp(wd + "/tree_cut.bin", cut) || cut.size() != nb_nodes.size()) {
             fprintf(stderr, "tree_cut.bin: %zu entries, tree-cut has %zu nodes\n", cut.size(), nb_nodes.size());
@@ -556,9 +587,11 @@ int main(int argc, char **argv)
     const uint32_t in_dims = c_module.input_network_dims, out_dims = c_pt.output_network_dims;
     Buffers b = make_buffers(n_pix, in_dims, out_dims);
 
-    // ---- parity hooks
+    // ---- parity hooks (skipped in path mode: image goldens and timings only)
+    const bool path_mode  = argc >= 9 && std::string(argv[7]) == "path";
     const uint32_t blocks = (n_pix + 255) / 256;
     float *d_rays = dalloc<float>((size_t)n_pix * 6);
+    if (!path_mode) {
     hk_raygen<<<blocks, 256>>>(n_pix, 0, 0, d_rays);
     CK(cudaDeviceSynchronize());
     dump(wd + "/rays.f32", download(d_rays, (size_t)n_pix * 6));
@@ -580,16 +613,20 @@ int main(int argc, char **argv)
         dump(wd + "/blas_hit.bin", download(bh, n_pix));
         cudaFree(bh);
     }
+    }
 
     // ---- one recorded frame (sample 0), then timed frames
     HitRec *d_hits = dalloc<HitRec>(n_pix);
     std::vector<float> s0in, s0out;
     std::vector<uint32_t> s0px;
-    FrameStats st = reference_frame(b, net, nbvh, scene, n_pix, 0, 0, max_depth, in_dims, out_dims, d_hits, &s0in, &s0out, &s0px);
-    dump(wd + "/hits.bin", download(d_hits, n_pix));
-    dump(wd + "/step0_in.f32", s0in);
-    dump(wd + "/step0_out.f32", s0out);
-    dump(wd + "/step0_pixel.u32", s0px);
+    FrameStats st = path_mode ? reference_frame(b, net, nbvh, scene, n_pix, 0, 0, max_depth, in_dims, out_dims, nullptr, nullptr, nullptr, nullptr)
+                              : reference_frame(b, net, nbvh, scene, n_pix, 0, 0, max_depth, in_dims, out_dims, d_hits, &s0in, &s0out, &s0px);
+    if (!path_mode) {
+        dump(wd + "/hits.bin", download(d_hits, n_pix));
+        dump(wd + "/step0_in.f32", s0in);
+        dump(wd + "/step0_out.f32", s0out);
+        dump(wd + "/step0_pixel.u32", s0px);
+    }
     {
         std::vector<uchar4> ldr((size_t)n_pix);
         CK(cudaMemcpy2DFromArray(ldr.data(), W * 4, arr_ldr, 0, 0, W * 4, H, cudaMemcpyDeviceToHost));
@@ -598,6 +635,20 @@ int main(int argc, char **argv)
     printf("[ref_render_harness] frame: %llu queries, %llu neural steps, %llu tlas steps, %llu launches, %llu host syncs\n",
            (unsigned long long)st.queries, (unsigned long long)st.neural_steps, (unsigned long long)st.tlas_steps,
            (unsigned long long)st.launches, (unsigned long long)st.host_syncs);
+
+    // ---- path mode: accumulate `spp` samples through the reference's frame loop and dump the RGBA32F accumulation buffer
+    if (path_mode) {
+        const int spp = atoi(argv[8]);
+        std::vector<float4> acc((size_t)n_pix);
+        CK(cudaMemcpy2DFromArray(acc.data(), W * 16, arr_acc, 0, 0, W * 16, H, cudaMemcpyDeviceToHost));
+        dump(wd + "/path_accum_1spp.f32", acc);
+        unsigned long long q = st.queries;
+        for (int sidx = 1; sidx < spp; sidx++)
+            q += reference_frame(b, net, nbvh, scene, n_pix, sidx, 0, max_depth, in_dims, out_dims, nullptr, nullptr, nullptr, nullptr).queries;
+        CK(cudaMemcpy2DFromArray(acc.data(), W * 16, arr_acc, 0, 0, W * 16, H, cudaMemcpyDeviceToHost));
+        dump(wd + "/path_accum.f32", acc);
+        printf("[ref_render_harness] path: %d spp accumulated, %llu queries\n", spp, q);
+    }
 
     float best_ms = 1e30f, sum_ms = 0.f;
     cudaEvent_t e0, e1;
