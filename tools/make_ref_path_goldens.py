@@ -6,7 +6,7 @@ hybrid_scatter_and_get_next_tlas_traversal_step (material unpack, Disney BSDF sa
 map), its host loop NeuralPathModule::neural_path_tracing and tiny-cuda-nn inference, on the shipped Chess scene / config /
 tree-cut / weights / HDRI with the chessboard's own glTF material and textures:
 
-  * 256x144, shipped max_depth 3 -> tests/golden/ref_chess_path_256x144.npz  (RGB radiance after 1 and after 16 spp)
+  * 256x144, shipped max_depth 3 -> tests/golden/ref_chess_path_256x144.npz  (RGB radiance after 1, 16 and 256 spp)
   * 1920x1080 max_depth 3 (BASELINE config 2b) and 3840x2160 max_depth 4 (config 4) -> tests/golden/ref_chess_path_timing.json
 
 Outputs land in gpurun_out/ref_golden/; copy the two files to tests/golden/ and commit."""
@@ -22,6 +22,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tools"))
 OUT = os.path.join(REPO, "gpurun_out", "ref_golden")
 SPP = 16
+SPP_CONVERGED = 256
 
 
 def stage_shading(root, wd, blas):
@@ -68,8 +69,11 @@ def main():
     info = run(R.HARNESS, wd, W, H, 3, log2_hashmap, 3, SPP)
     a1 = np.fromfile(os.path.join(wd, "path_accum_1spp.f32"), dtype="<f4").reshape(H, W, 4)
     an = np.fromfile(os.path.join(wd, "path_accum.f32"), dtype="<f4").reshape(H, W, 4)
-    np.savez_compressed(os.path.join(OUT, "ref_chess_path_256x144.npz"), W=W, H=H, max_depth=3, spp=SPP,
-                        rgb_1spp=a1[..., :3].copy(), rgb_nspp=(an[..., :3] / SPP).astype(np.float32), queries_1spp=info["queries"])
+    run(R.HARNESS, wd, W, H, 3, log2_hashmap, 1, SPP_CONVERGED)
+    ac = np.fromfile(os.path.join(wd, "path_accum.f32"), dtype="<f4").reshape(H, W, 4)
+    np.savez_compressed(os.path.join(OUT, "ref_chess_path_256x144.npz"), W=W, H=H, max_depth=3, spp=SPP, spp_converged=SPP_CONVERGED,
+                        rgb_1spp=a1[..., :3].copy(), rgb_nspp=(an[..., :3] / SPP).astype(np.float32),
+                        rgb_converged=(ac[..., :3] / SPP_CONVERGED).astype(np.float32), queries_1spp=info["queries"])
     print("[path goldens] 256x144: mean radiance 1spp %.5f, %dspp %.5f" % (a1[..., :3].mean(), SPP, an[..., :3].mean() / SPP))
 
     timing = {"gpu": gpu}

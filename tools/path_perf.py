@@ -31,8 +31,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         c = mod.counters()
-        rays = c[0] / iters
-        out[name] = {"ms_per_frame": ms, "pixels": W * H, "rays_per_frame": rays, "queries_per_frame": c[1] / iters,
+        rays = c["rays"] / iters
+        out[name] = {"ms_per_frame": ms, "pixels": W * H, "rays_per_frame": rays, "queries_per_frame": c["queries"] / iters,
                      "Mrays_s_all_rays": rays / ms / 1e3, "Mpixels_s": W * H / ms / 1e3}
         print(name, json.dumps(out[name]), flush=True)
         mod.close()
