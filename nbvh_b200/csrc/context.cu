@@ -251,8 +251,8 @@ struct nbvh_ctx {
     cudaTextureObject_t envmap = 0;                                        // envmap_texture (cuda_backend_constants.cuh); 0 = white
 
     // multi-bounce path state (max_depth > 1): one PathState + PathHit per pixel, 2 queue counters per bounce
-    PathState *d_paths = nullptr;
-    PathHit *d_path_hits = nullptr;
+    PathState *d_paths[2] = {nullptr, nullptr}; // ping-pong path lists (survivors are compacted at every bounce)
+    PathHit *d_path_hits[2] = {nullptr, nullptr};
     size_t path_capacity = 0;
     uint32_t *d_bounce_counters = nullptr;
 
@@ -586,8 +586,8 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     cudaFree(ctx->d_queue);
-    cudaFree(ctx->d_paths);
-    cudaFree(ctx->d_path_hits);
+    for (int k = 0; k < 2; k++)
+        cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
     cudaFree(ctx->d_bounce_counters);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->own_grads);
@@ -1486,16 +1486,19 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
     if (ctx->max_depth > 1) {
         // hybrid neural path tracing (path.cu): shading + re-queue per bounce, no host synchronisation
         if (ctx->path_capacity < (size_t)total) {
-            cudaFree(ctx->d_paths), cudaFree(ctx->d_path_hits);
-            ctx->d_paths = nullptr, ctx->d_path_hits = nullptr, ctx->path_capacity = 0;
-            CU_TRY(ctx, cudaMalloc(&ctx->d_paths, (size_t)total * sizeof(PathState)));
-            CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits, (size_t)total * sizeof(PathHit)));
+            ctx->path_capacity = 0;
+            for (int k = 0; k < 2; k++) {
+                cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
+                ctx->d_paths[k] = nullptr, ctx->d_path_hits[k] = nullptr;
+                CU_TRY(ctx, cudaMalloc(&ctx->d_paths[k], (size_t)total * sizeof(PathState)));
+                CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits[k], (size_t)total * sizeof(PathHit)));
+            }
             ctx->path_capacity = total;
         }
+        const size_t counter_bytes = kPathCountersPerDepth * (kMaxPathDepth + 1) * sizeof(uint32_t);
         if (!ctx->d_bounce_counters)
-            CU_TRY(ctx, cudaMalloc(&ctx->d_bounce_counters, 2u * (kMaxPathDepth + 1) * sizeof(uint32_t)));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_bounce_counters, 0, 2u * (kMaxPathDepth + 1) * sizeof(uint32_t), st));
-        rp.paths = ctx->d_paths, rp.path_hits = ctx->d_path_hits;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_bounce_counters, counter_bytes));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_bounce_counters, 0, counter_bytes, st));
         PathConst pc;
         memset(&pc, 0, sizeof(pc));
         for (size_t i = 0; i < ctx->blas_desc.size() && i < (size_t)kMaxBlas; i++) {
@@ -1523,7 +1526,7 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
         NbvhConst nbvh_bounce = rp.nbvh;
         if (ctx->bvh_const.path_lod_switch && ctx->bvh_const.num_lods_learned > 0)
             nbvh_bounce.leaf_lod_max = 2u + (uint32_t)ctx->bvh_const.lod_switch;
-        CU_TRY(ctx, launch_render_path(rp, pc, nc, nbvh_bounce, ctx->d_bounce_counters, ctx->num_sms, st));
+        CU_TRY(ctx, launch_render_path(rp, pc, nc, nbvh_bounce, ctx->d_paths, ctx->d_path_hits, ctx->d_bounce_counters, ctx->num_sms, st));
     } else if (ctx->mega_kernel) {
         CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
     } else if (3u * (ctx->stage_used + 1u) <= ctx->stage_ev.size()) {

@@ -4,21 +4,22 @@
 // hybrid_scatter_and_get_next_tlas_traversal_step (K9: shading, BSDF sampling, Russian roulette, re-queue)
 // (/root/reference/src/cuda/neural/path/path_inference_kernels.cu:195-429).
 //
-// Per frame:   k_path_bounce<first>  ->  k_neural<path>  ->  k_path_bounce  ->  k_neural<path>  ->  ...  ->  k_path_bounce(last)
+// Per depth d = 1 .. max_depth:   k_path_trace  ->  k_neural<path>  ->  k_path_shade
 //
-//   k_path_bounce   one thread per pixel slot.  Except in the first launch (camera rays) it first SHADES the closest hit that the
-//                   previous trace + k_neural left in path_hits[slot]: background for escaped rays, last-bounce splat,
-//                   intersection data and material of classical hits (texture fetches), the network's normal/albedo with the
-//                   module's constant metallic/roughness/specular for neural hits, emission, Disney BSDF sampling, throughput
-//                   update, Russian roulette, and the bounce ray.  It then TRACES the new ray exactly like k_primary does for
-//                   camera rays: whole TLAS walk with every classical BLAS closest hit, N-BVH walk to the first leaf interval,
-//                   ballot-compacted append to the neural ray queue.  Rays that need no network query leave their hit in
-//                   path_hits[slot] directly.
-//   k_neural<true>  the persistent tcgen05 tile kernel of render.cu; queue entries name path slots, rays come from the path
-//                   state, the closest hit goes to path_hits[slot].
+//   k_path_trace    one thread per path of the current list (depth 1: per pixel, camera rays): whole TLAS walk with every
+//                   classical BLAS closest hit, N-BVH walk to the first leaf interval, ballot-compacted append to the neural
+//                   ray queue -- exactly what k_primary does.  Rays that need no network query leave their hit in path_hits.
+//   k_neural<true>  the persistent tcgen05 tile kernel of render.cu; queue entries name list indices, rays come from the path
+//                   state, the closest hit goes to path_hits.
+//   k_path_shade    one thread per path: background for escaped rays, last-bounce splat, intersection data and material of
+//                   classical hits (texture fetches), the network's normal/albedo with the module's constant
+//                   metallic/roughness/specular for neural hits, emission, Disney BSDF sampling, throughput update, Russian
+//                   roulette, and the bounce ray.  Survivors are COMPACTED into the next path list (one atomic per warp), so
+//                   every later kernel runs on dense warps although most paths die early (Chess: 42 % of the camera rays
+//                   escape, and only 25 % of the pixels still carry a path at depth 3).
 //
-// No host synchronisation and no ray-state ping-pong: 1 + 2 * max_depth launches per frame (the reference: ~125 launches and
-// ~22 host round trips per bounce).  The reference interleaves BLAS visits in TLAS order over several wavefront iterations;
+// No host synchronisation: 3 * max_depth launches per frame, list lengths stay on the device (the reference: ~180 launches
+// and ~30 host round trips per bounce).  The reference interleaves BLAS visits in TLAS order over several wavefront iterations;
 // the closest hit is the minimum over the same candidate set, so the paths are the same (see render.cu's header).
 // Random numbers are drawn in the reference's order (2 camera jitter, 3 per BSDF sample, 1 per roulette), so every pixel
 // follows the same path as in the reference up to floating-point rounding of the shading arithmetic.
@@ -94,44 +95,82 @@ __device__ __forceinline__ bool shade_and_scatter(const RenderParams &p, const P
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ k_path_shade
+// One thread per path of the current (compacted) list: shades the closest hit, splats finished paths, and appends the
+// survivors -- with their bounce ray -- to the next list (warp ballot/prefix-sum compaction, one atomic per warp), so
+// that the following trace and network kernels run on dense warps.
+__global__ void __launch_bounds__(256)
+k_path_shade(const __grid_constant__ RenderParams p, const __grid_constant__ PathConst pc, const __grid_constant__ PathIo io)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_in = io.count_in ? *io.count_in : p.pixel_count;
+    if (i - lane >= n_in)
+        return; // whole warp beyond the list
+    bool alive = false;
+    PathState st;
+    if (i < n_in) {
+        st = io.in[i];
+        const PathHit ph = io.hits_in[i];
+        uint32_t rng = st.s3.x, depth = st.s3.y;
+        const uint32_t pixel = st.s3.z;
+        Ray ray;
+        ray.ox = st.s0.x, ray.oy = st.s0.y, ray.oz = st.s0.z, ray.dx = st.s0.w, ray.dy = st.s1.x, ray.dz = st.s1.y;
+        V3 throughput = v3(st.s1.z, st.s1.w, st.s2.x), illumination = v3(st.s2.y, st.s2.z, st.s2.w);
+        alive = shade_and_scatter(p, pc, pixel, ray, depth, ph, throughput, illumination, rng);
+        if (alive) {
+            st.s0 = make_float4(ray.ox, ray.oy, ray.oz, ray.dx);
+            st.s1 = make_float4(ray.dy, ray.dz, throughput.x, throughput.y);
+            st.s2 = make_float4(throughput.z, illumination.x, illumination.y, illumination.z);
+            st.s3 = make_uint4(rng, depth + 1u, pixel, 0u);
+        }
+    }
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, alive);
+    if (mask) {
+        uint32_t base = 0;
+        if (lane == (uint32_t)(__ffs(mask) - 1))
+            base = atomicAdd(io.count_out, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+        if (alive)
+            io.out[base + __popc(mask & ((1u << lane) - 1u))] = st;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ k_path_trace
+// One thread per path of the list (kFirst: per pixel, camera rays): TLAS walk + classical BLAS closest hits + first
+// N-BVH interval, exactly like k_primary; rays with a pending interval go to the neural ray queue (entry id = list index),
+// all others leave their closest hit in path_hits.
 template <bool kFirst>
 __global__ void __launch_bounds__(256)
-k_path_bounce(const __grid_constant__ RenderParams p, const __grid_constant__ PathConst pc)
+k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ PathIo io)
 {
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t sidx  = chunk * 32u + lane;
-    bool active          = sidx < p.pixel_count;
+    const uint32_t n_in  = kFirst ? p.pixel_count : *io.count_in;
+    if (chunk * 32u >= n_in)
+        return;
+    const bool active = sidx < n_in;
     uint32_t cnt_blas = 0, cnt_tri = 0, cnt_nbvh = 0;
-    uint32_t pixel = 0, rng = 0, depth = 0;
+    uint32_t pixel = 0;
     Ray ray;
-    V3 throughput = splat3(1.f), illumination = splat3(0.f);
     if (active) {
         if constexpr (kFirst) {
+            uint32_t rng;
             pixel = swizzle_pixel(p, p.first_pixel + sidx);
             ray   = camera_ray(p.cam, pixel, p.sample_idx, p.sample_offset, rng);
-            depth = 1u;
+            PathState st;
+            st.s0 = make_float4(ray.ox, ray.oy, ray.oz, ray.dx);
+            st.s1 = make_float4(ray.dy, ray.dz, 1.f, 1.f);
+            st.s2 = make_float4(1.f, 0.f, 0.f, 0.f);
+            st.s3 = make_uint4(rng, 1u, pixel, 0u);
+            p.paths[sidx] = st;
         } else {
-            const PathState st = p.paths[sidx];
-            depth = st.s3.y;
-            if (depth == 0u) {
-                active = false;
-            } else {
-                rng = st.s3.x, pixel = st.s3.z;
-                ray.ox = st.s0.x, ray.oy = st.s0.y, ray.oz = st.s0.z, ray.dx = st.s0.w, ray.dy = st.s1.x, ray.dz = st.s1.y;
-                throughput   = v3(st.s1.z, st.s1.w, st.s2.x);
-                illumination = v3(st.s2.y, st.s2.z, st.s2.w);
-                const PathHit ph = p.path_hits[sidx];
-                if (shade_and_scatter(p, pc, pixel, ray, depth, ph, throughput, illumination, rng)) {
-                    ++depth;
-                } else {
-                    active            = false;
-                    p.paths[sidx].s3 = make_uint4(rng, 0u, pixel, 0u);
-                }
-            }
+            const float4 s0 = p.paths[sidx].s0, s1 = p.paths[sidx].s1;
+            ray.ox = s0.x, ray.oy = s0.y, ray.oz = s0.z, ray.dx = s0.w, ray.dy = s1.x, ray.dz = s1.y;
+            ray_prepare(ray, p.cam.nodes_safe != 0u);
         }
     }
-    // ---- trace the ray: TLAS walk + classical BLAS closest hits + first N-BVH interval (same as k_primary)
     bool neural = false;
     uint32_t nstack[kNeuralStackSize];
     int nss        = 0;
@@ -167,12 +206,6 @@ k_path_bounce(const __grid_constant__ RenderParams p, const __grid_constant__ Pa
             nstack[0] = 0u, nss = 1;
             neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
         }
-        PathState st;
-        st.s0 = make_float4(ray.ox, ray.oy, ray.oz, ray.dx);
-        st.s1 = make_float4(ray.dy, ray.dz, throughput.x, throughput.y);
-        st.s2 = make_float4(throughput.z, illumination.x, illumination.y, illumination.z);
-        st.s3 = make_uint4(rng, depth, pixel, 0u);
-        p.paths[sidx] = st;
     }
     const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
     if (qmask) {
@@ -210,33 +243,39 @@ k_path_bounce(const __grid_constant__ RenderParams p, const __grid_constant__ Pa
     warp_add_counter(p.counters, CNT_QUEUED, active && neural ? 1u : 0u);
 }
 
-// One frame of NeuralPathModule::neural_path_tracing.  `counters` holds 2 zeroed words per bounce (queue count, cursor).
+// One frame of NeuralPathModule::neural_path_tracing.  `counters`: kPathCountersPerDepth zeroed words per depth
+// (neural queue count, queue cursor, length of the path list).  paths[2] / hits[2]: ping-pong path lists.
 cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
-                               uint32_t *bounce_counters, int num_sms, cudaStream_t stream)
+                               PathState *const paths[2], PathHit *const hits[2], uint32_t *counters, int num_sms, cudaStream_t stream)
 {
     if (rp_in.pixel_count == 0)
         return cudaSuccess;
-    RenderParams rp         = rp_in;
-    const uint32_t n_chunks = (rp.pixel_count + 31u) >> 5;
-    const uint32_t blocks   = (n_chunks + 7u) / 8u;
-    for (uint32_t depth = 1; depth <= rp.max_depth + 1u; ++depth) {
-        // launch `depth` shades the hits of the rays at depth-1 and traces the rays at `depth`
-        rp.queue_count  = bounce_counters + 2u * (depth - 1u);
-        rp.queue_cursor = rp.queue_count + 1;
+    RenderParams rp       = rp_in;
+    const uint32_t blocks = ((rp.pixel_count + 31u) / 32u + 7u) / 8u;
+    cudaError_t e;
+    for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
+        uint32_t *c     = counters + kPathCountersPerDepth * (depth - 1u);
+        const int cur   = (int)((depth - 1u) & 1u);
+        rp.queue_count  = c;
+        rp.queue_cursor = c + 1;
         rp.ray_depth    = depth;
-        if (depth > 1u)
+        rp.paths = paths[cur], rp.path_hits = hits[cur];
+        PathIo io;
+        io.in = paths[cur], io.hits_in = hits[cur], io.out = paths[cur ^ 1];
+        io.count_in  = depth == 1u ? nullptr : c + 2; // list length written by the previous shade pass
+        io.count_out = c + kPathCountersPerDepth + 2;
+        if (depth == 1u) {
+            k_path_trace<true><<<blocks, 256, 0, stream>>>(rp, io);
+        } else {
             rp.nbvh = nbvh_bounce; // path_lod_switch: bounce rays may walk a coarser LoD (neural_bvh_module_common.cuh:333-335)
-        if (depth == 1u)
-            k_path_bounce<true><<<blocks, 256, 0, stream>>>(rp, pc);
-        else
-            k_path_bounce<false><<<blocks, 256, 0, stream>>>(rp, pc);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess)
+            k_path_trace<false><<<blocks, 256, 0, stream>>>(rp, io);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
-        if (depth == rp.max_depth + 1u)
-            break; // the last launch only shades (every path ends at max_depth)
-        e = launch_neural(rp, nc, num_sms, true, stream);
-        if (e != cudaSuccess)
+        if ((e = launch_neural(rp, nc, num_sms, true, stream)) != cudaSuccess)
+            return e;
+        k_path_shade<<<blocks, 256, 0, stream>>>(rp, pc, io);
+        if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }
     return cudaSuccess;

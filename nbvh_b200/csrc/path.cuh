@@ -18,7 +18,18 @@ struct PathConst {
     float constant_roughness, constant_specular, constant_metallic;
 };
 
+// path lists of one shade pass: in/hits_in (length *count_in, or the pixel count when null) -> survivors appended to out
+struct PathIo {
+    const PathState *in;
+    const PathHit *hits_in;
+    PathState *out;
+    const uint32_t *count_in;
+    uint32_t *count_out;
+};
+
+constexpr uint32_t kPathCountersPerDepth = 4; // neural queue count, queue cursor, path-list length, pad
+
 cudaError_t launch_render_path(const RenderParams &rp, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
-                               uint32_t *bounce_counters, int num_sms, cudaStream_t stream);
+                               PathState *const paths[2], PathHit *const hits[2], uint32_t *counters, int num_sms, cudaStream_t stream);
 
 } // namespace nbvh
