@@ -228,6 +228,89 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
 
+    # ---------------- hybrid neural path tracing (BASELINE configs[1] at the shipped max_depth = "2b", and configs[3]):
+    # shading + BSDF sampling + Russian roulette + HDRI per bounce, 3 launches per depth (path.cu)
+    path_info = None
+    if root is not None and nbvh_b200.has_shading_fixture(root):
+        path_info = {}
+        pmod = nbvh_b200.load_chess_module(device=local_rank, max_depth=3, envmap_eval=True, shading=True)
+
+        def time_frames(fn, n):
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for i in range(n):
+                flush.fill_(i & 0xFF)
+                ev[i][0].record(stream)
+                fn(i)
+                ev[i][1].record(stream)
+            barrier()
+            return float(sum(a.elapsed_time(b) for a, b in ev)) / n
+
+        # config 2b: 1920x1080, shipped max_depth 3, one sample per rank per step (spp sharding like the headline)
+        pmod.attach_framebuffer((W, H))
+        for i in range(3):
+            pmod.neural_render(i * world + rank, 0, stream=stream.cuda_stream)
+        barrier()
+        pmod.reset_counters()
+        n2 = max(5, min(args.steps, 30))
+        ms2 = time_frames(lambda i: pmod.neural_render((3 + i) * world + rank, 0, stream=stream.cuda_stream), n2)
+        c2 = {k: v / n2 for k, v in pmod.counters().items()}
+        # config 4: 3840x2160, max_depth 4, 16 spp; the image is cut into 8*world pixel ranges dealt round-robin to the ranks
+        # (balances the board-vs-pieces cost skew), each rank accumulates its ranges over 16 samples, one NCCL reduce
+        # of the RGBA32F image to rank 0 at the end (the ranges are disjoint, the other ranks contribute zeros)
+        W4, H4, spp4 = 3840, 2160, 16
+        pmod.max_depth = 4
+        accum4, _ = pmod.attach_framebuffer((W4, H4))
+        n_pix4 = W4 * H4
+        if world == 1:
+            ranges = [(0, n_pix4)]
+        else:
+            per = ((n_pix4 // (8 * world)) + 31) // 32 * 32
+            ranges = [(k * per, min(per, n_pix4 - k * per)) for k in range(8 * world) if k % world == rank and k * per < n_pix4]
+
+        def image4(_i):
+            for s_ in range(spp4):
+                for first, count in ranges:
+                    pmod.neural_render(s_, 0, first, count, stream=stream.cuda_stream)
+            if world > 1:
+                dist.reduce(accum4, dst=0)
+
+        image4(0)
+        barrier()
+        pmod.reset_counters()
+        n4 = 3
+        ms4 = time_frames(image4, n4)
+        c4 = {k: v / n4 for k, v in pmod.counters().items()}
+        pmod.close()
+        tt_ = torch.tensor([ms2, ms4, c4["rays"], c4["queries"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = tt_.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt_, op=dist.ReduceOp.SUM)
+            ms2, ms4 = float(tmax[0]), float(tmax[1])
+            c4["rays"], c4["queries"] = float(tt_[2]), float(tt_[3])
+        path_info["config2b"] = {
+            "workload": "Chess hybrid neural path tracing, shipped settings (max_depth 3, Russian roulette from depth 2, HDRI, chessboard glTF "
+                        "material), 1920x1080, 1 spp per rank per step", "ms_per_frame": ms2, "frames": n2,
+            "Mpixels_s": world * n_rays / (ms2 * 1e-3) / 1e6, "rays_per_frame": c2["rays"],
+            "Mrays_s_all_rays": world * c2["rays"] / (ms2 * 1e-3) / 1e6, "queries_per_frame": c2["queries"],
+            "neural_queries_per_s": world * c2["queries"] / (ms2 * 1e-3), "launches_per_frame": 9}
+        path_info["config4"] = {
+            "workload": "Chess + shipped HDRI, max_depth 4, 3840x2160, 16 spp; image cut into %d pixel ranges dealt round-robin to %d rank(s), "
+                        "RGBA32F image reduced to rank 0" % (len(ranges) * world, world), "scaling": "strong",
+            "ms_per_16spp_image": ms4, "images": n4, "Mpixel_samples_s": n_pix4 * spp4 / (ms4 * 1e-3) / 1e6,
+            "rays_per_image": c4["rays"], "Mrays_s_all_rays": c4["rays"] / (ms4 * 1e-3) / 1e6,
+            "neural_queries_per_s": c4["queries"] / (ms4 * 1e-3)}
+        try:
+            rp_ = json.load(open(os.path.join(REPO, "tests", "golden", "ref_chess_path_timing.json")))
+            a, b = rp_["config2b_1080p_depth3"], rp_["config4_2160p_depth4"]
+            path_info["config2b"]["reference_b200"] = {"ms_per_frame": a["ms_best"], "Mpixels_s": n_rays / a["ms_best"] / 1e3, "queries": a["queries"],
+                                                       "launches": a["launches"], "host_syncs": a["host_syncs"], "what": a["what"]}
+            path_info["config4"]["reference_b200"] = {"ms_per_1spp_frame": b["ms_best"], "ms_per_16spp_image": 16 * b["ms_best"],
+                                                      "Mpixel_samples_s": n_pix4 / b["ms_best"] / 1e3, "launches_per_frame": b["launches"],
+                                                      "host_syncs_per_frame": b["host_syncs"], "what": b["what"] + " (single GPU: the reference has no multi-GPU mode)"}
+        except Exception:
+            pass
+
     # ---------------- online optimisation (second half of BASELINE's metric: train samples/s), data parallel:
     # every rank owns 2^18 batch slots; per step: sample generation (K10: tree-cut walk + neural-mesh BLAS trace +
     # material lookups), hash-grid encode + fused MLP forward/loss/backward + grid backward, fp32 gradient allreduce
@@ -352,6 +435,7 @@ def main():
                               "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam" +
                               ("; fp32 gradient allreduce (NCCL) per step" if world > 1 else ""),
                       "reference_b200": ref_train},
+            "path": path_info,
             "counters_per_step": per,
             "neural_queries_per_s": per["queries"] / (ms_per_step * 1e-3),
             "clocks": sampler.summary(),
