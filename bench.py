@@ -22,6 +22,8 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints exactly one JSON line on stdout (NCCL's version banner goes there too)
 
 METRIC = "neural ray queries/sec (Mrays/s, 1080p Chess)"
 UNIT = "Mrays/s"
@@ -254,25 +256,21 @@ def main():
         n2 = max(5, min(args.steps, 30))
         ms2 = time_frames(lambda i: pmod.neural_render((3 + i) * world + rank, 0, stream=stream.cuda_stream), n2)
         c2 = {k: v / n2 for k, v in pmod.counters().items()}
-        # config 4: 3840x2160, max_depth 4, 16 spp; the image is cut into 8*world pixel ranges dealt round-robin to the ranks
-        # (balances the board-vs-pieces cost skew), each rank accumulates its ranges over 16 samples, one NCCL reduce
-        # of the RGBA32F image to rank 0 at the end (the ranges are disjoint, the other ranks contribute zeros)
+        # config 4: 3840x2160, max_depth 4, 16 spp; image tiles (8x4-pixel blocks) are dealt round-robin to the ranks
+        # (nbvh_render_interleaved: balances the board-vs-pieces cost skew), each rank accumulates its tiles over 16 samples,
+        # one NCCL reduce of the RGBA32F image to rank 0 at the end (the tiles are disjoint, the other ranks contribute zeros)
         W4, H4, spp4 = 3840, 2160, 16
         pmod.max_depth = 4
         accum4, _ = pmod.attach_framebuffer((W4, H4))
         n_pix4 = W4 * H4
-        if world == 1:
-            ranges = [(0, n_pix4)]
-        else:
-            per = ((n_pix4 // (8 * world)) + 31) // 32 * 32
-            ranges = [(k * per, min(per, n_pix4 - k * per)) for k in range(8 * world) if k % world == rank and k * per < n_pix4]
+        img4 = torch.empty_like(accum4) if world > 1 else accum4
 
         def image4(_i):
             for s_ in range(spp4):
-                for first, count in ranges:
-                    pmod.neural_render(s_, 0, first, count, stream=stream.cuda_stream)
+                pmod.neural_render_shard(s_, 0, rank, world, stream=stream.cuda_stream)
             if world > 1:
-                dist.reduce(accum4, dst=0)
+                img4.copy_(accum4)
+                dist.reduce(img4, dst=0)
 
         image4(0)
         barrier()
@@ -295,8 +293,8 @@ def main():
             "Mrays_s_all_rays": world * c2["rays"] / (ms2 * 1e-3) / 1e6, "queries_per_frame": c2["queries"],
             "neural_queries_per_s": world * c2["queries"] / (ms2 * 1e-3), "launches_per_frame": 9}
         path_info["config4"] = {
-            "workload": "Chess + shipped HDRI, max_depth 4, 3840x2160, 16 spp; image cut into %d pixel ranges dealt round-robin to %d rank(s), "
-                        "RGBA32F image reduced to rank 0" % (len(ranges) * world, world), "scaling": "strong",
+            "workload": "Chess + shipped HDRI, max_depth 4, 3840x2160, 16 spp; 8x4-pixel tiles dealt round-robin to %d rank(s), "
+                        "RGBA32F image reduced to rank 0" % world, "scaling": "strong",
             "ms_per_16spp_image": ms4, "images": n4, "Mpixel_samples_s": n_pix4 * spp4 / (ms4 * 1e-3) / 1e6,
             "rays_per_image": c4["rays"], "Mrays_s_all_rays": c4["rays"] / (ms4 * 1e-3) / 1e6,
             "neural_queries_per_s": c4["queries"] / (ms4 * 1e-3)}

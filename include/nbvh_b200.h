@@ -324,6 +324,11 @@ int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const fl
  * shard of the image (count = 0 -> whole frame). */
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel,
                 uint32_t pixel_count, void *stream);
+/* Multi-GPU tile partition of neural_render: shard `shard_index` of `shard_count` renders every
+ * shard_count-th 32-pixel block (8x4 pixels) of the frame -- an interleaved tile partition that balances the per-pixel cost skew.
+ * The RNG is keyed by the global pixel id, so the union of the shards is bit-identical to the full frame. */
+int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t shard_index,
+                            uint32_t shard_count, void *stream);
 /* End-to-end variant with HOST buffers: uploads `camera_host` (may be NULL), renders, copies the
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,

@@ -1418,8 +1418,32 @@ int nbvh_destroy_textures(nbvh_ctx *ctx)
     return NBVH_OK;
 }
 
+static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
+                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream);
+
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
                 void *stream)
+{
+    return render_impl(ctx, accumulated_spp, sample_offset, first_pixel, pixel_count, 1u, 0u, stream);
+}
+
+int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t shard_index, uint32_t shard_count,
+                            void *stream)
+{
+    if (!ctx || shard_count == 0 || shard_index >= shard_count)
+        return NBVH_ERR_INVALID_ARG;
+    const uint32_t total = ctx->fb_w * ctx->fb_h;
+    if ((total & 31u) != 0u)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "interleaved shards need a pixel count that is a multiple of 32");
+    const uint32_t n_chunks = total >> 5;
+    const uint32_t mine     = n_chunks / shard_count + (shard_index < n_chunks % shard_count ? 1u : 0u);
+    if (mine == 0u)
+        return NBVH_OK;
+    return render_impl(ctx, accumulated_spp, sample_offset, 0u, mine * 32u, shard_count, shard_index, stream);
+}
+
+static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
+                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream)
 {
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
@@ -1466,6 +1490,7 @@ int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
         rp.bg.envmap   = ctx->envmap;
     }
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
+    rp.chunk_stride = chunk_stride, rp.chunk_offset = chunk_offset;
     rp.next_chunk    = ctx->d_next_chunk;
     if (ctx->queue_capacity < (size_t)total) {
         cudaFree(ctx->d_queue);

@@ -121,9 +121,13 @@ __device__ __forceinline__ void background(const RenderParams &p, const Ray &ray
     bg[0] = c.x, bg[1] = c.y, bg[2] = c.z;
 }
 
-// 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1)
+// 8x4 pixel blocks per 32-pixel chunk keep the rays of a warp spatially coherent (hash-grid and node reuse in L1).
+// Interleaved shards (multi-GPU tile partition): the launch owns every chunk_stride-th 32-pixel chunk starting at
+// chunk_offset, so its slot s maps to the global slot ((s / 32) * stride + offset) * 32 + s % 32.
 __device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_t s)
 {
+    if (p.chunk_stride > 1u)
+        s = (((s - p.first_pixel) >> 5) * p.chunk_stride + p.chunk_offset) * 32u + (s & 31u);
     const uint32_t w = p.cam.fb_w, h = p.cam.fb_h;
     if ((w & 7u) || (h & 3u))
         return s;

@@ -310,6 +310,10 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_render(self._h, int(accumulated_spp), int(sample_offset), int(first_pixel),
                                           int(pixel_count), stream))
 
+    def neural_render_shard(self, accumulated_spp, sample_offset, shard_index, shard_count, stream=None):
+        """neural_render restricted to an interleaved tile shard (every shard_count-th 8x4-pixel block): the multi-GPU partition."""
+        self._check(self._lib.nbvh_render_interleaved(self._h, int(accumulated_spp), int(sample_offset), int(shard_index), int(shard_count), stream))
+
     def neural_render_host(self, accumulated_spp, sample_offset, ldr_host=None, hits_host=None, camera=None):
         """End-to-end call with HOST buffers (numpy arrays, ideally pinned)."""
         cam = C.byref(camera) if camera is not None else None

@@ -240,6 +240,22 @@ def test_gpu_path_shards_and_accumulation(syn_path, torch_cuda):
     assert (ldr.cpu().numpy() == ldr_full).all()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_depth", [1, 3])
+def test_gpu_interleaved_tile_shards_reproduce_full_frame(syn_path, torch_cuda, max_depth):
+    """Multi-GPU tile partition (nbvh_render_interleaved): the union of the shards is bit-identical to the full frame."""
+    mod, W, H = syn_path["mod"], syn_path["W"], syn_path["H"]
+    mod.max_depth = max_depth
+    full, ldr_full = gpu_render(mod, torch_cuda, W, H, spp=2)
+    accum, ldr = mod.attach_framebuffer((W, H))
+    for s in range(2):
+        for shard in (2, 0, 1):
+            mod.neural_render_shard(s, 0, shard, 3)
+    torch_cuda.cuda.synchronize()
+    assert (accum.cpu().numpy()[..., :3].reshape(H, W, 3).view(np.uint32) == full.view(np.uint32)).all()
+    assert (ldr.cpu().numpy() == ldr_full).all()
+
+
 @pytest.fixture(scope="module")
 def chess_path(torch_cuda, oracle, chess_root):
     import nbvh_b200
