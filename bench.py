@@ -22,8 +22,7 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"  # rank 0 prints exactly one JSON line on stdout (NCCL's version banner goes there too)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL's version banner would go there too)
 
 METRIC = "neural ray queries/sec (Mrays/s, 1080p Chess)"
 UNIT = "Mrays/s"

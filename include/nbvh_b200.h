@@ -225,7 +225,7 @@ typedef struct {
     const uint32_t *blas_indices;
     const nbvh_cuda_blas *mesh_bvhs; /* DEVICE array of num_meshes descriptors */
     uint32_t num_meshes;
-    const void *materials; /* PackedMaterial* (unused until the shading row) */
+    const void *materials; /* PackedMaterial* (96-byte records; read by the sample generator and the shading kernel) */
     const void *textures;  /* cudaTextureObject_t* */
 } nbvh_scene_data;
 
