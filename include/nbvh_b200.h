@@ -324,6 +324,13 @@ int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const fl
  * shard of the image (count = 0 -> whole frame). */
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel,
                 uint32_t pixel_count, void *stream);
+/* Closest-hit neural ray query of an arbitrary ray batch: what one wavefront iteration of the reference computes for the rays
+ * of one depth (tlas_traversal_and_fill_next_hybrid_traversal + non_neural_bvh_intersection + neural_bvh_traversal,
+ * path_module.cu:54-137, neural_bvh_module_common.cuh:291-420): TLAS walk, classical BLAS closest hits, N-BVH leaf intervals,
+ * hash grid + MLP per interval, closest-hit bookkeeping.  o, d: n x 3 (d normalised); ray_depth selects the visibility
+ * threshold and LoD (1 = camera rays); hits: n records, same content as the primary-hit records of nbvh_render. */
+int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t ray_depth, nbvh_hit_record *hits,
+                    void *stream);
 /* Multi-GPU tile partition of neural_render: shard `shard_index` of `shard_count` renders every
  * shard_count-th 32-pixel block (8x4 pixels) of the frame -- an interleaved tile partition that balances the per-pixel cost skew.
  * The RNG is keyed by the global pixel id, so the union of the shards is bit-identical to the full frame. */

@@ -8,8 +8,8 @@ from ._capi import (CONST_CAMERA, CONST_MODULE, CONST_NETWORK, CONST_OPTIMIZER, 
                     CONST_RENDERER, CONST_SCENE, CONST_SCENE_BBOX, load_library)
 from .module import HIT_DTYPE, MATERIAL_DTYPE, NODE_DTYPE, TREE_CUT_DTYPE, NbvhError, NeuralPathModule
 from .scene_io import (chess_fixture_dir, has_shading_fixture, load_chess_module, load_scene_arrays, load_shading_arrays,
-                       procedural_materials, procedural_tree_cut, synthetic_scene)
+                       procedural_materials, procedural_tree_cut, synthetic_instanced_scene, synthetic_ray_batch, synthetic_scene)
 
 __all__ = ["NeuralPathModule", "NbvhError", "NODE_DTYPE", "HIT_DTYPE", "load_library", "chess_fixture_dir",
            "load_chess_module", "load_scene_arrays", "synthetic_scene", "procedural_materials", "procedural_tree_cut",
-           "MATERIAL_DTYPE", "TREE_CUT_DTYPE", "load_shading_arrays", "has_shading_fixture"]
+           "MATERIAL_DTYPE", "TREE_CUT_DTYPE", "load_shading_arrays", "has_shading_fixture", "synthetic_instanced_scene", "synthetic_ray_batch"]

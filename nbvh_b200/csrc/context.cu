@@ -1567,6 +1567,60 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     return NBVH_OK;
 }
 
+int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t ray_depth, nbvh_hit_record *hits, void *stream)
+{
+    if (!ctx || (n && (!o || !d || !hits)) || ray_depth == 0)
+        return NBVH_ERR_INVALID_ARG;
+    int rc = check_ready(ctx, true, true, true);
+    if (rc == NBVH_OK)
+        rc = refresh_dilated(ctx);
+    if (rc != NBVH_OK)
+        return rc;
+    if (n == 0)
+        return NBVH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->queue_capacity < (size_t)n) {
+        cudaFree(ctx->d_queue);
+        ctx->d_queue = nullptr, ctx->queue_capacity = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_queue, (size_t)n * sizeof(NeuralQueueEntry)));
+        ctx->queue_capacity = n;
+    }
+    if (ctx->path_capacity < (size_t)n) {
+        ctx->path_capacity = 0;
+        for (int k = 0; k < 2; k++) {
+            cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
+            ctx->d_paths[k] = nullptr, ctx->d_path_hits[k] = nullptr;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_paths[k], (size_t)n * sizeof(PathState)));
+            CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits[k], (size_t)n * sizeof(PathHit)));
+        }
+        ctx->path_capacity = n;
+    }
+    const size_t counter_bytes = kPathCountersPerDepth * (kMaxPathDepth + 1) * sizeof(uint32_t);
+    if (!ctx->d_bounce_counters)
+        CU_TRY(ctx, cudaMalloc(&ctx->d_bounce_counters, counter_bytes));
+    RenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.cam   = make_camera_const(ctx); // only nodes_safe is read
+    rp.nbvh  = make_nbvh_const(ctx, true);
+    if (ray_depth > 1u && ctx->bvh_const.path_lod_switch && ctx->bvh_const.num_lods_learned > 0)
+        rp.nbvh.leaf_lod_max = 2u + (uint32_t)ctx->bvh_const.lod_switch;
+    rp.scene = ctx->scene;
+    rp.enc   = make_encode_const(ctx);
+    rp.dec.primary_thr         = ctx->pt_const.primary_visibility_threshold;
+    rp.dec.secondary_thr       = ctx->pt_const.secondary_visibility_threshold;
+    rp.dec.depth_epsilon       = ctx->pt_const.depth_epsilon;
+    rp.dec.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
+    rp.ignore_neural_blas      = ctx->bvh_const.ignore_neural_blas;
+    rp.max_depth               = ray_depth;
+    rp.queue                   = ctx->d_queue;
+    rp.counters                = ctx->d_counters;
+    const NetConst nc = make_net_const(ctx);
+    KernelTimer kt(ctx, st);
+    CU_TRY(ctx, launch_trace_rays(rp, nc, o, d, n, ray_depth, ctx->d_paths[0], ctx->d_path_hits[0], ctx->d_bounce_counters, hits, ctx->num_sms, st));
+    kt.stop();
+    return NBVH_OK;
+}
+
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                      uint8_t *ldr_host, nbvh_hit_record *hits_host)
 {

@@ -243,6 +243,69 @@ k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
     warp_add_counter(p.counters, CNT_QUEUED, active && neural ? 1u : 0u);
 }
 
+// ------------------------------------------------------------------------------------------------ ray batches
+// Closest-hit query of an arbitrary ray batch (BASELINE config 5, and the general "neural ray query" entry point):
+// rays -> path list -> k_path_trace -> k_neural<path> -> hit records.  Same kernels as one depth of the path tracer.
+__global__ void __launch_bounds__(256)
+k_rays_to_paths(const float *__restrict__ o, const float *__restrict__ d, uint32_t n, uint32_t ray_depth, PathState *paths, uint32_t *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    if (i == 0u)
+        counters[2] = n; // list length read by k_path_trace
+    PathState st;
+    st.s0 = make_float4(o[3u * i], o[3u * i + 1u], o[3u * i + 2u], d[3u * i]);
+    st.s1 = make_float4(d[3u * i + 1u], d[3u * i + 2u], 1.f, 1.f);
+    st.s2 = make_float4(1.f, 0.f, 0.f, 0.f);
+    st.s3 = make_uint4(0u, ray_depth, i, 0u);
+    paths[i] = st;
+}
+
+__global__ void __launch_bounds__(256)
+k_hits_to_records(const PathHit *__restrict__ hits, uint32_t n, nbvh_hit_record *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const PathHit ph = hits[i];
+    nbvh_hit_record r;
+    r.t = ph.h0.x, r.valid_hit = __float_as_uint(ph.h0.y);
+    r.normal_or_uv[0] = ph.h0.z, r.normal_or_uv[1] = ph.h0.w, r.normal_or_uv[2] = ph.h1.x;
+    r.albedo_or_ids[0] = ph.h1.y, r.albedo_or_ids[1] = ph.h1.z, r.albedo_or_ids[2] = ph.h1.w;
+    out[i] = r;
+}
+
+// counters: [0] queue count, [1] queue cursor (zeroed here), [2] list length (written by k_rays_to_paths)
+cudaError_t launch_trace_rays(const RenderParams &rp_in, const NetConst &nc, const float *o, const float *d, uint32_t n, uint32_t ray_depth,
+                              PathState *paths, PathHit *hits, uint32_t *counters, nbvh_hit_record *out, int num_sms, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    RenderParams rp = rp_in;
+    rp.pixel_count  = n;
+    rp.first_pixel  = 0;
+    rp.chunk_stride = 1, rp.chunk_offset = 0;
+    rp.queue_count = counters, rp.queue_cursor = counters + 1;
+    rp.ray_depth = ray_depth;
+    rp.paths = paths, rp.path_hits = hits;
+    rp.hits = nullptr;
+    PathIo io;
+    io.in = paths, io.hits_in = hits, io.out = nullptr, io.count_in = counters + 2, io.count_out = nullptr;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), stream)) != cudaSuccess)
+        return e;
+    const uint32_t blocks = (n + 255u) / 256u;
+    k_rays_to_paths<<<blocks, 256, 0, stream>>>(o, d, n, ray_depth, paths, counters);
+    k_path_trace<false><<<blocks, 256, 0, stream>>>(rp, io);
+    if ((e = cudaGetLastError()) != cudaSuccess)
+        return e;
+    if ((e = launch_neural(rp, nc, num_sms, true, stream)) != cudaSuccess)
+        return e;
+    k_hits_to_records<<<blocks, 256, 0, stream>>>(hits, n, out);
+    return cudaGetLastError();
+}
+
 // One frame of NeuralPathModule::neural_path_tracing.  `counters`: kPathCountersPerDepth zeroed words per depth
 // (neural queue count, queue cursor, length of the path list).  paths[2] / hits[2]: ping-pong path lists.
 cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,

@@ -32,4 +32,7 @@ constexpr uint32_t kPathCountersPerDepth = 4; // neural queue count, queue curso
 cudaError_t launch_render_path(const RenderParams &rp, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
                                PathState *const paths[2], PathHit *const hits[2], uint32_t *counters, int num_sms, cudaStream_t stream);
 
+cudaError_t launch_trace_rays(const RenderParams &rp, const NetConst &nc, const float *o, const float *d, uint32_t n, uint32_t ray_depth,
+                              PathState *paths, PathHit *hits, uint32_t *counters, nbvh_hit_record *out, int num_sms, cudaStream_t stream);
+
 } // namespace nbvh

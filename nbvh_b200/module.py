@@ -310,6 +310,16 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_render(self._h, int(accumulated_spp), int(sample_offset), int(first_pixel),
                                           int(pixel_count), stream))
 
+    def trace_rays(self, o, d, ray_depth=1, hits=None, stream=None):
+        """Closest-hit neural ray query of a ray batch (o, d: (N, 3) float32 CUDA tensors).  Returns a uint8 tensor holding N
+        HIT_DTYPE records."""
+        torch = _torch()
+        n = int(o.shape[0])
+        if hits is None:
+            hits = torch.empty(n * HIT_DTYPE.itemsize, dtype=torch.uint8, device=o.device)
+        self._check(self._lib.nbvh_trace_rays(self._h, _ptr(o), _ptr(d), n, int(ray_depth), _ptr(hits), stream))
+        return hits
+
     def neural_render_shard(self, accumulated_spp, sample_offset, shard_index, shard_count, stream=None):
         """neural_render restricted to an interleaved tile shard (every shard_count-th 8x4-pixel block): the multi-GPU partition."""
         self._check(self._lib.nbvh_render_interleaved(self._h, int(accumulated_spp), int(sample_offset), int(shard_index), int(shard_count), stream))

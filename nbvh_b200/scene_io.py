@@ -270,3 +270,129 @@ def synthetic_scene(seed=1234, n_spheres=24, subdiv=12, cut_depth=9, fb=(256, 19
         },
     }
     return cfg, nbvh, tlas, tlas_idx, blas
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 5
+def _icosphere(subdiv):
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+                  [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    for _ in range(subdiv):
+        a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+        ab, bc, ca = a + b, b + c, c + a
+        n0 = len(v)
+        nf = len(f)
+        v = np.concatenate([v, ab / np.linalg.norm(ab, axis=1, keepdims=True), bc / np.linalg.norm(bc, axis=1, keepdims=True),
+                            ca / np.linalg.norm(ca, axis=1, keepdims=True)])
+        iab, ibc, ica = n0 + np.arange(nf), n0 + nf + np.arange(nf), n0 + 2 * nf + np.arange(nf)
+        f = np.concatenate([np.stack([f[:, 0], iab, ica], 1), np.stack([f[:, 1], ibc, iab], 1), np.stack([f[:, 2], ica, ibc], 1),
+                            np.stack([iab, ibc, ica], 1)])
+    return v, f  # (vertices are duplicated along shared edges: irrelevant for bounds)
+
+
+def synthetic_instanced_scene(lattice=(12, 13, 13), subdiv=4, cut_depth=17, seed=1234, log2_hashmap=18, fb=(1920, 1080), device=None):
+    """BASELINE.json configs[4]: K = prod(lattice) instances of a displaced, subdivided icosphere "piece" (20 * 4^subdiv triangles
+    each; defaults: 2,028 x 5,120 = 10.38 M triangles) on a jittered 3-D lattice inside the unit cube, pre-transformed and
+    flattened into ONE neural mesh (the reference supports exactly one, scene.cpp:225-251); std::mt19937-free: numpy PCG64
+    with the given seed.  The neural BLAS is a median-split BVH2 over the triangles, cut at a fixed depth (neural_bvh_min_depth,
+    neural_bvh_renderer_accel.cpp:24-74): 2^(cut_depth+1) - 1 tree-cut nodes, 2^cut_depth neural leaves.  Only the tree-cut is
+    needed for inference, so the build stops at the cut (level-synchronous, vectorised with torch on `device`).
+    Returns (config dict, nbvh nodes, tlas_nodes, tlas_indices, blas_list, info)."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    rng = np.random.default_rng(seed)
+    K = int(np.prod(lattice))
+    bv, bf = _icosphere(subdiv)
+    # displaced "piece": radial bumps, same for every instance; per-instance scale + jittered lattice position
+    disp = 1.0 + 0.25 * np.sin(5.0 * bv[:, 0]) * np.cos(4.0 * bv[:, 1]) + 0.15 * np.sin(7.0 * bv[:, 2])
+    piece = (bv * disp[:, None]).astype(np.float32)
+    gx, gy, gz = np.meshgrid(*[(np.arange(n) + 0.5) / n for n in lattice], indexing="ij")
+    cell = 1.0 / np.array(lattice)
+    centers = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], 1) + rng.uniform(-0.2, 0.2, (K, 3)) * cell
+    radii = rng.uniform(0.22, 0.32, K) * cell.min()
+    tri = torch.from_numpy(piece[bf]).to(dev)                                   # (F, 3, 3)
+    c_t = torch.from_numpy(centers.astype(np.float32)).to(dev)
+    r_t = torch.from_numpy(radii.astype(np.float32)).to(dev)
+    F = tri.shape[0]
+    lo = (tri.amin(dim=1)[None] * r_t[:, None, None] + c_t[:, None, :]).reshape(-1, 3)   # (K*F, 3) triangle bounds
+    hi = (tri.amax(dim=1)[None] * r_t[:, None, None] + c_t[:, None, :]).reshape(-1, 3)
+    cen = (tri.mean(dim=1)[None] * r_t[:, None, None] + c_t[:, None, :]).reshape(-1, 3)
+    N = lo.shape[0]
+    n_nodes = (1 << (cut_depth + 1)) - 1
+    node_lo = torch.empty((n_nodes, 3), dtype=torch.float32, device=dev)
+    node_hi = torch.empty((n_nodes, 3), dtype=torch.float32, device=dev)
+    seg = torch.zeros(N, dtype=torch.int64, device=dev)  # index of each triangle's node within the current level
+    for depth in range(cut_depth + 1):
+        n_seg = 1 << depth
+        first = n_seg - 1
+        idx3 = seg[:, None].expand(-1, 3)
+        blo = torch.full((n_seg, 3), float("inf"), device=dev).scatter_reduce_(0, idx3, lo, "amin")
+        bhi = torch.full((n_seg, 3), float("-inf"), device=dev).scatter_reduce_(0, idx3, hi, "amax")
+        node_lo[first:first + n_seg], node_hi[first:first + n_seg] = blo, bhi
+        if depth == cut_depth:
+            break
+        clo = torch.full((n_seg, 3), float("inf"), device=dev).scatter_reduce_(0, idx3, cen, "amin")
+        chi = torch.full((n_seg, 3), float("-inf"), device=dev).scatter_reduce_(0, idx3, cen, "amax")
+        axis = (chi - clo).argmax(dim=1)                                         # split axis of each node: longest centroid extent
+        key = cen.gather(1, axis[seg][:, None]).squeeze(1)
+        order = torch.argsort(key, stable=True)
+        order = order[torch.argsort(seg[order], stable=True)]                    # sorted by (node, coordinate)
+        count = torch.bincount(seg, minlength=n_seg)
+        start = torch.cumsum(count, 0) - count
+        rank = torch.empty(N, dtype=torch.int64, device=dev)
+        rank[order] = torch.arange(N, device=dev) - start[seg[order]]
+        seg = 2 * seg + (rank >= (count[seg] + 1) // 2).to(torch.int64)          # median split: left gets ceil(n/2)
+    nbvh = np.zeros(n_nodes, dtype=NODE_DTYPE)
+    nbvh["mn"], nbvh["mx"] = node_lo.cpu().numpy(), node_hi.cpu().numpy()
+    n_int = (1 << cut_depth) - 1
+    nbvh["a"][:n_int] = 0
+    nbvh["b"][:n_int] = 2 * np.arange(n_int, dtype=np.uint32) + 1              # children adjacent: (2i+1, 2i+2)
+    nbvh["a"][n_int:] = 8                                                       # LOWEST_BVH_LOD: a cut leaf that could still be split
+    nbvh["b"][n_int:] = 0xFFFFFFFF
+    leaf_count = torch.bincount(seg, minlength=1 << cut_depth)
+    stub = dict(nodes=np.zeros(1, NODE_DTYPE), prim_ids=np.zeros(1, np.uint32), vertices=np.zeros(9, np.float32), indices=np.zeros(3, np.uint32))
+    tlas = np.zeros(1, dtype=NODE_DTYPE)
+    tlas[0] = (nbvh[0]["mn"], 0, nbvh[0]["mx"], 2)                              # a single neural TLAS leaf
+    tlas_idx = np.array([0], dtype=np.uint32)
+    cfg = {
+        "cuda_scene": {"fb_size": list(fb), "camera": {"yfov": 0.7, "matrix": [1.0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, -0.5, -0.5, -2.5, 1]},
+                       "scene_constants": {"envmap_eval": False, "ema_accumulate": False}},
+        "neural_bvh_renderer": {
+            "neural_module": {
+                "max_depth": 1,
+                "pt_output_constants": {"output_albedo_dim": 3, "output_depth_dim": 1, "output_network_dims": 8,
+                                        "output_normal_dim": 3, "output_visibility_dim": 1},
+                "bvh_module_constants": {"input_network_dims": 9, "input_segment_points": 3,
+                                         "input_segment_points_dim": 9, "segment_distribution": "EquidistantExterior"},
+                "segment_encoding": {"type": "HashGrid", "hashgrid_options": {"log2_hashmap_size": log2_hashmap}},
+            },
+            "bvh_constants": {"rendered_lod": 0, "current_learned_lod": 6},
+        },
+    }
+    info = dict(triangles=int(N), instances=K, triangles_per_instance=int(F), nbvh_nodes=int(n_nodes), neural_leaves=1 << cut_depth,
+                triangles_per_leaf_min=int(leaf_count.min()), triangles_per_leaf_max=int(leaf_count.max()))
+    return cfg, nbvh, tlas, tlas_idx, [stub], info
+
+
+def synthetic_ray_batch(nbvh_root, n, seed=42, device=None):
+    """BASELINE config 5 rays: uniform random origins on the surface of the 1.5x-scaled scene box, directions toward uniformly
+    sampled interior points.  Returns float32 (n, 3) origin and (normalised) direction tensors on `device`."""
+    import torch
+    dev = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    mn = torch.tensor(np.asarray(nbvh_root["mn"], np.float32), device=dev)
+    mx = torch.tensor(np.asarray(nbvh_root["mx"], np.float32), device=dev)
+    c, e = 0.5 * (mn + mx), 0.5 * (mx - mn)
+    u = torch.rand((n, 3), generator=g, device=dev) * 2.0 - 1.0
+    face = torch.randint(0, 6, (n,), generator=g, device=dev)                   # equal-area faces of the (near-)cube
+    axis, sign = face // 2, (face % 2).to(torch.float32) * 2.0 - 1.0
+    u.scatter_(1, axis[:, None], sign[:, None])
+    o = c + 1.5 * e * u
+    tgt = mn + (mx - mn) * torch.rand((n, 3), generator=g, device=dev)
+    d = tgt - o
+    d = d / d.norm(dim=1, keepdim=True)
+    return o.contiguous(), d.contiguous()

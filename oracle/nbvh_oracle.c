@@ -1612,6 +1612,26 @@ static void path_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, 
     radiance[0] = ill[0], radiance[1] = ill[1], radiance[2] = ill[2];
 }
 
+/* closest-hit query of a ray batch: one trace_ray per ray (what nbvh_trace_rays computes) */
+void onbvh_trace_rays(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t n, const float *o,
+                      const float *d, uint32_t ray_depth, uint32_t lod, int mlp_mode, ohit_t *hits, uint64_t *counters, int n_threads)
+{
+    uint64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#ifdef _OPENMP
+    if (n_threads > 0)
+        omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : c0, c1, c2, c3)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        uint64_t cnt[4] = {0, 0, 0, 0};
+        trace_ray(s, nbvh, c, net, o + 3 * i, d + 3 * i, ray_depth, lod, mlp_mode, &hits[i], cnt);
+        c0 += cnt[0], c1 += cnt[1], c2 += cnt[2], c3 += cnt[3];
+    }
+    if (counters) {
+        counters[0] = c0, counters[1] = c1, counters[2] = c2, counters[3] = c3;
+    }
+}
+
 void onbvh_render_path(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const opath_t *pc,
                        uint32_t pixel_begin, uint32_t pixel_end, uint32_t pixel_stride, int sample_idx, int rnd_offset,
                        int mlp_mode, float *radiance, ohit_t *primary_hits, uint64_t *counters, int n_threads)

@@ -220,6 +220,10 @@ void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t
                           uint64_t *counters /* [0]=queries [1]=nbvh interior steps [2]=blas interior [3]=tri tests */,
                           int n_threads);
 
+/* closest hit of arbitrary rays (o, d: n x 3) through TLAS, classical BLAS and the neural BLAS; lod = rendered_lod normally */
+void onbvh_trace_rays(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, uint32_t n, const float *o,
+                      const float *d, uint32_t ray_depth, uint32_t lod, int mlp_mode, ohit_t *hits, uint64_t *counters, int n_threads);
+
 /* --- hybrid neural path tracing, max_depth >= 1 (a15 / f1: shading, BSDF sampling, Russian roulette, re-queue) --- */
 typedef struct {
     const float *normals, *texcoords;

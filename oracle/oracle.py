@@ -382,6 +382,18 @@ def tex2d(img, u, v):
     return np.array(out[:], dtype=np.float32)
 
 
+def trace_rays(scene, nbvh_nodes, const, net, o, d, ray_depth=1, mlp_mode=0, n_threads=0):
+    nbvh_nodes = np.ascontiguousarray(nbvh_nodes, dtype=NODE_DTYPE)
+    o = np.ascontiguousarray(o, dtype=np.float32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    n = o.shape[0]
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    cnt = (C.c_uint64 * 4)()
+    lib().onbvh_trace_rays(C.byref(scene.c), _p(nbvh_nodes), C.byref(const), C.byref(net), C.c_uint32(n), _p(o), _p(d),
+                           C.c_uint32(ray_depth), C.c_uint32(const.rendered_lod), C.c_int(mlp_mode), _p(hits), cnt, C.c_int(n_threads))
+    return hits, [cnt[i] for i in range(4)]
+
+
 # ----------------------------------------------------------------------------- hybrid neural path tracing (a15 / f1)
 class OAttr(C.Structure):
     _fields_ = [("normals", C.c_void_p), ("texcoords", C.c_void_p), ("material_ids", C.c_void_p), ("material_map", C.c_void_p),
