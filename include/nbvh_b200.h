@@ -390,6 +390,27 @@ int nbvh_destroy_textures(nbvh_ctx *ctx);
 int nbvh_create_envmap_rgba32f(nbvh_ctx *ctx, const float *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out);
 int nbvh_set_envmap(nbvh_ctx *ctx, uint64_t envmap_texture);
 int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads);
+
+/* ---- tree-cut learning (tree_cut_learning: true in the shipped configs) ----------------------------------------------
+ * The reference keeps this state in NeuralBVHRenderer (m_neural_bvh_nodes, m_neural_tree_cut_data, m_neural_node_map,
+ * include/cuda/neural/neural_bvh_renderer.h); here the context owns it and every step stays on the device.
+ * The scene given to nbvh_set_scene must carry the classical BLAS of the neural mesh (bvh_const.neural_bvh_idx). */
+/* == build_and_upload_neural_bvh(neural_bvh_min_depth) (neural_bvh_renderer_accel.cpp:24-74,152-206): the initial cut */
+int nbvh_tree_cut_init(nbvh_ctx *ctx, uint32_t min_depth);
+/* == reinitialise_neural_bvh_learning_states (neural_bvh_renderer_accel.cpp:76-150) for the tree-cut already loaded */
+int nbvh_tree_cut_attach(nbvh_ctx *ctx);
+/* == update_neural_tree_cut_loss + (k+1) x update_neural_tree_cut_decisions + split_neural_bvh_at (neural_bvh_renderer.cu:199-268,
+ * neural_bvh_renderer_kernels.cu:202-287): per_sample_loss = ctx->L of the training step (stride x batch, first `dims` rows used).
+ * Writes m_max_node_loss_host and the number of leaves split. num_splits = BvhSplitScheduler::get_bvh_splits(step) (0: statistics only). */
+int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
+                       uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream);
+/* == assign_lod_to_current_neural_leaf_nodes (neural_bvh_renderer_accel.cpp:394-441) */
+int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned);
+/* device pointers for nbvh_optimisation_data_generation (tree_cut_data) and inspection; host copies for tests / save */
+const nbvh_tree_cut_data *nbvh_tree_cut_data_device(const nbvh_ctx *ctx);
+const nbvh_node32 *nbvh_neural_bvh_device(const nbvh_ctx *ctx);
+int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, uint32_t *node_map_host, uint32_t n);
+uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);
 

@@ -157,6 +157,14 @@ SYMBOLS = {
     "nbvh_set_gradient_buffer": (_i, [_vp, _vp]),
     "nbvh_optimizer_step": (_i, [_vp, _vp]),
     "nbvh_training_step_count": (_u32, [_vp]),
+    "nbvh_tree_cut_init": (_i, [_vp, _u32]),
+    "nbvh_tree_cut_attach": (_i, [_vp]),
+    "nbvh_tree_cut_step": (_i, [_vp, _vp, _u32, _u32, _vp, _u32, _u32, C.POINTER(_f), C.POINTER(_u32), _vp]),
+    "nbvh_tree_cut_assign_lod": (_i, [_vp, C.POINTER(_i)]),
+    "nbvh_tree_cut_data_device": (_vp, [_vp]),
+    "nbvh_neural_bvh_device": (_vp, [_vp]),
+    "nbvh_get_tree_cut_host": (_i, [_vp, _vp, _vp, _u32]),
+    "nbvh_tree_cut_max_depth": (_u32, [_vp]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include "kernels.cuh"
 #include "sampler.cuh"
 #include "path.cuh"
+#include "treecut.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -237,6 +238,15 @@ struct nbvh_ctx {
     // tree-cut
     float4 *d_nbvh = nullptr, *d_nbvh_dilated = nullptr;
     uint32_t nbvh_nodes = 0;
+    uint32_t nbvh_capacity = 0; // allocated nodes (tree-cut learning appends two nodes per split)
+    // tree-cut learning state (the reference keeps it in NeuralBVHRenderer: m_neural_tree_cut_data, m_neural_node_map)
+    nbvh_tree_cut_data *d_tree_cut = nullptr;
+    uint32_t *d_node_map = nullptr;       // tree-cut node -> node of the neural mesh's classical BLAS
+    void *d_tc_workspace = nullptr;
+    size_t tc_workspace_bytes = 0;
+    TreeCutResult *d_tc_result = nullptr;
+    bool tree_cut_ready = false;
+    uint32_t tree_cut_max_depth = 0;
     float dilated_with  = -1.f;
     bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
     bool blas_safe[kMaxBlas] = {};
@@ -588,6 +598,10 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
+    cudaFree(ctx->d_tree_cut);
+    cudaFree(ctx->d_node_map);
+    cudaFree(ctx->d_tc_workspace);
+    cudaFree(ctx->d_tc_result);
     cudaFree(ctx->d_bounce_counters);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->own_grads);
@@ -920,14 +934,19 @@ static int adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKi
 {
     if (n == 0)
         return fail(ctx, NBVH_ERR_INVALID_ARG, "empty neural BVH");
-    if (ctx->nbvh_nodes != n) {
+    if (ctx->nbvh_capacity < n) {
         cudaFree(ctx->d_nbvh);
         cudaFree(ctx->d_nbvh_dilated);
+        cudaFree(ctx->d_tree_cut), cudaFree(ctx->d_node_map); // node-indexed arrays share one capacity
+        ctx->d_tree_cut = nullptr, ctx->d_node_map = nullptr;
         ctx->d_nbvh = ctx->d_nbvh_dilated = nullptr;
+        ctx->nbvh_capacity = 0;
         CU_TRY(ctx, cudaMalloc(&ctx->d_nbvh, (size_t)n * 32));
         CU_TRY(ctx, cudaMalloc(&ctx->d_nbvh_dilated, (size_t)n * 32));
-        ctx->nbvh_nodes = n;
+        ctx->nbvh_capacity = n;
     }
+    ctx->nbvh_nodes     = n;
+    ctx->tree_cut_ready = false; // a new tree-cut invalidates the learning state (reinitialise_neural_bvh_learning_states)
     CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes, (size_t)n * 32, kind));
     ctx->dilated_with = -1.f;
     if (!ctx->scene_bbox_set) {
@@ -1620,6 +1639,242 @@ int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, u
     kt.stop();
     return NBVH_OK;
 }
+
+// ---- tree-cut learning ---------------------------------------------------------------------
+namespace {
+
+// grow the node-indexed arrays (nodes, dilated nodes, tree-cut data, node map) to `capacity`, keeping their contents
+int grow_tree_cut(nbvh_ctx *ctx, uint32_t capacity)
+{
+    if (capacity > ctx->nbvh_capacity || !ctx->d_tree_cut) {
+        const uint32_t cap = capacity > ctx->nbvh_capacity ? capacity : ctx->nbvh_capacity;
+        float4 *nodes = nullptr, *dil = nullptr;
+        nbvh_tree_cut_data *cut = nullptr;
+        uint32_t *map = nullptr;
+        CU_TRY(ctx, cudaMalloc(&nodes, (size_t)cap * 32));
+        CU_TRY(ctx, cudaMalloc(&dil, (size_t)cap * 32));
+        CU_TRY(ctx, cudaMalloc(&cut, (size_t)cap * sizeof(nbvh_tree_cut_data)));
+        CU_TRY(ctx, cudaMalloc(&map, (size_t)cap * 4));
+        if (ctx->d_nbvh)
+            CU_TRY(ctx, cudaMemcpy(nodes, ctx->d_nbvh, (size_t)ctx->nbvh_nodes * 32, cudaMemcpyDeviceToDevice));
+        if (ctx->d_tree_cut)
+            CU_TRY(ctx, cudaMemcpy(cut, ctx->d_tree_cut, (size_t)ctx->nbvh_nodes * sizeof(nbvh_tree_cut_data), cudaMemcpyDeviceToDevice));
+        if (ctx->d_node_map)
+            CU_TRY(ctx, cudaMemcpy(map, ctx->d_node_map, (size_t)ctx->nbvh_nodes * 4, cudaMemcpyDeviceToDevice));
+        cudaFree(ctx->d_nbvh), cudaFree(ctx->d_nbvh_dilated), cudaFree(ctx->d_tree_cut), cudaFree(ctx->d_node_map);
+        ctx->d_nbvh = nodes, ctx->d_nbvh_dilated = dil, ctx->d_tree_cut = cut, ctx->d_node_map = map;
+        ctx->nbvh_capacity = cap;
+        ctx->dilated_with  = -1.f;
+    }
+    const size_t need = tree_cut_workspace_bytes(ctx->nbvh_capacity);
+    if (need > ctx->tc_workspace_bytes) {
+        cudaFree(ctx->d_tc_workspace);
+        ctx->d_tc_workspace = nullptr, ctx->tc_workspace_bytes = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_tc_workspace, need));
+        ctx->tc_workspace_bytes = need;
+    }
+    if (!ctx->d_tc_result) {
+        CU_TRY(ctx, cudaMalloc(&ctx->d_tc_result, sizeof(TreeCutResult)));
+        CU_TRY(ctx, cudaMemset(ctx->d_tc_result, 0, sizeof(TreeCutResult)));
+    }
+    return NBVH_OK;
+}
+
+int neural_blas_nodes_host(nbvh_ctx *ctx, std::vector<nbvh_node32> &out)
+{
+    const uint32_t idx = ctx->bvh_const.neural_bvh_idx;
+    if (!ctx->scene_set || idx >= ctx->blas_desc.size() || ctx->blas_desc[idx].num_nodes < 1 || !ctx->blas_desc[idx].nodes)
+        return fail(ctx, NBVH_ERR_STATE, "tree-cut learning needs the classical BLAS of the neural mesh in the scene");
+    out.resize(ctx->blas_desc[idx].num_nodes);
+    CU_TRY(ctx, cudaMemcpy(out.data(), ctx->blas_desc[idx].nodes, out.size() * sizeof(nbvh_node32), cudaMemcpyDeviceToHost));
+    return NBVH_OK;
+}
+
+int upload_tree_cut_state(nbvh_ctx *ctx, const std::vector<nbvh_node32> &nodes, const std::vector<nbvh_tree_cut_data> &cut,
+                          const std::vector<uint32_t> &map, uint32_t max_depth)
+{
+    const uint32_t n = (uint32_t)nodes.size();
+    ctx->nbvh_nodes  = ctx->nbvh_nodes < n ? ctx->nbvh_nodes : n; // grow_tree_cut copies the first nbvh_nodes entries
+    int rc = grow_tree_cut(ctx, n > 4u ? n : 4u);
+    if (rc != NBVH_OK)
+        return rc;
+    CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes.data(), (size_t)n * 32, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_tree_cut, cut.data(), (size_t)n * sizeof(nbvh_tree_cut_data), cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_node_map, map.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    TreeCutResult r{0.f, 0u, max_depth, 0u};
+    CU_TRY(ctx, cudaMemcpy(ctx->d_tc_result, &r, sizeof(r), cudaMemcpyHostToDevice));
+    ctx->nbvh_nodes         = n;
+    ctx->tree_cut_max_depth = max_depth;
+    ctx->dilated_with       = -1.f;
+    ctx->tree_cut_ready     = true;
+    return refresh_dilated(ctx);
+}
+
+} // namespace
+
+// build_and_upload_neural_bvh + traverse_and_build_neural_bvh (neural_bvh_renderer_accel.cpp:24-74): the initial cut of the
+// neural mesh's BLAS at `min_depth` (neural_bvh_min_depth; 0 = the root alone), node numbering as the reference's recursion
+int nbvh_tree_cut_init(nbvh_ctx *ctx, uint32_t min_depth)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    std::vector<nbvh_node32> blas;
+    int rc = neural_blas_nodes_host(ctx, blas);
+    if (rc != NBVH_OK)
+        return rc;
+    const uint32_t first_lod = (uint32_t)ctx->bvh_const.current_learned_lod;
+    std::vector<nbvh_node32> nodes(1);
+    std::vector<nbvh_tree_cut_data> cut(1);
+    std::vector<uint32_t> map(1);
+    uint32_t max_depth = 0;
+    struct Item { uint32_t bvh, neural, depth; };
+    // the reference recurses left subtree first; an explicit stack that pushes right before left visits in the same order
+    std::vector<Item> stack{{0u, 0u, 0u}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const nbvh_node32 &b = blas[it.bvh];
+        map[it.neural]       = it.bvh;
+        nodes[it.neural]     = b;
+        cut[it.neural]       = nbvh_tree_cut_data{0.f, 1u, it.depth, 0u};
+        max_depth            = it.depth > max_depth ? it.depth : max_depth;
+        const bool blas_leaf = b.prim_count_or_left > 0u;
+        if (blas_leaf || it.depth == min_depth) {
+            nodes[it.neural].prim_count_or_left  = blas_leaf ? 1u : 2u + first_lod;
+            nodes[it.neural].left_or_prim_offset = 0xFFFFFFFFu;
+            continue;
+        }
+        const uint32_t left = (uint32_t)nodes.size();
+        nodes.resize(left + 2), cut.resize(left + 2), map.resize(left + 2);
+        nodes[it.neural].prim_count_or_left  = 0u;
+        nodes[it.neural].left_or_prim_offset = left;
+        stack.push_back({b.left_or_prim_offset + 1u, left + 1u, it.depth + 1u});
+        stack.push_back({b.left_or_prim_offset, left, it.depth + 1u});
+    }
+    // NOTE: the reference allocates the children of a node before descending, but descends depth-first, so the children of
+    // the LEFT subtree are numbered before those of the right one -- the stack order above reproduces exactly that.
+    memcpy(ctx->scene_bbox.min, blas[0].aabb_min, 12);
+    memcpy(ctx->scene_bbox.max, blas[0].aabb_max, 12);
+    return upload_tree_cut_state(ctx, nodes, cut, map, max_depth);
+}
+
+// reinitialise_neural_bvh_learning_states + traverse_neural_bvh_and_update_states (neural_bvh_renderer_accel.cpp:76-150):
+// learning state for the tree-cut already in the context (loaded from a .nbvh file): node map, depths, zeroed statistics
+int nbvh_tree_cut_attach(nbvh_ctx *ctx)
+{
+    if (!ctx || !ctx->d_nbvh)
+        return ctx ? fail(ctx, NBVH_ERR_STATE, "no neural BVH set") : NBVH_ERR_INVALID_ARG;
+    std::vector<nbvh_node32> blas;
+    int rc = neural_blas_nodes_host(ctx, blas);
+    if (rc != NBVH_OK)
+        return rc;
+    const uint32_t n = ctx->nbvh_nodes;
+    std::vector<nbvh_node32> nodes(n);
+    CU_TRY(ctx, cudaMemcpy(nodes.data(), ctx->d_nbvh, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    std::vector<nbvh_tree_cut_data> cut(n, nbvh_tree_cut_data{0.f, 1u, 0u, 0u});
+    std::vector<uint32_t> map(n, 0u);
+    uint32_t max_depth = 0;
+    struct Item { uint32_t bvh, neural, depth; };
+    std::vector<Item> stack{{0u, 0u, 0u}};
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        if (it.neural >= n || it.bvh >= blas.size())
+            return fail(ctx, NBVH_ERR_STATE, "the tree-cut is not a cut of the neural mesh's BLAS");
+        map[it.neural]       = it.bvh;
+        cut[it.neural].depth = it.depth;
+        max_depth            = it.depth > max_depth ? it.depth : max_depth;
+        if (nodes[it.neural].left_or_prim_offset == 0xFFFFFFFFu)
+            continue;
+        if (blas[it.bvh].prim_count_or_left > 0u)
+            return fail(ctx, NBVH_ERR_STATE, "the tree-cut is not a cut of the neural mesh's BLAS");
+        stack.push_back({blas[it.bvh].left_or_prim_offset + 1u, nodes[it.neural].left_or_prim_offset + 1u, it.depth + 1u});
+        stack.push_back({blas[it.bvh].left_or_prim_offset, nodes[it.neural].left_or_prim_offset, it.depth + 1u});
+    }
+    return upload_tree_cut_state(ctx, nodes, cut, map, max_depth);
+}
+
+const nbvh_tree_cut_data *nbvh_tree_cut_data_device(const nbvh_ctx *ctx) { return ctx && ctx->tree_cut_ready ? ctx->d_tree_cut : nullptr; }
+const nbvh_node32 *nbvh_neural_bvh_device(const nbvh_ctx *ctx) { return ctx ? reinterpret_cast<const nbvh_node32 *>(ctx->d_nbvh) : nullptr; }
+
+int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, uint32_t *node_map_host, uint32_t n)
+{
+    if (!ctx || !ctx->tree_cut_ready || n > ctx->nbvh_nodes)
+        return NBVH_ERR_INVALID_ARG;
+    if (cut_host && cudaMemcpy(cut_host, ctx->d_tree_cut, (size_t)n * sizeof(nbvh_tree_cut_data), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return NBVH_ERR_CUDA;
+    if (node_map_host && cudaMemcpy(node_map_host, ctx->d_node_map, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return NBVH_ERR_CUDA;
+    return NBVH_OK;
+}
+
+// The tree-cut part of one optimisation step (neural_bvh_renderer.cu:199-283): scatter the per-element losses of the batch
+// into the nodes' statistics, age the leaves, find the num_splits largest loss heuristics, split those leaves.
+int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
+                       uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream)
+{
+    if (!ctx || !per_sample_loss || !sampled_node_indices || dims > stride)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->tree_cut_ready)
+        return fail(ctx, NBVH_ERR_STATE, "tree-cut learning state missing: call nbvh_tree_cut_init or nbvh_tree_cut_attach");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n = ctx->nbvh_nodes;
+    // room for the splits of this step: m_neural_nodes_alloc_count doubles in the reference; here grow to what is needed, x2
+    const uint32_t limit = num_splits < (n + 1u) / 2u ? num_splits : (n + 1u) / 2u;
+    if (n + 2u * limit > ctx->nbvh_capacity) {
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        int rc = grow_tree_cut(ctx, 2u * (n + 2u * limit));
+        if (rc != NBVH_OK)
+            return rc;
+    } else if (tree_cut_workspace_bytes(ctx->nbvh_capacity) > ctx->tc_workspace_bytes) {
+        int rc = grow_tree_cut(ctx, ctx->nbvh_capacity);
+        if (rc != NBVH_OK)
+            return rc;
+    }
+    CU_TRY(ctx, launch_tree_cut_accumulate(per_sample_loss, stride, dims, sampled_node_indices, batch, ctx->d_tree_cut, st));
+    const uint32_t blas_idx = ctx->bvh_const.neural_bvh_idx;
+    CU_TRY(ctx, launch_tree_cut_decide_and_split(ctx->d_nbvh, n, ctx->nbvh_capacity, ctx->d_tree_cut, ctx->d_node_map,
+                                                 ctx->scene.blas[blas_idx].nodes, num_splits, (uint32_t)ctx->bvh_const.current_learned_lod,
+                                                 ctx->d_tc_workspace, ctx->tc_workspace_bytes, ctx->d_tc_result, st));
+    TreeCutResult r;
+    CU_TRY(ctx, cudaMemcpyAsync(&r, ctx->d_tc_result, sizeof(r), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (r.n_split) {
+        ctx->nbvh_nodes   = n + 2u * r.n_split;
+        ctx->dilated_with = -1.f; // the pre-dilated copy is rebuilt before the next traversal
+        int rc = refresh_dilated(ctx);
+        if (rc != NBVH_OK)
+            return rc;
+    }
+    ctx->tree_cut_max_depth = r.max_depth;
+    if (max_node_loss_host)
+        *max_node_loss_host = r.max_node_loss;
+    if (n_split_host)
+        *n_split_host = r.n_split;
+    return NBVH_OK;
+}
+
+// assign_lod_to_current_neural_leaf_nodes (neural_bvh_renderer_accel.cpp:394-441): tags the current leaves with the level
+// being learned and moves on to the next finer level.  Returns the new current_learned_lod through the constant block.
+int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned)
+{
+    if (!ctx || !ctx->d_nbvh)
+        return NBVH_ERR_INVALID_ARG;
+    const int level = ctx->bvh_const.current_learned_lod;
+    if (level < 0 || level >= 7)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "current_learned_lod out of range");
+    if (level != 6) // at the coarsest level the leaves already carry LEAF_LOD(6) (NUM_BVH_LODS - 1)
+        CU_TRY(ctx, launch_tree_cut_assign_lod(ctx->d_nbvh, ctx->nbvh_nodes, (uint32_t)level, 0));
+    const bool done = level == 0;
+    if (!done)
+        ctx->bvh_const.current_learned_lod--;
+    if (all_lods_assigned)
+        *all_lods_assigned = done ? 1 : 0;
+    ctx->dilated_with = -1.f;
+    return refresh_dilated(ctx);
+}
+
+uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx) { return ctx ? ctx->tree_cut_max_depth : 0; }
 
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                      uint8_t *ldr_host, nbvh_hit_record *hits_host)

@@ -21,9 +21,19 @@
 
 namespace nbvh {
 
-constexpr int kNeuralTiles   = 2;                        // 128-lane tiles per CTA
+#ifndef NBVH_NEURAL_TILES
+#define NBVH_NEURAL_TILES 2
+#endif
+#ifndef NBVH_NEURAL_CTAS_PER_SM
+#define NBVH_NEURAL_CTAS_PER_SM 2
+#endif
+#ifndef NBVH_WALK_ROUNDS
+#define NBVH_WALK_ROUNDS 2
+#endif
+constexpr int kNeuralTiles   = NBVH_NEURAL_TILES;        // 128-lane tiles per CTA
 constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
-constexpr int kWalkRounds    = 4;                        // refill/advance rounds before a tile runs the network
+constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
+constexpr int kWalkRounds    = NBVH_WALK_ROUNDS;         // refill/advance rounds before a tile runs the network
 
 // ------------------------------------------------------------------------------------------------ shared helpers
 // hybrid_scatter_and_get_next_tlas_traversal_step at ray_depth == max_depth (path_inference_kernels.cu:306-321)
@@ -153,7 +163,7 @@ __device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, 
 }
 
 template <bool kPath>
-__global__ void __launch_bounds__(kNeuralThreads, 2)
+__global__ void __launch_bounds__(kNeuralThreads, kNeuralCtasPerSm)
 k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetConst nc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -317,9 +327,9 @@ cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream)
 {
     if (path_mode)
-        k_neural<true><<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+        k_neural<true><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
     else
-        k_neural<false><<<(uint32_t)num_sms * 2u, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+        k_neural<false><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
     return cudaGetLastError();
 }
 

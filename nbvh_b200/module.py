@@ -38,7 +38,11 @@ def _torch():
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
+    if t is None:
+        return None
+    if isinstance(t, int):  # a raw device pointer (e.g. the context-owned tree-cut statistics)
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
 
 
 class NeuralPathModule:
@@ -367,6 +371,41 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_training_step(self._h, _ptr(inputs), _ptr(targets), n, _ptr(per_sample_loss),
                                                  C.byref(loss) if want_loss else None, stream))
         return loss.value if want_loss else None
+
+    # ------------------------------------------------------------------ tree-cut learning (NeuralBVHRenderer's part of a step)
+    def tree_cut_init(self, min_depth=0):
+        """== build_and_upload_neural_bvh(neural_bvh_min_depth): initial cut of the neural mesh's BLAS (0 = the root alone)."""
+        self._check(self._lib.nbvh_tree_cut_init(self._h, int(min_depth)))
+
+    def tree_cut_attach(self):
+        """== reinitialise_neural_bvh_learning_states for the tree-cut already loaded (node map, depths, zero statistics)."""
+        self._check(self._lib.nbvh_tree_cut_attach(self._h))
+
+    def tree_cut_step(self, per_sample_loss, sampled_node_indices, num_splits, dims=None, stream=None):
+        """== update_neural_tree_cut_loss + update_neural_tree_cut_decisions + split_neural_bvh_at.  per_sample_loss: (B, 16) float32
+        CUDA tensor (tcnn's ctx.L).  Returns (max_node_loss, leaves split)."""
+        batch, stride = int(per_sample_loss.shape[0]), int(per_sample_loss.shape[1])
+        mx, ns = C.c_float(0.0), C.c_uint32(0)
+        self._check(self._lib.nbvh_tree_cut_step(self._h, _ptr(per_sample_loss), stride, int(dims if dims is not None else self.network_output_dims()),
+                                                 _ptr(sampled_node_indices), batch, int(num_splits), C.byref(mx), C.byref(ns), stream))
+        return mx.value, ns.value
+
+    def tree_cut_assign_lod(self):
+        """== assign_lod_to_current_neural_leaf_nodes.  Returns True when all LoDs have been assigned."""
+        done = C.c_int(0)
+        self._check(self._lib.nbvh_tree_cut_assign_lod(self._h, C.byref(done)))
+        return bool(done.value)
+
+    def tree_cut_data_ptr(self):
+        return self._lib.nbvh_tree_cut_data_device(self._h)
+
+    def tree_cut_state(self):
+        """Host copies of (tree-cut nodes, NeuralTreeCutData, node map)."""
+        n = self._lib.nbvh_neural_bvh_num_nodes(self._h)
+        cut = np.zeros(n, dtype=TREE_CUT_DTYPE)
+        nmap = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.nbvh_get_tree_cut_host(self._h, cut.ctypes.data_as(C.c_void_p), nmap.ctypes.data_as(C.c_void_p), n))
+        return self.neural_bvh_nodes(), cut, nmap
 
     def training_step_count(self):
         return int(self._lib.nbvh_training_step_count(self._h))

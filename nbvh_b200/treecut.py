@@ -1,0 +1,114 @@
+"""Host-side schedule of the tree-cut learning: mirror of BvhSplitScheduler
+(/root/reference/include/cuda/neural/utils/bvh_split_scheduler.h:14-150) and of the renderer's per-step control flow
+(/root/reference/src/cuda/neural/neural_bvh_renderer.cu:140-290).  Pure integer logic: the device work is nbvh_tree_cut_step."""
+
+NUM_BVH_LODS = 7  # include/cuda/neural/accel/neural_bvh2.cuh:14
+
+
+class BvhSplitScheduler:
+    def __init__(self, splitting_interval=50, last_split_iteration=2000, start_split_num=1, split_scaling=2.0,
+                 split_interval_scaling=2.0, lod_decision_type="EqualIterations"):
+        self.splitting_interval = int(splitting_interval)
+        self.last_split_iteration = int(last_split_iteration)
+        self.start_split_num = int(start_split_num)
+        self.split_scaling = float(split_scaling)
+        self.split_interval_scaling = float(split_interval_scaling)
+        self.lod_decision_type = lod_decision_type
+        self.stats = dict(total_splits=0, num_cuts=0, expected_bvh_num_nodes=0, expected_bvh_depth=0)
+        self._reset()
+
+    @classmethod
+    def from_config(cls, cfg):
+        """bvh_split_scheduler block of the config JSON (neural_bvh_renderer_init.cu:712, from_json :139-148)."""
+        j = cfg.get("neural_bvh_renderer", {}).get("bvh_split_scheduler", {})
+        return cls(j.get("splitting_interval", 50), j.get("last_split_iteration", 2000), j.get("start_split_num", 1),
+                   j.get("split_scaling", 2.0), j.get("split_interval_scaling", 2.0))
+
+    def _reset(self):
+        self.current_num_splits = self.start_split_num
+        self.current_splitting_interval = self.splitting_interval
+        self.current_total_splits = 0
+
+    def get_bvh_splits(self, it):
+        """get_bvh_splits (:73-95): C++ `int *= float` truncates toward zero."""
+        if it == 0:
+            self._reset()
+        if it > self.last_split_iteration:
+            return 0
+        n = 0
+        if it % self.splitting_interval == 0:
+            n = self.current_num_splits
+            self.current_total_splits += n
+        if it % self.current_splitting_interval == 0:
+            self.current_num_splits = int(self.current_num_splits * self.split_scaling)
+            self.current_splitting_interval = int(self.current_splitting_interval * self.split_interval_scaling)
+        return n
+
+    def update_stats_and_reset(self, bvh_start_num_nodes, num_iterations):
+        """update_stats_and_reset (:38-71).  Returns the cumulative-splits graph."""
+        import math
+        self._reset()
+        st = dict(total_splits=0, num_cuts=0, expected_bvh_num_nodes=int(bvh_start_num_nodes), expected_bvh_depth=0)
+        graph = []
+        for i in range(num_iterations):
+            leaves = (st["expected_bvh_num_nodes"] + 1) // 2
+            s = self.get_bvh_splits(i)
+            if s > 0:
+                s = min(s, leaves)
+                st["total_splits"] += s
+                st["expected_bvh_num_nodes"] += 2 * s
+                st["num_cuts"] += 1
+            graph.append(float(st["total_splits"]))
+        st["expected_bvh_depth"] = int(math.log2(float(st["expected_bvh_num_nodes"]))) if st["expected_bvh_num_nodes"] > 0 else 0
+        self.stats = st
+        self._reset()
+        return graph
+
+    def should_assign_new_lod(self, it, current_learned_lod, num_lods_learned, max_bvh_lods=NUM_BVH_LODS):
+        """should_assign_new_lod (:97-125); integer arithmetic as in C++ (left-to-right, truncating division)."""
+        if self.lod_decision_type == "EqualIterations":
+            nxt = (max_bvh_lods - current_learned_lod) * self.last_split_iteration // num_lods_learned
+            assign = nxt <= it
+        else:
+            nxt = (max_bvh_lods - current_learned_lod) * self.stats["total_splits"] // num_lods_learned
+            assign = nxt <= self.current_total_splits
+        return assign or it >= self.last_split_iteration
+
+
+class TreeCutLearner:
+    """Per-step control flow of NeuralBVHRenderer's optimisation loop around one NeuralPathModule
+    (neural_bvh_renderer.cu:140-290): sample generation -> training step -> tree-cut statistics / split -> LoD assignment."""
+
+    def __init__(self, module, scheduler, batch_size, num_lods_learned=1, log2_bvh_max_traversals=0):
+        import torch
+        self.mod, self.sched = module, scheduler
+        self.batch = int(batch_size)
+        self.num_lods_learned = int(num_lods_learned)
+        self.log2_trav = int(log2_bvh_max_traversals)
+        dev = torch.device("cuda", module.device)
+        self.sampled = torch.zeros(self.batch, dtype=torch.int32, device=dev)
+        self.inputs = torch.zeros((self.batch, 9), dtype=torch.float32, device=dev)
+        self.targets = torch.zeros((self.batch, 8), dtype=torch.float32, device=dev)
+        self.L = torch.zeros((self.batch, 16), dtype=torch.float32, device=dev)
+        self.max_node_loss = 0.0
+        self.step_no = 0
+        self.tree_cut_learning = True
+        self.all_lods_assigned = False
+
+    def step(self, stream=None):
+        from ._capi import CONST_RENDERER
+        m = self.mod
+        current_max_loss = 0.0 if self.step_no == 0 else self.max_node_loss
+        m.optimisation_data_generation(self.step_no, self.batch, self.log2_trav, self.sampled, current_max_loss, m.tree_cut_data_ptr(),
+                                       self.inputs, self.targets, stream=stream)
+        n_splits = self.sched.get_bvh_splits(self.step_no) if self.tree_cut_learning else 0
+        loss = m.training_step(self.inputs, self.targets, per_sample_loss=self.L, want_loss=True, stream=stream)
+        self.max_node_loss, n_split = m.tree_cut_step(self.L, self.sampled, n_splits, stream=stream)
+        if self.tree_cut_learning and self.num_lods_learned > 1 and not self.all_lods_assigned:
+            lod = m.get_constants(CONST_RENDERER).current_learned_lod
+            if self.sched.should_assign_new_lod(self.step_no, lod, self.num_lods_learned):
+                self.all_lods_assigned = m.tree_cut_assign_lod()
+                if self.all_lods_assigned:
+                    self.tree_cut_learning = False
+        self.step_no += 1
+        return loss, n_split

@@ -490,6 +490,90 @@ def render_path(scene, nbvh_nodes, const, net, path, pixel_begin, pixel_end, str
     return rad, hits, [cnt[i] for i in range(5)]
 
 
+# ----------------------------------------------------------------------------- tree-cut learning (f2)
+TREE_CUT_DTYPE = np.dtype([("loss", "<f4"), ("iter_alive", "<u4"), ("depth", "<u4"), ("samples", "<u4")])
+NO_NEURAL_CHILD = 0xFFFFFFFF
+
+
+def tree_cut_initial(blas_nodes, min_depth, first_learned_lod):
+    """traverse_and_build_neural_bvh (neural_bvh_renderer_accel.cpp:24-74), recursive exactly as written there."""
+    import sys
+    nodes, cut, nmap = [None], [None], [None]
+
+    def rec(bi, ni, depth):
+        b = blas_nodes[bi]
+        nmap[ni] = bi
+        cut[ni] = (0.0, 1, depth, 0)
+        if b["a"] > 0 or depth == min_depth:
+            nodes[ni] = (b["mn"], 1 if b["a"] > 0 else 2 + first_learned_lod, b["mx"], NO_NEURAL_CHILD)
+            return
+        left = len(nodes)
+        nodes.extend([None, None]), cut.extend([None, None]), nmap.extend([None, None])
+        nodes[ni] = (b["mn"], 0, b["mx"], left)
+        rec(int(b["b"]), left, depth + 1)
+        rec(int(b["b"]) + 1, left + 1, depth + 1)
+
+    old = sys.getrecursionlimit()
+    sys.setrecursionlimit(10000)
+    rec(0, 0, 0)
+    sys.setrecursionlimit(old)
+    out = np.zeros(len(nodes), dtype=NODE_DTYPE)
+    for i, t in enumerate(nodes):
+        out[i] = t
+    return out, np.array(cut, dtype=TREE_CUT_DTYPE), np.array(nmap, dtype=np.uint32)
+
+
+def tree_cut_step(nodes, cut, nmap, blas_nodes, L, sampled, num_splits, current_learned_lod, dims=8):
+    """One step of the reference's tree-cut learning, restated sequentially (neural_bvh_renderer_kernels.cu:202-287,
+    neural_bvh_renderer.cu:199-268, neural_bvh_renderer_accel.cpp:256-392).  Loss sums in float64 then rounded (the reference's
+    float atomics are unordered).  Returns (nodes, cut, nmap, max_node_loss, n_split)."""
+    nodes, cut, nmap = nodes.copy(), cut.copy(), nmap.copy()
+    per_sample = L[:, :dims].astype(np.float64).sum(axis=1)
+    loss = cut["loss"].astype(np.float64)
+    np.add.at(loss, sampled, per_sample)
+    cut["loss"] = loss.astype(np.float32)
+    np.add.at(cut["samples"], sampled, np.uint32(dims))
+    leaf = nodes["b"] == NO_NEURAL_CHILD
+    cut["iter_alive"][leaf] += 1
+    cand = leaf & (nodes["a"] != 1) & (cut["samples"] > 0)
+    ia = cut["iter_alive"].astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        h = cut["loss"] / (ia * np.sqrt(cut["samples"].astype(np.float32) / ia))
+    h = np.where(cand, h, -np.inf).astype(np.float32)
+    pos = np.flatnonzero(h > 0)
+    order = pos[np.argsort(-h[pos], kind="stable")]
+    max_loss = float(h[order[0]]) if len(order) else 0.0
+    # distinct values, best first; at most min(k, #leaves) of them; then ascending node index (std::set)
+    vals, first = np.unique(-h[order], return_index=True)
+    chosen = order[np.sort(first)][: min(num_splits, (len(nodes) + 1) // 2)]
+    n_split = 0
+    new_nodes, new_cut, new_map = [], [], []
+    n = len(nodes)
+    for idx in np.sort(chosen):
+        b = blas_nodes[nmap[idx]]
+        if b["a"] > 0:
+            continue
+        left = n + 2 * n_split
+        if nodes["a"][idx] == 2 + current_learned_lod:
+            nodes["a"][idx] = 0
+        nodes["b"][idx] = left
+        nodes["mn"][idx], nodes["mx"][idx] = b["mn"], b["mx"]
+        for c in (0, 1):
+            ch = blas_nodes[int(b["b"]) + c]
+            new_nodes.append((ch["mn"], 1 if ch["a"] > 0 else 2 + current_learned_lod, ch["mx"], NO_NEURAL_CHILD))
+            new_cut.append((0.0, 1, cut["depth"][idx] + 1, 0))
+            new_map.append(int(b["b"]) + c)
+        n_split += 1
+    if n_split:
+        add = np.zeros(len(new_nodes), dtype=NODE_DTYPE)
+        for i, t in enumerate(new_nodes):
+            add[i] = t
+        nodes = np.concatenate([nodes, add])
+        cut = np.concatenate([cut, np.array(new_cut, dtype=TREE_CUT_DTYPE)])
+        nmap = np.concatenate([nmap, np.array(new_map, dtype=np.uint32)])
+    return nodes, cut, nmap, max_loss, n_split
+
+
 # ----------------------------------------------------------------------------- online optimisation
 LOSS_TYPES = ["RelativeL2", "L2", "RelativeL1", "L1", "RelativeL2Luminance", "BinaryCrossEntropy", "LogL2", "LHalf"]
 
