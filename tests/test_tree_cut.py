@@ -116,7 +116,7 @@ def test_gpu_tree_cut_steps_match_oracle(tc_env, oracle):
         assert (gc["samples"] == cut["samples"]).all() and (gc["iter_alive"] == cut["iter_alive"]).all()
         assert np.allclose(gc["loss"], cut["loss"], rtol=1e-5, atol=1e-6)
         assert abs(mx - rmx) <= 1e-5 * max(1.0, abs(rmx))
-    assert len(nodes) > 1000  # the cut grew well past the initial 7 nodes
+    assert len(nodes) > 150  # the cut grew well past the initial 7 nodes (each step splits at most half of the leaves)
     # inference still works on the grown cut, and agrees with the oracle walking the same nodes
     const = oracle.config_constants(tc_env["cfg"], nodes)
     o, d = mod.raygen(0, 4096)
