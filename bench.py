@@ -22,7 +22,9 @@ import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line (NCCL's version banner would go there too)
+# stdout carries exactly one JSON line: everything native libraries print (NCCL's version banner goes to fd 1) is sent to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 METRIC = "neural ray queries/sec (Mrays/s, 1080p Chess)"
 UNIT = "Mrays/s"
@@ -191,7 +193,7 @@ def sweep(args, rank, local_rank, world, dev):
                            "sharding": "each batch split evenly across the ranks, scene and weights replicated, no collective",
                            "l2": "256 MiB buffer written between timed repetitions", "scene_build_s": build_s},
                 "sweep": results, "api": "nbvh_trace_rays (C ABI)", "gpu_launches": 4 * reps}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -241,7 +243,7 @@ def main():
                 "config": {"workload": workload + " -- reference arm: CPU closest-hit traversal of the non-neural BLAS (BASELINE config 1)"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": info[1], "kind": info[2], "sample": info[3]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
         return 0
 
     import numpy as np
@@ -528,7 +530,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, cores, kind, sample, _, _ = cpu_reference_run(5, root, W, H)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
