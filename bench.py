@@ -444,10 +444,33 @@ def main():
     barrier()
     gen_ms = te0.elapsed_time(te1) / train_steps
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms], dtype=torch.float64, device=dev)
+    # strong scaling of the same step: the GLOBAL batch stays 2^18, every rank owns 2^18 / world slots
+    strong_ms = train_ms
+    if world > 1:
+        sB = train_B // world
+        sx, st_, sn = tx[:sB], tt[:sB], nodes_dev[:sB]
+
+        def strong_step():
+            mod.optimisation_data_generation(step_no[0] * world + rank, sB, 0, sn, 1.0, cut_dev, sx, st_, stream=stream.cuda_stream)
+            step_no[0] += 1
+            mod.training_forward_backward(sx, st_, global_batch=train_B, stream=stream.cuda_stream)
+            dist.all_reduce(grads)
+            mod.optimizer_step(stream=stream.cuda_stream)
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        te0.record(stream)
+        for _ in range(train_steps):
+            strong_step()
+        te1.record(stream)
+        barrier()
+        strong_ms = te0.elapsed_time(te1) / train_steps
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms, strong_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, train_ms = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_ms, train_ms, strong_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -517,6 +540,7 @@ def main():
             "train": {"metric": "train samples/s", "value": world * train_B / (train_ms * 1e-3), "unit": "samples/s",
                       "ms_per_step": train_ms, "batch_per_gpu": train_B, "steps": train_steps,
                       "sample_generation_ms": gen_ms,
+                      "strong_scaling": {"global_batch": train_B, "ms_per_step": strong_ms, "samples_s": train_B / (strong_ms * 1e-3)},
                       "what": "per step: sample generation on the Chess tree-cut + neural-mesh BLAS (K10, procedural materials), "
                               "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam" +
                               ("; fp32 gradient allreduce (NCCL) per step" if world > 1 else ""),

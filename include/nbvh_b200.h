@@ -404,6 +404,14 @@ int nbvh_tree_cut_attach(nbvh_ctx *ctx);
  * Writes m_max_node_loss_host and the number of leaves split. num_splits = BvhSplitScheduler::get_bvh_splits(step) (0: statistics only). */
 int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
                        uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream);
+/* Data-parallel form of nbvh_tree_cut_step (one process per GPU): nbvh_tree_cut_accumulate scatters the losses of this rank's batch
+ * shard into two caller-owned node-indexed delta arrays (nbvh_neural_bvh_num_nodes entries each, zeroed by the call); the host
+ * allreduces both (ncclAllReduce sum); nbvh_tree_cut_decide applies the sums and runs the deterministic decision + split, so every
+ * rank ends the step with the same tree-cut. */
+int nbvh_tree_cut_accumulate(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
+                             uint32_t batch, float *loss_delta, uint32_t *samples_delta, void *stream);
+int nbvh_tree_cut_decide(nbvh_ctx *ctx, const float *loss_delta, const uint32_t *samples_delta, uint32_t num_splits,
+                         float *max_node_loss_host, uint32_t *n_split_host, void *stream);
 /* == assign_lod_to_current_neural_leaf_nodes (neural_bvh_renderer_accel.cpp:394-441) */
 int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned);
 /* device pointers for nbvh_optimisation_data_generation (tree_cut_data) and inspection; host copies for tests / save */

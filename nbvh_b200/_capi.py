@@ -160,6 +160,8 @@ SYMBOLS = {
     "nbvh_tree_cut_init": (_i, [_vp, _u32]),
     "nbvh_tree_cut_attach": (_i, [_vp]),
     "nbvh_tree_cut_step": (_i, [_vp, _vp, _u32, _u32, _vp, _u32, _u32, C.POINTER(_f), C.POINTER(_u32), _vp]),
+    "nbvh_tree_cut_accumulate": (_i, [_vp, _vp, _u32, _u32, _vp, _u32, _vp, _vp, _vp]),
+    "nbvh_tree_cut_decide": (_i, [_vp, _vp, _vp, _u32, C.POINTER(_f), C.POINTER(_u32), _vp]),
     "nbvh_tree_cut_assign_lod": (_i, [_vp, C.POINTER(_i)]),
     "nbvh_tree_cut_data_device": (_vp, [_vp]),
     "nbvh_neural_bvh_device": (_vp, [_vp]),

@@ -1810,28 +1810,9 @@ int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, ui
 
 // The tree-cut part of one optimisation step (neural_bvh_renderer.cu:199-283): scatter the per-element losses of the batch
 // into the nodes' statistics, age the leaves, find the num_splits largest loss heuristics, split those leaves.
-int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
-                       uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream)
+static int tree_cut_decide(nbvh_ctx *ctx, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, cudaStream_t st)
 {
-    if (!ctx || !per_sample_loss || !sampled_node_indices || dims > stride)
-        return NBVH_ERR_INVALID_ARG;
-    if (!ctx->tree_cut_ready)
-        return fail(ctx, NBVH_ERR_STATE, "tree-cut learning state missing: call nbvh_tree_cut_init or nbvh_tree_cut_attach");
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t n = ctx->nbvh_nodes;
-    // room for the splits of this step: m_neural_nodes_alloc_count doubles in the reference; here grow to what is needed, x2
-    const uint32_t limit = num_splits < (n + 1u) / 2u ? num_splits : (n + 1u) / 2u;
-    if (n + 2u * limit > ctx->nbvh_capacity) {
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        int rc = grow_tree_cut(ctx, 2u * (n + 2u * limit));
-        if (rc != NBVH_OK)
-            return rc;
-    } else if (tree_cut_workspace_bytes(ctx->nbvh_capacity) > ctx->tc_workspace_bytes) {
-        int rc = grow_tree_cut(ctx, ctx->nbvh_capacity);
-        if (rc != NBVH_OK)
-            return rc;
-    }
-    CU_TRY(ctx, launch_tree_cut_accumulate(per_sample_loss, stride, dims, sampled_node_indices, batch, ctx->d_tree_cut, st));
+    const uint32_t n        = ctx->nbvh_nodes;
     const uint32_t blas_idx = ctx->bvh_const.neural_bvh_idx;
     CU_TRY(ctx, launch_tree_cut_decide_and_split(ctx->d_nbvh, n, ctx->nbvh_capacity, ctx->d_tree_cut, ctx->d_node_map,
                                                  ctx->scene.blas[blas_idx].nodes, num_splits, (uint32_t)ctx->bvh_const.current_learned_lod,
@@ -1852,6 +1833,63 @@ int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t str
     if (n_split_host)
         *n_split_host = r.n_split;
     return NBVH_OK;
+}
+
+// room for the splits of one step: m_neural_nodes_alloc_count doubles in the reference; here grow to what is needed, x2
+static int tree_cut_reserve(nbvh_ctx *ctx, uint32_t num_splits, cudaStream_t st)
+{
+    if (!ctx->tree_cut_ready)
+        return fail(ctx, NBVH_ERR_STATE, "tree-cut learning state missing: call nbvh_tree_cut_init or nbvh_tree_cut_attach");
+    const uint32_t n     = ctx->nbvh_nodes;
+    const uint32_t limit = num_splits < (n + 1u) / 2u ? num_splits : (n + 1u) / 2u;
+    if (n + 2u * limit > ctx->nbvh_capacity) {
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        return grow_tree_cut(ctx, 2u * (n + 2u * limit));
+    }
+    if (tree_cut_workspace_bytes(ctx->nbvh_capacity) > ctx->tc_workspace_bytes)
+        return grow_tree_cut(ctx, ctx->nbvh_capacity);
+    return NBVH_OK;
+}
+
+int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
+                       uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream)
+{
+    if (!ctx || !per_sample_loss || !sampled_node_indices || dims > stride)
+        return NBVH_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = tree_cut_reserve(ctx, num_splits, st);
+    if (rc != NBVH_OK)
+        return rc;
+    CU_TRY(ctx, launch_tree_cut_accumulate(per_sample_loss, stride, dims, sampled_node_indices, batch, ctx->d_tree_cut, st));
+    return tree_cut_decide(ctx, num_splits, max_node_loss_host, n_split_host, st);
+}
+
+// Data-parallel form of the same step: every rank scatters the losses of ITS batch shard into two node-indexed
+// delta arrays (caller-owned, num_nodes entries each), the host allreduces them (ncclAllReduce sum), and every rank applies the
+// summed deltas and runs the deterministic decision + split -> identical tree-cuts on all ranks.
+int nbvh_tree_cut_accumulate(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
+                             uint32_t batch, float *loss_delta, uint32_t *samples_delta, void *stream)
+{
+    if (!ctx || !per_sample_loss || !sampled_node_indices || !loss_delta || !samples_delta || dims > stride)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->tree_cut_ready)
+        return fail(ctx, NBVH_ERR_STATE, "tree-cut learning state missing: call nbvh_tree_cut_init or nbvh_tree_cut_attach");
+    CU_TRY(ctx, launch_tree_cut_accumulate_delta(per_sample_loss, stride, dims, sampled_node_indices, batch, ctx->nbvh_nodes, loss_delta,
+                                                 samples_delta, (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
+int nbvh_tree_cut_decide(nbvh_ctx *ctx, const float *loss_delta, const uint32_t *samples_delta, uint32_t num_splits, float *max_node_loss_host,
+                         uint32_t *n_split_host, void *stream)
+{
+    if (!ctx || !loss_delta || !samples_delta)
+        return NBVH_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = tree_cut_reserve(ctx, num_splits, st);
+    if (rc != NBVH_OK)
+        return rc;
+    CU_TRY(ctx, launch_tree_cut_apply_delta(ctx->d_tree_cut, ctx->nbvh_nodes, loss_delta, samples_delta, st));
+    return tree_cut_decide(ctx, num_splits, max_node_loss_host, n_split_host, st);
 }
 
 // assign_lod_to_current_neural_leaf_nodes (neural_bvh_renderer_accel.cpp:394-441): tags the current leaves with the level

@@ -39,6 +39,33 @@ __global__ void k_tc_accumulate(const float *__restrict__ L, uint32_t stride, ui
     atomicAdd(&nd->samples, dims); // the reference counts every loss element
 }
 
+// data-parallel variant: the batch shard's statistics go to delta arrays, which the host allreduces (NCCL) before they are applied
+__global__ void k_tc_accumulate_delta(const float *__restrict__ L, uint32_t stride, uint32_t dims, const uint32_t *__restrict__ sampled_nodes,
+                                      uint32_t batch, float *loss_delta, uint32_t *samples_delta)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch)
+        return;
+    float s = 0.f;
+    for (uint32_t c = 0; c < dims; ++c)
+        s += L[(size_t)i * stride + c];
+    const uint32_t node = sampled_nodes[i];
+    atomicAdd(loss_delta + node, s);
+    atomicAdd(samples_delta + node, dims);
+}
+
+__global__ void k_tc_apply_delta(nbvh_tree_cut_data *cut, uint32_t n, const float *__restrict__ loss_delta, const uint32_t *__restrict__ samples_delta)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t ds = samples_delta[i];
+    if (ds) {
+        cut[i].loss += loss_delta[i];
+        cut[i].samples += ds;
+    }
+}
+
 // update_neural_tree_cut_decisions, first pass: age the leaves, emit their loss heuristic as sort key
 __global__ void k_tc_candidates(const float4 *__restrict__ nodes, uint32_t n, nbvh_tree_cut_data *cut, float *keys, uint32_t *vals)
 {
@@ -152,6 +179,28 @@ cudaError_t launch_tree_cut_accumulate(const float *L, uint32_t stride, uint32_t
     if (batch == 0)
         return cudaSuccess;
     k_tc_accumulate<<<(batch + 255u) / 256u, 256, 0, stream>>>(L, stride, dims, sampled_nodes, batch, cut);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tree_cut_accumulate_delta(const float *L, uint32_t stride, uint32_t dims, const uint32_t *sampled_nodes, uint32_t batch,
+                                             uint32_t n_nodes, float *loss_delta, uint32_t *samples_delta, cudaStream_t stream)
+{
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(loss_delta, 0, (size_t)n_nodes * 4, stream)) != cudaSuccess)
+        return e;
+    if ((e = cudaMemsetAsync(samples_delta, 0, (size_t)n_nodes * 4, stream)) != cudaSuccess)
+        return e;
+    if (batch == 0)
+        return cudaSuccess;
+    k_tc_accumulate_delta<<<(batch + 255u) / 256u, 256, 0, stream>>>(L, stride, dims, sampled_nodes, batch, loss_delta, samples_delta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tree_cut_apply_delta(nbvh_tree_cut_data *cut, uint32_t n, const float *loss_delta, const uint32_t *samples_delta, cudaStream_t stream)
+{
+    if (n == 0)
+        return cudaSuccess;
+    k_tc_apply_delta<<<(n + 255u) / 256u, 256, 0, stream>>>(cut, n, loss_delta, samples_delta);
     return cudaGetLastError();
 }
 

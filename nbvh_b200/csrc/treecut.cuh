@@ -14,6 +14,9 @@ struct TreeCutResult {
 size_t tree_cut_workspace_bytes(uint32_t capacity);
 cudaError_t launch_tree_cut_accumulate(const float *L, uint32_t stride, uint32_t dims, const uint32_t *sampled_nodes, uint32_t batch,
                                        nbvh_tree_cut_data *cut, cudaStream_t stream);
+cudaError_t launch_tree_cut_accumulate_delta(const float *L, uint32_t stride, uint32_t dims, const uint32_t *sampled_nodes, uint32_t batch,
+                                             uint32_t n_nodes, float *loss_delta, uint32_t *samples_delta, cudaStream_t stream);
+cudaError_t launch_tree_cut_apply_delta(nbvh_tree_cut_data *cut, uint32_t n, const float *loss_delta, const uint32_t *samples_delta, cudaStream_t stream);
 cudaError_t launch_tree_cut_decide_and_split(float4 *nodes, uint32_t n, uint32_t capacity, nbvh_tree_cut_data *cut, uint32_t *node_map,
                                              const float4 *blas_nodes, uint32_t num_splits, uint32_t current_learned_lod, void *workspace,
                                              size_t workspace_bytes, TreeCutResult *result_dev, cudaStream_t stream);

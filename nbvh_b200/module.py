@@ -390,6 +390,24 @@ class NeuralPathModule:
                                                  _ptr(sampled_node_indices), batch, int(num_splits), C.byref(mx), C.byref(ns), stream))
         return mx.value, ns.value
 
+    def tree_cut_step_data_parallel(self, per_sample_loss, sampled_node_indices, num_splits, dims=None, group=None, stream=None):
+        """tree_cut_step for one process per GPU: per-rank statistics -> allreduce (NCCL) -> identical decisions and splits everywhere."""
+        import torch.distributed as dist
+        torch = _torch()
+        n = self._lib.nbvh_neural_bvh_num_nodes(self._h)
+        dev = per_sample_loss.device
+        loss_d = torch.empty(n, dtype=torch.float32, device=dev)
+        samp_d = torch.empty(n, dtype=torch.int32, device=dev)
+        batch, stride = int(per_sample_loss.shape[0]), int(per_sample_loss.shape[1])
+        self._check(self._lib.nbvh_tree_cut_accumulate(self._h, _ptr(per_sample_loss), stride, int(dims if dims is not None else self.network_output_dims()),
+                                                       _ptr(sampled_node_indices), batch, _ptr(loss_d), _ptr(samp_d), stream))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(loss_d, group=group)
+            dist.all_reduce(samp_d, group=group)
+        mx, ns = C.c_float(0.0), C.c_uint32(0)
+        self._check(self._lib.nbvh_tree_cut_decide(self._h, _ptr(loss_d), _ptr(samp_d), int(num_splits), C.byref(mx), C.byref(ns), stream))
+        return mx.value, ns.value
+
     def tree_cut_assign_lod(self):
         """== assign_lod_to_current_neural_leaf_nodes.  Returns True when all LoDs have been assigned."""
         done = C.c_int(0)

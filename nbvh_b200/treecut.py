@@ -79,8 +79,11 @@ class TreeCutLearner:
     """Per-step control flow of NeuralBVHRenderer's optimisation loop around one NeuralPathModule
     (neural_bvh_renderer.cu:140-290): sample generation -> training step -> tree-cut statistics / split -> LoD assignment."""
 
-    def __init__(self, module, scheduler, batch_size, num_lods_learned=1, log2_bvh_max_traversals=0):
+    def __init__(self, module, scheduler, batch_size, num_lods_learned=1, log2_bvh_max_traversals=0, rank=0, world=1):
+        """batch_size = slots of THIS rank; with world > 1 the ranks train data parallel: gradients and tree-cut statistics are
+        allreduced (torch.distributed must be initialised), weights and tree-cut stay identical on all ranks."""
         import torch
+        self.rank, self.world = int(rank), int(world)
         self.mod, self.sched = module, scheduler
         self.batch = int(batch_size)
         self.num_lods_learned = int(num_lods_learned)
@@ -99,11 +102,27 @@ class TreeCutLearner:
         from ._capi import CONST_RENDERER
         m = self.mod
         current_max_loss = 0.0 if self.step_no == 0 else self.max_node_loss
-        m.optimisation_data_generation(self.step_no, self.batch, self.log2_trav, self.sampled, current_max_loss, m.tree_cut_data_ptr(),
-                                       self.inputs, self.targets, stream=stream)
+        # the sampler's RNG is keyed by training_step * batch + slot: step * world + rank gives every rank its own global slots
+        m.optimisation_data_generation(self.step_no * self.world + self.rank, self.batch, self.log2_trav, self.sampled, current_max_loss,
+                                       m.tree_cut_data_ptr(), self.inputs, self.targets, stream=stream)
         n_splits = self.sched.get_bvh_splits(self.step_no) if self.tree_cut_learning else 0
-        loss = m.training_step(self.inputs, self.targets, per_sample_loss=self.L, want_loss=True, stream=stream)
-        self.max_node_loss, n_split = m.tree_cut_step(self.L, self.sampled, n_splits, stream=stream)
+        if self.world == 1:
+            loss = m.training_step(self.inputs, self.targets, per_sample_loss=self.L, want_loss=True, stream=stream)
+            self.max_node_loss, n_split = m.tree_cut_step(self.L, self.sampled, n_splits, stream=stream)
+        else:
+            import torch
+            import torch.distributed as dist
+            if not hasattr(self, "grads"):
+                self.grads = m.gradient_buffer()
+                self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.L.device)
+            self.loss_sum.zero_()
+            m.training_forward_backward(self.inputs, self.targets, global_batch=self.batch * self.world, per_sample_loss=self.L,
+                                        loss_sum=self.loss_sum, stream=stream)
+            dist.all_reduce(self.grads)
+            dist.all_reduce(self.loss_sum)
+            m.optimizer_step(stream=stream)
+            loss = float(self.loss_sum.item())
+            self.max_node_loss, n_split = m.tree_cut_step_data_parallel(self.L, self.sampled, n_splits, stream=stream)
         if self.tree_cut_learning and self.num_lods_learned > 1 and not self.all_lods_assigned:
             lod = m.get_constants(CONST_RENDERER).current_learned_lod
             if self.sched.should_assign_new_lod(self.step_no, lod, self.num_lods_learned):
