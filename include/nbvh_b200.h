@@ -336,6 +336,12 @@ int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, u
  * The RNG is keyed by the global pixel id, so the union of the shards is bit-identical to the full frame. */
 int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t shard_index,
                             uint32_t shard_count, void *stream);
+/* == compute_and_display_render_error + its mean (src/cuda/neural/neural_bvh_renderer_kernels.cu:91-160, neural_bvh_renderer.cu:346-358):
+ * error of the accumulated image (accum / accumulated_spp) against a device RGBA32F reference image of the framebuffer's size.
+ * mode = PostprocessMode (neural_bvh_renderer.h:83): 3 AbsError, 4 RelAbsError |d|/(ref+0.1), 5 MSEError, 6 RelMSEError d^2/(ref+0.1).
+ * write_error_image != 0 also writes the sRGB8 error image into the 8-bit framebuffer, as the reference's validation mode does. */
+int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, int mode, int write_error_image,
+                     float *mean_error_host, void *stream);
 /* End-to-end variant with HOST buffers: uploads `camera_host` (may be NULL), renders, copies the
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,

@@ -1914,6 +1914,27 @@ int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned)
 
 uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx) { return ctx ? ctx->tree_cut_max_depth : 0; }
 
+// == compute_and_display_render_error + the mean (neural_bvh_renderer.cu:346-358): error of the accumulated image (accum / spp)
+// against a reference RGBA32F image on the device.  mode = PostprocessMode: 3 AbsError, 4 RelAbsError, 5 MSEError, 6 RelMSEError.
+int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, int mode, int write_error_image,
+                     float *mean_error_host, void *stream)
+{
+    if (!ctx || !reference_rgba32f || !mean_error_host || mode < 3 || mode > 6 || accumulated_spp == 0)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->accum)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    const uint32_t n = ctx->fb_w * ctx->fb_h;
+    float *sum_dev   = reinterpret_cast<float *>(ctx->d_next_chunk + 5);
+    cudaStream_t st  = (cudaStream_t)stream;
+    CU_TRY(ctx, launch_image_error(ctx->accum, reinterpret_cast<const float4 *>(reference_rgba32f), n, accumulated_spp, mode, sum_dev,
+                                   write_error_image ? ctx->ldr : nullptr, st));
+    float sum = 0.f;
+    CU_TRY(ctx, cudaMemcpyAsync(&sum, sum_dev, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    *mean_error_host = sum / (float)n;
+    return NBVH_OK;
+}
+
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                      uint8_t *ldr_host, nbvh_hit_record *hits_host)
 {

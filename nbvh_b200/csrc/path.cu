@@ -306,6 +306,59 @@ cudaError_t launch_trace_rays(const RenderParams &rp_in, const NetConst &nc, con
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ image error metrics (f4)
+// compute_and_display_render_error (neural_bvh_renderer_kernels.cu:91-160) on linear memory: per-pixel error of accum / spp
+// against a reference RGBA32F image, block-reduced sum of the channel-mean error (the reference: one atomicAdd per pixel),
+// optional sRGB8 error image.  mode: 3 AbsError, 4 RelAbsError, 5 MSEError, 6 RelMSEError (PostprocessMode).
+__global__ void __launch_bounds__(256)
+k_image_error(const float4 *__restrict__ accum, const float4 *__restrict__ reference, uint32_t n, float inv_spp, int mode, float *sum, uchar4 *ldr)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float e = 0.f;
+    if (i < n) {
+        const float4 a = accum[i], r = reference[i];
+        const float c[3] = {a.x * inv_spp, a.y * inv_spp, a.z * inv_spp}, ref[3] = {r.x, r.y, r.z};
+        float err[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float d = ref[k] - c[k];
+            err[k] = mode == 3 ? fabsf(d) : mode == 4 ? fabsf(d) / (ref[k] + 0.1f) : mode == 5 ? d * d : d * d / (ref[k] + 0.1f);
+        }
+        e = (err[0] + err[1] + err[2]) / 3.f;
+        if (ldr) {
+            uchar4 px;
+            px.x = (unsigned char)min(max(int(linear_to_srgb(err[0]) * 256.0f), 0), 255);
+            px.y = (unsigned char)min(max(int(linear_to_srgb(err[1]) * 256.0f), 0), 255);
+            px.z = (unsigned char)min(max(int(linear_to_srgb(err[2]) * 256.0f), 0), 255);
+            px.w = 255;
+            ldr[i] = px;
+        }
+    }
+    __shared__ float s_part[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+    if ((threadIdx.x & 31u) == 0u)
+        s_part[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w)
+            t += s_part[w];
+        atomicAdd(sum, t);
+    }
+}
+
+cudaError_t launch_image_error(const float4 *accum, const float4 *reference, uint32_t n, uint32_t spp, int mode, float *sum_dev, uchar4 *ldr,
+                               cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(sum_dev, 0, sizeof(float), stream);
+    if (e != cudaSuccess || n == 0)
+        return e;
+    k_image_error<<<(n + 255u) / 256u, 256, 0, stream>>>(accum, reference, n, 1.f / (float)(spp ? spp : 1u), mode, sum_dev, ldr);
+    return cudaGetLastError();
+}
+
 // One frame of NeuralPathModule::neural_path_tracing.  `counters`: kPathCountersPerDepth zeroed words per depth
 // (neural queue count, queue cursor, length of the path list).  paths[2] / hits[2]: ping-pong path lists.
 cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,

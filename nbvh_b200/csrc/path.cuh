@@ -35,4 +35,7 @@ cudaError_t launch_render_path(const RenderParams &rp, const PathConst &pc, cons
 cudaError_t launch_trace_rays(const RenderParams &rp, const NetConst &nc, const float *o, const float *d, uint32_t n, uint32_t ray_depth,
                               PathState *paths, PathHit *hits, uint32_t *counters, nbvh_hit_record *out, int num_sms, cudaStream_t stream);
 
+cudaError_t launch_image_error(const float4 *accum, const float4 *reference, uint32_t n, uint32_t spp, int mode, float *sum_dev, uchar4 *ldr,
+                               cudaStream_t stream);
+
 } // namespace nbvh

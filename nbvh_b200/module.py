@@ -328,6 +328,15 @@ class NeuralPathModule:
         """neural_render restricted to an interleaved tile shard (every shard_count-th 8x4-pixel block): the multi-GPU partition."""
         self._check(self._lib.nbvh_render_interleaved(self._h, int(accumulated_spp), int(sample_offset), int(shard_index), int(shard_count), stream))
 
+    ERROR_MODES = {"AbsError": 3, "RelAbsError": 4, "MSEError": 5, "RelMSEError": 6}  # PostprocessMode, neural_bvh_renderer.h:83
+
+    def image_error(self, reference, accumulated_spp, mode="RelMSEError", write_error_image=False, stream=None):
+        """== compute_and_display_render_error: mean error of accum / spp against a (H, W, 4) float32 CUDA reference image."""
+        out = C.c_float(0.0)
+        self._check(self._lib.nbvh_image_error(self._h, _ptr(reference), int(accumulated_spp), self.ERROR_MODES[mode], int(write_error_image),
+                                               C.byref(out), stream))
+        return out.value
+
     def neural_render_host(self, accumulated_spp, sample_offset, ldr_host=None, hits_host=None, camera=None):
         """End-to-end call with HOST buffers (numpy arrays, ideally pinned)."""
         cam = C.byref(camera) if camera is not None else None

@@ -277,6 +277,12 @@ def test_gpu_path_image_matches_reference_path_tracer(chess_path, torch_cuda):
     en = relmse(imgn / spp, g["rgb_nspp"])
     print("relMSE vs the reference path tracer: 1 spp %.4g, %d spp %.4g; mean radiance %.5f vs %.5f" %
           (e1, spp, en, (imgn / spp).mean(), g["rgb_nspp"].mean()))
+    # the library's own metric kernel (compute_and_display_render_error) agrees with the numpy definition
+    ref4 = torch_cuda.from_numpy(np.concatenate([g["rgb_nspp"], np.ones((H, W, 1), np.float32)], axis=-1)).cuda().contiguous()
+    for mode, fn in (("RelMSEError", lambda x, r: np.square(r - x) / (r + 0.1)), ("MSEError", lambda x, r: np.square(r - x)),
+                     ("AbsError", lambda x, r: np.abs(r - x)), ("RelAbsError", lambda x, r: np.abs(r - x) / (r + 0.1))):
+        dev_err = mod.image_error(ref4, spp, mode)
+        assert abs(dev_err - float(fn(imgn / spp, g["rgb_nspp"]).mean())) <= 1e-4 * max(1e-3, dev_err), mode
     assert e1 <= RELMSE_1SPP and en <= RELMSE_NSPP
     assert abs((imgn / spp).mean() - g["rgb_nspp"].mean()) <= MEAN_TOL * g["rgb_nspp"].mean()
     if "rgb_converged" in g:
