@@ -128,9 +128,22 @@ def sweep(args, rank, local_rank, world, dev):
     import torch.distributed as dist
     import nbvh_b200
     t0 = time.time()
-    cfg, nbvh, tlas, tlas_idx, blas, info = nbvh_b200.synthetic_instanced_scene(device=dev)
+    cfg, nbvh, tlas, tlas_idx, blas, info = nbvh_b200.synthetic_instanced_scene(device=dev, return_mesh=(rank == 0))
     build_s = time.time() - t0
     mod = nbvh_b200.NeuralPathModule(cfg, device=local_rank)
+    blas_build = None
+    if rank == 0:  # device LBVH build of the full 10 M-triangle classical BLAS (nbvh_build_blas): the host stage it replaces takes seconds
+        try:
+            mv, mi = info.pop("mesh_vertices"), info.pop("mesh_indices")
+            mod.build_blas(mv, mi)
+            torch.cuda.synchronize()
+            tb = time.time()
+            _, _, depth = mod.build_blas(mv, mi)
+            torch.cuda.synchronize()
+            blas_build = {"triangles": int(mi.shape[0]), "ms": (time.time() - tb) * 1e3, "tree_depth": depth}
+            del mv, mi
+        except Exception as ex:  # a tree deeper than the traversal stack is refused
+            blas_build = {"error": str(ex)}
     mod.set_neural_bvh(nbvh)
     mod.set_scene(tlas, tlas_idx, blas)
     rng = np.random.default_rng(1337)
@@ -192,7 +205,7 @@ def sweep(args, rank, local_rank, world, dev):
                                           info["neural_leaves"], info["triangles_per_leaf_min"], info["triangles_per_leaf_max"]),
                            "sharding": "each batch split evenly across the ranks, scene and weights replicated, no collective",
                            "l2": "256 MiB buffer written between timed repetitions", "scene_build_s": build_s},
-                "sweep": results, "api": "nbvh_trace_rays (C ABI)", "gpu_launches": 4 * reps}
+                "sweep": results, "blas_build": blas_build, "api": "nbvh_trace_rays (C ABI)", "gpu_launches": 4 * reps}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

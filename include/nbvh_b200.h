@@ -342,6 +342,13 @@ int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
  * write_error_image != 0 also writes the sRGB8 error image into the 8-bit framebuffer, as the reference's validation mode does. */
 int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, int mode, int write_error_image,
                      float *mean_error_host, void *stream);
+/* Device-side BLAS build: an LBVH (27-bit Morton codes, Karras hierarchy, bottom-up fit) over n_tris triangles, written in the
+ * reference's BVH2Node layout (include/base/accel/bvh.h:66-71; children adjacent, root 0, one triangle per leaf) into caller-owned
+ * device arrays: nodes_out[2 * n_tris - 1], prim_indices_out[n_tris] (size_t, as CudaBVH2::prim_indices).  Stands in for the host
+ * ext/bvh build of CudaBackend (src/cuda/cuda_backend.cpp:186-385) when the ext/bvh tree itself is not needed (shipped .nbvh files
+ * are cuts of that tree).  max_depth_host receives the tree depth; trees deeper than the 32-entry traversal stack are refused. */
+int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indices, uint32_t n_tris, nbvh_node32 *nodes_out,
+                    uint64_t *prim_indices_out, uint32_t *max_depth_host, void *stream);
 /* End-to-end variant with HOST buffers: uploads `camera_host` (may be NULL), renders, copies the
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,

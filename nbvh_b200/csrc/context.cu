@@ -1935,6 +1935,37 @@ int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t acc
     return NBVH_OK;
 }
 
+// Device-side BLAS build (f3): LBVH over n_tris triangles into caller-owned arrays: nodes_out (2 * n_tris - 1 BVH2Node records),
+// prim_indices_out (n_tris size_t entries).  Replaces the host ext/bvh build of CudaBackend (cuda_backend.cpp:186-385) for scenes
+// that do not need the ext/bvh tree (shipped .nbvh files are cuts of that tree).  The traversal kernels keep a 32-entry stack
+// like the reference (bvh2.cuh:13-88): a tree deeper than that is refused.
+int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indices, uint32_t n_tris, nbvh_node32 *nodes_out,
+                    uint64_t *prim_indices_out, uint32_t *max_depth_host, void *stream)
+{
+    if (!ctx || !vertices || !indices || !nodes_out || !prim_indices_out || n_tris == 0 || n_tris > (1u << 30))
+        return NBVH_ERR_INVALID_ARG;
+    cudaStream_t st    = (cudaStream_t)stream;
+    const size_t bytes = build_blas_workspace_bytes(n_tris);
+    void *ws           = nullptr;
+    CU_TRY(ctx, cudaMalloc(&ws, bytes));
+    uint32_t *depth_dev = ctx->d_next_chunk + 6;
+    cudaError_t e = launch_build_blas(vertices, indices, n_tris, reinterpret_cast<float4 *>(nodes_out),
+                                      reinterpret_cast<unsigned long long *>(prim_indices_out), ws, bytes, depth_dev, st);
+    uint32_t depth = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&depth, depth_dev, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(ws);
+    if (e != cudaSuccess)
+        return fail(ctx, NBVH_ERR_CUDA, std::string("nbvh_build_blas: ") + cudaGetErrorString(e));
+    if (max_depth_host)
+        *max_depth_host = depth;
+    if (depth > (uint32_t)kBlasStackSize)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_build_blas: tree deeper than the traversal stack (32)");
+    return NBVH_OK;
+}
+
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                      uint8_t *ldr_host, nbvh_hit_record *hits_host)
 {

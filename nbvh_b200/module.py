@@ -328,6 +328,17 @@ class NeuralPathModule:
         """neural_render restricted to an interleaved tile shard (every shard_count-th 8x4-pixel block): the multi-GPU partition."""
         self._check(self._lib.nbvh_render_interleaved(self._h, int(accumulated_spp), int(sample_offset), int(shard_index), int(shard_count), stream))
 
+    def build_blas(self, vertices, indices, stream=None):
+        """Device LBVH build (== CudaBackend's per-mesh BLAS build, on the GPU).  vertices: (V, 3) float32, indices: (T, 3) int32 CUDA
+        tensors.  Returns (nodes uint8 tensor of 2T-1 32-byte records, prim_indices int64 tensor [T], tree depth)."""
+        torch = _torch()
+        n = int(indices.shape[0])
+        nodes = torch.empty((2 * n - 1) * 32, dtype=torch.uint8, device=vertices.device)
+        prims = torch.empty(n, dtype=torch.int64, device=vertices.device)
+        depth = C.c_uint32(0)
+        self._check(self._lib.nbvh_build_blas(self._h, _ptr(vertices), _ptr(indices), n, _ptr(nodes), _ptr(prims), C.byref(depth), stream))
+        return nodes, prims, depth.value
+
     ERROR_MODES = {"AbsError": 3, "RelAbsError": 4, "MSEError": 5, "RelMSEError": 6}  # PostprocessMode, neural_bvh_renderer.h:83
 
     def image_error(self, reference, accumulated_spp, mode="RelMSEError", write_error_image=False, stream=None):

@@ -293,7 +293,8 @@ def _icosphere(subdiv):
     return v, f  # (vertices are duplicated along shared edges: irrelevant for bounds)
 
 
-def synthetic_instanced_scene(lattice=(12, 13, 13), subdiv=4, cut_depth=17, seed=1234, log2_hashmap=18, fb=(1920, 1080), device=None):
+def synthetic_instanced_scene(lattice=(12, 13, 13), subdiv=4, cut_depth=17, seed=1234, log2_hashmap=18, fb=(1920, 1080), device=None,
+                              return_mesh=False):
     """BASELINE.json configs[4]: K = prod(lattice) instances of a displaced, subdivided icosphere "piece" (20 * 4^subdiv triangles
     each; defaults: 2,028 x 5,120 = 10.38 M triangles) on a jittered 3-D lattice inside the unit cube, pre-transformed and
     flattened into ONE neural mesh (the reference supports exactly one, scene.cpp:225-251); std::mt19937-free: numpy PCG64
@@ -374,6 +375,12 @@ def synthetic_instanced_scene(lattice=(12, 13, 13), subdiv=4, cut_depth=17, seed
     }
     info = dict(triangles=int(N), instances=K, triangles_per_instance=int(F), nbvh_nodes=int(n_nodes), neural_leaves=1 << cut_depth,
                 triangles_per_leaf_min=int(leaf_count.min()), triangles_per_leaf_max=int(leaf_count.max()))
+    if return_mesh:  # the flattened neural mesh itself (device tensors): (K * Vp, 3) float32 vertices, (K * F, 3) int32 indices
+        pv = torch.from_numpy(piece).to(dev)
+        Vp = pv.shape[0]
+        info["mesh_vertices"] = (pv[None] * r_t[:, None, None] + c_t[:, None, :]).reshape(-1, 3).contiguous()
+        info["mesh_indices"] = (torch.from_numpy(bf.astype(np.int32)).to(dev)[None] +
+                                (torch.arange(K, device=dev, dtype=torch.int32) * Vp)[:, None, None]).reshape(-1, 3).contiguous()
     return cfg, nbvh, tlas, tlas_idx, [stub], info
 
 

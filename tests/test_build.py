@@ -1,0 +1,94 @@
+"""Device-side BLAS build (nbvh_build_blas): an LBVH in the reference's BVH2Node layout.
+
+  * structure: 2n-1 nodes, children adjacent, every interior box is exactly the union of its children's boxes, every leaf holds
+    one triangle and encloses it, every triangle appears once, depth within the 32-entry traversal stack
+  * function: closest hits through the built tree are bit-identical (t, u, v) to the closest hits through the median-split BVH
+    of the same mesh (same triangle test on the same triangles: only the visiting order differs), on the GPU and in the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def validate_tree(nodes, prims, verts, tris):
+    n = len(tris)
+    assert len(nodes) == 2 * n - 1 and len(prims) == n
+    assert sorted(prims.tolist()) == list(range(n))
+    interior = nodes["a"] == 0
+    assert interior.sum() == n - 1 and (nodes["a"][~interior] == 1).all()
+    left = nodes["b"][interior].astype(np.int64)
+    assert (left >= 1).all() and (left + 1 < len(nodes)).all()
+    kids = np.concatenate([left, left + 1])
+    assert len(np.unique(kids)) == 2 * (n - 1) and 0 not in kids  # every non-root node has exactly one parent
+    assert (nodes["mn"][interior] == np.minimum(nodes["mn"][left], nodes["mn"][left + 1])).all()
+    assert (nodes["mx"][interior] == np.maximum(nodes["mx"][left], nodes["mx"][left + 1])).all()
+    leaf_tri = prims[nodes["b"][~interior]]
+    tv = verts[tris[leaf_tri]]
+    assert (nodes["mn"][~interior] <= tv.min(axis=1)).all() and (nodes["mx"][~interior] >= tv.max(axis=1)).all()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_gpu_lbvh_structure_and_closest_hits(oracle, synthetic, which):
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, nbvh, tlas, tlas_idx, blas = synthetic
+    mesh = blas[which]
+    verts = np.asarray(mesh["vertices"], np.float32).reshape(-1, 3)
+    tris = np.asarray(mesh["indices"], np.uint32).reshape(-1, 3)
+    mod = nbvh_b200.NeuralPathModule(cfg)
+    nodes_t, prims_t, depth = mod.build_blas(torch.from_numpy(verts).cuda(), torch.from_numpy(tris.astype(np.int32)).cuda())
+    nodes = nodes_t.cpu().numpy().view(nbvh_b200.NODE_DTYPE)
+    prims = prims_t.cpu().numpy().astype(np.uint32)
+    assert 0 < depth <= 32
+    validate_tree(nodes, prims, verts, tris)
+    # closest hits through the built tree vs through the median-split tree of the same mesh
+    built = dict(nodes=nodes, prim_ids=prims, vertices=mesh["vertices"], indices=mesh["indices"])
+    blas2 = list(blas)
+    blas2[which] = built
+    rng = np.random.default_rng(4)
+    n = 20000
+    lo, hi = verts.min(axis=0), verts.max(axis=0)
+    o = (lo + (hi - lo) * rng.uniform(-0.5, 1.5, (n, 3))).astype(np.float32)
+    tgt = (lo + (hi - lo) * rng.uniform(0, 1, (n, 3))).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    res = []
+    for b in (blas, blas2):
+        mod.set_neural_bvh(nbvh)
+        mod.set_scene(tlas, tlas_idx, b)
+        t, u, v, prim = mod.blas_intersect(which, torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda())
+        res.append((t.cpu().numpy(), u.cpu().numpy(), v.cpu().numpy(), prim.cpu().numpy()))
+    (t0, u0, v0, p0), (t1, u1, v1, p1) = res
+    assert (t0 < 3e38).sum() > n // 10
+    assert (t0.view(np.uint32) == t1.view(np.uint32)).all()
+    same_prim = p0 == p1
+    assert same_prim.mean() > 0.999  # exact ties between two triangles may resolve to either one
+    assert (u0.view(np.uint32)[same_prim] == u1.view(np.uint32)[same_prim]).all()
+    # the CPU oracle walks the built tree to the same hits
+    sc = oracle.Scene(tlas, tlas_idx, blas2)
+    tc, uc, vc, pc, _ = oracle.blas_intersect(sc, which, o[:4000], d[:4000])
+    assert (tc.view(np.uint32) == t1[:4000].view(np.uint32)).all() and (pc == p1[:4000]).all()
+    mod.close()
+
+
+def test_gpu_lbvh_degenerate_inputs(synthetic):
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    mod = nbvh_b200.NeuralPathModule(synthetic[0])
+    # one triangle; two identical triangles; a flat grid of coincident centroids
+    v = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=torch.float32, device="cuda")
+    for tris in ([[0, 1, 2]], [[0, 1, 2], [0, 1, 2]], [[0, 1, 2]] * 37):
+        idx = torch.tensor(tris, dtype=torch.int32, device="cuda")
+        nodes_t, prims_t, depth = mod.build_blas(v, idx)
+        nodes = nodes_t.cpu().numpy().view(nbvh_b200.NODE_DTYPE)
+        prims = prims_t.cpu().numpy().astype(np.uint32)
+        if len(tris) == 1:
+            assert nodes["a"][0] == 1 and nodes["b"][0] == 0 and depth == 0
+        else:
+            validate_tree(nodes, prims, v.cpu().numpy(), np.asarray(tris, np.uint32))
+            assert depth <= 8
+    mod.close()
