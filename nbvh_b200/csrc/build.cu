@@ -64,17 +64,25 @@ __global__ void k_tri_bounds(const float *__restrict__ vertices, const uint32_t 
         tri_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
         tri_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
     }
-    // warp reduction, one atomic set per warp
+    // warp + block reduction, one atomic set per block
+    __shared__ float s_lo[8][3], s_hi[8][3];
     for (int a = 0; a < 3; ++a) {
         for (int o = 16; o > 0; o >>= 1) {
             lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
         }
+        if ((threadIdx.x & 31u) == 0u)
+            s_lo[threadIdx.x >> 5][a] = lo[a], s_hi[threadIdx.x >> 5][a] = hi[a];
     }
-    if ((threadIdx.x & 31u) == 0u && lo[0] <= hi[0]) {
-        for (int a = 0; a < 3; ++a) {
-            atomic_min_float(scene + a, lo[a]);
-            atomic_max_float(scene + 3 + a, hi[a]);
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int a = threadIdx.x;
+        float l = s_lo[0][a], h = s_hi[0][a];
+        for (int w = 1; w < 8; ++w)
+            l = fminf(l, s_lo[w][a]), h = fmaxf(h, s_hi[w][a]);
+        if (l <= h) {
+            atomic_min_float(scene + a, l);
+            atomic_max_float(scene + 3 + a, h);
         }
     }
 }

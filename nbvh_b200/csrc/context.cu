@@ -242,6 +242,8 @@ struct nbvh_ctx {
     // tree-cut learning state (the reference keeps it in NeuralBVHRenderer: m_neural_tree_cut_data, m_neural_node_map)
     nbvh_tree_cut_data *d_tree_cut = nullptr;
     uint32_t *d_node_map = nullptr;       // tree-cut node -> node of the neural mesh's classical BLAS
+    void *d_build_ws = nullptr; // nbvh_build_blas scratch (grow-only)
+    size_t build_ws_bytes = 0;
     void *d_tc_workspace = nullptr;
     size_t tc_workspace_bytes = 0;
     TreeCutResult *d_tc_result = nullptr;
@@ -598,6 +600,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
+    cudaFree(ctx->d_build_ws);
     cudaFree(ctx->d_tree_cut);
     cudaFree(ctx->d_node_map);
     cudaFree(ctx->d_tc_workspace);
@@ -1946,8 +1949,13 @@ int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indice
         return NBVH_ERR_INVALID_ARG;
     cudaStream_t st    = (cudaStream_t)stream;
     const size_t bytes = build_blas_workspace_bytes(n_tris);
-    void *ws           = nullptr;
-    CU_TRY(ctx, cudaMalloc(&ws, bytes));
+    if (ctx->build_ws_bytes < bytes) { // grow-only scratch: cudaMalloc / cudaFree of ~60 B per triangle cost far more than the build
+        cudaFree(ctx->d_build_ws);
+        ctx->d_build_ws = nullptr, ctx->build_ws_bytes = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_build_ws, bytes));
+        ctx->build_ws_bytes = bytes;
+    }
+    void *ws            = ctx->d_build_ws;
     uint32_t *depth_dev = ctx->d_next_chunk + 6;
     cudaError_t e = launch_build_blas(vertices, indices, n_tris, reinterpret_cast<float4 *>(nodes_out),
                                       reinterpret_cast<unsigned long long *>(prim_indices_out), ws, bytes, depth_dev, st);
@@ -1956,7 +1964,6 @@ int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indice
         e = cudaMemcpyAsync(&depth, depth_dev, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
         e = cudaStreamSynchronize(st);
-    cudaFree(ws);
     if (e != cudaSuccess)
         return fail(ctx, NBVH_ERR_CUDA, std::string("nbvh_build_blas: ") + cudaGetErrorString(e));
     if (max_depth_host)

@@ -69,7 +69,7 @@ def test_gpu_lbvh_structure_and_closest_hits(oracle, synthetic, which):
     # the CPU oracle walks the built tree to the same hits
     sc = oracle.Scene(tlas, tlas_idx, blas2)
     tc, uc, vc, pc, _ = oracle.blas_intersect(sc, which, o[:4000], d[:4000])
-    assert (tc.view(np.uint32) == t1[:4000].view(np.uint32)).all() and (pc == p1[:4000]).all()
+    assert (tc.view(np.uint32) == t1[:4000].view(np.uint32)).all() and (pc.astype(np.uint32) == p1[:4000].astype(np.uint32)).all()
     mod.close()
 
 
