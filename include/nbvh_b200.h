@@ -353,6 +353,12 @@ int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indice
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
                      const nbvh_camera_params *camera_host, uint8_t *ldr_rgba8_host, nbvh_hit_record *hits_host);
+/* Frames in flight: nbvh_render_host split into submit and wait (two frame buffers, a render and a copy stream), so that the
+ * device-to-host copy of one frame overlaps the kernels of the next.  ldr_rgba8_host must be pinned; slot in {0, 1}; wait for a
+ * slot before reusing it (and before reading its host buffer). */
+int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
+                            uint8_t *ldr_rgba8_host, uint32_t slot);
+int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot);
 /* device self-test of the hoisted IEEE division used by the slab tests (csrc/device_core.cuh): compares n_trials random
  * quotients inside the documented operand range against div.rn and returns the number of differing bit patterns */
 int nbvh_selftest_division(nbvh_ctx *ctx, uint64_t seed, uint64_t n_trials, uint64_t *mismatches_host);

@@ -139,6 +139,8 @@ SYMBOLS = {
     "nbvh_trace_rays": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "nbvh_render_interleaved": (_i, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_build_blas": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u32), _vp]),
+    "nbvh_render_host_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _u32]),
+    "nbvh_render_host_wait": (_i, [_vp, _u32]),
     "nbvh_image_error": (_i, [_vp, _vp, _u32, _i, _i, C.POINTER(_f), _vp]),
     "nbvh_render_host": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_selftest_division": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),

@@ -242,6 +242,11 @@ struct nbvh_ctx {
     // tree-cut learning state (the reference keeps it in NeuralBVHRenderer: m_neural_tree_cut_data, m_neural_node_map)
     nbvh_tree_cut_data *d_tree_cut = nullptr;
     uint32_t *d_node_map = nullptr;       // tree-cut node -> node of the neural mesh's classical BLAS
+    // frames in flight (nbvh_render_host_submit / _wait): two 8-bit frame buffers, a render and a copy stream
+    uchar4 *d_ldr_slot[2] = {nullptr, nullptr};
+    size_t ldr_slot_pixels = 0;
+    cudaStream_t pipe_render = nullptr, pipe_copy = nullptr;
+    cudaEvent_t pipe_rendered[2] = {nullptr, nullptr}, pipe_copied[2] = {nullptr, nullptr};
     void *d_build_ws = nullptr; // nbvh_build_blas scratch (grow-only)
     size_t build_ws_bytes = 0;
     void *d_tc_workspace = nullptr;
@@ -601,6 +606,17 @@ void nbvh_destroy(nbvh_ctx *ctx)
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
     cudaFree(ctx->d_build_ws);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(ctx->d_ldr_slot[k]);
+        if (ctx->pipe_rendered[k])
+            cudaEventDestroy(ctx->pipe_rendered[k]);
+        if (ctx->pipe_copied[k])
+            cudaEventDestroy(ctx->pipe_copied[k]);
+    }
+    if (ctx->pipe_render)
+        cudaStreamDestroy(ctx->pipe_render);
+    if (ctx->pipe_copy)
+        cudaStreamDestroy(ctx->pipe_copy);
     cudaFree(ctx->d_tree_cut);
     cudaFree(ctx->d_node_map);
     cudaFree(ctx->d_tc_workspace);
@@ -1994,6 +2010,59 @@ int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_of
     if (hits_host)
         CU_TRY(ctx, cudaMemcpyAsync(hits_host, ctx->hits, n * sizeof(nbvh_hit_record), cudaMemcpyDeviceToHost, 0));
     CU_TRY(ctx, cudaStreamSynchronize(0));
+    return NBVH_OK;
+}
+
+// Frames in flight: the same work as nbvh_render_host, split into submit and wait so that the device-to-host copy of frame i
+// overlaps the kernels of frame i + 1 (two frame buffers, a render stream and a copy stream, events in between).  ldr_host
+// must be pinned memory for the copy to be asynchronous.  slot in {0, 1}; a slot must be waited for before it is reused.
+int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
+                            uint8_t *ldr_host, uint32_t slot)
+{
+    if (!ctx || !ldr_host || slot > 1u)
+        return NBVH_ERR_INVALID_ARG;
+    const size_t n = (size_t)ctx->fb_w * ctx->fb_h;
+    if (n == 0)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    if (!ctx->pipe_render) {
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render, cudaStreamNonBlocking));
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_rendered[k], cudaEventDisableTiming));
+            CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_copied[k], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->ldr_slot_pixels != n) {
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        for (int k = 0; k < 2; k++) {
+            cudaFree(ctx->d_ldr_slot[k]);
+            ctx->d_ldr_slot[k] = nullptr;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_ldr_slot[k], n * sizeof(uchar4)));
+        }
+        ctx->ldr_slot_pixels = n;
+    }
+    if (camera_host)
+        ctx->camera = *camera_host;
+    // the slot's previous copy must have drained before the kernels overwrite its frame buffer
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_render, ctx->pipe_copied[slot], 0));
+    uchar4 *saved = ctx->ldr;
+    ctx->ldr      = ctx->d_ldr_slot[slot];
+    const int rc  = nbvh_render(ctx, accumulated_spp, sample_offset, 0, 0, ctx->pipe_render);
+    ctx->ldr      = saved;
+    if (rc != NBVH_OK)
+        return rc;
+    CU_TRY(ctx, cudaEventRecord(ctx->pipe_rendered[slot], ctx->pipe_render));
+    CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_rendered[slot], 0));
+    CU_TRY(ctx, cudaMemcpyAsync(ldr_host, ctx->d_ldr_slot[slot], n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->pipe_copy));
+    CU_TRY(ctx, cudaEventRecord(ctx->pipe_copied[slot], ctx->pipe_copy));
+    return NBVH_OK;
+}
+
+int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot)
+{
+    if (!ctx || slot > 1u || !ctx->pipe_copied[slot])
+        return NBVH_ERR_INVALID_ARG;
+    CU_TRY(ctx, cudaEventSynchronize(ctx->pipe_copied[slot]));
     return NBVH_OK;
 }
 

@@ -355,6 +355,16 @@ class NeuralPathModule:
         hp = hits_host.ctypes.data_as(C.c_void_p) if hits_host is not None else None
         self._check(self._lib.nbvh_render_host(self._h, int(accumulated_spp), int(sample_offset), cam, lp, hp))
 
+    def neural_render_host_submit(self, accumulated_spp, sample_offset, ldr_host, slot, camera=None):
+        """Frames in flight: like neural_render_host, but returns once the work is queued; ldr_host (pinned numpy array) is valid
+        after neural_render_host_wait(slot).  Two slots: the copy of one frame overlaps the kernels of the next."""
+        cam = C.byref(camera) if camera is not None else None
+        self._check(self._lib.nbvh_render_host_submit(self._h, int(accumulated_spp), int(sample_offset), cam,
+                                                      ldr_host.ctypes.data_as(C.c_void_p), int(slot)))
+
+    def neural_render_host_wait(self, slot):
+        self._check(self._lib.nbvh_render_host_wait(self._h, int(slot)))
+
     # ------------------------------------------------------------------ online optimisation
     def gradient_buffer(self):
         """fp32 gradient vector (n_params) owned by torch and registered with the library: NCCL allreduces it in place."""

@@ -263,3 +263,28 @@ def test_hoisted_division_is_ieee(syn):
     operand range every quotient must carry the same bits as div.rn: 2^28 random + boundary-mantissa pairs on the device."""
     assert syn["mod"].selftest_division(1 << 28, seed=12345) == 0
     assert syn["mod"].selftest_division(1 << 24, seed=777) == 0
+
+
+def test_pipelined_host_render_equals_synchronous(syn, torch_cuda):
+    """nbvh_render_host_submit / _wait (two frames in flight) returns the same frames as the blocking nbvh_render_host."""
+    mod = syn["mod"]
+    W, H = syn["const"].fb_w, syn["const"].fb_h
+    mod.reinitialise_inference_data((W, H))
+    n = W * H
+    ref = []
+    for s in range(4):
+        buf = np.zeros(n * 4, np.uint8)
+        mod.neural_render_host(0, s, ldr_host=buf)
+        ref.append(buf.copy())
+    bufs = [torch_cuda.empty(n * 4, dtype=torch_cuda.uint8, pin_memory=True).numpy() for _ in range(2)]
+    got = []
+    for s in range(4):
+        if s >= 2:
+            mod.neural_render_host_wait(s & 1)
+            got.append(bufs[s & 1].copy())
+        mod.neural_render_host_submit(0, s, bufs[s & 1], s & 1)
+    for s in (0, 1):
+        mod.neural_render_host_wait(s)
+        got.append(bufs[s].copy())
+    for a, b in zip(ref, got):
+        assert (a == b).all()
