@@ -552,6 +552,7 @@ def main():
                        "l2": "256 MiB buffer written between timed steps (outside the event intervals)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n_rays * 4,
                     "api": "nbvh_render_host_submit / _wait (C ABI), two frames in flight: camera constants in, sRGB8 frame out, pinned host memory",
+                    "note": "back-to-back frames (no L2 flush between them, unlike `value`): the copy is hidden behind the next frame's kernels",
                     "synchronous_value": world * n_rays * args.steps / (e2e_sync_ms * 1e-3) / 1e6,
                     "synchronous_api": "nbvh_render_host (one blocking call per frame, the reference's calling pattern)"},
             "gpu_launches": 2 * args.steps,

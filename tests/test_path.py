@@ -208,6 +208,56 @@ def test_gpu_path_matches_oracle_synthetic(syn_path, oracle, torch_cuda, max_dep
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["ignore_neural_blas", "force_constant_material", "dielectric", "anisotropic", "skylike_no_rr"])
+def test_gpu_path_shading_branches_match_oracle(oracle, synthetic, torch_cuda, variant):
+    """The remaining branches of the shading kernel against the oracle: the non-neural rendering of the neural mesh
+    (ignore_neural_blas: its classical BLAS, unpack_albedo + the module's constant specular parameters), force_constant_material,
+    a fully transmissive material (dielectric lobe), an anisotropic + sheen material, sky-like background without roulette."""
+    import nbvh_b200
+    from nbvh_b200 import _capi as A
+    inputs = synthetic_path_inputs(synthetic)
+    cfg, nbvh, tlas, tlas_idx, blas, mats, textures, env = inputs
+    cfg = json.loads(json.dumps(cfg))
+    mats = mats.copy()
+    sc = cfg["cuda_scene"]["scene_constants"]
+    if variant == "ignore_neural_blas":
+        cfg["neural_bvh_renderer"]["bvh_constants"]["ignore_neural_blas"] = True
+    elif variant == "force_constant_material":
+        sc.update(force_constant_material=True, constant_metallic=0.3, constant_roughness=0.6, constant_specular=0.4)
+    elif variant == "dielectric":
+        mats["specular_transmission"][:] = 1.0
+        mats["ior"][:] = 1.45
+    elif variant == "anisotropic":
+        mats["anisotropy"][:] = 0.7
+        mats["sheen"][:] = 0.5
+        mats["sheen_tint"][:] = 0.3
+        mats["specular_tint"][:] = 0.4
+        mats["roughness"][1] = 0.25
+    elif variant == "skylike_no_rr":
+        sc.update(skylike_background=True)
+        cfg["neural_bvh_renderer"]["neural_module"]["path_module_constants"]["apply_russian_roulette"] = False
+    inputs = (cfg, nbvh, tlas, tlas_idx, blas, mats, textures, env)
+    mod = nbvh_b200.NeuralPathModule(cfg)
+    mod.set_neural_bvh(nbvh)
+    mod.set_scene(tlas, tlas_idx, blas, materials=mats, textures=textures)
+    mod.set_envmap(env)
+    params = spread_params(mod.n_params(), N_MLP, 11)
+    mod.load_params(params)
+    mod.max_depth = 3
+    assert bool(mod.get_constants(A.CONST_RENDERER).ignore_neural_blas) == (variant == "ignore_neural_blas")
+    W, H = cfg["cuda_scene"]["fb_size"]
+    img, _ = gpu_render(mod, torch_cuda, W, H)
+    rad, hits, _ = oracle_synthetic(oracle, inputs, params, max_depth=3)
+    rad = rad.reshape(H, W, 3)
+    m = pixel_match(img, rad)
+    print("%s: %.4f of the pixels agree with the oracle" % (variant, m))
+    assert np.isfinite(img).all() and m >= PIXEL_MATCH
+    if variant == "ignore_neural_blas":
+        assert (hits["valid_hit"] != 1).all() and (hits["valid_hit"] == 2).sum() > 1000
+    mod.close()
+
+
+@pytest.mark.gpu
 def test_gpu_path_primary_hits_equal_single_bounce_pipeline(syn_path, torch_cuda):
     import nbvh_b200
     mod, W, H = syn_path["mod"], syn_path["W"], syn_path["H"]
