@@ -349,6 +349,12 @@ int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t acc
  * are cuts of that tree).  max_depth_host receives the tree depth; trees deeper than the 32-entry traversal stack are refused. */
 int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indices, uint32_t n_tris, nbvh_node32 *nodes_out,
                     uint64_t *prim_indices_out, uint32_t *max_depth_host, void *stream);
+/* n_spp samples per pixel (first_spp .. first_spp + n_spp - 1) of an interleaved shard in ONE launch sequence (max_depth > 1): the
+ * path lists hold pixels x n_spp slots, which keeps the persistent kernels full on small shards (8-GPU tile partitions) and small
+ * frames.  Samples of a pixel accumulate with 16-byte reductions, so the fp32 sum order differs from calling nbvh_render once per
+ * sample; the 8-bit frame is resolved at the end.  first_spp == 0 clears the shard's accumulation first. */
+int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint32_t sample_offset, uint32_t shard_index,
+                        uint32_t shard_count, void *stream);
 /* End-to-end variant with HOST buffers: uploads `camera_host` (may be NULL), renders, copies the
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,

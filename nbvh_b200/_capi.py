@@ -137,6 +137,7 @@ SYMBOLS = {
     "nbvh_encode_segments": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp]),
     "nbvh_render": (_i, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_trace_rays": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "nbvh_render_samples": (_i, [_vp, _u32, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_render_interleaved": (_i, [_vp, _u32, _u32, _u32, _u32, _vp]),
     "nbvh_build_blas": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u32), _vp]),
     "nbvh_render_host_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _u32]),

@@ -1457,7 +1457,7 @@ int nbvh_destroy_textures(nbvh_ctx *ctx)
 }
 
 static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
-                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream);
+                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream, uint32_t spp_count = 1u);
 
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
                 void *stream)
@@ -1480,8 +1480,35 @@ int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
     return render_impl(ctx, accumulated_spp, sample_offset, 0u, mine * 32u, shard_count, shard_index, stream);
 }
 
+// Several samples per pixel in ONE launch sequence (multi-bounce mode): n_spp samples starting at first_spp for the interleaved
+// shard (shard_count 1 = the whole frame).  The path lists hold pixels x n_spp slots, so small shards / frames still fill the
+// persistent kernels; samples of a pixel accumulate with 16-byte reductions (fp32 sum order differs from sample-by-sample
+// accumulation), the 8-bit frame is resolved once at the end.  first_spp == 0 clears the shard's accumulation first.
+int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint32_t sample_offset, uint32_t shard_index,
+                        uint32_t shard_count, void *stream)
+{
+    if (!ctx || shard_count == 0 || shard_index >= shard_count || n_spp == 0)
+        return NBVH_ERR_INVALID_ARG;
+    if (n_spp == 1u)
+        return nbvh_render_interleaved(ctx, first_spp, sample_offset, shard_index, shard_count, stream);
+    if (ctx->max_depth < 2)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_render_samples: multi-sample launches exist for max_depth > 1 (the path lists)");
+    if (ctx->scene_const.ema_accumulate)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_render_samples: ema_accumulate needs sample-by-sample accumulation");
+    const uint32_t total = ctx->fb_w * ctx->fb_h;
+    if ((total & 31u) != 0u)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "multi-sample launches need a pixel count that is a multiple of 32");
+    const uint32_t n_chunks = total >> 5;
+    const uint32_t mine     = n_chunks / shard_count + (shard_index < n_chunks % shard_count ? 1u : 0u);
+    if (mine == 0u)
+        return NBVH_OK;
+    if ((uint64_t)mine * 32u * n_spp > 0x7FFFFFFFull)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_render_samples: pixels x samples exceeds 2^31 path slots");
+    return render_impl(ctx, first_spp, sample_offset, 0u, mine * 32u, shard_count, shard_index, stream, n_spp);
+}
+
 static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
-                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream)
+                       uint32_t chunk_stride, uint32_t chunk_offset, void *stream, uint32_t spp_count)
 {
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
@@ -1529,12 +1556,14 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     }
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
     rp.chunk_stride = chunk_stride, rp.chunk_offset = chunk_offset;
+    rp.spp_count     = spp_count;
     rp.next_chunk    = ctx->d_next_chunk;
-    if (ctx->queue_capacity < (size_t)total) {
+    const size_t slots = spp_count > 1u ? (size_t)pixel_count * spp_count : (size_t)total; // path / queue slots this launch may use
+    if (ctx->queue_capacity < slots) {
         cudaFree(ctx->d_queue);
         ctx->d_queue = nullptr, ctx->queue_capacity = 0;
-        CU_TRY(ctx, cudaMalloc(&ctx->d_queue, (size_t)total * sizeof(NeuralQueueEntry)));
-        ctx->queue_capacity = total;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_queue, slots * sizeof(NeuralQueueEntry)));
+        ctx->queue_capacity = slots;
     }
     rp.queue = ctx->d_queue, rp.queue_count = ctx->d_next_chunk + 1, rp.queue_cursor = ctx->d_next_chunk + 2;
     rp.sample_idx    = (int)accumulated_spp;
@@ -1548,15 +1577,15 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     KernelTimer kt(ctx, st);
     if (ctx->max_depth > 1) {
         // hybrid neural path tracing (path.cu): shading + re-queue per bounce, no host synchronisation
-        if (ctx->path_capacity < (size_t)total) {
+        if (ctx->path_capacity < slots) {
             ctx->path_capacity = 0;
             for (int k = 0; k < 2; k++) {
                 cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
                 ctx->d_paths[k] = nullptr, ctx->d_path_hits[k] = nullptr;
-                CU_TRY(ctx, cudaMalloc(&ctx->d_paths[k], (size_t)total * sizeof(PathState)));
-                CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits[k], (size_t)total * sizeof(PathHit)));
+                CU_TRY(ctx, cudaMalloc(&ctx->d_paths[k], slots * sizeof(PathState)));
+                CU_TRY(ctx, cudaMalloc(&ctx->d_path_hits[k], slots * sizeof(PathHit)));
             }
-            ctx->path_capacity = total;
+            ctx->path_capacity = slots;
         }
         const size_t counter_bytes = kPathCountersPerDepth * (kMaxPathDepth + 1) * sizeof(uint32_t);
         if (!ctx->d_bounce_counters)

@@ -66,6 +66,7 @@ struct RenderParams {
     BackgroundConst bg; // radiance of rays that escape
     // work distribution
     uint32_t first_pixel, pixel_count; // shard of the frame rendered by this launch
+    uint32_t spp_count; // samples per launch (multi-sample path launches: slot = sample * pixel_count + pixel slot; 0/1 = one)
     uint32_t chunk_stride, chunk_offset; // interleaved shard: every chunk_stride-th 32-pixel chunk from chunk_offset (0/1 = contiguous)
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
     NeuralQueueEntry *queue;            // neural ray queue filled by k_primary, drained by k_neural

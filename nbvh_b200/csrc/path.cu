@@ -104,7 +104,7 @@ k_path_shade(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
 {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t i    = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_in = io.count_in ? *io.count_in : p.pixel_count;
+    const uint32_t n_in = io.count_in ? *io.count_in : p.pixel_count * (p.spp_count > 1u ? p.spp_count : 1u);
     if (i - lane >= n_in)
         return; // whole warp beyond the list
     bool alive = false;
@@ -147,7 +147,8 @@ k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t sidx  = chunk * 32u + lane;
-    const uint32_t n_in  = kFirst ? p.pixel_count : *io.count_in;
+    const uint32_t n_spp = p.spp_count > 1u ? p.spp_count : 1u;
+    const uint32_t n_in  = kFirst ? p.pixel_count * n_spp : *io.count_in;
     if (chunk * 32u >= n_in)
         return;
     const bool active = sidx < n_in;
@@ -157,8 +158,11 @@ k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
     if (active) {
         if constexpr (kFirst) {
             uint32_t rng;
-            pixel = swizzle_pixel(p, p.first_pixel + sidx);
-            ray   = camera_ray(p.cam, pixel, p.sample_idx, p.sample_offset, rng);
+            // multi-sample launch: slot = sample * pixel_count + pixel slot (pixel_count is a multiple of 32, so a warp stays in
+            // one sample and on one 8x4-pixel block)
+            const uint32_t smp = sidx / p.pixel_count, local = sidx - smp * p.pixel_count;
+            pixel = swizzle_pixel(p, p.first_pixel + local);
+            ray   = camera_ray(p.cam, pixel, p.sample_idx + (int)smp, p.sample_offset, rng);
             PathState st;
             st.s0 = make_float4(ray.ox, ray.oy, ray.oz, ray.dx);
             st.s1 = make_float4(ray.dy, ray.dz, 1.f, 1.f);
@@ -359,6 +363,31 @@ cudaError_t launch_image_error(const float4 *accum, const float4 *reference, uin
     return cudaGetLastError();
 }
 
+// 8-bit frame of the shard's pixels after a multi-sample launch sequence: sRGB(accum / samples), as accumulate_pixel_value writes it
+__global__ void __launch_bounds__(256)
+k_resolve_ldr(const __grid_constant__ RenderParams p, float inv_samples)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.pixel_count)
+        return;
+    const uint32_t pixel = swizzle_pixel(p, p.first_pixel + i);
+    const float4 a = p.accum[pixel];
+    uchar4 px;
+    px.x = (unsigned char)min(max(int(linear_to_srgb(a.x * inv_samples) * 256.0f), 0), 255);
+    px.y = (unsigned char)min(max(int(linear_to_srgb(a.y * inv_samples) * 256.0f), 0), 255);
+    px.z = (unsigned char)min(max(int(linear_to_srgb(a.z * inv_samples) * 256.0f), 0), 255);
+    px.w = 255;
+    p.ldr[pixel] = px;
+}
+
+__global__ void __launch_bounds__(256)
+k_clear_accum(const __grid_constant__ RenderParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.pixel_count)
+        p.accum[swizzle_pixel(p, p.first_pixel + i)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // One frame of NeuralPathModule::neural_path_tracing.  `counters`: kPathCountersPerDepth zeroed words per depth
 // (neural queue count, queue cursor, length of the path list).  paths[2] / hits[2]: ping-pong path lists.
 cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,
@@ -367,8 +396,11 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
     if (rp_in.pixel_count == 0)
         return cudaSuccess;
     RenderParams rp       = rp_in;
-    const uint32_t blocks = ((rp.pixel_count + 31u) / 32u + 7u) / 8u;
+    const uint32_t slots  = rp.pixel_count * (rp.spp_count > 1u ? rp.spp_count : 1u);
+    const uint32_t blocks = ((slots + 31u) / 32u + 7u) / 8u;
     cudaError_t e;
+    if (rp.spp_count > 1u && rp.sample_idx == 0) // sample 0 overwrites the accumulation (accumulate_pixel_value); here: clear, then reduce
+        k_clear_accum<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp);
     for (uint32_t depth = 1; depth <= rp.max_depth; ++depth) {
         uint32_t *c     = counters + kPathCountersPerDepth * (depth - 1u);
         const int cur   = (int)((depth - 1u) & 1u);
@@ -391,6 +423,11 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
         if ((e = launch_neural(rp, nc, num_sms, true, stream)) != cudaSuccess)
             return e;
         k_path_shade<<<blocks, 256, 0, stream>>>(rp, pc, io);
+        if ((e = cudaGetLastError()) != cudaSuccess)
+            return e;
+    }
+    if (rp.spp_count > 1u && rp.ldr) {
+        k_resolve_ldr<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp, 1.f / (float)(rp.sample_idx + (int)rp.spp_count));
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }

@@ -85,6 +85,12 @@ __device__ __forceinline__ float linear_to_srgb(float x)
 
 __device__ __forceinline__ void splat(const RenderParams &p, uint32_t pixel, float r, float g, float b, float alpha)
 {
+    if (p.spp_count > 1u) {
+        // several samples of one pixel are in flight in the same launch: accumulate with one 16-byte reduction
+        // (RED.E.ADD.F32x4); the 8-bit frame is resolved by k_resolve_ldr when the launch sequence is complete
+        atomicAdd(p.accum + pixel, make_float4(r, g, b, alpha));
+        return;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.sample_idx > 0)
         acc = p.accum[pixel];

@@ -348,6 +348,11 @@ class NeuralPathModule:
                                                C.byref(out), stream))
         return out.value
 
+    def neural_render_samples(self, first_spp, n_spp, sample_offset=0, shard_index=0, shard_count=1, stream=None):
+        """n_spp samples per pixel of an interleaved shard in one launch sequence (max_depth > 1): keeps the persistent kernels full."""
+        self._check(self._lib.nbvh_render_samples(self._h, int(first_spp), int(n_spp), int(sample_offset), int(shard_index), int(shard_count),
+                                                  stream))
+
     def neural_render_host(self, accumulated_spp, sample_offset, ldr_host=None, hits_host=None, camera=None):
         """End-to-end call with HOST buffers (numpy arrays, ideally pinned)."""
         cam = C.byref(camera) if camera is not None else None

@@ -306,6 +306,28 @@ def test_gpu_interleaved_tile_shards_reproduce_full_frame(syn_path, torch_cuda, 
     assert (ldr.cpu().numpy() == ldr_full).all()
 
 
+@pytest.mark.gpu
+def test_gpu_multi_sample_launch_equals_sample_by_sample(syn_path, torch_cuda):
+    """nbvh_render_samples: 5 samples per pixel in one launch sequence (and 3 + 2 over two shards) == five nbvh_render calls, up
+    to the fp32 order of the per-pixel sum (16-byte reductions instead of read-modify-write)."""
+    mod, W, H = syn_path["mod"], syn_path["W"], syn_path["H"]
+    mod.max_depth = 3
+    ref, ldr_ref = gpu_render(mod, torch_cuda, W, H, spp=5)
+    accum, ldr = mod.attach_framebuffer((W, H))
+    mod.neural_render_samples(0, 5)
+    torch_cuda.cuda.synchronize()
+    a = accum.cpu().numpy()[..., :3]
+    assert np.allclose(a, ref, rtol=2e-5, atol=1e-6)
+    assert np.abs(ldr.cpu().numpy().astype(int) - ldr_ref.astype(int)).max() <= 1
+    accum, ldr = mod.attach_framebuffer((W, H))
+    for shard in (1, 0):
+        mod.neural_render_samples(0, 3, 0, shard, 2)
+        mod.neural_render_samples(3, 2, 0, shard, 2)
+    torch_cuda.cuda.synchronize()
+    assert np.allclose(accum.cpu().numpy()[..., :3], ref, rtol=2e-5, atol=1e-6)
+    assert np.abs(ldr.cpu().numpy().astype(int) - ldr_ref.astype(int)).max() <= 1
+
+
 @pytest.fixture(scope="module")
 def chess_path(torch_cuda, oracle, chess_root):
     import nbvh_b200
