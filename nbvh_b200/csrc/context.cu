@@ -1566,6 +1566,8 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
         ctx->queue_capacity = slots;
     }
     rp.queue = ctx->d_queue, rp.queue_count = ctx->d_next_chunk + 1, rp.queue_cursor = ctx->d_next_chunk + 2;
+    rp.queue_count_back = ctx->d_next_chunk + 3; // zeroed with the other counters below
+    rp.queue_capacity   = (uint32_t)ctx->queue_capacity;
     rp.sample_idx    = (int)accumulated_spp;
     rp.sample_offset = (int)sample_offset;
     rp.accum = ctx->accum, rp.ldr = ctx->ldr, rp.hits = ctx->hits;

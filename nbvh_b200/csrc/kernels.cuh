@@ -71,6 +71,8 @@ struct RenderParams {
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
     NeuralQueueEntry *queue;            // neural ray queue filled by k_primary, drained by k_neural
     uint32_t *queue_count, *queue_cursor;
+    uint32_t *queue_count_back; // rays expected to need few queries are queued from the END of the array (drained last); may be null
+    uint32_t queue_capacity;
     int sample_idx, sample_offset;
     // outputs
     float4 *accum;          // RGBA32F accumulation buffer (linear memory replaces the GL surface)

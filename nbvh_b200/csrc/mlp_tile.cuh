@@ -288,6 +288,11 @@ __device__ __forceinline__ void encode_row_to_tile(const NetConst &nc, uint8_t *
 {
 #ifndef NBVH_GRID_DEDUP
     const uint32_t pairs = nc.in_k >> 3; // 16-byte chunks per row; chunk j holds flattened (point,level) 2j, 2j+1
+#if defined(NBVH_ENCODE_UNROLL2)
+#pragma unroll 2
+#elif defined(NBVH_ENCODE_UNROLL3)
+#pragma unroll 3
+#endif
     for (uint32_t j = 0; j < pairs; ++j) {
         uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {

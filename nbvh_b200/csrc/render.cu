@@ -33,6 +33,10 @@ namespace nbvh {
 constexpr int kNeuralTiles   = NBVH_NEURAL_TILES;        // 128-lane tiles per CTA
 constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
 constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
+#ifndef NBVH_LONG_STACK
+#define NBVH_LONG_STACK 4
+#endif
+constexpr int kLongStack     = NBVH_LONG_STACK;          // pending-stack depth from which a queued ray counts as a long query chain
 constexpr int kWalkRounds    = NBVH_WALK_ROUNDS;         // refill/advance rounds before a tile runs the network
 
 // ------------------------------------------------------------------------------------------------ shared helpers
@@ -104,22 +108,32 @@ k_primary(const __grid_constant__ RenderParams p)
             neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
         }
     }
-    // ---- queue compaction: one atomic per warp
-    const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
-    if (qmask) {
-        uint32_t base = 0;
-        if (lane == (uint32_t)(__ffs(qmask) - 1))
-            base = atomicAdd(p.queue_count, (uint32_t)__popc(qmask));
-        base = __shfl_sync(0xFFFFFFFFu, base, __ffs(qmask) - 1);
-        if (active && neural) {
-            const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
-            NeuralQueueEntry *q = p.queue + slot;
-            q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
-            q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
-            q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), 0u, 0u);
-            for (int i = 0; i < nss; i += 4)
-                q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
-        }
+    // ---- queue compaction: one atomic per warp and class.  Longest-processing-time-first: rays whose pending N-BVH stack is deep
+    // (many leaves still ahead) are queued from the front and drained first, the others from the back of the array -- the
+    // persistent kernel's tail then consists of short query chains (k_neural header)
+    const bool is_long    = nss >= kLongStack || p.queue_count_back == nullptr;
+    const uint32_t qlong  = __ballot_sync(0xFFFFFFFFu, active && neural && is_long);
+    const uint32_t qshort = __ballot_sync(0xFFFFFFFFu, active && neural && !is_long);
+    uint32_t base_l = 0, base_s = 0;
+    if (qlong) {
+        if (lane == (uint32_t)(__ffs(qlong) - 1))
+            base_l = atomicAdd(p.queue_count, (uint32_t)__popc(qlong));
+        base_l = __shfl_sync(0xFFFFFFFFu, base_l, __ffs(qlong) - 1);
+    }
+    if (qshort) {
+        if (lane == (uint32_t)(__ffs(qshort) - 1))
+            base_s = atomicAdd(p.queue_count_back, (uint32_t)__popc(qshort));
+        base_s = __shfl_sync(0xFFFFFFFFu, base_s, __ffs(qshort) - 1);
+    }
+    if (active && neural) {
+        const uint32_t below = (1u << lane) - 1u;
+        const uint32_t slot  = is_long ? base_l + __popc(qlong & below) : p.queue_capacity - 1u - (base_s + __popc(qshort & below));
+        NeuralQueueEntry *q = p.queue + slot;
+        q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
+        q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
+        q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), 0u, 0u);
+        for (int i = 0; i < nss; i += 4)
+            q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
     }
     if (active && !neural)
         finish_pixel(p, pixel, ray, h);
@@ -176,7 +190,8 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     const uint32_t warp      = threadIdx.x >> 5;
     TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
 
-    const uint32_t n_queued = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
+    const uint32_t n_front  = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
+    const uint32_t n_queued = n_front + (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u);
     uint32_t nstack[kNeuralStackSize];
     NeuralLane s;
     s.have_ray = s.have_query = false;
@@ -207,7 +222,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 if (!s.have_ray && rank < avail) {
                     const uint32_t qi = chunk_base + chunk_used + rank;
                     if (qi < n_queued) {
-                        const NeuralQueueEntry *q = p.queue + qi;
+                        const NeuralQueueEntry *q = p.queue + (qi < n_front ? qi : p.queue_capacity - 1u - (qi - n_front));
                         const uint4 a = q->a, b = q->b, c = q->c;
                         uint32_t rng;
                         s.pixel       = a.x;
