@@ -42,7 +42,7 @@ def golden_inputs(log2_hashmap, n_query, batch, n_batches, seed):
     return p.view(np.uint16), q, tin, tgt
 
 
-def run_case(name, log2_hashmap, n_query, batch, n_batches, steps, seed, params=None, keep=True):
+def run_case(name, log2_hashmap, n_query, batch, n_batches, steps, seed, params=None, keep=True, curve_only=False):
     wd = os.path.join(REPO, "gpurun_out", "tcnn_work_" + name)
     os.makedirs(wd, exist_ok=True)
     p, q, tin, tgt = golden_inputs(log2_hashmap, n_query, batch, n_batches, seed)
@@ -63,7 +63,9 @@ def run_case(name, log2_hashmap, n_query, batch, n_batches, steps, seed, params=
         meta=np.array([log2_hashmap, n_query, batch, n_batches, steps, seed], dtype=np.int64),
         query_out=np.fromfile(os.path.join(wd, "query_out.f32"), dtype="<f4").reshape(n_query, 8),
     )
-    if steps:
+    if steps and curve_only:  # long runs: the loss curve is the golden
+        gold = dict(meta=gold["meta"], train_loss=np.fromfile(os.path.join(wd, "train_loss.f32"), dtype="<f4"))
+    elif steps:
         gold.update(train_loss=np.fromfile(os.path.join(wd, "train_loss.f32"), dtype="<f4"),
                     train_L0=np.fromfile(os.path.join(wd, "train_L0.f32"), dtype="<f4").reshape(batch, 16),
                     train_out0=np.fromfile(os.path.join(wd, "train_out0.u16"), dtype="<u2").reshape(batch, 16),
@@ -78,8 +80,14 @@ def run_case(name, log2_hashmap, n_query, batch, n_batches, steps, seed, params=
 
 def main():
     timings = {}
+    if "--long-only" in sys.argv:
+        timings["long"] = run_case("long", 12, 256, 2048, 8, 1000, 20241018, curve_only=True)
+        print(json.dumps(timings))
+        return
     # small network (2^12 table): inference + 30 optimisation steps over 4 rotating batches of 2048 samples
     timings["small"] = run_case("small", 12, 2048, 2048, 4, 30, 20241017)
+    # the same network for 1,000 steps (8 rotating batches): long-horizon loss curve of tcnn's Trainer (fp16 gradients, Adam, decay)
+    timings["long"] = run_case("long", 12, 256, 2048, 8, 1000, 20241018, curve_only=True)
     # shipped Chess weights: inference only
     import nbvh_b200
     root = nbvh_b200.chess_fixture_dir()
