@@ -168,22 +168,20 @@ def test_training_error_paths(env):
     mod.close()
 
 
-def smooth(x, k=25):
-    return np.convolve(x, np.ones(k) / k, mode="valid")
-
-
 def test_long_loss_curve_matches_tcnn():
-    """1,000 optimisation steps over 8 rotating batches against tcnn's Trainer (tests/golden/tcnn_long.npz): single steps are
-    chaotic (tcnn accumulates gradients with fp16 atomics), so the 25-step moving averages are compared: within CURVE_TOL
-    everywhere, and the final plateau within 2 %."""
+    """1,000 optimisation steps over 8 rotating batches against tcnn's Trainer (tests/golden/tcnn_long.npz: FOUR runs of the
+    reference's trainer on identical inputs).  tcnn accumulates gradients with unordered fp16 atomics, so its own curve differs
+    from run to run (100-step window means spread by 1 % early and by up to 50 % late, where occasional loss spikes fall into
+    different windows).  Gate: every 100-step window mean of the B200 curve lies inside the band spanned by the reference's own
+    runs, widened by BAND_MARGIN; the first 25 steps (before the trajectories decorrelate; the reference's own runs differ by 0.3 % there) agree within 0.5 % step by step."""
     import torch
     import nbvh_b200
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     path = os.path.join(GOLDEN, "tcnn_long.npz")
     if not os.path.exists(path):
-        pytest.skip("tcnn_long.npz not generated yet (tools/make_tcnn_goldens.py on a GPU box)")
-    CURVE_TOL = 0.05
+        pytest.skip("tcnn_long.npz not generated yet (tools/make_tcnn_goldens.py --long-only on a GPU box)")
+    BAND_MARGIN = 0.03
     g = np.load(path)
     log2, nq, B, nb, steps, seed = [int(x) for x in g["meta"]]
     p, q, tin, tgt = golden_inputs(log2, nq, B, nb, seed)
@@ -193,9 +191,17 @@ def test_long_loss_curve_matches_tcnn():
     ts = [torch.from_numpy(tgt[k]).cuda() for k in range(nb)]
     losses = np.array([mod.training_step(xs[s % nb], ts[s % nb]) for s in range(steps)])
     mod.close()
-    a, b = smooth(losses), smooth(g["train_loss"])
-    dev = np.abs(a - b) / b
-    print("1000-step loss curve vs tcnn: start %.4f / %.4f, end %.5f / %.5f, max deviation of the 25-step average %.3f %%" %
-          (losses[0], g["train_loss"][0], a[-1], b[-1], 100 * dev.max()))
-    assert dev.max() <= CURVE_TOL
-    assert abs(a[-1] - b[-1]) <= 0.02 * b[-1] and a[-1] < 0.5 * a[0]
+    if os.path.isdir(os.path.join(REPO, "gpurun_out")):
+        np.save(os.path.join(REPO, "gpurun_out", "long_curve_b200.npy"), losses)
+    runs = g["train_loss_runs"]
+    w = 100
+    ours = losses.reshape(-1, w).mean(axis=1)
+    ref = runs.reshape(runs.shape[0], -1, w).mean(axis=2)
+    lo, hi = ref.min(axis=0) * (1 - BAND_MARGIN), ref.max(axis=0) * (1 + BAND_MARGIN)
+    print("window means  B200:", np.round(ours, 4))
+    print("tcnn band lo     :", np.round(lo, 4))
+    print("tcnn band hi     :", np.round(hi, 4))
+    assert ((ours >= lo) & (ours <= hi)).all()
+    early = np.abs(losses[:25] - runs[:, :25].mean(axis=0)) / runs[:, :25].mean(axis=0)
+    assert early.max() <= 5e-3, early.max()
+    assert ours[-1] < 0.3 * ours[0]
