@@ -283,6 +283,7 @@ struct nbvh_ctx {
     uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor, [3] node-check flag, [4] sampler slot counter
     NeuralQueueEntry *d_queue = nullptr;
     size_t queue_capacity = 0;
+    bool l2_prefetch = false; // NBVH_L2_PREFETCH=1 enables a per-frame L2 warm-up of the gather tables (A/B: no effect measured)
     bool mega_kernel = false; // NBVH_RENDER_MODE=mega: the single persistent kernel of the first design (kept for A/B timing)
     unsigned long long *d_counters = nullptr;
 
@@ -573,6 +574,8 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
     ctx->num_sms  = prop.multiProcessorCount;
     if (const char *m = getenv("NBVH_RENDER_MODE"))
         ctx->mega_kernel = std::string(m) == "mega";
+    if (const char *m = getenv("NBVH_L2_PREFETCH"))
+        ctx->l2_prefetch = std::string(m) != "0";
     if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
@@ -1577,6 +1580,25 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     const NetConst nc = make_net_const(ctx);
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, 4 * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
+    if (ctx->l2_prefetch) {
+        // warm L2 with the tables the scattered gathers of this frame touch (see k_prefetch_l2)
+        const void *ptrs[12];
+        size_t bytes[12];
+        int n = 0;
+        ptrs[n] = ctx->d_params, bytes[n++] = (size_t)ctx->n_params * 2;
+        ptrs[n] = ctx->d_nbvh_dilated, bytes[n++] = (size_t)ctx->nbvh_nodes * 32;
+        for (size_t i = 0; i < ctx->blas_desc.size() && n + 3 <= 12; i++) {
+            const nbvh_cuda_blas &b = ctx->blas_desc[i];
+            if ((i == ctx->bvh_const.neural_bvh_idx && !ctx->bvh_const.ignore_neural_blas) || b.num_nodes < 2)
+                continue; // the neural mesh's classical BLAS is not traversed at inference
+            if ((size_t)b.num_nodes * 32 > (32u << 20))
+                continue; // large meshes stream through L2 anyway
+            ptrs[n] = b.nodes, bytes[n++] = (size_t)b.num_nodes * 32;
+            ptrs[n] = b.prim_indices, bytes[n++] = (size_t)b.num_prim_indices * 8;
+            ptrs[n] = b.indices, bytes[n++] = (size_t)b.num_prim_indices * 12;
+        }
+        CU_TRY(ctx, launch_prefetch_l2(ptrs, bytes, n, ctx->num_sms, st));
+    }
     if (ctx->max_depth > 1) {
         // hybrid neural path tracing (path.cu): shading + re-queue per bounce, no host synchronisation
         if (ctx->path_capacity < slots) {

@@ -164,6 +164,7 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k);
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream);
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);
+cudaError_t launch_prefetch_l2(const void *const *ptrs, const size_t *bytes, int n, int num_sms, cudaStream_t stream);
 size_t build_blas_workspace_bytes(uint32_t n_tris);
 cudaError_t launch_build_blas(const float *vertices, const uint32_t *indices, uint32_t n_tris, float4 *nodes, unsigned long long *prim_indices,
                               void *workspace, size_t workspace_bytes, uint32_t *max_depth_dev, cudaStream_t stream);
