@@ -443,6 +443,7 @@ int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned);
 const nbvh_tree_cut_data *nbvh_tree_cut_data_device(const nbvh_ctx *ctx);
 const nbvh_node32 *nbvh_neural_bvh_device(const nbvh_ctx *ctx);
 int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, uint32_t *node_map_host, uint32_t n);
+int nbvh_set_tree_cut_host(nbvh_ctx *ctx, const nbvh_tree_cut_data *cut_host, uint32_t n);
 uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);

@@ -170,6 +170,7 @@ SYMBOLS = {
     "nbvh_tree_cut_assign_lod": (_i, [_vp, C.POINTER(_i)]),
     "nbvh_tree_cut_data_device": (_vp, [_vp]),
     "nbvh_neural_bvh_device": (_vp, [_vp]),
+    "nbvh_set_tree_cut_host": (_i, [_vp, _vp, _u32]),
     "nbvh_get_tree_cut_host": (_i, [_vp, _vp, _vp, _u32]),
     "nbvh_tree_cut_max_depth": (_u32, [_vp]),
 }

@@ -1869,6 +1869,15 @@ int nbvh_tree_cut_attach(nbvh_ctx *ctx)
 const nbvh_tree_cut_data *nbvh_tree_cut_data_device(const nbvh_ctx *ctx) { return ctx && ctx->tree_cut_ready ? ctx->d_tree_cut : nullptr; }
 const nbvh_node32 *nbvh_neural_bvh_device(const nbvh_ctx *ctx) { return ctx ? reinterpret_cast<const nbvh_node32 *>(ctx->d_nbvh) : nullptr; }
 
+// test / restore hook: overwrite the per-node statistics (the reference restores them when it reloads a training state)
+int nbvh_set_tree_cut_host(nbvh_ctx *ctx, const nbvh_tree_cut_data *cut_host, uint32_t n)
+{
+    if (!ctx || !cut_host || !ctx->tree_cut_ready || n != ctx->nbvh_nodes)
+        return NBVH_ERR_INVALID_ARG;
+    CU_TRY(ctx, cudaMemcpy(ctx->d_tree_cut, cut_host, (size_t)n * sizeof(nbvh_tree_cut_data), cudaMemcpyHostToDevice));
+    return NBVH_OK;
+}
+
 int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, uint32_t *node_map_host, uint32_t n)
 {
     if (!ctx || !ctx->tree_cut_ready || n > ctx->nbvh_nodes)

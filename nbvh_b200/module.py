@@ -452,6 +452,10 @@ class NeuralPathModule:
     def tree_cut_data_ptr(self):
         return self._lib.nbvh_tree_cut_data_device(self._h)
 
+    def set_tree_cut_data(self, cut):
+        cut = np.ascontiguousarray(cut, dtype=TREE_CUT_DTYPE)
+        self._check(self._lib.nbvh_set_tree_cut_host(self._h, cut.ctypes.data_as(C.c_void_p), len(cut)))
+
     def tree_cut_state(self):
         """Host copies of (tree-cut nodes, NeuralTreeCutData, node map)."""
         n = self._lib.nbvh_neural_bvh_num_nodes(self._h)

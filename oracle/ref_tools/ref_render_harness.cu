@@ -516,6 +516,37 @@ int main(int argc, char **argv)
         printf("[ref_render_harness] envmap %dx%d\n", ew, eh);
     }
 
+    // ---- treecut mode: the reference's tree-cut learning kernels (K17) for one optimisation step
+    //      usage: ... 0 treecut <batch> <num_splits>; reads tree_cut.bin, tc_L.f32 (batch x 16), tc_sampled.u32 (batch);
+    //      runs update_neural_tree_cut_loss + (k + 1) x update_neural_tree_cut_decisions exactly as neural_bvh_renderer.cu:199-236;
+    //      writes tc_cut_out.bin (NeuralTreeCutData per node), tc_max_losses.f32 (k), tc_split.u32 (k)
+    if (argc >= 10 && std::string(argv[7]) == "treecut") {
+        const uint32_t batch = atoi(argv[8]), k = atoi(argv[9]);
+        std::vector<NeuralTreeCutData> cut;
+        std::vector<float> L;
+        std::vector<uint32_t> sampled;
+        if (!slurp(wd + "/tree_cut.bin", cut) || cut.size() != nb_nodes.size() || !slurp(wd + "/tc_L.f32", L) || L.size() != (size_t)batch * 16 ||
+            !slurp(wd + "/tc_sampled.u32", sampled) || sampled.size() != batch) {
+            fprintf(stderr, "treecut mode: bad inputs in %s\n", wd.c_str());
+            return 4;
+        }
+        NeuralTreeCutData *d_cut = upload(cut);
+        float *d_L               = upload(L);
+        uint32_t *d_sampled      = upload(sampled);
+        float *d_max             = dalloc<float>(std::max(1u, k));
+        uint32_t *d_split        = dalloc<uint32_t>(std::max(1u, k));
+        LINEAR_KERNEL(update_neural_tree_cut_loss, 0, batch * 16u, 16u, c_pt.output_network_dims, d_L, d_sampled, d_cut, batch);
+        CK(cudaDeviceSynchronize());
+        for (uint32_t i = 0; i <= k; i++)
+            LINEAR_KERNEL(update_neural_tree_cut_decisions, 0, nbvh.num_nodes, nbvh, d_cut, d_max, d_split, i, i == k);
+        CK(cudaDeviceSynchronize());
+        dump(wd + "/tc_cut_out.bin", download(d_cut, cut.size()));
+        dump(wd + "/tc_max_losses.f32", download(d_max, k));
+        dump(wd + "/tc_split.u32", download(d_split, k));
+        printf("[ref_render_harness] treecut: %zu nodes, batch %u, %u splits requested\n", cut.size(), batch, k);
+        return 0;
+    }
+
     // ---- sampler mode: the reference's training-sample generator (K10) for a few steps
     if (argc >= 11 && std::string(argv[7]) == "sampler") {
         const uint32_t batch = atoi(argv[8]), log2_trav = atoi(argv[9]), steps = atoi(argv[10]);

@@ -151,3 +151,73 @@ def test_gpu_from_scratch_optimisation_with_tree_cut_learning(tc_env):
     assert np.isfinite(losses).all() and np.mean(losses[-10:]) < np.mean(losses[:10])
     leaves = nodes["b"] == 0xFFFFFFFF
     assert leaves.sum() == grown + 1 and cut["depth"].max() == mod._lib.nbvh_tree_cut_max_depth(mod._h)
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own K17 kernels
+G_TC = os.path.join(HERE, "golden", "ref_chess_treecut.npz")
+
+
+def _treecut_case():
+    import sys
+    from nbvh_b200.scene_io import CHESS_BASE
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+    from make_ref_treecut_goldens import treecut_inputs
+    if not os.path.exists(G_TC):
+        pytest.skip("ref_chess_treecut.npz not generated yet (tools/make_ref_treecut_goldens.py on a GPU box)")
+    g = np.load(G_TC)
+    return g, treecut_inputs, CHESS_BASE
+
+
+def check_against_reference_kernels(g, nodes_before, nodes_after, cut_after, max_loss, blas_nodes, nmap):
+    n = len(nodes_before)
+    # statistics: sample counts and leaf ages exactly, loss sums to the order of the fp32 atomics
+    assert (cut_after["samples"][:n] == g["samples"]).all() and (cut_after["iter_alive"][:n] == g["iter_alive"]).all()
+    assert np.allclose(cut_after["loss"][:n], g["loss"], rtol=2e-5, atol=1e-6)
+    assert abs(max_loss - g["max_losses"][0]) <= 2e-5 * g["max_losses"][0]
+    # decisions: the reference's k split indices (distinct maxima, best first) are exactly the leaves that were split here,
+    # except those whose BLAS node is a leaf (the reference's host split skips them: "Leaf node reached, no split")
+    ref_split = set(int(i) for i in g["split"])
+    mine = set(np.flatnonzero((nodes_before["b"] == 0xFFFFFFFF) & (nodes_after["b"][:n] != 0xFFFFFFFF)).tolist())
+    assert mine <= ref_split
+    for i in ref_split - mine:
+        assert nodes_before["b"][i] != 0xFFFFFFFF or blas_nodes["a"][nmap[i]] > 0 or i == 0
+    assert len(mine) > 0.9 * int(g["k"])
+
+
+def test_oracle_tree_cut_step_matches_reference_kernels(oracle, chess_root):
+    g, treecut_inputs, base = _treecut_case()
+    nodes = oracle.read_nbvh(os.path.join(chess_root, base + ".nbvh"))
+    blas_nodes = np.fromfile(os.path.join(chess_root, "mesh0_bvh_nodes.bin"), dtype=oracle.NODE_DTYPE)
+    cut, L, sampled = treecut_inputs(nodes, int(g["batch"]), int(g["seed"]))
+    # node map by walking the BLAS and the tree-cut together (reinitialise_neural_bvh_learning_states)
+    nmap = np.zeros(len(nodes), np.uint32)
+    stack = [(0, 0)]
+    while stack:
+        bi, ni = stack.pop()
+        nmap[ni] = bi
+        if nodes["b"][ni] != 0xFFFFFFFF:
+            stack.append((int(blas_nodes["b"][bi]) + 1, int(nodes["b"][ni]) + 1))
+            stack.append((int(blas_nodes["b"][bi]), int(nodes["b"][ni])))
+    n2, c2, m2, mx, ns = oracle.tree_cut_step(nodes, cut.astype(oracle.TREE_CUT_DTYPE), nmap, blas_nodes, L, sampled, int(g["k"]), 6)
+    check_against_reference_kernels(g, nodes, n2, c2, mx, blas_nodes, nmap)
+
+
+@pytest.mark.gpu
+def test_gpu_tree_cut_step_matches_reference_kernels(oracle, chess_root):
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    g, treecut_inputs, base = _treecut_case()
+    mod = nbvh_b200.load_chess_module(with_neural_mesh=True)
+    mod.tree_cut_attach()
+    nodes, cut0, nmap = mod.tree_cut_state()
+    cut, L, sampled = treecut_inputs(nodes, int(g["batch"]), int(g["seed"]))
+    cut["depth"] = cut0["depth"]
+    mod.set_tree_cut_data(cut)
+    mx, ns = mod.tree_cut_step(torch.from_numpy(L).cuda(), torch.from_numpy(sampled.astype(np.int32)).cuda(), int(g["k"]), dims=8)
+    n2, c2, m2 = mod.tree_cut_state()
+    blas_nodes = np.fromfile(os.path.join(chess_root, "mesh0_bvh_nodes.bin"), dtype=oracle.NODE_DTYPE)
+    check_against_reference_kernels(g, nodes, n2, c2, mx, blas_nodes, nmap)
+    assert len(n2) == len(nodes) + 2 * ns
+    mod.close()
