@@ -186,18 +186,9 @@ def check_against_reference_kernels(g, nodes_before, nodes_after, cut_after, max
 
 def test_oracle_tree_cut_step_matches_reference_kernels(oracle, chess_root):
     g, treecut_inputs, base = _treecut_case()
-    nodes = oracle.read_nbvh(os.path.join(chess_root, base + ".nbvh"))
     blas_nodes = np.fromfile(os.path.join(chess_root, "mesh0_bvh_nodes.bin"), dtype=oracle.NODE_DTYPE)
+    nodes, cut0, nmap = oracle.tree_cut_initial(blas_nodes, int(g["cut_depth"]), 6)
     cut, L, sampled = treecut_inputs(nodes, int(g["batch"]), int(g["seed"]))
-    # node map by walking the BLAS and the tree-cut together (reinitialise_neural_bvh_learning_states)
-    nmap = np.zeros(len(nodes), np.uint32)
-    stack = [(0, 0)]
-    while stack:
-        bi, ni = stack.pop()
-        nmap[ni] = bi
-        if nodes["b"][ni] != 0xFFFFFFFF:
-            stack.append((int(blas_nodes["b"][bi]) + 1, int(nodes["b"][ni]) + 1))
-            stack.append((int(blas_nodes["b"][bi]), int(nodes["b"][ni])))
     n2, c2, m2, mx, ns = oracle.tree_cut_step(nodes, cut.astype(oracle.TREE_CUT_DTYPE), nmap, blas_nodes, L, sampled, int(g["k"]), 6)
     check_against_reference_kernels(g, nodes, n2, c2, mx, blas_nodes, nmap)
 
@@ -210,8 +201,12 @@ def test_gpu_tree_cut_step_matches_reference_kernels(oracle, chess_root):
         pytest.skip("no CUDA device")
     g, treecut_inputs, base = _treecut_case()
     mod = nbvh_b200.load_chess_module(with_neural_mesh=True)
-    mod.tree_cut_attach()
+    with pytest.raises(nbvh_b200.NbvhError):  # the shipped .nbvh is a cut of the authors' BLAS build, not of the one built here
+        mod.tree_cut_attach()
+    mod.tree_cut_init(int(g["cut_depth"]))
     nodes, cut0, nmap = mod.tree_cut_state()
+    rn, _, rm = oracle.tree_cut_initial(np.fromfile(os.path.join(chess_root, "mesh0_bvh_nodes.bin"), dtype=oracle.NODE_DTYPE), int(g["cut_depth"]), 6)
+    assert same_nodes(nodes, rn) and (nmap == rm).all()
     cut, L, sampled = treecut_inputs(nodes, int(g["batch"]), int(g["seed"]))
     cut["depth"] = cut0["depth"]
     mod.set_tree_cut_data(cut)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Goldens of the reference's OWN tree-cut learning kernels (TEST INFRASTRUCTURE; run ON THE GPU BOX): update_neural_tree_cut_loss and
 update_neural_tree_cut_decisions (neural_bvh_renderer_kernels.cu:202-287), driven as neural_bvh_renderer.cu:199-236 drives them, on the
-shipped Chess tree-cut with seeded per-node statistics, per-element losses and sampled node indices (treecut_inputs below).
+depth-13 cut of the Chess neural mesh's BLAS (nbvh_tree_cut_init(13): 16 k nodes; the shipped .nbvh is a cut of the AUTHORS' ext/bvh
+build, which differs from the BLAS built here in ~10 % of the boxes, so it cannot be split further against this BLAS) with seeded per-node statistics, per-element losses and sampled node indices (treecut_inputs below).
 Output: gpurun_out/ref_golden/ref_chess_treecut.npz -> copy to tests/golden/."""
 import json
 import os
@@ -14,7 +15,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tools"))
 OUT = os.path.join(REPO, "gpurun_out", "ref_golden")
-BATCH, K, SEED = 1 << 16, 187, 424242
+BATCH, K, SEED, CUT_DEPTH = 1 << 16, 187, 424242, 13
 CUT_DTYPE = np.dtype([("loss", "<f4"), ("iter_alive", "<u4"), ("depth", "<u4"), ("samples", "<u4")])
 
 
@@ -40,7 +41,8 @@ def main():
     from nbvh_b200.scene_io import CHESS_BASE, chess_fixture_dir
     root = chess_fixture_dir()
     cfg = json.load(open(os.path.join(root, CHESS_BASE + "_neural.json")))
-    mod = nbvh_b200.load_chess_module(max_depth=1, envmap_eval=False)
+    mod = nbvh_b200.load_chess_module(max_depth=1, envmap_eval=False, with_neural_mesh=True)
+    mod.tree_cut_init(CUT_DEPTH)
     tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root)
     wd = os.path.join(OUT, "work_treecut")
     R.prepare(mod, cfg, wd, 64, 32, (tl, ti, bl))
@@ -54,7 +56,7 @@ def main():
     if out.returncode != 0:
         raise SystemExit("ref_render_harness treecut failed")
     cut_out = np.fromfile(os.path.join(wd, "tc_cut_out.bin"), dtype=CUT_DTYPE)
-    np.savez_compressed(os.path.join(OUT, "ref_chess_treecut.npz"), batch=BATCH, k=K, seed=SEED, loss=cut_out["loss"], samples=cut_out["samples"],
+    np.savez_compressed(os.path.join(OUT, "ref_chess_treecut.npz"), batch=BATCH, k=K, seed=SEED, cut_depth=CUT_DEPTH, loss=cut_out["loss"], samples=cut_out["samples"],
                         iter_alive=cut_out["iter_alive"], max_losses=np.fromfile(os.path.join(wd, "tc_max_losses.f32"), dtype="<f4"),
                         split=np.fromfile(os.path.join(wd, "tc_split.u32"), dtype="<u4"))
     for fn in os.listdir(wd):
