@@ -258,6 +258,12 @@ enum {
     NBVH_CNT_TILE_ITERATIONS,   /* 128-row MLP tiles executed                */
     NBVH_CNT_QUEUED_RAYS,       /* rays handed from k_primary to k_neural    */
     NBVH_CNT_NBVH_STEPS_NEURAL, /* the part of NBVH_STEPS taken in k_neural  */
+    /* timeline of the LAST k_neural launches since the reset (%globaltimer, ns): bitwise-inverted minimum start time, inverted
+     * time of the first queue exhaustion, maximum end time, sum of the CTA lifetimes */
+    NBVH_CNT_T_START_INV,
+    NBVH_CNT_T_EXHAUST_INV,
+    NBVH_CNT_T_END,
+    NBVH_CNT_T_CTA_SUM,
     NBVH_CNT_COUNT
 };
 

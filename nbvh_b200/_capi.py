@@ -12,7 +12,7 @@ CONST_RENDERER, CONST_MODULE, CONST_PT_OUTPUT, CONST_PATH, CONST_SCENE, CONST_CA
     CONST_NETWORK, CONST_OPTIMIZER = range(9)
 
 COUNTER_NAMES = ["rays", "queries", "nbvh_steps", "blas_steps", "tri_tests", "tile_iterations", "queued_rays",
-                 "nbvh_steps_neural"]
+                 "nbvh_steps_neural", "t_start_inv", "t_exhaust_inv", "t_end", "t_cta_sum"]
 
 
 class RendererConstants(C.Structure):

@@ -18,6 +18,11 @@ enum Counter {
     CNT_TILE_ITERS,
     CNT_QUEUED,
     CNT_NBVH_STEPS_NEURAL,
+    // k_neural timeline (globaltimer ns): start = ~min, first queue exhaustion = ~min, end = max, summed CTA lifetimes
+    CNT_T_START_INV,
+    CNT_T_EXHAUST_INV,
+    CNT_T_END,
+    CNT_T_CTA_SUM,
     CNT_COUNT
 };
 
