@@ -1494,8 +1494,8 @@ int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint3
         return NBVH_ERR_INVALID_ARG;
     if (n_spp == 1u)
         return nbvh_render_interleaved(ctx, first_spp, sample_offset, shard_index, shard_count, stream);
-    if (ctx->max_depth < 2)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_render_samples: multi-sample launches exist for max_depth > 1 (the path lists)");
+    if (ctx->mega_kernel)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_render_samples: not available in NBVH_RENDER_MODE=mega");
     if (ctx->scene_const.ema_accumulate)
         return fail(ctx, NBVH_ERR_UNSUPPORTED, "nbvh_render_samples: ema_accumulate needs sample-by-sample accumulation");
     const uint32_t total = ctx->fb_w * ctx->fb_h;

@@ -363,31 +363,6 @@ cudaError_t launch_image_error(const float4 *accum, const float4 *reference, uin
     return cudaGetLastError();
 }
 
-// 8-bit frame of the shard's pixels after a multi-sample launch sequence: sRGB(accum / samples), as accumulate_pixel_value writes it
-__global__ void __launch_bounds__(256)
-k_resolve_ldr(const __grid_constant__ RenderParams p, float inv_samples)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.pixel_count)
-        return;
-    const uint32_t pixel = swizzle_pixel(p, p.first_pixel + i);
-    const float4 a = p.accum[pixel];
-    uchar4 px;
-    px.x = (unsigned char)min(max(int(linear_to_srgb(a.x * inv_samples) * 256.0f), 0), 255);
-    px.y = (unsigned char)min(max(int(linear_to_srgb(a.y * inv_samples) * 256.0f), 0), 255);
-    px.z = (unsigned char)min(max(int(linear_to_srgb(a.z * inv_samples) * 256.0f), 0), 255);
-    px.w = 255;
-    p.ldr[pixel] = px;
-}
-
-__global__ void __launch_bounds__(256)
-k_clear_accum(const __grid_constant__ RenderParams p)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p.pixel_count)
-        p.accum[swizzle_pixel(p, p.first_pixel + i)] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 // One frame of NeuralPathModule::neural_path_tracing.  `counters`: kPathCountersPerDepth zeroed words per depth
 // (neural queue count, queue cursor, length of the path list).  paths[2] / hits[2]: ping-pong path lists.
 cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, const NetConst &nc, const NbvhConst &nbvh_bounce,

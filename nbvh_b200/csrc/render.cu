@@ -64,6 +64,32 @@ __device__ __forceinline__ void finish_pixel(const RenderParams &p, uint32_t pix
     }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-sample helpers
+// 8-bit frame of the shard's pixels after a multi-sample launch sequence: sRGB(accum / samples), as accumulate_pixel_value writes it
+__global__ void __launch_bounds__(256)
+k_resolve_ldr(const __grid_constant__ RenderParams p, float inv_samples)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.pixel_count)
+        return;
+    const uint32_t pixel = swizzle_pixel(p, p.first_pixel + i);
+    const float4 a = p.accum[pixel];
+    uchar4 px;
+    px.x = (unsigned char)min(max(int(linear_to_srgb(a.x * inv_samples) * 256.0f), 0), 255);
+    px.y = (unsigned char)min(max(int(linear_to_srgb(a.y * inv_samples) * 256.0f), 0), 255);
+    px.z = (unsigned char)min(max(int(linear_to_srgb(a.z * inv_samples) * 256.0f), 0), 255);
+    px.w = 255;
+    p.ldr[pixel] = px;
+}
+
+__global__ void __launch_bounds__(256)
+k_clear_accum(const __grid_constant__ RenderParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.pixel_count)
+        p.accum[swizzle_pixel(p, p.first_pixel + i)] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------ k_primary
 __global__ void __launch_bounds__(256)
 k_primary(const __grid_constant__ RenderParams p)
@@ -71,7 +97,10 @@ k_primary(const __grid_constant__ RenderParams p)
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t sidx  = chunk * 32u + lane;
-    const bool active    = sidx < p.pixel_count;
+    const uint32_t n_spp = p.spp_count > 1u ? p.spp_count : 1u;
+    const bool active    = sidx < p.pixel_count * n_spp;
+    // multi-sample launch: slot = sample * pixel_count + pixel slot (pixel_count is a multiple of 32: a warp stays in one sample)
+    const uint32_t smp   = sidx / p.pixel_count;
     uint32_t cnt_blas = 0, cnt_tri = 0, cnt_nbvh = 0;
     bool neural       = false;
     uint32_t pixel    = 0;
@@ -85,8 +114,8 @@ k_primary(const __grid_constant__ RenderParams p)
     h.alb_or_ids[0] = h.alb_or_ids[1] = h.alb_or_ids[2] = 0.f;
     if (active) {
         uint32_t rng;
-        pixel = swizzle_pixel(p, p.first_pixel + sidx);
-        ray   = camera_ray(p.cam, pixel, p.sample_idx, p.sample_offset, rng);
+        pixel = swizzle_pixel(p, p.first_pixel + (sidx - smp * p.pixel_count));
+        ray   = camera_ray(p.cam, pixel, p.sample_idx + (int)smp, p.sample_offset, rng);
         uint32_t tstack[kTlasStackSize];
         int tss   = 1;
         tstack[0] = 0u;
@@ -139,7 +168,7 @@ k_primary(const __grid_constant__ RenderParams p)
         NeuralQueueEntry *q = p.queue + slot;
         q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
         q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
-        q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), 0u, 0u);
+        q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), smp, 0u); // c.z: sample of a multi-sample launch
         for (int i = 0; i < nss; i += 4)
             q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
     }
@@ -263,7 +292,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                             s.ray.dx = s0.w, s.ray.dy = s1.x, s.ray.dz = s1.y;
                             ray_prepare(s.ray, p.cam.nodes_safe != 0u);
                         } else {
-                            s.ray = camera_ray(p.cam, s.pixel, p.sample_idx, p.sample_offset, rng);
+                            s.ray = camera_ray(p.cam, s.pixel, p.sample_idx + (int)c.z, p.sample_offset, rng);
                         }
                         s.h.best_t    = __uint_as_float(a.y);
                         s.h.valid_hit = a.z;
@@ -480,14 +509,24 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
 {
     if (rp.pixel_count == 0)
         return cudaSuccess;
-    const uint32_t n_chunks = (rp.pixel_count + 31u) >> 5;
+    const uint32_t slots    = rp.pixel_count * (rp.spp_count > 1u ? rp.spp_count : 1u);
+    const uint32_t n_chunks = (slots + 31u) >> 5;
+    if (rp.spp_count > 1u && rp.sample_idx == 0) // sample 0 overwrites the accumulation; here: clear, then 16-byte reductions
+        k_clear_accum<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp);
     k_primary<<<(n_chunks + 7u) / 8u, 256, 0, stream>>>(rp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return e;
     if (between && (e = cudaEventRecord(between, stream)) != cudaSuccess)
         return e;
-    return launch_neural(rp, nc, num_sms, false, stream);
+    e = launch_neural(rp, nc, num_sms, false, stream);
+    if (e != cudaSuccess)
+        return e;
+    if (rp.spp_count > 1u && rp.ldr) {
+        k_resolve_ldr<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp, 1.f / (float)(rp.sample_idx + (int)rp.spp_count));
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
 }
 
 } // namespace nbvh

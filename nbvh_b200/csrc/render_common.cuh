@@ -143,4 +143,8 @@ __device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_
     return (by * 4u + (k >> 3)) * w + bx * 8u + (k & 7u);
 }
 
+// multi-sample launches (render.cu): clear / resolve the shard's pixels
+__global__ void k_clear_accum(const __grid_constant__ RenderParams p);
+__global__ void k_resolve_ldr(const __grid_constant__ RenderParams p, float inv_samples);
+
 } // namespace nbvh

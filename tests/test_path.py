@@ -307,11 +307,13 @@ def test_gpu_interleaved_tile_shards_reproduce_full_frame(syn_path, torch_cuda, 
 
 
 @pytest.mark.gpu
-def test_gpu_multi_sample_launch_equals_sample_by_sample(syn_path, torch_cuda):
+@pytest.mark.parametrize("max_depth", [1, 3])
+def test_gpu_multi_sample_launch_equals_sample_by_sample(syn_path, torch_cuda, max_depth):
     """nbvh_render_samples: 5 samples per pixel in one launch sequence (and 3 + 2 over two shards) == five nbvh_render calls, up
-    to the fp32 order of the per-pixel sum (16-byte reductions instead of read-modify-write)."""
+    to the fp32 order of the per-pixel sum (16-byte reductions instead of read-modify-write); max_depth 1 exercises the
+    k_primary / k_neural pair, max_depth 3 the path pipeline."""
     mod, W, H = syn_path["mod"], syn_path["W"], syn_path["H"]
-    mod.max_depth = 3
+    mod.max_depth = max_depth
     ref, ldr_ref = gpu_render(mod, torch_cuda, W, H, spp=5)
     accum, ldr = mod.attach_framebuffer((W, H))
     mod.neural_render_samples(0, 5)
