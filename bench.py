@@ -348,6 +348,22 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
 
+    # ---------------- the same frame with 8 samples per launch pair (nbvh_render_samples): k_neural's drain of in-flight rays (60 % of
+    # the 1-spp launch) is paid once per launch instead of once per sample; same images up to the fp32 sum order
+    ms_n = 8
+    for i in range(2):
+        mod.neural_render_samples(i * ms_n, ms_n, stream=stream.cuda_stream)
+    barrier()
+    ms_reps = max(3, min(args.steps // ms_n, 20))
+    ms_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ms_reps)]
+    for i in range(ms_reps):
+        flush.fill_(i & 0xFF)
+        ms_ev[i][0].record(stream)
+        mod.neural_render_samples(((2 + i) * world + rank) * ms_n, ms_n, stream=stream.cuda_stream)
+        ms_ev[i][1].record(stream)
+    barrier()
+    multi_ms = float(sum(a.elapsed_time(b) for a, b in ms_ev)) / ms_reps
+
     # ---------------- hybrid neural path tracing (BASELINE configs[1] at the shipped max_depth = "2b", and configs[3]):
     # shading + BSDF sampling + Russian roulette + HDRI per bounce, 3 launches per depth (path.cu)
     path_info = None
@@ -500,10 +516,10 @@ def main():
         barrier()
         strong_ms = te0.elapsed_time(te1) / train_steps
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms, strong_ms, e2e_sync_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s * 1e3, train_ms, strong_ms, e2e_sync_s * 1e3, multi_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, train_ms, strong_ms, e2e_sync_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
+    total_ms, e2e_ms, train_ms, strong_ms, e2e_sync_ms, multi_ms = (float(t[k]) for k in range(6))
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -581,6 +597,10 @@ def main():
                               "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam" +
                               ("; fp32 gradient allreduce (NCCL) per step" if world > 1 else ""),
                       "reference_b200": ref_train},
+            "multi_sample": {"samples_per_launch": ms_n, "ms_per_launch": multi_ms, "ms_per_sample_frame": multi_ms / ms_n,
+                             "value": world * n_rays * ms_n / (multi_ms * 1e-3) / 1e6, "unit": UNIT, "launches": ms_reps,
+                             "what": "the headline workload with 8 samples of the frame per launch pair (nbvh_render_samples): k_primary over "
+                                     "pixels x samples, one k_neural drain per launch, 16-byte reductions into the accumulation; L2 flushed between launches"},
             "path": path_info,
             "counters_per_step": per,
             "neural_queries_per_s": per["queries"] / (ms_per_step * 1e-3),
