@@ -243,6 +243,13 @@ struct nbvh_ctx {
     nbvh_tree_cut_data *d_tree_cut = nullptr;
     uint32_t *d_node_map = nullptr;       // tree-cut node -> node of the neural mesh's classical BLAS
     // frames in flight (nbvh_render_host_submit / _wait): two 8-bit frame buffers, a render and a copy stream
+    // slot 1 renders on its own stream with its own neural ray queue and counters, so that its k_primary overlaps the drain of
+    // slot 0's k_neural (60 % of a 1080p launch leaves the SMs mostly idle)
+    int render_slot = 0; // which queue / counter set render_impl uses (set by nbvh_render_host_submit)
+    uint32_t *d_next_chunk_alt = nullptr;
+    NeuralQueueEntry *d_queue_alt = nullptr;
+    size_t queue_capacity_alt = 0;
+    cudaStream_t pipe_render_alt = nullptr;
     uchar4 *d_ldr_slot[2] = {nullptr, nullptr};
     size_t ldr_slot_pixels = 0;
     cudaStream_t pipe_render = nullptr, pipe_copy = nullptr;
@@ -609,6 +616,10 @@ void nbvh_destroy(nbvh_ctx *ctx)
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
     cudaFree(ctx->d_build_ws);
+    cudaFree(ctx->d_next_chunk_alt);
+    cudaFree(ctx->d_queue_alt);
+    if (ctx->pipe_render_alt)
+        cudaStreamDestroy(ctx->pipe_render_alt);
     for (int k = 0; k < 2; k++) {
         cudaFree(ctx->d_ldr_slot[k]);
         if (ctx->pipe_rendered[k])
@@ -1560,17 +1571,26 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
     rp.chunk_stride = chunk_stride, rp.chunk_offset = chunk_offset;
     rp.spp_count     = spp_count;
-    rp.next_chunk    = ctx->d_next_chunk;
-    const size_t slots = spp_count > 1u ? (size_t)pixel_count * spp_count : (size_t)total; // path / queue slots this launch may use
-    if (ctx->queue_capacity < slots) {
-        cudaFree(ctx->d_queue);
-        ctx->d_queue = nullptr, ctx->queue_capacity = 0;
-        CU_TRY(ctx, cudaMalloc(&ctx->d_queue, slots * sizeof(NeuralQueueEntry)));
-        ctx->queue_capacity = slots;
+    const bool alt = ctx->render_slot == 1;
+    if (alt && !ctx->d_next_chunk_alt) {
+        CU_TRY(ctx, cudaMalloc(&ctx->d_next_chunk_alt, 8 * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemset(ctx->d_next_chunk_alt, 0, 8 * sizeof(uint32_t)));
     }
-    rp.queue = ctx->d_queue, rp.queue_count = ctx->d_next_chunk + 1, rp.queue_cursor = ctx->d_next_chunk + 2;
-    rp.queue_count_back = ctx->d_next_chunk + 3; // zeroed with the other counters below
-    rp.queue_capacity   = (uint32_t)ctx->queue_capacity;
+    uint32_t *chunk_ctr        = alt ? ctx->d_next_chunk_alt : ctx->d_next_chunk;
+    NeuralQueueEntry *&queue   = alt ? ctx->d_queue_alt : ctx->d_queue;
+    size_t &queue_capacity     = alt ? ctx->queue_capacity_alt : ctx->queue_capacity;
+    rp.next_chunk    = chunk_ctr;
+    const size_t slots = spp_count > 1u ? (size_t)pixel_count * spp_count : (size_t)total; // path / queue slots this launch may use
+    if (queue_capacity < slots) {
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        cudaFree(queue);
+        queue = nullptr, queue_capacity = 0;
+        CU_TRY(ctx, cudaMalloc(&queue, slots * sizeof(NeuralQueueEntry)));
+        queue_capacity = slots;
+    }
+    rp.queue = queue, rp.queue_count = chunk_ctr + 1, rp.queue_cursor = chunk_ctr + 2;
+    rp.queue_count_back = chunk_ctr + 3; // zeroed with the other counters below
+    rp.queue_capacity   = (uint32_t)queue_capacity;
     rp.sample_idx    = (int)accumulated_spp;
     rp.sample_offset = (int)sample_offset;
     rp.accum = ctx->accum, rp.ldr = ctx->ldr, rp.hits = ctx->hits;
@@ -1578,7 +1598,7 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     rp.ema_weight     = ctx->scene_const.ema_weight;
     rp.counters       = ctx->d_counters;
     const NetConst nc = make_net_const(ctx);
-    CU_TRY(ctx, cudaMemsetAsync(ctx->d_next_chunk, 0, 4 * sizeof(uint32_t), st));
+    CU_TRY(ctx, cudaMemsetAsync(chunk_ctr, 0, 4 * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
     if (ctx->l2_prefetch) {
         // warm L2 with the tables the scattered gathers of this frame touch (see k_prefetch_l2)
@@ -2088,6 +2108,7 @@ int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
         return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
     if (!ctx->pipe_render) {
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render, cudaStreamNonBlocking));
+        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render_alt, cudaStreamNonBlocking));
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
         for (int k = 0; k < 2; k++) {
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_rendered[k], cudaEventDisableTiming));
@@ -2105,15 +2126,24 @@ int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
     }
     if (camera_host)
         ctx->camera = *camera_host;
+    // Independent frames (accumulated_spp == 0: the accumulation is overwritten, never read) at max_depth 1 render on one stream
+    // per slot with their own queue and counters, so the kernels of consecutive frames overlap; accumulating samples and the
+    // multi-bounce pipeline (one set of path lists) stay on a single stream.
+    const bool concurrent  = accumulated_spp == 0 && ctx->max_depth == 1 && !ctx->mega_kernel && !ctx->scene_const.ema_accumulate && !ctx->hits;
+    cudaStream_t rstream   = (concurrent && slot == 1) ? ctx->pipe_render_alt : ctx->pipe_render;
+    if (!concurrent) // order after whatever the other slot's stream still runs
+        CU_TRY(ctx, cudaStreamWaitEvent(rstream, ctx->pipe_rendered[slot ^ 1u], 0));
     // the slot's previous copy must have drained before the kernels overwrite its frame buffer
-    CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_render, ctx->pipe_copied[slot], 0));
-    uchar4 *saved = ctx->ldr;
-    ctx->ldr      = ctx->d_ldr_slot[slot];
-    const int rc  = nbvh_render(ctx, accumulated_spp, sample_offset, 0, 0, ctx->pipe_render);
-    ctx->ldr      = saved;
+    CU_TRY(ctx, cudaStreamWaitEvent(rstream, ctx->pipe_copied[slot], 0));
+    uchar4 *saved     = ctx->ldr;
+    ctx->ldr          = ctx->d_ldr_slot[slot];
+    ctx->render_slot  = (concurrent && slot == 1) ? 1 : 0;
+    const int rc      = nbvh_render(ctx, accumulated_spp, sample_offset, 0, 0, rstream);
+    ctx->render_slot  = 0;
+    ctx->ldr          = saved;
     if (rc != NBVH_OK)
         return rc;
-    CU_TRY(ctx, cudaEventRecord(ctx->pipe_rendered[slot], ctx->pipe_render));
+    CU_TRY(ctx, cudaEventRecord(ctx->pipe_rendered[slot], rstream));
     CU_TRY(ctx, cudaStreamWaitEvent(ctx->pipe_copy, ctx->pipe_rendered[slot], 0));
     CU_TRY(ctx, cudaMemcpyAsync(ldr_host, ctx->d_ldr_slot[slot], n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->pipe_copy));
     CU_TRY(ctx, cudaEventRecord(ctx->pipe_copied[slot], ctx->pipe_copy));
