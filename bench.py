@@ -392,6 +392,11 @@ def main():
         n2 = max(5, min(args.steps, 30))
         ms2 = time_frames(lambda i: pmod.neural_render((3 + i) * world + rank, 0, stream=stream.cuda_stream), n2)
         c2 = {k: v / n2 for k, v in pmod.counters().items()}
+        # the same with 4 samples of the frame per launch sequence (nbvh_render_samples)
+        for i in range(2):
+            pmod.neural_render_samples(4 * i, 4, stream=stream.cuda_stream)
+        barrier()
+        ms2_multi = time_frames(lambda i: pmod.neural_render_samples(4 * ((2 + i) * world + rank), 4, stream=stream.cuda_stream), max(3, n2 // 4)) / 4.0
         # config 4: 3840x2160, max_depth 4, 16 spp; image tiles (8x4-pixel blocks) are dealt round-robin to the ranks
         # (nbvh_render_interleaved: balances the board-vs-pieces cost skew), each rank accumulates its tiles over 16 samples,
         # one NCCL reduce of the RGBA32F image to rank 0 at the end (the tiles are disjoint, the other ranks contribute zeros)
@@ -418,19 +423,20 @@ def main():
         ms4 = time_frames(image4, n4)
         c4 = {k: v / n4 for k, v in pmod.counters().items()}
         pmod.close()
-        tt_ = torch.tensor([ms2, ms4, c4["rays"], c4["queries"]], dtype=torch.float64, device=dev)
+        tt_ = torch.tensor([ms2, ms4, c4["rays"], c4["queries"], ms2_multi], dtype=torch.float64, device=dev)
         if world > 1:
             tmax = tt_.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(tt_, op=dist.ReduceOp.SUM)
-            ms2, ms4 = float(tmax[0]), float(tmax[1])
+            ms2, ms4, ms2_multi = float(tmax[0]), float(tmax[1]), float(tmax[4])
             c4["rays"], c4["queries"] = float(tt_[2]), float(tt_[3])
         path_info["config2b"] = {
             "workload": "Chess hybrid neural path tracing, shipped settings (max_depth 3, Russian roulette from depth 2, HDRI, chessboard glTF "
                         "material), 1920x1080, 1 spp per rank per step", "ms_per_frame": ms2, "frames": n2,
             "Mpixels_s": world * n_rays / (ms2 * 1e-3) / 1e6, "rays_per_frame": c2["rays"],
             "Mrays_s_all_rays": world * c2["rays"] / (ms2 * 1e-3) / 1e6, "queries_per_frame": c2["queries"],
-            "neural_queries_per_s": world * c2["queries"] / (ms2 * 1e-3), "launches_per_frame": 9}
+            "neural_queries_per_s": world * c2["queries"] / (ms2 * 1e-3), "launches_per_frame": 9,
+            "multi_sample": {"samples_per_launch": 4, "ms_per_sample_frame": ms2_multi, "Mpixels_s": world * n_rays / (ms2_multi * 1e-3) / 1e6}}
         path_info["config4"] = {
             "workload": "Chess + shipped HDRI, max_depth 4, 3840x2160, 16 spp; 8x4-pixel tiles dealt round-robin to %d rank(s), "
                         "RGBA32F image reduced to rank 0; %d sample(s) per launch sequence (nbvh_render_samples)" % (world, spl4), "scaling": "strong",
