@@ -407,7 +407,7 @@ def main():
         img4 = torch.empty_like(accum4) if world > 1 else accum4
 
         # samples per launch sequence: as many as keep pixels x samples near one 4K frame of path slots per rank
-        spl4 = max(2, min(spp4, world))
+        spl4 = min(spp4, max(4, world))
 
         def image4(_i):
             for s_ in range(0, spp4, spl4):
