@@ -27,12 +27,28 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        build_host()
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     print("[nbvh_b200.build]", " ".join(cmd), flush=True)
     subprocess.check_call(cmd)
+    build_host()
     return LIB
+
+
+def build_host():
+    """The C++ host side above the C ABI: include/nbvh_b200.hpp (header-only wrapper) + the command line host nbvh_render_cli."""
+    src = os.path.join(HERE, "host", "nbvh_render_cli.cpp")
+    out = os.path.join(HERE, "host", "nbvh_render_cli")
+    deps = [src, os.path.join(HERE, "..", "include", "nbvh_b200.hpp"), os.path.join(HERE, "..", "include", "nbvh_b200.h"), LIB]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(HERE, "..", "include"), "-I/usr/local/cuda/include", src, "-L" + HERE,
+           "-lnbvh_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN/..", "-o", out]
+    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return out
 
 
 def build_variant(name, defines):
