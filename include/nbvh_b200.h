@@ -454,6 +454,24 @@ uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);
 
+/* ---- f4: result writers and configuration round trip ------------------------------------------------------------ */
+/* == write_exr (include/base/bitmap.h:97-182) as called by RenderApp::save_framebuffer (src/app/render_app.cpp:132-165): scanline
+ * OpenEXR, channels A,B,G,R as 32-bit float, no compression, every value divided by rgb_renormalisation.  Host memory only; the file
+ * is byte-identical to the one the reference's tinyexr writes. */
+int nbvh_write_exr_host(const char *path, uint32_t width, uint32_t height, const float *rgba_host, float rgb_renormalisation);
+/* == NeuralBVHRenderer::save_image (src/cuda/neural/neural_bvh_renderer_init.cu:361-383): accumulation buffer / accumulated_spp -> EXR;
+ * NBVH_ERR_STATE while scene_constants.ema_accumulate is on (the reference refuses as well). */
+int nbvh_save_image_exr(nbvh_ctx *ctx, const char *path, uint32_t accumulated_spp, void *stream);
+/* == FrameTimer::write_to_file (include/utils/frame_timer.h:33-58): learning (with losses) / inference (losses NULL) timing CSV */
+int nbvh_write_frame_times_csv_host(const char *path, const double *frame_ms, const float *losses_or_null, uint32_t n);
+/* Result file names of validation mode (neural_bvh_renderer_init.cu:328-372).  kind 0: results/<base>_<variant>_spp_<n>.exr,
+ * 1: results/<base>_<variant>_learning_spp_<n>.csv, 2: results/<base>_<variant>_inference_spp_<n>.csv */
+int nbvh_result_path(const char *scene_dir, const char *base_config_name, const char *variant_config_name, int kind,
+                     uint32_t accumulated_spp, char *out, size_t out_capacity);
+/* == the module-owned part of NeuralBVHRenderer::save_config (neural_bvh_renderer_init.cu:406-509), reference key names; loading the
+ * result with nbvh_load_config_json restores every constant block bit for bit.  *needed = bytes required including the NUL. */
+int nbvh_save_config_json(const nbvh_ctx *ctx, char *out, size_t capacity, size_t *needed);
+
 #ifdef __cplusplus
 }
 #endif

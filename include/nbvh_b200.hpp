@@ -7,6 +7,7 @@
 #pragma once
 #include "nbvh_b200.h"
 
+#include <chrono>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -116,6 +117,21 @@ public:
         return max_loss;
     }
 
+    // ---- results (f4): save_image / save_config / save_performance_metrics (neural_bvh_renderer_init.cu:328-383,406-509)
+    void save_image(const std::string &path, uint32_t accumulated_spp, void *stream = nullptr)
+    {
+        check(nbvh_save_image_exr(m_ctx, path.c_str(), accumulated_spp, stream));
+    }
+    std::string save_config() const
+    {
+        size_t needed = 0;
+        nbvh_save_config_json(m_ctx, nullptr, 0, &needed);
+        std::string text(needed, '\0');
+        check(nbvh_save_config_json(m_ctx, text.data(), needed, nullptr));
+        text.resize(needed - 1);
+        return text;
+    }
+
     std::vector<uint64_t> counters() const
     {
         std::vector<uint64_t> c(NBVH_CNT_COUNT);
@@ -131,6 +147,35 @@ private:
             throw std::runtime_error(std::string("nbvh_b200: ") + nbvh_last_error(m_ctx));
     }
     nbvh_ctx *m_ctx = nullptr;
+};
+
+// == FrameTimer (include/utils/frame_timer.h): start_frame / end_frame / write_to_file with the reference's CSV layout
+class FrameTimer {
+public:
+    void start_frame(uint32_t frame_idx)
+    {
+        if (frame_idx == 0)
+            m_frame_times.clear();
+        m_start = std::chrono::high_resolution_clock::now();
+    }
+    void end_frame()
+    {
+        const auto now = std::chrono::high_resolution_clock::now();
+        m_frame_times.push_back(std::chrono::duration<double, std::milli>(now - m_start).count());
+        m_start = now;
+    }
+    bool write_to_file(const std::string &filename, const std::vector<float> *losses = nullptr) const
+    {
+        if (losses && losses->size() < m_frame_times.size())
+            return false;
+        return nbvh_write_frame_times_csv_host(filename.c_str(), m_frame_times.data(), losses ? losses->data() : nullptr,
+                                               (uint32_t)m_frame_times.size()) == NBVH_OK;
+    }
+    const std::vector<double> &frame_times() const { return m_frame_times; }
+
+private:
+    std::chrono::time_point<std::chrono::high_resolution_clock> m_start;
+    std::vector<double> m_frame_times;
 };
 
 } // namespace nbvh_b200

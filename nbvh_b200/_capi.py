@@ -142,6 +142,11 @@ SYMBOLS = {
     "nbvh_build_blas": (_i, [_vp, _vp, _vp, _u32, _vp, _vp, C.POINTER(_u32), _vp]),
     "nbvh_render_host_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _u32]),
     "nbvh_render_host_wait": (_i, [_vp, _u32]),
+    "nbvh_write_exr_host": (_i, [C.c_char_p, _u32, _u32, _vp, _f]),
+    "nbvh_save_image_exr": (_i, [_vp, C.c_char_p, _u32, _vp]),
+    "nbvh_write_frame_times_csv_host": (_i, [C.c_char_p, _vp, _vp, _u32]),
+    "nbvh_result_path": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _i, _u32, C.c_char_p, C.c_size_t]),
+    "nbvh_save_config_json": (_i, [_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nbvh_image_error": (_i, [_vp, _vp, _u32, _i, _i, C.POINTER(_f), _vp]),
     "nbvh_render_host": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_selftest_division": (_i, [_vp, _u64, _u64, C.POINTER(_u64)]),

@@ -217,6 +217,10 @@ struct nbvh_ctx {
     nbvh_path_constants path_const = default_path_constants();
     nbvh_scene_constants scene_const = default_scene_constants();
     nbvh_camera_params camera{};
+    float cam_matrix[16] = {};  // as given to nbvh_set_camera (save_config writes it back)
+    float cam_yfov = 0.f;
+    bool cam_set = false;
+    std::string dir_enc_type = "Identity"; // direction_encoding.type: kept for save_config (unused while input_segment_direction_dim == 0)
     nbvh_bbox3f scene_bbox{};
     bool scene_bbox_set = false;
     nbvh_network_desc net_desc{8, 4, 18, 8, 2.0f, 64, 4};
@@ -834,6 +838,7 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
         o.epsilon        = (float)op.value("epsilon", (double)1e-8f);
         o.l2_reg         = (float)op.value("l2_reg", (double)1e-8f);
     }
+    ctx->dir_enc_type  = mod.object("direction_encoding").value("type", std::string("Identity"));
     ctx->training_step = (uint32_t)rend.value("training_step", 0.0);
     // framebuffer size + camera
     if (const Json *fb = scene.find("fb_size")) {
@@ -915,6 +920,8 @@ int nbvh_set_camera(nbvh_ctx *ctx, const float matrix16_host[16], float yfov_rad
     if (ctx->fb_w == 0 || ctx->fb_h == 0)
         return fail(ctx, NBVH_ERR_STATE, "set the framebuffer size before the camera (aspect ratio)");
     ctx->camera = camera_from_matrix(matrix16_host, yfov_rad, ctx->fb_w, ctx->fb_h);
+    memcpy(ctx->cam_matrix, matrix16_host, sizeof(ctx->cam_matrix));
+    ctx->cam_yfov = yfov_rad, ctx->cam_set = true;
     return NBVH_OK;
 }
 
@@ -2395,3 +2402,264 @@ int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx) { return ctx ? ctx->training_step : 0; }
 
 } // extern "C"
+
+// ---- f4: result writers -------------------------------------------------------------------------------------------
+// == write_exr (include/base/bitmap.h:97-182) as the reference calls it from RenderApp::save_framebuffer (render_app.cpp:132-165):
+// scanline OpenEXR 2.0, channels A, B, G, R as 32-bit float, no compression (one scanline per chunk), every value -- alpha too --
+// divided by rgb_renormalisation (the accumulated sample count).  Byte-identical to the file the reference's tinyexr writes
+// (tests/golden/ref_exr_7x5.exr, generated by oracle/ref_tools/exr_golden.cpp).
+namespace {
+void exr_attr(std::string &h, const char *name, const char *type, const void *data, int32_t size)
+{
+    h.append(name, strlen(name) + 1);
+    h.append(type, strlen(type) + 1);
+    h.append(reinterpret_cast<const char *>(&size), 4);
+    h.append(reinterpret_cast<const char *>(data), (size_t)size);
+}
+} // namespace
+
+int nbvh_write_exr_host(const char *path, uint32_t width, uint32_t height, const float *rgba_host, float rgb_renormalisation)
+{
+    if (!path || !rgba_host || width == 0 || height == 0)
+        return NBVH_ERR_INVALID_ARG;
+    std::string h;
+    const unsigned char magic[8] = {0x76, 0x2f, 0x31, 0x01, 2, 0, 0, 0};
+    h.append(reinterpret_cast<const char *>(magic), 8);
+    std::string ch;
+    for (const char name : {'A', 'B', 'G', 'R'}) {
+        ch.push_back(name), ch.push_back('\0');
+        const int32_t v[4] = {2 /* FLOAT */, 0 /* pLinear + 3 reserved bytes */, 1, 1};
+        ch.append(reinterpret_cast<const char *>(v), 16);
+    }
+    ch.push_back('\0');
+    exr_attr(h, "channels", "chlist", ch.data(), (int32_t)ch.size());
+    const unsigned char zero = 0;
+    exr_attr(h, "compression", "compression", &zero, 1);
+    const int32_t win[4] = {0, 0, (int32_t)width - 1, (int32_t)height - 1};
+    exr_attr(h, "dataWindow", "box2i", win, 16);
+    exr_attr(h, "displayWindow", "box2i", win, 16);
+    exr_attr(h, "lineOrder", "lineOrder", &zero, 1);
+    const float one = 1.f, centre[2] = {0.f, 0.f};
+    exr_attr(h, "pixelAspectRatio", "float", &one, 4);
+    exr_attr(h, "screenWindowCenter", "v2f", centre, 8);
+    exr_attr(h, "screenWindowWidth", "float", &one, 4);
+    h.push_back('\0');
+    FILE *f = fopen(path, "wb");
+    if (!f)
+        return NBVH_ERR_IO;
+    const size_t row_bytes = (size_t)width * 16, chunk = 8 + row_bytes;
+    std::vector<uint64_t> offsets(height);
+    for (uint32_t y = 0; y < height; y++)
+        offsets[y] = h.size() + (size_t)height * 8 + (size_t)y * chunk;
+    bool ok = fwrite(h.data(), 1, h.size(), f) == h.size() && fwrite(offsets.data(), 8, height, f) == height;
+    std::vector<float> row((size_t)width * 4);
+    for (uint32_t y = 0; y < height && ok; y++) {
+        const float *src = rgba_host + (size_t)y * width * 4;
+        for (int c = 0; c < 4; c++) // file channel c = A, B, G, R = source component 3 - c
+            for (uint32_t x = 0; x < width; x++)
+                row[(size_t)c * width + x] = src[4 * x + (3 - c)] / rgb_renormalisation;
+        const int32_t hdr[2] = {(int32_t)y, (int32_t)row_bytes};
+        ok = fwrite(hdr, 4, 2, f) == 2 && fwrite(row.data(), 4, row.size(), f) == row.size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? NBVH_OK : NBVH_ERR_IO;
+}
+
+// == NeuralBVHRenderer::save_image (neural_bvh_renderer_init.cu:361-383): reads the accumulation buffer back and writes it divided by
+// accumulated_spp; refuses while ema_accumulate is on, like the reference ("would just save incorrect images").
+int nbvh_save_image_exr(nbvh_ctx *ctx, const char *path, uint32_t accumulated_spp, void *stream)
+{
+    if (!ctx || !path || accumulated_spp == 0)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->accum)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    if (ctx->scene_const.ema_accumulate)
+        return fail(ctx, NBVH_ERR_STATE, "saving images while ema_accumulate is on is not supported");
+    std::vector<float> host((size_t)ctx->fb_w * ctx->fb_h * 4);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(ctx, cudaMemcpyAsync(host.data(), ctx->accum, host.size() * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    const int rc = nbvh_write_exr_host(path, ctx->fb_w, ctx->fb_h, host.data(), (float)accumulated_spp);
+    return rc == NBVH_OK ? rc : fail(ctx, rc, std::string("cannot write ") + path);
+}
+
+// == FrameTimer::write_to_file (include/utils/frame_timer.h:33-58): "frame index,frame time (ms)[, loss]" and one line per frame with
+// the default ostream formatting (6 significant digits).
+int nbvh_write_frame_times_csv_host(const char *path, const double *frame_ms, const float *losses_or_null, uint32_t n)
+{
+    if (!path || (!frame_ms && n))
+        return NBVH_ERR_INVALID_ARG;
+    FILE *f = fopen(path, "w");
+    if (!f)
+        return NBVH_ERR_IO;
+    fputs(losses_or_null ? "frame index,frame time (ms), loss\n" : "frame index,frame time (ms)\n", f);
+    for (uint32_t i = 0; i < n; i++) {
+        if (losses_or_null)
+            fprintf(f, "%u,%g,%g\n", i, frame_ms[i], (double)losses_or_null[i]);
+        else
+            fprintf(f, "%u,%g\n", i, frame_ms[i]);
+    }
+    return fclose(f) == 0 ? NBVH_OK : NBVH_ERR_IO;
+}
+
+// Result file names of the reference's validation mode (neural_bvh_renderer_init.cu:328-372):
+// kind 0: <dir>/results/<base>_<variant>_spp_<n>.exr, 1: ..._learning_spp_<n>.csv, 2: ..._inference_spp_<n>.csv
+int nbvh_result_path(const char *scene_dir, const char *base_config_name, const char *variant_config_name, int kind, uint32_t accumulated_spp,
+                     char *out, size_t out_capacity)
+{
+    if (!scene_dir || !base_config_name || !variant_config_name || !out || kind < 0 || kind > 2)
+        return NBVH_ERR_INVALID_ARG;
+    const char *tag[] = {"", "_learning", "_inference"};
+    const std::string p = std::string(scene_dir) + "/results/" + base_config_name + "_" + variant_config_name + tag[kind] + "_spp_" +
+                          std::to_string(accumulated_spp) + (kind == 0 ? ".exr" : ".csv");
+    if (p.size() + 1 > out_capacity)
+        return NBVH_ERR_INVALID_ARG;
+    memcpy(out, p.c_str(), p.size() + 1);
+    return NBVH_OK;
+}
+
+// == the module-owned part of NeuralBVHRenderer::save_config (neural_bvh_renderer_init.cu:406-509): cuda_scene {fb_size, camera,
+// scene_constants} and neural_bvh_renderer {neural_module {max_depth, pt_output_constants, path_module_constants, bvh_module_constants,
+// network, optimizer, segment_encoding, direction_encoding}, training_step, bvh_constants} with the reference's key names, floats
+// printed with 9 significant digits so that nbvh_load_config_json(save(x)) restores every constant block bit for bit.  The renderer
+// adds the keys it owns (batch_size, tree_cut_learning, bvh_split_scheduler, ...).  Writes at most `capacity` bytes (NUL-terminated)
+// and the needed size (including the NUL) into *needed.
+int nbvh_save_config_json(const nbvh_ctx *ctx, char *out, size_t capacity, size_t *needed)
+{
+    if (!ctx || (!out && capacity))
+        return NBVH_ERR_INVALID_ARG;
+    std::string s;
+    char buf[64];
+    bool first = true;
+    auto key = [&](const char *k) {
+        if (!first)
+            s += ", ";
+        first = false;
+        s += "\"", s += k, s += "\": ";
+    };
+    auto open  = [&](const char *k) { key(k), s += "{", first = true; };
+    auto close = [&]() { s += "}", first = false; };
+    auto F = [&](const char *k, float v) { key(k), snprintf(buf, sizeof(buf), "%.9g", (double)v), s += buf; };
+    auto I = [&](const char *k, long long v) { key(k), s += std::to_string(v); };
+    auto B = [&](const char *k, bool v) { key(k), s += v ? "true" : "false"; };
+    auto S = [&](const char *k, const char *v) { key(k), s += "\"", s += v, s += "\""; };
+    s += "{", first = true;
+    open("cuda_scene");
+    key("fb_size"), s += "[" + std::to_string(ctx->fb_w) + ", " + std::to_string(ctx->fb_h) + "]";
+    if (ctx->cam_set) {
+        open("camera");
+        S("type", "perspective");
+        F("yfov", ctx->cam_yfov);
+        key("matrix"), s += "[";
+        for (int i = 0; i < 16; i++)
+            snprintf(buf, sizeof(buf), i ? ", %.9g" : "%.9g", (double)ctx->cam_matrix[i]), s += buf;
+        s += "]";
+        close();
+    }
+    {
+        const nbvh_scene_constants &c = ctx->scene_const;
+        open("scene_constants");
+        B("force_constant_material", c.force_constant_material), F("constant_roughness", c.constant_roughness);
+        F("constant_specular", c.constant_specular), F("constant_metallic", c.constant_metallic);
+        F("envmap_rotation", c.envmap_rotation), F("envmap_strength", c.envmap_strength);
+        B("ema_accumulate", c.ema_accumulate), F("ema_weight", c.ema_weight), B("envmap_eval", c.envmap_eval);
+        B("emission_eval", c.emission_eval), B("skylike_background", c.skylike_background);
+        close();
+    }
+    close();
+    open("neural_bvh_renderer");
+    S("bvh_module_type", "Path");
+    open("neural_module");
+    I("max_depth", ctx->max_depth);
+    {
+        const nbvh_pt_output_constants &c = ctx->pt_const;
+        open("pt_output_constants");
+        I("output_visibility_dim", c.output_visibility_dim), I("output_depth_dim", c.output_depth_dim);
+        I("output_normal_dim", c.output_normal_dim), I("output_albedo_dim", c.output_albedo_dim);
+        I("output_network_dims", c.output_network_dims);
+        S("visibility_loss", kLossTypes[c.visibility_loss]), S("depth_loss", kLossTypes[c.depth_loss]);
+        S("normal_loss", kLossTypes[c.normal_loss]), S("albedo_loss", kLossTypes[c.albedo_loss]);
+        F("visibility_loss_scale", c.visibility_loss_scale), F("depth_loss_scale", c.depth_loss_scale);
+        F("normal_loss_scale", c.normal_loss_scale), F("albedo_loss_scale", c.albedo_loss_scale);
+        S("depth_learning_mode", kDepthModes[c.depth_learning_mode]);
+        B("output_normal_linear_activation", c.output_normal_linear_activation);
+        B("output_depth_linear_activation", c.output_depth_linear_activation);
+        B("output_albedo_linear_activation", c.output_albedo_linear_activation);
+        B("visibility_masking_loss", c.visibility_masking_loss);
+        F("primary_visibility_threshold", c.primary_visibility_threshold);
+        F("secondary_visibility_threshold", c.secondary_visibility_threshold);
+        F("depth_epsilon", c.depth_epsilon), F("fixed_depth_epsilon", c.fixed_depth_epsilon);
+        close();
+    }
+    {
+        const nbvh_path_constants &c = ctx->path_const;
+        open("path_module_constants");
+        S("output_mode", kOutputModes[c.output_mode]), F("normal_epsilon_offset", c.normal_epsilon_offset);
+        B("apply_russian_roulette", c.apply_russian_roulette), I("rr_start_depth", c.rr_start_depth);
+        F("neural_roughness", c.neural_roughness), F("neural_specular", c.neural_specular), F("neural_metallic", c.neural_metallic);
+        close();
+    }
+    {
+        const nbvh_module_constants &c = ctx->module_const;
+        open("bvh_module_constants");
+        I("input_segment_point_dim", c.input_segment_point_dim), I("input_segment_points", c.input_segment_points);
+        I("input_segment_points_dim", c.input_segment_points_dim), I("input_segment_direction_dim", c.input_segment_direction_dim);
+        I("input_network_dims", c.input_network_dims), S("segment_distribution", kSegmentDistributions[c.segment_distribution]);
+        B("antialias_direction", c.antialias_direction), B("merge_operator", c.merge_operator);
+        B("apply_encoding_trafo", c.apply_encoding_trafo);
+        close();
+    }
+    {
+        const nbvh_network_desc &d = ctx->net_desc;
+        open("network");
+        S("network", "FullyFusedMLP"), I("n_neurons", d.n_neurons), I("n_hidden_layers", d.n_hidden_layers);
+        S("activation", "ReLU"), S("output_activation", "Sigmoid");
+        close();
+        const nbvh_optimizer_desc &o = ctx->opt_desc;
+        open("optimizer");
+        S("type", "Adam"), F("learning_rate", o.learning_rate), I("decay_start", o.decay_start), I("decay_interval", o.decay_interval);
+        F("decay_base", o.decay_base), F("beta1", o.beta1), F("beta2", o.beta2), F("epsilon", o.epsilon), F("l2_reg", o.l2_reg);
+        F("relative_decay", 0.f), F("absolute_decay", 0.f), B("adabound", false);
+        close();
+        open("segment_encoding");
+        S("type", "HashGrid");
+        open("hashgrid_options");
+        S("otype", "HashGrid"), I("n_levels", d.n_levels), I("n_features_per_level", d.n_features_per_level);
+        I("log2_hashmap_size", d.log2_hashmap_size), I("base_resolution", d.base_resolution), F("per_level_scale", d.per_level_scale);
+        S("hash", "CoherentPrime"), S("interpolation", "Linear"), B("stochastic_interpolation", false);
+        close();
+        S("reduction", "Concatenation");
+        close();
+        open("direction_encoding");
+        S("type", ctx->dir_enc_type.c_str());
+        close();
+    }
+    close(); // neural_module
+    I("training_step", ctx->training_step);
+    {
+        const nbvh_renderer_constants &c = ctx->bvh_const;
+        open("bvh_constants");
+        I("num_lods_learned", c.num_lods_learned), I("current_learned_lod", c.current_learned_lod), I("rendered_lod", c.rendered_lod);
+        B("ignore_neural_blas", c.ignore_neural_blas), F("leaf_boundary_sampling_ratio", c.leaf_boundary_sampling_ratio);
+        F("inference_mint_epsilon", c.inference_mint_epsilon), F("inference_maxt_epsilon", c.inference_maxt_epsilon);
+        F("learning_mint_epsilon", c.learning_mint_epsilon), F("learning_maxt_epsilon", c.learning_maxt_epsilon);
+        F("sampling_bbox_scaling", c.sampling_bbox_scaling), F("fixed_node_dilation", c.fixed_node_dilation);
+        F("node_extent_dilation", c.node_extent_dilation), F("loss_exposure", c.loss_exposure);
+        B("show_loss_heuristic", c.show_loss_heuristic), B("ellipsoidal_bvh", c.ellipsoidal_bvh), B("rescale_ellipsoid", c.rescale_ellipsoid);
+        I("log2_bvh_max_traversals", c.log2_bvh_max_traversals), B("sample_cosine_weighted", c.sample_cosine_weighted);
+        B("backface_bounce_training", c.backface_bounce_training), I("max_training_bounces", c.max_training_bounces);
+        B("training_node_survival", c.training_node_survival), F("survival_probability_scale", c.survival_probability_scale);
+        F("min_rr_survival_prob", c.min_rr_survival_prob);
+        close();
+    }
+    close(); // neural_bvh_renderer
+    s += "}";
+    if (needed)
+        *needed = s.size() + 1;
+    if (capacity) {
+        const size_t n = s.size() < capacity - 1 ? s.size() : capacity - 1;
+        memcpy(out, s.data(), n);
+        out[n] = '\0';
+    }
+    return s.size() + 1 <= capacity || !capacity ? NBVH_OK : NBVH_ERR_INVALID_ARG;
+}

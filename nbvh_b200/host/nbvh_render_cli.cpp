@@ -2,9 +2,10 @@
 // reduced to a command line tool.  Loads a scene directory in the layout tools/make_fixtures.py writes (config JSON, .nbvh tree-cut,
 // network_models JSON unchanged from the reference; TLAS / BLAS arrays as raw files), uploads it (CudaBackend::build_and_upload,
 // /root/reference/src/cuda/cuda_backend.cpp:186-441), renders `spp` samples through nbvh_b200::NeuralPathModule::neural_render
-// (== NeuralBVHRenderer::render -> neural_render, neural_bvh_renderer.cu:292-312) and writes the 8-bit frame as a PPM.
+// (== NeuralBVHRenderer::render -> neural_render, neural_bvh_renderer.cu:292-312) and writes the 8-bit frame as a PPM, or (out.exr) the accumulation / spp
+// as the reference's save_image does.
 //
-// usage: nbvh_render_cli <scene_dir> <base_config_name> <out.ppm> [W H] [spp] [max_depth]
+// usage: nbvh_render_cli <scene_dir> <base_config_name> <out.ppm | out.exr> [W H] [spp] [max_depth]
 // build: g++ -std=c++17 -O2 -Iinclude nbvh_b200/host/nbvh_render_cli.cpp -Lnbvh_b200 -lnbvh_b200 -L/usr/local/cuda/lib64 -lcudart
 #include "nbvh_b200.hpp"
 
@@ -97,13 +98,17 @@ int main(int argc, char **argv)
             mod.neural_render(s, 0);
         mod.neural_render_host(spp > 1 ? spp - 1 : 0, 0, ldr.data());
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        FILE *f = fopen(out.c_str(), "wb");
-        if (!f)
-            throw std::runtime_error("cannot write " + out);
-        fprintf(f, "P6\n%u %u\n255\n", W, H);
-        for (size_t i = 0; i < (size_t)W * H; ++i)
-            fwrite(&ldr[4 * i], 1, 3, f);
-        fclose(f);
+        if (out.size() > 4 && out.compare(out.size() - 4, 4, ".exr") == 0) {
+            mod.save_image(out, spp); // == NeuralBVHRenderer::save_image: accumulation / spp as an A,B,G,R float EXR
+        } else {
+            FILE *f = fopen(out.c_str(), "wb");
+            if (!f)
+                throw std::runtime_error("cannot write " + out);
+            fprintf(f, "P6\n%u %u\n255\n", W, H);
+            for (size_t i = 0; i < (size_t)W * H; ++i)
+                fwrite(&ldr[4 * i], 1, 3, f);
+            fclose(f);
+        }
         const auto c = mod.counters();
         printf("{\"module\": \"%s\", \"W\": %u, \"H\": %u, \"spp\": %u, \"max_depth\": %d, \"tree_cut_nodes\": %u, \"n_params\": %llu, "
                "\"rays\": %llu, \"queries\": %llu, \"ms_after_first_sample\": %.3f}\n",

@@ -348,6 +348,19 @@ class NeuralPathModule:
                                                C.byref(out), stream))
         return out.value
 
+    # ------------------------------------------------------------------ results (f4)
+    def save_image(self, path, accumulated_spp, stream=None):
+        """== NeuralBVHRenderer::save_image (neural_bvh_renderer_init.cu:361-383): accumulation / accumulated_spp as an A,B,G,R float EXR."""
+        self._check(self._lib.nbvh_save_image_exr(self._h, os.fsencode(path), int(accumulated_spp), stream))
+
+    def save_config(self):
+        """== the module-owned part of NeuralBVHRenderer::save_config (neural_bvh_renderer_init.cu:406-509); returns the JSON text."""
+        need = C.c_size_t(0)
+        self._lib.nbvh_save_config_json(self._h, None, 0, C.byref(need))
+        buf = C.create_string_buffer(need.value)
+        self._check(self._lib.nbvh_save_config_json(self._h, buf, need.value, None))
+        return buf.value.decode()
+
     def neural_render_samples(self, first_spp, n_spp, sample_offset=0, shard_index=0, shard_count=1, stream=None):
         """n_spp samples per pixel of an interleaved shard in one launch sequence (max_depth > 1): keeps the persistent kernels full."""
         self._check(self._lib.nbvh_render_samples(self._h, int(first_spp), int(n_spp), int(sample_offset), int(shard_index), int(shard_count),

@@ -77,3 +77,32 @@ def test_cli_frame_equals_python_host_frame(tmp_path, spp):
     mod.close()
     assert ldr[..., :3].std() > 5                 # a real picture, not a constant frame
     assert (cli_img == ldr[..., :3]).all()
+
+
+@pytest.mark.gpu
+def test_cli_exr_is_accumulation_over_spp(tmp_path):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nbvh_b200 import results, scene_io
+    from nbvh_b200._capi import CONST_SCENE
+    root = scene_io.chess_fixture_dir()
+    if root is None:
+        pytest.skip("Chess fixture missing")
+    W, H, spp = 128, 72, 2
+    out = tmp_path / "cli.exr"
+    r = subprocess.run([_cli(), root, scene_io.CHESS_BASE, str(out), str(W), str(H), str(spp), "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    img = results.read_exr(str(out))
+    mod = scene_io.load_chess_module(max_depth=1, envmap_eval=True)
+    sc = mod.get_constants(CONST_SCENE)
+    sc.skylike_background = True
+    mod.set_constants(CONST_SCENE, sc)
+    accum, _ = mod.attach_framebuffer((W, H))
+    for s in range(spp):
+        mod.neural_render(s, 0)
+    torch.cuda.synchronize()
+    want = accum.cpu().numpy() / np.float32(spp)
+    mod.close()
+    assert img.shape == (H, W, 4) and np.isfinite(img).all() and img[..., :3].std() > 0
+    np.testing.assert_allclose(img, want, rtol=0, atol=1e-6)   # same kernels; fp32 atomics free (one sample per pixel per launch)
