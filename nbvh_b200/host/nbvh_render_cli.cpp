@@ -11,6 +11,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -85,18 +86,18 @@ int main(int argc, char **argv)
         if (argc >= 6)
             W = (uint32_t)atoi(argv[4]), H = (uint32_t)atoi(argv[5]);
         if (argc >= 7)
-            spp = (uint32_t)atoi(argv[6]);
+            spp = (uint32_t)std::max(1, atoi(argv[6]));
         mod.set_max_depth(argc >= 8 ? atoi(argv[7]) : 1);
         auto sc        = mod.get_constants<nbvh_scene_constants>(NBVH_CONST_SCENE);
         sc.envmap_eval = true, sc.skylike_background = true; // no HDRI in this tool: the reference's sky-like background
         mod.set_constants(NBVH_CONST_SCENE, sc);
         mod.reinitialise_inference_data(W, H);
         std::vector<uint8_t> ldr((size_t)W * H * 4);
-        mod.neural_render_host(0, 0, ldr.data()); // warm-up + first sample
+        mod.neural_render_host(0, 0, ldr.data()); // warm-up (sample 0 again below: accumulated_spp 0 restarts the accumulation)
         const auto t0 = std::chrono::steady_clock::now();
-        for (uint32_t s = 1; s < spp; ++s)
+        for (uint32_t s = 0; s + 1 < spp; ++s)
             mod.neural_render(s, 0);
-        mod.neural_render_host(spp > 1 ? spp - 1 : 0, 0, ldr.data());
+        mod.neural_render_host(spp - 1, 0, ldr.data()); // last sample + LDR resolve + copy to the host
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (out.size() > 4 && out.compare(out.size() - 4, 4, ".exr") == 0) {
             mod.save_image(out, spp); // == NeuralBVHRenderer::save_image: accumulation / spp as an A,B,G,R float EXR
@@ -111,7 +112,7 @@ int main(int argc, char **argv)
         }
         const auto c = mod.counters();
         printf("{\"module\": \"%s\", \"W\": %u, \"H\": %u, \"spp\": %u, \"max_depth\": %d, \"tree_cut_nodes\": %u, \"n_params\": %llu, "
-               "\"rays\": %llu, \"queries\": %llu, \"ms_after_first_sample\": %.3f}\n",
+               "\"rays\": %llu, \"queries\": %llu, \"ms_all_samples\": %.3f}\n",
                mod.name().c_str(), W, H, spp, mod.max_depth(), mod.neural_bvh_num_nodes(), (unsigned long long)mod.n_params(),
                (unsigned long long)c[NBVH_CNT_RAYS], (unsigned long long)c[NBVH_CNT_QUERIES], ms);
         return 0;
