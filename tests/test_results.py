@@ -156,3 +156,56 @@ def test_save_config_round_trip(source, synthetic):
     assert b.save_config() == text
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_full_validation_run_writes_reference_layout_and_reloads(tmp_path, chess_root):
+    """ValidationMode::Full, headless and short: 40 optimisation steps with tree-cut learning, 3 frames; the files have the reference's
+    names and formats, and a fresh module created from the SAVED config + .nbvh + network JSON reproduces the frame bit for bit."""
+    import torch
+    import nbvh_b200
+    from nbvh_b200 import results, validation
+    from nbvh_b200.scene_io import CHESS_BASE
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    W, H = 160, 90
+    cfg = json.load(open(os.path.join(chess_root, CHESS_BASE + "_neural.json")))
+    cfg["cuda_scene"]["fb_size"] = [W, H]
+    mod = nbvh_b200.NeuralPathModule(json.dumps(cfg))
+    tl, ti, bl, _ = nbvh_b200.load_scene_arrays(chess_root, with_neural_mesh=True, with_attributes=True)
+    mats, texs = nbvh_b200.procedural_materials(int(max(b["material_ids"].max() for b in bl)) + 1)
+    mod.set_scene(tl, ti, bl, materials=mats, textures=texs)
+    mod.max_depth = 1
+    accum, _ = mod.attach_framebuffer((W, H))
+    res = validation.run_full_validation(mod, cfg, str(tmp_path), max_training_steps=40, max_accumulated_spp=3, base=CHESS_BASE, variant="t")
+    p = res["paths"]
+    assert os.path.relpath(p["image"], tmp_path) == "results/%s_t_spp_3.exr" % CHESS_BASE
+    assert os.path.relpath(p["learning_csv"], tmp_path) == "results/%s_t_learning_spp_0.csv" % CHESS_BASE
+    assert os.path.relpath(p["inference_csv"], tmp_path) == "results/%s_t_inference_spp_3.csv" % CHESS_BASE
+    lines = open(p["learning_csv"]).read().splitlines()
+    assert lines[0] == "frame index,frame time (ms), loss" and len(lines) == 41
+    assert abs(float(lines[1].split(",")[2]) - res["losses"][0]) <= 1e-5 * abs(res["losses"][0])
+    assert len(open(p["inference_csv"]).read().splitlines()) == 4
+    assert np.isfinite(res["losses"]).all() and np.mean(res["losses"][-10:]) < 0.8 * max(res["losses"])   # the first splits raise the loss, then it falls
+    assert res["tree_cut_nodes"] > 1                               # the schedule split the root-only cut
+    img = results.read_exr(p["image"])
+    torch.cuda.synchronize()
+    assert (img.view(np.uint32) == (accum.cpu().numpy() / np.float32(3.0)).view(np.uint32)).all()
+    saved = json.load(open(p["config"]))
+    for k in ("batch_size", "tree_cut_learning", "bvh_split_scheduler", "max_training_steps"):
+        assert saved["neural_bvh_renderer"][k] == cfg["neural_bvh_renderer"][k]
+    assert saved["neural_bvh_renderer"]["training_step"] == 40
+    mod.neural_render(0, 0)
+    torch.cuda.synchronize()
+    first = accum.cpu().numpy().copy()
+    mod.close()
+    mod2 = nbvh_b200.NeuralPathModule(open(p["config"]).read())
+    mod2.load_neural_bvh(p["nbvh"])
+    mod2.load_network_model(p["network"])
+    mod2.set_scene(tl, ti, bl, materials=mats, textures=texs)
+    assert mod2.max_depth == 1 and len(mod2.neural_bvh_nodes()) == res["tree_cut_nodes"]
+    accum2, _ = mod2.attach_framebuffer((W, H))
+    mod2.neural_render(0, 0)
+    torch.cuda.synchronize()
+    assert first.std() > 0 and (accum2.cpu().numpy().view(np.uint32) == first.view(np.uint32)).all()
+    mod2.close()
