@@ -740,6 +740,10 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
         c.antialias_direction  = j.value("antialias_direction", d.antialias_direction);
         c.merge_operator       = j.value("merge_operator", d.merge_operator);
         c.apply_encoding_trafo = j.value("apply_encoding_trafo", d.apply_encoding_trafo);
+        // derived, whatever the file says: NeuralBVHModule::reinitialise_neural_model (neural_bvh_module.cu:126-131) -- the shipped
+        // partial configs state only input_segment_points / input_segment_direction_dim
+        c.input_segment_points_dim = c.input_segment_points * c.input_segment_point_dim;
+        c.input_network_dims       = c.input_segment_points_dim + c.input_segment_direction_dim;
         if (c.apply_encoding_trafo)
             return fail(ctx, NBVH_ERR_UNSUPPORTED, "apply_encoding_trafo (asserted off in the reference) is not implemented");
     }
@@ -751,7 +755,8 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
         c.output_depth_dim      = (uint32_t)j.value("output_depth_dim", (double)d.output_depth_dim);
         c.output_normal_dim     = (uint32_t)j.value("output_normal_dim", (double)d.output_normal_dim);
         c.output_albedo_dim     = (uint32_t)j.value("output_albedo_dim", (double)d.output_albedo_dim);
-        c.output_network_dims   = (uint32_t)j.value("output_network_dims", (double)d.output_network_dims);
+        // derived: NeuralPathModule::update_neural_model_module (path_module_init.cu:259-265) overrides the file's value with the sum
+        c.output_network_dims   = c.output_visibility_dim + c.output_depth_dim + c.output_normal_dim + c.output_albedo_dim;
         struct {
             const char *key;
             uint8_t *dst;

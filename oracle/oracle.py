@@ -172,7 +172,10 @@ def make_net(cfg, params_bits):
     net.n_neurons = nw.get("n_neurons", 64)
     n_points = mc.get("input_segment_points", 3)
     net.n_input = n_points * net.n_levels * net.n_features
-    net.n_output = pt.get("output_network_dims", 8)
+    # derived like NeuralPathModule::update_neural_model_module (path_module_init.cu:259-265): the sum of the four dims with the
+    # struct defaults 1, 1, 0, 0 (neural_bvh_module.h:243-248); the file's own "output_network_dims" is ignored by the reference
+    net.n_output = (pt.get("output_visibility_dim", 1) + pt.get("output_depth_dim", 1) + pt.get("output_normal_dim", 0) +
+                    pt.get("output_albedo_dim", 0))
     net.n_output_padded = (net.n_output + 15) // 16 * 16
     params_bits = np.ascontiguousarray(params_bits, dtype=np.uint16)
     net.params = params_bits.ctypes.data

@@ -170,6 +170,12 @@ def main():
     shutil.copy(os.path.join(SCENE_DIR, "configs", "nodes_155_hash_14_lvl_8_tsteps_10000_neural.json"),
                 os.path.join(OUT, "nodes_155_hash_14_lvl_8_tsteps_10000_neural.json"))
 
+    # every shipped configuration of the scene (7 node budgets x 5 hash-table sizes), unchanged: tests/test_shipped_configs.py
+    os.makedirs(os.path.join(OUT, "configs"), exist_ok=True)
+    for name in sorted(os.listdir(os.path.join(SCENE_DIR, "configs"))):
+        if name.endswith("_neural.json"):
+            shutil.copy(os.path.join(SCENE_DIR, "configs", name), os.path.join(OUT, "configs", name))
+
     g = json.load(open(os.path.join(SCENE_DIR, "chess.gltf")))
     if os.path.exists(os.path.join(OUT, "manifest.json")) and "--force" not in sys.argv:
         print("[make_fixtures] scene arrays already present (use --force to rebuild)")
