@@ -454,6 +454,13 @@ uint32_t nbvh_tree_cut_max_depth(const nbvh_ctx *ctx);
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream);
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx);
 
+/* Device-side TLAS build (f3) == CudaBackend::build_tlas (src/cuda/cuda_backend.cpp:312-383): a sweep-SAH binary tree over the root
+ * boxes of the per-mesh BLAS in the TLASNode layout (include/cuda/accel/tlas.cuh:64-68), one mesh per leaf.  mesh_bvhs_device is the
+ * DEVICE descriptor array later passed as nbvh_scene_data.mesh_bvhs; neural_meshes_host lists the meshes the N-BVH stands for.
+ * Outputs are caller-owned device arrays: 2 * num_meshes - 1 nodes, num_meshes blas_indices. */
+int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint32_t num_meshes, const uint32_t *neural_meshes_host,
+                    uint32_t n_neural, nbvh_node32 *tlas_nodes_out, uint32_t *blas_indices_out, void *stream);
+
 /* ---- f4: result writers and configuration round trip ------------------------------------------------------------ */
 /* == write_exr (include/base/bitmap.h:97-182) as called by RenderApp::save_framebuffer (src/app/render_app.cpp:132-165): scanline
  * OpenEXR, channels A,B,G,R as 32-bit float, no compression, every value divided by rgb_renormalisation.  Host memory only; the file

@@ -284,4 +284,112 @@ cudaError_t launch_build_blas(const float *vertices, const uint32_t *indices, ui
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ TLAS build (f3)
+// == CudaBackend::build_tlas (cuda_backend.cpp:312-383) on the device: a binary tree over the root boxes of the per-mesh BLAS, one mesh
+// per leaf, in the TLASNode layout the traversal reads (tlas.cuh:64-68: interior = {box, left child, 0} with the children adjacent,
+// leaf = {box, offset into blas_indices, 1 | 2 for a neural mesh}).  A scene has a handful of meshes (the traversal kernels cap them at
+// 16), so one thread runs an exact sweep-SAH build: per node the best of the (k - 1) x 3 centroid-ordered splits.
+struct BlasDescDev { // layout of nbvh_cuda_blas (include/nbvh_b200.h)
+    uint32_t num_nodes;
+    const unsigned long long *prim_indices;
+    uint32_t num_prim_indices;
+    const float *vertices;
+    const uint32_t *indices;
+    const float *normals;
+    const float *texcoords;
+    const int *material_ids;
+    const uint32_t *material_map;
+    uint32_t num_materials;
+    const float4 *nodes;
+};
+
+constexpr int kMaxTlasMeshes = 32;
+
+__device__ inline float half_area(const float *lo, const float *hi)
+{
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, uint32_t neural_mask, float4 *nodes, uint32_t *blas_indices)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    float lo[kMaxTlasMeshes][3], hi[kMaxTlasMeshes][3];
+    uint32_t order[kMaxTlasMeshes];
+    for (uint32_t i = 0; i < n; i++) {
+        const float4 a = meshes[i].nodes[0], b = meshes[i].nodes[1]; // root_bbox() of the mesh's BLAS
+        lo[i][0] = a.x, lo[i][1] = a.y, lo[i][2] = a.z, hi[i][0] = b.x, hi[i][1] = b.y, hi[i][2] = b.z;
+        order[i] = i;
+    }
+    struct Task {
+        uint32_t node, begin, end;
+    } stack[kMaxTlasMeshes];
+    int ss          = 0;
+    uint32_t n_nodes = 1;
+    stack[ss++]     = {0u, 0u, n};
+    while (ss > 0) {
+        const Task t     = stack[--ss];
+        const uint32_t k = t.end - t.begin;
+        float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (uint32_t i = t.begin; i < t.end; i++)
+            for (int c = 0; c < 3; c++)
+                blo[c] = fminf(blo[c], lo[order[i]][c]), bhi[c] = fmaxf(bhi[c], hi[order[i]][c]);
+        if (k == 1) {
+            const uint32_t mesh = order[t.begin];
+            nodes[2 * t.node]     = make_float4(blo[0], blo[1], blo[2], __uint_as_float(t.begin));
+            nodes[2 * t.node + 1] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float((neural_mask >> mesh) & 1u ? 2u : 1u));
+            continue;
+        }
+        int best_axis = 0;
+        uint32_t best_split = 1;
+        float best_cost = FLT_MAX;
+        for (int pass = 0; pass < 4; pass++) { // 3 evaluation passes, then re-sort along the winning axis
+            const int axis = pass < 3 ? pass : best_axis;
+            for (uint32_t i = t.begin + 1; i < t.end; i++) { // insertion sort by centroid (stable: ties keep the mesh order)
+                const uint32_t m = order[i];
+                const float c    = lo[m][axis] + hi[m][axis];
+                uint32_t j       = i;
+                while (j > t.begin && lo[order[j - 1]][axis] + hi[order[j - 1]][axis] > c)
+                    order[j] = order[j - 1], --j;
+                order[j] = m;
+            }
+            if (pass == 3)
+                break;
+            float right_area[kMaxTlasMeshes];
+            float rlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (uint32_t i = t.end; i-- > t.begin + 1;) {
+                for (int c = 0; c < 3; c++)
+                    rlo[c] = fminf(rlo[c], lo[order[i]][c]), rhi[c] = fmaxf(rhi[c], hi[order[i]][c]);
+                right_area[i - t.begin] = half_area(rlo, rhi);
+            }
+            float llo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (uint32_t s = 1; s < k; s++) { // s meshes on the left
+                for (int c = 0; c < 3; c++)
+                    llo[c] = fminf(llo[c], lo[order[t.begin + s - 1]][c]), lhi[c] = fmaxf(lhi[c], hi[order[t.begin + s - 1]][c]);
+                const float cost = half_area(llo, lhi) * (float)s + right_area[s] * (float)(k - s);
+                if (cost < best_cost)
+                    best_cost = cost, best_axis = axis, best_split = s;
+            }
+        }
+        const uint32_t left = n_nodes;
+        n_nodes += 2;
+        nodes[2 * t.node]     = make_float4(blo[0], blo[1], blo[2], __uint_as_float(left));
+        nodes[2 * t.node + 1] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float(0u));
+        stack[ss++] = {left + 1u, t.begin + best_split, t.end};
+        stack[ss++] = {left, t.begin, t.begin + best_split};
+    }
+    for (uint32_t i = 0; i < n; i++)
+        blas_indices[i] = order[i];
+}
+
+cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, uint32_t neural_mask, float4 *tlas_nodes, uint32_t *blas_indices,
+                              cudaStream_t stream)
+{
+    if (num_meshes == 0 || num_meshes > (uint32_t)kMaxTlasMeshes)
+        return cudaErrorInvalidValue;
+    k_build_tlas<<<1, 32, 0, stream>>>(reinterpret_cast<const BlasDescDev *>(mesh_bvhs_device), num_meshes, neural_mask, tlas_nodes, blas_indices);
+    return cudaGetLastError();
+}
+
 } // namespace nbvh

@@ -2408,6 +2408,28 @@ uint32_t nbvh_training_step_count(const nbvh_ctx *ctx) { return ctx ? ctx->train
 
 } // extern "C"
 
+// Device-side TLAS build (f3): == CudaBackend::build_tlas (cuda_backend.cpp:312-383).  mesh_bvhs_device: the DEVICE array of descriptors
+// that nbvh_scene_data.mesh_bvhs will point to (each BLAS already built: its root box is read from nodes[0]); neural_meshes_host lists
+// the meshes represented by the N-BVH (the reference's m_neural_bvh_indices).  Outputs (device, caller-owned): 2 * num_meshes - 1
+// TLASNode records and num_meshes blas_indices.
+int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint32_t num_meshes, const uint32_t *neural_meshes_host,
+                    uint32_t n_neural, nbvh_node32 *tlas_nodes_out, uint32_t *blas_indices_out, void *stream)
+{
+    if (!ctx || !mesh_bvhs_device || !tlas_nodes_out || !blas_indices_out || num_meshes == 0 || (n_neural && !neural_meshes_host))
+        return NBVH_ERR_INVALID_ARG;
+    if (num_meshes > (uint32_t)kMaxBlas)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "more than 16 BLAS");
+    uint32_t mask = 0;
+    for (uint32_t i = 0; i < n_neural; i++) {
+        if (neural_meshes_host[i] >= num_meshes)
+            return fail(ctx, NBVH_ERR_INVALID_ARG, "neural mesh index out of range");
+        mask |= 1u << neural_meshes_host[i];
+    }
+    CU_TRY(ctx, launch_build_tlas(mesh_bvhs_device, num_meshes, mask, reinterpret_cast<float4 *>(tlas_nodes_out), blas_indices_out,
+                                  (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
 // ---- f4: result writers -------------------------------------------------------------------------------------------
 // == write_exr (include/base/bitmap.h:97-182) as the reference calls it from RenderApp::save_framebuffer (render_app.cpp:132-165):
 // scanline OpenEXR 2.0, channels A, B, G, R as 32-bit float, no compression (one scanline per chunk), every value -- alpha too --

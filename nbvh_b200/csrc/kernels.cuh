@@ -173,5 +173,7 @@ cudaError_t launch_prefetch_l2(const void *const *ptrs, const size_t *bytes, int
 size_t build_blas_workspace_bytes(uint32_t n_tris);
 cudaError_t launch_build_blas(const float *vertices, const uint32_t *indices, uint32_t n_tris, float4 *nodes, unsigned long long *prim_indices,
                               void *workspace, size_t workspace_bytes, uint32_t *max_depth_dev, cudaStream_t stream);
+cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, uint32_t neural_mask, float4 *tlas_nodes, uint32_t *blas_indices,
+                              cudaStream_t stream);
 
 } // namespace nbvh

@@ -119,12 +119,14 @@ class NeuralPathModule:
         return self.get_constants(CONST_PT_OUTPUT).output_network_dims
 
     # ------------------------------------------------------------------ scene / tree-cut / weights
-    def set_scene(self, tlas_nodes, tlas_indices, blas_list, materials=None, textures=None):
+    def set_scene(self, tlas_nodes, tlas_indices, blas_list, materials=None, textures=None, neural_meshes=None):
         """Uploads a scene description (numpy arrays) and hands the device pointers over, standing in for
         CudaBackend's buffers (cuda_backend.cpp:186-441).  blas_list: dicts with nodes, prim_ids, vertices,
         indices (prim ids are widened to 64 bit: the reference stores size_t) and, for the training sampler, the optional
         shading attributes normals, texcoords, material_ids, material_map.  materials: MATERIAL_DTYPE array
-        (PackedMaterial); textures: list of (H, W, 4) uint8 images (RGBA8, wrap + linear like the reference's)."""
+        (PackedMaterial); textures: list of (H, W, 4) uint8 images (RGBA8, wrap + linear like the reference's).
+        tlas_nodes=None builds the TLAS on the device (nbvh_build_tlas) over the uploaded BLAS; neural_meshes: indices of the meshes the
+        N-BVH stands for (default: bvh_constants.neural_bvh_idx).  self.tlas_arrays() reads the result back."""
         torch = _torch()
         dev = torch.device("cuda", self.device)
 
@@ -133,9 +135,11 @@ class NeuralPathModule:
             return torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
 
         keep = []
-        t_nodes = up(np.ascontiguousarray(tlas_nodes, dtype=NODE_DTYPE), None)
-        t_idx = up(np.ascontiguousarray(tlas_indices, dtype=np.uint32), None)
-        keep += [t_nodes, t_idx]
+        build_tlas = tlas_nodes is None          # device TLAS build (nbvh_build_tlas) once the descriptors are uploaded
+        if not build_tlas:
+            t_nodes = up(np.ascontiguousarray(tlas_nodes, dtype=NODE_DTYPE), None)
+            t_idx = up(np.ascontiguousarray(tlas_indices, dtype=np.uint32), None)
+            keep += [t_nodes, t_idx]
         descs = (_capi.CudaBlas * len(blas_list))()
         for i, b in enumerate(blas_list):
             nodes = up(np.ascontiguousarray(b["nodes"], dtype=NODE_DTYPE), None)
@@ -158,9 +162,18 @@ class NeuralPathModule:
                 descs[i].num_materials = len(b["material_map"])
         d_descs = torch.from_numpy(np.frombuffer(bytes(descs), dtype=np.uint8).copy()).to(dev)
         keep.append(d_descs)
+        n_tlas_nodes = len(tlas_nodes) if not build_tlas else 2 * len(blas_list) - 1
+        if build_tlas:
+            t_nodes = torch.zeros(n_tlas_nodes * 32, dtype=torch.uint8, device=dev)
+            t_idx = torch.zeros(len(blas_list), dtype=torch.int32, device=dev)
+            keep += [t_nodes, t_idx]
+            neural = list(neural_meshes) if neural_meshes is not None else [int(self.get_constants(CONST_RENDERER).neural_bvh_idx)]
+            arr = (C.c_uint32 * max(1, len(neural)))(*neural)
+            self._check(self._lib.nbvh_build_tlas(self._h, d_descs.data_ptr(), len(blas_list), arr, len(neural), _ptr(t_nodes), _ptr(t_idx), None))
+            torch.cuda.synchronize(dev)
         sd = _capi.SceneData()
         sd.tlas_nodes = t_nodes.data_ptr()
-        sd.num_tlas_nodes = len(tlas_nodes)
+        sd.num_tlas_nodes = n_tlas_nodes
         sd.blas_indices = t_idx.data_ptr()
         sd.mesh_bvhs = d_descs.data_ptr()
         sd.num_meshes = len(blas_list)
@@ -182,6 +195,12 @@ class NeuralPathModule:
             sd.textures = t.data_ptr()
         self._check(self._lib.nbvh_set_scene(self._h, C.byref(sd)))
         self._keep["scene"] = keep
+        self._keep["tlas"] = (t_nodes, t_idx)
+
+    def tlas_arrays(self):
+        """Host copies of the TLAS in use: (nodes NODE_DTYPE array, blas_indices uint32 array)."""
+        t_nodes, t_idx = self._keep["tlas"]
+        return t_nodes.cpu().numpy().view(NODE_DTYPE).copy(), t_idx.cpu().numpy().view(np.uint32).copy()
 
     def set_envmap(self, pixels):
         """== CudaBackend::load_envmap (cuda_backend.cpp:455-500): (H, W, 4) float32 lat-long radiance map, or None for the

@@ -92,3 +92,74 @@ def test_gpu_lbvh_degenerate_inputs(synthetic):
             validate_tree(nodes, prims, v.cpu().numpy(), np.asarray(tris, np.uint32))
             assert depth <= 8
     mod.close()
+
+
+# ------------------------------------------------------------------------------------------------ device TLAS build (nbvh_build_tlas)
+def _one_triangle_mesh(rng):
+    c = rng.uniform(-3, 3, 3)
+    v = (c + rng.uniform(-0.4, 0.4, (3, 3))).astype(np.float32)
+    import nbvh_b200
+    nodes = np.zeros(1, nbvh_b200.NODE_DTYPE)
+    nodes[0] = (v.min(axis=0), 1, v.max(axis=0), 0)
+    return dict(nodes=nodes, prim_ids=np.zeros(1, np.uint32), vertices=v.reshape(-1), indices=np.arange(3, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("n_meshes", [1, 2, 5, 16])
+def test_gpu_tlas_structure(synthetic, n_meshes):
+    """TLASNode layout (tlas.cuh:64-68): 2n-1 nodes, adjacent children, every mesh in exactly one leaf whose box is the mesh's root box,
+    interior boxes are the union of their children, neural meshes carry leaf type 2."""
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    rng = np.random.default_rng(n_meshes)
+    meshes = [_one_triangle_mesh(rng) for _ in range(n_meshes)]
+    neural = [0] if n_meshes < 5 else [1, n_meshes - 2]
+    mod = nbvh_b200.NeuralPathModule(synthetic[0])
+    mod.set_scene(None, None, meshes, neural_meshes=neural)
+    nodes, idx = mod.tlas_arrays()
+    assert len(nodes) == 2 * n_meshes - 1 and sorted(idx.tolist()) == list(range(n_meshes))
+    leaf = nodes["b"] >= 1
+    assert leaf.sum() == n_meshes
+    mesh_of_leaf = idx[nodes["a"][leaf]]
+    assert sorted(mesh_of_leaf.tolist()) == list(range(n_meshes))
+    for node, m in zip(nodes[leaf], mesh_of_leaf):
+        assert (node["mn"] == meshes[m]["nodes"]["mn"][0]).all() and (node["mx"] == meshes[m]["nodes"]["mx"][0]).all()
+        assert node["b"] == (2 if m in neural else 1)
+    left = nodes["a"][~leaf].astype(np.int64)
+    kids = np.concatenate([left, left + 1])
+    assert len(np.unique(kids)) == 2 * (n_meshes - 1) and 0 not in kids and (kids < len(nodes)).all()
+    assert (nodes["mn"][~leaf] == np.minimum(nodes["mn"][left], nodes["mn"][left + 1])).all()
+    assert (nodes["mx"][~leaf] == np.maximum(nodes["mx"][left], nodes["mx"][left + 1])).all()
+    with pytest.raises(nbvh_b200.NbvhError):
+        mod.set_scene(None, None, meshes, neural_meshes=[n_meshes])   # neural mesh index out of range
+    mod.close()
+
+
+def test_gpu_tlas_renders_like_host_tlas(synthetic):
+    """The frame through the device-built TLAS is bit-identical (hit records and accumulation) to the frame through the host-built one."""
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, nbvh, tlas, tlas_idx, blas = synthetic
+    w, h = cfg["cuda_scene"]["fb_size"]
+    out = []
+    for device_tlas in (False, True):
+        mod = nbvh_b200.NeuralPathModule(cfg)
+        mod.set_neural_bvh(nbvh)
+        if device_tlas:
+            mod.set_scene(None, None, blas, neural_meshes=[int(tlas_idx[tlas["a"][tlas["b"] == 2][0]])])
+            assert len(mod.tlas_arrays()[0]) == len(tlas)
+        else:
+            mod.set_scene(tlas, tlas_idx, blas)
+        mod.init_params(1337)
+        accum, _ = mod.attach_framebuffer((w, h))
+        hits = mod.attach_hit_buffer(w * h)
+        mod.neural_render(0, 0)
+        torch.cuda.synchronize()
+        out.append((accum.cpu().numpy().copy(), hits.cpu().numpy().copy()))
+        mod.close()
+    assert out[0][0].std() > 0
+    assert (out[0][0].view(np.uint32) == out[1][0].view(np.uint32)).all()
+    assert (out[0][1] == out[1][1]).all()

@@ -229,6 +229,26 @@ def test_file_format_round_trips(syn, oracle, tmp_path):
     assert (mod.get_params() == syn["params"]).all()
 
 
+def test_network_file_float_payload_and_errors(syn, tmp_path):
+    """tcnn's deserialize also accepts params_type "float" (trainer.h:292-295): fp32 payloads are converted to the fp16 parameters;
+    malformed files fail loudly and leave the loaded parameters untouched."""
+    import nbvh_b200
+    mod = syn["mod"]
+    bits = syn["params"]
+    f32 = bits.view(np.float16).astype(np.float32)
+    doc = {"n_params": int(bits.size), "params_binary": {"bytes": f32.view(np.uint8).tolist(), "subtype": None}, "params_type": "float"}
+    q = str(tmp_path / "net_float.json")
+    json.dump(doc, open(q, "w"))
+    mod.load_params(np.zeros_like(bits))
+    mod.load_network_model(q)
+    assert (mod.get_params() == bits).all()
+    for bad in ({**doc, "params_type": "double"}, {**doc, "n_params": int(bits.size) + 1}, {"n_params": 4}):
+        json.dump(bad, open(q, "w"))
+        with pytest.raises(nbvh_b200.NbvhError):
+            mod.load_network_model(q)
+        assert (mod.get_params() == bits).all()
+
+
 # ------------------------------------------------------------------------------------------------ shipped Chess
 def test_chess_loaders_match_independent_readers(chess):
     assert chess["mod"].neural_bvh_nodes().tobytes() == chess["nbvh"].tobytes()
