@@ -462,6 +462,14 @@ int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint3
                     uint32_t n_neural, nbvh_node32 *tlas_nodes_out, uint32_t *blas_indices_out, void *stream);
 
 /* ---- f4: result writers and configuration round trip ------------------------------------------------------------ */
+/* == NeuralBVHRenderer::compute_and_display_flip_error (src/cuda/neural/neural_bvh_renderer.cu:34-96; replaces ext/flip-cuda): mean
+ * LDR-FLIP of accum / accumulated_spp against a device RGBA32F reference image of the framebuffer's size.  ppd <= 0: the reference's
+ * viewing conditions (67.02 pixels per degree).  error_map_out: optional device array of W x H floats (per-pixel FLIP error). */
+int nbvh_flip_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, float ppd, float *error_map_out,
+                    float *mean_flip_host, void *stream);
+/* the same for two arbitrary device RGBA32F images (linear RGB, alpha ignored); test is divided by test_divisor first */
+int nbvh_flip_images(nbvh_ctx *ctx, const float *reference_rgba32f, const float *test_rgba32f, float test_divisor, uint32_t width,
+                     uint32_t height, float ppd, float *error_map_out, float *mean_flip_host, void *stream);
 /* == write_exr (include/base/bitmap.h:97-182) as called by RenderApp::save_framebuffer (src/app/render_app.cpp:132-165): scanline
  * OpenEXR, channels A,B,G,R as 32-bit float, no compression, every value divided by rgb_renormalisation.  Host memory only; the file
  * is byte-identical to the one the reference's tinyexr writes. */

@@ -143,6 +143,8 @@ SYMBOLS = {
     "nbvh_render_host_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _u32]),
     "nbvh_render_host_wait": (_i, [_vp, _u32]),
     "nbvh_build_tlas": (_i, [_vp, _vp, _u32, C.POINTER(_u32), _u32, _vp, _vp, _vp]),
+    "nbvh_flip_error": (_i, [_vp, _vp, _u32, _f, _vp, C.POINTER(_f), _vp]),
+    "nbvh_flip_images": (_i, [_vp, _vp, _vp, _f, _u32, _u32, _f, _vp, C.POINTER(_f), _vp]),
     "nbvh_write_exr_host": (_i, [C.c_char_p, _u32, _u32, _vp, _f]),
     "nbvh_save_image_exr": (_i, [_vp, C.c_char_p, _u32, _vp]),
     "nbvh_write_frame_times_csv_host": (_i, [C.c_char_p, _vp, _vp, _u32]),

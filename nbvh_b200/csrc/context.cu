@@ -258,7 +258,8 @@ struct nbvh_ctx {
     size_t ldr_slot_pixels = 0;
     cudaStream_t pipe_render = nullptr, pipe_copy = nullptr;
     cudaEvent_t pipe_rendered[2] = {nullptr, nullptr}, pipe_copied[2] = {nullptr, nullptr};
-    void *d_build_ws = nullptr; // nbvh_build_blas scratch (grow-only)
+    void *d_build_ws = nullptr; // nbvh_build_blas / nbvh_flip_images scratch (grow-only)
+    float flip_ppd = 0.f;       // pixels per degree the FLIP filters in constant memory were built for
     size_t build_ws_bytes = 0;
     void *d_tc_workspace = nullptr;
     size_t tc_workspace_bytes = 0;
@@ -2427,6 +2428,53 @@ int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint3
     }
     CU_TRY(ctx, launch_build_tlas(mesh_bvhs_device, num_meshes, mask, reinterpret_cast<float4 *>(tlas_nodes_out), blas_indices_out,
                                   (cudaStream_t)stream));
+    return NBVH_OK;
+}
+
+// == NeuralBVHRenderer::compute_and_display_flip_error (neural_bvh_renderer.cu:34-96) without the colour-mapped display: mean LDR-FLIP of
+// the accumulated image (accum / accumulated_spp) against a device RGBA32F reference image of the framebuffer's size; ppd <= 0 selects the
+// reference's viewing conditions (0.7 m from a 0.7 m wide 3840-pixel monitor: 67.02 pixels per degree).  error_map_out: optional device
+// array of W x H floats (the per-pixel FLIP error the reference colour-maps with magma).
+int nbvh_flip_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, float ppd, float *error_map_out,
+                    float *mean_flip_host, void *stream)
+{
+    if (!ctx || !reference_rgba32f || !mean_flip_host || accumulated_spp == 0)
+        return NBVH_ERR_INVALID_ARG;
+    if (!ctx->accum)
+        return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
+    return nbvh_flip_images(ctx, reference_rgba32f, reinterpret_cast<const float *>(ctx->accum), (float)accumulated_spp, ctx->fb_w, ctx->fb_h,
+                            ppd, error_map_out, mean_flip_host, stream);
+}
+
+// The same for two arbitrary device RGBA32F images (linear RGB; alpha ignored); the test image is divided by test_divisor first.
+int nbvh_flip_images(nbvh_ctx *ctx, const float *reference_rgba32f, const float *test_rgba32f, float test_divisor, uint32_t width,
+                     uint32_t height, float ppd, float *error_map_out, float *mean_flip_host, void *stream)
+{
+    if (!ctx || !reference_rgba32f || !test_rgba32f || !mean_flip_host || width == 0 || height == 0 || !(test_divisor > 0.f))
+        return NBVH_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!(ppd > 0.f))
+        ppd = 0.7f * (3840.0f / 0.7f) * (3.14159265358979f / 180.0f);
+    if (ctx->flip_ppd != ppd) {
+        if (flip_set_ppd(ppd, st) != cudaSuccess)
+            return fail(ctx, NBVH_ERR_INVALID_ARG, "FLIP: pixels-per-degree value out of range (filter radius 1..64)");
+        ctx->flip_ppd = ppd;
+    }
+    const size_t bytes = flip_workspace_bytes(width, height);
+    if (ctx->build_ws_bytes < bytes) { // shares the grow-only scratch of nbvh_build_blas
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        cudaFree(ctx->d_build_ws);
+        ctx->d_build_ws = nullptr, ctx->build_ws_bytes = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_build_ws, bytes));
+        ctx->build_ws_bytes = bytes;
+    }
+    double *sum_dev = reinterpret_cast<double *>(ctx->d_counters + CNT_COUNT); // spare 8-byte slot
+    CU_TRY(ctx, launch_flip(reinterpret_cast<const float4 *>(reference_rgba32f), reinterpret_cast<const float4 *>(test_rgba32f), test_divisor,
+                            width, height, ctx->d_build_ws, error_map_out, sum_dev, st));
+    double sum = 0.0;
+    CU_TRY(ctx, cudaMemcpyAsync(&sum, sum_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    *mean_flip_host = (float)(sum / ((double)width * height));
     return NBVH_OK;
 }
 

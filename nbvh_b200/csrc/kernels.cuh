@@ -175,5 +175,10 @@ cudaError_t launch_build_blas(const float *vertices, const uint32_t *indices, ui
                               void *workspace, size_t workspace_bytes, uint32_t *max_depth_dev, cudaStream_t stream);
 cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, uint32_t neural_mask, float4 *tlas_nodes, uint32_t *blas_indices,
                               cudaStream_t stream);
+// LDR-FLIP (flip.cu)
+size_t flip_workspace_bytes(uint32_t w, uint32_t h);
+cudaError_t flip_set_ppd(float ppd, cudaStream_t stream);
+cudaError_t launch_flip(const float4 *reference, const float4 *test, float test_divisor, uint32_t w, uint32_t h, void *workspace,
+                        float *error_map, double *sum_dev, cudaStream_t stream);
 
 } // namespace nbvh

@@ -367,6 +367,27 @@ class NeuralPathModule:
                                                C.byref(out), stream))
         return out.value
 
+    def flip_error(self, reference, accumulated_spp, ppd=0.0, want_map=False, stream=None):
+        """== compute_and_display_flip_error: mean LDR-FLIP of accum / spp against a (H, W, 4) float32 CUDA reference image; with
+        want_map also the (H, W) per-pixel error map."""
+        torch = _torch()
+        assert reference.is_cuda and reference.dtype == torch.float32 and reference.is_contiguous()
+        emap = torch.empty(reference.shape[:2], dtype=torch.float32, device=reference.device) if want_map else None
+        mean = C.c_float(0)
+        self._check(self._lib.nbvh_flip_error(self._h, _ptr(reference), int(accumulated_spp), float(ppd), _ptr(emap), C.byref(mean), stream))
+        return (mean.value, emap) if want_map else mean.value
+
+    def flip_images(self, reference, test, test_divisor=1.0, ppd=0.0, stream=None):
+        """LDR-FLIP of two (H, W, 4) float32 CUDA images (linear RGB): returns (mean, (H, W) error map)."""
+        torch = _torch()
+        for t in (reference, test):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape == reference.shape and t.shape[2] == 4
+        emap = torch.empty(reference.shape[:2], dtype=torch.float32, device=reference.device)
+        mean = C.c_float(0)
+        self._check(self._lib.nbvh_flip_images(self._h, _ptr(reference), _ptr(test), float(test_divisor), int(reference.shape[1]),
+                                               int(reference.shape[0]), float(ppd), _ptr(emap), C.byref(mean), stream))
+        return mean.value, emap
+
     # ------------------------------------------------------------------ results (f4)
     def save_image(self, path, accumulated_spp, stream=None):
         """== NeuralBVHRenderer::save_image (neural_bvh_renderer_init.cu:361-383): accumulation / accumulated_spp as an A,B,G,R float EXR."""
