@@ -117,6 +117,35 @@ public:
         return max_loss;
     }
 
+    // ---- validation metrics: compute_and_display_render_error / compute_and_display_flip_error (neural_bvh_renderer.cu:34-96,346-358)
+    float image_error(const float *reference_rgba32f, uint32_t accumulated_spp, int postprocess_mode, bool write_error_image = false,
+                      void *stream = nullptr)
+    {
+        float mean = 0.f;
+        check(nbvh_image_error(m_ctx, reference_rgba32f, accumulated_spp, postprocess_mode, write_error_image ? 1 : 0, &mean, stream));
+        return mean;
+    }
+    float flip_error(const float *reference_rgba32f, uint32_t accumulated_spp, float *error_map_device = nullptr, void *stream = nullptr)
+    {
+        float mean = 0.f;
+        check(nbvh_flip_error(m_ctx, reference_rgba32f, accumulated_spp, 0.f, error_map_device, &mean, stream));
+        return mean;
+    }
+    // ---- scene build on the device: CudaBackend's BLAS / TLAS builds (cuda_backend.cpp:186-385)
+    uint32_t build_blas(const float *vertices, const uint32_t *indices, uint32_t n_tris, nbvh_node32 *nodes_out, uint64_t *prim_indices_out,
+                        void *stream = nullptr)
+    {
+        uint32_t depth = 0;
+        check(nbvh_build_blas(m_ctx, vertices, indices, n_tris, nodes_out, prim_indices_out, &depth, stream));
+        return depth;
+    }
+    void build_tlas(const nbvh_cuda_blas *mesh_bvhs_device, uint32_t num_meshes, const std::vector<uint32_t> &neural_meshes,
+                    nbvh_node32 *tlas_nodes_out, uint32_t *blas_indices_out, void *stream = nullptr)
+    {
+        check(nbvh_build_tlas(m_ctx, mesh_bvhs_device, num_meshes, neural_meshes.data(), (uint32_t)neural_meshes.size(), tlas_nodes_out,
+                              blas_indices_out, stream));
+    }
+
     // ---- results (f4): save_image / save_config / save_performance_metrics (neural_bvh_renderer_init.cu:328-383,406-509)
     void save_image(const std::string &path, uint32_t accumulated_spp, void *stream = nullptr)
     {

@@ -40,6 +40,14 @@ def main():
     # the frame first: the training steps below change the weights (and with them the number of queries per frame)
     ms = timeit(lambda: mod.neural_render(0, 0), iters=20)
     out["render_1080p"] = {"ms": ms, "Mrays_s": 1920 * 1080 / ms / 1e3}
+    # validation metrics on the 1080p frame (mean read back per call, like the reference's validation mode)
+    accum, _ = mod.attach_framebuffer((1920, 1080))
+    mod.neural_render(0, 0)
+    ref_img = (torch.roll(accum, 2, dims=1) * 0.9 + 0.01).contiguous()
+    ms = timeit(lambda: mod.flip_error(ref_img, 1), iters=20)
+    out["flip_1080p"] = {"ms": ms, "Mpixels_s": 1920 * 1080 / ms / 1e3, "what": "nbvh_flip_error incl. the mean read-back"}
+    ms = timeit(lambda: mod.image_error(ref_img, 1), iters=20)
+    out["relmse_1080p"] = {"ms": ms}
     rng = np.random.default_rng(0)
     for n in (1 << 16, 1 << 20, 1 << 22):
         x = torch.from_numpy(rng.uniform(0, 1, size=(n, 9)).astype(np.float32)).cuda()
