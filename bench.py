@@ -330,23 +330,25 @@ def main():
         mod.neural_render_host(0, args.warmup + i, ldr_host=ldr_host, camera=cam)
     torch.cuda.synchronize()
     e2e_sync_s = time.time() - t0
-    # the same call with two frames in flight (nbvh_render_host_submit / _wait): the 8.3 MB device-to-host copy of frame i overlaps
-    # the kernels of frame i + 1; every step still uploads its camera block and reads its frame back into pinned host memory
-    ldr_host2 = [ldr_host, torch.empty(n_rays * 4, dtype=torch.uint8, pin_memory=True).numpy()]
-    # independent frames (sample 0 of a new frame each step, RNG offset = frame number): the two slots then render on two streams
-    # with their own queues, and k_primary of frame i + 1 overlaps the drain of frame i's k_neural
-    for i in range(2):
-        mod.neural_render_host_submit(0, i, ldr_host2[i & 1], i & 1, camera=cam)
-    for i in range(2):
+    # the same call with frames in flight (nbvh_render_host_submit / _wait): the 8.3 MB device-to-host copy of frame i overlaps
+    # the kernels of the next frames; every step still uploads its camera block and reads its frame back into pinned host memory.
+    # Independent frames (sample 0 of a new frame each step, RNG offset = frame number): every slot renders on its own stream with
+    # its own queue, so k_primary of the following frames overlaps the drain of frame i's k_neural
+    # (tools/frames_in_flight.py: 1,915 / 2,697 / 2,835 / 2,849 Mrays/s at 1 / 2 / 3 / 4 frames in flight; identical frames)
+    n_fif = 4
+    ldr_hosts = [ldr_host] + [torch.empty(n_rays * 4, dtype=torch.uint8, pin_memory=True).numpy() for _ in range(n_fif - 1)]
+    for i in range(n_fif):
+        mod.neural_render_host_submit(0, i, ldr_hosts[i], i, camera=cam)
+    for i in range(n_fif):
         mod.neural_render_host_wait(i)
     barrier()
     t0 = time.time()
     for i in range(args.steps):
-        if i >= 2:
-            mod.neural_render_host_wait(i & 1)
-        mod.neural_render_host_submit(0, args.warmup + i, ldr_host2[i & 1], i & 1, camera=cam)
-    mod.neural_render_host_wait(0)
-    mod.neural_render_host_wait(1)
+        if i >= n_fif:
+            mod.neural_render_host_wait(i % n_fif)
+        mod.neural_render_host_submit(0, args.warmup + i, ldr_hosts[i % n_fif], i % n_fif, camera=cam)
+    for i in range(min(n_fif, args.steps)):
+        mod.neural_render_host_wait(i)
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
 
@@ -578,7 +580,7 @@ def main():
                        "sharding": "one full-frame sample per rank per step (spp sharding), scene and weights replicated",
                        "l2": "256 MiB buffer written between timed steps (outside the event intervals)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": n_rays * 4,
-                    "api": "nbvh_render_host_submit / _wait (C ABI), two independent frames in flight on two streams: camera constants in, sRGB8 frame out, pinned host memory",
+                    "api": "nbvh_render_host_submit / _wait (C ABI), four independent frames in flight, one stream and queue per slot: camera constants in, sRGB8 frame out, pinned host memory", "frames_in_flight": 4,
                     "note": "back-to-back frames (no L2 flush between them, unlike `value`): the copy is hidden behind the next frame's kernels",
                     "synchronous_value": world * n_rays * args.steps / (e2e_sync_ms * 1e-3) / 1e6,
                     "synchronous_api": "nbvh_render_host (one blocking call per frame, the reference's calling pattern)"},

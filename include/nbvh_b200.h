@@ -365,9 +365,11 @@ int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint3
  * 8-bit framebuffer (and hit records if hits_host != NULL) back.  Synchronous. */
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset,
                      const nbvh_camera_params *camera_host, uint8_t *ldr_rgba8_host, nbvh_hit_record *hits_host);
-/* Frames in flight: nbvh_render_host split into submit and wait (two frame buffers, a render and a copy stream), so that the
- * device-to-host copy of one frame overlaps the kernels of the next.  ldr_rgba8_host must be pinned; slot in {0, 1}; wait for a
- * slot before reusing it (and before reading its host buffer). */
+/* Frames in flight: nbvh_render_host split into submit and wait (one frame buffer, neural ray queue and render stream per slot, one
+ * copy stream), so that the device-to-host copy of one frame and the drain of its k_neural overlap the kernels of the next frames.
+ * ldr_rgba8_host must be pinned; slot < NBVH_MAX_FRAMES_IN_FLIGHT; wait for a slot before reusing it (and before reading its host
+ * buffer). */
+#define NBVH_MAX_FRAMES_IN_FLIGHT 4
 int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                             uint8_t *ldr_rgba8_host, uint32_t slot);
 int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot);

@@ -206,6 +206,8 @@ uint16_t f32_to_f16_host(float f) { return __half_as_ushort(__float2half_rn(f));
 } // namespace
 
 // ================================================================================================ context
+constexpr int kPipeSlots = NBVH_MAX_FRAMES_IN_FLIGHT; // frames in flight of nbvh_render_host_submit
+
 struct nbvh_ctx {
     int device = 0;
     int num_sms = 148;
@@ -250,14 +252,15 @@ struct nbvh_ctx {
     // slot 1 renders on its own stream with its own neural ray queue and counters, so that its k_primary overlaps the drain of
     // slot 0's k_neural (60 % of a 1080p launch leaves the SMs mostly idle)
     int render_slot = 0; // which queue / counter set render_impl uses (set by nbvh_render_host_submit)
-    uint32_t *d_next_chunk_alt = nullptr;
-    NeuralQueueEntry *d_queue_alt = nullptr;
-    size_t queue_capacity_alt = 0;
-    cudaStream_t pipe_render_alt = nullptr;
-    uchar4 *d_ldr_slot[2] = {nullptr, nullptr};
+    // slots 1 .. kPipeSlots-1 each own a queue, a counter block and a render stream (index slot - 1); slot 0 uses the main ones
+    uint32_t *d_next_chunk_alt[kPipeSlots - 1] = {};
+    NeuralQueueEntry *d_queue_alt[kPipeSlots - 1] = {};
+    size_t queue_capacity_alt[kPipeSlots - 1] = {};
+    cudaStream_t pipe_render_alt[kPipeSlots - 1] = {};
+    uchar4 *d_ldr_slot[kPipeSlots] = {};
     size_t ldr_slot_pixels = 0;
     cudaStream_t pipe_render = nullptr, pipe_copy = nullptr;
-    cudaEvent_t pipe_rendered[2] = {nullptr, nullptr}, pipe_copied[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_rendered[kPipeSlots] = {}, pipe_copied[kPipeSlots] = {};
     void *d_build_ws = nullptr; // nbvh_build_blas / nbvh_flip_images scratch (grow-only)
     float flip_ppd = 0.f;       // pixels per degree the FLIP filters in constant memory were built for
     size_t build_ws_bytes = 0;
@@ -621,11 +624,13 @@ void nbvh_destroy(nbvh_ctx *ctx)
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
     cudaFree(ctx->d_build_ws);
-    cudaFree(ctx->d_next_chunk_alt);
-    cudaFree(ctx->d_queue_alt);
-    if (ctx->pipe_render_alt)
-        cudaStreamDestroy(ctx->pipe_render_alt);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kPipeSlots - 1; k++) {
+        cudaFree(ctx->d_next_chunk_alt[k]);
+        cudaFree(ctx->d_queue_alt[k]);
+        if (ctx->pipe_render_alt[k])
+            cudaStreamDestroy(ctx->pipe_render_alt[k]);
+    }
+    for (int k = 0; k < kPipeSlots; k++) {
         cudaFree(ctx->d_ldr_slot[k]);
         if (ctx->pipe_rendered[k])
             cudaEventDestroy(ctx->pipe_rendered[k]);
@@ -1584,14 +1589,15 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     rp.first_pixel = first_pixel, rp.pixel_count = pixel_count;
     rp.chunk_stride = chunk_stride, rp.chunk_offset = chunk_offset;
     rp.spp_count     = spp_count;
-    const bool alt = ctx->render_slot == 1;
-    if (alt && !ctx->d_next_chunk_alt) {
-        CU_TRY(ctx, cudaMalloc(&ctx->d_next_chunk_alt, 8 * sizeof(uint32_t)));
-        CU_TRY(ctx, cudaMemset(ctx->d_next_chunk_alt, 0, 8 * sizeof(uint32_t)));
+    const bool alt = ctx->render_slot >= 1 && ctx->render_slot < kPipeSlots;
+    const int ai   = alt ? ctx->render_slot - 1 : 0;
+    if (alt && !ctx->d_next_chunk_alt[ai]) {
+        CU_TRY(ctx, cudaMalloc(&ctx->d_next_chunk_alt[ai], 8 * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemset(ctx->d_next_chunk_alt[ai], 0, 8 * sizeof(uint32_t)));
     }
-    uint32_t *chunk_ctr        = alt ? ctx->d_next_chunk_alt : ctx->d_next_chunk;
-    NeuralQueueEntry *&queue   = alt ? ctx->d_queue_alt : ctx->d_queue;
-    size_t &queue_capacity     = alt ? ctx->queue_capacity_alt : ctx->queue_capacity;
+    uint32_t *chunk_ctr        = alt ? ctx->d_next_chunk_alt[ai] : ctx->d_next_chunk;
+    NeuralQueueEntry *&queue   = alt ? ctx->d_queue_alt[ai] : ctx->d_queue;
+    size_t &queue_capacity     = alt ? ctx->queue_capacity_alt[ai] : ctx->queue_capacity;
     rp.next_chunk    = chunk_ctr;
     const size_t slots = spp_count > 1u ? (size_t)pixel_count * spp_count : (size_t)total; // path / queue slots this launch may use
     if (queue_capacity < slots) {
@@ -2114,23 +2120,24 @@ int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_of
 int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                             uint8_t *ldr_host, uint32_t slot)
 {
-    if (!ctx || !ldr_host || slot > 1u)
+    if (!ctx || !ldr_host || slot >= (uint32_t)kPipeSlots)
         return NBVH_ERR_INVALID_ARG;
     const size_t n = (size_t)ctx->fb_w * ctx->fb_h;
     if (n == 0)
         return fail(ctx, NBVH_ERR_STATE, "framebuffer not set");
     if (!ctx->pipe_render) {
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render, cudaStreamNonBlocking));
-        CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render_alt, cudaStreamNonBlocking));
+        for (int k = 0; k < kPipeSlots - 1; k++)
+            CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_render_alt[k], cudaStreamNonBlocking));
         CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->pipe_copy, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kPipeSlots; k++) {
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_rendered[k], cudaEventDisableTiming));
             CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->pipe_copied[k], cudaEventDisableTiming));
         }
     }
     if (ctx->ldr_slot_pixels != n) {
         CU_TRY(ctx, cudaDeviceSynchronize());
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < kPipeSlots; k++) {
             cudaFree(ctx->d_ldr_slot[k]);
             ctx->d_ldr_slot[k] = nullptr;
             CU_TRY(ctx, cudaMalloc(&ctx->d_ldr_slot[k], n * sizeof(uchar4)));
@@ -2143,14 +2150,17 @@ int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
     // per slot with their own queue and counters, so the kernels of consecutive frames overlap; accumulating samples and the
     // multi-bounce pipeline (one set of path lists) stay on a single stream.
     const bool concurrent  = accumulated_spp == 0 && ctx->max_depth == 1 && !ctx->mega_kernel && !ctx->scene_const.ema_accumulate && !ctx->hits;
-    cudaStream_t rstream   = (concurrent && slot == 1) ? ctx->pipe_render_alt : ctx->pipe_render;
-    if (!concurrent) // order after whatever the other slot's stream still runs
-        CU_TRY(ctx, cudaStreamWaitEvent(rstream, ctx->pipe_rendered[slot ^ 1u], 0));
+    cudaStream_t rstream   = (concurrent && slot >= 1u) ? ctx->pipe_render_alt[slot - 1u] : ctx->pipe_render;
+    if (!concurrent) { // order after whatever the other slots' streams still run
+        for (uint32_t k = 0; k < (uint32_t)kPipeSlots; k++)
+            if (k != slot)
+                CU_TRY(ctx, cudaStreamWaitEvent(rstream, ctx->pipe_rendered[k], 0));
+    }
     // the slot's previous copy must have drained before the kernels overwrite its frame buffer
     CU_TRY(ctx, cudaStreamWaitEvent(rstream, ctx->pipe_copied[slot], 0));
     uchar4 *saved     = ctx->ldr;
     ctx->ldr          = ctx->d_ldr_slot[slot];
-    ctx->render_slot  = (concurrent && slot == 1) ? 1 : 0;
+    ctx->render_slot  = concurrent ? (int)slot : 0;
     const int rc      = nbvh_render(ctx, accumulated_spp, sample_offset, 0, 0, rstream);
     ctx->render_slot  = 0;
     ctx->ldr          = saved;
@@ -2165,7 +2175,7 @@ int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
 
 int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot)
 {
-    if (!ctx || slot > 1u || !ctx->pipe_copied[slot])
+    if (!ctx || slot >= (uint32_t)kPipeSlots || !ctx->pipe_copied[slot])
         return NBVH_ERR_INVALID_ARG;
     CU_TRY(ctx, cudaEventSynchronize(ctx->pipe_copied[slot]));
     return NBVH_OK;

@@ -308,3 +308,20 @@ def test_pipelined_host_render_equals_synchronous(syn, torch_cuda):
         got.append(bufs[s].copy())
     for a, b in zip(ref, got):
         assert (a == b).all()
+    # up to NBVH_MAX_FRAMES_IN_FLIGHT = 4 slots, each with its own queue and stream; a fifth slot is refused
+    import nbvh_b200
+    for depth in (3, 4):
+        bufs = [torch_cuda.empty(n * 4, dtype=torch_cuda.uint8, pin_memory=True).numpy() for _ in range(depth)]
+        got = {}
+        for s in range(9):
+            k = s % depth
+            if s >= depth:
+                mod.neural_render_host_wait(k)
+                got[s - depth] = bufs[k].copy()
+            mod.neural_render_host_submit(0, s % 4, bufs[k], k)
+        for s in range(9 - depth, 9):
+            mod.neural_render_host_wait(s % depth)
+            got[s] = bufs[s % depth].copy()
+        assert all((got[s] == ref[s % 4]).all() for s in range(9))
+    with pytest.raises(nbvh_b200.NbvhError):
+        mod.neural_render_host_submit(0, 0, bufs[0], 4)
