@@ -9,8 +9,10 @@
 //   magnitudes -> (|difference| / sqrt 2)^qf;   error = colour^(1 - feature).
 // Three kernels instead of flip-cuda's seven (both images and both pipelines share each pass): k_flip_prepare (per pixel),
 // k_flip_rows (horizontal pass: 14 partial sums per pixel), k_flip_cols (vertical pass + differences + error + block-reduced sum).
-// Edge handling = clamp to the border, summation order = -r ... +r, both like the reference.  Floating point: not bit-exact against
-// flip-cuda (it is built with FMA contraction); the tests state 2e-4 on the error map.
+// Edge handling = clamp to the border, summation order = -r ... +r, both like the reference; the filter sums use explicit fmaf (the
+// library is built with -fmad=false for the traversal kernels; flip-cuda is built with FMA contraction).  Floating point, not
+// bit-exact against flip-cuda: the tests state 2e-4 on the error map.  Intermediate images are planar (one plane per image / per partial
+// sum), so both passes read and write contiguous rows per warp.
 #include "kernels.cuh"
 
 #include <cfloat>
@@ -97,7 +99,7 @@ __device__ inline C3 to_ycxcz(float r, float g, float b)
     return xyz_to_ycxcz(linear_to_xyz(lin));
 }
 
-// ycc[2 * i] = reference, ycc[2 * i + 1] = test (accum / test_divisor)
+// ycc[i] = reference, ycc[n + i] = test (accum / test_divisor): one plane per image, so that a warp's loads are contiguous
 __global__ void __launch_bounds__(256) k_flip_prepare(const float4 *reference, const float4 *test, float test_divisor, uint32_t n, float4 *ycc)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,11 +107,12 @@ __global__ void __launch_bounds__(256) k_flip_prepare(const float4 *reference, c
         return;
     const float4 r = reference[i], t = test[i];
     const C3 a = to_ycxcz(r.x, r.y, r.z), b = to_ycxcz(t.x / test_divisor, t.y / test_divisor, t.z / test_divisor);
-    ycc[2 * i]     = make_float4(a.x, a.y, a.z, 0.f);
-    ycc[2 * i + 1] = make_float4(b.x, b.y, b.z, 0.f);
+    ycc[i]             = make_float4(a.x, a.y, a.z, 0.f);
+    ycc[(size_t)n + i] = make_float4(b.x, b.y, b.z, 0.f);
 }
 
-// rows[14 * i + ...]: per image (reference 0..6, test 7..13): Y, Cx, Cz partial 1, Cz partial 2, dx, ddx, Gaussian
+// rows[k * n + i], 14 planes of n = w * h floats (coalesced in both passes): per image (reference k = 0..6, test 7..13):
+// Y, Cx, Cz partial 1, Cz partial 2, dx, ddx, Gaussian
 __global__ void __launch_bounds__(256) k_flip_rows(const float4 *ycc, int w, int h, float *rows)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -120,14 +123,16 @@ __global__ void __launch_bounds__(256) k_flip_rows(const float4 *ycc, int w, int
     for (int k = 0; k < 14; k++)
         s[k] = 0.f;
     const int rs = c_flip.r_spatial, rf = c_flip.r_feature;
+    const size_t n = (size_t)w * h;
     for (int ix = -rs; ix <= rs; ix++) {
         const int xx     = min(max(0, x + ix), w - 1);
         const size_t src = (size_t)y * w + xx;
         const float wy = c_flip.ycx[ix + rs][0], wcx = c_flip.ycx[ix + rs][1], wz1 = c_flip.cz[ix + rs][0], wz2 = c_flip.cz[ix + rs][1];
 #pragma unroll
         for (int im = 0; im < 2; im++) {
-            const float4 c = ycc[2 * src + im];
-            s[7 * im + 0] += wy * c.x, s[7 * im + 1] += wcx * c.y, s[7 * im + 2] += wz1 * c.z, s[7 * im + 3] += wz2 * c.z;
+            const float4 c = ycc[im * n + src];
+            s[7 * im + 0] = fmaf(wy, c.x, s[7 * im + 0]), s[7 * im + 1] = fmaf(wcx, c.y, s[7 * im + 1]);
+            s[7 * im + 2] = fmaf(wz1, c.z, s[7 * im + 2]), s[7 * im + 3] = fmaf(wz2, c.z, s[7 * im + 3]);
         }
     }
     for (int ix = -rf; ix <= rf; ix++) {
@@ -136,14 +141,14 @@ __global__ void __launch_bounds__(256) k_flip_rows(const float4 *ycc, int w, int
         const float g = c_flip.feat[ix + rf][0], dg = c_flip.feat[ix + rf][1], ddg = c_flip.feat[ix + rf][2];
 #pragma unroll
         for (int im = 0; im < 2; im++) {
-            const float yn = ycc[2 * src + im].x * (1.0f / 116.0f) + (16.0f / 116.0f);
-            s[7 * im + 4] += dg * yn, s[7 * im + 5] += ddg * yn, s[7 * im + 6] += g * yn;
+            const float yn = fmaf(ycc[im * n + src].x, 1.0f / 116.0f, 16.0f / 116.0f);
+            s[7 * im + 4] = fmaf(dg, yn, s[7 * im + 4]), s[7 * im + 5] = fmaf(ddg, yn, s[7 * im + 5]), s[7 * im + 6] = fmaf(g, yn, s[7 * im + 6]);
         }
     }
-    float *dst = rows + 14 * ((size_t)y * w + x);
+    float *dst = rows + ((size_t)y * w + x);
 #pragma unroll
     for (int k = 0; k < 14; k++)
-        dst[k] = s[k];
+        dst[k * n] = s[k];
 }
 
 __global__ void __launch_bounds__(256) k_flip_cols(const float *rows, int w, int h, float *error_map, double *sum)
@@ -152,15 +157,16 @@ __global__ void __launch_bounds__(256) k_flip_cols(const float *rows, int w, int
     float err = 0.f;
     if (x < w) {
         const int rs = c_flip.r_spatial, rf = c_flip.r_feature;
+        const size_t n = (size_t)w * h;
         float col[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         for (int iy = -rs; iy <= rs; iy++) {
             const int yy   = min(max(0, y + iy), h - 1);
-            const float *p = rows + 14 * ((size_t)yy * w + x);
+            const float *p = rows + ((size_t)yy * w + x);
             const float wy = c_flip.ycx[iy + rs][0], wcx = c_flip.ycx[iy + rs][1], wz1 = c_flip.cz[iy + rs][0], wz2 = c_flip.cz[iy + rs][1];
 #pragma unroll
             for (int im = 0; im < 2; im++)
-                col[im][0] += wy * p[7 * im], col[im][1] += wcx * p[7 * im + 1], col[im][2] += wz1 * p[7 * im + 2],
-                    col[im][3] += wz2 * p[7 * im + 3];
+                col[im][0] = fmaf(wy, p[(7 * im) * n], col[im][0]), col[im][1] = fmaf(wcx, p[(7 * im + 1) * n], col[im][1]),
+                col[im][2] = fmaf(wz1, p[(7 * im + 2) * n], col[im][2]), col[im][3] = fmaf(wz2, p[(7 * im + 3) * n], col[im][3]);
         }
         C3 lab[2];
 #pragma unroll
@@ -177,11 +183,12 @@ __global__ void __launch_bounds__(256) k_flip_cols(const float *rows, int w, int
         float f[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}; // dx, ddx, dy, ddy
         for (int iy = -rf; iy <= rf; iy++) {
             const int yy   = min(max(0, y + iy), h - 1);
-            const float *p = rows + 14 * ((size_t)yy * w + x);
+            const float *p = rows + ((size_t)yy * w + x);
             const float g = c_flip.feat[iy + rf][0], dg = c_flip.feat[iy + rf][1], ddg = c_flip.feat[iy + rf][2];
 #pragma unroll
             for (int im = 0; im < 2; im++)
-                f[im][0] += g * p[7 * im + 4], f[im][1] += g * p[7 * im + 5], f[im][2] += dg * p[7 * im + 6], f[im][3] += ddg * p[7 * im + 6];
+                f[im][0] = fmaf(g, p[(7 * im + 4) * n], f[im][0]), f[im][1] = fmaf(g, p[(7 * im + 5) * n], f[im][1]),
+                f[im][2] = fmaf(dg, p[(7 * im + 6) * n], f[im][2]), f[im][3] = fmaf(ddg, p[(7 * im + 6) * n], f[im][3]);
         }
         const float edge_r = sqrtf(f[0][0] * f[0][0] + f[0][2] * f[0][2]), edge_t = sqrtf(f[1][0] * f[1][0] + f[1][2] * f[1][2]);
         const float pt_r = sqrtf(f[0][1] * f[0][1] + f[0][3] * f[0][3]), pt_t = sqrtf(f[1][1] * f[1][1] + f[1][3] * f[1][3]);
