@@ -1033,7 +1033,7 @@ int nbvh_load_neural_bvh_file(nbvh_ctx *ctx, const char *path)
     uint64_t n_nodes, n_prims;
     memcpy(&n_nodes, data.data(), 8);
     memcpy(&n_prims, data.data() + 8, 8);
-    if (n_nodes == 0 || n_nodes > 0x7FFFFFFFull || data.size() != 16 + n_nodes * 40 + n_prims * 8)
+    if (n_nodes == 0 || n_nodes > 0x7FFFFFFFull || n_prims > data.size() / 8 || data.size() != 16 + n_nodes * 40 + n_prims * 8)
         return fail(ctx, NBVH_ERR_PARSE, ".nbvh size does not match its header");
     std::vector<nbvh_node32> nodes(n_nodes);
     const char *p = data.data() + 16;

@@ -116,3 +116,35 @@ def test_single_chunk_and_tail_shards_equal_full_frame(env):
     assert (got_a[rendered].view(np.uint32) == full_a[rendered].view(np.uint32)).all()
     assert got_h[rendered].tobytes() == full_h[rendered].tobytes()
     assert not got_a[~rendered].any()
+
+
+def test_malformed_files_fail_loudly_and_leave_state_untouched(env, tmp_path):
+    import struct
+    mod, nb = env["mod"], env["nb"]
+    good = str(tmp_path / "good.nbvh")
+    mod.save_neural_bvh(good)
+    raw = open(good, "rb").read()
+    nodes_before, params_before = mod.neural_bvh_nodes().tobytes(), mod.get_params().tobytes()
+    n_nodes, n_prims = struct.unpack_from("<QQ", raw)
+    cases = {"truncated": raw[:len(raw) - 13], "short": raw[:7], "empty": b"", "zero_nodes": struct.pack("<QQ", 0, 0),
+             "huge_counts": struct.pack("<QQ", n_nodes, (1 << 61) + n_prims) + raw[16:],      # n_prims * 8 wraps around 2^64
+             "trailing": raw + b"\0" * 8}
+    for name, blob in cases.items():
+        p = tmp_path / (name + ".nbvh")
+        p.write_bytes(blob)
+        with pytest.raises(nb.NbvhError):
+            mod.load_neural_bvh(str(p))
+        assert mod.neural_bvh_nodes().tobytes() == nodes_before, name
+    for name, text in {"garbage": "{not json", "no_bytes": '{"n_params": 3, "params_type": "__half"}',
+                       "short_bytes": '{"n_params": 4, "params_binary": {"bytes": [1, 2]}, "params_type": "__half"}'}.items():
+        p = tmp_path / (name + ".json")
+        p.write_text(text)
+        with pytest.raises(nb.NbvhError):
+            mod.load_network_model(str(p))
+        assert mod.get_params().tobytes() == params_before, name
+    for text in ("{", '{"neural_bvh_renderer": {"neural_module": {"pt_output_constants": {"depth_loss": "Nope"}}}}',
+                 '{"cuda_scene": {"camera": {"matrix": [1, 2, 3]}}}'):
+        with pytest.raises(nb.NbvhError):
+            nb.NeuralPathModule(text)
+    mod.load_neural_bvh(good)
+    assert mod.neural_bvh_nodes().tobytes() == nodes_before
