@@ -62,6 +62,7 @@ public:
     void save_neural_bvh(const std::string &path) { check(nbvh_save_neural_bvh_file(m_ctx, path.c_str())); }
     void load_network_model(const std::string &path) { check(nbvh_load_network_file(m_ctx, path.c_str())); }
     void save_network_model(const std::string &path) { check(nbvh_save_network_file(m_ctx, path.c_str())); }
+    void init_params(uint64_t seed = 1337) { check(nbvh_init_params(m_ctx, seed)); } // tcnn's Trainer initialisation (trainer.h:50-57)
     uint64_t n_params() const { return nbvh_n_params(m_ctx); }
     uint32_t neural_bvh_num_nodes() const { return nbvh_neural_bvh_num_nodes(m_ctx); }
 

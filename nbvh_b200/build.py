@@ -38,17 +38,22 @@ def build(force=False, verbose=False):
 
 
 def build_host():
-    """The C++ host side above the C ABI: include/nbvh_b200.hpp (header-only wrapper) + the command line host nbvh_render_cli."""
-    src = os.path.join(HERE, "host", "nbvh_render_cli.cpp")
-    out = os.path.join(HERE, "host", "nbvh_render_cli")
-    deps = [src, os.path.join(HERE, "..", "include", "nbvh_b200.hpp"), os.path.join(HERE, "..", "include", "nbvh_b200.h"), LIB]
-    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
-        return out
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(HERE, "..", "include"), "-I/usr/local/cuda/include", src, "-L" + HERE,
-           "-lnbvh_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN/..", "-o", out]
-    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
-    return out
+    """The C++ host side above the C ABI: include/nbvh_b200.hpp (header-only wrapper) + the command line hosts nbvh_render_cli
+    (inference) and nbvh_train_cli (validation-mode run: optimisation with tree-cut learning, then frames and result files)."""
+    outs = []
+    for name in ("nbvh_render_cli", "nbvh_train_cli"):
+        src = os.path.join(HERE, "host", name + ".cpp")
+        out = os.path.join(HERE, "host", name)
+        deps = [src, os.path.join(HERE, "..", "include", "nbvh_b200.hpp"), os.path.join(HERE, "..", "include", "nbvh_b200.h"),
+                os.path.join(CSRC, "json_min.hpp"), LIB]
+        outs.append(out)
+        if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+            continue
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I" + os.path.join(HERE, "..", "include"), "-I/usr/local/cuda/include", src, "-L" + HERE,
+               "-lnbvh_b200", "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,$ORIGIN/..", "-o", out]
+        print("[nbvh_b200.build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return outs
 
 
 def build_variant(name, defines):

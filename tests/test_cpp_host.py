@@ -105,3 +105,62 @@ def test_cli_exr_is_accumulation_over_spp(tmp_path):
     mod.close()
     assert img.shape == (H, W, 4) and np.isfinite(img).all() and img[..., :3].std() > 0
     np.testing.assert_allclose(img, want, rtol=0, atol=1e-6)   # same kernels; fp32 atomics free (one sample per pixel per launch)
+
+
+def test_train_cli_links_and_fails_loudly_without_inputs(tmp_path):
+    _cli()
+    cli = os.path.join(REPO, "nbvh_b200", "host", "nbvh_train_cli")
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    r = subprocess.run([cli, str(tmp_path), "nothing", str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode == 1 and "nbvh_train_cli:" in r.stderr
+
+
+@pytest.mark.gpu
+def test_train_cli_matches_python_validation_run(tmp_path):
+    """The C++ validation-mode host (optimisation with tree-cut learning, frames, result files) against the Python host on the same
+    scene files: same tree-cut growth, the same first loss (same RNG keys and initial weights), loss curves within 2 % (the gradient
+    atomics make runs differ in the last bits), the reference's file layout, and close images."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import nbvh_b200
+    from nbvh_b200 import results, scene_io, validation
+    root = scene_io.chess_fixture_dir()
+    if root is None or not scene_io.has_shading_fixture(root):
+        pytest.skip("Chess fixture missing")
+    _cli()
+    base, W, H, steps, spp = scene_io.CHESS_BASE, 160, 90, 45, 2
+    out = tmp_path / "cpp"
+    r = subprocess.run([os.path.join(REPO, "nbvh_b200", "host", "nbvh_train_cli"), root, base, str(out), str(steps), str(spp), str(W), str(H)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    for rel in ("results/%s_cpp_learning_spp_0.csv", "results/%s_cpp_spp_2.exr", "results/%s_cpp_inference_spp_2.csv", "nbvhs/%s.nbvh",
+                "network_models/%s_network.json", "configs/%s_cpp.json"):
+        assert (out / (rel % base)).exists(), rel
+    rows = (out / ("results/%s_cpp_learning_spp_0.csv" % base)).read_text().splitlines()
+    assert rows[0] == "frame index,frame time (ms), loss" and len(rows) == steps + 1
+    cpp_losses = np.array([float(x.split(",")[2]) for x in rows[1:]])
+
+    cfg = json.load(open(os.path.join(root, base + "_neural.json")))
+    cfg["cuda_scene"]["fb_size"] = [W, H]
+    mod = nbvh_b200.NeuralPathModule(json.dumps(cfg))
+    tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root, with_neural_mesh=True, with_attributes=True)
+    mats, textures, _ = nbvh_b200.load_shading_arrays(root, with_envmap=False)
+    mod.set_scene(tl, ti, bl, materials=mats, textures=textures)
+    mod.max_depth = 1
+    mod.attach_framebuffer((W, H))
+    res = validation.run_full_validation(mod, cfg, str(tmp_path / "py"), max_training_steps=steps, max_accumulated_spp=spp, base=base, variant="py")
+    assert info["tree_cut_nodes"] == res["tree_cut_nodes"] > 1
+    py_losses = np.array(res["losses"])
+    assert abs(cpp_losses[0] - py_losses[0]) <= 2e-5 * py_losses[0]
+    assert np.abs(cpp_losses - py_losses).max() <= 0.02 * py_losses.max()
+    a = results.read_exr(str(out / ("results/%s_cpp_spp_2.exr" % base)))
+    b = results.read_exr(res["paths"]["image"])
+    assert a.shape == b.shape == (H, W, 4) and np.abs(a - b).mean() < 0.02
+    # the C++ host's files load back: its tree-cut and weights render through the Python host
+    mod.load_neural_bvh(str(out / ("nbvhs/%s.nbvh" % base)))
+    mod.load_network_model(str(out / ("network_models/%s_network.json" % base)))
+    assert len(mod.neural_bvh_nodes()) == info["tree_cut_nodes"]
+    mod.close()
