@@ -466,7 +466,9 @@ int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint3
 /* ---- f4: result writers and configuration round trip ------------------------------------------------------------ */
 /* == NeuralBVHRenderer::compute_and_display_flip_error (src/cuda/neural/neural_bvh_renderer.cu:34-96; replaces ext/flip-cuda): mean
  * LDR-FLIP of accum / accumulated_spp against a device RGBA32F reference image of the framebuffer's size.  ppd <= 0: the reference's
- * viewing conditions (67.02 pixels per degree).  error_map_out: optional device array of W x H floats (per-pixel FLIP error). */
+ * viewing conditions (67.02 pixels per degree).  error_map_out: optional device array of W x H floats (per-pixel FLIP error).
+ * Like the reference, the images are NOT clamped to [0, 1] first: LDR-FLIP is defined on that range, and HDR highlights can drive the
+ * feature exponent past 1 (per-pixel errors above 1 or infinite, in flip-cuda as well); clamp or tone-map beforehand for such images. */
 int nbvh_flip_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, float ppd, float *error_map_out,
                     float *mean_flip_host, void *stream);
 /* the same for two arbitrary device RGBA32F images (linear RGB, alpha ignored); test is divided by test_divisor first */
