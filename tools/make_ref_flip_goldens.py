@@ -34,9 +34,17 @@ def image_pair(w, h, seed, hdr):
     return ref.astype(np.float32), test.astype(np.float32)
 
 
+F = np.float32
+DEFAULT_PPD = float(F(0.7) * (F(3840.0) / F(0.7)) * (F(3.14159265358979) / F(180.0)))  # neural_bvh_renderer.cu:34-38,43-47
+
+
+def linear_to_srgb(l):  # the reference converts both images with LinearRGB2sRGB before FLIP (neural_bvh_renderer.cu:65-66)
+    l = l.astype(F)
+    return np.where(l <= F(0.0031308), l * F(12.92), F(1.055) * np.power(l, F(1.0 / 2.4), dtype=F) - F(0.055)).astype(F)
+
+
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "py"
-    from oracle import flip as OF
     if mode == "py":
         import types
         sys.path.insert(0, "/root/reference/figures")
@@ -44,9 +52,9 @@ def main():
             sys.modules.setdefault(missing, types.ModuleType(missing))
         from flip.flip_api import compute_ldrflip
         ref, test = image_pair(64, 48, 7, hdr=False)
-        err = np.squeeze(compute_ldrflip(OF.linear_to_srgb(ref).transpose(2, 0, 1), OF.linear_to_srgb(test).transpose(2, 0, 1), OF.DEFAULT_PPD))
+        err = np.squeeze(compute_ldrflip(linear_to_srgb(ref).transpose(2, 0, 1), linear_to_srgb(test).transpose(2, 0, 1), DEFAULT_PPD))
         out = os.path.join(REPO, "tests", "golden", "ref_flip_py_64x48.npz")
-        np.savez_compressed(out, reference=ref, test=test, error_map=err.astype(np.float32), ppd=np.float32(OF.DEFAULT_PPD))
+        np.savez_compressed(out, reference=ref, test=test, error_map=err.astype(np.float32), ppd=np.float32(DEFAULT_PPD))
         print("wrote", out, "mean", float(err.mean()))
         return 0
     tool = os.path.join(REPO, "oracle", "_ref", "flip_harness")
@@ -60,8 +68,8 @@ def main():
         err = np.fromfile(os.path.join(d, "e.f32"), "<f4").reshape(90, 160)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     out = os.path.join(REPO, "gpurun_out", "ref_flip_cuda_160x90.npz")
-    np.savez_compressed(out, reference=ref, test=test, error_map=err, ppd=np.float32(OF.DEFAULT_PPD))
-    print("wrote", out, "mean", float(err.mean()), "oracle max|diff|", float(np.abs(OF.flip(ref, test) - err).max()))
+    np.savez_compressed(out, reference=ref, test=test, error_map=err, ppd=np.float32(DEFAULT_PPD))
+    print("wrote", out, "mean", float(err.mean()))
     return 0
 
 
