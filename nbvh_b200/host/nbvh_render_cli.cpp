@@ -54,7 +54,8 @@ int main(int argc, char **argv)
         mod.load_neural_bvh(dir + "/" + base + ".nbvh");
         mod.load_network_model(dir + "/" + base + "_network.json");
         // scene: TLAS + per-mesh BLAS (the neural mesh's own BLAS is not needed for inference: a one-node placeholder)
-        const auto tlas = slurp(dir + "/tlas_nodes.bin"), tlas_idx = slurp(dir + "/tlas_indices.u32");
+        // TLAS: the host-built files when present (ext/bvh, like CudaBackend::build_tlas), otherwise built on the device below
+        const auto tlas = slurp(dir + "/tlas_nodes.bin", false), tlas_idx = slurp(dir + "/tlas_indices.u32", false);
         std::vector<nbvh_cuda_blas> meshes;
         for (int m = 0;; ++m) {
             const std::string p = dir + "/mesh" + std::to_string(m);
@@ -63,7 +64,10 @@ int main(int argc, char **argv)
                 break;
             nbvh_cuda_blas b{};
             if (m == 0) { // neural mesh (manifest.json: neural_mesh 0)
-                std::vector<uint8_t> one(32, 0), tri(36, 0), idx(12, 0), prim(8, 0);
+                // one-node placeholder that keeps the real root box (the device TLAS build reads it) and holds one degenerate triangle
+                std::vector<uint8_t> one(nodes.begin(), nodes.begin() + 32), tri(36, 0), idx(12, 0), prim(8, 0);
+                reinterpret_cast<nbvh_node32 *>(one.data())->prim_count_or_left = 1;
+                reinterpret_cast<nbvh_node32 *>(one.data())->left_or_prim_offset = 0;
                 b.num_nodes = 1, b.nodes = upload<nbvh_node32>(one.data(), 32), b.vertices = upload<float>(tri.data(), 36);
                 b.indices = upload<uint32_t>(idx.data(), 12), b.prim_indices = upload<uint64_t>(prim.data(), 8), b.num_prim_indices = 1;
             } else {
@@ -78,9 +82,20 @@ int main(int argc, char **argv)
             meshes.push_back(b);
         }
         nbvh_scene_data scene{};
-        scene.tlas_nodes = upload<nbvh_node32>(tlas.data(), tlas.size()), scene.num_tlas_nodes = (uint32_t)(tlas.size() / 32);
-        scene.blas_indices = upload<uint32_t>(tlas_idx.data(), tlas_idx.size());
         scene.mesh_bvhs = upload<nbvh_cuda_blas>(meshes.data(), meshes.size() * sizeof(nbvh_cuda_blas)), scene.num_meshes = (uint32_t)meshes.size();
+        if (!tlas.empty() && !tlas_idx.empty()) {
+            scene.tlas_nodes = upload<nbvh_node32>(tlas.data(), tlas.size()), scene.num_tlas_nodes = (uint32_t)(tlas.size() / 32);
+            scene.blas_indices = upload<uint32_t>(tlas_idx.data(), tlas_idx.size());
+        } else { // nbvh_build_tlas over the meshes' root boxes; mesh 0 is the mesh the N-BVH stands for (manifest.json)
+            const uint32_t n = (uint32_t)meshes.size();
+            nbvh_node32 *nodes_dev = nullptr;
+            cudaMalloc(reinterpret_cast<void **>(&nodes_dev), (size_t)(2 * n - 1) * sizeof(nbvh_node32));
+            uint32_t *idx_dev = nullptr;
+            cudaMalloc(reinterpret_cast<void **>(&idx_dev), n * sizeof(uint32_t));
+            mod.build_tlas(scene.mesh_bvhs, n, {0u}, nodes_dev, idx_dev);
+            cudaDeviceSynchronize();
+            scene.tlas_nodes = nodes_dev, scene.num_tlas_nodes = 2 * n - 1, scene.blas_indices = idx_dev;
+        }
         mod.set_scene(scene);
         uint32_t W = 1920, H = 1080, spp = 1;
         if (argc >= 6)

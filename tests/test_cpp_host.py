@@ -79,6 +79,30 @@ def test_cli_frame_equals_python_host_frame(tmp_path, spp):
 
 
 @pytest.mark.gpu
+def test_cli_with_device_built_tlas_renders_the_same_frame(tmp_path):
+    """Without the TLAS files the C++ host builds the TLAS on the device (nbvh_build_tlas): same frame, byte for byte."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nbvh_b200 import scene_io
+    root = scene_io.chess_fixture_dir()
+    if root is None:
+        pytest.skip("Chess fixture missing")
+    view = tmp_path / "scene"
+    view.mkdir()
+    for name in os.listdir(root):
+        if not name.startswith("tlas_") and os.path.isfile(os.path.join(root, name)):
+            os.symlink(os.path.join(root, name), view / name)
+    imgs = []
+    for d in (root, str(view)):
+        out = tmp_path / ("a.ppm" if d == root else "b.ppm")
+        r = subprocess.run([_cli(), d, scene_io.CHESS_BASE, str(out), "320", "180", "1", "1"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        imgs.append(_read_ppm(out))
+    assert imgs[0].std() > 5 and (imgs[0] == imgs[1]).all()
+
+
+@pytest.mark.gpu
 def test_cli_exr_is_accumulation_over_spp(tmp_path):
     import torch
     if not torch.cuda.is_available():
