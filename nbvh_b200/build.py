@@ -15,24 +15,54 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared",
 ]
+LINK_LIBS = ["-ldl"]
+
+
+OBJ_DIR = os.path.join(HERE, "_obj")
+
+
+def _deps():
+    return [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
 
 
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def _compile_and_link(out, defines=(), tag="default", force=False, verbose=False):
+    """One nvcc -c per translation unit (in parallel; only the units whose sources or headers changed), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    odir = os.path.join(OBJ_DIR, tag)
+    os.makedirs(odir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for s in SOURCES:
+        src, obj = os.path.join(CSRC, s), os.path.join(odir, s.replace(".cu", ".o"))
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_t, os.path.getmtime(src)):
+            jobs.append([nvcc] + flags + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        print("[nbvh_b200.build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(odir, s.replace(".cu", ".o")) for s in SOURCES]
+    run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-shared", "-o", out] + objs + LINK_LIBS)
+    return out
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         build_host()
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
+    _compile_and_link(LIB, force=force, verbose=verbose)
     build_host()
     return LIB
 
@@ -60,11 +90,7 @@ def build_variant(name, defines):
     """A/B experiments on the GPU box: the same sources with extra -D switches -> libnbvh_b200_<name>.so, selected at
     load time with NBVH_B200_LIB=<path> (development only; the product library is libnbvh_b200.so)."""
     out = os.path.join(HERE, "libnbvh_b200_%s.so" % name)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
-    print("[nbvh_b200.build]", " ".join(cmd), flush=True)
-    subprocess.check_call(cmd)
-    return out
+    return _compile_and_link(out, defines=defines, tag="variant_" + name, force=True)
 
 
 if __name__ == "__main__":

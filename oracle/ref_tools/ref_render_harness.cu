@@ -9,6 +9,9 @@
 // render_app.cpp:307-312) are replaced by plain cudaMalloc buffers and cudaArray surfaces.
 //
 // usage: ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames>
+//        ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames> timing
+//          (bench.py's live reference-GPU arm: the reference's frame loop only, 3 warm-up + <n_timed_frames> timed frames,
+//           no parity hooks and no dumps besides ref_frame.json; shading inputs are read when present, as in `path` mode)
 //        ref_render_harness <workdir> <W> <H> <max_depth> <log2_hashmap> <n_timed_frames> path <spp>
 //          (hybrid neural path tracing with shading: also reads materials.bin, tex<k>.rgba8 + tex<k>.dims, envmap.f32 + envmap.dims,
 //           mesh<i>_{normals.f32,texcoords.f32,material_ids.i32,material_map.u32}; writes path_accum_1spp.f32 / path_accum.f32 =
@@ -619,7 +622,9 @@ int main(int argc, char **argv)
     Buffers b = make_buffers(n_pix, in_dims, out_dims);
 
     // ---- parity hooks (skipped in path mode: image goldens and timings only)
-    const bool path_mode  = argc >= 9 && std::string(argv[7]) == "path";
+    // `timing` (bench.py's live reference-GPU arm): the frame loop only -- no parity hooks, no dumps besides ref_frame.json
+    const bool timing_only = argc >= 8 && std::string(argv[7]) == "timing";
+    const bool path_mode  = timing_only || (argc >= 9 && std::string(argv[7]) == "path");
     const uint32_t blocks = (n_pix + 255) / 256;
     float *d_rays = dalloc<float>((size_t)n_pix * 6);
     if (!path_mode) {
@@ -658,7 +663,7 @@ int main(int argc, char **argv)
         dump(wd + "/step0_out.f32", s0out);
         dump(wd + "/step0_pixel.u32", s0px);
     }
-    {
+    if (!timing_only) {
         std::vector<uchar4> ldr((size_t)n_pix);
         CK(cudaMemcpy2DFromArray(ldr.data(), W * 4, arr_ldr, 0, 0, W * 4, H, cudaMemcpyDeviceToHost));
         dump(wd + "/frame_ldr.u8", ldr);
@@ -668,7 +673,7 @@ int main(int argc, char **argv)
            (unsigned long long)st.launches, (unsigned long long)st.host_syncs);
 
     // ---- path mode: accumulate `spp` samples through the reference's frame loop and dump the RGBA32F accumulation buffer
-    if (path_mode) {
+    if (path_mode && !timing_only) {
         const int spp = atoi(argv[8]);
         std::vector<float4> acc((size_t)n_pix);
         CK(cudaMemcpy2DFromArray(acc.data(), W * 16, arr_acc, 0, 0, W * 16, H, cudaMemcpyDeviceToHost));
