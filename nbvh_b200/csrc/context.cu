@@ -269,6 +269,8 @@ struct nbvh_ctx {
     TreeCutResult *d_tc_result = nullptr;
     bool tree_cut_ready = false;
     uint32_t tree_cut_max_depth = 0;
+    void *d_sampler_items = nullptr; // two-pass sample generator: 48-byte items handed from k_sample_walk to k_sample_targets (grow-only)
+    uint32_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
     bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
     bool blas_safe[kMaxBlas] = {};
@@ -295,7 +297,7 @@ struct nbvh_ctx {
     nbvh_hit_record *hits = nullptr;
     nbvh_hit_record *own_hits = nullptr;
 
-    uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor, [3] node-check flag, [4] sampler slot counter
+    uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor, [3] node-check flag, [4] sampler slot counter, [5] image-error sum, [6] BLAS depth, [7] sampler item count
     NeuralQueueEntry *d_queue = nullptr;
     size_t queue_capacity = 0;
     bool l2_prefetch = false; // NBVH_L2_PREFETCH=1 enables a per-frame L2 warm-up of the gather tables (A/B: no effect measured)
@@ -620,6 +622,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaFree(ctx->ldr);
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
+    cudaFree(ctx->d_sampler_items);
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
@@ -1410,6 +1413,17 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.current_max_loss = current_max_loss;
     sp.tree_cut         = tree_cut_data;
     sp.counters         = ctx->d_counters;
+    if (sp.n_sub_batch == 1) {
+        if (ctx->sampler_item_capacity < batch_size) {
+            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); // an earlier generation may still read the old list
+            cudaFree(ctx->d_sampler_items);
+            ctx->d_sampler_items = nullptr, ctx->sampler_item_capacity = 0;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_items, (size_t)batch_size * 48u));
+            ctx->sampler_item_capacity = batch_size;
+        }
+        sp.items      = ctx->d_sampler_items;
+        sp.item_count = ctx->d_next_chunk ? ctx->d_next_chunk + 7 : nullptr;
+    }
     CU_TRY(ctx, launch_generate_batch(sp, ctx->d_next_chunk ? ctx->d_next_chunk + 4 : nullptr, ctx->num_sms, (cudaStream_t)stream));
     return NBVH_OK;
 }

@@ -33,14 +33,9 @@ namespace nbvh {
 constexpr int kNeuralTiles   = NBVH_NEURAL_TILES;        // 128-lane tiles per CTA
 constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
 constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
-#ifndef NBVH_SPECULATE
-#define NBVH_SPECULATE 0 // measured on B200 (tools/neural_timeline.py): tile fill 0.65 -> 0.82, kernel time unchanged -- the 16 KB of
-                         // staging smem cost L1 capacity in the steady state (queue dry 231 -> 282 us) and the drain got only 50 us shorter
+#ifndef NBVH_COOP_ENCODE
+#define NBVH_COOP_ENCODE 1 // warp-cooperative hash-grid gathers (render_common.cuh: encode_rows_coop); 0 = one row per lane
 #endif
-#ifndef NBVH_MAX_SPEC
-#define NBVH_MAX_SPEC 3
-#endif
-constexpr int kMaxSpec = NBVH_MAX_SPEC; // look-ahead intervals per ray when the tile has free rows
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
@@ -226,12 +221,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
-#if NBVH_SPECULATE
-    // speculative look-ahead (see below): extra queries of a tile, their results, and per-warp query counts
-    __shared__ float4 s_xq[kNeuralTiles][kTileRows][2];
-    __shared__ float4 s_res[kNeuralTiles][kTileRows][2];
-    __shared__ uint32_t s_cnt[kNeuralThreads / 32];
-#endif
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles);
     const uint32_t tmem_base = cta_setup<kNeuralTiles>(nc, smem, lay);
     const uint32_t tile      = threadIdx.x / kTileRows;
@@ -255,9 +244,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         t_cta0 = global_timer_ns();
         atomicMax(p.counters + CNT_T_START_INV, ~t_cta0);
     }
-#if NBVH_SPECULATE
-    uint32_t n_q = 0, q_before = 0, q_rank = 0, f_rank = 0, tile_flags = 0;
-#endif
 
     for (;;) {
         // ---------------- walk phase: every lane works until it owns a pending interval (or the queue is drained)
@@ -333,11 +319,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         {
             const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
             const uint32_t live = (__any_sync(0xFFFFFFFFu, s.have_ray) || !exhausted) ? 2u : 0u;
-#if NBVH_SPECULATE
-            const uint32_t qmask_w = __ballot_sync(0xFFFFFFFFu, s.have_query);
-            if (lane == 0)
-                s_cnt[warp] = __popc(qmask_w);
-#endif
             if (lane == 0)
                 s_flags[warp] = q | live | (exhausted ? 0u : 4u); // bit 2: this warp can still refill from the queue
             named_bar_sync(t.bar_id, kTileRows);
@@ -345,77 +326,26 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #pragma unroll
             for (int w = 0; w < kTileRows / 32; ++w)
                 f |= s_flags[tile * (kTileRows / 32) + w];
-#if NBVH_SPECULATE
-            n_q = 0, q_before = 0;
-#pragma unroll
-            for (int w = 0; w < kTileRows / 32; ++w) {
-                const uint32_t c = s_cnt[tile * (kTileRows / 32) + w];
-                if ((uint32_t)w < (warp % (kTileRows / 32)))
-                    q_before += c;
-                n_q += c;
-            }
-            q_rank = q_before + __popc(qmask_w & ((1u << lane) - 1u));                         // rank among the tile's query lanes
-            f_rank = (warp % (kTileRows / 32)) * 32u - q_before + __popc(~qmask_w & ((1u << lane) - 1u)); // rank among its free lanes
-#endif
             named_bar_sync(t.bar_id, kTileRows);
             if ((f & 3u) == 0u)
                 break;
             if (!(f & 1u))
                 continue;
-#if NBVH_SPECULATE
-            tile_flags = f;
-#endif
         }
-#if NBVH_SPECULATE
-        // ---------------- speculative look-ahead.  The queries of one ray form a dependent chain (the walk resumes with the hit
-        // found so far), and the end of the launch is a tail of such chains at low tile fill.  When at least half of the tile's
-        // rows are free and the queue is drained (no refills any more: the tail), every lane with a pending interval walks on to its next n_spec intervals (with the closest t it knows
-        // NOW) and hands them to free rows; after the network pass it consumes the results in order and drops those whose
-        // interval the in-order walk would not have returned (entry not nearer than the then-closest hit).  Pruning only removes
-        // intervals from the in-order sequence and never reorders it, and the hit update is a minimum, so the final hit is
-        // bit-identical -- the chain is n_spec + 1 times shorter, paid with rows that would have idled.
-        const uint32_t n_spec = (!(tile_flags & 4u) && n_q > 0u && 2u * n_q <= (uint32_t)kTileRows) ? min((uint32_t)kMaxSpec, ((uint32_t)kTileRows - n_q) / n_q) : 0u;
-        bool helper = false;
-        Ray hray;
-        float h_mint = 0.f, h_maxt = 0.f;
-        if (n_spec) {
-            if (s.have_query) {
-                for (uint32_t j = 0; j < n_spec; ++j) {
-                    float mint = 1.f, maxt = 0.f; // invalid
-                    uint32_t node;
-                    if (s.nss > 0 && !nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, mint, maxt, node, cnt_nbvh))
-                        mint = 1.f, maxt = 0.f, s.nss = 0;
-                    s_xq[tile][q_rank * n_spec + j][0] = make_float4(s.ray.ox, s.ray.oy, s.ray.oz, s.ray.dx);
-                    s_xq[tile][q_rank * n_spec + j][1] = make_float4(s.ray.dy, s.ray.dz, mint, maxt);
-                }
-            }
-            named_bar_sync(t.bar_id, kTileRows);
-            if (!s.have_query && f_rank < n_q * n_spec) {
-                const float4 a = s_xq[tile][f_rank][0], b = s_xq[tile][f_rank][1];
-                if (b.z <= b.w) {
-                    helper  = true;
-                    hray.ox = a.x, hray.oy = a.y, hray.oz = a.z, hray.dx = a.w, hray.dy = b.x, hray.dz = b.y;
-                    h_mint = b.z, h_maxt = b.w;
-                }
-            }
-        }
-#endif
         // ---------------- segment encoding + hash grid -> A tile (a8, a9)
-        float pts[12];
-#if NBVH_SPECULATE
-        const bool row_valid = s.have_query || helper;
-        if (row_valid) {
-            float eo[3], ei[3];
-            if (helper)
-                encode_endpoints(p.enc, hray, h_mint, h_maxt, eo, ei);
-            else
+#if NBVH_COOP_ENCODE
+        {
+            float eo[3] = {0.f, 0.f, 0.f}, ei[3] = {0.f, 0.f, 0.f};
+            if (s.have_query)
                 encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
+            encode_rows_coop(nc, p.enc, t.a_tile, row & ~31u, lane, eo, ei, s.have_query);
+        }
 #else
+        float pts[12];
         const bool row_valid = s.have_query;
         if (s.have_query) {
             float eo[3], ei[3];
             encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
-#endif
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k) {
                 if (k < p.enc.n_points) {
@@ -426,20 +356,12 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
             }
         }
         encode_row_to_tile(nc, t.a_tile, row, pts, row_valid);
+#endif
         fence_proxy_async_smem();
         // ---------------- MLP on tensor cores (a10), decode + closest-hit update (a11)
         float y[8];
         mlp_tile_forward(nc, t, row, y);
         ++cnt_iters;
-#if NBVH_SPECULATE
-        if (n_spec) {
-            if (helper) {
-                s_res[tile][f_rank][0] = make_float4(y[0], y[1], y[2], y[3]);
-                s_res[tile][f_rank][1] = make_float4(y[4], y[5], y[6], y[7]);
-            }
-            named_bar_sync(t.bar_id, kTileRows);
-        }
-#endif
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
@@ -449,23 +371,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 decode_normal(y[2], y[3], y[4], s.h.n_or_uv);
                 s.h.alb_or_ids[0] = y[5], s.h.alb_or_ids[1] = y[6], s.h.alb_or_ids[2] = y[7];
             }
-#if NBVH_SPECULATE
-            for (uint32_t j = 0; j < n_spec; ++j) { // the look-ahead intervals, in walk order
-                const float4 b = s_xq[tile][q_rank * n_spec + j][1];
-                if (!(b.z <= b.w))
-                    break; // the walk ended here
-                if (!(b.z < s.h.best_t))
-                    continue; // the in-order walk (ray.maxt = closest t so far) would have skipped this leaf
-                ++cnt_q;
-                const float4 r0 = s_res[tile][q_rank * n_spec + j][0], r1 = s_res[tile][q_rank * n_spec + j][1];
-                if (decode_hit(p.dec, r0.x, r0.y, b.z, b.w, kPath ? p.ray_depth : 1u, t_hit) && t_hit < s.h.best_t) {
-                    s.h.best_t    = t_hit;
-                    s.h.valid_hit = 1u;
-                    decode_normal(r0.z, r0.w, r1.x, s.h.n_or_uv);
-                    s.h.alb_or_ids[0] = r1.y, s.h.alb_or_ids[1] = r1.z, s.h.alb_or_ids[2] = r1.w;
-                }
-            }
-#endif
             s.have_query = false;
         }
     }

@@ -70,6 +70,43 @@ __device__ __forceinline__ TileCtx make_tile(uint8_t *smem, const SmemLayout &la
     return t;
 }
 
+// Warp-cooperative segment encoding for SPARSE tiles (k_neural: walk divergence and the drain of dependent query chains leave
+// ~19 of 32 lanes with a pending query, far fewer in the tail).  The 16-byte chunks (two (point, level) pairs, 16 table gathers)
+// of the warp's ACTIVE rows are dealt round-robin to all 32 lanes, so a warp with n active rows spends ceil(n * in_k/8 / 32)
+// gather rounds instead of in_k/8 and idle lanes hide the gather latency of busy ones.  The segment end points travel by
+// shuffle; every chunk is computed by the same arithmetic as encode_row_to_tile (lerp_point + grid_level_features), so the A tile
+// holds the same bits.  Rows without a query are not written: rows of a GEMM are independent and their outputs are never read.
+__device__ __forceinline__ void encode_rows_coop(const NetConst &nc, const EncodeConst &ec, uint8_t *a_tile, uint32_t warp_row0,
+                                                 uint32_t lane, const float eo[3], const float ei[3], bool valid)
+{
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid);
+    if (mask == 0u)
+        return;
+    const uint32_t pairs  = nc.in_k >> 3;
+    const uint32_t items  = (uint32_t)__popc(mask) * pairs;
+    const uint32_t my_src = __fns(mask, 0u, lane + 1u); // lane of the (lane+1)-th active row (garbage beyond the count: never used)
+    for (uint32_t base = 0; base < items; base += 32u) {
+        const uint32_t it = base + lane;
+        const bool on     = it < items;
+        const uint32_t r  = on ? it / pairs : 0u;
+        const uint32_t j  = it - r * pairs;
+        const uint32_t src = __shfl_sync(0xFFFFFFFFu, my_src, r) & 31u;
+        const float ox = __shfl_sync(0xFFFFFFFFu, eo[0], src), oy = __shfl_sync(0xFFFFFFFFu, eo[1], src),
+                    oz = __shfl_sync(0xFFFFFFFFu, eo[2], src);
+        const float ix = __shfl_sync(0xFFFFFFFFu, ei[0], src), iy = __shfl_sync(0xFFFFFFFFu, ei[1], src),
+                    iz = __shfl_sync(0xFFFFFFFFu, ei[2], src);
+        if (on) {
+            const uint32_t q0 = 2u * j, q1 = 2u * j + 1u;
+            const uint32_t p0 = q0 / nc.n_levels, l0 = q0 - p0 * nc.n_levels;
+            const uint32_t p1 = q1 / nc.n_levels, l1 = q1 - p1 * nc.n_levels;
+            const float s0 = ec.point_s[p0], s1 = ec.point_s[p1];
+            const uint2 f0 = grid_level_features(nc.grid, nc.lv[l0], lerp_point(ox, ix, s0), lerp_point(oy, iy, s0), lerp_point(oz, iz, s0));
+            const uint2 f1 = grid_level_features(nc.grid, nc.lv[l1], lerp_point(ox, ix, s1), lerp_point(oy, iy, s1), lerp_point(oz, iz, s1));
+            *reinterpret_cast<uint4 *>(a_tile + tile_chunk_off(warp_row0 + src, j, nc.in_k)) = make_uint4(f0.x, f0.y, f1.x, f1.y);
+        }
+    }
+}
+
 __device__ __forceinline__ void warp_add_counter(unsigned long long *counters, int slot, uint32_t v)
 {
     v = __reduce_add_sync(0xFFFFFFFFu, v);

@@ -234,46 +234,63 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ n_sub_batch == 1
-// One slot per reference thread means slots are independent (the RNG is keyed by the slot id), so a persistent warp may
-// process them in any order.  Each lane runs the retry walk as a state machine; a lane whose ray found a surviving leaf
-// PARKS, and when enough lanes are parked the warp traces their leaf segments together (emit_slot).  Idle lanes are
-// refilled from a global slot counter.  Per slot the draws and the arithmetic are exactly those of k_generate_batch,
-// so the outputs are bit-identical; only the lane <-> slot assignment changes.
-constexpr uint32_t kParkThreshold   = 20u; // parked lanes that trigger the target pass
-constexpr uint32_t kRefillThreshold = 8u;  // idle lanes that trigger a refill
+// One slot per reference thread means slots are independent (the RNG is keyed by the slot id), so they may be processed in any
+// order and in two passes.  Per slot the draws and the arithmetic are exactly those of k_generate_batch, so the outputs are
+// bit-identical; only the lane <-> slot assignment changes.
+//
+//   k_sample_walk     persistent warps, nothing but the retry walk (85 % of a slot's work on Chess: 8 origins and 70 interior
+//                     steps per slot on average, heavy-tailed): every lane visits ONE node per iteration (per-node state
+//                     machine), a lane whose ray met a leaf appends a 48-byte item {slot, node, rng, ray, interval} with one atomic
+//                     per warp and refills at once from the global slot counter -- no lane waits for others.  The stack carries
+//                     the raw slab result of every pushed (far) child, so a popped leaf needs no second slab test: the leaf
+//                     branch is a handful of compares and the warp executes one instruction stream, the interior step.
+//                     (Same ray, same dilated box, same operations -> the stored values are the bits the reference's re-test
+//                     computes.)  The direction of a slot never changes, so its reciprocals are refined once per slot.
+//   k_sample_targets  one thread per item: node-survival roulette, segment encoding, leaf-segment trace against the neural
+//                     mesh's BLAS, surface attributes, texture fetches, targets (emit_slot).
+struct SampleItem {
+    uint4 a; // slot, node, rng, ox
+    uint4 b; // oy, oz, dx, dy
+    uint4 c; // dz, leaf_mint, leaf_maxt, -
+};
+
+constexpr uint32_t kRefillThreshold = 8u; // idle lanes that trigger a refill
+constexpr uint32_t kRestartVote     = 3u; // lanes waiting for a new origin that trigger the restart block
 
 __global__ void __launch_bounds__(128)
-k_generate_batch_wq(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ slot_counter)
+k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ slot_counter)
 {
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t total = (uint32_t)p.sub_batch_size;
     NbvhConst bc = p.nbvh;
-    uint32_t nstack[kNeuralStackSize];
+    // stack of far children with their raw slab results (thread-private)
+    uint32_t st_idx[kNeuralStackSize];
+    float st_cmax[kNeuralStackSize], st_cmin[kNeuralStackSize];
     int nss = 0;
-    float leaf_mint = 0.f, leaf_maxt = 0.f;
     Ray ray;
     ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
     ray_prepare(ray, false);
-    WalkState w;
-    w.node_idx = 0u, w.have_raw = false, w.cmax = w.cmin = 0.f;
-    w.node.a = w.node.b = 0u;
-    uint32_t rng = 0u, slot = 0u, node_idx = 0u;
-    bool have_slot = false, walking = false, parked = false, exhausted = false;
-    uint32_t cnt_nbvh = 0, cnt_blas = 0, cnt_tri = 0, cnt_written = 0;
+    Node node;
+    node.mnx = node.mny = node.mnz = node.mxx = node.mxy = node.mxz = 0.f, node.a = node.b = 0u;
+    uint32_t node_idx = 0u;
+    float cmax = 0.f, cmin = 0.f;
+    bool have_raw = false;
+    uint32_t rng = 0u, slot = 0u;
+    bool have_slot = false, walking = false, exhausted = false;
+    uint32_t cnt_nbvh = 0;
     const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
     const uint32_t n_lods = p.num_bvh_lods - p.current_learned_lod;
 
     for (;;) {
         // ---------------- refill idle lanes from the global counter (one atomic per refill)
         const uint32_t idle_mask = __ballot_sync(0xFFFFFFFFu, !have_slot);
-        const uint32_t busy      = 32u - (uint32_t)__popc(idle_mask);
-        if (!exhausted && ((uint32_t)__popc(idle_mask) >= kRefillThreshold || busy == 0u)) {
-            const uint32_t want = (uint32_t)__popc(idle_mask);
+        const uint32_t n_idle    = (uint32_t)__popc(idle_mask);
+        if (!exhausted && (n_idle >= kRefillThreshold || n_idle == 32u)) {
             uint32_t base = 0u;
             if (lane == 0u)
-                base = atomicAdd(slot_counter, want);
+                base = atomicAdd(slot_counter, n_idle);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base + want >= total)
+            if (base + n_idle >= total)
                 exhausted = true;
             if (!have_slot) {
                 const uint32_t sl = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
@@ -283,54 +300,150 @@ k_generate_batch_wq(const __grid_constant__ SamplerParams p, uint32_t *__restric
                     const float s0 = lcg_randomf(rng), s1 = lcg_randomf(rng);
                     const V3 dir   = square_to_uniform_sphere(s0, s1);
                     ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+                    ray_prepare_guarded(ray); // the direction is fixed for the slot: only origins are redrawn
                     const uint32_t lod = p.current_learned_lod + min((uint32_t)__fmul_rn(lcg_randomf(rng), __uint2float_rn(n_lods)), n_lods - 1u);
                     bc.leaf_lod_max = 2u + lod;
                     bc.dilation     = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
-                    have_slot = true, walking = false, parked = false;
+                    have_slot = true, walking = false;
                 }
             }
         }
-        const bool active = have_slot && !parked;
         if (!__any_sync(0xFFFFFFFFu, have_slot))
             break; // nothing in flight and the counter is exhausted
-        // ---------------- one node visit for every lane with a live slot
-        if (active) {
-            if (!walking) {
-                nstack[0] = 0u, nss = 1;
-                const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
-                const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
-                            lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
-                ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]);
-                ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
-                ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
-                ray_prepare_guarded(ray);
-                walk_pop(bc, w, nstack, nss);
-                walking = true;
-            }
-            const WalkResult r = nbvh_walk_step(bc, ray, w, nstack, nss, FLT_MAX, leaf_mint, leaf_maxt, node_idx, cnt_nbvh);
-            if (r == WALK_EXHAUSTED) {
-                walking = false;
-            } else if (r == WALK_FOUND) {
-                p.sampled_node_indices[slot] = node_idx;
-                if (p.training_node_survival && !node_survives(p, node_idx, rng))
-                    have_slot = false; // rejected: the slot keeps its previous contents
-                else
-                    parked = true;
+        // ---------------- new origin for lanes whose walk ended without a leaf (voted: the block costs the whole warp)
+        {
+            const uint32_t need = __ballot_sync(0xFFFFFFFFu, have_slot && !walking);
+            const uint32_t busy = __ballot_sync(0xFFFFFFFFu, have_slot && walking);
+            if (need && ((uint32_t)__popc(need) >= kRestartVote || busy == 0u || (uint32_t)__popc(need) * 4u >= (uint32_t)__popc(busy))) {
+                if (have_slot && !walking) {
+                    const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
+                    const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
+                                lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
+                    ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
+                    ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
+                    ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
+                    nss      = 0; // the root is the current node (the reference pops it from the stack [0])
+                    node_idx = 0u;
+                    node     = load_node(bc.nodes, 0u);
+                    have_raw = false;
+                    walking  = true;
+                }
             }
         }
-        // ---------------- target pass once enough lanes are parked (or nothing else is left to walk)
-        const uint32_t parked_mask = __ballot_sync(0xFFFFFFFFu, parked);
-        const bool any_walking     = __any_sync(0xFFFFFFFFu, have_slot && !parked);
-        if (parked_mask && ((uint32_t)__popc(parked_mask) >= kParkThreshold || !any_walking)) {
-            if (parked) {
-                ItsData its;
-                emit_slot(p, slot, ray, leaf_mint, leaf_maxt, false, its, cnt_blas, cnt_tri);
-                ++cnt_written;
-                parked = false, have_slot = false;
+        // ---------------- one node visit for every walking lane
+        bool found = false;
+        if (have_slot && walking) {
+            const bool is_leaf = (node.a > 0u && node.a <= bc.leaf_lod_max);
+            if (is_leaf || node.b == kNoNeuralChild) {
+                if (!have_raw) { // only a root that is a leaf itself arrives here without its slab result
+                    dilate_node(node, bc.dilation);
+                    slab_raw(node, ray, cmax, cmin);
+                }
+                if (cmax <= cmin) {
+                    // cur_maxt = FLT_MAX: the reference's `cmax < ray.maxt` only rejects cmax = +inf / NaN
+                    const bool valid = (cmax < FLT_MAX) && ((cmax < 0.f) ? (cmin > bc.maxt_eps) : (cmax > bc.mint_eps));
+                    found = valid;
+                }
+                if (!found) {
+                    if (nss == 0) {
+                        walking = false;
+                    } else {
+                        --nss;
+                        node_idx = st_idx[nss], cmax = st_cmax[nss], cmin = st_cmin[nss];
+                        const float4 lo = __ldg(bc.nodes + 2u * node_idx), hi = __ldg(bc.nodes + 2u * node_idx + 1u);
+                        node.a = __float_as_uint(lo.w), node.b = __float_as_uint(hi.w); // only the tags are needed: the box was tested at push time
+                        have_raw = true;
+                    }
+                }
+            } else {
+                ++cnt_nbvh;
+                uint32_t c1 = node.b, c2 = node.b + 1u;
+                Node n1 = load_node(bc.nodes, c1), n2 = load_node(bc.nodes, c2);
+                dilate_node(n1, bc.dilation);
+                dilate_node(n2, bc.dilation);
+                float cmax1, cmin1, cmax2, cmin2;
+                slab_raw(n1, ray, cmax1, cmin1);
+                slab_raw(n2, ray, cmax2, cmin2);
+                const float e1 = gmax(-FLT_MAX, cmax1), x1 = gmin(FLT_MAX, cmin1);
+                const float e2 = gmax(-FLT_MAX, cmax2), x2 = gmin(FLT_MAX, cmin2);
+                float m1 = (e1 <= x1) ? e1 : FLT_MAX;
+                float m2 = (e2 <= x2) ? e2 : FLT_MAX;
+                const bool swap = m1 > m2;
+                if (swap) {
+                    const float t = m1;
+                    m1 = m2, m2 = t;
+                    const uint32_t ti = c1;
+                    c1 = c2, c2 = ti;
+                }
+                if (m1 == FLT_MAX) {
+                    if (nss == 0) {
+                        walking = false;
+                    } else {
+                        --nss;
+                        node_idx = st_idx[nss], cmax = st_cmax[nss], cmin = st_cmin[nss];
+                        const float4 lo = __ldg(bc.nodes + 2u * node_idx), hi = __ldg(bc.nodes + 2u * node_idx + 1u);
+                        node.a = __float_as_uint(lo.w), node.b = __float_as_uint(hi.w);
+                        have_raw = true;
+                    }
+                } else {
+                    node_idx = c1;
+                    node.a   = swap ? n2.a : n1.a;
+                    node.b   = swap ? n2.b : n1.b;
+                    cmax     = swap ? cmax2 : cmax1;
+                    cmin     = swap ? cmin2 : cmin1;
+                    have_raw = true;
+                    if (m2 != FLT_MAX) {
+                        st_idx[nss] = c2, st_cmax[nss] = swap ? cmax1 : cmax2, st_cmin[nss] = swap ? cmin1 : cmin2;
+                        ++nss;
+                        if (nss >= kNeuralStackSize)
+                            walking = false; // reference: printf("Out of bound stack!") and the walk returns "no intersection"
+                    }
+                }
+            }
+        }
+        // ---------------- lanes that met a leaf append their item (one atomic per warp) and become idle
+        const uint32_t found_mask = __ballot_sync(0xFFFFFFFFu, found);
+        if (found_mask) {
+            uint32_t base = 0u;
+            const uint32_t leader = (uint32_t)__ffs(found_mask) - 1u;
+            if (lane == leader)
+                base = atomicAdd(p.item_count, (uint32_t)__popc(found_mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (found) {
+                uint4 *it = reinterpret_cast<uint4 *>(p.items) + 3u * (size_t)(base + (uint32_t)__popc(found_mask & ((1u << lane) - 1u)));
+                it[0] = make_uint4(slot, node_idx, rng, __float_as_uint(ray.ox));
+                it[1] = make_uint4(__float_as_uint(ray.oy), __float_as_uint(ray.oz), __float_as_uint(ray.dx), __float_as_uint(ray.dy));
+                it[2] = make_uint4(__float_as_uint(ray.dz), __float_as_uint(cmax), __float_as_uint(cmin), 0u);
+                have_slot = false, walking = false;
             }
         }
     }
     warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+}
+
+__global__ void __launch_bounds__(128)
+k_sample_targets(const __grid_constant__ SamplerParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *reinterpret_cast<const volatile uint32_t *>(p.item_count);
+    uint32_t cnt_blas = 0, cnt_tri = 0, cnt_written = 0;
+    if (i < n) {
+        const uint4 *it = reinterpret_cast<const uint4 *>(p.items) + 3u * (size_t)i;
+        const uint4 a = it[0], b = it[1], c = it[2];
+        const uint32_t slot = a.x, node_idx = a.y;
+        uint32_t rng        = a.z;
+        p.sampled_node_indices[slot] = node_idx;
+        // rejected: the slot keeps its previous contents (reference quirk)
+        if (!p.training_node_survival || node_survives(p, node_idx, rng)) {
+            Ray ray;
+            ray.ox = __uint_as_float(a.w), ray.oy = __uint_as_float(b.x), ray.oz = __uint_as_float(b.y);
+            ray.dx = __uint_as_float(b.z), ray.dy = __uint_as_float(b.w), ray.dz = __uint_as_float(c.x);
+            ray_prepare_guarded(ray);
+            ItsData its;
+            emit_slot(p, slot, ray, __uint_as_float(c.y), __uint_as_float(c.z), false, its, cnt_blas, cnt_tri);
+            ++cnt_written;
+        }
+    }
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
     warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
     warp_add_counter(p.counters, CNT_RAYS, cnt_written);
@@ -340,19 +453,27 @@ cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter
 {
     if (p.sub_batch_size <= 0)
         return cudaSuccess;
-    if (p.n_sub_batch == 1 && slot_counter && !getenv("NBVH_SAMPLER_SIMPLE")) {
+    if (p.n_sub_batch == 1 && slot_counter && p.items && p.item_count && !getenv("NBVH_SAMPLER_SIMPLE")) {
         cudaError_t e = cudaMemsetAsync(slot_counter, 0, sizeof(uint32_t), stream);
         if (e != cudaSuccess)
             return e;
+        if ((e = cudaMemsetAsync(p.item_count, 0, sizeof(uint32_t), stream)) != cudaSuccess)
+            return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_generate_batch_wq, 128, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0);
         if (e != cudaSuccess)
             return e;
-        const uint32_t want = ((uint32_t)p.sub_batch_size + 127u) / 128u;
+        // every lane should own several slots (the retry count is heavy-tailed): small batches get a smaller grid
+        const uint32_t want = ((uint32_t)p.sub_batch_size + 4u * 128u - 1u) / (4u * 128u);
         uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1));
         if (grid > want)
             grid = want;
-        k_generate_batch_wq<<<grid, 128, 0, stream>>>(p, slot_counter);
+        if (grid < (uint32_t)num_sms) // ... but never fewer CTAs than SMs (one warp per scheduler at least)
+            grid = min((uint32_t)num_sms, ((uint32_t)p.sub_batch_size + 127u) / 128u);
+        k_sample_walk<<<grid, 128, 0, stream>>>(p, slot_counter);
+        if ((e = cudaGetLastError()) != cudaSuccess)
+            return e;
+        k_sample_targets<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);
         return cudaGetLastError();
     }
     k_generate_batch<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);

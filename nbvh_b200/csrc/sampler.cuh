@@ -27,6 +27,9 @@ struct SamplerParams {
     float current_max_loss;
     const nbvh_tree_cut_data *tree_cut;
     unsigned long long *counters;
+    // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes each, capacity = batch)
+    void *items;
+    uint32_t *item_count;
 };
 
 cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter, int num_sms, cudaStream_t stream);
