@@ -264,6 +264,11 @@ enum {
     NBVH_CNT_T_EXHAUST_INV,
     NBVH_CNT_T_END,
     NBVH_CNT_T_CTA_SUM,
+    /* development builds (-DNBVH_PHASE_TIMING=1) only, zero otherwise: SM cycles k_neural's tiles spent in the walk / tile barrier /
+     * encode / MLP phases while the queue had entries, the same four during the drain, and the drain's tile iterations */
+    NBVH_CNT_PH_WALK, NBVH_CNT_PH_SYNC, NBVH_CNT_PH_ENCODE, NBVH_CNT_PH_MLP,
+    NBVH_CNT_PH_WALK_D, NBVH_CNT_PH_SYNC_D, NBVH_CNT_PH_ENCODE_D, NBVH_CNT_PH_MLP_D,
+    NBVH_CNT_ITERS_DRAIN,
     NBVH_CNT_COUNT
 };
 

@@ -12,7 +12,8 @@ CONST_RENDERER, CONST_MODULE, CONST_PT_OUTPUT, CONST_PATH, CONST_SCENE, CONST_CA
     CONST_NETWORK, CONST_OPTIMIZER = range(9)
 
 COUNTER_NAMES = ["rays", "queries", "nbvh_steps", "blas_steps", "tri_tests", "tile_iterations", "queued_rays",
-                 "nbvh_steps_neural", "t_start_inv", "t_exhaust_inv", "t_end", "t_cta_sum"]
+                 "nbvh_steps_neural", "t_start_inv", "t_exhaust_inv", "t_end", "t_cta_sum",
+                 "ph_walk", "ph_sync", "ph_encode", "ph_mlp", "ph_walk_d", "ph_sync_d", "ph_encode_d", "ph_mlp_d", "iters_drain"]
 
 
 class RendererConstants(C.Structure):

@@ -269,6 +269,8 @@ struct nbvh_ctx {
     TreeCutResult *d_tc_result = nullptr;
     bool tree_cut_ready = false;
     uint32_t tree_cut_max_depth = 0;
+    float *d_node_keep = nullptr;    // per-node survival probability of the sampler's roulette (grow-only)
+    uint32_t node_keep_capacity = 0;
     void *d_sampler_items = nullptr; // two-pass sample generator: 48-byte items handed from k_sample_walk to k_sample_targets (grow-only)
     uint32_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
@@ -623,6 +625,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     cudaFree(ctx->d_sampler_items);
+    cudaFree(ctx->d_node_keep);
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
@@ -1421,6 +1424,15 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
             CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_items, (size_t)batch_size * 48u));
             ctx->sampler_item_capacity = batch_size;
         }
+        if (ctx->node_keep_capacity < ctx->nbvh_nodes) {
+            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(ctx->d_node_keep);
+            ctx->d_node_keep = nullptr, ctx->node_keep_capacity = 0;
+            const uint32_t cap = ctx->nbvh_capacity > ctx->nbvh_nodes ? ctx->nbvh_capacity : ctx->nbvh_nodes;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_node_keep, (size_t)cap * sizeof(float)));
+            ctx->node_keep_capacity = cap;
+        }
+        sp.node_keep  = ctx->d_node_keep;
         sp.items      = ctx->d_sampler_items;
         sp.item_count = ctx->d_next_chunk ? ctx->d_next_chunk + 7 : nullptr;
     }

@@ -23,6 +23,11 @@ enum Counter {
     CNT_T_EXHAUST_INV,
     CNT_T_END,
     CNT_T_CTA_SUM,
+    // k_neural phase clocks (NBVH_PHASE_TIMING builds only; SM cycles summed over tiles): walk / tile barrier / encode / MLP while the
+    // queue still has entries, then the same four during the drain, and the tile iterations of the drain
+    CNT_PH_WALK, CNT_PH_SYNC, CNT_PH_ENCODE, CNT_PH_MLP,
+    CNT_PH_WALK_D, CNT_PH_SYNC_D, CNT_PH_ENCODE_D, CNT_PH_MLP_D,
+    CNT_ITERS_DRAIN,
     CNT_COUNT
 };
 

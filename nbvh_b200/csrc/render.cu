@@ -36,6 +36,9 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #ifndef NBVH_COOP_ENCODE
 #define NBVH_COOP_ENCODE 1 // warp-cooperative hash-grid gathers (render_common.cuh: encode_rows_coop); 0 = one row per lane
 #endif
+#ifndef NBVH_PHASE_TIMING
+#define NBVH_PHASE_TIMING 0 // development builds: per-phase SM-cycle sums of k_neural (tools/perf_r2.py prints them)
+#endif
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
@@ -245,7 +248,15 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         atomicMax(p.counters + CNT_T_START_INV, ~t_cta0);
     }
 
+#if NBVH_PHASE_TIMING
+    unsigned long long ph[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    uint32_t iters_drain = 0u;
+#endif
     for (;;) {
+#if NBVH_PHASE_TIMING
+        const long long pt0 = clock64();
+        const uint32_t pdr  = exhausted ? 4u : 0u;
+#endif
         // ---------------- walk phase: every lane works until it owns a pending interval (or the queue is drained)
         for (int round = 0; round < kWalkRounds; ++round) {
             uint32_t need_mask = __ballot_sync(0xFFFFFFFFu, !s.have_ray);
@@ -315,6 +326,9 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
             if (exhausted && !__any_sync(0xFFFFFFFFu, s.have_ray && !s.have_query))
                 break;
         }
+#if NBVH_PHASE_TIMING
+        const long long pt1 = clock64();
+#endif
         // ---------------- tile-wide agreement: anything to infer?  anything left at all?
         {
             const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
@@ -333,6 +347,9 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 continue;
         }
         // ---------------- segment encoding + hash grid -> A tile (a8, a9)
+#if NBVH_PHASE_TIMING
+        const long long pt2 = clock64();
+#endif
 #if NBVH_COOP_ENCODE
         {
             float eo[3] = {0.f, 0.f, 0.f}, ei[3] = {0.f, 0.f, 0.f};
@@ -358,10 +375,21 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         encode_row_to_tile(nc, t.a_tile, row, pts, row_valid);
 #endif
         fence_proxy_async_smem();
+#if NBVH_PHASE_TIMING
+        const long long pt3 = clock64();
+#endif
         // ---------------- MLP on tensor cores (a10), decode + closest-hit update (a11)
         float y[8];
         mlp_tile_forward(nc, t, row, y);
         ++cnt_iters;
+#if NBVH_PHASE_TIMING
+        {
+            const long long pt4 = clock64();
+            ph[pdr + 0] += (unsigned long long)(pt1 - pt0), ph[pdr + 1] += (unsigned long long)(pt2 - pt1);
+            ph[pdr + 2] += (unsigned long long)(pt3 - pt2), ph[pdr + 3] += (unsigned long long)(pt4 - pt3);
+            iters_drain += pdr ? 1u : 0u;
+        }
+#endif
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
@@ -379,6 +407,13 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     warp_add_counter(p.counters, CNT_NBVH_STEPS_NEURAL, cnt_nbvh);
     if (row == 0 && p.counters && cnt_iters)
         atomicAdd(p.counters + CNT_TILE_ITERS, (unsigned long long)cnt_iters);
+#if NBVH_PHASE_TIMING
+    if (row == 0 && p.counters) {
+        for (int k = 0; k < 8; ++k)
+            atomicAdd(p.counters + CNT_PH_WALK + k, ph[k]);
+        atomicAdd(p.counters + CNT_ITERS_DRAIN, (unsigned long long)iters_drain);
+    }
+#endif
     __syncthreads();
     if (threadIdx.x == 0 && p.counters) {
         const unsigned long long t1 = global_timer_ns();

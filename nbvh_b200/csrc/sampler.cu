@@ -256,6 +256,162 @@ struct SampleItem {
 
 constexpr uint32_t kRefillThreshold = 8u; // idle lanes that trigger a refill
 constexpr uint32_t kRestartVote     = 3u; // lanes waiting for a new origin that trigger the restart block
+constexpr uint32_t kCoopLanes       = 8u; // live slots per warp at or below which the drained warp retries cooperatively
+
+// scale * keep of node_survives() for every tree-cut node, once per generation (the roulette then costs one load per found leaf)
+__global__ void __launch_bounds__(256)
+k_node_keep(const __grid_constant__ SamplerParams p, uint32_t n_nodes)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes)
+        return;
+    const nbvh_tree_cut_data nd = p.tree_cut[i];
+    float est = -FLT_MAX;
+    if (nd.samples != 0u) {
+        const float ia = __uint2float_rn(nd.iter_alive);
+        est = __fdiv_rn(nd.loss, __fmul_rn(ia, __fsqrt_rn(__fdiv_rn(__uint2float_rn(nd.samples), ia))));
+    }
+    float keep = fmaxf(p.min_rr_survival_prob, __fdiv_rn(est, p.current_max_loss));
+    if (!(est <= p.current_max_loss))
+        keep = 1.f;
+    p.node_keep[i] = __fmul_rn(p.survival_probability_scale, keep);
+}
+
+// lcg_randomf's generator advanced by n draws: x -> a x + c composed n times (binary powers of the affine map)
+__device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n)
+{
+    uint32_t A = 1664525u, C = 1013904223u, acc_a = 1u, acc_c = 0u;
+    while (n) {
+        if (n & 1u) {
+            acc_a = acc_a * A;
+            acc_c = acc_c * A + C;
+        }
+        C = C * (A + 1u);
+        A = A * A;
+        n >>= 1;
+    }
+    return acc_a * state + acc_c;
+}
+
+// The retry walk of one ray as a per-node state machine.  The stack carries the raw slab result of every pushed (far) child.
+struct CutWalk {
+    uint32_t st_idx[kNeuralStackSize];
+    float st_cmax[kNeuralStackSize], st_cmin[kNeuralStackSize];
+    int nss;
+    Node node; // only the tags a / b are maintained after the root
+    uint32_t node_idx;
+    float cmax, cmin;
+    bool have_raw;
+};
+
+__device__ __forceinline__ void cut_walk_start(const NbvhConst &bc, CutWalk &w)
+{
+    w.nss      = 0; // the root is the current node (the reference pops it from the stack [0])
+    w.node_idx = 0u;
+    w.node     = load_node(bc.nodes, 0u);
+    w.have_raw = false;
+}
+
+__device__ __forceinline__ bool cut_walk_pop(const NbvhConst &bc, CutWalk &w)
+{
+    if (w.nss == 0)
+        return false;
+    --w.nss;
+    w.node_idx = w.st_idx[w.nss], w.cmax = w.st_cmax[w.nss], w.cmin = w.st_cmin[w.nss];
+    // only the tags are needed: the box was tested when the node was pushed
+    w.node.a   = __float_as_uint(__ldg(reinterpret_cast<const float *>(bc.nodes + 2u * w.node_idx) + 3));
+    w.node.b   = __float_as_uint(__ldg(reinterpret_cast<const float *>(bc.nodes + 2u * w.node_idx + 1u) + 3));
+    w.have_raw = true;
+    return true;
+}
+
+// one node visit; returns WALK_FOUND (leaf interval in w.cmax / w.cmin, node w.node_idx), WALK_EXHAUSTED or WALK_CONTINUE
+__device__ __forceinline__ WalkResult cut_walk_step(const NbvhConst &bc, const Ray &ray, CutWalk &w, uint32_t &steps)
+{
+    const bool is_leaf = (w.node.a > 0u && w.node.a <= bc.leaf_lod_max);
+    if (is_leaf || w.node.b == kNoNeuralChild) {
+        if (!w.have_raw) { // only a root that is a leaf itself arrives here without its slab result
+            dilate_node(w.node, bc.dilation);
+            slab_raw(w.node, ray, w.cmax, w.cmin);
+        }
+        // cur_maxt = FLT_MAX: the reference's `cmax < ray.maxt` only rejects cmax = +inf / NaN
+        if (w.cmax <= w.cmin && (w.cmax < FLT_MAX) && ((w.cmax < 0.f) ? (w.cmin > bc.maxt_eps) : (w.cmax > bc.mint_eps)))
+            return WALK_FOUND;
+        return cut_walk_pop(bc, w) ? WALK_CONTINUE : WALK_EXHAUSTED;
+    }
+    ++steps;
+    uint32_t c1 = w.node.b, c2 = w.node.b + 1u;
+    Node n1 = load_node(bc.nodes, c1), n2 = load_node(bc.nodes, c2);
+    dilate_node(n1, bc.dilation);
+    dilate_node(n2, bc.dilation);
+    float cmax1, cmin1, cmax2, cmin2;
+    slab_raw(n1, ray, cmax1, cmin1);
+    slab_raw(n2, ray, cmax2, cmin2);
+    const float e1 = gmax(-FLT_MAX, cmax1), x1 = gmin(FLT_MAX, cmin1);
+    const float e2 = gmax(-FLT_MAX, cmax2), x2 = gmin(FLT_MAX, cmin2);
+    float m1 = (e1 <= x1) ? e1 : FLT_MAX;
+    float m2 = (e2 <= x2) ? e2 : FLT_MAX;
+    const bool swap = m1 > m2;
+    if (swap) {
+        const float t = m1;
+        m1 = m2, m2 = t;
+        const uint32_t ti = c1;
+        c1 = c2, c2 = ti;
+    }
+    if (m1 == FLT_MAX)
+        return cut_walk_pop(bc, w) ? WALK_CONTINUE : WALK_EXHAUSTED;
+    w.node_idx = c1;
+    w.node.a   = swap ? n2.a : n1.a;
+    w.node.b   = swap ? n2.b : n1.b;
+    w.cmax     = swap ? cmax2 : cmax1;
+    w.cmin     = swap ? cmin2 : cmin1;
+    w.have_raw = true;
+    if (m2 != FLT_MAX) {
+        w.st_idx[w.nss] = c2, w.st_cmax[w.nss] = swap ? cmax1 : cmax2, w.st_cmin[w.nss] = swap ? cmin1 : cmin2;
+        ++w.nss;
+        if (w.nss >= kNeuralStackSize)
+            return WALK_EXHAUSTED; // reference: printf("Out of bound stack!") and the walk returns "no intersection"
+    }
+    return WALK_CONTINUE;
+}
+
+// sample a new origin in the scaled scene box (three draws; the direction of the slot is kept)
+__device__ __forceinline__ void draw_origin(const SamplerParams &p, float off, uint32_t &rng, Ray &ray)
+{
+    const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
+    const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
+                lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
+    ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
+    ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
+    ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
+}
+
+// A found leaf: node id of the slot, node-survival roulette (one draw), and -- for survivors -- the item of the target pass,
+// appended with one atomic per warp.  Must be called by the whole warp.
+__device__ __forceinline__ void emit_found(const SamplerParams &p, uint32_t lane, bool found, uint32_t slot, const CutWalk &w, uint32_t rng,
+                                           const Ray &ray)
+{
+    bool keep = false;
+    if (found) {
+        p.sampled_node_indices[slot] = w.node_idx;
+        // rejected: the slot keeps its previous contents (reference quirk, SURVEY a17)
+        keep = !p.training_node_survival || !(__ldg(p.node_keep + w.node_idx) < lcg_randomf(rng));
+    }
+    const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
+    if (keep_mask == 0u)
+        return;
+    uint32_t base = 0u;
+    const uint32_t leader = (uint32_t)__ffs(keep_mask) - 1u;
+    if (lane == leader)
+        base = atomicAdd(p.item_count, (uint32_t)__popc(keep_mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (keep) {
+        uint4 *it = reinterpret_cast<uint4 *>(p.items) + 3u * (size_t)(base + (uint32_t)__popc(keep_mask & ((1u << lane) - 1u)));
+        it[0] = make_uint4(slot, w.node_idx, rng, __float_as_uint(ray.ox));
+        it[1] = make_uint4(__float_as_uint(ray.oy), __float_as_uint(ray.oz), __float_as_uint(ray.dx), __float_as_uint(ray.dy));
+        it[2] = make_uint4(__float_as_uint(ray.dz), __float_as_uint(w.cmax), __float_as_uint(w.cmin), 0u);
+    }
+}
 
 __global__ void __launch_bounds__(128)
 k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ slot_counter)
@@ -263,19 +419,13 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t total = (uint32_t)p.sub_batch_size;
     NbvhConst bc = p.nbvh;
-    // stack of far children with their raw slab results (thread-private)
-    uint32_t st_idx[kNeuralStackSize];
-    float st_cmax[kNeuralStackSize], st_cmin[kNeuralStackSize];
-    int nss = 0;
+    CutWalk w;
+    w.nss = 0, w.node_idx = 0u, w.cmax = w.cmin = 0.f, w.have_raw = false;
+    w.node.mnx = w.node.mny = w.node.mnz = w.node.mxx = w.node.mxy = w.node.mxz = 0.f, w.node.a = w.node.b = 0u;
     Ray ray;
     ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
     ray_prepare(ray, false);
-    Node node;
-    node.mnx = node.mny = node.mnz = node.mxx = node.mxy = node.mxz = 0.f, node.a = node.b = 0u;
-    uint32_t node_idx = 0u;
-    float cmax = 0.f, cmin = 0.f;
-    bool have_raw = false;
-    uint32_t rng = 0u, slot = 0u;
+    uint32_t rng = 0u, rng0 = 0u, slot = 0u, n_origins = 0u;
     bool have_slot = false, walking = false, exhausted = false;
     uint32_t cnt_nbvh = 0;
     const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
@@ -304,117 +454,103 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
                     const uint32_t lod = p.current_learned_lod + min((uint32_t)__fmul_rn(lcg_randomf(rng), __uint2float_rn(n_lods)), n_lods - 1u);
                     bc.leaf_lod_max = 2u + lod;
                     bc.dilation     = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
+                    rng0 = rng, n_origins = 0u; // origin k of the slot uses draws 3k+1 .. 3k+3 after rng0
                     have_slot = true, walking = false;
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, have_slot))
+        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
+        if (live_mask == 0u)
             break; // nothing in flight and the counter is exhausted
+        if (exhausted && (uint32_t)__popc(live_mask) <= kCoopLanes)
+            break; // drained warp: the few slots left are finished cooperatively below
         // ---------------- new origin for lanes whose walk ended without a leaf (voted: the block costs the whole warp)
         {
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, have_slot && !walking);
             const uint32_t busy = __ballot_sync(0xFFFFFFFFu, have_slot && walking);
             if (need && ((uint32_t)__popc(need) >= kRestartVote || busy == 0u || (uint32_t)__popc(need) * 4u >= (uint32_t)__popc(busy))) {
                 if (have_slot && !walking) {
-                    const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
-                    const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
-                                lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
-                    ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
-                    ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
-                    ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
-                    nss      = 0; // the root is the current node (the reference pops it from the stack [0])
-                    node_idx = 0u;
-                    node     = load_node(bc.nodes, 0u);
-                    have_raw = false;
-                    walking  = true;
+                    draw_origin(p, off, rng, ray);
+                    ++n_origins;
+                    cut_walk_start(bc, w);
+                    walking = true;
                 }
             }
         }
         // ---------------- one node visit for every walking lane
         bool found = false;
         if (have_slot && walking) {
-            const bool is_leaf = (node.a > 0u && node.a <= bc.leaf_lod_max);
-            if (is_leaf || node.b == kNoNeuralChild) {
-                if (!have_raw) { // only a root that is a leaf itself arrives here without its slab result
-                    dilate_node(node, bc.dilation);
-                    slab_raw(node, ray, cmax, cmin);
-                }
-                if (cmax <= cmin) {
-                    // cur_maxt = FLT_MAX: the reference's `cmax < ray.maxt` only rejects cmax = +inf / NaN
-                    const bool valid = (cmax < FLT_MAX) && ((cmax < 0.f) ? (cmin > bc.maxt_eps) : (cmax > bc.mint_eps));
-                    found = valid;
-                }
-                if (!found) {
-                    if (nss == 0) {
-                        walking = false;
-                    } else {
-                        --nss;
-                        node_idx = st_idx[nss], cmax = st_cmax[nss], cmin = st_cmin[nss];
-                        const float4 lo = __ldg(bc.nodes + 2u * node_idx), hi = __ldg(bc.nodes + 2u * node_idx + 1u);
-                        node.a = __float_as_uint(lo.w), node.b = __float_as_uint(hi.w); // only the tags are needed: the box was tested at push time
-                        have_raw = true;
-                    }
-                }
-            } else {
-                ++cnt_nbvh;
-                uint32_t c1 = node.b, c2 = node.b + 1u;
-                Node n1 = load_node(bc.nodes, c1), n2 = load_node(bc.nodes, c2);
-                dilate_node(n1, bc.dilation);
-                dilate_node(n2, bc.dilation);
-                float cmax1, cmin1, cmax2, cmin2;
-                slab_raw(n1, ray, cmax1, cmin1);
-                slab_raw(n2, ray, cmax2, cmin2);
-                const float e1 = gmax(-FLT_MAX, cmax1), x1 = gmin(FLT_MAX, cmin1);
-                const float e2 = gmax(-FLT_MAX, cmax2), x2 = gmin(FLT_MAX, cmin2);
-                float m1 = (e1 <= x1) ? e1 : FLT_MAX;
-                float m2 = (e2 <= x2) ? e2 : FLT_MAX;
-                const bool swap = m1 > m2;
-                if (swap) {
-                    const float t = m1;
-                    m1 = m2, m2 = t;
-                    const uint32_t ti = c1;
-                    c1 = c2, c2 = ti;
-                }
-                if (m1 == FLT_MAX) {
-                    if (nss == 0) {
-                        walking = false;
-                    } else {
-                        --nss;
-                        node_idx = st_idx[nss], cmax = st_cmax[nss], cmin = st_cmin[nss];
-                        const float4 lo = __ldg(bc.nodes + 2u * node_idx), hi = __ldg(bc.nodes + 2u * node_idx + 1u);
-                        node.a = __float_as_uint(lo.w), node.b = __float_as_uint(hi.w);
-                        have_raw = true;
-                    }
-                } else {
-                    node_idx = c1;
-                    node.a   = swap ? n2.a : n1.a;
-                    node.b   = swap ? n2.b : n1.b;
-                    cmax     = swap ? cmax2 : cmax1;
-                    cmin     = swap ? cmin2 : cmin1;
-                    have_raw = true;
-                    if (m2 != FLT_MAX) {
-                        st_idx[nss] = c2, st_cmax[nss] = swap ? cmax1 : cmax2, st_cmin[nss] = swap ? cmin1 : cmin2;
-                        ++nss;
-                        if (nss >= kNeuralStackSize)
-                            walking = false; // reference: printf("Out of bound stack!") and the walk returns "no intersection"
-                    }
-                }
+            const WalkResult r = cut_walk_step(bc, ray, w, cnt_nbvh);
+            found   = r == WALK_FOUND;
+            walking = r == WALK_CONTINUE;
+        }
+        // ---------------- lanes that met a leaf hand their slot over and become idle
+        if (__any_sync(0xFFFFFFFFu, found)) {
+            emit_found(p, lane, found, slot, w, rng, ray);
+            if (found)
+                have_slot = false;
+        }
+    }
+
+    // ---------------- cooperative tail.  The number of origins a slot needs is heavy-tailed (a fixed direction may rarely meet a
+    // leaf: hundreds of origins), and with the slot counter exhausted nothing refills the other lanes -- the longest slot would
+    // set the kernel time.  The origins of one slot are independent draws at known offsets of its LCG stream (lcg_skip), so the
+    // warp splits into groups of G lanes per live slot and walks G consecutive origins of that slot at once; the lowest origin
+    // that meets a leaf is the one the sequential loop would have stopped at (same draws, same walk -> same item).
+    for (;;) {
+        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
+        const uint32_t n_live    = (uint32_t)__popc(live_mask);
+        if (n_live == 0u)
+            break;
+        const uint32_t G     = n_live == 1u ? 32u : n_live == 2u ? 16u : n_live <= 4u ? 8u : 4u; // lanes per slot (n_live <= 8)
+        const uint32_t group = lane / G, g = lane % G;
+        const bool has       = group < n_live;
+        const uint32_t owner = has ? (uint32_t)__fns(live_mask, 0u, group + 1u) : 0u;
+        // the owner's in-flight origin (if any) is redone: origin index of the group's first lane
+        const uint32_t first = n_origins - ((have_slot && walking) ? 1u : 0u);
+        const uint32_t o_slot  = __shfl_sync(0xFFFFFFFFu, slot, owner);
+        const uint32_t o_rng0  = __shfl_sync(0xFFFFFFFFu, rng0, owner);
+        const uint32_t o_first = __shfl_sync(0xFFFFFFFFu, first, owner);
+        Ray cray;
+        cray.dx = __shfl_sync(0xFFFFFFFFu, ray.dx, owner), cray.dy = __shfl_sync(0xFFFFFFFFu, ray.dy, owner);
+        cray.dz = __shfl_sync(0xFFFFFFFFu, ray.dz, owner);
+        cray.ix = __shfl_sync(0xFFFFFFFFu, ray.ix, owner), cray.iy = __shfl_sync(0xFFFFFFFFu, ray.iy, owner);
+        cray.iz = __shfl_sync(0xFFFFFFFFu, ray.iz, owner);
+        cray.fast = __shfl_sync(0xFFFFFFFFu, ray.fast, owner);
+        cray.ox = cray.oy = cray.oz = 0.f;
+        NbvhConst cbc    = p.nbvh;
+        cbc.leaf_lod_max = __shfl_sync(0xFFFFFFFFu, bc.leaf_lod_max, owner);
+        cbc.dilation     = __shfl_sync(0xFFFFFFFFu, bc.dilation, owner);
+        uint32_t crng    = lcg_skip(o_rng0, 3u * (o_first + g));
+        bool cwalking = false, cfound = false;
+        CutWalk &cw = w; // the owner's own walk state is dead: its in-flight origin is redone by the group
+        if (has) {
+            draw_origin(p, off, crng, cray);
+            cut_walk_start(cbc, cw);
+            cwalking = true;
+        }
+        while (__any_sync(0xFFFFFFFFu, cwalking)) {
+            if (cwalking) {
+                const WalkResult r = cut_walk_step(cbc, cray, cw, cnt_nbvh);
+                cfound   = r == WALK_FOUND;
+                cwalking = r == WALK_CONTINUE;
             }
         }
-        // ---------------- lanes that met a leaf append their item (one atomic per warp) and become idle
-        const uint32_t found_mask = __ballot_sync(0xFFFFFFFFu, found);
-        if (found_mask) {
-            uint32_t base = 0u;
-            const uint32_t leader = (uint32_t)__ffs(found_mask) - 1u;
-            if (lane == leader)
-                base = atomicAdd(p.item_count, (uint32_t)__popc(found_mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (found) {
-                uint4 *it = reinterpret_cast<uint4 *>(p.items) + 3u * (size_t)(base + (uint32_t)__popc(found_mask & ((1u << lane) - 1u)));
-                it[0] = make_uint4(slot, node_idx, rng, __float_as_uint(ray.ox));
-                it[1] = make_uint4(__float_as_uint(ray.oy), __float_as_uint(ray.oz), __float_as_uint(ray.dx), __float_as_uint(ray.dy));
-                it[2] = make_uint4(__float_as_uint(ray.dz), __float_as_uint(cmax), __float_as_uint(cmin), 0u);
-                have_slot = false, walking = false;
+        // the lowest origin of every group that met a leaf wins
+        const uint32_t found_mask = __ballot_sync(0xFFFFFFFFu, cfound);
+        const uint32_t gmask      = G == 32u ? 0xFFFFFFFFu : (((1u << G) - 1u) << (group * G));
+        const uint32_t gfound     = found_mask & gmask;
+        const bool winner         = cfound && ((uint32_t)__ffs(gfound) - 1u == lane);
+        emit_found(p, lane, winner, o_slot, cw, crng, cray);
+        // owners: slot done, or G more origins consumed
+        if (have_slot) {
+            const uint32_t my_group = (uint32_t)__popc(live_mask & ((1u << lane) - 1u));
+            const uint32_t mine     = G == 32u ? found_mask : ((found_mask >> (my_group * G)) & ((1u << G) - 1u));
+            if (mine) {
+                have_slot = false;
+            } else {
+                n_origins = first + G;
+                walking   = false;
             }
         }
     }
@@ -430,19 +566,13 @@ k_sample_targets(const __grid_constant__ SamplerParams p)
     if (i < n) {
         const uint4 *it = reinterpret_cast<const uint4 *>(p.items) + 3u * (size_t)i;
         const uint4 a = it[0], b = it[1], c = it[2];
-        const uint32_t slot = a.x, node_idx = a.y;
-        uint32_t rng        = a.z;
-        p.sampled_node_indices[slot] = node_idx;
-        // rejected: the slot keeps its previous contents (reference quirk, SURVEY a17)
-        if (!p.training_node_survival || node_survives(p, node_idx, rng)) {
-            Ray ray;
-            ray.ox = __uint_as_float(a.w), ray.oy = __uint_as_float(b.x), ray.oz = __uint_as_float(b.y);
-            ray.dx = __uint_as_float(b.z), ray.dy = __uint_as_float(b.w), ray.dz = __uint_as_float(c.x);
-            ray_prepare_guarded(ray);
-            ItsData its;
-            emit_slot(p, slot, ray, __uint_as_float(c.y), __uint_as_float(c.z), false, its, cnt_blas, cnt_tri);
-            ++cnt_written;
-        }
+        Ray ray;
+        ray.ox = __uint_as_float(a.w), ray.oy = __uint_as_float(b.x), ray.oz = __uint_as_float(b.y);
+        ray.dx = __uint_as_float(b.z), ray.dy = __uint_as_float(b.w), ray.dz = __uint_as_float(c.x);
+        ray_prepare_guarded(ray);
+        ItsData its;
+        emit_slot(p, a.x, ray, __uint_as_float(c.y), __uint_as_float(c.z), false, its, cnt_blas, cnt_tri);
+        ++cnt_written;
     }
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
     warp_add_counter(p.counters, CNT_TRI_TESTS, cnt_tri);
@@ -453,7 +583,8 @@ cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter
 {
     if (p.sub_batch_size <= 0)
         return cudaSuccess;
-    if (p.n_sub_batch == 1 && slot_counter && p.items && p.item_count && !getenv("NBVH_SAMPLER_SIMPLE")) {
+    if (p.n_sub_batch == 1 && slot_counter && p.items && p.item_count && (p.node_keep || !p.training_node_survival) &&
+        !getenv("NBVH_SAMPLER_SIMPLE")) {
         cudaError_t e = cudaMemsetAsync(slot_counter, 0, sizeof(uint32_t), stream);
         if (e != cudaSuccess)
             return e;
@@ -463,13 +594,15 @@ cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0);
         if (e != cudaSuccess)
             return e;
-        // every lane should own several slots (the retry count is heavy-tailed): small batches get a smaller grid
-        const uint32_t want = ((uint32_t)p.sub_batch_size + 4u * 128u - 1u) / (4u * 128u);
+        if (p.training_node_survival) {
+            k_node_keep<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p, p.nbvh.num_nodes);
+            if ((e = cudaGetLastError()) != cudaSuccess)
+                return e;
+        }
+        const uint32_t want = ((uint32_t)p.sub_batch_size + 127u) / 128u;
         uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1));
         if (grid > want)
             grid = want;
-        if (grid < (uint32_t)num_sms) // ... but never fewer CTAs than SMs (one warp per scheduler at least)
-            grid = min((uint32_t)num_sms, ((uint32_t)p.sub_batch_size + 127u) / 128u);
         k_sample_walk<<<grid, 128, 0, stream>>>(p, slot_counter);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;

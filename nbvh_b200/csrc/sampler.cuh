@@ -30,6 +30,7 @@ struct SamplerParams {
     // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes each, capacity = batch)
     void *items;
     uint32_t *item_count;
+    float *node_keep; // survival_probability_scale * keep per tree-cut node (k_node_keep), capacity = tree-cut nodes
 };
 
 cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter, int num_sms, cudaStream_t stream);

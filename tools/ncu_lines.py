@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Per-source-line instruction / stall-sample totals from an .ncu-rep (needs -lineinfo and --import-source on).
-usage: ncu_lines.py <rep> <kernel regex> [top N]"""
+usage: ncu_lines.py <rep> <kernel regex> [top N] [--by-samples]"""
 import csv
 import io
 import subprocess
@@ -9,7 +9,7 @@ import sys
 
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 40
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kern],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -30,7 +30,10 @@ def main():
             tot_inst += inst
             tot_samp += samp
     print("total warp instructions %d, stall samples %d" % (tot_inst, tot_samp))
-    out.sort(reverse=True)
+    if "--by-samples" in sys.argv:
+        out.sort(key=lambda t: t[1], reverse=True)
+    else:
+        out.sort(reverse=True)
     for inst, samp, f, ln, src in out[:top]:
         print("%6.2f%% inst %6.2f%% samp  %s:%d  %s" % (100.0 * inst / max(tot_inst, 1), 100.0 * samp / max(tot_samp, 1), f, ln, src))
 

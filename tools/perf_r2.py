@@ -65,6 +65,11 @@ def main():
     c = mod.counters()
     t0, tx, t1 = M - c["t_start_inv"], M - c["t_exhaust_inv"], c["t_end"]
     out["k_neural_timeline_us"] = {"span": (t1 - t0) / 1e3, "queue_dry_at": (tx - t0) / 1e3, "mean_cta_lifetime": c["t_cta_sum"] / 296 / 1e3}
+    if c.get("ph_mlp", 0) or c.get("ph_mlp_d", 0):
+        it_s, it_d = max(c["tile_iterations"] - c["iters_drain"], 1), max(c["iters_drain"], 1)
+        out["k_neural_phase_cycles_per_iteration"] = {
+            "steady": {k: c["ph_" + k] / it_s for k in ("walk", "sync", "encode", "mlp")}, "steady_iterations": it_s,
+            "drain": {k: c["ph_" + k + "_d"] / it_d for k in ("walk", "sync", "encode", "mlp")}, "drain_iterations": it_d}
     ms8 = timeit(lambda: mod.neural_render_samples(0, 8), iters=5, warmup=2)
     out["frame_8spl"] = {"ms_per_launch": ms8, "ms_per_sample_frame": ms8 / 8}
     print(json.dumps(out), flush=True)
