@@ -24,9 +24,10 @@ def main():
             try:
                 inst = int(r[7])
                 samp = int(r[4])
+                tinst = int(r[8])
             except ValueError:
                 continue
-            out.append((inst, samp, fname, int(r[0]), r[1].strip()[:110]))
+            out.append((inst, samp, fname, int(r[0]), r[1].strip()[:100], tinst))
             tot_inst += inst
             tot_samp += samp
     print("total warp instructions %d, stall samples %d" % (tot_inst, tot_samp))
@@ -34,8 +35,9 @@ def main():
         out.sort(key=lambda t: t[1], reverse=True)
     else:
         out.sort(reverse=True)
-    for inst, samp, f, ln, src in out[:top]:
-        print("%6.2f%% inst %6.2f%% samp  %s:%d  %s" % (100.0 * inst / max(tot_inst, 1), 100.0 * samp / max(tot_samp, 1), f, ln, src))
+    for inst, samp, f, ln, src, tinst in out[:top]:
+        print("%6.2f%% inst %6.2f%% samp %5.1f lanes  %s:%d  %s" % (100.0 * inst / max(tot_inst, 1), 100.0 * samp / max(tot_samp, 1),
+                                                                    tinst / max(inst, 1), f, ln, src))
 
 
 if __name__ == "__main__":
