@@ -405,6 +405,27 @@ int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint
 int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch,
                                    uint32_t global_batch, float *per_sample_loss, float *loss_sum_dev, void *stream);
 float *nbvh_gradients(nbvh_ctx *ctx);
+
+/* ---- data-parallel optimisation inside the library (NCCL over NVLink / NVSwitch; SURVEY.md 8b "nbvh_allreduce_setup(ctx, ncclComm_t)") --
+ * The reference is single-GPU (tcnn::Trainer steps on its own batch, ext/tiny-cuda-nn trainer.h:163-190).  With a communicator attached,
+ * nbvh_training_forward_backward -- and nbvh_training_step -- sum the gradients of all ranks before returning control to `stream`: the MLP
+ * matrices in one allreduce that overlaps the hash-grid backward kernels, the grid table and the loss scalar in a second one, both on the
+ * library's communication stream.  Every rank passes its own share of the batch and the GLOBAL batch size; the optimiser step is
+ * replicated and leaves bit-identical parameters on all ranks.  NCCL is bound with dlopen("libnccl.so.2") (NBVH_NCCL_LIB overrides the
+ * name): single-GPU hosts need no NCCL at all.
+ *   nbvh_allreduce_setup            attaches the CALLER's communicator (an ncclComm_t, passed as void *; stays the caller's)
+ *   nbvh_nccl_unique_id             == ncclGetUniqueId: 128 bytes that rank 0 hands to the other ranks (any channel: MPI, a file, a socket)
+ *   nbvh_allreduce_setup_unique_id  == ncclCommInitRank on the context's device; the library owns the communicator
+ *   nbvh_allreduce_buffer           sums a device array over the ranks in place on `stream` (tree-cut statistics, loss sums, image tiles)
+ *   nbvh_data_parallel_world        -> number of ranks (1 without a communicator), optionally this context's rank */
+#define NBVH_NCCL_UNIQUE_ID_BYTES 128
+enum { NBVH_DTYPE_F32 = 0, NBVH_DTYPE_U32 = 1, NBVH_DTYPE_I32 = 2, NBVH_DTYPE_U64 = 3, NBVH_DTYPE_F64 = 4 };
+int nbvh_nccl_unique_id(void *id_out_128_bytes);
+int nbvh_allreduce_setup(nbvh_ctx *ctx, void *nccl_comm);
+int nbvh_allreduce_setup_unique_id(nbvh_ctx *ctx, const void *unique_id_128_bytes, int rank, int world);
+int nbvh_allreduce_teardown(nbvh_ctx *ctx);
+int nbvh_allreduce_buffer(nbvh_ctx *ctx, void *device_ptr, uint64_t count, int dtype, void *stream);
+int nbvh_data_parallel_world(const nbvh_ctx *ctx, int *rank_out);
 /* Lets the host own the fp32 gradient vector (n_params floats of device memory; NULL -> back to the internal buffer), so
  * the process that drives NCCL can allreduce it in place without a copy. */
 /* == NeuralBVHModule::optimisation_data_generation -> generate_and_fill_bvh_output_reference (path_module.cu:20-52,

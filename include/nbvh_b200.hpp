@@ -9,8 +9,11 @@
 
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <fstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace nbvh_b200 {
@@ -107,6 +110,54 @@ public:
         check(nbvh_training_step(m_ctx, in, target, batch, per_sample_loss, &loss, stream));
         return loss;
     }
+    // ---- data-parallel optimisation inside the library (nbvh_allreduce_*): one process per GPU, gradients and tree-cut statistics
+    //      summed by NCCL; the host's launcher only carries the 128-byte unique id from rank 0 to the other ranks
+    static std::vector<uint8_t> nccl_unique_id()
+    {
+        std::vector<uint8_t> id(NBVH_NCCL_UNIQUE_ID_BYTES);
+        if (nbvh_nccl_unique_id(id.data()) != NBVH_OK)
+            throw std::runtime_error("nbvh_b200: NCCL is not loadable (libnccl.so.2)");
+        return id;
+    }
+    void setup_data_parallel(const std::vector<uint8_t> &unique_id, int rank, int world)
+    {
+        if (unique_id.size() != NBVH_NCCL_UNIQUE_ID_BYTES)
+            throw std::runtime_error("nbvh_b200: bad NCCL unique id");
+        check(nbvh_allreduce_setup_unique_id(m_ctx, unique_id.data(), rank, world));
+    }
+    void setup_data_parallel(void *nccl_comm) { check(nbvh_allreduce_setup(m_ctx, nccl_comm)); } // the caller's ncclComm_t
+    int data_parallel_world(int *rank = nullptr) const { return nbvh_data_parallel_world(m_ctx, rank); }
+    void allreduce(void *device_ptr, uint64_t count, int dtype, void *stream = nullptr)
+    {
+        check(nbvh_allreduce_buffer(m_ctx, device_ptr, count, dtype, stream));
+    }
+    // this rank's share of the batch, the GLOBAL batch size; on return (stream order) the gradients and *loss_sum_dev are global sums
+    void training_forward_backward(const float *in, const float *target, uint32_t batch, uint32_t global_batch, float *per_sample_loss,
+                                   float *loss_sum_dev, void *stream = nullptr)
+    {
+        check(nbvh_training_forward_backward(m_ctx, in, target, batch, global_batch, per_sample_loss, loss_sum_dev, stream));
+    }
+    void optimizer_step(void *stream = nullptr) { check(nbvh_optimizer_step(m_ctx, stream)); }
+    // per-rank statistics -> allreduce -> the same deterministic decisions and splits on every rank; scratch: one float and one
+    // uint32 per tree-cut node (capacity: the node count the schedule will reach)
+    float tree_cut_step_data_parallel(const float *per_sample_loss, const uint32_t *sampled_node_indices, uint32_t batch, uint32_t num_splits,
+                                      float *loss_scratch, uint32_t *samples_scratch, uint32_t *n_split = nullptr, void *stream = nullptr)
+    {
+        const uint32_t n = nbvh_neural_bvh_num_nodes(m_ctx);
+        check(nbvh_tree_cut_accumulate(m_ctx, per_sample_loss, 16, network_output_dims(), sampled_node_indices, batch, loss_scratch,
+                                       samples_scratch, stream));
+        allreduce(loss_scratch, n, NBVH_DTYPE_F32, stream);
+        allreduce(samples_scratch, n, NBVH_DTYPE_U32, stream);
+        float max_loss = 0.f;
+        check(nbvh_tree_cut_decide(m_ctx, loss_scratch, samples_scratch, num_splits, &max_loss, n_split, stream));
+        return max_loss;
+    }
+    bool tree_cut_assign_lod() // == assign_lod_to_current_neural_leaf_nodes; true when every LoD has been assigned
+    {
+        int done = 0;
+        check(nbvh_tree_cut_assign_lod(m_ctx, &done));
+        return done != 0;
+    }
     void tree_cut_init(uint32_t min_depth) { check(nbvh_tree_cut_init(m_ctx, min_depth)); }
     const nbvh_tree_cut_data *tree_cut_data() const { return nbvh_tree_cut_data_device(m_ctx); }
     float tree_cut_step(const float *per_sample_loss, const uint32_t *sampled_node_indices, uint32_t batch, uint32_t num_splits,
@@ -178,6 +229,32 @@ private:
     }
     nbvh_ctx *m_ctx = nullptr;
 };
+
+// Carries the NCCL unique id from rank 0 to the other ranks of a one-process-per-GPU launch through a file (any launcher that sets
+// RANK / WORLD_SIZE works: `python -m torch.distributed.run --no-python`, mpirun with a wrapper, a shell loop).  Rank 0 writes
+// `path` atomically (rename), the others poll for it.
+inline std::vector<uint8_t> exchange_unique_id_via_file(const std::string &path, int rank, int timeout_s = 120)
+{
+    if (rank == 0) {
+        const std::vector<uint8_t> id = NeuralPathModule::nccl_unique_id();
+        const std::string tmp         = path + ".tmp";
+        std::ofstream(tmp, std::ios::binary).write(reinterpret_cast<const char *>(id.data()), (std::streamsize)id.size());
+        if (std::rename(tmp.c_str(), path.c_str()) != 0)
+            throw std::runtime_error("nbvh_b200: cannot publish the NCCL unique id at " + path);
+        return id;
+    }
+    for (int waited_ms = 0; waited_ms < timeout_s * 1000; waited_ms += 20) {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        if (f && (size_t)f.tellg() == NBVH_NCCL_UNIQUE_ID_BYTES) {
+            std::vector<uint8_t> id(NBVH_NCCL_UNIQUE_ID_BYTES);
+            f.seekg(0);
+            f.read(reinterpret_cast<char *>(id.data()), (std::streamsize)id.size());
+            return id;
+        }
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+    throw std::runtime_error("nbvh_b200: timed out waiting for the NCCL unique id at " + path);
+}
 
 // == FrameTimer (include/utils/frame_timer.h): start_frame / end_frame / write_to_file with the reference's CSV layout
 class FrameTimer {

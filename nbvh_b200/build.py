@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnbvh_b200.so")
-SOURCES = ["context.cu", "config.cu", "io.cu", "abi_render.cu", "abi_train.cu", "kernels.cu", "render.cu", "path.cu", "treecut.cu", "build.cu", "training.cu", "sampler.cu", "flip.cu"]
+SOURCES = ["context.cu", "config.cu", "io.cu", "abi_render.cu", "abi_train.cu", "comm.cu", "kernels.cu", "render.cu", "path.cu", "treecut.cu", "build.cu", "training.cu", "sampler.cu", "flip.cu"]
 HEADERS = ["host_context.hpp", "device_core.cuh", "mlp_tile.cuh", "kernels.cuh", "render_common.cuh", "sampler.cuh", "shading.cuh", "path.cuh", "treecut.cuh", "json_min.hpp", "../../include/nbvh_b200.h"]
 
 NVCC_FLAGS = [

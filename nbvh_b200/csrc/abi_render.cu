@@ -6,6 +6,7 @@ extern "C" {
 
 int nbvh_query(nbvh_ctx *ctx, const float *in, float *out, uint32_t n, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!in || !out)))
         return NBVH_ERR_INVALID_ARG;
     int rc = check_ready(ctx, false, false, true);
@@ -22,6 +23,7 @@ int nbvh_query(nbvh_ctx *ctx, const float *in, float *out, uint32_t n, void *str
 int nbvh_trace_intervals(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t max_intervals, uint32_t *counts,
                          uint32_t *node_idx, float *mint, float *maxt, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!o || !d || !counts || !node_idx || !mint || !maxt)))
         return NBVH_ERR_INVALID_ARG;
     int rc = check_ready(ctx, false, true, false);
@@ -39,6 +41,7 @@ int nbvh_trace_intervals(nbvh_ctx *ctx, const float *o, const float *d, uint32_t
 int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const float *d, const float *maxt, uint32_t n,
                         float *t, float *u, float *v, uint32_t *prim, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!o || !d || !t || !u || !v || !prim)))
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->scene_set || blas_idx >= ctx->scene.n_blas)
@@ -72,6 +75,7 @@ extern "C" {
 int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx, int sample_offset, float *o, float *d,
                 void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!o || !d)))
         return NBVH_ERR_INVALID_ARG;
     if (ctx->fb_w == 0)
@@ -83,6 +87,7 @@ int nbvh_raygen(nbvh_ctx *ctx, uint32_t first_pixel, uint32_t n, int sample_idx,
 int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n, float *out,
                          void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!o || !d || !mint || !maxt || !out)))
         return NBVH_ERR_INVALID_ARG;
     if (ctx->module_const.input_network_dims != 3u * ctx->module_const.input_segment_points)
@@ -93,6 +98,7 @@ int nbvh_encode_segments(nbvh_ctx *ctx, const float *o, const float *d, const fl
 
 int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !pixels_host || !tex_out || w == 0 || h == 0)
         return NBVH_ERR_INVALID_ARG;
     cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
@@ -122,6 +128,7 @@ int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_
 
 int nbvh_create_envmap_rgba32f(nbvh_ctx *ctx, const float *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !pixels_host || !tex_out || w == 0 || h == 0)
         return NBVH_ERR_INVALID_ARG;
     // CudaBackend::load_envmap (cuda_backend.cpp:474-500): float4 array, linear filter, normalized coordinates, clamp
@@ -146,6 +153,7 @@ int nbvh_create_envmap_rgba32f(nbvh_ctx *ctx, const float *pixels_host, uint32_t
 
 int nbvh_set_envmap(nbvh_ctx *ctx, uint64_t envmap_texture)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     ctx->envmap = (cudaTextureObject_t)envmap_texture;
@@ -154,6 +162,7 @@ int nbvh_set_envmap(nbvh_ctx *ctx, uint64_t envmap_texture)
 
 int nbvh_destroy_textures(nbvh_ctx *ctx)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     for (auto &t : ctx->own_textures) {
@@ -171,12 +180,14 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
 int nbvh_render(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
                 void *stream)
 {
+    DeviceGuard device_guard(ctx);
     return render_impl(ctx, accumulated_spp, sample_offset, first_pixel, pixel_count, 1u, 0u, stream);
 }
 
 int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t shard_index, uint32_t shard_count,
                             void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || shard_count == 0 || shard_index >= shard_count)
         return NBVH_ERR_INVALID_ARG;
     const uint32_t total = ctx->fb_w * ctx->fb_h;
@@ -196,6 +207,7 @@ int nbvh_render_interleaved(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
 int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint32_t sample_offset, uint32_t shard_index,
                         uint32_t shard_count, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || shard_count == 0 || shard_index >= shard_count || n_spp == 0)
         return NBVH_ERR_INVALID_ARG;
     if (n_spp == 1u)
@@ -376,6 +388,7 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
 
 int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, uint32_t ray_depth, nbvh_hit_record *hits, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (n && (!o || !d || !hits)) || ray_depth == 0)
         return NBVH_ERR_INVALID_ARG;
     int rc = check_ready(ctx, true, true, true);
@@ -433,6 +446,7 @@ int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, u
 int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, int mode, int write_error_image,
                      float *mean_error_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !reference_rgba32f || !mean_error_host || mode < 3 || mode > 6 || accumulated_spp == 0)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->accum)
@@ -456,6 +470,7 @@ int nbvh_image_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t acc
 int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indices, uint32_t n_tris, nbvh_node32 *nodes_out,
                     uint64_t *prim_indices_out, uint32_t *max_depth_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !vertices || !indices || !nodes_out || !prim_indices_out || n_tris == 0 || n_tris > (1u << 30))
         return NBVH_ERR_INVALID_ARG;
     cudaStream_t st    = (cudaStream_t)stream;
@@ -487,6 +502,7 @@ int nbvh_build_blas(nbvh_ctx *ctx, const float *vertices, const uint32_t *indice
 int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                      uint8_t *ldr_host, nbvh_hit_record *hits_host)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     if (camera_host)
@@ -514,6 +530,7 @@ int nbvh_render_host(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_of
 int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, const nbvh_camera_params *camera_host,
                             uint8_t *ldr_host, uint32_t slot)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !ldr_host || slot >= (uint32_t)kPipeSlots)
         return NBVH_ERR_INVALID_ARG;
     const size_t n = (size_t)ctx->fb_w * ctx->fb_h;
@@ -569,6 +586,7 @@ int nbvh_render_host_submit(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sa
 
 int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || slot >= (uint32_t)kPipeSlots || !ctx->pipe_copied[slot])
         return NBVH_ERR_INVALID_ARG;
     CU_TRY(ctx, cudaEventSynchronize(ctx->pipe_copied[slot]));
@@ -584,6 +602,7 @@ int nbvh_render_host_wait(nbvh_ctx *ctx, uint32_t slot)
 int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint32_t num_meshes, const uint32_t *neural_meshes_host,
                     uint32_t n_neural, nbvh_node32 *tlas_nodes_out, uint32_t *blas_indices_out, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !mesh_bvhs_device || !tlas_nodes_out || !blas_indices_out || num_meshes == 0 || (n_neural && !neural_meshes_host))
         return NBVH_ERR_INVALID_ARG;
     if (num_meshes > (uint32_t)kMaxBlas)
@@ -606,6 +625,7 @@ int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint3
 int nbvh_flip_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accumulated_spp, float ppd, float *error_map_out,
                     float *mean_flip_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !reference_rgba32f || !mean_flip_host || accumulated_spp == 0)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->accum)
@@ -618,6 +638,7 @@ int nbvh_flip_error(nbvh_ctx *ctx, const float *reference_rgba32f, uint32_t accu
 int nbvh_flip_images(nbvh_ctx *ctx, const float *reference_rgba32f, const float *test_rgba32f, float test_divisor, uint32_t width,
                      uint32_t height, float ppd, float *error_map_out, float *mean_flip_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !reference_rgba32f || !test_rgba32f || !mean_flip_host || width == 0 || height == 0 || !(test_divisor > 0.f))
         return NBVH_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;

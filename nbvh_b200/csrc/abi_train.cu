@@ -8,6 +8,7 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
                                       uint32_t *sampled_node_indices, float current_max_loss, const nbvh_tree_cut_data *tree_cut_data,
                                       float *inputs, float *targets, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !sampled_node_indices || !inputs || !targets)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->d_nbvh || !ctx->scene_set)
@@ -180,12 +181,16 @@ int upload_tree_cut_state(nbvh_ctx *ctx, const std::vector<nbvh_node32> &nodes, 
 // neural mesh's BLAS at `min_depth` (neural_bvh_min_depth; 0 = the root alone), node numbering as the reference's recursion
 int nbvh_tree_cut_init(nbvh_ctx *ctx, uint32_t min_depth)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     std::vector<nbvh_node32> blas;
     int rc = neural_blas_nodes_host(ctx, blas);
     if (rc != NBVH_OK)
         return rc;
+    // build_and_upload_neural_bvh resets the level unconditionally (neural_bvh_renderer_accel.cpp:520): learning starts at the
+    // coarsest LoD whatever the config file said (34 of the 35 shipped Chess configs omit the key)
+    ctx->bvh_const.current_learned_lod = 6; // NUM_BVH_LODS - 1
     const uint32_t first_lod = (uint32_t)ctx->bvh_const.current_learned_lod;
     std::vector<nbvh_node32> nodes(1);
     std::vector<nbvh_tree_cut_data> cut(1);
@@ -226,6 +231,7 @@ int nbvh_tree_cut_init(nbvh_ctx *ctx, uint32_t min_depth)
 // learning state for the tree-cut already in the context (loaded from a .nbvh file): node map, depths, zeroed statistics
 int nbvh_tree_cut_attach(nbvh_ctx *ctx)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !ctx->d_nbvh)
         return ctx ? fail(ctx, NBVH_ERR_STATE, "no neural BVH set") : NBVH_ERR_INVALID_ARG;
     std::vector<nbvh_node32> blas;
@@ -238,8 +244,12 @@ int nbvh_tree_cut_attach(nbvh_ctx *ctx)
     std::vector<nbvh_tree_cut_data> cut(n, nbvh_tree_cut_data{0.f, 1u, 0u, 0u});
     std::vector<uint32_t> map(n, 0u);
     uint32_t max_depth = 0;
-    struct Item { uint32_t bvh, neural, depth; };
-    std::vector<Item> stack{{0u, 0u, 0u}};
+    // traverse_neural_bvh_and_update_states also tracks the LoD the walk is in: an interior node tagged as a leaf of levels
+    // t-2 .. current moves the walk to level t-3 (accel.cpp:126-134); the coarsest level any childless node is reached at
+    // decides where learning resumes (accel.cpp:496-501)
+    int min_traversed_lod = 6; // NUM_BVH_LODS - 1
+    struct Item { uint32_t bvh, neural, depth; int lod; };
+    std::vector<Item> stack{{0u, 0u, 0u, 6}};
     while (!stack.empty()) {
         const Item it = stack.back();
         stack.pop_back();
@@ -248,13 +258,24 @@ int nbvh_tree_cut_attach(nbvh_ctx *ctx)
         map[it.neural]       = it.bvh;
         cut[it.neural].depth = it.depth;
         max_depth            = it.depth > max_depth ? it.depth : max_depth;
-        if (nodes[it.neural].left_or_prim_offset == 0xFFFFFFFFu)
+        if (nodes[it.neural].left_or_prim_offset == 0xFFFFFFFFu) {
+            min_traversed_lod = it.lod < min_traversed_lod ? it.lod : min_traversed_lod;
             continue;
+        }
         if (blas[it.bvh].prim_count_or_left > 0u)
             return fail(ctx, NBVH_ERR_STATE, "the tree-cut is not a cut of the neural mesh's BLAS");
-        stack.push_back({blas[it.bvh].left_or_prim_offset + 1u, nodes[it.neural].left_or_prim_offset + 1u, it.depth + 1u});
-        stack.push_back({blas[it.bvh].left_or_prim_offset, nodes[it.neural].left_or_prim_offset, it.depth + 1u});
+        int lod = it.lod;
+        const uint32_t tag = nodes[it.neural].prim_count_or_left;
+        for (int l = it.lod; l >= 0; --l)
+            if (tag > 0u && tag <= 2u + (uint32_t)l) // is_leaf_at_lod(l)
+                --lod;
+        if (lod < 0)
+            return fail(ctx, NBVH_ERR_STATE, "the tree-cut nests more LoD levels than NUM_BVH_LODS");
+        stack.push_back({blas[it.bvh].left_or_prim_offset + 1u, nodes[it.neural].left_or_prim_offset + 1u, it.depth + 1u, lod});
+        stack.push_back({blas[it.bvh].left_or_prim_offset, nodes[it.neural].left_or_prim_offset, it.depth + 1u, lod});
     }
+    const int nl = ctx->bvh_const.num_lods_learned;
+    ctx->bvh_const.current_learned_lod = (min_traversed_lod == 7 - nl && nl > 1) ? 0 : min_traversed_lod;
     return upload_tree_cut_state(ctx, nodes, cut, map, max_depth);
 }
 
@@ -264,6 +285,7 @@ const nbvh_node32 *nbvh_neural_bvh_device(const nbvh_ctx *ctx) { return ctx ? re
 // test / restore hook: overwrite the per-node statistics (the reference restores them when it reloads a training state)
 int nbvh_set_tree_cut_host(nbvh_ctx *ctx, const nbvh_tree_cut_data *cut_host, uint32_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !cut_host || !ctx->tree_cut_ready || n != ctx->nbvh_nodes)
         return NBVH_ERR_INVALID_ARG;
     CU_TRY(ctx, cudaMemcpy(ctx->d_tree_cut, cut_host, (size_t)n * sizeof(nbvh_tree_cut_data), cudaMemcpyHostToDevice));
@@ -272,6 +294,7 @@ int nbvh_set_tree_cut_host(nbvh_ctx *ctx, const nbvh_tree_cut_data *cut_host, ui
 
 int nbvh_get_tree_cut_host(const nbvh_ctx *ctx, nbvh_tree_cut_data *cut_host, uint32_t *node_map_host, uint32_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !ctx->tree_cut_ready || n > ctx->nbvh_nodes)
         return NBVH_ERR_INVALID_ARG;
     if (cut_host && cudaMemcpy(cut_host, ctx->d_tree_cut, (size_t)n * sizeof(nbvh_tree_cut_data), cudaMemcpyDeviceToHost) != cudaSuccess)
@@ -327,6 +350,7 @@ static int tree_cut_reserve(nbvh_ctx *ctx, uint32_t num_splits, cudaStream_t st)
 int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
                        uint32_t batch, uint32_t num_splits, float *max_node_loss_host, uint32_t *n_split_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !per_sample_loss || !sampled_node_indices || dims > stride)
         return NBVH_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -343,6 +367,7 @@ int nbvh_tree_cut_step(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t str
 int nbvh_tree_cut_accumulate(nbvh_ctx *ctx, const float *per_sample_loss, uint32_t stride, uint32_t dims, const uint32_t *sampled_node_indices,
                              uint32_t batch, float *loss_delta, uint32_t *samples_delta, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !per_sample_loss || !sampled_node_indices || !loss_delta || !samples_delta || dims > stride)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->tree_cut_ready)
@@ -355,6 +380,7 @@ int nbvh_tree_cut_accumulate(nbvh_ctx *ctx, const float *per_sample_loss, uint32
 int nbvh_tree_cut_decide(nbvh_ctx *ctx, const float *loss_delta, const uint32_t *samples_delta, uint32_t num_splits, float *max_node_loss_host,
                          uint32_t *n_split_host, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !loss_delta || !samples_delta)
         return NBVH_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -369,6 +395,7 @@ int nbvh_tree_cut_decide(nbvh_ctx *ctx, const float *loss_delta, const uint32_t 
 // being learned and moves on to the next finer level.  Returns the new current_learned_lod through the constant block.
 int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !ctx->d_nbvh)
         return NBVH_ERR_INVALID_ARG;
     const int level = ctx->bvh_const.current_learned_lod;
@@ -432,6 +459,7 @@ static int ensure_training_state(nbvh_ctx *ctx, uint32_t batch, cudaStream_t st)
 int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch, uint32_t global_batch,
                                    float *per_sample_loss, float *loss_sum_dev, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !in || !target || batch == 0)
         return ctx ? fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_training_forward_backward: null input or empty batch") : NBVH_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -465,8 +493,18 @@ int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *
     tp.loss.normal_linear = pc.output_normal_linear_activation, tp.loss.depth_linear = pc.output_depth_linear_activation;
     tp.loss.albedo_linear = pc.output_albedo_linear_activation, tp.loss.vis_masking = pc.visibility_masking_loss;
     CU_TRY(ctx, launch_train_mlp(nc, tp, ctx->num_sms, st));
+    // data parallel (comm.cu): the MLP gradients (and the loss scalar) are summed across the ranks while the grid backward runs,
+    // the grid table afterwards; `st` resumes when both buckets are reduced, so the caller (and Adam) only ever see global sums
+    if ((rc = dp_allreduce_bucket(ctx, 0, ctx->d_grads, ctx->n_mlp_params, st)) != NBVH_OK)
+        return rc;
     CU_TRY(ctx, launch_grid_backward(nc, in, ctx->d_dfeat, batch, ctx->module_const.input_network_dims, ctx->d_grads + ctx->n_mlp_params,
                                      ctx->num_sms, st));
+    if ((rc = dp_allreduce_bucket(ctx, 1, ctx->d_grads + ctx->n_mlp_params, ctx->n_params - ctx->n_mlp_params, st)) != NBVH_OK)
+        return rc;
+    if (ctx->nccl_comm && ctx->dp_world > 1 && (rc = nbvh_allreduce_buffer(ctx, loss_dev, 1, NBVH_DTYPE_F32, ctx->comm_stream)) != NBVH_OK)
+        return rc;
+    if ((rc = dp_join(ctx, st)) != NBVH_OK)
+        return rc;
     kt.stop();
     return NBVH_OK;
 }
@@ -475,6 +513,7 @@ float *nbvh_gradients(nbvh_ctx *ctx) { return ctx ? ctx->d_grads : nullptr; }
 
 int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     if (grads) {
@@ -489,6 +528,7 @@ int nbvh_set_gradient_buffer(nbvh_ctx *ctx, float *grads)
 
 int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->train_state_valid || !ctx->d_grads)
@@ -520,6 +560,7 @@ int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream)
 int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint32_t batch, float *per_sample_loss, float *loss_host,
                        void *stream)
 {
+    DeviceGuard device_guard(ctx);
     int rc = nbvh_training_forward_backward(ctx, in, target, batch, batch, per_sample_loss, nullptr, stream);
     if (rc != NBVH_OK)
         return rc;

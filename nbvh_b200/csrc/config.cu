@@ -153,8 +153,41 @@ nbvh_camera_params camera_from_matrix(const float *m, float yfov_rad, uint32_t w
 extern "C" {
 
 // ---- configuration ---------------------------------------------------------------------------------
-int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
+} // extern "C"
+
+// The constant blocks and descriptions a config file decides: a file that is rejected half-way (unknown loss, unsupported network
+// shape, malformed camera) must leave all of them -- and with them the allocated parameter layout -- as they were.
+namespace {
+struct ConfigSnapshot {
+    nbvh_scene_constants scene_const;
+    nbvh_renderer_constants bvh_const;
+    nbvh_module_constants module_const;
+    nbvh_pt_output_constants pt_const;
+    nbvh_path_constants path_const;
+    nbvh_network_desc net_desc;
+    nbvh_optimizer_desc opt_desc;
+    std::string dir_enc_type;
+    int max_depth;
+    uint32_t training_step;
+    explicit ConfigSnapshot(const nbvh_ctx *c)
+        : scene_const(c->scene_const), bvh_const(c->bvh_const), module_const(c->module_const), pt_const(c->pt_const),
+          path_const(c->path_const), net_desc(c->net_desc), opt_desc(c->opt_desc), dir_enc_type(c->dir_enc_type), max_depth(c->max_depth),
+          training_step(c->training_step)
+    {
+    }
+    void restore(nbvh_ctx *c) const
+    {
+        c->scene_const = scene_const, c->bvh_const = bvh_const, c->module_const = module_const, c->pt_const = pt_const;
+        c->path_const = path_const, c->net_desc = net_desc, c->opt_desc = opt_desc, c->dir_enc_type = dir_enc_type;
+        c->max_depth = max_depth, c->training_step = training_step;
+    }
+};
+int load_config_body(nbvh_ctx *ctx, const Json &root);
+} // namespace
+
+extern "C" int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !json_text)
         return NBVH_ERR_INVALID_ARG;
     Json root;
@@ -163,6 +196,21 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
     } catch (const std::exception &e) {
         return fail(ctx, NBVH_ERR_PARSE, e.what());
     }
+    const ConfigSnapshot snapshot(ctx);
+    int rc;
+    try {
+        rc = load_config_body(ctx, root);
+    } catch (const std::exception &e) {
+        rc = fail(ctx, NBVH_ERR_PARSE, e.what());
+    }
+    if (rc != NBVH_OK)
+        snapshot.restore(ctx);
+    return rc;
+}
+
+namespace {
+int load_config_body(nbvh_ctx *ctx, const Json &root)
+{
     const Json &scene = root.object("cuda_scene");
     const Json &rend  = root.object("neural_bvh_renderer");
     const Json &mod   = rend.object("neural_module");
@@ -339,6 +387,15 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
     }
     ctx->dir_enc_type  = mod.object("direction_encoding").value("type", std::string("Identity"));
     ctx->training_step = (uint32_t)rend.value("training_step", 0.0);
+    // everything that can be refused is checked before the first side effect (framebuffer, camera, parameter layout)
+    {
+        const std::string err = layout_error(ctx);
+        if (!err.empty())
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
+        if (const Json *m = scene.object("camera").find("matrix"))
+            if (m->size() != 16)
+                return fail(ctx, NBVH_ERR_PARSE, "camera.matrix must have 16 entries");
+    }
     // framebuffer size + camera
     if (const Json *fb = scene.find("fb_size")) {
         if (fb->size() == 2) {
@@ -362,6 +419,9 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
     ctx->dilated_with = -1.f;
     return rebuild_layout(ctx);
 }
+} // namespace
+
+extern "C" {
 
 // == the module-owned part of NeuralBVHRenderer::save_config (neural_bvh_renderer_init.cu:406-509): cuda_scene {fb_size, camera,
 // scene_constants} and neural_bvh_renderer {neural_module {max_depth, pt_output_constants, path_module_constants, bvh_module_constants,
@@ -371,6 +431,7 @@ int nbvh_load_config_json(nbvh_ctx *ctx, const char *json_text)
 // and the needed size (including the NUL) into *needed.
 int nbvh_save_config_json(const nbvh_ctx *ctx, char *out, size_t capacity, size_t *needed)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || (!out && capacity))
         return NBVH_ERR_INVALID_ARG;
     std::string s;

@@ -32,25 +32,36 @@ float grid_scale(uint32_t level, float log2_pls, uint32_t base) { return exp2f((
 
 // Parameter layout: FullyFusedMLP matrices (row-major W[out][in]) then the grid levels
 // (network_with_input_encoding.h:115-122, fully_fused_mlp.cu:636-678, grid.h:692-723)
-int rebuild_layout(nbvh_ctx *ctx)
+// What the kernels cannot run, as a message (empty = fine).  Pure check: callers validate BEFORE they commit a new description.
+std::string layout_error(const nbvh_ctx *ctx)
 {
     const nbvh_network_desc &d = ctx->net_desc;
     if (d.n_features_per_level != 4)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only n_features_per_level == 4 is implemented");
+        return "only n_features_per_level == 4 is implemented";
     if (d.n_neurons != kNeurons)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only n_neurons == 64 is implemented");
+        return "only n_neurons == 64 is implemented";
     if (d.n_levels < 1 || d.n_levels > kMaxLevels || d.n_hidden_layers < 1 || d.n_hidden_layers + 1 > kMaxLayers)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "n_levels / n_hidden_layers out of range");
+        return "n_levels / n_hidden_layers out of range";
     if (ctx->module_const.input_segment_direction_dim != 0)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "direction encoding input is not implemented");
+        return "direction encoding input is not implemented";
     const uint32_t n_points = ctx->module_const.input_segment_points;
     if (n_points < 1 || n_points > 4)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "1..4 segment points supported");
-    ctx->in_k = n_points * d.n_levels * d.n_features_per_level;
-    if (ctx->in_k % 16u != 0u || ctx->in_k > kMaxInputK)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "encoded input width must be a multiple of 16 and <= 128");
+        return "1..4 segment points supported";
+    const uint32_t in_k = n_points * d.n_levels * d.n_features_per_level;
+    if (in_k % 16u != 0u || in_k > kMaxInputK)
+        return "encoded input width must be a multiple of 16 and <= 128";
     if (ctx->pt_const.output_network_dims > 8)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "output_network_dims > 8");
+        return "output_network_dims > 8";
+    return std::string();
+}
+
+int rebuild_layout(nbvh_ctx *ctx)
+{
+    const nbvh_network_desc &d = ctx->net_desc;
+    const std::string err      = layout_error(ctx);
+    if (!err.empty())
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
+    ctx->in_k = ctx->module_const.input_segment_points * d.n_levels * d.n_features_per_level;
     ctx->n_layers = (uint32_t)d.n_hidden_layers + 1u;
 
     ctx->level_offsets.assign(d.n_levels + 1, 0);
@@ -292,6 +303,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaFree(ctx->ldr);
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
+    dp_release(ctx);
     cudaFree(ctx->d_sampler_items);
     cudaFree(ctx->d_node_keep);
     cudaFree(ctx->d_queue);
@@ -356,18 +368,26 @@ static void *block_ptr(nbvh_ctx *ctx, int which, size_t &bytes)
 
 int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t bytes)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !pod_host)
         return NBVH_ERR_INVALID_ARG;
     size_t want = 0;
     void *dst   = block_ptr(ctx, which, want);
     if (!dst || bytes != want)
         return fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_set_constants: unknown block or size mismatch");
-    if (which == NBVH_CONST_NETWORK || which == NBVH_CONST_MODULE) {
-        // these change the parameter layout: compare first so per-frame re-uploads stay cheap
+    if (which == NBVH_CONST_NETWORK || which == NBVH_CONST_MODULE || which == NBVH_CONST_PT_OUTPUT) {
+        // these decide the parameter layout / the output width: compare first so per-frame re-uploads stay cheap, and validate the
+        // new description before committing it -- a rejected block leaves the context (parameters included) untouched
         if (memcmp(dst, pod_host, bytes) == 0)
             return NBVH_OK;
+        std::vector<uint8_t> old((const uint8_t *)dst, (const uint8_t *)dst + bytes);
         memcpy(dst, pod_host, bytes);
-        return rebuild_layout(ctx);
+        const std::string err = layout_error(ctx);
+        if (!err.empty()) {
+            memcpy(dst, old.data(), bytes);
+            return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
+        }
+        return which == NBVH_CONST_PT_OUTPUT ? NBVH_OK : rebuild_layout(ctx);
     }
     memcpy(dst, pod_host, bytes);
     if (which == NBVH_CONST_SCENE_BBOX)
@@ -377,6 +397,7 @@ int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t by
 
 int nbvh_get_constants(const nbvh_ctx *ctx, int which, void *pod_host, size_t bytes)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !pod_host)
         return NBVH_ERR_INVALID_ARG;
     size_t want     = 0;
@@ -389,6 +410,7 @@ int nbvh_get_constants(const nbvh_ctx *ctx, int which, void *pod_host, size_t by
 
 int nbvh_set_camera(nbvh_ctx *ctx, const float matrix16_host[16], float yfov_rad)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !matrix16_host)
         return NBVH_ERR_INVALID_ARG;
     if (ctx->fb_w == 0 || ctx->fb_h == 0)
@@ -402,6 +424,7 @@ int nbvh_set_camera(nbvh_ctx *ctx, const float matrix16_host[16], float yfov_rad
 int nbvh_get_max_depth(const nbvh_ctx *ctx) { return ctx ? ctx->max_depth : NBVH_ERR_INVALID_ARG; }
 int nbvh_set_max_depth(nbvh_ctx *ctx, int max_depth)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || max_depth < 1)
         return NBVH_ERR_INVALID_ARG;
     ctx->max_depth = max_depth;
@@ -411,6 +434,7 @@ int nbvh_set_max_depth(nbvh_ctx *ctx, int max_depth)
 // ---- scene, tree-cut, weights --------------------------------------------------------------------------
 int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !s)
         return NBVH_ERR_INVALID_ARG;
     if (s->num_meshes > (uint32_t)kMaxBlas)
@@ -480,6 +504,7 @@ extern "C" {
 
 int nbvh_set_neural_bvh(nbvh_ctx *ctx, const nbvh_node32 *nodes, uint32_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !nodes)
         return NBVH_ERR_INVALID_ARG;
     return adopt_nbvh(ctx, nodes, n, cudaMemcpyDeviceToDevice);
@@ -489,6 +514,7 @@ uint32_t nbvh_neural_bvh_num_nodes(const nbvh_ctx *ctx) { return ctx ? ctx->nbvh
 
 int nbvh_get_neural_bvh_host(const nbvh_ctx *ctx, nbvh_node32 *nodes_host, uint32_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !nodes_host || n != ctx->nbvh_nodes || !ctx->d_nbvh)
         return NBVH_ERR_INVALID_ARG;
     return cudaMemcpy(nodes_host, ctx->d_nbvh, (size_t)n * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? NBVH_OK : NBVH_ERR_CUDA;
@@ -498,6 +524,7 @@ uint64_t nbvh_n_params(const nbvh_ctx *ctx) { return ctx ? ctx->n_params : 0; }
 
 int nbvh_load_params_host(nbvh_ctx *ctx, const uint16_t *fp16, uint64_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !fp16)
         return NBVH_ERR_INVALID_ARG;
     if (n != ctx->n_params)
@@ -515,6 +542,7 @@ int nbvh_load_params_host(nbvh_ctx *ctx, const uint16_t *fp16, uint64_t n)
 
 int nbvh_get_params_host(const nbvh_ctx *ctx, uint16_t *fp16, uint64_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !fp16 || n != ctx->n_params)
         return NBVH_ERR_INVALID_ARG;
     return cudaMemcpy(fp16, ctx->d_params, n * sizeof(uint16_t), cudaMemcpyDeviceToHost) == cudaSuccess ? NBVH_OK : NBVH_ERR_CUDA;
@@ -524,6 +552,7 @@ int nbvh_get_params_host(const nbvh_ctx *ctx, uint16_t *fp16, uint64_t n)
 // Own splitmix64 stream (tcnn uses pcg32 seed 1337; initial weights are statistically, not bitwise, equivalent).
 int nbvh_init_params(nbvh_ctx *ctx, uint64_t seed)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     std::vector<uint16_t> p(ctx->n_params);
@@ -552,6 +581,7 @@ int nbvh_init_params(nbvh_ctx *ctx, uint64_t seed)
 // ---- inference ------------------------------------------------------------------------------------------
 int nbvh_set_framebuffer(nbvh_ctx *ctx, float *accum, uint8_t *ldr, uint32_t w, uint32_t h)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || w == 0 || h == 0)
         return NBVH_ERR_INVALID_ARG;
     if (ctx->own_accum)
@@ -583,6 +613,7 @@ int nbvh_set_framebuffer(nbvh_ctx *ctx, float *accum, uint8_t *ldr, uint32_t w, 
 
 int nbvh_set_hit_buffer(nbvh_ctx *ctx, nbvh_hit_record *hits)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     ctx->hits = hits;
@@ -591,6 +622,7 @@ int nbvh_set_hit_buffer(nbvh_ctx *ctx, nbvh_hit_record *hits)
 
 int nbvh_selftest_division(nbvh_ctx *ctx, uint64_t seed, uint64_t n_trials, uint64_t *mismatches_host)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !mismatches_host)
         return NBVH_ERR_INVALID_ARG;
     unsigned long long *d = ctx->d_counters + CNT_COUNT; // spare slot
@@ -604,6 +636,7 @@ int nbvh_selftest_division(nbvh_ctx *ctx, uint64_t seed, uint64_t n_trials, uint
 
 int nbvh_get_counters(nbvh_ctx *ctx, uint64_t *out_host, uint32_t n)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !out_host || n > CNT_COUNT)
         return NBVH_ERR_INVALID_ARG;
     CU_TRY(ctx, cudaMemcpy(out_host, ctx->d_counters, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
@@ -612,6 +645,7 @@ int nbvh_get_counters(nbvh_ctx *ctx, uint64_t *out_host, uint32_t n)
 
 int nbvh_reset_counters(nbvh_ctx *ctx)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     CU_TRY(ctx, cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * CNT_COUNT));
@@ -621,6 +655,7 @@ int nbvh_reset_counters(nbvh_ctx *ctx)
 
 int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     ctx->timing = enable != 0;
@@ -629,6 +664,7 @@ int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable)
 
 int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     if (total_ms)
@@ -640,6 +676,7 @@ int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
 
 int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     for (cudaEvent_t e : ctx->stage_ev)
@@ -656,6 +693,7 @@ int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
 
 int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_ms_total, uint32_t *frames)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx)
         return NBVH_ERR_INVALID_ARG;
     float a = 0.f, b = 0.f;

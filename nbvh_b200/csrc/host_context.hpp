@@ -126,6 +126,13 @@ struct nbvh_ctx {
     uint32_t tree_cut_max_depth = 0;
     float *d_node_keep = nullptr;    // per-node survival probability of the sampler's roulette (grow-only)
     uint32_t node_keep_capacity = 0;
+    // data-parallel optimisation (comm.cu): NCCL communicator (the caller's, or one the library created from a unique id),
+    // communication stream and the events that order the gradient buckets against the compute stream
+    void *nccl_comm = nullptr;
+    bool nccl_owned = false;
+    int dp_rank = 0, dp_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_reduced = nullptr;
     void *d_sampler_items = nullptr; // two-pass sample generator: 48-byte items handed from k_sample_walk to k_sample_targets (grow-only)
     uint32_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
@@ -185,7 +192,27 @@ struct nbvh_ctx {
 
 namespace nbvh_host {
 
+// Every entry point runs on the context's device: several contexts (one per GPU) may live in one process, and the caller's
+// current device is restored on return.
+struct DeviceGuard {
+    int prev      = -1;
+    bool switched = false;
+    explicit DeviceGuard(const nbvh_ctx *ctx)
+    {
+        if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+            switched = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched)
+            cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard &)            = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 int fail(nbvh_ctx *ctx, int code, const std::string &msg);
+std::string layout_error(const nbvh_ctx *ctx);
 int rebuild_layout(nbvh_ctx *ctx);
 int upload_weight_image(nbvh_ctx *ctx, const uint16_t *mlp_host);
 NetConst make_net_const(const nbvh_ctx *ctx);
@@ -196,6 +223,10 @@ EncodeConst make_encode_const(const nbvh_ctx *ctx);
 int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params);
 CameraConst make_camera_const(const nbvh_ctx *ctx);
 int adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKind kind);
+// comm.cu
+int dp_allreduce_bucket(nbvh_ctx *ctx, int bucket, float *ptr, size_t count, cudaStream_t st);
+int dp_join(nbvh_ctx *ctx, cudaStream_t st);
+void dp_release(nbvh_ctx *ctx);
 
 struct KernelTimer {
     nbvh_ctx *ctx;

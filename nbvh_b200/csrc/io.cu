@@ -9,6 +9,7 @@ extern "C" {
 // (/root/reference/ext/bvh/src/bvh/v2/bvh.h:133-153, node.h:119-133)
 int nbvh_load_neural_bvh_file(nbvh_ctx *ctx, const char *path)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !path)
         return NBVH_ERR_INVALID_ARG;
     std::string data;
@@ -40,6 +41,7 @@ int nbvh_load_neural_bvh_file(nbvh_ctx *ctx, const char *path)
 
 int nbvh_save_neural_bvh_file(nbvh_ctx *ctx, const char *path)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !path)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->d_nbvh)
@@ -67,6 +69,7 @@ int nbvh_save_neural_bvh_file(nbvh_ctx *ctx, const char *path)
 // (ext/tiny-cuda-nn trainer.h:275-320, gpu_memory_json.h:36-60); "float" payloads are accepted too (trainer.h:292-295)
 int nbvh_load_network_file(nbvh_ctx *ctx, const char *path)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !path)
         return NBVH_ERR_INVALID_ARG;
     std::string text;
@@ -107,6 +110,7 @@ int nbvh_load_network_file(nbvh_ctx *ctx, const char *path)
 
 int nbvh_save_network_file(nbvh_ctx *ctx, const char *path)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !path)
         return NBVH_ERR_INVALID_ARG;
     std::vector<uint16_t> half(ctx->n_params);
@@ -200,6 +204,7 @@ int nbvh_write_exr_host(const char *path, uint32_t width, uint32_t height, const
 // accumulated_spp; refuses while ema_accumulate is on, like the reference ("would just save incorrect images").
 int nbvh_save_image_exr(nbvh_ctx *ctx, const char *path, uint32_t accumulated_spp, void *stream)
 {
+    DeviceGuard device_guard(ctx);
     if (!ctx || !path || accumulated_spp == 0)
         return NBVH_ERR_INVALID_ARG;
     if (!ctx->accum)

@@ -419,7 +419,6 @@ __global__ void k_selftest_division(uint64_t seed, uint32_t iters, unsigned long
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static uint32_t g_smem_bytes = 0;
 
 cudaError_t launch_check_nodes(const float4 *nodes, uint32_t n, uint32_t *ok_dev, cudaStream_t stream)
 {
@@ -474,12 +473,11 @@ cudaError_t launch_prefetch_l2(const void *const *ptrs, const size_t *bytes, int
 
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k)
 {
-    const SmemLayout lay = smem_layout(wimg_bytes, in_k, kTilesPerCta);
-    g_smem_bytes         = lay.total;
-    cudaError_t e = cudaFuncSetAttribute(k_query, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    (void)wimg_bytes, (void)in_k;
+    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_query));
     if (e != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    return allow_max_dynamic_smem(reinterpret_cast<const void *>(k_render));
 }
 
 cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32_t n, uint32_t n_in_dims,
@@ -492,7 +490,7 @@ cudaError_t launch_query(const NetConst &nc, const float *in, float *out, uint32
     const uint32_t cap     = (uint32_t)num_sms * 2u;
     if (grid > cap)
         grid = cap;
-    k_query<<<grid, kCtaThreads, g_smem_bytes, stream>>>(nc, in, out, n, n_in_dims, counters);
+    k_query<<<grid, kCtaThreads, smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta).total, stream>>>(nc, in, out, n, n_in_dims, counters);
     return cudaGetLastError();
 }
 
@@ -550,7 +548,7 @@ cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sm
     const uint32_t needed   = (n_chunks + (kCtaThreads / 32) - 1) / (kCtaThreads / 32);
     if (grid > needed)
         grid = needed;
-    k_render<<<grid, kCtaThreads, g_smem_bytes, stream>>>(rp, nc);
+    k_render<<<grid, kCtaThreads, smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta).total, stream>>>(rp, nc);
     return cudaGetLastError();
 }
 

@@ -114,6 +114,20 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t wimg_bytes, uint32_t 
     return s;
 }
 
+// The tile kernels take their dynamic shared-memory size from the network description of EACH launch (contexts with different
+// network shapes may live in one process, on any device): the per-function limit is raised to the device's opt-in maximum once
+// per context creation, and nothing about the size is kept in process-global state.
+inline cudaError_t allow_max_dynamic_smem(const void *func)
+{
+    int dev = 0, max_optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    if ((e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+}
+
 // ---- online optimisation (training.cu)
 struct LossConst { // PathTracingOutputConstants subset read by the composite loss
     uint32_t vis_dim, depth_dim, normal_dim, albedo_dim;

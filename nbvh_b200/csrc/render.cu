@@ -424,24 +424,22 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static uint32_t g_neural_smem = 0;
-
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
 {
-    const SmemLayout lay = smem_layout(wimg_bytes, in_k, kNeuralTiles);
-    g_neural_smem        = lay.total;
-    cudaError_t e = cudaFuncSetAttribute(k_neural<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    (void)wimg_bytes, (void)in_k;
+    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<false>));
     if (e != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(k_neural<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    return allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<true>));
 }
 
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream)
 {
+    const uint32_t smem_bytes = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles).total;
     if (path_mode)
-        k_neural<true><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+        k_neural<true><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
     else
-        k_neural<false><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, g_neural_smem, stream>>>(rp, nc);
+        k_neural<false><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
     return cudaGetLastError();
 }
 

@@ -602,13 +602,10 @@ __global__ void k_half_to_float(const __half *__restrict__ src, float *__restric
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static uint32_t g_train_smem = 0;
-
 cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_layers)
 {
-    const TrainSmem lay = train_smem_layout(wimg_bytes, in_k, n_layers - 1u);
-    g_train_smem        = lay.total;
-    cudaError_t e = cudaFuncSetAttribute(k_train_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    (void)wimg_bytes, (void)in_k, (void)n_layers;
+    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_train_mlp));
     if (e != cudaSuccess)
         return e;
     return cudaFuncSetAttribute(k_grid_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -635,7 +632,7 @@ cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_
         return cudaSuccess;
     const uint32_t n_tiles = (tp.batch + kTileRows - 1u) / kTileRows;
     const uint32_t grid    = n_tiles < (uint32_t)num_sms ? n_tiles : (uint32_t)num_sms;
-    k_train_mlp<<<grid, kTileRows, g_train_smem, stream>>>(nc, tp);
+    k_train_mlp<<<grid, kTileRows, train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u).total, stream>>>(nc, tp);
     return cudaGetLastError();
 }
 

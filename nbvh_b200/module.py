@@ -478,10 +478,68 @@ class NeuralPathModule:
                                                  _ptr(sampled_node_indices), batch, int(num_splits), C.byref(mx), C.byref(ns), stream))
         return mx.value, ns.value
 
+    # ------------------------------------------------------------------ data-parallel optimisation inside the library (comm.cu)
+    def setup_data_parallel(self, rank=None, world=None, group=None):
+        """Gives the library its own NCCL communicator (nbvh_allreduce_setup_unique_id): rank 0 draws the unique id, the host's
+        launcher -- here torch.distributed, any backend -- only carries those 128 bytes to the other ranks.  From then on
+        training_forward_backward / training_step sum the gradients across the ranks themselves (two buckets on the library's
+        communication stream, the first overlapping the grid backward)."""
+        import torch.distributed as dist
+        torch = _torch()
+        from ._capi import NCCL_UNIQUE_ID_BYTES
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES)()
+        if rank == 0:
+            self._check(self._lib.nbvh_nccl_unique_id(buf))
+        if world > 1:
+            on_gpu = dist.get_backend(group) == "nccl"
+            t = torch.tensor(list(buf), dtype=torch.uint8, device=torch.device("cuda", self.device) if on_gpu else "cpu")
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            buf = (C.c_ubyte * NCCL_UNIQUE_ID_BYTES)(*t.cpu().tolist())
+        self._check(self._lib.nbvh_allreduce_setup_unique_id(self._h, buf, int(rank), int(world)))
+        return rank, world
+
+    def teardown_data_parallel(self):
+        self._check(self._lib.nbvh_allreduce_teardown(self._h))
+
+    def data_parallel_world(self):
+        r = C.c_int(0)
+        w = self._lib.nbvh_data_parallel_world(self._h, C.byref(r))
+        return r.value, w
+
+    def allreduce(self, tensor, stream=None):
+        """Sums a CUDA tensor over the library's ranks in place (no-op without a communicator)."""
+        torch = _torch()
+        from ._capi import DTYPE_F32, DTYPE_F64, DTYPE_I32, DTYPE_U32, DTYPE_U64
+        kinds = {torch.float32: DTYPE_F32, torch.int32: DTYPE_I32, torch.float64: DTYPE_F64, torch.int64: DTYPE_U64, torch.uint8: None}
+        if tensor.dtype == torch.uint8:  # bytes of disjoint tiles: summed as 32-bit words (no carries between disjoint non-zero bytes)
+            assert tensor.numel() % 4 == 0
+            self._check(self._lib.nbvh_allreduce_buffer(self._h, _ptr(tensor), tensor.numel() // 4, DTYPE_U32, stream))
+            return tensor
+        self._check(self._lib.nbvh_allreduce_buffer(self._h, _ptr(tensor), tensor.numel(), kinds[tensor.dtype], stream))
+        return tensor
+
     def tree_cut_step_data_parallel(self, per_sample_loss, sampled_node_indices, num_splits, dims=None, group=None, stream=None):
         """tree_cut_step for one process per GPU: per-rank statistics -> allreduce (NCCL) -> identical decisions and splits everywhere."""
         import torch.distributed as dist
         torch = _torch()
+        if self.data_parallel_world()[1] > 1:  # the library's own communicator
+            n = self._lib.nbvh_neural_bvh_num_nodes(self._h)
+            dev = per_sample_loss.device
+            loss_d = torch.empty(n, dtype=torch.float32, device=dev)
+            samp_d = torch.empty(n, dtype=torch.int32, device=dev)
+            batch, stride = int(per_sample_loss.shape[0]), int(per_sample_loss.shape[1])
+            self._check(self._lib.nbvh_tree_cut_accumulate(self._h, _ptr(per_sample_loss), stride,
+                                                           int(dims if dims is not None else self.network_output_dims()),
+                                                           _ptr(sampled_node_indices), batch, _ptr(loss_d), _ptr(samp_d), stream))
+            self.allreduce(loss_d, stream=stream)
+            self.allreduce(samp_d, stream=stream)
+            mx, ns = C.c_float(0.0), C.c_uint32(0)
+            self._check(self._lib.nbvh_tree_cut_decide(self._h, _ptr(loss_d), _ptr(samp_d), int(num_splits), C.byref(mx), C.byref(ns), stream))
+            return mx.value, ns.value
         n = self._lib.nbvh_neural_bvh_num_nodes(self._h)
         dev = per_sample_loss.device
         loss_d = torch.empty(n, dtype=torch.float32, device=dev)

@@ -90,8 +90,12 @@ class TreeCutLearner:
         self.log2_trav = int(log2_bvh_max_traversals)
         dev = torch.device("cuda", module.device)
         self.sampled = torch.zeros(self.batch, dtype=torch.int32, device=dev)
-        self.inputs = torch.zeros((self.batch, 9), dtype=torch.float32, device=dev)
-        self.targets = torch.zeros((self.batch, 8), dtype=torch.float32, device=dev)
+        # the sampler and the trainer stride these by the config's dims (3 * input_segment_points, output_network_dims)
+        from ._capi import CONST_MODULE
+        in_dims = int(module.get_constants(CONST_MODULE).input_network_dims)
+        out_dims = int(module.network_output_dims())
+        self.inputs = torch.zeros((self.batch, in_dims), dtype=torch.float32, device=dev)
+        self.targets = torch.zeros((self.batch, out_dims), dtype=torch.float32, device=dev)
         self.L = torch.zeros((self.batch, 16), dtype=torch.float32, device=dev)
         self.max_node_loss = 0.0
         self.step_no = 0
@@ -118,8 +122,9 @@ class TreeCutLearner:
             self.loss_sum.zero_()
             m.training_forward_backward(self.inputs, self.targets, global_batch=self.batch * self.world, per_sample_loss=self.L,
                                         loss_sum=self.loss_sum, stream=stream)
-            dist.all_reduce(self.grads)
-            dist.all_reduce(self.loss_sum)
+            if m.data_parallel_world()[1] <= 1:  # no communicator inside the library (setup_data_parallel): the host's process group sums
+                dist.all_reduce(self.grads)
+                dist.all_reduce(self.loss_sum)
             m.optimizer_step(stream=stream)
             loss = float(self.loss_sum.item())
             self.max_node_loss, n_split = m.tree_cut_step_data_parallel(self.L, self.sampled, n_splits, stream=stream)

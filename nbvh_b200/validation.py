@@ -54,8 +54,11 @@ def run_full_validation(mod, cfg, out_dir, max_training_steps=None, max_accumula
     mod.init_params(1337)
     mod.tree_cut_init(rend.get("neural_bvh_min_depth", 0))
     sched = BvhSplitScheduler.from_config(cfg)
-    sched.update_stats_and_reset(1, rend["max_training_steps"])
-    learner = TreeCutLearner(mod, sched, batch_size=rend["batch_size"], num_lods_learned=rend["bvh_constants"]["num_lods_learned"])
+    # the schedule's statistics start from the node count of the initial cut (neural_bvh_renderer_init.cu: update_stats_and_reset
+    # (m_neural_nodes_used, ...)), and the sampler runs with the config's log2_bvh_max_traversals
+    sched.update_stats_and_reset(len(mod.neural_bvh_nodes()), rend["max_training_steps"])
+    learner = TreeCutLearner(mod, sched, batch_size=rend["batch_size"], num_lods_learned=rend["bvh_constants"]["num_lods_learned"],
+                             log2_bvh_max_traversals=rend["bvh_constants"].get("log2_bvh_max_traversals", 0))
     learner.tree_cut_learning = bool(rend.get("tree_cut_learning", True))
     timer, losses = results.FrameTimer(), []
     torch.cuda.synchronize()
@@ -82,7 +85,12 @@ def run_full_validation(mod, cfg, out_dir, max_training_steps=None, max_accumula
         torch.cuda.synchronize()          # the reference's frame ends with the display sync
         timer.end_frame()
     paths["image"] = results.result_path(out_dir, base, variant, "image", spp)
-    mod.save_image(paths["image"], spp)
+    try:
+        mod.save_image(paths["image"], spp)
+    except Exception as ex:  # e.g. ema_accumulate: the reference logs the failed save and goes on with the CSV and the config
+        paths["image"] = None
+        if log:
+            log("image not saved: %s" % ex)
     paths["inference_csv"] = results.result_path(out_dir, base, variant, "inference", spp)
     timer.write_to_file(paths["inference_csv"])
     paths["config"] = os.path.join(out_dir, "configs", "%s_%s.json" % (base, variant))

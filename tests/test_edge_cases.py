@@ -146,5 +146,33 @@ def test_malformed_files_fail_loudly_and_leave_state_untouched(env, tmp_path):
                  '{"cuda_scene": {"camera": {"matrix": [1, 2, 3]}}}'):
         with pytest.raises(nb.NbvhError):
             nb.NeuralPathModule(text)
+    # a config that is refused half-way (after the scene / renderer blocks parsed fine) leaves every constant block, the network
+    # description and the loaded parameters as they were; the same for a constant block the kernels cannot run
+    import copy
+    import json
+    from nbvh_b200 import _capi as A
+    blocks = (A.CONST_RENDERER, A.CONST_MODULE, A.CONST_PT_OUTPUT, A.CONST_PATH, A.CONST_SCENE, A.CONST_NETWORK, A.CONST_OPTIMIZER)
+    before = [bytes(mod.get_constants(w)) for w in blocks]
+    bad = copy.deepcopy(env["cfg"])
+    bad.setdefault("cuda_scene", {}).setdefault("scene_constants", {})["envmap_strength"] = 7.5
+    bad["neural_bvh_renderer"].setdefault("bvh_constants", {})["rendered_lod"] = 3
+    for breakage in ({"pt_output_constants": {"depth_loss": "Nope"}}, {"network": {"n_neurons": 32}},
+                     {"bvh_module_constants": {"input_segment_points": 5}}):
+        cfg_bad = copy.deepcopy(bad)
+        for k, v in breakage.items():
+            cfg_bad["neural_bvh_renderer"]["neural_module"].setdefault(k, {}).update(v)
+        with pytest.raises(nb.NbvhError):
+            mod.load_config_from_json(json.dumps(cfg_bad))
+        assert [bytes(mod.get_constants(w)) for w in blocks] == before, breakage
+        assert mod.get_params().tobytes() == params_before, breakage
+    net = mod.get_constants(A.CONST_NETWORK)
+    net.n_neurons = 128
+    with pytest.raises(nb.NbvhError):
+        mod.set_constants(A.CONST_NETWORK, net)
+    pt = mod.get_constants(A.CONST_PT_OUTPUT)
+    pt.output_network_dims = 12
+    with pytest.raises(nb.NbvhError):
+        mod.set_constants(A.CONST_PT_OUTPUT, pt)
+    assert [bytes(mod.get_constants(w)) for w in blocks] == before and mod.get_params().tobytes() == params_before
     mod.load_neural_bvh(good)
     assert mod.neural_bvh_nodes().tobytes() == nodes_before

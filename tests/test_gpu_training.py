@@ -205,3 +205,36 @@ def test_long_loss_curve_matches_tcnn():
         print("steps [%d, %d): median loss %.4f, tcnn runs %s" % (lo, hi, ours, np.round(ref, 4)))
         assert 0.90 * ref.min() <= ours <= 1.10 * ref.max(), (lo, hi, ours, ref)
     assert np.median(losses[-100:]) < 0.3 * losses[0]
+
+
+def test_library_communicator_with_one_rank_leaves_the_step_unchanged(env):
+    """comm.cu on a single GPU: a one-rank NCCL communicator created from a unique id (nbvh_allreduce_setup_unique_id) -- the
+    gradient buckets go through ncclAllReduce on the library's communication stream and come back unchanged, so gradients, loss
+    and the Adam step are bit-identical to the step without a communicator.  (Two and more ranks: tools/dp_grad_check.py and
+    tools/dp_tree_cut_check.py under torchrun.)"""
+    torch, mod = env["torch"], env["mod"]
+    x = torch.from_numpy(env["tin"][0]).cuda()
+    t = torch.from_numpy(env["tgt"][0]).cuda()
+    out = []
+    for attach in (False, True):
+        mod.load_params(env["p"])
+        if attach:
+            assert mod.setup_data_parallel(0, 1) == (0, 1)
+            assert mod.data_parallel_world() == (0, 1)
+        grads = mod.gradient_buffer()
+        loss = torch.zeros(1, dtype=torch.float32, device="cuda")
+        mod.training_forward_backward(x, t, loss_sum=loss)
+        torch.cuda.synchronize()
+        g = grads.clone()
+        mod.optimizer_step()
+        torch.cuda.synchronize()
+        out.append((g, float(loss.item()), mod.get_params().copy()))
+        scratch = torch.arange(8, dtype=torch.float32, device="cuda")
+        mod.allreduce(scratch)
+        assert scratch.cpu().tolist() == list(range(8))
+    mod.teardown_data_parallel()
+    assert mod.data_parallel_world() == (0, 1)
+    # the MLP gradients are flushed with fp32 atomics (order varies run to run): compare with the tolerance of two plain runs
+    assert rel(out[1][0].cpu().numpy(), out[0][0].cpu().numpy()) < 1e-5
+    assert abs(out[1][1] - out[0][1]) <= 1e-5 * abs(out[0][1])
+    assert (out[1][2] != out[0][2]).mean() < 1e-3

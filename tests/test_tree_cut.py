@@ -96,6 +96,46 @@ def test_gpu_initial_cut_and_attach_match_oracle(tc_env, oracle, min_depth):
 
 
 @pytest.mark.gpu
+def test_gpu_tree_cut_init_resets_and_attach_rederives_the_learned_lod(oracle, synthetic):
+    """build_and_upload_neural_bvh starts learning at NUM_BVH_LODS - 1 whatever the config says (accel.cpp:520; 34 of the 35 shipped
+    Chess configs omit current_learned_lod), and reinitialise_neural_bvh_learning_states re-derives it from the coarsest level a
+    childless node is reached at (accel.cpp:496-501)."""
+    import copy
+    import torch
+    import nbvh_b200
+    from nbvh_b200 import _capi as A
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, nbvh, tlas, tlas_idx, blas = synthetic
+    cfg = copy.deepcopy(cfg)
+    cfg["neural_bvh_renderer"]["bvh_constants"].pop("current_learned_lod", None)  # a partial config: the key defaults to 0
+    mod = nbvh_b200.NeuralPathModule(cfg)
+    mod.set_scene(tlas, tlas_idx, blas)
+    assert mod.get_constants(A.CONST_RENDERER).current_learned_lod == 0
+    mod.tree_cut_init(3)
+    assert mod.get_constants(A.CONST_RENDERER).current_learned_lod == 6
+    nodes, _, _ = mod.tree_cut_state()
+    leaves = nodes["b"] == 0xFFFFFFFF
+    assert set(np.unique(nodes["a"][leaves]).tolist()) <= {1, 8}  # LEAF_FINAL or LEAF_LOD(6), like the shipped .nbvh files
+    # attach on a cut whose childless nodes are all reached at level 6: learning resumes at 6
+    mod2 = nbvh_b200.NeuralPathModule(cfg)
+    mod2.set_scene(tlas, tlas_idx, blas)
+    mod2.set_neural_bvh(nodes)
+    mod2.tree_cut_attach()
+    assert mod2.get_constants(A.CONST_RENDERER).current_learned_lod == 6
+    # an interior node tagged LEAF_LOD(6) (= a leaf of level 6 that was split while level 5 was learned): its subtree is level 5
+    rn, _, _ = oracle.tree_cut_initial(blas[0]["nodes"], 4, 5)
+    deep = np.ascontiguousarray(rn).copy()
+    interior = np.flatnonzero(deep["b"] != 0xFFFFFFFF)
+    deep["a"][interior[len(interior) // 2:]] = 8
+    mod2.set_neural_bvh(deep)
+    mod2.tree_cut_attach()
+    assert mod2.get_constants(A.CONST_RENDERER).current_learned_lod == 5
+    mod.close()
+    mod2.close()
+
+
+@pytest.mark.gpu
 def test_gpu_tree_cut_steps_match_oracle(tc_env, oracle):
     mod, bn, torch = tc_env["mod"], tc_env["blas"][0]["nodes"], tc_env["torch"]
     mod.tree_cut_init(2)

@@ -30,6 +30,9 @@ def main():
     mod.set_scene(tlas, tlas_idx, blas)
     mod.init_params(1337)
     mod.tree_cut_init(0)
+    mode = os.environ.get("NBVH_DP", "lib")
+    if world > 1 and mode == "lib":  # the library's own NCCL communicator (comm.cu); "torch": the host's process group sums
+        mod.setup_data_parallel(rank, world)
     sched = BvhSplitScheduler(splitting_interval=10, last_split_iteration=100, start_split_num=1, split_scaling=2.0, split_interval_scaling=2.0)
     sched.update_stats_and_reset(1, steps)
     learner = TreeCutLearner(mod, sched, batch_size=(1 << 15) // world, rank=rank, world=world)
@@ -47,7 +50,7 @@ def main():
         dist.all_gather(gathered, ht)
         same = all(bool((g == gathered[0]).all()) for g in gathered)
     if rank == 0:
-        print(json.dumps({"world": world, "steps": steps, "identical_tree_cut_and_weights_on_all_ranks": same, "tree_cut_nodes": len(nodes),
+        print(json.dumps({"world": world, "steps": steps, "gradient_exchange": mode if world > 1 else None, "identical_tree_cut_and_weights_on_all_ranks": same, "tree_cut_nodes": len(nodes),
                           "loss_first10": float(np.mean(losses[:10])), "loss_last10": float(np.mean(losses[-10:]))}))
     ok = same and np.mean(losses[-10:]) < np.mean(losses[:10]) and len(nodes) > 1
     if world > 1:
