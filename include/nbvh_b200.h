@@ -392,6 +392,11 @@ int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable);
  * launching stream; nbvh_get_stage_times synchronises on them, returns the two summed durations and re-arms. */
 int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames);
 int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_ms_total, uint32_t *frames);
+/* the same for the optimisation step: the next `max_steps` nbvh_training_forward_backward + nbvh_optimizer_step pairs record events
+ * between their kernels; nbvh_get_training_stage_times returns the summed milliseconds of
+ * {k_encode_features, k_train_mlp, k_grid_backward (both launches), wait for the gradient exchange, k_adam} and re-arms. */
+int nbvh_enable_training_stage_timing(nbvh_ctx *ctx, uint32_t max_steps);
+int nbvh_get_training_stage_times(nbvh_ctx *ctx, float ms_total_out[5], uint32_t *steps);
 
 /* ---- online optimisation ------------------------------------------------------------------------ */
 /* == trainer->training_step(stream, in 9xB, target 8xB) -> ctx.L (16xB) + trainer->loss()
@@ -417,6 +422,7 @@ float *nbvh_gradients(nbvh_ctx *ctx);
  *   nbvh_nccl_unique_id             == ncclGetUniqueId: 128 bytes that rank 0 hands to the other ranks (any channel: MPI, a file, a socket)
  *   nbvh_allreduce_setup_unique_id  == ncclCommInitRank on the context's device; the library owns the communicator
  *   nbvh_allreduce_buffer           sums a device array over the ranks in place on `stream` (tree-cut statistics, loss sums, image tiles)
+ *   nbvh_nccl_comm                  the attached communicator, to share it with another context of the same process
  *   nbvh_data_parallel_world        -> number of ranks (1 without a communicator), optionally this context's rank */
 #define NBVH_NCCL_UNIQUE_ID_BYTES 128
 enum { NBVH_DTYPE_F32 = 0, NBVH_DTYPE_U32 = 1, NBVH_DTYPE_I32 = 2, NBVH_DTYPE_U64 = 3, NBVH_DTYPE_F64 = 4 };
@@ -426,6 +432,9 @@ int nbvh_allreduce_setup_unique_id(nbvh_ctx *ctx, const void *unique_id_128_byte
 int nbvh_allreduce_teardown(nbvh_ctx *ctx);
 int nbvh_allreduce_buffer(nbvh_ctx *ctx, void *device_ptr, uint64_t count, int dtype, void *stream);
 int nbvh_data_parallel_world(const nbvh_ctx *ctx, int *rank_out);
+/* the attached communicator (ncclComm_t as void *, NULL without one): lets several contexts of one process share it through
+ * nbvh_allreduce_setup (the context that created it must outlive the others) */
+void *nbvh_nccl_comm(const nbvh_ctx *ctx);
 /* Lets the host own the fp32 gradient vector (n_params floats of device memory; NULL -> back to the internal buffer), so
  * the process that drives NCCL can allreduce it in place without a copy. */
 /* == NeuralBVHModule::optimisation_data_generation -> generate_and_fill_bvh_output_reference (path_module.cu:20-52,

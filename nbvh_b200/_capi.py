@@ -182,12 +182,15 @@ SYMBOLS = {
     "nbvh_set_tree_cut_host": (_i, [_vp, _vp, _u32]),
     "nbvh_get_tree_cut_host": (_i, [_vp, _vp, _vp, _u32]),
     "nbvh_tree_cut_max_depth": (_u32, [_vp]),
+    "nbvh_enable_training_stage_timing": (_i, [_vp, _u32]),
+    "nbvh_get_training_stage_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_nccl_unique_id": (_i, [_vp]),
     "nbvh_allreduce_setup": (_i, [_vp, _vp]),
     "nbvh_allreduce_setup_unique_id": (_i, [_vp, _vp, _i, _i]),
     "nbvh_allreduce_teardown": (_i, [_vp]),
     "nbvh_allreduce_buffer": (_i, [_vp, _vp, _u64, _i, _vp]),
     "nbvh_data_parallel_world": (_i, [_vp, C.POINTER(_i)]),
+    "nbvh_nccl_comm": (_vp, [_vp]),
 }
 NCCL_UNIQUE_ID_BYTES = 128
 DTYPE_F32, DTYPE_U32, DTYPE_I32, DTYPE_U64, DTYPE_F64 = range(5)

@@ -476,7 +476,12 @@ int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *
     CU_TRY(ctx, cudaMemsetAsync(ctx->d_grads, 0, ctx->n_params * sizeof(float), st));
     CU_TRY(ctx, cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
     KernelTimer kt(ctx, st);
+    cudaEvent_t *tev = ctx->train_ev_fb < ctx->train_ev_steps ? ctx->train_ev.data() + 7u * ctx->train_ev_fb : nullptr;
+    if (tev)
+        CU_TRY(ctx, cudaEventRecord(tev[0], st));
     CU_TRY(ctx, launch_encode_features(nc, in, batch, ctx->module_const.input_network_dims, ctx->d_feat, ctx->num_sms, st));
+    if (tev)
+        CU_TRY(ctx, cudaEventRecord(tev[1], st));
     TrainParams tp;
     memset(&tp, 0, sizeof(tp));
     tp.feat = ctx->d_feat, tp.dfeat = ctx->d_dfeat, tp.target = target, tp.per_sample_loss = per_sample_loss;
@@ -493,18 +498,26 @@ int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *
     tp.loss.normal_linear = pc.output_normal_linear_activation, tp.loss.depth_linear = pc.output_depth_linear_activation;
     tp.loss.albedo_linear = pc.output_albedo_linear_activation, tp.loss.vis_masking = pc.visibility_masking_loss;
     CU_TRY(ctx, launch_train_mlp(nc, tp, ctx->num_sms, st));
+    if (tev)
+        CU_TRY(ctx, cudaEventRecord(tev[2], st));
     // data parallel (comm.cu): the MLP gradients (and the loss scalar) are summed across the ranks while the grid backward runs,
     // the grid table afterwards; `st` resumes when both buckets are reduced, so the caller (and Adam) only ever see global sums
     if ((rc = dp_allreduce_bucket(ctx, 0, ctx->d_grads, ctx->n_mlp_params, st)) != NBVH_OK)
         return rc;
     CU_TRY(ctx, launch_grid_backward(nc, in, ctx->d_dfeat, batch, ctx->module_const.input_network_dims, ctx->d_grads + ctx->n_mlp_params,
                                      ctx->num_sms, st));
+    if (tev)
+        CU_TRY(ctx, cudaEventRecord(tev[3], st));
     if ((rc = dp_allreduce_bucket(ctx, 1, ctx->d_grads + ctx->n_mlp_params, ctx->n_params - ctx->n_mlp_params, st)) != NBVH_OK)
         return rc;
     if (ctx->nccl_comm && ctx->dp_world > 1 && (rc = nbvh_allreduce_buffer(ctx, loss_dev, 1, NBVH_DTYPE_F32, ctx->comm_stream)) != NBVH_OK)
         return rc;
     if ((rc = dp_join(ctx, st)) != NBVH_OK)
         return rc;
+    if (tev) {
+        CU_TRY(ctx, cudaEventRecord(tev[4], st));
+        ctx->train_ev_fb++;
+    }
     kt.stop();
     return NBVH_OK;
 }
@@ -551,7 +564,14 @@ int nbvh_optimizer_step(nbvh_ctx *ctx, void *stream)
     ap.in_k = ctx->in_k, ap.n_layers = ctx->n_layers;
     for (uint32_t l = 0; l < ctx->n_layers; l++)
         ap.layer_off[l] = ctx->layer_off[l];
+    cudaEvent_t *tev = ctx->train_ev_opt < ctx->train_ev_steps ? ctx->train_ev.data() + 7u * ctx->train_ev_opt : nullptr;
+    if (tev)
+        CU_TRY(ctx, cudaEventRecord(tev[5], st));
     CU_TRY(ctx, launch_adam(ap, st));
+    if (tev) {
+        CU_TRY(ctx, cudaEventRecord(tev[6], st));
+        ctx->train_ev_opt++;
+    }
     ctx->opt_step++;
     ctx->training_step++;
     return NBVH_OK;
@@ -575,5 +595,49 @@ int nbvh_training_step(nbvh_ctx *ctx, const float *in, const float *target, uint
 }
 
 uint32_t nbvh_training_step_count(const nbvh_ctx *ctx) { return ctx ? ctx->training_step : 0; }
+
+int nbvh_enable_training_stage_timing(nbvh_ctx *ctx, uint32_t max_steps)
+{
+    DeviceGuard device_guard(ctx);
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    for (cudaEvent_t e : ctx->train_ev)
+        cudaEventDestroy(e);
+    ctx->train_ev.clear();
+    ctx->train_ev_steps = ctx->train_ev_fb = ctx->train_ev_opt = 0;
+    for (uint32_t i = 0; i < 7u * max_steps; i++) {
+        cudaEvent_t e;
+        CU_TRY(ctx, cudaEventCreate(&e));
+        ctx->train_ev.push_back(e);
+    }
+    ctx->train_ev_steps = max_steps;
+    return NBVH_OK;
+}
+
+int nbvh_get_training_stage_times(nbvh_ctx *ctx, float ms_total_out[5], uint32_t *steps)
+{
+    DeviceGuard device_guard(ctx);
+    if (!ctx || !ms_total_out)
+        return NBVH_ERR_INVALID_ARG;
+    const uint32_t n = ctx->train_ev_fb < ctx->train_ev_opt ? ctx->train_ev_fb : ctx->train_ev_opt;
+    float sum[5]     = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (uint32_t i = 0; i < n; i++) {
+        cudaEvent_t *e = ctx->train_ev.data() + 7u * i;
+        CU_TRY(ctx, cudaEventSynchronize(e[6]));
+        float ms = 0.f;
+        for (int k = 0; k < 4; k++) { // encode | mlp | grid backward | wait for the gradient exchange
+            CU_TRY(ctx, cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+            sum[k] += ms;
+        }
+        CU_TRY(ctx, cudaEventElapsedTime(&ms, e[5], e[6])); // Adam
+        sum[4] += ms;
+    }
+    for (int k = 0; k < 5; k++)
+        ms_total_out[k] = sum[k];
+    if (steps)
+        *steps = n;
+    ctx->train_ev_fb = ctx->train_ev_opt = 0;
+    return NBVH_OK;
+}
 
 } // extern "C"

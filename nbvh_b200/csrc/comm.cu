@@ -196,6 +196,8 @@ int nbvh_allreduce_teardown(nbvh_ctx *ctx)
     return NBVH_OK;
 }
 
+void *nbvh_nccl_comm(const nbvh_ctx *ctx) { return ctx ? ctx->nccl_comm : nullptr; }
+
 int nbvh_data_parallel_world(const nbvh_ctx *ctx, int *rank_out)
 {
     if (!ctx)

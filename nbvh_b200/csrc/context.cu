@@ -347,6 +347,8 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->stage_ev)
         cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->train_ev)
+        cudaEventDestroy(e);
     delete ctx;
 }
 

@@ -177,6 +177,10 @@ struct nbvh_ctx {
     // without host synchronisation; read back by nbvh_get_stage_times
     std::vector<cudaEvent_t> stage_ev;
     uint32_t stage_used = 0; // frames recorded
+    // the same for the optimisation step: per recorded step 7 events (before encode | mlp | grid backward | gradient exchange |
+    // end of forward_backward; before | after Adam), read back by nbvh_get_training_stage_times
+    std::vector<cudaEvent_t> train_ev;
+    uint32_t train_ev_steps = 0, train_ev_fb = 0, train_ev_opt = 0;
 
     // training state (allocated lazily): tcnn::Trainer's buffers (trainer.h:68-87) + Adam moments and step counters
     float *d_grads = nullptr, *d_master = nullptr, *d_m = nullptr, *d_v = nullptr;

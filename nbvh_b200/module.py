@@ -502,6 +502,13 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_allreduce_setup_unique_id(self._h, buf, int(rank), int(world)))
         return rank, world
 
+    def share_data_parallel(self, other):
+        """Attaches the communicator `other` (a module of this process, which must outlive this one) already owns."""
+        comm = other._lib.nbvh_nccl_comm(other._h)
+        if not comm:
+            raise NbvhError(-1, "share_data_parallel: the other module has no communicator")
+        self._check(self._lib.nbvh_allreduce_setup(self._h, C.c_void_p(comm)))
+
     def teardown_data_parallel(self):
         self._check(self._lib.nbvh_allreduce_teardown(self._h))
 
@@ -603,6 +610,15 @@ class NeuralPathModule:
     def enable_stage_timing(self, max_frames):
         """Event triples around k_primary / k_neural for the next `max_frames` frames (no host synchronisation)."""
         self._check(self._lib.nbvh_enable_stage_timing(self._h, int(max_frames)))
+
+    def enable_training_stage_timing(self, max_steps):
+        self._check(self._lib.nbvh_enable_training_stage_timing(self._h, int(max_steps)))
+
+    def training_stage_times(self):
+        """-> ({encode, mlp, grid_backward, exchange_wait, adam} total ms, steps) since the last call."""
+        ms, n = (C.c_float * 5)(), C.c_uint32(0)
+        self._check(self._lib.nbvh_get_training_stage_times(self._h, ms, C.byref(n)))
+        return dict(zip(("encode", "mlp", "grid_backward", "exchange_wait", "adam"), [float(v) for v in ms])), n.value
 
     def stage_times(self):
         """-> (k_primary total ms, k_neural total ms, frames) since the last call; synchronises on the events."""
