@@ -125,7 +125,11 @@ inline cudaError_t allow_max_dynamic_smem(const void *func)
         return e;
     if ((e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, func)) != cudaSuccess)
+        return e;
+    // the opt-in limit covers static + dynamic shared memory of the kernel
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa.sharedSizeBytes);
 }
 
 // ---- online optimisation (training.cu)
