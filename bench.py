@@ -461,6 +461,69 @@ def main():
         barrier()
         multi_ms = float(sum(a.elapsed_time(b) for a, b in ms_ev)) / ms_reps
 
+    # ---------------- online optimisation (second half of BASELINE's metric: train samples/s), data parallel inside the library:
+    # every rank owns 2^18 batch slots; per step: sample generation (K10: tree-cut walk + neural-mesh BLAS trace + material lookups),
+    # hash-grid encode + fused MLP forward/loss/backward + grid backward, the gradient exchange (comm.cu: two NCCL buckets on the
+    # library's communication stream, the MLP bucket overlapping the grid backward) and the replicated Adam step
+    train = None
+    if not args.no_train:
+        train_B = 1 << 18
+        if root is not None:
+            tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root, with_neural_mesh=True, with_attributes=True)
+            mats, texs = nbvh_b200.procedural_materials(int(max(b["material_ids"].max() for b in bl)) + 1)
+            mod.set_scene(tl, ti, bl, materials=mats, textures=texs)
+        cut = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()), seed=11)
+        cut_dev = torch.from_numpy(cut.view(np.uint8).reshape(-1).copy()).to(dev)
+        in_dims = int(mod.get_constants(nbvh_b200.CONST_MODULE).input_network_dims)
+        out_dims = int(mod.network_output_dims())
+        nodes_dev = torch.zeros(train_B, dtype=torch.int32, device=dev)
+        tx = torch.zeros((train_B, in_dims), dtype=torch.float32, device=dev)
+        tt = torch.zeros((train_B, out_dims), dtype=torch.float32, device=dev)
+        train_steps = max(5, min(args.steps, 50))
+        step_no = [0]
+
+        def run_steps(B_local, B_global, n, what="step"):
+            sx, st_, sn = tx[:B_local], tt[:B_local], nodes_dev[:B_local]
+            for _ in range(n):
+                # rank r samples its own slots of the global batch: the RNG is keyed by training_step * batch + slot
+                mod.optimisation_data_generation(step_no[0] * world + rank, B_local, 0, sn, 1.0, cut_dev, sx, st_, stream=stream.cuda_stream)
+                step_no[0] += 1
+                if what == "step":
+                    mod.training_forward_backward(sx, st_, global_batch=B_global, stream=stream.cuda_stream)
+                    mod.optimizer_step(stream=stream.cuda_stream)
+
+        def time_steps(B_local, B_global, what="step"):
+            run_steps(B_local, B_global, 3, what)
+            barrier()
+            te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            te0.record(stream)
+            run_steps(B_local, B_global, train_steps, what)
+            te1.record(stream)
+            barrier()
+            return te0.elapsed_time(te1) / train_steps
+
+        train_ms = time_steps(train_B, train_B * world)
+        mod.enable_training_stage_timing(train_steps)
+        run_steps(train_B, train_B * world, train_steps)
+        torch.cuda.synchronize()
+        stage, stage_n = mod.training_stage_times()
+        mod.enable_training_stage_timing(0)
+        gen_ms = time_steps(train_B, train_B * world, what="generate")
+        # strong scaling of the same step (SURVEY 8d config 3): the GLOBAL batch stays 2^18, every rank owns 2^18 / world slots
+        strong_ms, strong_stage = train_ms, None
+        if world > 1:
+            strong_ms = time_steps(train_B // world, train_B)
+            mod.enable_training_stage_timing(train_steps)
+            run_steps(train_B // world, train_B, train_steps)
+            torch.cuda.synchronize()
+            strong_stage, sn_ = mod.training_stage_times()
+            mod.enable_training_stage_timing(0)
+            strong_stage = {k: v / max(sn_, 1) for k, v in strong_stage.items()}
+            strong_gen = time_steps(train_B // world, train_B, what="generate")
+            strong_stage["sample_generation"] = strong_gen
+        train = dict(train_B=train_B, train_ms=train_ms, gen_ms=gen_ms, strong_ms=strong_ms, strong_stage=strong_stage,
+                     stage={k: v / max(stage_n, 1) for k, v in stage.items()}, steps=train_steps)
+
     # ---------------- hybrid neural path tracing (BASELINE configs[1] at the shipped max_depth = "2b", and configs[3]):
     # shading + BSDF sampling + Russian roulette + HDRI per bounce, 3 launches per depth (path.cu)
     path_info = None
@@ -543,69 +606,6 @@ def main():
             "ms_per_16spp_image": ms4, "images": n4, "Mpixel_samples_s": n_pix4 * spp4 / (ms4 * 1e-3) / 1e6,
             "rays_per_image": c4["rays"], "Mrays_s_all_rays": c4["rays"] / (ms4 * 1e-3) / 1e6,
             "neural_queries_per_s": c4["queries"] / (ms4 * 1e-3)}
-
-    # ---------------- online optimisation (second half of BASELINE's metric: train samples/s), data parallel inside the library:
-    # every rank owns 2^18 batch slots; per step: sample generation (K10: tree-cut walk + neural-mesh BLAS trace + material lookups),
-    # hash-grid encode + fused MLP forward/loss/backward + grid backward, the gradient exchange (comm.cu: two NCCL buckets on the
-    # library's communication stream, the MLP bucket overlapping the grid backward) and the replicated Adam step
-    train = None
-    if not args.no_train:
-        train_B = 1 << 18
-        if root is not None:
-            tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root, with_neural_mesh=True, with_attributes=True)
-            mats, texs = nbvh_b200.procedural_materials(int(max(b["material_ids"].max() for b in bl)) + 1)
-            mod.set_scene(tl, ti, bl, materials=mats, textures=texs)
-        cut = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()), seed=11)
-        cut_dev = torch.from_numpy(cut.view(np.uint8).reshape(-1).copy()).to(dev)
-        in_dims = int(mod.get_constants(nbvh_b200.CONST_MODULE).input_network_dims)
-        out_dims = int(mod.network_output_dims())
-        nodes_dev = torch.zeros(train_B, dtype=torch.int32, device=dev)
-        tx = torch.zeros((train_B, in_dims), dtype=torch.float32, device=dev)
-        tt = torch.zeros((train_B, out_dims), dtype=torch.float32, device=dev)
-        train_steps = max(5, min(args.steps, 50))
-        step_no = [0]
-
-        def run_steps(B_local, B_global, n, what="step"):
-            sx, st_, sn = tx[:B_local], tt[:B_local], nodes_dev[:B_local]
-            for _ in range(n):
-                # rank r samples its own slots of the global batch: the RNG is keyed by training_step * batch + slot
-                mod.optimisation_data_generation(step_no[0] * world + rank, B_local, 0, sn, 1.0, cut_dev, sx, st_, stream=stream.cuda_stream)
-                step_no[0] += 1
-                if what == "step":
-                    mod.training_forward_backward(sx, st_, global_batch=B_global, stream=stream.cuda_stream)
-                    mod.optimizer_step(stream=stream.cuda_stream)
-
-        def time_steps(B_local, B_global, what="step"):
-            run_steps(B_local, B_global, 3, what)
-            barrier()
-            te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            te0.record(stream)
-            run_steps(B_local, B_global, train_steps, what)
-            te1.record(stream)
-            barrier()
-            return te0.elapsed_time(te1) / train_steps
-
-        train_ms = time_steps(train_B, train_B * world)
-        mod.enable_training_stage_timing(train_steps)
-        run_steps(train_B, train_B * world, train_steps)
-        torch.cuda.synchronize()
-        stage, stage_n = mod.training_stage_times()
-        mod.enable_training_stage_timing(0)
-        gen_ms = time_steps(train_B, train_B * world, what="generate")
-        # strong scaling of the same step (SURVEY 8d config 3): the GLOBAL batch stays 2^18, every rank owns 2^18 / world slots
-        strong_ms, strong_stage = train_ms, None
-        if world > 1:
-            strong_ms = time_steps(train_B // world, train_B)
-            mod.enable_training_stage_timing(train_steps)
-            run_steps(train_B // world, train_B, train_steps)
-            torch.cuda.synchronize()
-            strong_stage, sn_ = mod.training_stage_times()
-            mod.enable_training_stage_timing(0)
-            strong_stage = {k: v / max(sn_, 1) for k, v in strong_stage.items()}
-            strong_gen = time_steps(train_B // world, train_B, what="generate")
-            strong_stage["sample_generation"] = strong_gen
-        train = dict(train_B=train_B, train_ms=train_ms, gen_ms=gen_ms, strong_ms=strong_ms, strong_stage=strong_stage,
-                     stage={k: v / max(stage_n, 1) for k, v in stage.items()}, steps=train_steps)
 
     vals = [total_ms, e2e_s * 1e3, train["train_ms"] if train else 0.0, train["strong_ms"] if train else 0.0,
             (e2e_sync_s or 0.0) * 1e3, multi_ms or 0.0, strong or 0.0]
