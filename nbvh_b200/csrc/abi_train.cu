@@ -82,11 +82,13 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.tree_cut         = tree_cut_data;
     sp.counters         = ctx->d_counters;
     if (sp.n_sub_batch == 1) {
+        // two-pass generator: 48-byte items + 8-byte hard-slot records per batch slot, one float per tree-cut node, 8 counter words
         if (ctx->sampler_item_capacity < batch_size) {
-            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); // an earlier generation may still read the old list
-            cudaFree(ctx->d_sampler_items);
-            ctx->d_sampler_items = nullptr, ctx->sampler_item_capacity = 0;
+            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); // an earlier generation may still read the old lists
+            cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_hard);
+            ctx->d_sampler_items = ctx->d_sampler_hard = nullptr, ctx->sampler_item_capacity = 0;
             CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_items, (size_t)batch_size * 48u));
+            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_hard, (size_t)batch_size * 8u));
             ctx->sampler_item_capacity = batch_size;
         }
         if (ctx->node_keep_capacity < ctx->nbvh_nodes) {
@@ -97,11 +99,13 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
             CU_TRY(ctx, cudaMalloc(&ctx->d_node_keep, (size_t)cap * sizeof(float)));
             ctx->node_keep_capacity = cap;
         }
+        if (!ctx->d_sampler_counters)
+            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_counters, 8 * sizeof(uint32_t)));
         sp.node_keep  = ctx->d_node_keep;
         sp.items      = ctx->d_sampler_items;
-        sp.item_count = ctx->d_next_chunk ? ctx->d_next_chunk + 7 : nullptr;
+        sp.hard_slots = reinterpret_cast<uint2 *>(ctx->d_sampler_hard);
     }
-    CU_TRY(ctx, launch_generate_batch(sp, ctx->d_next_chunk ? ctx->d_next_chunk + 4 : nullptr, ctx->num_sms, (cudaStream_t)stream));
+    CU_TRY(ctx, launch_generate_batch(sp, ctx->d_sampler_counters, ctx->num_sms, (cudaStream_t)stream));
     return NBVH_OK;
 }
 

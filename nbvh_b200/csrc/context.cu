@@ -304,7 +304,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     dp_release(ctx);
-    cudaFree(ctx->d_sampler_items);
+    cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_hard), cudaFree(ctx->d_sampler_counters);
     cudaFree(ctx->d_node_keep);
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)

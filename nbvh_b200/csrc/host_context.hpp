@@ -133,6 +133,8 @@ struct nbvh_ctx {
     int dp_rank = 0, dp_world = 1;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_reduced = nullptr;
+    void *d_sampler_hard = nullptr;          // (slot, origins) records of the slots handed to the group-parallel search
+    uint32_t *d_sampler_counters = nullptr;  // cursors / counts / flags of one sample generation (sampler.cu)
     void *d_sampler_items = nullptr; // two-pass sample generator: 48-byte items handed from k_sample_walk to k_sample_targets (grow-only)
     uint32_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;

@@ -238,16 +238,21 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
 // order and in two passes.  Per slot the draws and the arithmetic are exactly those of k_generate_batch, so the outputs are
 // bit-identical; only the lane <-> slot assignment changes.
 //
-//   k_sample_walk     persistent warps, nothing but the retry walk (85 % of a slot's work on Chess: 8 origins and 70 interior
-//                     steps per slot on average, heavy-tailed): every lane visits ONE node per iteration (per-node state
-//                     machine), a lane whose ray met a leaf appends a 48-byte item {slot, node, rng, ray, interval} with one atomic
-//                     per warp and refills at once from the global slot counter -- no lane waits for others.  The stack carries
-//                     the raw slab result of every pushed (far) child, so a popped leaf needs no second slab test: the leaf
-//                     branch is a handful of compares and the warp executes one instruction stream, the interior step.
-//                     (Same ray, same dilated box, same operations -> the stored values are the bits the reference's re-test
-//                     computes.)  The direction of a slot never changes, so its reciprocals are refined once per slot.
-//   k_sample_targets  one thread per item: node-survival roulette, segment encoding, leaf-segment trace against the neural
-//                     mesh's BLAS, surface attributes, texture fetches, targets (emit_slot).
+//   k_sample_walk       persistent warps, nothing but the retry walk (85 % of a slot's work on Chess: 8 origins and 70 interior
+//                       steps per slot on average, heavy-tailed): every lane visits ONE node per iteration (per-node state machine),
+//                       a lane whose ray met a leaf appends a 48-byte item {slot, node, rng, ray, interval} with one atomic per warp
+//                       and refills at once from the global slot counter -- no lane waits for others.  The stack carries the raw
+//                       slab result of every pushed (far) child, so a popped leaf needs no second slab test: the leaf branch is a
+//                       handful of compares and the warp executes one instruction stream, the interior step.  (Same ray, same
+//                       dilated box, same operations -> the stored values are the bits the reference's re-test computes.)  The
+//                       direction of a slot never changes, so its reciprocals are refined once per slot, and whether the hoisted
+//                       division needs its per-box guard is decided once per launch for the tree-cut (k_check_dilation_safe) and once
+//                       per origin.  A slot that has used kHardOrigins origins is handed to
+//   k_sample_walk_hard  groups of kGroup lanes searching the origins of one slot in parallel (LCG skip-ahead; the lowest origin that
+//                       meets a leaf wins, exactly the one the sequential loop stops at).
+//   k_sample_targets    one thread per surviving item: segment encoding, leaf-segment trace against the neural mesh's BLAS, surface
+//                       attributes, texture fetches, targets (emit_slot).  The node-survival roulette is a table lookup at the end of
+//                       the walk (k_node_keep evaluates the survival probability of every tree-cut node once per generation).
 struct SampleItem {
     uint4 a; // slot, node, rng, ox
     uint4 b; // oy, oz, dx, dy
@@ -256,7 +261,32 @@ struct SampleItem {
 
 constexpr uint32_t kRefillThreshold = 8u; // idle lanes that trigger a refill
 constexpr uint32_t kRestartVote     = 3u; // lanes waiting for a new origin that trigger the restart block
-constexpr uint32_t kCoopLanes       = 8u; // live slots per warp at or below which the drained warp retries cooperatively
+constexpr uint32_t kHardOrigins     = 8u; // origins after which a slot is handed to the group-parallel search (k_sample_walk_hard)
+constexpr uint32_t kGroup           = 8u; // lanes that search the origins of one hard slot in parallel
+
+// Per generation, over the current tree-cut: may the retry walk divide with the hoisted reciprocal WITHOUT the per-box guard of
+// slab_raw?  The walk dilates every box with a per-sample factor s = 1 + delta, delta in [0, 1): per axis e = max - min,
+// ctr = min + e/2, h = (e s)/2, box' = ctr -+ h.  If e and ctr are each 0 or of magnitude >= 2^-36 (then h is 0 or >= 2^-37), a
+// coordinate of box' is 0 or >= 2^-60 (the difference of two floats of magnitude >= 2^-37 is a multiple of 2^-60), and with an
+// origin whose coordinates are 0 or >= 2^-61 every numerator (coordinate - origin) is 0 or >= 2^-84: the precondition of
+// hoisted_div (device_core.cuh) holds for every dilation, so the guard is decided once per origin instead of once per box.
+__global__ void __launch_bounds__(256)
+k_check_dilation_safe(const float4 *__restrict__ nodes, uint32_t n, uint32_t *unsafe)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4 lo = nodes[2u * i], hi = nodes[2u * i + 1u];
+    const float mn[3] = {lo.x, lo.y, lo.z}, mx[3] = {hi.x, hi.y, hi.z};
+    bool good = true;
+    for (int k = 0; k < 3; ++k) {
+        const float e = __fsub_rn(mx[k], mn[k]), ctr = __fadd_rn(mn[k], __fmul_rn(e, 0.5f));
+        const float tiny = 1.4551915228366852e-11f /* 2^-36 */, big = 274877906944.0f /* 2^38 */;
+        good = good && (e == 0.f || e >= tiny) && (ctr == 0.f || fabsf(ctr) >= tiny) && fabsf(mn[k]) <= big && fabsf(mx[k]) <= big;
+    }
+    if (!good) // NaN coordinates fail the comparisons above
+        *unsafe = 1u;
+}
 
 // scale * keep of node_survives() for every tree-cut node, once per generation (the roulette then costs one load per found leaf)
 __global__ void __launch_bounds__(256)
@@ -291,6 +321,25 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n)
         n >>= 1;
     }
     return acc_a * state + acc_c;
+}
+
+// the affine map of n LCG draws, evaluated at compile time (n = 3 (kGroup - 1): from one origin of a lane to its next one)
+struct LcgMap {
+    uint32_t a, c;
+};
+__host__ __device__ constexpr LcgMap lcg_map(uint32_t n)
+{
+    uint32_t A = 1664525u, C = 1013904223u, acc_a = 1u, acc_c = 0u;
+    while (n) {
+        if (n & 1u) {
+            acc_a = acc_a * A;
+            acc_c = acc_c * A + C;
+        }
+        C = C * (A + 1u);
+        A = A * A;
+        n >>= 1;
+    }
+    return LcgMap{acc_a, acc_c};
 }
 
 // The retry walk of one ray as a per-node state machine.  The stack carries the raw slab result of every pushed (far) child.
@@ -386,6 +435,15 @@ __device__ __forceinline__ void draw_origin(const SamplerParams &p, float off, u
     ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
 }
 
+// ray.fast for a new origin: 1 = every slab test of this walk may use the hoisted reciprocal unguarded (k_check_dilation_safe said
+// so for the tree-cut, the direction passed ray_prepare_guarded, and the origin is in range), 2 = guarded per box, 0 = div.rn
+__device__ __forceinline__ void set_walk_division_mode(Ray &ray, bool dir_ok, bool cut_safe)
+{
+    const float lo = 4.336808689942018e-19f /* 2^-61 */, hi = 549755813888.0f /* 2^39 */;
+    const bool origin_ok = in_range_or_zero(ray.ox, lo, hi) && in_range_or_zero(ray.oy, lo, hi) && in_range_or_zero(ray.oz, lo, hi);
+    ray.fast = !dir_ok ? 0u : (cut_safe && origin_ok) ? 1u : 2u;
+}
+
 // A found leaf: node id of the slot, node-survival roulette (one draw), and -- for survivors -- the item of the target pass,
 // appended with one atomic per warp.  Must be called by the whole warp.
 __device__ __forceinline__ void emit_found(const SamplerParams &p, uint32_t lane, bool found, uint32_t slot, const CutWalk &w, uint32_t rng,
@@ -413,11 +471,27 @@ __device__ __forceinline__ void emit_found(const SamplerParams &p, uint32_t lane
     }
 }
 
+// Everything a slot draws before its first origin: direction (fixed for the slot), LoD, node dilation.  rng ends at the state the
+// origin draws continue from (origin k of the slot uses draws 3k+1 .. 3k+3 after it).
+__device__ __forceinline__ bool begin_slot(const SamplerParams &p, uint32_t slot, uint32_t n_lods, uint32_t &rng, Ray &ray, NbvhConst &bc)
+{
+    rng            = lcg_rng_init(p.rng_index, 0u, slot);
+    const float s0 = lcg_randomf(rng), s1 = lcg_randomf(rng);
+    const V3 dir   = square_to_uniform_sphere(s0, s1);
+    ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+    ray_prepare_guarded(ray); // the direction is fixed for the slot: only origins are redrawn
+    const uint32_t lod = p.current_learned_lod + min((uint32_t)__fmul_rn(lcg_randomf(rng), __uint2float_rn(n_lods)), n_lods - 1u);
+    bc.leaf_lod_max = 2u + lod;
+    bc.dilation     = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
+    return ray.fast != 0u;
+}
+
 __global__ void __launch_bounds__(128)
 k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ slot_counter)
 {
     const uint32_t lane  = threadIdx.x & 31u;
     const uint32_t total = (uint32_t)p.sub_batch_size;
+    const bool cut_safe  = *reinterpret_cast<const volatile uint32_t *>(p.dilation_unsafe) == 0u;
     NbvhConst bc = p.nbvh;
     CutWalk w;
     w.nss = 0, w.node_idx = 0u, w.cmax = w.cmin = 0.f, w.have_raw = false;
@@ -425,8 +499,8 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
     Ray ray;
     ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
     ray_prepare(ray, false);
-    uint32_t rng = 0u, rng0 = 0u, slot = 0u, n_origins = 0u;
-    bool have_slot = false, walking = false, exhausted = false;
+    uint32_t rng = 0u, slot = 0u, n_origins = 0u;
+    bool have_slot = false, walking = false, exhausted = false, dir_ok = false;
     uint32_t cnt_nbvh = 0;
     const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
     const uint32_t n_lods = p.num_bvh_lods - p.current_learned_lod;
@@ -445,32 +519,38 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
             if (!have_slot) {
                 const uint32_t sl = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
                 if (sl < total) {
-                    slot = sl;
-                    rng  = lcg_rng_init(p.rng_index, 0u, slot);
-                    const float s0 = lcg_randomf(rng), s1 = lcg_randomf(rng);
-                    const V3 dir   = square_to_uniform_sphere(s0, s1);
-                    ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
-                    ray_prepare_guarded(ray); // the direction is fixed for the slot: only origins are redrawn
-                    const uint32_t lod = p.current_learned_lod + min((uint32_t)__fmul_rn(lcg_randomf(rng), __uint2float_rn(n_lods)), n_lods - 1u);
-                    bc.leaf_lod_max = 2u + lod;
-                    bc.dilation     = __fmaf_rn(lcg_randomf(rng), p.node_extent_dilation, p.fixed_node_dilation);
-                    rng0 = rng, n_origins = 0u; // origin k of the slot uses draws 3k+1 .. 3k+3 after rng0
+                    slot      = sl;
+                    dir_ok    = begin_slot(p, slot, n_lods, rng, ray, bc);
+                    n_origins = 0u;
                     have_slot = true, walking = false;
                 }
             }
         }
-        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
-        if (live_mask == 0u)
+        if (!__any_sync(0xFFFFFFFFu, have_slot))
             break; // nothing in flight and the counter is exhausted
-        if (exhausted && (uint32_t)__popc(live_mask) <= kCoopLanes)
-            break; // drained warp: the few slots left are finished cooperatively below
-        // ---------------- new origin for lanes whose walk ended without a leaf (voted: the block costs the whole warp)
+        // ---------------- lanes whose walk ended without a leaf: a new origin -- or, after kHardOrigins of them, the slot goes to the
+        // group-parallel search (the number of origins a slot needs is heavy-tailed: a fixed direction may rarely meet a leaf, and one
+        // such slot would occupy this lane for hundreds of sequential walks).  Voted: the block costs the whole warp.
         {
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, have_slot && !walking);
             const uint32_t busy = __ballot_sync(0xFFFFFFFFu, have_slot && walking);
             if (need && ((uint32_t)__popc(need) >= kRestartVote || busy == 0u || (uint32_t)__popc(need) * 4u >= (uint32_t)__popc(busy))) {
+                const bool hard          = have_slot && !walking && n_origins >= kHardOrigins;
+                const uint32_t hard_mask = __ballot_sync(0xFFFFFFFFu, hard);
+                if (hard_mask) {
+                    uint32_t base = 0u;
+                    const uint32_t leader = (uint32_t)__ffs(hard_mask) - 1u;
+                    if (lane == leader)
+                        base = atomicAdd(p.hard_count, (uint32_t)__popc(hard_mask));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (hard) {
+                        p.hard_slots[base + (uint32_t)__popc(hard_mask & ((1u << lane) - 1u))] = make_uint2(slot, n_origins);
+                        have_slot = false;
+                    }
+                }
                 if (have_slot && !walking) {
                     draw_origin(p, off, rng, ray);
+                    set_walk_division_mode(ray, dir_ok, cut_safe);
                     ++n_origins;
                     cut_walk_start(bc, w);
                     walking = true;
@@ -491,67 +571,96 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
                 have_slot = false;
         }
     }
+    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
+}
 
-    // ---------------- cooperative tail.  The number of origins a slot needs is heavy-tailed (a fixed direction may rarely meet a
-    // leaf: hundreds of origins), and with the slot counter exhausted nothing refills the other lanes -- the longest slot would
-    // set the kernel time.  The origins of one slot are independent draws at known offsets of its LCG stream (lcg_skip), so the
-    // warp splits into groups of G lanes per live slot and walks G consecutive origins of that slot at once; the lowest origin
-    // that meets a leaf is the one the sequential loop would have stopped at (same draws, same walk -> same item).
+// Hard slots: kGroup lanes search the origins of ONE slot in parallel.  The origins of a slot are independent draws at known
+// offsets of its LCG stream (lcg_skip), so lane g of the group walks origins first + g, first + g + kGroup, ... on its own; the
+// lowest origin that meets a leaf is the one the sequential loop would have stopped at (same draws, same walk -> same item), so
+// lanes past the best origin found so far stop, and the group is done when every lane has stopped or holds a leaf.  Groups are
+// independent: a finished group fetches the next hard slot at once (one atomic per warp and round).
+__global__ void __launch_bounds__(128)
+k_sample_walk_hard(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ hard_cursor)
+{
+    constexpr LcgMap kNext  = lcg_map(3u * (kGroup - 1u));
+    const uint32_t lane     = threadIdx.x & 31u;
+    const uint32_t g        = lane % kGroup;
+    const uint32_t gmask    = ((1u << kGroup) - 1u) << (lane - g);
+    const uint32_t n_hard   = *reinterpret_cast<const volatile uint32_t *>(p.hard_count);
+    const bool cut_safe     = *reinterpret_cast<const volatile uint32_t *>(p.dilation_unsafe) == 0u;
+    const float off         = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
+    const uint32_t n_lods   = p.num_bvh_lods - p.current_learned_lod;
+    NbvhConst bc = p.nbvh;
+    CutWalk w;
+    w.nss = 0, w.node_idx = 0u, w.cmax = w.cmin = 0.f, w.have_raw = false;
+    w.node.mnx = w.node.mny = w.node.mnz = w.node.mxx = w.node.mxy = w.node.mxz = 0.f, w.node.a = w.node.b = 0u;
+    Ray ray;
+    ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
+    ray_prepare(ray, false);
+    uint32_t rng = 0u, slot = 0u, my_r = 0u, best = 0xFFFFFFFFu;
+    bool group_active = false, retired = false, walking = false, frozen = false, stopped = false, dir_ok = false;
+    uint32_t cnt_nbvh = 0;
+
     for (;;) {
-        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
-        const uint32_t n_live    = (uint32_t)__popc(live_mask);
-        if (n_live == 0u)
+        // ---------------- idle groups fetch their next hard slot
+        const uint32_t want_mask = __ballot_sync(0xFFFFFFFFu, g == 0u && !group_active && !retired);
+        if (want_mask) {
+            uint32_t base = 0u;
+            if (lane == 0u)
+                base = atomicAdd(hard_cursor, (uint32_t)__popc(want_mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!group_active && !retired) {
+                const uint32_t idx = base + (uint32_t)__popc(want_mask & ((1u << (lane - g)) - 1u));
+                if (idx < n_hard) {
+                    const uint2 item = p.hard_slots[idx];
+                    slot   = item.x;
+                    dir_ok = begin_slot(p, slot, n_lods, rng, ray, bc);
+                    my_r   = item.y + g;
+                    rng    = lcg_skip(rng, 3u * my_r);
+                    best   = 0xFFFFFFFFu;
+                    group_active = true, walking = false, frozen = false, stopped = false;
+                } else {
+                    retired = true;
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, group_active))
             break;
-        const uint32_t G     = n_live == 1u ? 32u : n_live == 2u ? 16u : n_live <= 4u ? 8u : 4u; // lanes per slot (n_live <= 8)
-        const uint32_t group = lane / G, g = lane % G;
-        const bool has       = group < n_live;
-        const uint32_t owner = has ? (uint32_t)__fns(live_mask, 0u, group + 1u) : 0u;
-        // the owner's in-flight origin (if any) is redone: origin index of the group's first lane
-        const uint32_t first = n_origins - ((have_slot && walking) ? 1u : 0u);
-        const uint32_t o_slot  = __shfl_sync(0xFFFFFFFFu, slot, owner);
-        const uint32_t o_rng0  = __shfl_sync(0xFFFFFFFFu, rng0, owner);
-        const uint32_t o_first = __shfl_sync(0xFFFFFFFFu, first, owner);
-        Ray cray;
-        cray.dx = __shfl_sync(0xFFFFFFFFu, ray.dx, owner), cray.dy = __shfl_sync(0xFFFFFFFFu, ray.dy, owner);
-        cray.dz = __shfl_sync(0xFFFFFFFFu, ray.dz, owner);
-        cray.ix = __shfl_sync(0xFFFFFFFFu, ray.ix, owner), cray.iy = __shfl_sync(0xFFFFFFFFu, ray.iy, owner);
-        cray.iz = __shfl_sync(0xFFFFFFFFu, ray.iz, owner);
-        cray.fast = __shfl_sync(0xFFFFFFFFu, ray.fast, owner);
-        cray.ox = cray.oy = cray.oz = 0.f;
-        NbvhConst cbc    = p.nbvh;
-        cbc.leaf_lod_max = __shfl_sync(0xFFFFFFFFu, bc.leaf_lod_max, owner);
-        cbc.dilation     = __shfl_sync(0xFFFFFFFFu, bc.dilation, owner);
-        uint32_t crng    = lcg_skip(o_rng0, 3u * (o_first + g));
-        bool cwalking = false, cfound = false;
-        CutWalk &cw = w; // the owner's own walk state is dead: its in-flight origin is redone by the group
-        if (has) {
-            draw_origin(p, off, crng, cray);
-            cut_walk_start(cbc, cw);
-            cwalking = true;
-        }
-        while (__any_sync(0xFFFFFFFFu, cwalking)) {
-            if (cwalking) {
-                const WalkResult r = cut_walk_step(cbc, cray, cw, cnt_nbvh);
-                cfound   = r == WALK_FOUND;
-                cwalking = r == WALK_CONTINUE;
-            }
-        }
-        // the lowest origin of every group that met a leaf wins
-        const uint32_t found_mask = __ballot_sync(0xFFFFFFFFu, cfound);
-        const uint32_t gmask      = G == 32u ? 0xFFFFFFFFu : (((1u << G) - 1u) << (group * G));
-        const uint32_t gfound     = found_mask & gmask;
-        const bool winner         = cfound && ((uint32_t)__ffs(gfound) - 1u == lane);
-        emit_found(p, lane, winner, o_slot, cw, crng, cray);
-        // owners: slot done, or G more origins consumed
-        if (have_slot) {
-            const uint32_t my_group = (uint32_t)__popc(live_mask & ((1u << lane) - 1u));
-            const uint32_t mine     = G == 32u ? found_mask : ((found_mask >> (my_group * G)) & ((1u << G) - 1u));
-            if (mine) {
-                have_slot = false;
+        // ---------------- lanes between walks: past the best origin -> stop; otherwise the next origin of their stride
+        if (group_active && !walking && !frozen && !stopped) {
+            if (my_r > best) {
+                stopped = true;
             } else {
-                n_origins = first + G;
-                walking   = false;
+                draw_origin(p, off, rng, ray);
+                set_walk_division_mode(ray, dir_ok, cut_safe);
+                cut_walk_start(bc, w);
+                walking = true;
             }
+        }
+        // ---------------- one node visit for every walking lane
+        if (walking) {
+            const WalkResult r = cut_walk_step(bc, ray, w, cnt_nbvh);
+            if (r == WALK_FOUND) {
+                frozen = true, walking = false;
+            } else if (r == WALK_EXHAUSTED) {
+                walking = false;
+                my_r += kGroup;
+                rng = kNext.a * rng + kNext.c; // from the state after origin my_r - kGroup to the state before origin my_r
+            }
+        }
+        // ---------------- the group's best origin so far; walks past it are abandoned
+        best = __reduce_min_sync(gmask, (group_active && frozen) ? my_r : 0xFFFFFFFFu);
+        if (walking && my_r > best)
+            walking = false, stopped = true;
+        if (frozen && my_r > best)
+            frozen = false, stopped = true; // a lower origin met a leaf too
+        // ---------------- finished groups: the winner hands the slot over
+        const uint32_t open_mask = __ballot_sync(0xFFFFFFFFu, group_active && !frozen && !stopped);
+        const bool group_done    = group_active && (open_mask & gmask) == 0u;
+        if (__any_sync(0xFFFFFFFFu, group_done)) {
+            emit_found(p, lane, group_done && frozen && my_r == best, slot, w, rng, ray);
+            if (group_done)
+                group_active = false;
         }
     }
     warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
@@ -579,31 +688,41 @@ k_sample_targets(const __grid_constant__ SamplerParams p)
     warp_add_counter(p.counters, CNT_RAYS, cnt_written);
 }
 
-cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter, int num_sms, cudaStream_t stream)
+cudaError_t launch_generate_batch(const SamplerParams &p_in, uint32_t *sampler_counters, int num_sms, cudaStream_t stream)
 {
-    if (p.sub_batch_size <= 0)
+    if (p_in.sub_batch_size <= 0)
         return cudaSuccess;
-    if (p.n_sub_batch == 1 && slot_counter && p.items && p.item_count && (p.node_keep || !p.training_node_survival) &&
+    SamplerParams p = p_in;
+    if (p.n_sub_batch == 1 && sampler_counters && p.items && p.hard_slots && (p.node_keep || !p.training_node_survival) &&
         !getenv("NBVH_SAMPLER_SIMPLE")) {
-        cudaError_t e = cudaMemsetAsync(slot_counter, 0, sizeof(uint32_t), stream);
+        // counter block: [0] slot cursor, [1] item count, [2] hard-slot count, [3] hard-slot cursor, [4] "a node failed k_check_dilation_safe"
+        cudaError_t e = cudaMemsetAsync(sampler_counters, 0, 8 * sizeof(uint32_t), stream);
         if (e != cudaSuccess)
             return e;
-        if ((e = cudaMemsetAsync(p.item_count, 0, sizeof(uint32_t), stream)) != cudaSuccess)
-            return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0);
-        if (e != cudaSuccess)
-            return e;
-        if (p.training_node_survival) {
+        p.item_count = sampler_counters + 1, p.hard_count = sampler_counters + 2, p.dilation_unsafe = sampler_counters + 4;
+        if (p.training_node_survival)
             k_node_keep<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p, p.nbvh.num_nodes);
-            if ((e = cudaGetLastError()) != cudaSuccess)
-                return e;
-        }
+        k_check_dilation_safe<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p.nbvh.nodes, p.nbvh.num_nodes, p.dilation_unsafe);
+        if ((e = cudaGetLastError()) != cudaSuccess)
+            return e;
+        int per_sm = 0, per_sm_h = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0)) != cudaSuccess ||
+            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_h, k_sample_walk_hard, 128, 0)) != cudaSuccess)
+            return e;
         const uint32_t want = ((uint32_t)p.sub_batch_size + 127u) / 128u;
         uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1));
         if (grid > want)
             grid = want;
-        k_sample_walk<<<grid, 128, 0, stream>>>(p, slot_counter);
+        k_sample_walk<<<grid, 128, 0, stream>>>(p, sampler_counters);
+        // hard slots (>= kHardOrigins failed origins): group-parallel search; the grid is sized for a quarter of the batch being hard,
+        // groups are persistent (a larger share just takes more rounds)
+        const uint32_t groups_per_block = 128u / kGroup;
+        uint32_t want_h = ((uint32_t)p.sub_batch_size / 4u + groups_per_block - 1u) / groups_per_block;
+        want_h          = want_h > 0u ? want_h : 1u;
+        uint32_t grid_h = (uint32_t)(num_sms * (per_sm_h > 0 ? per_sm_h : 1));
+        if (grid_h > want_h)
+            grid_h = want_h;
+        k_sample_walk_hard<<<grid_h, 128, 0, stream>>>(p, sampler_counters + 3);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
         k_sample_targets<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);

@@ -30,9 +30,13 @@ struct SamplerParams {
     // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes each, capacity = batch)
     void *items;
     uint32_t *item_count;
+    uint2 *hard_slots;       // (slot, origins consumed) of slots handed to k_sample_walk_hard, capacity = batch
+    uint32_t *hard_count;    // their number
+    uint32_t *dilation_unsafe; // set when a tree-cut node fails k_check_dilation_safe (-> guarded hoisted division in the walk)
     float *node_keep; // survival_probability_scale * keep per tree-cut node (k_node_keep), capacity = tree-cut nodes
 };
 
-cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *slot_counter, int num_sms, cudaStream_t stream);
+// sampler_counters: 8 device words owned by the context (cleared by every launch)
+cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *sampler_counters, int num_sms, cudaStream_t stream);
 
 } // namespace nbvh
