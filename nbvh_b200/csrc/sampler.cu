@@ -259,10 +259,12 @@ struct SampleItem {
     uint4 c; // dz, leaf_mint, leaf_maxt, -
 };
 
-constexpr uint32_t kRefillThreshold = 8u; // idle lanes that trigger a refill
+constexpr uint32_t kRefillThreshold = 4u; // idle lanes that trigger a refill
 constexpr uint32_t kRestartVote     = 3u; // lanes waiting for a new origin that trigger the restart block
-constexpr uint32_t kHardOrigins     = 8u; // origins after which a slot is handed to the group-parallel search (k_sample_walk_hard)
-constexpr uint32_t kGroup           = 8u; // lanes that search the origins of one hard slot in parallel
+// tunables of the hard-slot search (SamplerParams::hard_origins / group; NBVH_SAMPLER_HARD / NBVH_SAMPLER_GROUP override the defaults):
+// origins after which a slot is handed to k_sample_walk_hard, and the lanes that search the origins of one hard slot in parallel
+constexpr uint32_t kHardOriginsDefault = 8u;
+constexpr uint32_t kGroupDefault       = 8u;
 
 // Per generation, over the current tree-cut: may the retry walk divide with the hoisted reciprocal WITHOUT the per-box guard of
 // slab_raw?  The walk dilates every box with a per-sample factor s = 1 + delta, delta in [0, 1): per axis e = max - min,
@@ -535,7 +537,7 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, have_slot && !walking);
             const uint32_t busy = __ballot_sync(0xFFFFFFFFu, have_slot && walking);
             if (need && ((uint32_t)__popc(need) >= kRestartVote || busy == 0u || (uint32_t)__popc(need) * 4u >= (uint32_t)__popc(busy))) {
-                const bool hard          = have_slot && !walking && n_origins >= kHardOrigins;
+                const bool hard          = have_slot && !walking && n_origins >= p.hard_origins;
                 const uint32_t hard_mask = __ballot_sync(0xFFFFFFFFu, hard);
                 if (hard_mask) {
                     uint32_t base = 0u;
@@ -582,10 +584,10 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
 __global__ void __launch_bounds__(128)
 k_sample_walk_hard(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ hard_cursor)
 {
-    constexpr LcgMap kNext  = lcg_map(3u * (kGroup - 1u));
+    const uint32_t kGroup   = p.group; // 4, 8, 16 or 32 lanes per slot
     const uint32_t lane     = threadIdx.x & 31u;
-    const uint32_t g        = lane % kGroup;
-    const uint32_t gmask    = ((1u << kGroup) - 1u) << (lane - g);
+    const uint32_t g        = lane & (kGroup - 1u);
+    const uint32_t gmask    = (kGroup == 32u ? 0xFFFFFFFFu : ((1u << kGroup) - 1u)) << (lane - g);
     const uint32_t n_hard   = *reinterpret_cast<const volatile uint32_t *>(p.hard_count);
     const bool cut_safe     = *reinterpret_cast<const volatile uint32_t *>(p.dilation_unsafe) == 0u;
     const float off         = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
@@ -645,7 +647,7 @@ k_sample_walk_hard(const __grid_constant__ SamplerParams p, uint32_t *__restrict
             } else if (r == WALK_EXHAUSTED) {
                 walking = false;
                 my_r += kGroup;
-                rng = kNext.a * rng + kNext.c; // from the state after origin my_r - kGroup to the state before origin my_r
+                rng = p.next_a * rng + p.next_c; // from the state after origin my_r - kGroup to the state before origin my_r
             }
         }
         // ---------------- the group's best origin so far; walks past it are abandoned
@@ -709,17 +711,30 @@ cudaError_t launch_generate_batch(const SamplerParams &p_in, uint32_t *sampler_c
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0)) != cudaSuccess ||
             (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_h, k_sample_walk_hard, 128, 0)) != cudaSuccess)
             return e;
+        auto env_u32 = [](const char *name, uint32_t fallback) {
+            const char *v = getenv(name);
+            return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : fallback;
+        };
+        p.hard_origins = env_u32("NBVH_SAMPLER_HARD", kHardOriginsDefault);
+        p.group        = env_u32("NBVH_SAMPLER_GROUP", kGroupDefault);
+        if (p.group != 4u && p.group != 8u && p.group != 16u && p.group != 32u)
+            p.group = kGroupDefault;
+        const LcgMap next = lcg_map(3u * (p.group - 1u));
+        p.next_a = next.a, p.next_c = next.c;
+        // every lane should own several slots (a warp's last slots finish at falling lane counts): the grid is a fraction of full occupancy
         const uint32_t want = ((uint32_t)p.sub_batch_size + 127u) / 128u;
-        uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1));
+        uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1)) / env_u32("NBVH_SAMPLER_GRID_DIV", 1u);
+        grid          = grid > 0u ? grid : 1u;
         if (grid > want)
             grid = want;
         k_sample_walk<<<grid, 128, 0, stream>>>(p, sampler_counters);
         // hard slots (>= kHardOrigins failed origins): group-parallel search; the grid is sized for a quarter of the batch being hard,
         // groups are persistent (a larger share just takes more rounds)
-        const uint32_t groups_per_block = 128u / kGroup;
+        const uint32_t groups_per_block = 128u / p.group;
         uint32_t want_h = ((uint32_t)p.sub_batch_size / 4u + groups_per_block - 1u) / groups_per_block;
         want_h          = want_h > 0u ? want_h : 1u;
-        uint32_t grid_h = (uint32_t)(num_sms * (per_sm_h > 0 ? per_sm_h : 1));
+        uint32_t grid_h = (uint32_t)(num_sms * (per_sm_h > 0 ? per_sm_h : 1)) / env_u32("NBVH_SAMPLER_HGRID_DIV", 1u);
+        grid_h          = grid_h > 0u ? grid_h : 1u;
         if (grid_h > want_h)
             grid_h = want_h;
         k_sample_walk_hard<<<grid_h, 128, 0, stream>>>(p, sampler_counters + 3);

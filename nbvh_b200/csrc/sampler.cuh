@@ -30,6 +30,7 @@ struct SamplerParams {
     // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes each, capacity = batch)
     void *items;
     uint32_t *item_count;
+    uint32_t hard_origins, group, next_a, next_c; // hard-slot search: threshold, lanes per slot, LCG map of 3 (group - 1) draws
     uint2 *hard_slots;       // (slot, origins consumed) of slots handed to k_sample_walk_hard, capacity = batch
     uint32_t *hard_count;    // their number
     uint32_t *dilation_unsafe; // set when a tree-cut node fails k_check_dilation_safe (-> guarded hoisted division in the walk)
