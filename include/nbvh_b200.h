@@ -447,6 +447,15 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
                                       uint32_t log2_bvh_max_traversals, uint32_t *sampled_node_indices,
                                       float current_max_loss, const nbvh_tree_cut_data *tree_cut_data, float *inputs,
                                       float *targets, void *stream);
+/* Walk-ahead of the sample generator.  The rejection walk of a batch slot (random ray until it meets a tree-cut leaf: 85 % of the
+ * generator's work) depends on the tree-cut, the sampler constants and the RNG only -- not on the network, nor on the per-node loss
+ * statistics, which enter the node-survival roulette of the target pass.  After nbvh_sampler_walk_ahead(ctx, K, stride), a call of
+ * nbvh_optimisation_data_generation for training step s that finds no walked items walks the slots of the K steps s, s + stride, ...,
+ * s + (K-1) stride in ONE launch (a 2^18-slot batch alone gives every lane of a B200 1.5 slots -- no steady state; four steps' worth
+ * give it 6), and the following calls for those steps only run their target pass.  Outputs are bit-identical to K = 1 (the default);
+ * items are discarded when the tree-cut or a constant block changes.  stride = number of data-parallel ranks when training_step is
+ * step * world + rank. */
+int nbvh_sampler_walk_ahead(nbvh_ctx *ctx, uint32_t steps, uint32_t step_stride);
 /* harness helper mirroring CudaBackend::create_cuda_textures_buffer (cuda_backend.cpp:387-441): RGBA8 array texture,
  * wrap addressing, linear filtering, normalized float reads.  Returns a cudaTextureObject_t in *tex_out. */
 int nbvh_create_texture_rgba8(nbvh_ctx *ctx, const uint8_t *pixels_host, uint32_t w, uint32_t h, uint64_t *tex_out);

@@ -163,6 +163,7 @@ SYMBOLS = {
     "nbvh_training_step": (_i, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_f), _vp]),
     "nbvh_training_forward_backward": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),
     "nbvh_optimisation_data_generation": (_i, [_vp, _u32, _u32, _u32, _vp, _f, _vp, _vp, _vp, _vp]),
+    "nbvh_sampler_walk_ahead": (_i, [_vp, _u32, _u32]),
     "nbvh_create_texture_rgba8": (_i, [_vp, _vp, _u32, _u32, C.POINTER(_u64)]),
     "nbvh_destroy_textures": (_i, [_vp]),
     "nbvh_create_envmap_rgba32f": (_i, [_vp, _vp, _u32, _u32, C.POINTER(_u64)]),

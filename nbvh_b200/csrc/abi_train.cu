@@ -4,6 +4,14 @@
 
 extern "C" {
 
+int nbvh_sampler_walk_ahead(nbvh_ctx *ctx, uint32_t steps, uint32_t step_stride)
+{
+    if (!ctx || steps == 0 || step_stride == 0)
+        return ctx ? fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_sampler_walk_ahead: steps and stride must be >= 1") : NBVH_ERR_INVALID_ARG;
+    ctx->walk_ahead_steps = steps, ctx->walk_ahead_stride = step_stride;
+    return NBVH_OK;
+}
+
 int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uint32_t batch_size, uint32_t log2_bvh_max_traversals,
                                       uint32_t *sampled_node_indices, float current_max_loss, const nbvh_tree_cut_data *tree_cut_data,
                                       float *inputs, float *targets, void *stream)
@@ -82,30 +90,56 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.tree_cut         = tree_cut_data;
     sp.counters         = ctx->d_counters;
     if (sp.n_sub_batch == 1) {
-        // two-pass generator: 48-byte items + 8-byte hard-slot records per batch slot, one float per tree-cut node, 8 counter words
-        if (ctx->sampler_item_capacity < batch_size) {
-            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); // an earlier generation may still read the old lists
-            cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_hard);
-            ctx->d_sampler_items = ctx->d_sampler_hard = nullptr, ctx->sampler_item_capacity = 0;
-            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_items, (size_t)batch_size * 48u));
-            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_hard, (size_t)batch_size * 8u));
-            ctx->sampler_item_capacity = batch_size;
+        // two-pass generator (sampler.cu).  The walk depends on the tree-cut, the sampler constants and the RNG only, so it may run for
+        // several steps at once (nbvh_sampler_walk_ahead); this step's statistics only enter the roulette of the target pass.
+        cudaStream_t st = (cudaStream_t)stream;
+        const uint32_t stride = ctx->walk_ahead_stride ? ctx->walk_ahead_stride : 1u;
+        uint32_t k = 0;
+        const bool hit = ctx->ahead_valid && ctx->ahead_version == ctx->walk_version && ctx->ahead_batch == batch_size &&
+                         ctx->ahead_stride == stride && training_step >= ctx->ahead_first_step &&
+                         (training_step - ctx->ahead_first_step) % stride == 0u &&
+                         (k = (training_step - ctx->ahead_first_step) / stride) < ctx->ahead_steps;
+        if (!hit) {
+            const uint32_t n_steps = ctx->walk_ahead_steps ? ctx->walk_ahead_steps : 1u;
+            const uint64_t n_items = (uint64_t)batch_size * n_steps;
+            if (n_items > 0xFFFFFFFFull)
+                return fail(ctx, NBVH_ERR_INVALID_ARG, "walk-ahead: batch_size x steps exceeds 2^32 slots");
+            if (ctx->sampler_item_capacity < n_items) {
+                CU_TRY(ctx, cudaDeviceSynchronize()); // an earlier generation (any stream) may still read the old list
+                cudaFree(ctx->d_sampler_items);
+                ctx->d_sampler_items = nullptr, ctx->sampler_item_capacity = 0;
+                CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_items, (size_t)n_items * 48u));
+                ctx->sampler_item_capacity = n_items;
+            }
+            if (!ctx->d_sampler_counters)
+                CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_counters, 8 * sizeof(uint32_t)));
+            if (!ctx->ahead_done)
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->ahead_done, cudaEventDisableTiming));
+            sp.items          = ctx->d_sampler_items;
+            sp.n_steps        = n_steps;
+            sp.rng_index_step = stride * batch_size;
+            CU_TRY(ctx, launch_sample_walk(sp, ctx->d_sampler_counters, ctx->num_sms, st));
+            CU_TRY(ctx, cudaEventRecord(ctx->ahead_done, st));
+            ctx->ahead_valid = true, ctx->ahead_first_step = training_step, ctx->ahead_stride = stride, ctx->ahead_steps = n_steps;
+            ctx->ahead_batch = batch_size, ctx->ahead_version = ctx->walk_version;
+            k = 0;
         }
         if (ctx->node_keep_capacity < ctx->nbvh_nodes) {
-            CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+            CU_TRY(ctx, cudaDeviceSynchronize());
             cudaFree(ctx->d_node_keep);
             ctx->d_node_keep = nullptr, ctx->node_keep_capacity = 0;
             const uint32_t cap = ctx->nbvh_capacity > ctx->nbvh_nodes ? ctx->nbvh_capacity : ctx->nbvh_nodes;
             CU_TRY(ctx, cudaMalloc(&ctx->d_node_keep, (size_t)cap * sizeof(float)));
             ctx->node_keep_capacity = cap;
         }
-        if (!ctx->d_sampler_counters)
-            CU_TRY(ctx, cudaMalloc(&ctx->d_sampler_counters, 8 * sizeof(uint32_t)));
-        sp.node_keep  = ctx->d_node_keep;
-        sp.items      = ctx->d_sampler_items;
-        sp.hard_slots = reinterpret_cast<uint2 *>(ctx->d_sampler_hard);
+        sp.node_keep = ctx->d_node_keep;
+        sp.items     = ctx->d_sampler_items;
+        sp.n_steps   = 1;
+        CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ahead_done, 0));
+        CU_TRY(ctx, launch_sample_targets(sp, k * batch_size, st));
+        return NBVH_OK;
     }
-    CU_TRY(ctx, launch_generate_batch(sp, ctx->d_sampler_counters, ctx->num_sms, (cudaStream_t)stream));
+    CU_TRY(ctx, launch_generate_batch(sp, ctx->num_sms, (cudaStream_t)stream));
     return NBVH_OK;
 }
 
@@ -322,7 +356,7 @@ static int tree_cut_decide(nbvh_ctx *ctx, uint32_t num_splits, float *max_node_l
     CU_TRY(ctx, cudaStreamSynchronize(st));
     if (r.n_split) {
         ctx->nbvh_nodes   = n + 2u * r.n_split;
-        ctx->dilated_with = -1.f; // the pre-dilated copy is rebuilt before the next traversal
+        ctx->dilated_with = -1.f, ctx->walk_version++; // the pre-dilated copy is rebuilt before the next traversal
         int rc = refresh_dilated(ctx);
         if (rc != NBVH_OK)
             return rc;
@@ -412,7 +446,7 @@ int nbvh_tree_cut_assign_lod(nbvh_ctx *ctx, int *all_lods_assigned)
         ctx->bvh_const.current_learned_lod--;
     if (all_lods_assigned)
         *all_lods_assigned = done ? 1 : 0;
-    ctx->dilated_with = -1.f;
+    ctx->dilated_with = -1.f, ctx->walk_version++;
     return refresh_dilated(ctx);
 }
 

@@ -416,7 +416,7 @@ int load_config_body(nbvh_ctx *ctx, const Json &root)
         if (rc != NBVH_OK)
             return rc;
     }
-    ctx->dilated_with = -1.f;
+    ctx->dilated_with = -1.f, ctx->walk_version++;
     return rebuild_layout(ctx);
 }
 } // namespace

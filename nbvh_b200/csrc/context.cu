@@ -304,7 +304,9 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     dp_release(ctx);
-    cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_hard), cudaFree(ctx->d_sampler_counters);
+    cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_counters);
+    if (ctx->ahead_done)
+        cudaEventDestroy(ctx->ahead_done);
     cudaFree(ctx->d_node_keep);
     cudaFree(ctx->d_queue);
     for (int k = 0; k < 2; k++)
@@ -389,9 +391,11 @@ int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t by
             memcpy(dst, old.data(), bytes);
             return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
         }
+        ctx->walk_version++;
         return which == NBVH_CONST_PT_OUTPUT ? NBVH_OK : rebuild_layout(ctx);
     }
     memcpy(dst, pod_host, bytes);
+    ctx->walk_version++; // sampler constants may have changed: walked-ahead items are stale
     if (which == NBVH_CONST_SCENE_BBOX)
         ctx->scene_bbox_set = true;
     return NBVH_OK;
@@ -490,7 +494,7 @@ int nbvh_host::adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemc
     ctx->nbvh_nodes     = n;
     ctx->tree_cut_ready = false; // a new tree-cut invalidates the learning state (reinitialise_neural_bvh_learning_states)
     CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes, (size_t)n * 32, kind));
-    ctx->dilated_with = -1.f;
+    ctx->dilated_with = -1.f, ctx->walk_version++;
     if (!ctx->scene_bbox_set) {
         // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
         // (neural_bvh_renderer_accel.cpp:40,248-251)

@@ -133,10 +133,16 @@ struct nbvh_ctx {
     int dp_rank = 0, dp_world = 1;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_reduced = nullptr;
-    void *d_sampler_hard = nullptr;          // (slot, origins) records of the slots handed to the group-parallel search
-    uint32_t *d_sampler_counters = nullptr;  // cursors / counts / flags of one sample generation (sampler.cu)
+    uint32_t *d_sampler_counters = nullptr;  // cursor / flags of one walk launch (sampler.cu)
+    // walk-ahead (nbvh_sampler_walk_ahead): one k_sample_walk launch walks the slots of `walk_ahead_steps` consecutive optimisation
+    // steps (training_step, training_step + stride, ...); the items stay valid while the tree-cut and the sampler constants do
+    uint32_t walk_ahead_steps = 1, walk_ahead_stride = 1;
+    uint32_t walk_version = 0; // bumped by everything the walk depends on (node array, constants)
+    bool ahead_valid = false;
+    uint32_t ahead_first_step = 0, ahead_stride = 1, ahead_steps = 0, ahead_batch = 0, ahead_version = 0;
+    cudaEvent_t ahead_done = nullptr; // the walk launch has finished (orders target passes issued on other streams)
     void *d_sampler_items = nullptr; // two-pass sample generator: 48-byte items handed from k_sample_walk to k_sample_targets (grow-only)
-    uint32_t sampler_item_capacity = 0;
+    uint64_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
     bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
     bool blas_safe[kMaxBlas] = {};

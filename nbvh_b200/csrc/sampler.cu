@@ -235,36 +235,36 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
 
 // ------------------------------------------------------------------------------------------------ n_sub_batch == 1
 // One slot per reference thread means slots are independent (the RNG is keyed by the slot id), so they may be processed in any
-// order and in two passes.  Per slot the draws and the arithmetic are exactly those of k_generate_batch, so the outputs are
-// bit-identical; only the lane <-> slot assignment changes.
+// order, in two passes, and ahead of time.  Per slot the draws and the arithmetic are exactly those of k_generate_batch, so the
+// outputs are bit-identical; only the lane <-> slot assignment changes.
 //
-//   k_sample_walk       persistent warps, nothing but the retry walk (85 % of a slot's work on Chess: 8 origins and 70 interior
-//                       steps per slot on average, heavy-tailed): every lane visits ONE node per iteration (per-node state machine),
-//                       a lane whose ray met a leaf appends a 48-byte item {slot, node, rng, ray, interval} with one atomic per warp
-//                       and refills at once from the global slot counter -- no lane waits for others.  The stack carries the raw
-//                       slab result of every pushed (far) child, so a popped leaf needs no second slab test: the leaf branch is a
-//                       handful of compares and the warp executes one instruction stream, the interior step.  (Same ray, same
-//                       dilated box, same operations -> the stored values are the bits the reference's re-test computes.)  The
-//                       direction of a slot never changes, so its reciprocals are refined once per slot, and whether the hoisted
-//                       division needs its per-box guard is decided once per launch for the tree-cut (k_check_dilation_safe) and once
-//                       per origin.  A slot that has used kHardOrigins origins is handed to
-//   k_sample_walk_hard  groups of kGroup lanes searching the origins of one slot in parallel (LCG skip-ahead; the lowest origin that
-//                       meets a leaf wins, exactly the one the sequential loop stops at).
-//   k_sample_targets    one thread per surviving item: segment encoding, leaf-segment trace against the neural mesh's BLAS, surface
-//                       attributes, texture fetches, targets (emit_slot).  The node-survival roulette is a table lookup at the end of
-//                       the walk (k_node_keep evaluates the survival probability of every tree-cut node once per generation).
+//   k_sample_walk     persistent warps, nothing but the retry walk (85 % of a slot's work on Chess: 8 origins and 70 interior steps
+//                     per slot on average, heavy-tailed): every lane visits ONE node per iteration (per-node state machine); a lane
+//                     whose ray met a leaf writes the 48-byte item {node, rng, ray, interval} of its slot and refills at once from the
+//                     global slot counter -- no lane waits for others.  The stack carries the raw slab result of every pushed (far)
+//                     child, so a popped leaf needs no second slab test: the leaf branch is a handful of compares and the warp
+//                     executes one instruction stream, the interior step.  (Same ray, same dilated box, same operations -> the
+//                     stored values are the bits the reference's re-test computes.)  The direction of a slot never changes, so its
+//                     reciprocals are refined once per slot, and whether the hoisted division needs its per-box guard is decided once
+//                     per launch for the tree-cut (k_check_dilation_safe) and once per origin.  When the slot counter is exhausted
+//                     and a warp is down to a few live slots, its lanes search the remaining origins of those slots in parallel
+//                     (LCG skip-ahead; the lowest origin that meets a leaf is the one the sequential loop stops at).
+//                     The walk depends on the tree-cut and the RNG only -- not on the network, nor on the per-node loss statistics --
+//                     so ONE launch may walk the slots of several consecutive optimisation steps (SamplerParams::n_steps): a batch of
+//                     2^18 slots gives every lane of the machine 1.5 slots (no steady state, warps run at 12 of 32 lanes); four steps'
+//                     worth give it 6.
+//   k_sample_targets  one thread per slot of ONE step: node id, node-survival roulette (per-node table of this step's statistics,
+//                     k_node_keep), block-wide compaction of the survivors, then segment encoding, leaf-segment trace against the
+//                     neural mesh's BLAS, surface attributes, texture fetches, targets (emit_slot).
 struct SampleItem {
-    uint4 a; // slot, node, rng, ox
-    uint4 b; // oy, oz, dx, dy
-    uint4 c; // dz, leaf_mint, leaf_maxt, -
+    uint4 a; // node, rng, ox, oy
+    uint4 b; // oz, dx, dy, dz
+    uint4 c; // leaf_mint, leaf_maxt, -, -
 };
 
 constexpr uint32_t kRefillThreshold = 4u; // idle lanes that trigger a refill
 constexpr uint32_t kRestartVote     = 3u; // lanes waiting for a new origin that trigger the restart block
-// tunables of the hard-slot search (SamplerParams::hard_origins / group; NBVH_SAMPLER_HARD / NBVH_SAMPLER_GROUP override the defaults):
-// origins after which a slot is handed to k_sample_walk_hard, and the lanes that search the origins of one hard slot in parallel
-constexpr uint32_t kHardOriginsDefault = 8u;
-constexpr uint32_t kGroupDefault       = 8u;
+constexpr uint32_t kCoopLanes       = 8u; // live slots per warp at or below which the drained warp searches origins in parallel
 
 // Per generation, over the current tree-cut: may the retry walk divide with the hoisted reciprocal WITHOUT the per-box guard of
 // slab_raw?  The walk dilates every box with a per-sample factor s = 1 + delta, delta in [0, 1): per axis e = max - min,
@@ -323,25 +323,6 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t state, uint32_t n)
         n >>= 1;
     }
     return acc_a * state + acc_c;
-}
-
-// the affine map of n LCG draws, evaluated at compile time (n = 3 (kGroup - 1): from one origin of a lane to its next one)
-struct LcgMap {
-    uint32_t a, c;
-};
-__host__ __device__ constexpr LcgMap lcg_map(uint32_t n)
-{
-    uint32_t A = 1664525u, C = 1013904223u, acc_a = 1u, acc_c = 0u;
-    while (n) {
-        if (n & 1u) {
-            acc_a = acc_a * A;
-            acc_c = acc_c * A + C;
-        }
-        C = C * (A + 1u);
-        A = A * A;
-        n >>= 1;
-    }
-    return LcgMap{acc_a, acc_c};
 }
 
 // The retry walk of one ray as a per-node state machine.  The stack carries the raw slab result of every pushed (far) child.
@@ -446,38 +427,21 @@ __device__ __forceinline__ void set_walk_division_mode(Ray &ray, bool dir_ok, bo
     ray.fast = !dir_ok ? 0u : (cut_safe && origin_ok) ? 1u : 2u;
 }
 
-// A found leaf: node id of the slot, node-survival roulette (one draw), and -- for survivors -- the item of the target pass,
-// appended with one atomic per warp.  Must be called by the whole warp.
-__device__ __forceinline__ void emit_found(const SamplerParams &p, uint32_t lane, bool found, uint32_t slot, const CutWalk &w, uint32_t rng,
-                                           const Ray &ray)
+// the item of a slot whose walk met a leaf (position = step * batch + slot)
+__device__ __forceinline__ void write_item(const SamplerParams &p, uint32_t idx, const CutWalk &w, uint32_t rng, const Ray &ray)
 {
-    bool keep = false;
-    if (found) {
-        p.sampled_node_indices[slot] = w.node_idx;
-        // rejected: the slot keeps its previous contents (reference quirk, SURVEY a17)
-        keep = !p.training_node_survival || !(__ldg(p.node_keep + w.node_idx) < lcg_randomf(rng));
-    }
-    const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
-    if (keep_mask == 0u)
-        return;
-    uint32_t base = 0u;
-    const uint32_t leader = (uint32_t)__ffs(keep_mask) - 1u;
-    if (lane == leader)
-        base = atomicAdd(p.item_count, (uint32_t)__popc(keep_mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (keep) {
-        uint4 *it = reinterpret_cast<uint4 *>(p.items) + 3u * (size_t)(base + (uint32_t)__popc(keep_mask & ((1u << lane) - 1u)));
-        it[0] = make_uint4(slot, w.node_idx, rng, __float_as_uint(ray.ox));
-        it[1] = make_uint4(__float_as_uint(ray.oy), __float_as_uint(ray.oz), __float_as_uint(ray.dx), __float_as_uint(ray.dy));
-        it[2] = make_uint4(__float_as_uint(ray.dz), __float_as_uint(w.cmax), __float_as_uint(w.cmin), 0u);
-    }
+    uint4 *it = reinterpret_cast<uint4 *>(p.items) + 3u * (size_t)idx;
+    it[0] = make_uint4(w.node_idx, rng, __float_as_uint(ray.ox), __float_as_uint(ray.oy));
+    it[1] = make_uint4(__float_as_uint(ray.oz), __float_as_uint(ray.dx), __float_as_uint(ray.dy), __float_as_uint(ray.dz));
+    it[2] = make_uint4(__float_as_uint(w.cmax), __float_as_uint(w.cmin), 0u, 0u);
 }
 
 // Everything a slot draws before its first origin: direction (fixed for the slot), LoD, node dilation.  rng ends at the state the
-// origin draws continue from (origin k of the slot uses draws 3k+1 .. 3k+3 after it).
-__device__ __forceinline__ bool begin_slot(const SamplerParams &p, uint32_t slot, uint32_t n_lods, uint32_t &rng, Ray &ray, NbvhConst &bc)
+// origin draws continue from (origin k of the slot uses draws 3k+1 .. 3k+3 after it).  idx = step * batch + slot of a walk-ahead launch.
+__device__ __forceinline__ bool begin_slot(const SamplerParams &p, uint32_t idx, uint32_t n_lods, uint32_t &rng, Ray &ray, NbvhConst &bc)
 {
-    rng            = lcg_rng_init(p.rng_index, 0u, slot);
+    const uint32_t step = idx / (uint32_t)p.sub_batch_size, slot = idx - step * (uint32_t)p.sub_batch_size;
+    rng            = lcg_rng_init(p.rng_index + step * p.rng_index_step, 0u, slot);
     const float s0 = lcg_randomf(rng), s1 = lcg_randomf(rng);
     const V3 dir   = square_to_uniform_sphere(s0, s1);
     ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
@@ -492,7 +456,7 @@ __global__ void __launch_bounds__(128)
 k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ slot_counter)
 {
     const uint32_t lane  = threadIdx.x & 31u;
-    const uint32_t total = (uint32_t)p.sub_batch_size;
+    const uint32_t total = (uint32_t)p.sub_batch_size * p.n_steps;
     const bool cut_safe  = *reinterpret_cast<const volatile uint32_t *>(p.dilation_unsafe) == 0u;
     NbvhConst bc = p.nbvh;
     CutWalk w;
@@ -501,7 +465,7 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
     Ray ray;
     ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
     ray_prepare(ray, false);
-    uint32_t rng = 0u, slot = 0u, n_origins = 0u;
+    uint32_t rng = 0u, rng0 = 0u, idx = 0u, n_origins = 0u;
     bool have_slot = false, walking = false, exhausted = false, dir_ok = false;
     uint32_t cnt_nbvh = 0;
     const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
@@ -521,35 +485,24 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
             if (!have_slot) {
                 const uint32_t sl = base + (uint32_t)__popc(idle_mask & ((1u << lane) - 1u));
                 if (sl < total) {
-                    slot      = sl;
-                    dir_ok    = begin_slot(p, slot, n_lods, rng, ray, bc);
+                    idx       = sl;
+                    dir_ok    = begin_slot(p, idx, n_lods, rng, ray, bc);
+                    rng0      = rng;
                     n_origins = 0u;
                     have_slot = true, walking = false;
                 }
             }
         }
-        if (!__any_sync(0xFFFFFFFFu, have_slot))
+        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
+        if (live_mask == 0u)
             break; // nothing in flight and the counter is exhausted
-        // ---------------- lanes whose walk ended without a leaf: a new origin -- or, after kHardOrigins of them, the slot goes to the
-        // group-parallel search (the number of origins a slot needs is heavy-tailed: a fixed direction may rarely meet a leaf, and one
-        // such slot would occupy this lane for hundreds of sequential walks).  Voted: the block costs the whole warp.
+        if (exhausted && (uint32_t)__popc(live_mask) <= kCoopLanes)
+            break; // drained warp: the few slots left are finished cooperatively below
+        // ---------------- new origin for lanes whose walk ended without a leaf (voted: the block costs the whole warp)
         {
             const uint32_t need = __ballot_sync(0xFFFFFFFFu, have_slot && !walking);
             const uint32_t busy = __ballot_sync(0xFFFFFFFFu, have_slot && walking);
             if (need && ((uint32_t)__popc(need) >= kRestartVote || busy == 0u || (uint32_t)__popc(need) * 4u >= (uint32_t)__popc(busy))) {
-                const bool hard          = have_slot && !walking && n_origins >= p.hard_origins;
-                const uint32_t hard_mask = __ballot_sync(0xFFFFFFFFu, hard);
-                if (hard_mask) {
-                    uint32_t base = 0u;
-                    const uint32_t leader = (uint32_t)__ffs(hard_mask) - 1u;
-                    if (lane == leader)
-                        base = atomicAdd(p.hard_count, (uint32_t)__popc(hard_mask));
-                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                    if (hard) {
-                        p.hard_slots[base + (uint32_t)__popc(hard_mask & ((1u << lane) - 1u))] = make_uint2(slot, n_origins);
-                        have_slot = false;
-                    }
-                }
                 if (have_slot && !walking) {
                     draw_origin(p, off, rng, ray);
                     set_walk_division_mode(ray, dir_ok, cut_safe);
@@ -559,130 +512,125 @@ k_sample_walk(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ sl
                 }
             }
         }
-        // ---------------- one node visit for every walking lane
-        bool found = false;
+        // ---------------- one node visit for every walking lane; a lane that met a leaf writes its item and becomes idle
         if (have_slot && walking) {
             const WalkResult r = cut_walk_step(bc, ray, w, cnt_nbvh);
-            found   = r == WALK_FOUND;
             walking = r == WALK_CONTINUE;
-        }
-        // ---------------- lanes that met a leaf hand their slot over and become idle
-        if (__any_sync(0xFFFFFFFFu, found)) {
-            emit_found(p, lane, found, slot, w, rng, ray);
-            if (found)
-                have_slot = false;
-        }
-    }
-    warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
-}
-
-// Hard slots: kGroup lanes search the origins of ONE slot in parallel.  The origins of a slot are independent draws at known
-// offsets of its LCG stream (lcg_skip), so lane g of the group walks origins first + g, first + g + kGroup, ... on its own; the
-// lowest origin that meets a leaf is the one the sequential loop would have stopped at (same draws, same walk -> same item), so
-// lanes past the best origin found so far stop, and the group is done when every lane has stopped or holds a leaf.  Groups are
-// independent: a finished group fetches the next hard slot at once (one atomic per warp and round).
-__global__ void __launch_bounds__(128)
-k_sample_walk_hard(const __grid_constant__ SamplerParams p, uint32_t *__restrict__ hard_cursor)
-{
-    const uint32_t kGroup   = p.group; // 4, 8, 16 or 32 lanes per slot
-    const uint32_t lane     = threadIdx.x & 31u;
-    const uint32_t g        = lane & (kGroup - 1u);
-    const uint32_t gmask    = (kGroup == 32u ? 0xFFFFFFFFu : ((1u << kGroup) - 1u)) << (lane - g);
-    const uint32_t n_hard   = *reinterpret_cast<const volatile uint32_t *>(p.hard_count);
-    const bool cut_safe     = *reinterpret_cast<const volatile uint32_t *>(p.dilation_unsafe) == 0u;
-    const float off         = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
-    const uint32_t n_lods   = p.num_bvh_lods - p.current_learned_lod;
-    NbvhConst bc = p.nbvh;
-    CutWalk w;
-    w.nss = 0, w.node_idx = 0u, w.cmax = w.cmin = 0.f, w.have_raw = false;
-    w.node.mnx = w.node.mny = w.node.mnz = w.node.mxx = w.node.mxy = w.node.mxz = 0.f, w.node.a = w.node.b = 0u;
-    Ray ray;
-    ray.ox = ray.oy = ray.oz = 0.f, ray.dx = ray.dy = ray.dz = 1.f;
-    ray_prepare(ray, false);
-    uint32_t rng = 0u, slot = 0u, my_r = 0u, best = 0xFFFFFFFFu;
-    bool group_active = false, retired = false, walking = false, frozen = false, stopped = false, dir_ok = false;
-    uint32_t cnt_nbvh = 0;
-
-    for (;;) {
-        // ---------------- idle groups fetch their next hard slot
-        const uint32_t want_mask = __ballot_sync(0xFFFFFFFFu, g == 0u && !group_active && !retired);
-        if (want_mask) {
-            uint32_t base = 0u;
-            if (lane == 0u)
-                base = atomicAdd(hard_cursor, (uint32_t)__popc(want_mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (!group_active && !retired) {
-                const uint32_t idx = base + (uint32_t)__popc(want_mask & ((1u << (lane - g)) - 1u));
-                if (idx < n_hard) {
-                    const uint2 item = p.hard_slots[idx];
-                    slot   = item.x;
-                    dir_ok = begin_slot(p, slot, n_lods, rng, ray, bc);
-                    my_r   = item.y + g;
-                    rng    = lcg_skip(rng, 3u * my_r);
-                    best   = 0xFFFFFFFFu;
-                    group_active = true, walking = false, frozen = false, stopped = false;
-                } else {
-                    retired = true;
-                }
-            }
-        }
-        if (!__any_sync(0xFFFFFFFFu, group_active))
-            break;
-        // ---------------- lanes between walks: past the best origin -> stop; otherwise the next origin of their stride
-        if (group_active && !walking && !frozen && !stopped) {
-            if (my_r > best) {
-                stopped = true;
-            } else {
-                draw_origin(p, off, rng, ray);
-                set_walk_division_mode(ray, dir_ok, cut_safe);
-                cut_walk_start(bc, w);
-                walking = true;
-            }
-        }
-        // ---------------- one node visit for every walking lane
-        if (walking) {
-            const WalkResult r = cut_walk_step(bc, ray, w, cnt_nbvh);
             if (r == WALK_FOUND) {
-                frozen = true, walking = false;
-            } else if (r == WALK_EXHAUSTED) {
-                walking = false;
-                my_r += kGroup;
-                rng = p.next_a * rng + p.next_c; // from the state after origin my_r - kGroup to the state before origin my_r
+                write_item(p, idx, w, rng, ray);
+                have_slot = false;
             }
         }
-        // ---------------- the group's best origin so far; walks past it are abandoned
-        best = __reduce_min_sync(gmask, (group_active && frozen) ? my_r : 0xFFFFFFFFu);
-        if (walking && my_r > best)
-            walking = false, stopped = true;
-        if (frozen && my_r > best)
-            frozen = false, stopped = true; // a lower origin met a leaf too
-        // ---------------- finished groups: the winner hands the slot over
-        const uint32_t open_mask = __ballot_sync(0xFFFFFFFFu, group_active && !frozen && !stopped);
-        const bool group_done    = group_active && (open_mask & gmask) == 0u;
-        if (__any_sync(0xFFFFFFFFu, group_done)) {
-            emit_found(p, lane, group_done && frozen && my_r == best, slot, w, rng, ray);
-            if (group_done)
-                group_active = false;
+    }
+
+    // ---------------- cooperative tail.  The number of origins a slot needs is heavy-tailed (a fixed direction may rarely meet a
+    // leaf: hundreds of origins), and with the slot counter exhausted nothing refills the other lanes -- the longest slot would
+    // set the kernel time.  The origins of one slot are independent draws at known offsets of its LCG stream (lcg_skip), so the
+    // warp splits into groups of G lanes per live slot and walks G consecutive origins of that slot at once; the lowest origin
+    // that meets a leaf is the one the sequential loop would have stopped at (same draws, same walk -> same item).
+    for (;;) {
+        const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, have_slot);
+        const uint32_t n_live    = (uint32_t)__popc(live_mask);
+        if (n_live == 0u)
+            break;
+        const uint32_t G     = n_live == 1u ? 32u : n_live == 2u ? 16u : n_live <= 4u ? 8u : 4u; // lanes per slot (n_live <= 8)
+        const uint32_t group = lane / G, g = lane % G;
+        const bool has       = group < n_live;
+        const uint32_t owner = has ? (uint32_t)__fns(live_mask, 0u, group + 1u) : 0u;
+        // the owner's in-flight origin (if any) is redone: origin index of the group's first lane
+        const uint32_t first   = n_origins - ((have_slot && walking) ? 1u : 0u);
+        const uint32_t o_idx   = __shfl_sync(0xFFFFFFFFu, idx, owner);
+        const uint32_t o_rng0  = __shfl_sync(0xFFFFFFFFu, rng0, owner);
+        const uint32_t o_first = __shfl_sync(0xFFFFFFFFu, first, owner);
+        const bool o_dir_ok    = __shfl_sync(0xFFFFFFFFu, dir_ok ? 1u : 0u, owner) != 0u;
+        Ray cray;
+        cray.dx = __shfl_sync(0xFFFFFFFFu, ray.dx, owner), cray.dy = __shfl_sync(0xFFFFFFFFu, ray.dy, owner);
+        cray.dz = __shfl_sync(0xFFFFFFFFu, ray.dz, owner);
+        cray.ix = __shfl_sync(0xFFFFFFFFu, ray.ix, owner), cray.iy = __shfl_sync(0xFFFFFFFFu, ray.iy, owner);
+        cray.iz = __shfl_sync(0xFFFFFFFFu, ray.iz, owner);
+        cray.fast = 0u;
+        cray.ox = cray.oy = cray.oz = 0.f;
+        NbvhConst cbc    = p.nbvh;
+        cbc.leaf_lod_max = __shfl_sync(0xFFFFFFFFu, bc.leaf_lod_max, owner);
+        cbc.dilation     = __shfl_sync(0xFFFFFFFFu, bc.dilation, owner);
+        uint32_t crng    = lcg_skip(o_rng0, 3u * (o_first + g));
+        bool cwalking = false, cfound = false;
+        CutWalk &cw = w; // the owner's own walk state is dead: its in-flight origin is redone by the group
+        if (has) {
+            draw_origin(p, off, crng, cray);
+            set_walk_division_mode(cray, o_dir_ok, cut_safe);
+            cut_walk_start(cbc, cw);
+            cwalking = true;
+        }
+        while (__any_sync(0xFFFFFFFFu, cwalking)) {
+            if (cwalking) {
+                const WalkResult r = cut_walk_step(cbc, cray, cw, cnt_nbvh);
+                cfound   = r == WALK_FOUND;
+                cwalking = r == WALK_CONTINUE;
+            }
+        }
+        // the lowest origin of every group that met a leaf wins
+        const uint32_t found_mask = __ballot_sync(0xFFFFFFFFu, cfound);
+        const uint32_t gmask      = G == 32u ? 0xFFFFFFFFu : (((1u << G) - 1u) << (group * G));
+        const uint32_t gfound     = found_mask & gmask;
+        if (cfound && ((uint32_t)__ffs(gfound) - 1u == lane))
+            write_item(p, o_idx, cw, crng, cray);
+        // owners: slot done, or G more origins consumed
+        if (have_slot) {
+            const uint32_t my_group = (uint32_t)__popc(live_mask & ((1u << lane) - 1u));
+            const uint32_t mine     = G == 32u ? found_mask : ((found_mask >> (my_group * G)) & ((1u << G) - 1u));
+            if (mine) {
+                have_slot = false;
+            } else {
+                n_origins = first + G;
+                walking   = false;
+            }
         }
     }
     warp_add_counter(p.counters, CNT_NBVH_STEPS, cnt_nbvh);
 }
 
+// One thread per slot of one step (items of that step: p.items + step_first_item).  The roulette's survivors are compacted inside
+// the block, so the trace against the neural mesh's BLAS runs on dense warps.
 __global__ void __launch_bounds__(128)
-k_sample_targets(const __grid_constant__ SamplerParams p)
+k_sample_targets(const __grid_constant__ SamplerParams p, uint32_t step_first_item)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n = *reinterpret_cast<const volatile uint32_t *>(p.item_count);
+    __shared__ uint32_t s_src[128];
+    __shared__ uint32_t s_warp_count[4];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t i   = blockIdx.x * blockDim.x + tid;
+    bool keep = false;
+    if (i < (uint32_t)p.sub_batch_size) {
+        const uint4 a = reinterpret_cast<const uint4 *>(p.items)[3u * (size_t)(step_first_item + i)];
+        uint32_t rng  = a.y;
+        p.sampled_node_indices[i] = a.x;
+        // rejected: the slot keeps its previous contents (reference quirk, SURVEY a17)
+        keep = !p.training_node_survival || !(__ldg(p.node_keep + a.x) < lcg_randomf(rng));
+    }
+    const uint32_t keep_mask = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0u)
+        s_warp_count[warp] = (uint32_t)__popc(keep_mask);
+    __syncthreads();
+    uint32_t before = 0u, n_keep = 0u;
+#pragma unroll
+    for (uint32_t k = 0; k < 4u; ++k) {
+        before += k < warp ? s_warp_count[k] : 0u;
+        n_keep += s_warp_count[k];
+    }
+    if (keep)
+        s_src[before + (uint32_t)__popc(keep_mask & ((1u << lane) - 1u))] = i;
+    __syncthreads();
     uint32_t cnt_blas = 0, cnt_tri = 0, cnt_written = 0;
-    if (i < n) {
-        const uint4 *it = reinterpret_cast<const uint4 *>(p.items) + 3u * (size_t)i;
+    if (tid < n_keep) {
+        const uint32_t slot = s_src[tid];
+        const uint4 *it     = reinterpret_cast<const uint4 *>(p.items) + 3u * (size_t)(step_first_item + slot);
         const uint4 a = it[0], b = it[1], c = it[2];
         Ray ray;
-        ray.ox = __uint_as_float(a.w), ray.oy = __uint_as_float(b.x), ray.oz = __uint_as_float(b.y);
-        ray.dx = __uint_as_float(b.z), ray.dy = __uint_as_float(b.w), ray.dz = __uint_as_float(c.x);
+        ray.ox = __uint_as_float(a.z), ray.oy = __uint_as_float(a.w), ray.oz = __uint_as_float(b.x);
+        ray.dx = __uint_as_float(b.y), ray.dy = __uint_as_float(b.z), ray.dz = __uint_as_float(b.w);
         ray_prepare_guarded(ray);
         ItsData its;
-        emit_slot(p, a.x, ray, __uint_as_float(c.y), __uint_as_float(c.z), false, its, cnt_blas, cnt_tri);
+        emit_slot(p, slot, ray, __uint_as_float(c.x), __uint_as_float(c.y), false, its, cnt_blas, cnt_tri);
         ++cnt_written;
     }
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);
@@ -690,59 +638,41 @@ k_sample_targets(const __grid_constant__ SamplerParams p)
     warp_add_counter(p.counters, CNT_RAYS, cnt_written);
 }
 
-cudaError_t launch_generate_batch(const SamplerParams &p_in, uint32_t *sampler_counters, int num_sms, cudaStream_t stream)
+// Walks the slots of p.n_steps consecutive optimisation steps into p.items (n_steps * batch items of 48 bytes).
+cudaError_t launch_sample_walk(const SamplerParams &p, uint32_t *sampler_counters, int num_sms, cudaStream_t stream)
 {
-    if (p_in.sub_batch_size <= 0)
+    // counter block: [0] slot cursor, [4] "a node failed k_check_dilation_safe"
+    cudaError_t e = cudaMemsetAsync(sampler_counters, 0, 8 * sizeof(uint32_t), stream);
+    if (e != cudaSuccess)
+        return e;
+    SamplerParams q   = p;
+    q.dilation_unsafe = sampler_counters + 4;
+    k_check_dilation_safe<<<(q.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(q.nbvh.nodes, q.nbvh.num_nodes, q.dilation_unsafe);
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0)) != cudaSuccess)
+        return e;
+    const uint64_t total = (uint64_t)q.sub_batch_size * q.n_steps;
+    const uint32_t want  = (uint32_t)((total + 127u) / 128u);
+    uint32_t grid        = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1));
+    if (grid > want)
+        grid = want;
+    k_sample_walk<<<grid, 128, 0, stream>>>(q, sampler_counters);
+    return cudaGetLastError();
+}
+
+// Roulette + targets of ONE step from its walked items (first item of the step: step_first_item).
+cudaError_t launch_sample_targets(const SamplerParams &p, uint32_t step_first_item, cudaStream_t stream)
+{
+    if (p.training_node_survival)
+        k_node_keep<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p, p.nbvh.num_nodes);
+    k_sample_targets<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p, step_first_item);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_batch(const SamplerParams &p, int num_sms, cudaStream_t stream)
+{
+    if (p.sub_batch_size <= 0)
         return cudaSuccess;
-    SamplerParams p = p_in;
-    if (p.n_sub_batch == 1 && sampler_counters && p.items && p.hard_slots && (p.node_keep || !p.training_node_survival) &&
-        !getenv("NBVH_SAMPLER_SIMPLE")) {
-        // counter block: [0] slot cursor, [1] item count, [2] hard-slot count, [3] hard-slot cursor, [4] "a node failed k_check_dilation_safe"
-        cudaError_t e = cudaMemsetAsync(sampler_counters, 0, 8 * sizeof(uint32_t), stream);
-        if (e != cudaSuccess)
-            return e;
-        p.item_count = sampler_counters + 1, p.hard_count = sampler_counters + 2, p.dilation_unsafe = sampler_counters + 4;
-        if (p.training_node_survival)
-            k_node_keep<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p, p.nbvh.num_nodes);
-        k_check_dilation_safe<<<(p.nbvh.num_nodes + 255u) / 256u, 256, 0, stream>>>(p.nbvh.nodes, p.nbvh.num_nodes, p.dilation_unsafe);
-        if ((e = cudaGetLastError()) != cudaSuccess)
-            return e;
-        int per_sm = 0, per_sm_h = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sample_walk, 128, 0)) != cudaSuccess ||
-            (e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_h, k_sample_walk_hard, 128, 0)) != cudaSuccess)
-            return e;
-        auto env_u32 = [](const char *name, uint32_t fallback) {
-            const char *v = getenv(name);
-            return v && *v ? (uint32_t)strtoul(v, nullptr, 10) : fallback;
-        };
-        p.hard_origins = env_u32("NBVH_SAMPLER_HARD", kHardOriginsDefault);
-        p.group        = env_u32("NBVH_SAMPLER_GROUP", kGroupDefault);
-        if (p.group != 4u && p.group != 8u && p.group != 16u && p.group != 32u)
-            p.group = kGroupDefault;
-        const LcgMap next = lcg_map(3u * (p.group - 1u));
-        p.next_a = next.a, p.next_c = next.c;
-        // every lane should own several slots (a warp's last slots finish at falling lane counts): the grid is a fraction of full occupancy
-        const uint32_t want = ((uint32_t)p.sub_batch_size + 127u) / 128u;
-        uint32_t grid = (uint32_t)(num_sms * (per_sm > 0 ? per_sm : 1)) / env_u32("NBVH_SAMPLER_GRID_DIV", 1u);
-        grid          = grid > 0u ? grid : 1u;
-        if (grid > want)
-            grid = want;
-        k_sample_walk<<<grid, 128, 0, stream>>>(p, sampler_counters);
-        // hard slots (>= kHardOrigins failed origins): group-parallel search; the grid is sized for a quarter of the batch being hard,
-        // groups are persistent (a larger share just takes more rounds)
-        const uint32_t groups_per_block = 128u / p.group;
-        uint32_t want_h = ((uint32_t)p.sub_batch_size / 4u + groups_per_block - 1u) / groups_per_block;
-        want_h          = want_h > 0u ? want_h : 1u;
-        uint32_t grid_h = (uint32_t)(num_sms * (per_sm_h > 0 ? per_sm_h : 1)) / env_u32("NBVH_SAMPLER_HGRID_DIV", 1u);
-        grid_h          = grid_h > 0u ? grid_h : 1u;
-        if (grid_h > want_h)
-            grid_h = want_h;
-        k_sample_walk_hard<<<grid_h, 128, 0, stream>>>(p, sampler_counters + 3);
-        if ((e = cudaGetLastError()) != cudaSuccess)
-            return e;
-        k_sample_targets<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);
-        return cudaGetLastError();
-    }
     k_generate_batch<<<((uint32_t)p.sub_batch_size + 127u) / 128u, 128, 0, stream>>>(p);
     return cudaGetLastError();
 }

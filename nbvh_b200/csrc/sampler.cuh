@@ -27,17 +27,18 @@ struct SamplerParams {
     float current_max_loss;
     const nbvh_tree_cut_data *tree_cut;
     unsigned long long *counters;
-    // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes each, capacity = batch)
+    // two-pass generator (n_sub_batch == 1): items handed from k_sample_walk to k_sample_targets (48 bytes per slot and step)
     void *items;
-    uint32_t *item_count;
-    uint32_t hard_origins, group, next_a, next_c; // hard-slot search: threshold, lanes per slot, LCG map of 3 (group - 1) draws
-    uint2 *hard_slots;       // (slot, origins consumed) of slots handed to k_sample_walk_hard, capacity = batch
-    uint32_t *hard_count;    // their number
+    uint32_t n_steps;          // optimisation steps walked by one k_sample_walk launch (walk-ahead), >= 1
+    uint32_t rng_index_step;   // rng_index of step k = rng_index + k * rng_index_step  (step stride * batch size)
     uint32_t *dilation_unsafe; // set when a tree-cut node fails k_check_dilation_safe (-> guarded hoisted division in the walk)
-    float *node_keep; // survival_probability_scale * keep per tree-cut node (k_node_keep), capacity = tree-cut nodes
+    float *node_keep;          // survival_probability_scale * keep per tree-cut node (k_node_keep), capacity = tree-cut nodes
 };
 
-// sampler_counters: 8 device words owned by the context (cleared by every launch)
-cudaError_t launch_generate_batch(const SamplerParams &p, uint32_t *sampler_counters, int num_sms, cudaStream_t stream);
+// n_sub_batch > 1 (rays continuing through the tree-cut): one thread per sub-batch
+cudaError_t launch_generate_batch(const SamplerParams &p, int num_sms, cudaStream_t stream);
+// n_sub_batch == 1: the walk of p.n_steps steps (sampler_counters: 8 device words owned by the context), then per step the targets
+cudaError_t launch_sample_walk(const SamplerParams &p, uint32_t *sampler_counters, int num_sms, cudaStream_t stream);
+cudaError_t launch_sample_targets(const SamplerParams &p, uint32_t step_first_item, cudaStream_t stream);
 
 } // namespace nbvh

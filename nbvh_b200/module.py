@@ -442,6 +442,11 @@ class NeuralPathModule:
                                                                 _ptr(sampled_node_indices), C.c_float(current_max_loss),
                                                                 _ptr(tree_cut_data), _ptr(inputs), _ptr(targets), stream))
 
+    def sampler_walk_ahead(self, steps, step_stride=1):
+        """One walk launch serves the next `steps` optimisation steps (training_step, training_step + stride, ...): same samples, the
+        generator's rejection walks run at several slots per lane instead of 1.5 (nbvh_sampler_walk_ahead)."""
+        self._check(self._lib.nbvh_sampler_walk_ahead(self._h, int(steps), int(step_stride)))
+
     def training_forward_backward(self, inputs, targets, global_batch=None, per_sample_loss=None, loss_sum=None, stream=None):
         """Forward + composite loss + backward; leaves loss-scaled (x128) fp32 gradients in the gradient buffer."""
         n = inputs.shape[0]

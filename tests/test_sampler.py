@@ -110,6 +110,61 @@ def test_gpu_sampler_bit_exact_against_reference_kernel(gold, gpu_mod):
 
 
 @pytest.mark.gpu
+def test_gpu_sampler_walk_ahead_is_bit_identical_and_invalidates(gold, gpu_mod):
+    """nbvh_sampler_walk_ahead: one walk launch serves K consecutive steps (any stride).  Every step's outputs are bit for bit those of
+    K = 1 -- hence of the reference kernel for the golden steps --, also when the loss statistics change between the steps (they
+    only enter the roulette of the target pass), and the walked items are dropped when the tree-cut or a constant block changes."""
+    import nbvh_b200
+    mod, cut_dev, torch = gpu_mod
+    name, batch, log2_trav, steps, gx, gt, gn = next(cases(gold))
+    max_loss = float(gold["max_loss"])
+    mk = lambda: (torch.zeros(batch, dtype=torch.int32, device="cuda"), torch.zeros((batch, 9), dtype=torch.float32, device="cuda"),
+                  torch.zeros((batch, 8), dtype=torch.float32, device="cuda"))
+
+    def run(step_ids, stats, ahead, stride):
+        mod.sampler_walk_ahead(ahead, stride)
+        nodes, x, t = mk()
+        out = []
+        for s in step_ids:
+            mod.optimisation_data_generation(s, batch, 0, nodes, max_loss, stats[s % len(stats)], x, t)
+            torch.cuda.synchronize()
+            out.append((nodes.cpu().numpy().copy(), x.cpu().numpy().view(np.uint32).copy(), t.cpu().numpy().view(np.uint32).copy()))
+        return out
+
+    try:
+        # golden steps through a walk of 4 steps at once
+        got = run(range(steps), [cut_dev], 4, 1)
+        for s in range(steps):
+            assert (got[s][0].astype(np.uint32) == gn[s]).all() and (got[s][1] == gx[s]).all() and (got[s][2] == gt[s]).all()
+        # strided steps (data-parallel rank 1 of 3), statistics that differ from step to step
+        other = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()), seed=23)
+        other_dev = torch.from_numpy(other.view(np.uint8).reshape(-1).copy()).cuda()
+        ids = [1 + 3 * k for k in range(6)]
+        ref = run(ids, [cut_dev, other_dev], 1, 1)
+        got = run(ids, [cut_dev, other_dev], 4, 3)
+        for a, b in zip(ref, got):
+            assert all((u == v).all() for u, v in zip(a, b))
+        # a changed constant block (the sampling box scale) invalidates the walked items
+        mod.sampler_walk_ahead(8, 1)
+        nodes, x, t = mk()
+        mod.optimisation_data_generation(0, batch, 0, nodes, max_loss, cut_dev, x, t)
+        rc = mod.get_constants(nbvh_b200.CONST_RENDERER)
+        saved = mod.get_constants(nbvh_b200.CONST_RENDERER)
+        rc.sampling_bbox_scaling = saved.sampling_bbox_scaling * 1.25
+        mod.set_constants(nbvh_b200.CONST_RENDERER, rc)
+        mod.optimisation_data_generation(1, batch, 0, nodes, max_loss, cut_dev, x, t)
+        torch.cuda.synchronize()
+        changed = x.cpu().numpy().view(np.uint32).copy()
+        mod.sampler_walk_ahead(1, 1)
+        mod.optimisation_data_generation(1, batch, 0, nodes, max_loss, cut_dev, x, t)
+        torch.cuda.synchronize()
+        assert (x.cpu().numpy().view(np.uint32) == changed).all() and not (changed == gx[1]).all()
+        mod.set_constants(nbvh_b200.CONST_RENDERER, saved)
+    finally:
+        mod.sampler_walk_ahead(1, 1)
+
+
+@pytest.mark.gpu
 def test_gpu_sampler_feeds_training_step(gpu_mod):
     """generate -> training_step, the loop of NeuralBVHRenderer::optimisation step (neural_bvh_renderer.cu:113-260):
     the loss on freshly sampled Chess batches decreases from a fresh initialisation."""

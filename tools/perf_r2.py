@@ -81,6 +81,21 @@ def main():
     cut = nbvh_b200.procedural_tree_cut(len(mod.neural_bvh_nodes()), seed=11)
     cut_dev = torch.from_numpy(cut.view(np.uint8).reshape(-1).copy()).to(dev)
     out["sampler"] = {}
+    for ahead in (4, 16):  # walk-ahead: one walk launch per `ahead` steps
+        mod.sampler_walk_ahead(ahead, 1)
+        for log2b in (18, 15):
+            B = 1 << log2b
+            nodes = torch.zeros(B, dtype=torch.int32, device=dev)
+            tx_ = torch.zeros((B, 9), dtype=torch.float32, device=dev)
+            tt_ = torch.zeros((B, 8), dtype=torch.float32, device=dev)
+            step = [0]
+
+            def gen():
+                mod.optimisation_data_generation(step[0], B, 0, nodes, 1.0, cut_dev, tx_, tt_)
+                step[0] += 1
+            ms = timeit(gen, iters=2 * ahead, warmup=ahead)
+            out["sampler"]["2^%d_walk_ahead_%d" % (log2b, ahead)] = {"ms_per_step": ms, "Msamples_s": B / ms / 1e3}
+    mod.sampler_walk_ahead(1, 1)
     for log2b in (18, 16, 15):
         B = 1 << log2b
         nodes = torch.zeros(B, dtype=torch.int32, device=dev)
