@@ -481,6 +481,8 @@ def main():
         tt = torch.zeros((train_B, out_dims), dtype=torch.float32, device=dev)
         train_steps = max(5, min(args.steps, 50))
         step_no = [0]
+        walk_ahead = 16
+        mod.sampler_walk_ahead(walk_ahead, world)  # one walk launch serves 16 steps of this rank (training_step = step * world + rank)
 
         def run_steps(B_local, B_global, n, what="step"):
             sx, st_, sn = tx[:B_local], tt[:B_local], nodes_dev[:B_local]
@@ -493,7 +495,7 @@ def main():
                     mod.optimizer_step(stream=stream.cuda_stream)
 
         def time_steps(B_local, B_global, what="step"):
-            run_steps(B_local, B_global, 3, what)
+            run_steps(B_local, B_global, walk_ahead - step_no[0] % walk_ahead + 3, what)  # warm-up; the timed steps start mid-group
             barrier()
             te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             te0.record(stream)
@@ -700,7 +702,8 @@ def main():
             stg = train["stage"]
             n_par = float(mod.n_params())
             kern = {
-                "sample_generation": {"ms": train["gen_ms"], "what": "k_node_keep + k_sample_walk + k_sample_targets (K10)"},
+                "sample_generation": {"ms": train["gen_ms"], "what": "K10 per step: k_node_keep + k_sample_targets, plus 1/16 of a k_sample_walk "
+                                                                      "launch that walks the slots of 16 steps (nbvh_sampler_walk_ahead)"},
                 "k_encode_features": {"ms": stg["encode"], "bound": "hbm", "achieved": 1536.0 * B / (stg["encode"] * 1e-3) / 1e9, "peak": peak,
                                       "unit": "GB/s", "algorithmic": "1536 B of table gathers per sample"},
                 "k_train_mlp": {"ms": stg["mlp"], "bound": "tensor", "achieved": 113664.0 * B / (stg["mlp"] * 1e-3) / 1e12, "peak": tensor_peak,

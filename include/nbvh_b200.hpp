@@ -104,6 +104,7 @@ public:
         check(nbvh_optimisation_data_generation(m_ctx, training_step, batch_size, log2_bvh_max_traversals, sampled_node_indices,
                                                 current_max_loss, tree_cut_data, inputs, targets, stream));
     }
+    void sampler_walk_ahead(uint32_t steps, uint32_t step_stride = 1) { check(nbvh_sampler_walk_ahead(m_ctx, steps, step_stride)); }
     float training_step(const float *in, const float *target, uint32_t batch, float *per_sample_loss = nullptr, void *stream = nullptr)
     {
         float loss = 0.f;

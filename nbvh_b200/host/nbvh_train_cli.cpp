@@ -237,6 +237,13 @@ int main(int argc, char **argv)
         bool all_lods_assigned = false;
         for (uint32_t s = 0; s < steps; ++s) {
             timer.start_frame(s);
+            // walk-ahead of the sample generator: up to 16 steps per walk launch, not past the next scheduled split
+            uint32_t ahead = 16;
+            if (tree_cut_learning && (int)s <= sched.last_split_iteration) {
+                const uint32_t iv = (uint32_t)std::max(1, sched.splitting_interval);
+                ahead = std::min(ahead, ((s + iv - 1u) / iv) * iv - s + 1u);
+            }
+            mod.sampler_walk_ahead(ahead, (uint32_t)world);
             // the sampler's RNG is keyed by training_step * batch + slot: step * world + rank gives every rank its own global slots
             mod.optimisation_data_generation(s * (uint32_t)world + (uint32_t)rank, B_local, log2_trav, sampled, s == 0 ? 0.f : max_node_loss,
                                              mod.tree_cut_data(), inputs, targets);

@@ -101,10 +101,18 @@ class TreeCutLearner:
         self.step_no = 0
         self.tree_cut_learning = True
         self.all_lods_assigned = False
+        self.walk_ahead = 16
 
     def step(self, stream=None):
         from ._capi import CONST_RENDERER
         m = self.mod
+        # walk-ahead of the sample generator: up to 16 steps per walk launch, but not past the next scheduled split (a split changes the
+        # tree-cut, and with it the walks of every later step)
+        ahead = self.walk_ahead
+        if self.tree_cut_learning and self.step_no <= self.sched.last_split_iteration:
+            iv = max(1, self.sched.splitting_interval)
+            ahead = min(ahead, ((self.step_no + iv - 1) // iv) * iv - self.step_no + 1)
+        m.sampler_walk_ahead(max(1, ahead), self.world)
         current_max_loss = 0.0 if self.step_no == 0 else self.max_node_loss
         # the sampler's RNG is keyed by training_step * batch + slot: step * world + rank gives every rank its own global slots
         m.optimisation_data_generation(self.step_no * self.world + self.rank, self.batch, self.log2_trav, self.sampled, current_max_loss,
