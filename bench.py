@@ -479,9 +479,9 @@ def main():
         nodes_dev = torch.zeros(train_B, dtype=torch.int32, device=dev)
         tx = torch.zeros((train_B, in_dims), dtype=torch.float32, device=dev)
         tt = torch.zeros((train_B, out_dims), dtype=torch.float32, device=dev)
-        train_steps = max(5, min(args.steps, 50))
-        step_no = [0]
         walk_ahead = 16
+        train_steps = max(walk_ahead, min(args.steps, 48) // walk_ahead * walk_ahead)  # whole walk-ahead groups inside the timed region
+        step_no = [0]
         mod.sampler_walk_ahead(walk_ahead, world)  # one walk launch serves 16 steps of this rank (training_step = step * world + rank)
 
         def run_steps(B_local, B_global, n, what="step"):
@@ -495,7 +495,7 @@ def main():
                     mod.optimizer_step(stream=stream.cuda_stream)
 
         def time_steps(B_local, B_global, what="step"):
-            run_steps(B_local, B_global, walk_ahead - step_no[0] % walk_ahead + 3, what)  # warm-up; the timed steps start mid-group
+            run_steps(B_local, B_global, (walk_ahead - step_no[0] % walk_ahead) % walk_ahead + walk_ahead, what)  # warm-up to a group boundary
             barrier()
             te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             te0.record(stream)
