@@ -89,8 +89,11 @@ def build_host():
 def build_variant(name, defines):
     """A/B experiments on the GPU box: the same sources with extra -D switches -> libnbvh_b200_<name>.so, selected at
     load time with NBVH_B200_LIB=<path> (development only; the product library is libnbvh_b200.so)."""
+    import shutil
     out = os.path.join(HERE, "libnbvh_b200_%s.so" % name)
-    return _compile_and_link(out, defines=defines, tag="variant_" + name, force=True)
+    _compile_and_link(out, defines=defines, tag="variant_" + name, force=True)
+    shutil.rmtree(os.path.join(OBJ_DIR, "variant_" + name), ignore_errors=True)  # the repo snapshot sent to the GPU box is size-limited
+    return out
 
 
 if __name__ == "__main__":

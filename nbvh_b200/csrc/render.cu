@@ -33,15 +33,6 @@ namespace nbvh {
 constexpr int kNeuralTiles   = NBVH_NEURAL_TILES;        // 128-lane tiles per CTA
 constexpr int kNeuralThreads = kNeuralTiles * kTileRows;
 constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
-#ifndef NBVH_LOOK_AHEAD
-#define NBVH_LOOK_AHEAD 1 // drain-phase look-ahead of k_neural (bit-exact speculation on free tile rows); 0 = one query per ray and pass
-#endif
-#ifndef NBVH_MAX_LOOK_AHEAD
-#define NBVH_MAX_LOOK_AHEAD 3
-#endif
-constexpr int kMaxLookAhead = NBVH_MAX_LOOK_AHEAD; // look-ahead intervals per ray when the tile has free rows
-// n_q query rows hand out n_q * min(kMaxLookAhead, (128 - n_q) / n_q) records: at most 128 * k / (k + 1) (n_q = 128 / (k + 1))
-constexpr int kLookAheadRecords = 128 * NBVH_MAX_LOOK_AHEAD / (NBVH_MAX_LOOK_AHEAD + 1);
 #ifndef NBVH_PHASE_TIMING
 #define NBVH_PHASE_TIMING 0 // development builds: per-phase SM-cycle sums of k_neural (tools/perf_r2.py prints them)
 #endif
@@ -230,12 +221,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
-#if NBVH_LOOK_AHEAD
-    // drain-phase look-ahead (below): per tile row one 32-byte record -- in: segment end points + interval of a look-ahead query,
-    // out: its decoded result -- and the per-warp query counts of the current iteration
-    __shared__ float4 s_la[kNeuralTiles][kLookAheadRecords][2];
-    __shared__ uint32_t s_cnt[kNeuralThreads / 32];
-#endif
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles);
     const uint32_t tmem_base = cta_setup<kNeuralTiles>(nc, smem, lay);
     const uint32_t tile      = threadIdx.x / kTileRows;
@@ -263,9 +248,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_PHASE_TIMING
     unsigned long long ph[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
     uint32_t iters_drain = 0u;
-#endif
-#if NBVH_LOOK_AHEAD
-    uint32_t q_rank = 0u, f_rank = 0u, n_la = 0u, n_q_tile = 0u;
 #endif
     for (;;) {
 #if NBVH_PHASE_TIMING
@@ -346,92 +328,30 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #endif
         // ---------------- tile-wide agreement: anything to infer?  anything left at all?
         {
-            const uint32_t qmask_w = __ballot_sync(0xFFFFFFFFu, s.have_query);
-            const uint32_t q    = qmask_w ? 1u : 0u;
+            const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
             const uint32_t live = (__any_sync(0xFFFFFFFFu, s.have_ray) || !exhausted) ? 2u : 0u;
-            if (lane == 0) {
+            if (lane == 0)
                 s_flags[warp] = q | live | (exhausted ? 0u : 4u); // bit 2: this warp can still refill from the queue
-#if NBVH_LOOK_AHEAD
-                s_cnt[warp] = (uint32_t)__popc(qmask_w);
-#endif
-            }
             named_bar_sync(t.bar_id, kTileRows);
             uint32_t f = 0;
 #pragma unroll
             for (int w = 0; w < kTileRows / 32; ++w)
                 f |= s_flags[tile * (kTileRows / 32) + w];
-#if NBVH_LOOK_AHEAD
-            uint32_t n_q = 0, q_before = 0;
-#pragma unroll
-            for (int w = 0; w < kTileRows / 32; ++w) {
-                const uint32_t c = s_cnt[tile * (kTileRows / 32) + w];
-                q_before += (uint32_t)w < (warp % (kTileRows / 32)) ? c : 0u;
-                n_q += c;
-            }
-            q_rank = q_before + (uint32_t)__popc(qmask_w & ((1u << lane) - 1u));                                          // among the tile's query lanes
-            f_rank = (warp % (kTileRows / 32)) * 32u - q_before + (uint32_t)__popc(~qmask_w & ((1u << lane) - 1u));       // among its free lanes
-            // only in the drain (no warp of the tile can refill any more) and when at least half of the rows are free
-            n_la = (!(f & 4u) && n_q > 0u && 2u * n_q <= (uint32_t)kTileRows) ? min((uint32_t)kMaxLookAhead, ((uint32_t)kTileRows - n_q) / n_q) : 0u;
-            n_q_tile = n_q;
-#endif
             named_bar_sync(t.bar_id, kTileRows);
             if ((f & 3u) == 0u)
                 break;
             if (!(f & 1u))
                 continue;
         }
-#if NBVH_LOOK_AHEAD
-        // ---------------- drain-phase look-ahead.  The queries of one ray form a dependent chain (the walk resumes with the hit found
-        // so far), and once the queue is empty the launch is a tail of such chains at falling tile fill (55 % of the
-        // 1080p launch).  Every lane with a pending interval walks on to its next n_la intervals -- with the closest t it knows NOW --
-        // and hands them to free rows of the tile; after the network pass it consumes the results in walk order and drops those whose
-        // interval the in-order walk would not have returned (entry not nearer than the then-closest hit).  Pruning only removes
-        // intervals from the in-order sequence and never reorders it, and the hit update is a minimum, so the final hit is
-        // bit-identical; the chain is n_la + 1 times shorter, paid with rows that would have idled.
-        uint32_t n_mine = 0u;
-        bool helper     = false;
-        if (n_la) {
-            if (s.have_query) {
-                for (uint32_t j = 0; j < n_la; ++j) {
-                    float mint, maxt;
-                    uint32_t node;
-                    if (s.nss <= 0 || !nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, mint, maxt, node, cnt_nbvh)) {
-                        s.nss = 0; // the walk ended (or overflowed its stack, which also ends it)
-                        break;
-                    }
-                    float eo[3], ei[3];
-                    encode_endpoints(p.enc, s.ray, mint, maxt, eo, ei);
-                    s_la[tile][q_rank * n_la + j][0] = make_float4(eo[0], eo[1], eo[2], ei[0]);
-                    s_la[tile][q_rank * n_la + j][1] = make_float4(ei[1], ei[2], mint, maxt);
-                    ++n_mine;
-                }
-                for (uint32_t j = n_mine; j < n_la; ++j) // unused records of this lane: no query
-                    s_la[tile][q_rank * n_la + j][1] = make_float4(0.f, 0.f, 1.f, 0.f);
-            }
-            named_bar_sync(t.bar_id, kTileRows);
-            if (!s.have_query && f_rank < n_q_tile * n_la) {
-                const float4 b = s_la[tile][f_rank][1];
-                helper         = b.z <= b.w;
-            }
-        }
-#endif
         // ---------------- segment encoding + hash grid -> A tile (a8, a9)
 #if NBVH_PHASE_TIMING
         const long long pt2 = clock64();
 #endif
         {
             float eo[3] = {0.f, 0.f, 0.f}, ei[3] = {0.f, 0.f, 0.f};
-            bool row_valid = s.have_query;
             if (s.have_query)
                 encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
-#if NBVH_LOOK_AHEAD
-            if (helper) {
-                const float4 a0 = s_la[tile][f_rank][0], a1 = s_la[tile][f_rank][1];
-                eo[0] = a0.x, eo[1] = a0.y, eo[2] = a0.z, ei[0] = a0.w, ei[1] = a1.x, ei[2] = a1.y;
-                row_valid = true;
-            }
-#endif
-            encode_rows_coop(nc, p.enc, t.a_tile, row & ~31u, lane, eo, ei, row_valid);
+            encode_rows_coop(nc, p.enc, t.a_tile, row & ~31u, lane, eo, ei, s.have_query);
         }
         fence_proxy_async_smem();
 #if NBVH_PHASE_TIMING
@@ -449,20 +369,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
             iters_drain += pdr ? 1u : 0u;
         }
 #endif
-#if NBVH_LOOK_AHEAD
-        if (n_la) {
-            if (helper) { // the decoded result of the look-ahead query of this row: (t or FLT_MAX, interval entry, normal, albedo)
-                const float4 in1 = s_la[tile][f_rank][1];
-                float t_hit, nrm[3];
-                if (!decode_hit(p.dec, y[0], y[1], in1.z, in1.w, kPath ? p.ray_depth : 1u, t_hit))
-                    t_hit = FLT_MAX;
-                decode_normal(y[2], y[3], y[4], nrm);
-                s_la[tile][f_rank][0] = make_float4(t_hit, in1.z, nrm[0], nrm[1]);
-                s_la[tile][f_rank][1] = make_float4(nrm[2], y[5], y[6], y[7]);
-            }
-            named_bar_sync(t.bar_id, kTileRows);
-        }
-#endif
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
@@ -472,20 +378,6 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 decode_normal(y[2], y[3], y[4], s.h.n_or_uv);
                 s.h.alb_or_ids[0] = y[5], s.h.alb_or_ids[1] = y[6], s.h.alb_or_ids[2] = y[7];
             }
-#if NBVH_LOOK_AHEAD
-            for (uint32_t j = 0; j < n_mine; ++j) { // the look-ahead intervals, in walk order
-                const float4 r0 = s_la[tile][q_rank * n_la + j][0], r1 = s_la[tile][q_rank * n_la + j][1];
-                if (!(r0.y < s.h.best_t))
-                    continue; // the in-order walk (ray.maxt = closest t so far) would have skipped this leaf
-                ++cnt_q;
-                if (r0.x != FLT_MAX && r0.x < s.h.best_t) {
-                    s.h.best_t    = r0.x;
-                    s.h.valid_hit = 1u;
-                    s.h.n_or_uv[0] = r0.z, s.h.n_or_uv[1] = r0.w, s.h.n_or_uv[2] = r1.x;
-                    s.h.alb_or_ids[0] = r1.y, s.h.alb_or_ids[1] = r1.z, s.h.alb_or_ids[2] = r1.w;
-                }
-            }
-#endif
             s.have_query = false;
         }
     }
