@@ -238,3 +238,42 @@ def test_library_communicator_with_one_rank_leaves_the_step_unchanged(env):
     assert rel(out[1][0].cpu().numpy(), out[0][0].cpu().numpy()) < 1e-5
     assert abs(out[1][1] - out[0][1]) <= 1e-5 * abs(out[0][1])
     assert (out[1][2] != out[0][2]).mean() < 1e-3
+
+
+def test_learning_rate_decay_on_the_device(env, oracle):
+    """ExponentialDecay on the device (k_adam's lr = learning_rate * decay_base^k; exponential_decay.h:60-71): decay_start 20,
+    decay_interval 10, 45 steps.  Every step the oracle's Adam gets the DEVICE gradients, so only the optimiser is compared: the
+    parameters stay bit-identical on > 99.99 % of the entries through all three decays, and the largest parameter change of a step
+    drops by the decay factor at steps 20, 30 and 40 (constant gradients' updates are lr-proportional)."""
+    import copy
+    import nbvh_b200
+    torch = env["torch"]
+    cfg = copy.deepcopy(env["cfg"])
+    cfg["neural_bvh_renderer"]["neural_module"]["optimizer"] = {"type": "Adam", "learning_rate": 1e-2, "decay_start": 20, "decay_interval": 10,
+                                                               "decay_base": 0.33}
+    mod = nbvh_b200.NeuralPathModule(cfg)
+    mod.load_params(env["p"])
+    tr = oracle.Trainer(cfg, env["p"])
+    xs = [torch.from_numpy(env["tin"][k]).cuda() for k in range(env["nb"])]
+    ts = [torch.from_numpy(env["tgt"][k]).cuda() for k in range(env["nb"])]
+    grads = mod.gradient_buffer()
+    prev = mod.get_params().view(np.float16).astype(np.float32)
+    step_max = []
+    for s_ in range(45):
+        mod.training_forward_backward(xs[s_ % env["nb"]], ts[s_ % env["nb"]])
+        torch.cuda.synchronize()
+        tr.grads[:] = grads.cpu().numpy()
+        tr.optimizer_step()
+        mod.optimizer_step()
+        torch.cuda.synchronize()
+        got = mod.get_params()
+        assert (got == tr.params).mean() > 0.9999, s_
+        cur = got.view(np.float16).astype(np.float32)
+        step_max.append(float(np.abs(cur[:N_MLP] - prev[:N_MLP]).max()))
+        prev = cur
+    mod.close()
+    # Adam's update is <= lr in magnitude and reaches it on some weight every step: the per-step maximum tracks the learning rate
+    lr = np.array(step_max)
+    for lo, hi, factor in ((10, 20, 1.0), (20, 30, 0.33), (30, 40, 0.33 ** 2), (40, 45, 0.33 ** 3)):
+        band = lr[lo:hi]
+        assert 0.5 * 1e-2 * factor < band.max() <= 1.3 * 1e-2 * factor, (lo, hi, band.max())

@@ -103,3 +103,56 @@ def test_gpu_trace_rays_equals_render_hit_records(synthetic):
     b = mod.trace_rays(o, d, ray_depth=1).cpu().numpy().view(nbvh_b200.HIT_DTYPE)
     assert a.tobytes() == b.tobytes()
     mod.close()
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_deep_cut_matches_oracle(oracle):
+    """BASELINE config 5 at the size bench.py --sweep times: the 10.38 M-triangle instanced scene with its depth-17 tree-cut (262,143
+    nodes, 131,072 neural leaves).  A 2^16-ray sample of the benched batch: the ordered leaf-interval lists (counts, node ids, entry /
+    exit parameters) are BIT-EXACT against the oracle's walk of the same deep cut, and the hit records of nbvh_trace_rays agree with
+    the oracle's per-ray restatement like on the small scenes (kinds up to the visibility-threshold tolerance, neural t within the
+    network tolerance, misses bit-exact)."""
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, nbvh, tlas, ti, blas, info = nbvh_b200.synthetic_instanced_scene(device="cuda")
+    assert info["neural_leaves"] == 1 << 17 and len(nbvh) == (1 << 18) - 1 and info["triangles"] > 10_000_000
+    mod = nbvh_b200.NeuralPathModule(cfg)
+    mod.set_neural_bvh(nbvh)
+    mod.set_scene(tlas, ti, blas)
+    rng = np.random.default_rng(1337)
+    n_mlp = 64 * 96 + 3 * 64 * 64 + 16 * 64
+    p = np.zeros(mod.n_params(), np.float16)
+    p[:n_mlp] = (rng.standard_normal(n_mlp) * 0.2).astype(np.float16)
+    p[n_mlp:] = (rng.standard_normal(len(p) - n_mlp) * 0.7).astype(np.float16)
+    params = p.view(np.uint16)
+    mod.load_params(params)
+    n = 1 << 16
+    o, d = nbvh_b200.synthetic_ray_batch(nbvh[0], n, seed=42, device="cuda")
+    oc, dc = o.cpu().numpy(), d.cpu().numpy()
+    const = oracle.config_constants(cfg, nbvh)
+    # ---- interval lists on the deep cut: bit-exact
+    MAX_IV = 32
+    cnt, node, mint, maxt = mod.trace_intervals(o, d, MAX_IV)
+    cnt_c, node_c, mint_c, maxt_c, _ = oracle.trace_intervals(nbvh, const, oc, dc, MAX_IV)
+    assert (cnt.cpu().numpy().astype(np.uint32) == cnt_c).all()
+    m = np.arange(MAX_IV)[None, :] < np.minimum(cnt_c, MAX_IV)[:, None]
+    assert m.sum() > 4 * n  # several leaves per ray on this cut
+    assert (node.cpu().numpy().astype(np.uint32)[m] == node_c[m]).all()
+    assert (mint.cpu().numpy().view(np.uint32)[m] == mint_c.view(np.uint32)[m]).all()
+    assert (maxt.cpu().numpy().view(np.uint32)[m] == maxt_c.view(np.uint32)[m]).all()
+    # ---- hit records of the ray-batch query
+    net = oracle.make_net(cfg, params)
+    scene = oracle.Scene(tlas, ti, blas)
+    hits = mod.trace_rays(o, d, ray_depth=1).cpu().numpy().view(nbvh_b200.HIT_DTYPE)
+    ref, _ = oracle.trace_rays(scene, nbvh, const, net, oc, dc, ray_depth=1)
+    same = hits["valid_hit"] == ref["valid_hit"]
+    assert (~same).sum() <= max(3, FLIP_RATE * n), "%d hit-kind flips" % (~same).sum()
+    hit = same & (ref["valid_hit"] == 1)
+    assert hit.sum() > n // 20
+    dt = np.abs(hits["t"][hit] - ref["t"][hit])
+    assert np.quantile(dt, 0.99) <= T_TOL
+    miss = same & (ref["valid_hit"] == 0)
+    assert (hits["t"][miss].view(np.uint32) == ref["t"][miss].view(np.uint32)).all()
+    mod.close()
