@@ -47,7 +47,7 @@ int nbvh_blas_intersect(nbvh_ctx *ctx, uint32_t blas_idx, const float *o, const 
     if (!ctx->scene_set || blas_idx >= ctx->scene.n_blas)
         return fail(ctx, NBVH_ERR_STATE, "scene not set or BLAS index out of range");
     KernelTimer kt(ctx, (cudaStream_t)stream);
-    CU_TRY(ctx, launch_blas_intersect(ctx->scene.blas[blas_idx], ctx->blas_safe[blas_idx] ? 1u : 0u, o, d, maxt, n, t, u, v, prim, ctx->d_counters,
+    CU_TRY(ctx, launch_blas_intersect(host_blas(ctx, blas_idx), ctx->blas_safe[blas_idx] ? 1u : 0u, o, d, maxt, n, t, u, v, prim, ctx->d_counters,
                                       (cudaStream_t)stream));
     kt.stop();
     return NBVH_OK;
@@ -353,6 +353,7 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
             pc.attr[i].material_map  = b.material_map;
             pc.attr[i].num_materials = b.material_map ? b.num_materials : 0u;
         }
+        pc.attr_ext  = ctx->d_attr_ext;
         pc.materials = reinterpret_cast<const MaterialPod *>(ctx->materials);
         pc.textures  = reinterpret_cast<const cudaTextureObject_t *>(ctx->textures);
         pc.neural_bvh_idx          = ctx->bvh_const.neural_bvh_idx;
@@ -605,16 +606,26 @@ int nbvh_build_tlas(nbvh_ctx *ctx, const nbvh_cuda_blas *mesh_bvhs_device, uint3
     DeviceGuard device_guard(ctx);
     if (!ctx || !mesh_bvhs_device || !tlas_nodes_out || !blas_indices_out || num_meshes == 0 || (n_neural && !neural_meshes_host))
         return NBVH_ERR_INVALID_ARG;
-    if (num_meshes > (uint32_t)kMaxBlas)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "more than 16 BLAS");
-    uint32_t mask = 0;
+    std::vector<uint32_t> flags(num_meshes, 0u);
     for (uint32_t i = 0; i < n_neural; i++) {
         if (neural_meshes_host[i] >= num_meshes)
             return fail(ctx, NBVH_ERR_INVALID_ARG, "neural mesh index out of range");
-        mask |= 1u << neural_meshes_host[i];
+        flags[neural_meshes_host[i]] = 1u;
     }
-    CU_TRY(ctx, launch_build_tlas(mesh_bvhs_device, num_meshes, mask, reinterpret_cast<float4 *>(tlas_nodes_out), blas_indices_out,
-                                  (cudaStream_t)stream));
+    // scratch: the sweep's per-mesh arrays + the neural flags (shares the grow-only scratch of nbvh_build_blas)
+    const size_t ws_bytes = build_tlas_workspace_bytes(num_meshes), bytes = ws_bytes + (size_t)num_meshes * sizeof(uint32_t);
+    if (ctx->build_ws_bytes < bytes) {
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->d_build_ws);
+        ctx->d_build_ws = nullptr, ctx->build_ws_bytes = 0;
+        CU_TRY(ctx, cudaMalloc(&ctx->d_build_ws, bytes));
+        ctx->build_ws_bytes = bytes;
+    }
+    uint32_t *flags_dev = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ctx->d_build_ws) + ws_bytes);
+    CU_TRY(ctx, cudaMemcpyAsync(flags_dev, flags.data(), flags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream)); // `flags` leaves scope
+    CU_TRY(ctx, launch_build_tlas(mesh_bvhs_device, num_meshes, flags_dev, ctx->d_build_ws, reinterpret_cast<float4 *>(tlas_nodes_out),
+                                  blas_indices_out, (cudaStream_t)stream));
     return NBVH_OK;
 }
 

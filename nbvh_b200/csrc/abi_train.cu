@@ -43,7 +43,7 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.nbvh.mint_eps   = bc.learning_mint_epsilon;
     sp.nbvh.maxt_eps   = bc.learning_maxt_epsilon;
     sp.nbvh.predilated = 0u;
-    sp.blas            = ctx->scene.blas[bc.neural_bvh_idx];
+    sp.blas            = host_blas(ctx, bc.neural_bvh_idx);
     sp.attr.normals       = nb.normals;
     sp.attr.texcoords     = nb.texcoords;
     sp.attr.material_ids  = nb.material_ids;
@@ -349,7 +349,7 @@ static int tree_cut_decide(nbvh_ctx *ctx, uint32_t num_splits, float *max_node_l
     const uint32_t n        = ctx->nbvh_nodes;
     const uint32_t blas_idx = ctx->bvh_const.neural_bvh_idx;
     CU_TRY(ctx, launch_tree_cut_decide_and_split(ctx->d_nbvh, n, ctx->nbvh_capacity, ctx->d_tree_cut, ctx->d_node_map,
-                                                 ctx->scene.blas[blas_idx].nodes, num_splits, (uint32_t)ctx->bvh_const.current_learned_lod,
+                                                 host_blas(ctx, blas_idx).nodes, num_splits, (uint32_t)ctx->bvh_const.current_learned_lod,
                                                  ctx->d_tc_workspace, ctx->tc_workspace_bytes, ctx->d_tc_result, st));
     TreeCutResult r;
     CU_TRY(ctx, cudaMemcpyAsync(&r, ctx->d_tc_result, sizeof(r), cudaMemcpyDeviceToHost, st));

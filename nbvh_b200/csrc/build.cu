@@ -303,28 +303,31 @@ struct BlasDescDev { // layout of nbvh_cuda_blas (include/nbvh_b200.h)
     const float4 *nodes;
 };
 
-constexpr int kMaxTlasMeshes = 32;
-
 __device__ inline float half_area(const float *lo, const float *hi)
 {
     const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, uint32_t neural_mask, float4 *nodes, uint32_t *blas_indices)
+// workspace per mesh: lo[3], hi[3], right_area (7 floats), order, neural flag, 3 words of task stack (5 uint32)
+size_t build_tlas_workspace_bytes(uint32_t n) { return (size_t)n * (7u * sizeof(float) + 5u * sizeof(uint32_t)); }
+
+__global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, const uint32_t *neural_flags, float *ws_f, uint32_t *ws_u, float4 *nodes,
+                             uint32_t *blas_indices)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
-    float lo[kMaxTlasMeshes][3], hi[kMaxTlasMeshes][3];
-    uint32_t order[kMaxTlasMeshes];
+    float *lo = ws_f, *hi = ws_f + 3u * n, *right_area = ws_f + 6u * n;
+    uint32_t *order = ws_u;
     for (uint32_t i = 0; i < n; i++) {
         const float4 a = meshes[i].nodes[0], b = meshes[i].nodes[1]; // root_bbox() of the mesh's BLAS
-        lo[i][0] = a.x, lo[i][1] = a.y, lo[i][2] = a.z, hi[i][0] = b.x, hi[i][1] = b.y, hi[i][2] = b.z;
+        lo[3 * i] = a.x, lo[3 * i + 1] = a.y, lo[3 * i + 2] = a.z, hi[3 * i] = b.x, hi[3 * i + 1] = b.y, hi[3 * i + 2] = b.z;
         order[i] = i;
     }
     struct Task {
         uint32_t node, begin, end;
-    } stack[kMaxTlasMeshes];
+    };
+    Task *stack     = reinterpret_cast<Task *>(ws_u + 2u * n); // depth-first with the smaller... at most n pending tasks
     int ss          = 0;
     uint32_t n_nodes = 1;
     stack[ss++]     = {0u, 0u, n};
@@ -334,11 +337,11 @@ __global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, uint32_t neu
         float blo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (uint32_t i = t.begin; i < t.end; i++)
             for (int c = 0; c < 3; c++)
-                blo[c] = fminf(blo[c], lo[order[i]][c]), bhi[c] = fmaxf(bhi[c], hi[order[i]][c]);
+                blo[c] = fminf(blo[c], lo[3 * order[i] + c]), bhi[c] = fmaxf(bhi[c], hi[3 * order[i] + c]);
         if (k == 1) {
             const uint32_t mesh = order[t.begin];
             nodes[2 * t.node]     = make_float4(blo[0], blo[1], blo[2], __uint_as_float(t.begin));
-            nodes[2 * t.node + 1] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float((neural_mask >> mesh) & 1u ? 2u : 1u));
+            nodes[2 * t.node + 1] = make_float4(bhi[0], bhi[1], bhi[2], __uint_as_float(neural_flags[mesh] ? 2u : 1u));
             continue;
         }
         int best_axis = 0;
@@ -348,25 +351,24 @@ __global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, uint32_t neu
             const int axis = pass < 3 ? pass : best_axis;
             for (uint32_t i = t.begin + 1; i < t.end; i++) { // insertion sort by centroid (stable: ties keep the mesh order)
                 const uint32_t m = order[i];
-                const float c    = lo[m][axis] + hi[m][axis];
+                const float c    = lo[3 * m + axis] + hi[3 * m + axis];
                 uint32_t j       = i;
-                while (j > t.begin && lo[order[j - 1]][axis] + hi[order[j - 1]][axis] > c)
+                while (j > t.begin && lo[3 * order[j - 1] + axis] + hi[3 * order[j - 1] + axis] > c)
                     order[j] = order[j - 1], --j;
                 order[j] = m;
             }
             if (pass == 3)
                 break;
-            float right_area[kMaxTlasMeshes];
             float rlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, rhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             for (uint32_t i = t.end; i-- > t.begin + 1;) {
                 for (int c = 0; c < 3; c++)
-                    rlo[c] = fminf(rlo[c], lo[order[i]][c]), rhi[c] = fmaxf(rhi[c], hi[order[i]][c]);
+                    rlo[c] = fminf(rlo[c], lo[3 * order[i] + c]), rhi[c] = fmaxf(rhi[c], hi[3 * order[i] + c]);
                 right_area[i - t.begin] = half_area(rlo, rhi);
             }
             float llo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             for (uint32_t s = 1; s < k; s++) { // s meshes on the left
                 for (int c = 0; c < 3; c++)
-                    llo[c] = fminf(llo[c], lo[order[t.begin + s - 1]][c]), lhi[c] = fmaxf(lhi[c], hi[order[t.begin + s - 1]][c]);
+                    llo[c] = fminf(llo[c], lo[3 * order[t.begin + s - 1] + c]), lhi[c] = fmaxf(lhi[c], hi[3 * order[t.begin + s - 1] + c]);
                 const float cost = half_area(llo, lhi) * (float)s + right_area[s] * (float)(k - s);
                 if (cost < best_cost)
                     best_cost = cost, best_axis = axis, best_split = s;
@@ -383,12 +385,16 @@ __global__ void k_build_tlas(const BlasDescDev *meshes, uint32_t n, uint32_t neu
         blas_indices[i] = order[i];
 }
 
-cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, uint32_t neural_mask, float4 *tlas_nodes, uint32_t *blas_indices,
-                              cudaStream_t stream)
+// workspace: build_tlas_workspace_bytes(num_meshes) of device memory; neural_flags: num_meshes device words (non-zero = neural mesh)
+cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, const uint32_t *neural_flags, void *workspace, float4 *tlas_nodes,
+                              uint32_t *blas_indices, cudaStream_t stream)
 {
-    if (num_meshes == 0 || num_meshes > (uint32_t)kMaxTlasMeshes)
+    if (num_meshes == 0)
         return cudaErrorInvalidValue;
-    k_build_tlas<<<1, 32, 0, stream>>>(reinterpret_cast<const BlasDescDev *>(mesh_bvhs_device), num_meshes, neural_mask, tlas_nodes, blas_indices);
+    float *ws_f    = reinterpret_cast<float *>(workspace);
+    uint32_t *ws_u = reinterpret_cast<uint32_t *>(ws_f + 7u * (size_t)num_meshes);
+    k_build_tlas<<<1, 32, 0, stream>>>(reinterpret_cast<const BlasDescDev *>(mesh_bvhs_device), num_meshes, neural_flags, ws_f, ws_u, tlas_nodes,
+                                       blas_indices);
     return cudaGetLastError();
 }
 

@@ -304,6 +304,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
     dp_release(ctx);
+    cudaFree(ctx->d_blas_ext), cudaFree(ctx->d_attr_ext);
     cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_counters);
     if (ctx->ahead_done)
         cudaEventDestroy(ctx->ahead_done);
@@ -443,8 +444,6 @@ int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
     DeviceGuard device_guard(ctx);
     if (!ctx || !s)
         return NBVH_ERR_INVALID_ARG;
-    if (s->num_meshes > (uint32_t)kMaxBlas)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "more than 16 BLAS");
     std::vector<nbvh_cuda_blas> blas(s->num_meshes);
     if (s->num_meshes)
         CU_TRY(ctx, cudaMemcpy(blas.data(), s->mesh_bvhs, sizeof(nbvh_cuda_blas) * s->num_meshes, cudaMemcpyDeviceToHost));
@@ -453,14 +452,36 @@ int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
     ctx->scene.tlas.blas_indices = s->blas_indices;
     ctx->scene.tlas.num_meshes   = s->num_meshes;
     ctx->scene.n_blas            = s->num_meshes;
+    std::vector<BlasConst> table(s->num_meshes);
+    std::vector<BlasAttr> attrs(s->num_meshes);
+    ctx->blas_safe.assign(s->num_meshes, 0);
     for (uint32_t i = 0; i < s->num_meshes; i++) {
-        ctx->scene.blas[i].nodes        = reinterpret_cast<const float4 *>(blas[i].nodes);
-        ctx->scene.blas[i].prim_indices = reinterpret_cast<const unsigned long long *>(blas[i].prim_indices);
-        ctx->scene.blas[i].vertices     = blas[i].vertices;
-        ctx->scene.blas[i].indices      = blas[i].indices;
-        int rc = check_nodes(ctx, ctx->scene.blas[i].nodes, blas[i].num_nodes, ctx->blas_safe[i]);
+        table[i].nodes        = reinterpret_cast<const float4 *>(blas[i].nodes);
+        table[i].prim_indices = reinterpret_cast<const unsigned long long *>(blas[i].prim_indices);
+        table[i].vertices     = blas[i].vertices;
+        table[i].indices      = blas[i].indices;
+        attrs[i].normals       = blas[i].normals;
+        attrs[i].texcoords     = blas[i].texcoords;
+        attrs[i].material_ids  = (blas[i].material_map && blas[i].num_materials) ? blas[i].material_ids : nullptr;
+        attrs[i].material_map  = blas[i].material_map;
+        attrs[i].num_materials = blas[i].material_map ? blas[i].num_materials : 0u;
+        if (i < (uint32_t)kMaxBlas)
+            ctx->scene.blas[i] = table[i];
+        bool safe = false;
+        int rc    = check_nodes(ctx, table[i].nodes, blas[i].num_nodes, safe);
         if (rc != NBVH_OK)
             return rc;
+        ctx->blas_safe[i] = safe ? 1 : 0;
+    }
+    // more meshes than fit the kernel parameters: the descriptors and shading attributes move to device tables
+    cudaFree(ctx->d_blas_ext), cudaFree(ctx->d_attr_ext);
+    ctx->d_blas_ext = nullptr, ctx->d_attr_ext = nullptr;
+    if (s->num_meshes > (uint32_t)kMaxBlas) {
+        CU_TRY(ctx, cudaMalloc(&ctx->d_blas_ext, table.size() * sizeof(BlasConst)));
+        CU_TRY(ctx, cudaMemcpy(ctx->d_blas_ext, table.data(), table.size() * sizeof(BlasConst), cudaMemcpyHostToDevice));
+        CU_TRY(ctx, cudaMalloc(&ctx->d_attr_ext, attrs.size() * sizeof(BlasAttr)));
+        CU_TRY(ctx, cudaMemcpy(ctx->d_attr_ext, attrs.data(), attrs.size() * sizeof(BlasAttr), cudaMemcpyHostToDevice));
+        ctx->scene.blas_ext = ctx->d_blas_ext;
     }
     {
         int rc = check_nodes(ctx, ctx->scene.tlas.nodes, s->num_tlas_nodes, ctx->tlas_safe);
@@ -475,6 +496,19 @@ int nbvh_set_scene(nbvh_ctx *ctx, const nbvh_scene_data *s)
 }
 
 } // extern "C"
+
+BlasConst nbvh_host::host_blas(const nbvh_ctx *ctx, uint32_t i)
+{
+    BlasConst b;
+    memset(&b, 0, sizeof(b));
+    if (i < ctx->blas_desc.size()) {
+        b.nodes        = reinterpret_cast<const float4 *>(ctx->blas_desc[i].nodes);
+        b.prim_indices = reinterpret_cast<const unsigned long long *>(ctx->blas_desc[i].prim_indices);
+        b.vertices     = ctx->blas_desc[i].vertices;
+        b.indices      = ctx->blas_desc[i].indices;
+    }
+    return b;
+}
 
 int nbvh_host::adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKind kind)
 {

@@ -10,6 +10,7 @@
 #include "sampler.cuh"
 #include "path.cuh"
 #include "treecut.cuh"
+#include "shading.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -145,7 +146,9 @@ struct nbvh_ctx {
     uint64_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
     bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
-    bool blas_safe[kMaxBlas] = {};
+    std::vector<uint8_t> blas_safe;   // per mesh: its BLAS nodes passed k_check_nodes
+    BlasConst *d_blas_ext = nullptr;  // device tables of the BLAS descriptors / shading attributes of scenes with more than kMaxBlas meshes
+    BlasAttr *d_attr_ext = nullptr;
     bool tlas_safe = false;
 
     // scene
@@ -235,6 +238,7 @@ EncodeConst make_encode_const(const nbvh_ctx *ctx);
 int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params);
 CameraConst make_camera_const(const nbvh_ctx *ctx);
 int adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKind kind);
+BlasConst host_blas(const nbvh_ctx *ctx, uint32_t i); // descriptor of mesh i (host copy: works for any mesh count)
 // comm.cu
 int dp_allreduce_bucket(nbvh_ctx *ctx, int bucket, float *ptr, size_t count, cudaStream_t st);
 int dp_join(nbvh_ctx *ctx, cudaStream_t st);

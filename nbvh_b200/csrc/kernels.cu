@@ -220,7 +220,7 @@ __device__ __forceinline__ void advance_ray(const RenderParams &p, LaneState &s,
                 return;
             }
         } else if (blas_idx < p.scene.n_blas) {
-            const TriHit h = blas_closest_hit(p.scene.blas[blas_idx], s.ray, 1e-4f, s.best_t, cnt_blas, cnt_tri);
+            const TriHit h = blas_closest_hit(scene_blas(p.scene, blas_idx), s.ray, 1e-4f, s.best_t, cnt_blas, cnt_tri);
             if (h.t < s.best_t) { // set_or_update_with_preliminary_its_data (path_module.h:150-175)
                 s.best_t        = h.t;
                 s.valid_hit     = 2u;

@@ -33,9 +33,25 @@ enum Counter {
 
 struct SceneConst {
     TlasConst tlas;
-    BlasConst blas[kMaxBlas];
+    BlasConst blas[kMaxBlas];  // the descriptors of scenes with up to kMaxBlas meshes travel in the kernel parameters ...
+    const BlasConst *blas_ext; // ... larger scenes (the reference's TLAS has no bound, cuda_backend.cpp:312-385) read a device table
     uint32_t n_blas;
 };
+
+__device__ __forceinline__ BlasConst scene_blas(const SceneConst &s, uint32_t i)
+{
+    if (s.blas_ext) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(s.blas_ext + i);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        BlasConst r;
+        r.nodes        = reinterpret_cast<const float4 *>(((unsigned long long)a.y << 32) | a.x);
+        r.prim_indices = reinterpret_cast<const unsigned long long *>(((unsigned long long)a.w << 32) | a.z);
+        r.vertices     = reinterpret_cast<const float *>(((unsigned long long)b.y << 32) | b.x);
+        r.indices      = reinterpret_cast<const uint32_t *>(((unsigned long long)b.w << 32) | b.z);
+        return r;
+    }
+    return s.blas[i];
+}
 
 // A ray with a pending neural leaf interval: pixel id, closest classical hit so far, the interval and the N-BVH stack
 // (a: pixel, best_t, valid_hit, u | b: v, blas_idx, prim, stack size | c: seg_mint, seg_maxt, -, - | st: 24 stack entries)
@@ -196,8 +212,9 @@ cudaError_t launch_prefetch_l2(const void *const *ptrs, const size_t *bytes, int
 size_t build_blas_workspace_bytes(uint32_t n_tris);
 cudaError_t launch_build_blas(const float *vertices, const uint32_t *indices, uint32_t n_tris, float4 *nodes, unsigned long long *prim_indices,
                               void *workspace, size_t workspace_bytes, uint32_t *max_depth_dev, cudaStream_t stream);
-cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, uint32_t neural_mask, float4 *tlas_nodes, uint32_t *blas_indices,
-                              cudaStream_t stream);
+size_t build_tlas_workspace_bytes(uint32_t num_meshes);
+cudaError_t launch_build_tlas(const void *mesh_bvhs_device, uint32_t num_meshes, const uint32_t *neural_flags, void *workspace, float4 *tlas_nodes,
+                              uint32_t *blas_indices, cudaStream_t stream);
 // LDR-FLIP (flip.cu)
 size_t flip_workspace_bytes(uint32_t w, uint32_t h);
 cudaError_t flip_set_ppd(float ppd, cudaStream_t stream);

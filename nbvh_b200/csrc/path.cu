@@ -55,7 +55,7 @@ __device__ __forceinline__ bool shade_and_scatter(const RenderParams &p, const P
         TriHit th;
         th.t = best_t, th.u = ph.h0.z, th.v = ph.h0.w, th.prim = __float_as_uint(ph.h1.z);
         const uint32_t mesh = __float_as_uint(ph.h1.y);
-        const ItsData its   = compute_its_data(p.scene.blas[mesh], pc.attr[mesh], pc.materials, pc.textures, th);
+        const ItsData its   = compute_its_data(scene_blas(p.scene, mesh), path_attr(pc, mesh), pc.materials, pc.textures, th);
         hit_pos = its.position, its_normal = its.sh_normal;
         const bool has_material = its.material_id != -1 && pc.materials;
         if (p.ignore_neural_blas && mesh == pc.neural_bvh_idx) {
@@ -195,7 +195,7 @@ k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
             if (is_neural && !p.ignore_neural_blas) {
                 neural = true;
             } else if (blas_idx < p.scene.n_blas) {
-                const TriHit th = blas_closest_hit(p.scene.blas[blas_idx], ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
+                const TriHit th = blas_closest_hit(scene_blas(p.scene, blas_idx), ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
                 if (th.t < h.best_t) {
                     h.best_t        = th.t;
                     h.valid_hit     = 2u;

@@ -5,7 +5,8 @@
 namespace nbvh {
 
 struct PathConst {
-    BlasAttr attr[kMaxBlas];       // shading attributes of every BLAS (CudaSceneData.tlas.mesh_bvhs[i])
+    BlasAttr attr[kMaxBlas];       // shading attributes of every BLAS (CudaSceneData.tlas.mesh_bvhs[i]) ...
+    const BlasAttr *attr_ext;      // ... or a device table when the scene has more than kMaxBlas meshes
     const MaterialPod *materials;  // CudaSceneData.materials
     const cudaTextureObject_t *textures;
     uint32_t neural_bvh_idx;       // bvh_const.neural_bvh_idx
@@ -17,6 +18,8 @@ struct PathConst {
     uint32_t force_constant_material, emission_eval;
     float constant_roughness, constant_specular, constant_metallic;
 };
+
+__device__ __forceinline__ BlasAttr path_attr(const PathConst &pc, uint32_t i) { return pc.attr_ext ? pc.attr_ext[i] : pc.attr[i]; }
 
 // path lists of one shade pass: in/hits_in (length *count_in, or the pixel count when null) -> survivors appended to out
 struct PathIo {

@@ -123,7 +123,7 @@ k_primary(const __grid_constant__ RenderParams p)
                 neural = true;
             } else if (blas_idx < p.scene.n_blas) {
                 // non_neural_bvh_intersection (path_inference_kernels.cu:195-222): ray.maxt = closest t so far
-                const TriHit th = blas_closest_hit(p.scene.blas[blas_idx], ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
+                const TriHit th = blas_closest_hit(scene_blas(p.scene, blas_idx), ray, 1e-4f, h.best_t, cnt_blas, cnt_tri);
                 if (th.t < h.best_t) { // set_or_update_with_preliminary_its_data (path_module.h:150-175)
                     h.best_t        = th.t;
                     h.valid_hit     = 2u;

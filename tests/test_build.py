@@ -104,7 +104,7 @@ def _one_triangle_mesh(rng):
     return dict(nodes=nodes, prim_ids=np.zeros(1, np.uint32), vertices=v.reshape(-1), indices=np.arange(3, dtype=np.uint32))
 
 
-@pytest.mark.parametrize("n_meshes", [1, 2, 5, 16])
+@pytest.mark.parametrize("n_meshes", [1, 2, 5, 16, 40, 300])
 def test_gpu_tlas_structure(synthetic, n_meshes):
     """TLASNode layout (tlas.cuh:64-68): 2n-1 nodes, adjacent children, every mesh in exactly one leaf whose box is the mesh's root box,
     interior boxes are the union of their children, neural meshes carry leaf type 2."""
@@ -163,3 +163,60 @@ def test_gpu_tlas_renders_like_host_tlas(synthetic):
     assert out[0][0].std() > 0
     assert (out[0][0].view(np.uint32) == out[1][0].view(np.uint32)).all()
     assert (out[0][1] == out[1][1]).all()
+
+
+def test_gpu_scene_with_more_than_16_meshes(synthetic):
+    """The reference's TLAS has no bound on the mesh count (cuda_backend.cpp:312-385).  The classical mesh of the synthetic scene is cut
+    into 40 meshes with their own device-built BLAS (41 meshes with the neural one: the descriptors no longer fit the kernel
+    parameters and travel through the device table, TLAS built on the device): the closest hits -- kind, t, and for neural hits normal
+    and albedo -- are bit-identical to the frame of the 2-mesh scene; classical hits name another (mesh, primitive) pair, of course."""
+    import torch
+    import nbvh_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg, nbvh, tlas, tlas_idx, blas = synthetic
+    w, h = cfg["cuda_scene"]["fb_size"]
+    neural_idx = int(tlas_idx[tlas["a"][tlas["b"] == 2][0]])
+    classical_idx = 1 - neural_idx
+    assert len(blas) == 2
+
+    def frame(meshes, t_nodes, t_idx, neural):
+        mod = nbvh_b200.NeuralPathModule(cfg)
+        mod.set_neural_bvh(nbvh)
+        if t_nodes is None:
+            mod.set_scene(None, None, meshes, neural_meshes=neural)
+        else:
+            mod.set_scene(t_nodes, t_idx, meshes)
+        mod.init_params(1337)
+        hits = mod.attach_hit_buffer(w * h)
+        mod.neural_render(0, 0)
+        torch.cuda.synchronize()
+        out = hits.cpu().numpy().view(nbvh_b200.HIT_DTYPE).copy()
+        mod.close()
+        return out
+
+    ref = frame(blas, tlas, tlas_idx, None)
+    # cut the classical mesh into 40 index ranges, one device-built BLAS each
+    c = blas[classical_idx]
+    verts = np.ascontiguousarray(c["vertices"], dtype=np.float32).reshape(-1, 3)
+    tris = np.ascontiguousarray(c["indices"], dtype=np.uint32).reshape(-1, 3)
+    builder = nbvh_b200.NeuralPathModule(cfg)
+    parts = []
+    for chunk in np.array_split(np.arange(len(tris)), 40):
+        v_t = torch.from_numpy(verts).cuda()
+        i_t = torch.from_numpy(tris[chunk].astype(np.int32)).cuda()
+        nodes, prim, _ = builder.build_blas(v_t, i_t)
+        torch.cuda.synchronize()
+        parts.append(dict(nodes=nodes.cpu().numpy().view(nbvh_b200.NODE_DTYPE).copy(), prim_ids=prim.cpu().numpy().astype(np.uint32),
+                          vertices=verts.reshape(-1), indices=tris[chunk].reshape(-1)))
+    builder.close()
+    meshes = parts[:7] + [blas[neural_idx]] + parts[7:]
+    got = frame(meshes, None, None, [7])
+    assert (ref["valid_hit"] == 2).sum() > 500 and (ref["valid_hit"] == 1).sum() > 500
+    assert (got["valid_hit"] == ref["valid_hit"]).all()
+    assert (got["t"].view(np.uint32) == ref["t"].view(np.uint32)).all()
+    neu = ref["valid_hit"] == 1
+    assert got[neu].tobytes() == ref[neu].tobytes()
+    cls = ref["valid_hit"] == 2
+    # barycentrics of the same triangle (a ray through a shared edge may report either neighbour: same t, other u / v)
+    assert (got["normal_or_uv"][cls].view(np.uint32) == ref["normal_or_uv"][cls].view(np.uint32)).all(axis=1).mean() > 0.999
