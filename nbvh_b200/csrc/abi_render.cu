@@ -235,6 +235,8 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
         return NBVH_ERR_INVALID_ARG;
     int rc = check_ready(ctx, true, true, true);
     if (rc == NBVH_OK)
+        rc = check_wavefront_modes(ctx);
+    if (rc == NBVH_OK)
         rc = refresh_dilated(ctx);
     if (rc != NBVH_OK)
         return rc;
@@ -260,10 +262,7 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     rp.nbvh  = make_nbvh_const(ctx, true);
     rp.scene = ctx->scene;
     rp.enc   = make_encode_const(ctx);
-    rp.dec.primary_thr         = ctx->pt_const.primary_visibility_threshold;
-    rp.dec.secondary_thr       = ctx->pt_const.secondary_visibility_threshold;
-    rp.dec.depth_epsilon       = ctx->pt_const.depth_epsilon;
-    rp.dec.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
+    rp.dec                     = make_decode_const(ctx);
     rp.ignore_neural_blas      = ctx->bvh_const.ignore_neural_blas;
     rp.max_depth               = (uint32_t)ctx->max_depth;
     rp.bg.envmap_eval          = ctx->scene_const.envmap_eval;
@@ -394,6 +393,8 @@ int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, u
         return NBVH_ERR_INVALID_ARG;
     int rc = check_ready(ctx, true, true, true);
     if (rc == NBVH_OK)
+        rc = check_wavefront_modes(ctx);
+    if (rc == NBVH_OK)
         rc = refresh_dilated(ctx);
     if (rc != NBVH_OK)
         return rc;
@@ -427,10 +428,7 @@ int nbvh_trace_rays(nbvh_ctx *ctx, const float *o, const float *d, uint32_t n, u
         rp.nbvh.leaf_lod_max = 2u + (uint32_t)ctx->bvh_const.lod_switch;
     rp.scene = ctx->scene;
     rp.enc   = make_encode_const(ctx);
-    rp.dec.primary_thr         = ctx->pt_const.primary_visibility_threshold;
-    rp.dec.secondary_thr       = ctx->pt_const.secondary_visibility_threshold;
-    rp.dec.depth_epsilon       = ctx->pt_const.depth_epsilon;
-    rp.dec.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
+    rp.dec                     = make_decode_const(ctx);
     rp.ignore_neural_blas      = ctx->bvh_const.ignore_neural_blas;
     rp.max_depth               = ray_depth;
     rp.queue                   = ctx->d_queue;

@@ -24,11 +24,14 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     const nbvh_renderer_constants &bc = ctx->bvh_const;
     if (batch_size == 0 || (batch_size & (batch_size - 1)) || log2_bvh_max_traversals > 31 || (batch_size >> log2_bvh_max_traversals) == 0)
         return fail(ctx, NBVH_ERR_INVALID_ARG, "batch_size must be a power of two >= 2^log2_bvh_max_traversals");
-    if (bc.ellipsoidal_bvh || bc.view_dependent_sampling || bc.leaf_boundary_sampling_ratio != 0.f)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: ellipsoidal_bvh / view_dependent_sampling / leaf_boundary_sampling_ratio are not implemented");
-    if (ctx->pt_const.depth_learning_mode != 0 /* LocalT */ || ctx->module_const.input_segment_direction_dim != 0 ||
-        ctx->module_const.segment_distribution == 2 /* Uniform */ || ctx->module_const.apply_encoding_trafo)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: only LocalT depth targets and equidistant segment points are implemented");
+    if (bc.ellipsoidal_bvh)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: ellipsoidal_bvh is not implemented");
+    if (ctx->module_const.input_segment_direction_dim != 0 || ctx->module_const.apply_encoding_trafo)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: directional inputs / apply_encoding_trafo are not implemented");
+    if ((uint32_t)ctx->pt_const.depth_learning_mode > 3u)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "depth_learning_mode out of range");
+    if (bc.leaf_boundary_sampling_ratio != 0.f && log2_bvh_max_traversals != 0)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "leaf_boundary_sampling_ratio needs log2_bvh_max_traversals == 0 (neural_bvh_module_kernels.cu:149)");
     if (bc.training_node_survival && !tree_cut_data)
         return fail(ctx, NBVH_ERR_INVALID_ARG, "training_node_survival needs tree_cut_data");
     if (bc.neural_bvh_idx >= ctx->blas_desc.size() || ctx->blas_desc[bc.neural_bvh_idx].num_nodes < 1 || !ctx->blas_desc[bc.neural_bvh_idx].nodes)
@@ -57,8 +60,15 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.enc        = make_encode_const(ctx);
     for (int i = 0; i < 3; i++) {
         sp.bbox_min[i] = ctx->scene_bbox.min[i];
+        sp.bbox_max[i] = ctx->scene_bbox.max[i];
         sp.bbox_ext[i] = ctx->scene_bbox.max[i] - ctx->scene_bbox.min[i];
     }
+    sp.uniform_points               = ctx->module_const.segment_distribution == 2 ? 1u : 0u;
+    sp.depth_mode                   = (uint32_t)ctx->pt_const.depth_learning_mode;
+    sp.view_dependent_sampling      = bc.view_dependent_sampling ? 1u : 0u;
+    sp.view_dependent_ratio         = bc.view_dependent_ratio;
+    sp.leaf_boundary_sampling_ratio = bc.leaf_boundary_sampling_ratio;
+    sp.cam                          = make_camera_const(ctx);
     sp.sampling_bbox_scaling      = bc.sampling_bbox_scaling;
     sp.fixed_node_dilation        = bc.fixed_node_dilation;
     sp.node_extent_dilation       = bc.node_extent_dilation;
@@ -77,7 +87,9 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.normal_dim  = ctx->pt_const.output_normal_dim;
     sp.albedo_dim  = ctx->pt_const.output_albedo_dim;
     sp.depth_linear = ctx->pt_const.output_depth_linear_activation ? 1u : 0u;
-    if (sp.depth_dim > 1u || (sp.normal_dim != 0u && sp.normal_dim != 3u) || (sp.albedo_dim != 0u && sp.albedo_dim != 3u) ||
+    const uint32_t want_depth_dim = sp.depth_mode >= 2u ? 3u : 1u; // Position / LocalPosition targets are points
+    if ((sp.depth_dim != 0u && sp.depth_dim != want_depth_dim) || (sp.normal_dim != 0u && sp.normal_dim != 3u) ||
+        (sp.albedo_dim != 0u && sp.albedo_dim != 3u) ||
         sp.vis_dim + sp.depth_dim + sp.normal_dim + sp.albedo_dim != sp.n_out)
         return fail(ctx, NBVH_ERR_UNSUPPORTED, "sampler: unsupported output layout");
     sp.sub_batch_size = (int)(batch_size >> log2_bvh_max_traversals);
@@ -89,7 +101,9 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.current_max_loss = current_max_loss;
     sp.tree_cut         = tree_cut_data;
     sp.counters         = ctx->d_counters;
-    if (sp.n_sub_batch == 1) {
+    // view-dependent and leaf-boundary sampling change the number of draws per origin / per slot: the general kernel follows the
+    // reference's loop literally; everything else takes the two-pass generator
+    if (sp.n_sub_batch == 1 && !sp.view_dependent_sampling && sp.leaf_boundary_sampling_ratio == 0.f) {
         // two-pass generator (sampler.cu).  The walk depends on the tree-cut, the sampler constants and the RNG only, so it may run for
         // several steps at once (nbvh_sampler_walk_ahead); this step's statistics only enter the roulette of the target pass.
         cudaStream_t st = (cudaStream_t)stream;
@@ -458,7 +472,7 @@ static int ensure_training_state(nbvh_ctx *ctx, uint32_t batch, cudaStream_t st)
     if (!ctx->params_loaded)
         return fail(ctx, NBVH_ERR_STATE, "network parameters not loaded (nbvh_init_params / nbvh_load_network_file)");
     // TMEM budget of k_train_mlp: working accumulators + one fp32 accumulator per weight matrix
-    if (192u + ctx->in_k + (ctx->n_layers - 2u) * kNeurons + kOutPadded > 512u)
+    if (train_tmem_cols(ctx->in_k, ctx->n_layers, 1u) > 512u)
         return fail(ctx, NBVH_ERR_UNSUPPORTED, "network too deep/wide for the TMEM-resident weight-gradient accumulators");
     const size_t n = ctx->n_params;
     if (!ctx->d_grads) {

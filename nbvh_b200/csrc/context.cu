@@ -231,6 +231,33 @@ EncodeConst make_encode_const(const nbvh_ctx *ctx)
     return ec;
 }
 
+DecodeConst make_decode_const(const nbvh_ctx *ctx)
+{
+    DecodeConst dc;
+    memset(&dc, 0, sizeof(dc));
+    dc.primary_thr         = ctx->pt_const.primary_visibility_threshold;
+    dc.secondary_thr       = ctx->pt_const.secondary_visibility_threshold;
+    dc.depth_epsilon       = ctx->pt_const.depth_epsilon;
+    dc.fixed_depth_epsilon = ctx->pt_const.fixed_depth_epsilon;
+    dc.depth_mode          = (uint32_t)ctx->pt_const.depth_learning_mode;
+    for (int i = 0; i < 3; i++)
+        dc.bbox_min[i] = ctx->scene_bbox.min[i], dc.bbox_max[i] = ctx->scene_bbox.max[i];
+    return dc;
+}
+
+// the wavefront kernels (segment encoding + output decode) implement equidistant segment points and the LocalT / WorldT depth modes
+int check_wavefront_modes(nbvh_ctx *ctx)
+{
+    if (ctx->module_const.segment_distribution == 2)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "Uniform segment distribution is not implemented");
+    // Position / LocalPosition: the training sampler produces their targets (sampler.cu); the inference-side decode is not
+    // implemented (the reference's LocalPosition branch prints every query, neural_bvh_module_common.cuh:131-134)
+    if (ctx->pt_const.depth_learning_mode > 1)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "inference supports depth_learning_mode LocalT and WorldT only");
+
+    return NBVH_OK;
+}
+
 int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params)
 {
     if (need_params && !ctx->params_loaded)
@@ -239,10 +266,6 @@ int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params
         return fail(ctx, NBVH_ERR_STATE, "neural BVH not set");
     if (need_scene && !ctx->scene_set)
         return fail(ctx, NBVH_ERR_STATE, "scene not set");
-    if (ctx->module_const.segment_distribution == 2)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "Uniform segment distribution is not implemented");
-    if (ctx->pt_const.depth_learning_mode != 0)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "only depth_learning_mode LocalT is implemented");
     return NBVH_OK;
 }
 

@@ -235,6 +235,8 @@ NbvhConst make_nbvh_const(const nbvh_ctx *ctx, bool inference);
 int check_nodes(nbvh_ctx *ctx, const float4 *nodes, uint32_t n, bool &ok);
 int refresh_dilated(nbvh_ctx *ctx);
 EncodeConst make_encode_const(const nbvh_ctx *ctx);
+DecodeConst make_decode_const(const nbvh_ctx *ctx);
+int check_wavefront_modes(nbvh_ctx *ctx);
 int check_ready(nbvh_ctx *ctx, bool need_scene, bool need_nbvh, bool need_params);
 CameraConst make_camera_const(const nbvh_ctx *ctx);
 int adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemcpyKind kind);

@@ -351,7 +351,7 @@ k_render(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
-            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, 1u, t_hit) && t_hit < s.best_t) {
+            if (decode_hit(p.dec, s.ray, y[0], y[1], s.seg_mint, s.seg_maxt, 1u, t_hit) && t_hit < s.best_t) {
                 s.best_t    = t_hit;
                 s.valid_hit = 1u;
                 decode_normal(y[2], y[3], y[4], s.n_or_uv);

@@ -183,6 +183,12 @@ struct AdamParams {
 cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_layers);
 cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t batch, uint32_t n_in_dims, uint8_t *feat, int num_sms,
                                    cudaStream_t stream);
+// TMEM columns of k_train_mlp (training.cu): per tile in flight one working accumulator, then one fp32 accumulator per weight matrix
+__host__ __device__ constexpr uint32_t train_slot_cols(uint32_t in_k) { return in_k > 64u ? (in_k + 31u) & ~31u : 64u; }
+__host__ __device__ constexpr uint32_t train_tmem_cols(uint32_t in_k, uint32_t n_layers, uint32_t slots)
+{
+    return slots * train_slot_cols(in_k) + in_k + (n_layers - 2u) * kNeurons + kOutPadded;
+}
 cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_sms, cudaStream_t stream);
 cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint8_t *dfeat, uint32_t batch, uint32_t n_in_dims,
                                  float *grid_grads, int num_sms, cudaStream_t stream);

@@ -368,11 +368,23 @@ __device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t,
         tc_fence_after_sync();
         // ---- epilogue: this thread's accumulator row -> registers
         if (!last) {
+#ifdef NBVH_EPI_WIDE
+            // A/B variant: all four 16-column loads in flight before one wait
+            uint32_t vv[4][16];
+#pragma unroll
+            for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u)
+                tmem_ld16(t.tmem_acc + lane_base + c0, vv[c0 >> 4]);
+            tmem_ld_wait();
+#endif
 #pragma unroll
             for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
+#ifdef NBVH_EPI_WIDE
+                uint32_t(&v)[16] = vv[c0 >> 4];
+#else
                 uint32_t v[16];
                 tmem_ld16(t.tmem_acc + lane_base + c0, v);
                 tmem_ld_wait();
+#endif
                 uint32_t h[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

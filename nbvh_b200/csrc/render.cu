@@ -86,7 +86,11 @@ k_clear_accum(const __grid_constant__ RenderParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ k_primary
+#ifdef NBVH_PRIMARY_MIN_CTAS // A/B variant builds
+__global__ void __launch_bounds__(256, NBVH_PRIMARY_MIN_CTAS)
+#else
 __global__ void __launch_bounds__(256)
+#endif
 k_primary(const __grid_constant__ RenderParams p)
 {
     const uint32_t lane  = threadIdx.x & 31u;
@@ -372,7 +376,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         if (s.have_query) {
             ++cnt_q;
             float t_hit;
-            if (decode_hit(p.dec, y[0], y[1], s.seg_mint, s.seg_maxt, kPath ? p.ray_depth : 1u, t_hit) && t_hit < s.h.best_t) {
+            if (decode_hit(p.dec, s.ray, y[0], y[1], s.seg_mint, s.seg_maxt, kPath ? p.ray_depth : 1u, t_hit) && t_hit < s.h.best_t) {
                 s.h.best_t    = t_hit;
                 s.h.valid_hit = 1u;
                 decode_normal(y[2], y[3], y[4], s.h.n_or_uv);

@@ -51,8 +51,15 @@ __device__ __forceinline__ bool node_survives(const SamplerParams &p, uint32_t n
 
 // Inputs (encode_segment_from_world_po_pi, neural_bvh_module_kernels.cu:10-97) and targets
 // (generate_single_bvh_network_output_reference, neural_bvh_module_common.cuh:783-861) of one slot.  Returns the hit flag.
+// slab test of the scene box with the plain IEEE divisions of Ray3f::intersect_bbox_min_max (ray.cuh:116-132): WorldT depth targets
+__device__ __forceinline__ void scene_box_interval(const SamplerParams &p, const Ray &r, float &mint, float &maxt)
+{
+    box_interval_ieee(p.bbox_min, p.bbox_max, r, mint, maxt);
+}
+
+// rng: the slot's generator after the roulette draw (SegmentDistribution::Uniform draws one number per segment point from it)
 __device__ __forceinline__ bool emit_slot(const SamplerParams &p, uint32_t slot, const Ray &ray, float leaf_mint, float leaf_maxt,
-                                          bool swap_dir, ItsData &its, uint32_t &cnt_blas, uint32_t &cnt_tri)
+                                          bool swap_dir, uint32_t node_idx, uint32_t &rng, ItsData &its, uint32_t &cnt_blas, uint32_t &cnt_tri)
 {
     {
         const float t_o = swap_dir ? leaf_maxt : leaf_mint, t_i = swap_dir ? leaf_mint : leaf_maxt;
@@ -60,9 +67,11 @@ __device__ __forceinline__ bool emit_slot(const SamplerParams &p, uint32_t slot,
         encode_endpoints_raw(p.enc, ray, t_o, t_i, eo, ei);
         float *in = p.inputs + (size_t)slot * p.n_in;
         for (uint32_t k = 0; k < p.enc.n_points; ++k) {
-            in[3u * k]      = lerp_point(eo[0], ei[0], p.enc.point_s[k]);
-            in[3u * k + 1u] = lerp_point(eo[1], ei[1], p.enc.point_s[k]);
-            in[3u * k + 2u] = lerp_point(eo[2], ei[2], p.enc.point_s[k]);
+            // Uniform (neural_bvh_module_kernels.cu:53-69): t = lcg_randomf(rng) per point, same blend expression
+            const float sk  = p.uniform_points ? lcg_randomf(rng) : p.enc.point_s[k];
+            in[3u * k]      = lerp_point(eo[0], ei[0], sk);
+            in[3u * k + 1u] = lerp_point(eo[1], ei[1], sk);
+            in[3u * k + 2u] = lerp_point(eo[2], ei[2], sk);
         }
     }
     Ray tr = ray;
@@ -80,15 +89,37 @@ __device__ __forceinline__ bool emit_slot(const SamplerParams &p, uint32_t slot,
     o += p.vis_dim;
     if (is_hit && (p.normal_dim || p.albedo_dim || p.max_training_bounces > 0))
         its = compute_its_data(p.blas, p.attr, p.materials, p.textures, hit);
-    if (p.depth_dim) { // LocalT: (t - mint) / ((double)len + 1e-3), evaluated in double like the reference's literal
-        float depth = 0.f;
+    if (p.depth_dim) { // compute_depth_or_position_output (neural_bvh_module_common.cuh:586-629)
+        float d3[3] = {0.f, 0.f, 0.f};
         if (is_hit) {
-            const float len = __fsub_rn(seg_maxt, seg_mint);
-            depth = __double2float_rn(__ddiv_rn((double)__fsub_rn(hit.t, seg_mint), __dadd_rn((double)len, 1e-3)));
+            if (p.depth_mode <= 1u) {
+                // LocalT / WorldT: (t - mint) / ((double)len + 1e-3), evaluated in double like the reference's literal; the interval is
+                // the leaf's (LocalT) or the scene box's along the traced ray (WorldT)
+                float lo = seg_mint, hi = seg_maxt;
+                if (p.depth_mode == 1u)
+                    scene_box_interval(p, tr, lo, hi);
+                const float len = __fsub_rn(hi, lo);
+                d3[0] = __double2float_rn(__ddiv_rn((double)__fsub_rn(hit.t, lo), __dadd_rn((double)len, 1e-3)));
+                d3[1] = d3[2] = d3[0];
+            } else {
+                // Position / LocalPosition: bbox_to_local(ray(t)) of the scene box, or of the node with the sampled node's INDEX in the
+                // neural mesh's BLAS array (the reference indexes neural_blas.nodes with the tree-cut node id: replicated)
+                const float px = __fmaf_rn(hit.t, tr.dx, tr.ox), py = __fmaf_rn(hit.t, tr.dy, tr.oy), pz = __fmaf_rn(hit.t, tr.dz, tr.oz);
+                float mn[3] = {p.bbox_min[0], p.bbox_min[1], p.bbox_min[2]}, mx[3] = {p.bbox_max[0], p.bbox_max[1], p.bbox_max[2]};
+                if (p.depth_mode == 3u) {
+                    const Node n = load_node(p.blas.nodes, node_idx);
+                    mn[0] = n.mnx, mn[1] = n.mny, mn[2] = n.mnz, mx[0] = n.mxx, mx[1] = n.mxy, mx[2] = n.mxz;
+                }
+                d3[0] = __fdiv_rn(__fsub_rn(px, mn[0]), __fsub_rn(mx[0], mn[0]));
+                d3[1] = __fdiv_rn(__fsub_rn(py, mn[1]), __fsub_rn(mx[1], mn[1]));
+                d3[2] = __fdiv_rn(__fsub_rn(pz, mn[2]), __fsub_rn(mx[2], mn[2]));
+            }
             if (p.depth_linear)
-                depth = __fmaf_rn(depth, 0.1f, 0.45f);
+                d3[0] = __fmaf_rn(d3[0], 0.1f, 0.45f), d3[1] = __fmaf_rn(d3[1], 0.1f, 0.45f), d3[2] = __fmaf_rn(d3[2], 0.1f, 0.45f);
         }
-        tg[o] = depth;
+        tg[o] = d3[0];
+        if (p.depth_mode >= 2u)
+            tg[o + 1u] = d3[1], tg[o + 2u] = d3[2];
         o += p.depth_dim;
     }
     if (p.normal_dim) {
@@ -156,17 +187,35 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
             bool walking = valid;
             if (walking)
                 walk_pop(bc, w, nstack, nss);
+            int failed_attempts = 0;
             for (;;) {
                 if (!walking) {
                     nstack[0] = 0u, nss = 1;
-                    const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
-                    const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
-                    const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
-                                lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
-                    ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
-                    ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
-                    ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
-                    ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+                    // view_dependent_sampling (neural_bvh_module_common.cuh:734-737): the first five attempts of a slot may take a camera
+                    // ray through a random image position instead of a random origin along the slot's direction
+                    bool camera = false;
+                    if (p.view_dependent_sampling && failed_attempts < 5)
+                        camera = lcg_randomf(rng) < p.view_dependent_ratio;
+                    if (camera) {
+                        // camera_raygen(lcg_randomf(rng), lcg_randomf(rng)): the device compiler evaluates the arguments left to right
+                        // (pinned by the reference kernel's outputs, tests/test_sampler.py)
+                        const float xf = lcg_randomf(rng), yf = lcg_randomf(rng);
+                        const float vx = __fadd_rn(__fmaf_rn(xf, p.cam.du[0], __fmul_rn(yf, p.cam.dv[0])), p.cam.top_left[0]);
+                        const float vy = __fadd_rn(__fmaf_rn(xf, p.cam.du[1], __fmul_rn(yf, p.cam.dv[1])), p.cam.top_left[1]);
+                        const float vz = __fadd_rn(__fmaf_rn(xf, p.cam.du[2], __fmul_rn(yf, p.cam.dv[2])), p.cam.top_left[2]);
+                        const float inv = __frcp_rn(__fsqrt_rn(__fmaf_rn(vz, vz, __fmaf_rn(vx, vx, __fmul_rn(vy, vy)))));
+                        ray.ox = p.cam.origin[0], ray.oy = p.cam.origin[1], ray.oz = p.cam.origin[2];
+                        ray.dx = __fmul_rn(vx, inv), ray.dy = __fmul_rn(vy, inv), ray.dz = __fmul_rn(vz, inv);
+                    } else {
+                        const float r0 = lcg_randomf(rng), r1 = lcg_randomf(rng), r2 = lcg_randomf(rng);
+                        const float off = __fmul_rn(__fsub_rn(p.sampling_bbox_scaling, 1.f), 0.5f);
+                        const float lx = __fmaf_rn(p.sampling_bbox_scaling, r0, -off), ly = __fmaf_rn(p.sampling_bbox_scaling, r1, -off),
+                                    lz = __fmaf_rn(p.sampling_bbox_scaling, r2, -off);
+                        ray.ox = __fmaf_rn(lx, p.bbox_ext[0], p.bbox_min[0]); // Bbox::local_to_bbox
+                        ray.oy = __fmaf_rn(ly, p.bbox_ext[1], p.bbox_min[1]);
+                        ray.oz = __fmaf_rn(lz, p.bbox_ext[2], p.bbox_min[2]);
+                        ray.dx = dir.x, ray.dy = dir.y, ray.dz = dir.z;
+                    }
                     ray_prepare_guarded(ray);
                     restarted = true;
                     walk_pop(bc, w, nstack, nss);
@@ -175,9 +224,48 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
                 const WalkResult r = nbvh_walk_step(bc, ray, w, nstack, nss, FLT_MAX, leaf_mint, leaf_maxt, node_idx, cnt_nbvh);
                 if (r == WALK_FOUND)
                     break;
-                if (r == WALK_EXHAUSTED)
+                if (r == WALK_EXHAUSTED) {
                     walking = false;
+                    ++failed_attempts;
+                }
             }
+        }
+        // leaf_boundary_sampling_ratio (neural_bvh_module_common.cuh:765-777, sample_bbox_position :636-660): the segment becomes a chord
+        // between two random points on two different faces of the sampled node's dilated box
+        if (p.leaf_boundary_sampling_ratio != 0.f && lcg_randomf(rng) <= p.leaf_boundary_sampling_ratio) {
+            const int face1 = min((int)__fmul_rn(lcg_randomf(rng), 6.f), 5);
+            int face2;
+            do {
+                face2 = min((int)__fmul_rn(lcg_randomf(rng), 6.f), 5);
+            } while (face1 == face2);
+            float l1[3], l2[3];
+            {   // get_cube_pos_on_face(face, lcg_randomf(rng), lcg_randomf(rng)): arguments evaluated left to right
+                const float u1 = lcg_randomf(rng), v1 = lcg_randomf(rng);
+                const float u2 = lcg_randomf(rng), v2 = lcg_randomf(rng);
+                const float fixed1 = (face1 & 1) ? 0.f : 1.f, fixed2 = (face2 & 1) ? 0.f : 1.f;
+                const int ax1 = face1 >> 1, ax2 = face2 >> 1; // faces 0,1: x fixed; 2,3: y fixed; 4,5: z fixed
+                l1[0] = ax1 == 0 ? fixed1 : u1, l1[1] = ax1 == 1 ? fixed1 : (ax1 == 0 ? u1 : v1), l1[2] = ax1 == 2 ? fixed1 : v1;
+                l2[0] = ax2 == 0 ? fixed2 : u2, l2[1] = ax2 == 1 ? fixed2 : (ax2 == 0 ? u2 : v2), l2[2] = ax2 == 2 ? fixed2 : v2;
+            }
+            const Node nd = load_node(p.nbvh.nodes, node_idx);
+            const float sc = __fadd_rn(1.f, bc.dilation);
+            const float mn[3] = {nd.mnx, nd.mny, nd.mnz}, mx[3] = {nd.mxx, nd.mxy, nd.mxz};
+            float en[3], ex[3];
+            for (int k = 0; k < 3; ++k) {
+                const float e = __fsub_rn(mx[k], mn[k]);
+                const float ext = __fmul_rn(e, sc);                                                       // bbox_extent() * (1 + dilation)
+                const float nmin = __fsub_rn(__fadd_rn(mn[k], __fmul_rn(e, 0.5f)), __fmul_rn(ext, 0.5f));  // bbox_center() - ext * 0.5
+                en[k] = __fmaf_rn(l1[k], ext, nmin);
+                ex[k] = __fmaf_rn(l2[k], ext, nmin);
+            }
+            const float dx = __fsub_rn(ex[0], en[0]), dy = __fsub_rn(ex[1], en[1]), dz = __fsub_rn(ex[2], en[2]);
+            const float l2n = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+            const float inv = __frcp_rn(__fsqrt_rn(l2n));
+            ray.ox = en[0], ray.oy = en[1], ray.oz = en[2];
+            ray.dx = __fmul_rn(dx, inv), ray.dy = __fmul_rn(dy, inv), ray.dz = __fmul_rn(dz, inv);
+            ray_prepare_guarded(ray);
+            leaf_mint = 0.f, leaf_maxt = __fsqrt_rn(l2n);
+            restarted = true;
         }
         p.sampled_node_indices[slot] = node_idx;
         if (restarted) {
@@ -190,7 +278,7 @@ k_generate_batch(const __grid_constant__ SamplerParams p)
         if (p.training_node_survival && !node_survives(p, node_idx, rng))
             continue; // the slot is NOT advanced and keeps its previous contents (reference quirk)
         ItsData its;
-        const bool is_hit = emit_slot(p, slot, ray, leaf_mint, leaf_maxt, swap_dir, its, cnt_blas, cnt_tri);
+        const bool is_hit = emit_slot(p, slot, ray, leaf_mint, leaf_maxt, swap_dir, node_idx, rng, its, cnt_blas, cnt_tri);
         ++cnt_written;
         swap_dir           = false;
         continue_traversal = !is_hit;
@@ -629,8 +717,11 @@ k_sample_targets(const __grid_constant__ SamplerParams p, uint32_t step_first_it
         ray.ox = __uint_as_float(a.z), ray.oy = __uint_as_float(a.w), ray.oz = __uint_as_float(b.x);
         ray.dx = __uint_as_float(b.y), ray.dy = __uint_as_float(b.z), ray.dz = __uint_as_float(b.w);
         ray_prepare_guarded(ray);
+        uint32_t rng = a.y;
+        if (p.training_node_survival)
+            lcg_randomf(rng); // the roulette's draw (above) precedes the segment points'
         ItsData its;
-        emit_slot(p, slot, ray, __uint_as_float(c.x), __uint_as_float(c.y), false, its, cnt_blas, cnt_tri);
+        emit_slot(p, slot, ray, __uint_as_float(c.x), __uint_as_float(c.y), false, a.x, rng, its, cnt_blas, cnt_tri);
         ++cnt_written;
     }
     warp_add_counter(p.counters, CNT_BLAS_STEPS, cnt_blas);

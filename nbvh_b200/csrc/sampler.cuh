@@ -12,7 +12,13 @@ struct SamplerParams {
     const MaterialPod *materials;
     const cudaTextureObject_t *textures;
     EncodeConst enc;
-    float bbox_min[3], bbox_ext[3];
+    float bbox_min[3], bbox_ext[3], bbox_max[3];
+    uint32_t uniform_points;            // SegmentDistribution::Uniform: random segment points
+    uint32_t depth_mode;                // DepthLearningMode: 0 LocalT, 1 WorldT, 2 Position, 3 LocalPosition
+    uint32_t view_dependent_sampling;   // bvh_const.view_dependent_sampling / view_dependent_ratio (general kernel only)
+    float view_dependent_ratio;
+    float leaf_boundary_sampling_ratio; // bvh_const.leaf_boundary_sampling_ratio (general kernel only)
+    CameraConst cam;                    // camera_params for view-dependent sampling
     float sampling_bbox_scaling, fixed_node_dilation, node_extent_dilation;
     uint32_t current_learned_lod, num_bvh_lods;
     uint32_t training_node_survival;

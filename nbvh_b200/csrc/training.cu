@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace nbvh {
 
@@ -198,49 +199,75 @@ __host__ __device__ constexpr uint32_t umma_idesc(uint32_t m, uint32_t n, uint32
     return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-// TMEM column map of the training kernel (512 columns allocated, fp32)
-constexpr uint32_t kColZ   = 0;   // 128 x 64 working accumulator (forward pre-activations / dgrad)
-constexpr uint32_t kColDA0 = 64;  // 128 x in_k (<= 128) dL/dfeatures
-constexpr uint32_t kColDW  = 192; // weight-gradient accumulators: layer 0 (64 x in_k), hidden (64 x 64 each), last (64 x 16, transposed)
+// ---- k_train_mlp: TMEM column map and shared-memory layout
+// kSlots tiles are in flight per CTA (two when shared memory and TMEM allow it).  Slot s owns TMEM columns
+// [s * slot_cols, (s + 1) * slot_cols): the 128 x 64 working accumulator (forward pre-activations / dgrad), which the
+// 128 x in_k dL/dfeatures accumulator of layer 0 overlays (the working accumulator is dead by then).  The weight-gradient
+// accumulators -- layer 0 (64 x in_k), hidden (64 x 64 each), last (64 x 16, transposed) -- follow and are SHARED by the slots.
+// (train_slot_cols / train_tmem_cols: kernels.cuh)
 
 struct TrainSmem {
-    uint32_t w_off, a0_off, h_off, dz_off, dzo_off, bar_off, tmem_off, total;
+    uint32_t w_off, slot_off, slot_bytes, a0_off, h_off, dzo_off, bar_off, tmem_off, total; // a0/h/dzo: relative to the slot
 };
 
-__host__ __device__ inline TrainSmem train_smem_layout(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_hidden)
+// Per slot: feature tile, one 128 x 64 tile per hidden layer (the activations H_l, overwritten IN PLACE by dZ_l during the
+// backward pass: dZ_l = dA_l . ReLU'(H_l) is computed row by row by the thread that owns the row, after every MMA that read
+// H_l has completed), and the 128 x 16 dZ tile of the output layer.
+__host__ __device__ inline TrainSmem train_smem_layout(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_hidden, uint32_t slots)
 {
     TrainSmem s;
-    s.w_off    = 0;
-    s.a0_off   = (wimg_bytes + 127u) & ~127u;
-    s.h_off    = s.a0_off + kTileRows * in_k * 2u;
-    s.dz_off   = s.h_off + n_hidden * kTileRows * kNeurons * 2u;
-    s.dzo_off  = s.dz_off + kTileRows * kNeurons * 2u;
-    s.bar_off  = s.dzo_off + kTileRows * kOutPadded * 2u;
-    s.tmem_off = s.bar_off + 32u;
-    s.total    = s.tmem_off + 16u;
+    s.w_off      = 0;
+    s.slot_off   = (wimg_bytes + 127u) & ~127u;
+    s.a0_off     = 0;
+    s.h_off      = kTileRows * in_k * 2u;
+    s.dzo_off    = s.h_off + n_hidden * kTileRows * kNeurons * 2u;
+    s.slot_bytes = s.dzo_off + kTileRows * kOutPadded * 2u;
+    s.bar_off    = s.slot_off + slots * s.slot_bytes;
+    s.tmem_off   = s.bar_off + 64u; // mbarriers: weights, then {features, operands ready, MMAs done} per slot
+    s.total      = s.tmem_off + 16u;
     return s;
 }
 
-__global__ void __launch_bounds__(kTileRows, 1)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp roles: warps [4 s, 4 s + 4) are the epilogue warps of slot s (thread r of the group owns sample row r = TMEM lane r of the
+// slot's accumulators); the last warp's lane 0 issues every tcgen05.mma of the CTA, alternating between the slots step by step, so
+// that one slot's epilogue (tcgen05.ld, ReLU / loss / ReLU', fp16 stores) runs under the other slot's MMAs.  Hand-over is by
+// mbarriers: `ready[s]` (128 arrivals: operands of the slot's next step are in shared memory and its TMEM reads are done) and
+// `done[s]` (tcgen05.commit of the step's MMAs).  A tile is 10 steps for the shipped network: 5 forward layers, then per layer,
+// last to first, the weight-gradient MMAs + the data-gradient MMAs.
+template <int kSlots>
+__global__ void __launch_bounds__(kSlots *kTileRows + 32, 1)
 k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t n_hidden = nc.n_layers - 1u;
-    const TrainSmem lay     = train_smem_layout(nc.wimg_bytes, nc.in_k, n_hidden);
-    const uint32_t row      = threadIdx.x;
-    const uint32_t warp     = row >> 5, lane = row & 31u;
-    const uint32_t bar_mma  = smem_u32(smem + lay.bar_off);
-    const uint32_t bar_w    = bar_mma + 8u;
-    const uint32_t bar_feat = bar_mma + 16u;
+    const TrainSmem lay     = train_smem_layout(nc.wimg_bytes, nc.in_k, n_hidden, kSlots);
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t warp     = tid >> 5, lane = tid & 31u;
+    const bool is_issuer    = warp == (uint32_t)(kSlots * 4);
+    const uint32_t slot     = is_issuer ? 0u : tid / kTileRows;
+    const uint32_t row      = tid % kTileRows;
+    const uint32_t bar0     = smem_u32(smem + lay.bar_off);
+    const uint32_t bar_w    = bar0;
+    auto bar_feat  = [&](uint32_t sl) { return bar0 + 8u + 24u * sl; };
+    auto bar_ready = [&](uint32_t sl) { return bar0 + 16u + 24u * sl; };
+    auto bar_done  = [&](uint32_t sl) { return bar0 + 24u + 24u * sl; };
 
-    if (row == 0) {
-        mbar_init(bar_mma, 1u);
+    if (tid == 0) {
         mbar_init(bar_w, 1u);
-        mbar_init(bar_feat, 1u);
+        for (uint32_t sl = 0; sl < (uint32_t)kSlots; ++sl) {
+            mbar_init(bar_feat(sl), 1u);
+            mbar_init(bar_ready(sl), (uint32_t)kTileRows);
+            mbar_init(bar_done(sl), 1u);
+        }
         fence_barrier_init();
     }
     __syncthreads();
-    if (row == 0) {
+    if (tid == 0) {
         mbar_expect_tx(bar_w, nc.wimg_bytes);
         tma_bulk_g2s(smem_u32(smem + lay.w_off), nc.wimg, nc.wimg_bytes, bar_w);
     }
@@ -249,227 +276,269 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    const uint32_t tmem      = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
-    const uint32_t lane_base = (row & ~31u) << 16;
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(smem + lay.tmem_off);
     mbar_wait(bar_w, 0u);
 
-    const uint32_t w_smem   = smem_u32(smem + lay.w_off);
-    uint8_t *a0_tile        = smem + lay.a0_off;
-    const uint32_t a0_addr  = smem_u32(a0_tile);
-    uint8_t *dz_tile        = smem + lay.dz_off;
-    const uint32_t dz_addr  = smem_u32(dz_tile);
-    uint8_t *dzo_tile       = smem + lay.dzo_off;
-    const uint32_t dzo_addr = smem_u32(dzo_tile);
+    const uint32_t w_smem     = smem_u32(smem + lay.w_off);
     const uint32_t tile_bytes = kTileRows * nc.in_k * 2u;
-    const uint32_t rg_a0    = (nc.in_k >> 3) * 128u;            // row-group stride of the feature tile
-    const uint32_t rg_h     = (uint32_t)(kNeurons >> 3) * 128u; // ... of the 64-wide tiles
-    const uint32_t rg_o     = (uint32_t)(kOutPadded >> 3) * 128u;
-    const float n_total_f   = (float)tp.n_total;
+    const uint32_t h_bytes    = kTileRows * kNeurons * 2u;
+    const uint32_t rg_a0      = (nc.in_k >> 3) * 128u;            // row-group stride of the feature tile
+    const uint32_t rg_h       = (uint32_t)(kNeurons >> 3) * 128u; // ... of the 64-wide tiles
+    const uint32_t rg_o       = (uint32_t)(kOutPadded >> 3) * 128u;
+    const uint32_t slot_cols  = train_slot_cols(nc.in_k);
+    const uint32_t col_dw     = (uint32_t)kSlots * slot_cols;
+    const uint32_t n_tiles    = (tp.batch + kTileRows - 1u) / kTileRows;
+    // tile of (round, slot): blockIdx.x + (round * kSlots + slot) * gridDim.x
+    const uint32_t my_tiles   = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+    const uint32_t n_rounds   = (my_tiles + (uint32_t)kSlots - 1u) / (uint32_t)kSlots;
 
-    uint32_t mma_phase = 0u, feat_phase = 0u;
-    uint32_t first_tile = 1u;
-    float loss_acc      = 0.f;
-
-    const uint32_t n_tiles = (tp.batch + kTileRows - 1u) / kTileRows;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- feature tile: one TMA bulk copy (the previous tile's MMAs that read a0 have completed: their commit was waited on)
-        if (row == 0) {
-            mbar_expect_tx(bar_feat, tile_bytes);
-            tma_bulk_g2s(a0_addr, tp.feat + (size_t)tile * tile_bytes, tile_bytes, bar_feat);
-        }
-        const uint32_t s  = tile * kTileRows + row;
-        const bool valid  = s < tp.batch;
-        float tgt[8];
+    if (is_issuer) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            uint32_t ready_phase[kSlots], feat_phase[kSlots];
+            for (int sl = 0; sl < kSlots; ++sl)
+                ready_phase[sl] = feat_phase[sl] = 0u;
+            uint32_t dw_started = 0u; // bit `layer`: the layer's weight-gradient accumulator holds a value
+            for (uint32_t round = 0; round < n_rounds; ++round) {
+                for (uint32_t step = 0; step < 2u * nc.n_layers; ++step) {
 #pragma unroll
-        for (uint32_t j = 0; j < 8; ++j)
-            tgt[j] = (valid && j < nc.n_out) ? __ldg(tp.target + (size_t)s * nc.n_out + j) : 0.f;
-        mbar_wait(bar_feat, feat_phase);
-        feat_phase ^= 1u;
-
-        // ================= forward: activations of every layer stay in shared memory
-        uint32_t k_in = nc.in_k, a_addr = a0_addr;
-        float y[8];
-        for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
-            const bool last      = layer + 1u == nc.n_layers;
-            const uint32_t n_out = last ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
-            tc_fence_before_sync();
-            __syncthreads();
-            if (row == 0) {
-                tc_fence_after_sync();
-                const uint32_t sbo   = (k_in >> 3) * 128u;
-                const uint32_t idesc = umma_idesc(128u, n_out, 0u, 0u);
-                const uint32_t w_l   = w_smem + nc.layer_off[layer];
-                for (uint32_t k = 0; k < k_in; k += 16u)
-                    umma_f16(tmem + kColZ, umma_desc(a_addr + (k >> 3) * 128u, kLBO, sbo), umma_desc(w_l + (k >> 3) * 128u, kLBO, sbo),
-                             idesc, k > 0u ? 1u : 0u);
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, mma_phase);
-            mma_phase ^= 1u;
-            tc_fence_after_sync();
-            if (!last) {
-                uint8_t *h_tile = smem + lay.h_off + layer * (kTileRows * kNeurons * 2u);
-#pragma unroll
-                for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + kColZ + lane_base + c0, v);
-                    tmem_ld_wait();
-                    uint32_t h[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __half2 p = __floats2half2_rn(fmaxf(__uint_as_float(v[2 * i]), 0.f), fmaxf(__uint_as_float(v[2 * i + 1]), 0.f));
-                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                    for (int sl = 0; sl < kSlots; ++sl) {
+                        if (round * (uint32_t)kSlots + (uint32_t)sl >= my_tiles)
+                            continue;
+                        const uint32_t base    = smem_u32(smem + lay.slot_off + (uint32_t)sl * lay.slot_bytes);
+                        const uint32_t a0_addr = base + lay.a0_off, h_addr = base + lay.h_off, dzo_addr = base + lay.dzo_off;
+                        const uint32_t col_z   = (uint32_t)sl * slot_cols;
+                        if (step == 0u) {
+                            mbar_wait(bar_feat((uint32_t)sl), feat_phase[sl]); // the tile's features landed (TMA)
+                            feat_phase[sl] ^= 1u;
+                            if (round > 0u) { // the previous tile's last epilogue released the slot's TMEM columns
+                                mbar_wait(bar_ready((uint32_t)sl), ready_phase[sl]);
+                                ready_phase[sl] ^= 1u;
+                            }
+                        } else {
+                            mbar_wait(bar_ready((uint32_t)sl), ready_phase[sl]);
+                            ready_phase[sl] ^= 1u;
+                        }
+                        tc_fence_after_sync();
+                        if (step < nc.n_layers) {
+                            // ---- forward layer `step`: Z = A . W^T
+                            const uint32_t layer = step;
+                            const uint32_t k_in  = layer == 0u ? nc.in_k : (uint32_t)kNeurons;
+                            const uint32_t a_addr = layer == 0u ? a0_addr : h_addr + (layer - 1u) * h_bytes;
+                            const uint32_t n_out = layer + 1u == nc.n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+                            const uint32_t sbo   = (k_in >> 3) * 128u;
+                            const uint32_t idesc = umma_idesc(128u, n_out, 0u, 0u);
+                            const uint32_t w_l   = w_smem + nc.layer_off[layer];
+                            for (uint32_t k = 0; k < k_in; k += 16u)
+                                umma_f16(tmem + col_z, umma_desc(a_addr + (k >> 3) * 128u, kLBO, sbo), umma_desc(w_l + (k >> 3) * 128u, kLBO, sbo),
+                                         idesc, k > 0u ? 1u : 0u);
+                        } else {
+                            // ---- backward of layer `layer`: dW_layer += dZ^T A_{layer-1};  dA_{layer-1} = dZ W_layer
+                            const uint32_t layer   = 2u * nc.n_layers - 1u - step;
+                            const bool last        = layer + 1u == nc.n_layers;
+                            const uint32_t kin     = layer == 0u ? nc.in_k : (uint32_t)kNeurons;
+                            const uint32_t in_addr = layer == 0u ? a0_addr : h_addr + (layer - 1u) * h_bytes;
+                            const uint32_t in_rg   = layer == 0u ? rg_a0 : rg_h;
+                            const uint32_t dz_addr = last ? dzo_addr : h_addr + layer * h_bytes; // dZ_l lives in H_l's tile
+                            const uint32_t dz_rg   = last ? rg_o : rg_h;
+                            const uint32_t dz_n    = last ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+                            const uint32_t dw_col  = col_dw + (layer == 0u ? 0u : nc.in_k + (layer - 1u) * kNeurons);
+                            const uint32_t fresh   = (dw_started >> layer) & 1u ? 0u : 1u;
+                            dw_started |= 1u << layer;
+                            // weight gradient, K = the 128 samples of the tile (8 steps of 16), both operands MN-major
+                            if (last) {
+                                // transposed: D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
+                                const uint32_t idesc = umma_idesc(64u, kOutPadded, 1u, 1u);
+                                for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
+                                    umma_f16(tmem + dw_col, umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u),
+                                             umma_desc_mn(dz_addr + ks * 2u * dz_rg, dz_rg, 128u), idesc, (fresh && ks == 0u) ? 0u : 1u);
+                            } else {
+                                // D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
+                                const uint32_t idesc = umma_idesc(64u, kin, 1u, 1u);
+                                for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
+                                    umma_f16(tmem + dw_col, umma_desc_mn(dz_addr + ks * 2u * dz_rg, dz_rg, 128u),
+                                             umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u), idesc, (fresh && ks == 0u) ? 0u : 1u);
+                            }
+                            // data gradient: D[128 x kin] = dZ (K-major, K = dz_n) . W_layer viewed MN-major (N = kin, K = out)
+                            {
+                                const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
+                                const uint32_t w_l   = w_smem + nc.layer_off[layer];
+                                const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
+                                for (uint32_t k = 0; k < dz_n; k += 16u)
+                                    umma_f16(tmem + col_z, umma_desc(dz_addr + (k >> 3) * 128u, kLBO, dz_rg),
+                                             umma_desc_mn(w_l + (k >> 3) * w_rg, w_rg, 128u), idesc, k > 0u ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(bar_done((uint32_t)sl)); // implies tcgen05.fence::before_thread_sync
                     }
-                    *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
                 }
-                fence_proxy_async_smem();
-                a_addr = smem_u32(h_tile);
-                k_in   = kNeurons;
-            } else {
-                uint32_t v[16];
-                tmem_ld16(tmem + kColZ + lane_base, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) // the training forward hands fp16 predictions to the loss (trainer.h:108-131)
-                    y[i] = h2f_round(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[i]))));
             }
         }
-        // ================= loss + output-activation backward -> dZ_out tile (128 x 16 fp16, loss-scaled)
-        {
-            float dz[8];
-            float lrow = 0.f;
-#pragma unroll
-            for (uint32_t e = 0; e < 8; ++e) {
-                float g       = 0.f;
-                const float l = (valid && e < nc.n_out) ? loss_element(tp.loss, tgt, y[e], e, n_total_f, tp.loss_scale, g) : 0.f;
-                if (tp.per_sample_loss && valid)
-                    tp.per_sample_loss[(size_t)s * kOutPadded + e] = l;
-                lrow += l;
-                g     = valid ? h2f_round(g) : 0.f;
-                dz[e] = g * (y[e] * (1.f - y[e])); // sigmoid' from the output value
-            }
-            if (tp.per_sample_loss && valid) {
-#pragma unroll
-                for (uint32_t e = 8; e < (uint32_t)kOutPadded; ++e)
-                    tp.per_sample_loss[(size_t)s * kOutPadded + e] = 0.f;
-            }
-            loss_acc += lrow;
-            uint32_t h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const __half2 p = __floats2half2_rn(dz[2 * i], dz[2 * i + 1]);
-                h[i]            = *reinterpret_cast<const uint32_t *>(&p);
-            }
-            *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 0u, kOutPadded)) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 1u, kOutPadded)) = make_uint4(0u, 0u, 0u, 0u);
-            fence_proxy_async_smem();
+    } else {
+        // ================================================================ epilogue warps of slot `slot`
+        uint8_t *base            = smem + lay.slot_off + slot * lay.slot_bytes;
+        uint8_t *a0_tile         = base + lay.a0_off;
+        uint8_t *h_tiles         = base + lay.h_off;
+        uint8_t *dzo_tile        = base + lay.dzo_off;
+        const uint32_t col_z     = slot * slot_cols;
+        const uint32_t lane_base = (row & ~31u) << 16;
+        const float n_total_f    = (float)tp.n_total;
+        uint32_t done_phase      = 0u;
+        float loss_acc           = 0.f;
+        if (row == 0 && slot < my_tiles) { // first tile of the slot
+            mbar_expect_tx(bar_feat(slot), tile_bytes);
+            tma_bulk_g2s(smem_u32(a0_tile), tp.feat + (size_t)(blockIdx.x + slot * gridDim.x) * tile_bytes, tile_bytes, bar_feat(slot));
         }
-        // ================= backward: for layer = last .. 0:  dW_layer += dZ^T A_{layer-1};  dA_{layer-1} = dZ W_layer
-        uint32_t cur_dz_addr = dzo_addr, cur_rg = rg_o, cur_n = kOutPadded; // dZ of the layer being processed
-        uint32_t dw_col      = kColDW + nc.in_k + (n_hidden - 1u) * kNeurons; // accumulator of the last layer
-        for (int layer = (int)nc.n_layers - 1; layer >= 0; --layer) {
-            const bool last        = layer + 1 == (int)nc.n_layers;
-            const uint32_t kin     = layer == 0 ? nc.in_k : (uint32_t)kNeurons;
-            const uint32_t in_addr = layer == 0 ? a0_addr : smem_u32(smem + lay.h_off + (uint32_t)(layer - 1) * (kTileRows * kNeurons * 2u));
-            const uint32_t in_rg   = layer == 0 ? rg_a0 : rg_h;
-            tc_fence_before_sync();
-            __syncthreads();
-            if (row == 0) {
+        for (uint32_t round = 0; round * (uint32_t)kSlots + slot < my_tiles; ++round) {
+            const uint32_t tile = blockIdx.x + (round * (uint32_t)kSlots + slot) * gridDim.x;
+            const uint32_t s    = tile * kTileRows + row;
+            const bool valid    = s < tp.batch;
+            float tgt[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                tgt[j] = (valid && j < nc.n_out) ? __ldg(tp.target + (size_t)s * nc.n_out + j) : 0.f;
+            // ================= forward: activations of every layer stay in shared memory
+            float y[8];
+            for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
+                const bool last = layer + 1u == nc.n_layers;
+                mbar_wait(bar_done(slot), done_phase);
+                done_phase ^= 1u;
                 tc_fence_after_sync();
-                // ---- weight gradient, K = the 128 samples of the tile (8 steps of 16), both operands MN-major
-                if (last) {
-                    // transposed: D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
-                    const uint32_t idesc = umma_idesc(64u, kOutPadded, 1u, 1u);
-                    for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
-                        umma_f16(tmem + dw_col, umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u),
-                                 umma_desc_mn(cur_dz_addr + ks * 2u * cur_rg, cur_rg, 128u), idesc, (first_tile && ks == 0u) ? 0u : 1u);
+                if (!last) {
+                    uint8_t *h_tile = h_tiles + layer * h_bytes;
+#pragma unroll
+                    for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + col_z + lane_base + c0, v);
+                        tmem_ld_wait();
+                        uint32_t h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 p = __floats2half2_rn(fmaxf(__uint_as_float(v[2 * i]), 0.f), fmaxf(__uint_as_float(v[2 * i + 1]), 0.f));
+                            h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                        }
+                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
+                    }
                 } else {
-                    // D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
-                    const uint32_t idesc = umma_idesc(64u, kin, 1u, 1u);
-                    for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
-                        umma_f16(tmem + dw_col, umma_desc_mn(cur_dz_addr + ks * 2u * cur_rg, cur_rg, 128u),
-                                 umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u), idesc, (first_tile && ks == 0u) ? 0u : 1u);
-                }
-                // ---- data gradient: D[128 x kin] = dZ (K-major, K = cur_n) . W_layer viewed MN-major (N = kin, K = out)
-                {
-                    const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
-                    const uint32_t w_l   = w_smem + nc.layer_off[layer];
-                    const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
-                    const uint32_t dcol  = layer == 0 ? kColDA0 : kColZ;
-                    for (uint32_t k = 0; k < cur_n; k += 16u)
-                        umma_f16(tmem + dcol, umma_desc(cur_dz_addr + (k >> 3) * 128u, kLBO, cur_rg),
-                                 umma_desc_mn(w_l + (k >> 3) * w_rg, w_rg, 128u), idesc, k > 0u ? 1u : 0u);
-                }
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, mma_phase);
-            mma_phase ^= 1u;
-            tc_fence_after_sync();
-            if (layer > 0) {
-                // dZ_{layer-1} = dA ⊙ ReLU'(H_{layer-1}) -> fp16 -> dz tile (both MMAs that read the old dZ have completed)
-                const uint8_t *h_tile = smem + lay.h_off + (uint32_t)(layer - 1) * (kTileRows * kNeurons * 2u);
-#pragma unroll
-                for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
                     uint32_t v[16];
-                    tmem_ld16(tmem + kColZ + lane_base + c0, v);
+                    tmem_ld16(tmem + col_z + lane_base, v);
                     tmem_ld_wait();
-                    const uint4 m0 = *reinterpret_cast<const uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons));
-                    const uint4 m1 = *reinterpret_cast<const uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons));
-                    const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                    uint32_t h[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a   = (mk[i] & 0x00007FFFu) ? __uint_as_float(v[2 * i]) : 0.f; // stored activation > 0 (fp16 bits)
-                        const float b   = (mk[i] & 0x7FFF0000u) ? __uint_as_float(v[2 * i + 1]) : 0.f;
-                        const __half2 p = __floats2half2_rn(a, b);
+                    for (int i = 0; i < 8; ++i) // the training forward hands fp16 predictions to the loss (trainer.h:108-131)
+                        y[i] = h2f_round(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[i]))));
+                    // ---- loss + output-activation backward -> dZ_out tile (128 x 16 fp16, loss-scaled)
+                    float dz[8];
+                    float lrow = 0.f;
+#pragma unroll
+                    for (uint32_t e = 0; e < 8; ++e) {
+                        float g       = 0.f;
+                        const float l = (valid && e < nc.n_out) ? loss_element(tp.loss, tgt, y[e], e, n_total_f, tp.loss_scale, g) : 0.f;
+                        if (tp.per_sample_loss && valid)
+                            tp.per_sample_loss[(size_t)s * kOutPadded + e] = l;
+                        lrow += l;
+                        g     = valid ? h2f_round(g) : 0.f;
+                        dz[e] = g * (y[e] * (1.f - y[e])); // sigmoid' from the output value
+                    }
+                    if (tp.per_sample_loss && valid) {
+#pragma unroll
+                        for (uint32_t e = 8; e < (uint32_t)kOutPadded; ++e)
+                            tp.per_sample_loss[(size_t)s * kOutPadded + e] = 0.f;
+                    }
+                    loss_acc += lrow;
+                    uint32_t h[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 p = __floats2half2_rn(dz[2 * i], dz[2 * i + 1]);
                         h[i]            = *reinterpret_cast<const uint32_t *>(&p);
                     }
-                    *reinterpret_cast<uint4 *>(dz_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(dz_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
+                    *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 0u, kOutPadded)) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 1u, kOutPadded)) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 fence_proxy_async_smem();
-                cur_dz_addr = dz_addr, cur_rg = rg_h, cur_n = kNeurons;
-                dw_col -= (layer == 1) ? nc.in_k : (uint32_t)kNeurons;
-            } else {
-                // dL/dfeatures -> fp16 -> global, same tile-canonical layout as the features
-                uint8_t *dst = tp.dfeat + (size_t)tile * tile_bytes;
-                for (uint32_t c0 = 0; c0 < nc.in_k; c0 += 16u) {
-                    uint32_t v[16];
-                    tmem_ld16(tmem + kColDA0 + lane_base + c0, v);
-                    tmem_ld_wait();
-                    uint32_t h[8];
+                tc_fence_before_sync();
+                mbar_arrive(bar_ready(slot));
+            }
+            // ================= backward, layer = last .. 0: the issuer ran dW_layer and dA_{layer-1}; here dZ_{layer-1}
+            for (int layer = (int)nc.n_layers - 1; layer >= 0; --layer) {
+                mbar_wait(bar_done(slot), done_phase);
+                done_phase ^= 1u;
+                tc_fence_after_sync();
+                if (layer > 0) {
+                    // dZ_{layer-1} = dA . ReLU'(H_{layer-1}) -> fp16, in place over H_{layer-1} (every MMA that read it has completed)
+                    uint8_t *h_tile = h_tiles + (uint32_t)(layer - 1) * h_bytes;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __half2 p = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                    for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + col_z + lane_base + c0, v);
+                        tmem_ld_wait();
+                        uint4 *p0 = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons));
+                        uint4 *p1 = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons));
+                        const uint4 m0 = *p0, m1 = *p1;
+                        const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+                        uint32_t h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float a   = (mk[i] & 0x00007FFFu) ? __uint_as_float(v[2 * i]) : 0.f; // stored activation > 0 (fp16 bits)
+                            const float b   = (mk[i] & 0x7FFF0000u) ? __uint_as_float(v[2 * i + 1]) : 0.f;
+                            const __half2 p = __floats2half2_rn(a, b);
+                            h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                        }
+                        *p0 = make_uint4(h[0], h[1], h[2], h[3]);
+                        *p1 = make_uint4(h[4], h[5], h[6], h[7]);
                     }
-                    *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, c0 >> 3, nc.in_k))        = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, (c0 >> 3) + 1u, nc.in_k)) = make_uint4(h[4], h[5], h[6], h[7]);
+                    fence_proxy_async_smem();
+                } else {
+                    // the feature tile is free (dW_0 has completed): fetch the slot's next tile under this epilogue
+                    const uint32_t next_idx = (round + 1u) * (uint32_t)kSlots + slot;
+                    if (row == 0 && next_idx < my_tiles) {
+                        mbar_expect_tx(bar_feat(slot), tile_bytes);
+                        tma_bulk_g2s(smem_u32(a0_tile), tp.feat + (size_t)(blockIdx.x + next_idx * gridDim.x) * tile_bytes, tile_bytes, bar_feat(slot));
+                    }
+                    // dL/dfeatures -> fp16 -> global, same tile-canonical layout as the features
+                    uint8_t *dst = tp.dfeat + (size_t)tile * tile_bytes;
+                    for (uint32_t c0 = 0; c0 < nc.in_k; c0 += 16u) {
+                        uint32_t v[16];
+                        tmem_ld16(tmem + col_z + lane_base + c0, v);
+                        tmem_ld_wait();
+                        uint32_t h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __half2 p = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                            h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                        }
+                        *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, c0 >> 3, nc.in_k))        = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(dst + tile_chunk_off(row, (c0 >> 3) + 1u, nc.in_k)) = make_uint4(h[4], h[5], h[6], h[7]);
+                    }
                 }
+                tc_fence_before_sync();
+                mbar_arrive(bar_ready(slot));
             }
         }
-        first_tile = 0u;
-        // all threads finished reading TMEM / smem of this tile before the next tile's TMA and MMAs overwrite them
-        tc_fence_before_sync();
-        __syncthreads();
+        loss_acc = warp_sum(loss_acc);
+        if (lane == 0 && tp.loss_sum && loss_acc != 0.f)
+            atomicAdd(tp.loss_sum, loss_acc);
     }
 
-    // ================= flush: loss and the TMEM-resident weight gradients
-    loss_acc = warp_sum(loss_acc);
-    if (lane == 0 && tp.loss_sum)
-        atomicAdd(tp.loss_sum, loss_acc);
-    if (!first_tile) {
-        tc_fence_after_sync();
-        // M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  ->  warp w, lanes 0..15 hold rows 16 w .. 16 w + 15
-        const uint32_t r = 16u * warp + lane;
-        uint32_t col     = kColDW;
-        size_t goff      = 0;
+    // ================= flush the TMEM-resident weight gradients (every commit has been waited on by its slot's epilogue warps)
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (!is_issuer && my_tiles > 0u) {
+        // M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  ->  warp w (mod 4), lanes 0..15 hold rows 16 w .. 16 w + 15;
+        // the 16-column chunks are dealt round-robin to the slots' warp groups
+        const uint32_t lane_base = (row & ~31u) << 16;
+        const uint32_t r         = 16u * (warp & 3u) + lane;
+        uint32_t col             = col_dw;
+        size_t goff              = 0;
+        uint32_t chunk           = 0;
         for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
             const bool last    = layer + 1u == nc.n_layers;
             const uint32_t kin = layer == 0 ? nc.in_k : (uint32_t)kNeurons;
             const uint32_t nn  = last ? (uint32_t)kOutPadded : kin; // accumulator columns
-            for (uint32_t c0 = 0; c0 < nn; c0 += 16u) {
+            for (uint32_t c0 = 0; c0 < nn; c0 += 16u, ++chunk) {
+                if (chunk % (uint32_t)kSlots != slot)
+                    continue;
                 uint32_t v[16];
                 tmem_ld16(tmem + col + lane_base + c0, v);
                 tmem_ld_wait();
@@ -605,8 +674,10 @@ __global__ void k_half_to_float(const __half *__restrict__ src, float *__restric
 cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_layers)
 {
     (void)wimg_bytes, (void)in_k, (void)n_layers;
-    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_train_mlp));
+    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_train_mlp<1>));
     if (e != cudaSuccess)
+        return e;
+    if ((e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_train_mlp<2>))) != cudaSuccess)
         return e;
     return cudaFuncSetAttribute(k_grid_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
@@ -626,13 +697,28 @@ cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t
     return cudaGetLastError();
 }
 
+// Two tiles in flight per CTA when the network's tiles fit shared memory (227 KB) and TMEM (512 columns) twice, else one.
+uint32_t train_mlp_slots(const NetConst &nc)
+{
+    const bool two = train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u, 2u).total <= 227u * 1024u &&
+                     train_tmem_cols(nc.in_k, nc.n_layers, 2u) <= 512u;
+    static const bool force_one = [] { const char *e = getenv("NBVH_TRAIN_SLOTS"); return e && e[0] == '1'; }(); // A/B measurements
+    return two && !force_one ? 2u : 1u;
+}
+
 cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_sms, cudaStream_t stream)
 {
     if (tp.batch == 0)
         return cudaSuccess;
     const uint32_t n_tiles = (tp.batch + kTileRows - 1u) / kTileRows;
-    const uint32_t grid    = n_tiles < (uint32_t)num_sms ? n_tiles : (uint32_t)num_sms;
-    k_train_mlp<<<grid, kTileRows, train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u).total, stream>>>(nc, tp);
+    const uint32_t slots   = train_mlp_slots(nc);
+    const uint32_t want    = (n_tiles + slots - 1u) / slots;
+    const uint32_t grid    = want < (uint32_t)num_sms ? want : (uint32_t)num_sms;
+    const uint32_t smem    = train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u, slots).total;
+    if (slots == 2u)
+        k_train_mlp<2><<<grid, 2 * kTileRows + 32, smem, stream>>>(nc, tp);
+    else
+        k_train_mlp<1><<<grid, kTileRows + 32, smem, stream>>>(nc, tp);
     return cudaGetLastError();
 }
 

@@ -245,6 +245,44 @@ def test_gpu_hit_records_match_reference_wavefront(gold, gpu_env):
 
 
 @pytest.mark.gpu
+def test_gpu_worldt_depth_mode_matches_reference_wavefront(gold, gpu_env):
+    """DepthLearningMode::WorldT (neural_bvh_module_common.cuh:58-88) against the reference's wavefront path run with the same
+    constant (tools/make_ref_worldt_golden.py): hit kinds, classical t bit-exact, neural t within the network tolerance scaled
+    by the scene-box interval the depth output is decoded against."""
+    import nbvh_b200
+    path = os.path.join(HERE, "golden", "ref_chess_worldt_256x144.npz")
+    if not os.path.exists(path):
+        pytest.skip("WorldT golden not generated (tools/make_ref_worldt_golden.py on a GPU box)")
+    g = np.load(path)
+    assert int(g["n"]) == gold["n"]
+    mod, torch = gpu_env["mod"], gpu_env["torch"]
+    pt = mod.get_constants(nbvh_b200.CONST_PT_OUTPUT)
+    saved = mod.get_constants(nbvh_b200.CONST_PT_OUTPUT)
+    pt.depth_learning_mode = 1
+    mod.set_constants(nbvh_b200.CONST_PT_OUTPUT, pt)
+    try:
+        hits_dev = mod.attach_hit_buffer(gold["n"])
+        mod.neural_render(0, 0)
+        torch.cuda.synchronize()
+        h = hits_dev.cpu().numpy().view(nbvh_b200.HIT_DTYPE)
+    finally:
+        mod.set_constants(nbvh_b200.CONST_PT_OUTPUT, saved)
+    kind, t = h["valid_hit"].astype(np.uint8), h["t"]
+    gk, gt = g["hit_kind"], g["hit_t"].view(np.float32)
+    assert (gk == 1).sum() > 1000 and not (gk == gold["hit_kind"]).all()  # the mode changes the frame
+    same = kind == gk
+    assert (~same).sum() <= int(0.02 * len(gk)), "%d hit-kind flips" % int((~same).sum())
+    cls = same & (gk == 2)
+    assert (bits(t[cls]) == g["hit_t"][cls]).mean() > 0.99
+    neu = same & (gk == 1)
+    box = mod.get_constants(nbvh_b200.CONST_SCENE_BBOX)
+    diag = float(np.linalg.norm(np.array(box.max[:3]) - np.array(box.min[:3])))
+    dt = np.abs(t[neu] - gt[neu])
+    assert np.median(dt) < 2e-3 * diag, "median |dt| %g (scene diagonal %g)" % (np.median(dt), diag)
+    assert (dt < NET_TOL_TCNN * diag).mean() > 0.99
+
+
+@pytest.mark.gpu
 def test_gpu_1080p_frame_matches_reference_summaries(chess_root, chess_cfg, gpu_env):
     """Full BASELINE.json size: per-pixel interval counts, per-row checksums of the interval lists, classical-hit row sums
     and hit kinds of the whole 1920x1080 frame against the reference's run."""

@@ -164,6 +164,49 @@ def test_gpu_sampler_walk_ahead_is_bit_identical_and_invalidates(gold, gpu_mod):
         mod.sampler_walk_ahead(1, 1)
 
 
+GOLD_OPTIONS = os.path.join(HERE, "golden", "ref_chess_sampler_options.npz")
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_options_bit_exact_against_reference_kernel(gpu_mod):
+    """The sampler options no shipped config uses -- Uniform segment points, WorldT / Position / LocalPosition depth targets,
+    view-dependent sampling, leaf-boundary sampling, training bounces (neural_bvh_module_kernels.cu:53-69,227-262,
+    neural_bvh_module_common.cuh:586-629,679-777) -- against the reference's own kernel run with the same constant blocks
+    (tools/make_ref_sampler_option_goldens.py): node ids, inputs and targets of every slot bit for bit."""
+    if not os.path.exists(GOLD_OPTIONS):
+        pytest.skip("sampler option goldens not generated (tools/make_ref_sampler_option_goldens.py on a GPU box)")
+    from tools.make_ref_sampler_option_goldens import CASES, apply_case, restore
+    import nbvh_b200
+    gold = np.load(GOLD_OPTIONS)
+    mod, cut_dev, torch = gpu_mod
+    failures = []
+    for name, (log2_trav, changes) in CASES.items():
+        if name + "_in" not in gold:
+            continue
+        batch, g_trav, steps = [int(v) for v in gold[name + "_cfg"]]
+        assert g_trav == log2_trav
+        gx, gt, gn = gold[name + "_in"], gold[name + "_tgt"], gold[name + "_nodes"]
+        saved = apply_case(mod, changes)
+        try:
+            n_out = int(mod.get_constants(nbvh_b200.CONST_PT_OUTPUT).output_network_dims)
+            assert gt.shape[-1] == n_out
+            nodes = torch.zeros(batch, dtype=torch.int32, device="cuda")
+            x = torch.zeros((batch, 9), dtype=torch.float32, device="cuda")
+            t = torch.zeros((batch, n_out), dtype=torch.float32, device="cuda")
+            for s in range(steps):
+                mod.optimisation_data_generation(s, batch, log2_trav, nodes, float(gold["max_loss"]), cut_dev, x, t)
+                torch.cuda.synchronize()
+                bad_n = nodes.cpu().numpy().astype(np.uint32) != gn[s]
+                bad_x = (x.cpu().numpy().view(np.uint32) != gx[s]).any(axis=1)
+                bad_t = (t.cpu().numpy().view(np.uint32) != gt[s]).any(axis=1)
+                if bad_n.any() or bad_x.any() or bad_t.any():
+                    failures.append("%s step %d: %d / %d / %d of %d slots differ in node id / inputs / targets (first %s)" % (
+                        name, s, int(bad_n.sum()), int(bad_x.sum()), int(bad_t.sum()), batch, np.flatnonzero(bad_n | bad_x | bad_t)[:4]))
+        finally:
+            restore(mod, saved)
+    assert not failures, "\n".join(failures)
+
+
 @pytest.mark.gpu
 def test_gpu_sampler_feeds_training_step(gpu_mod):
     """generate -> training_step, the loop of NeuralBVHRenderer::optimisation step (neural_bvh_renderer.cu:113-260):
