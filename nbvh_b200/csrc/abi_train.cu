@@ -486,6 +486,8 @@ static int ensure_training_state(nbvh_ctx *ctx, uint32_t batch, cudaStream_t st)
         CU_TRY(ctx, cudaMalloc(&ctx->d_steps, n * sizeof(uint32_t)));
         ctx->train_state_valid = false;
     }
+    if (!ctx->d_wgrad_partial)
+        CU_TRY(ctx, cudaMalloc(&ctx->d_wgrad_partial, (size_t)ctx->num_sms * ctx->n_mlp_params * sizeof(float)));
     if (!ctx->d_loss)
         CU_TRY(ctx, cudaMalloc(&ctx->d_loss, sizeof(float)));
     if (!ctx->train_state_valid) {
@@ -538,6 +540,7 @@ int nbvh_training_forward_backward(nbvh_ctx *ctx, const float *in, const float *
     memset(&tp, 0, sizeof(tp));
     tp.feat = ctx->d_feat, tp.dfeat = ctx->d_dfeat, tp.target = target, tp.per_sample_loss = per_sample_loss;
     tp.wgrad = ctx->d_grads, tp.loss_sum = loss_dev, tp.batch = batch;
+    tp.wgrad_partial = ctx->d_wgrad_partial, tp.n_matrix = (uint32_t)ctx->n_mlp_params;
     tp.n_total    = global_batch * ctx->pt_const.output_network_dims;
     tp.loss_scale = 128.f; // default_loss_scale<__half>() (ext/tiny-cuda-nn common.h:232)
     const nbvh_pt_output_constants &pc = ctx->pt_const;

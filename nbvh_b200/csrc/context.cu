@@ -99,8 +99,8 @@ int rebuild_layout(nbvh_ctx *ctx)
         cudaFree(ctx->d_wimg);
     ctx->d_params = nullptr, ctx->d_wimg = nullptr;
     ctx->params_loaded = false;
-    cudaFree(ctx->own_grads), cudaFree(ctx->d_master), cudaFree(ctx->d_m), cudaFree(ctx->d_v), cudaFree(ctx->d_steps);
-    ctx->d_grads = ctx->own_grads = ctx->d_master = ctx->d_m = ctx->d_v = nullptr;
+    cudaFree(ctx->own_grads), cudaFree(ctx->d_master), cudaFree(ctx->d_m), cudaFree(ctx->d_v), cudaFree(ctx->d_steps), cudaFree(ctx->d_wgrad_partial);
+    ctx->d_grads = ctx->own_grads = ctx->d_master = ctx->d_m = ctx->d_v = ctx->d_wgrad_partial = nullptr;
     ctx->d_steps = nullptr;
     ctx->train_state_valid = false;
     CU_TRY(ctx, cudaMalloc(&ctx->d_params, ctx->n_params * sizeof(uint16_t)));
@@ -364,6 +364,7 @@ void nbvh_destroy(nbvh_ctx *ctx)
     cudaFree(ctx->d_m);
     cudaFree(ctx->d_v);
     cudaFree(ctx->d_steps);
+    cudaFree(ctx->d_wgrad_partial);
     cudaFree(ctx->d_feat);
     cudaFree(ctx->d_dfeat);
     cudaFree(ctx->d_loss);

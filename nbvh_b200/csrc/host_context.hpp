@@ -196,6 +196,7 @@ struct nbvh_ctx {
     // training state (allocated lazily): tcnn::Trainer's buffers (trainer.h:68-87) + Adam moments and step counters
     float *d_grads = nullptr, *d_master = nullptr, *d_m = nullptr, *d_v = nullptr;
     uint32_t *d_steps = nullptr;
+    float *d_wgrad_partial = nullptr; // num_sms x n_mlp_params: per-CTA weight-gradient sums of k_train_mlp (training.cu)
     uint8_t *d_feat = nullptr, *d_dfeat = nullptr;
     uint32_t feat_capacity = 0; // samples
     float *d_loss = nullptr;

@@ -161,7 +161,10 @@ struct TrainParams {
     uint8_t *dfeat;         // fp16 dL/dfeatures, same layout
     const float *target;    // batch x n_out
     float *per_sample_loss; // batch x 16 (ctx.L of tcnn) or nullptr
-    float *wgrad;           // fp32 gradients of the MLP matrices (accumulated with atomics)
+    float *wgrad;           // fp32 gradients of the MLP matrices
+    float *wgrad_partial;   // gridDim.x x n_matrix: every CTA stores its TMEM-resident sums here, k_reduce_wgrad adds them up in a fixed
+                            // order (148 CTAs adding atomically to the same 19 k addresses cost a quarter of the kernel); null: atomics
+    uint32_t n_matrix;      // number of MLP matrix weights
     float *loss_sum;        // device accumulator of the batch loss
     uint32_t batch, n_total;
     float loss_scale;

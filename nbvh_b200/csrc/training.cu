@@ -239,8 +239,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 // mbarriers: `ready[s]` (128 arrivals: operands of the slot's next step are in shared memory and its TMEM reads are done) and
 // `done[s]` (tcgen05.commit of the step's MMAs).  A tile is 10 steps for the shipped network: 5 forward layers, then per layer,
 // last to first, the weight-gradient MMAs + the data-gradient MMAs.
+#ifdef NBVH_TRAIN_TWO_ISSUERS // A/B variant: one MMA-issuing warp per slot (the weight-gradient accumulators are zeroed up front)
+#define NBVH_TRAIN_ISSUER_WARPS(slots) (slots)
+#else
+#define NBVH_TRAIN_ISSUER_WARPS(slots) 1
+#endif
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
+}
+
 template <int kSlots>
-__global__ void __launch_bounds__(kSlots *kTileRows + 32, 1)
+__global__ void __launch_bounds__(kSlots *kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(kSlots), 1)
 k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -248,7 +258,7 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     const TrainSmem lay     = train_smem_layout(nc.wimg_bytes, nc.in_k, n_hidden, kSlots);
     const uint32_t tid      = threadIdx.x;
     const uint32_t warp     = tid >> 5, lane = tid & 31u;
-    const bool is_issuer    = warp == (uint32_t)(kSlots * 4);
+    const bool is_issuer    = warp >= (uint32_t)(kSlots * 4);
     const uint32_t slot     = is_issuer ? 0u : tid / kTileRows;
     const uint32_t row      = tid % kTileRows;
     const uint32_t bar0     = smem_u32(smem + lay.bar_off);
@@ -292,6 +302,17 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     const uint32_t my_tiles   = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
     const uint32_t n_rounds   = (my_tiles + (uint32_t)kSlots - 1u) / (uint32_t)kSlots;
 
+#ifdef NBVH_TRAIN_TWO_ISSUERS
+    if (!is_issuer && slot == 0u) {
+        const uint32_t total = train_tmem_cols(nc.in_k, nc.n_layers, (uint32_t)kSlots);
+        for (uint32_t c0 = col_dw; c0 < total; c0 += 16u)
+            tmem_st16_zero(tmem + ((row & ~31u) << 16) + c0);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+#endif
     if (is_issuer) {
         // ================================================================ MMA issuer
         if (lane == 0) {
@@ -305,6 +326,10 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                     for (int sl = 0; sl < kSlots; ++sl) {
                         if (round * (uint32_t)kSlots + (uint32_t)sl >= my_tiles)
                             continue;
+#ifdef NBVH_TRAIN_TWO_ISSUERS
+                        if ((uint32_t)sl != warp - (uint32_t)(kSlots * 4))
+                            continue;
+#endif
                         const uint32_t base    = smem_u32(smem + lay.slot_off + (uint32_t)sl * lay.slot_bytes);
                         const uint32_t a0_addr = base + lay.a0_off, h_addr = base + lay.h_off, dzo_addr = base + lay.dzo_off;
                         const uint32_t col_z   = (uint32_t)sl * slot_cols;
@@ -320,18 +345,22 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                             ready_phase[sl] ^= 1u;
                         }
                         tc_fence_after_sync();
+                        // Descriptors advance by constant increments (16-byte units in the low word), so one MMA costs two 64-bit adds:
+                        // this thread's instruction stream paces the whole CTA.
                         if (step < nc.n_layers) {
                             // ---- forward layer `step`: Z = A . W^T
-                            const uint32_t layer = step;
-                            const uint32_t k_in  = layer == 0u ? nc.in_k : (uint32_t)kNeurons;
+                            const uint32_t layer  = step;
+                            const uint32_t k_in   = layer == 0u ? nc.in_k : (uint32_t)kNeurons;
                             const uint32_t a_addr = layer == 0u ? a0_addr : h_addr + (layer - 1u) * h_bytes;
-                            const uint32_t n_out = layer + 1u == nc.n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
-                            const uint32_t sbo   = (k_in >> 3) * 128u;
-                            const uint32_t idesc = umma_idesc(128u, n_out, 0u, 0u);
-                            const uint32_t w_l   = w_smem + nc.layer_off[layer];
-                            for (uint32_t k = 0; k < k_in; k += 16u)
-                                umma_f16(tmem + col_z, umma_desc(a_addr + (k >> 3) * 128u, kLBO, sbo), umma_desc(w_l + (k >> 3) * 128u, kLBO, sbo),
-                                         idesc, k > 0u ? 1u : 0u);
+                            const uint32_t n_out  = layer + 1u == nc.n_layers ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
+                            const uint32_t sbo    = (k_in >> 3) * 128u;
+                            const uint32_t idesc  = umma_idesc(128u, n_out, 0u, 0u);
+                            uint64_t ad = umma_desc(a_addr, kLBO, sbo), bd = umma_desc(w_smem + nc.layer_off[layer], kLBO, sbo);
+                            umma_f16(tmem + col_z, ad, bd, idesc, 0u);
+                            for (uint32_t k = 16u; k < k_in; k += 16u) {
+                                ad += 16u, bd += 16u; // two core matrices (256 bytes) along K
+                                umma_f16(tmem + col_z, ad, bd, idesc, 1u);
+                            }
                         } else {
                             // ---- backward of layer `layer`: dW_layer += dZ^T A_{layer-1};  dA_{layer-1} = dZ W_layer
                             const uint32_t layer   = 2u * nc.n_layers - 1u - step;
@@ -343,30 +372,39 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                             const uint32_t dz_rg   = last ? rg_o : rg_h;
                             const uint32_t dz_n    = last ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
                             const uint32_t dw_col  = col_dw + (layer == 0u ? 0u : nc.in_k + (layer - 1u) * kNeurons);
+#ifdef NBVH_TRAIN_TWO_ISSUERS
+                            const uint32_t fresh   = 0u;
+                            (void)dw_started;
+#else
                             const uint32_t fresh   = (dw_started >> layer) & 1u ? 0u : 1u;
                             dw_started |= 1u << layer;
-                            // weight gradient, K = the 128 samples of the tile (8 steps of 16), both operands MN-major
-                            if (last) {
-                                // transposed: D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
-                                const uint32_t idesc = umma_idesc(64u, kOutPadded, 1u, 1u);
-                                for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
-                                    umma_f16(tmem + dw_col, umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u),
-                                             umma_desc_mn(dz_addr + ks * 2u * dz_rg, dz_rg, 128u), idesc, (fresh && ks == 0u) ? 0u : 1u);
-                            } else {
-                                // D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
-                                const uint32_t idesc = umma_idesc(64u, kin, 1u, 1u);
-                                for (uint32_t ks = 0; ks < (uint32_t)kTileRows / 16u; ++ks)
-                                    umma_f16(tmem + dw_col, umma_desc_mn(dz_addr + ks * 2u * dz_rg, dz_rg, 128u),
-                                             umma_desc_mn(in_addr + ks * 2u * in_rg, in_rg, 128u), idesc, (fresh && ks == 0u) ? 0u : 1u);
+#endif
+                            // weight gradient, K = the 128 samples of the tile (8 steps of 16 rows = two row groups), both operands MN-major:
+                            //   hidden / first: D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
+                            //   last (transposed): D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
+                            {
+                                const uint32_t idesc = last ? umma_idesc(64u, kOutPadded, 1u, 1u) : umma_idesc(64u, kin, 1u, 1u);
+                                const uint64_t dzd = umma_desc_mn(dz_addr, dz_rg, 128u), ind = umma_desc_mn(in_addr, in_rg, 128u);
+                                uint64_t ad = last ? ind : dzd, bd = last ? dzd : ind;
+                                const uint32_t a_inc = (last ? in_rg : dz_rg) >> 3, b_inc = (last ? dz_rg : in_rg) >> 3; // 2 row groups / 16 bytes
+                                umma_f16(tmem + dw_col, ad, bd, idesc, fresh ? 0u : 1u);
+#pragma unroll
+                                for (uint32_t ks = 1; ks < (uint32_t)kTileRows / 16u; ++ks) {
+                                    ad += a_inc, bd += b_inc;
+                                    umma_f16(tmem + dw_col, ad, bd, idesc, 1u);
+                                }
                             }
                             // data gradient: D[128 x kin] = dZ (K-major, K = dz_n) . W_layer viewed MN-major (N = kin, K = out)
                             {
                                 const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
-                                const uint32_t w_l   = w_smem + nc.layer_off[layer];
                                 const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
-                                for (uint32_t k = 0; k < dz_n; k += 16u)
-                                    umma_f16(tmem + col_z, umma_desc(dz_addr + (k >> 3) * 128u, kLBO, dz_rg),
-                                             umma_desc_mn(w_l + (k >> 3) * w_rg, w_rg, 128u), idesc, k > 0u ? 1u : 0u);
+                                uint64_t ad = umma_desc(dz_addr, kLBO, dz_rg), bd = umma_desc_mn(w_smem + nc.layer_off[layer], w_rg, 128u);
+                                const uint32_t b_inc = w_rg >> 3;
+                                umma_f16(tmem + col_z, ad, bd, idesc, 0u);
+                                for (uint32_t k = 16u; k < dz_n; k += 16u) {
+                                    ad += 16u, bd += b_inc;
+                                    umma_f16(tmem + col_z, ad, bd, idesc, 1u);
+                                }
                             }
                         }
                         umma_commit(bar_done((uint32_t)sl)); // implies tcgen05.fence::before_thread_sync
@@ -405,20 +443,21 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                 done_phase ^= 1u;
                 tc_fence_after_sync();
                 if (!last) {
+                    // ReLU after the fp16 rounding (same values: rounding is monotonic and keeps zero), two activations per instruction
                     uint8_t *h_tile = h_tiles + layer * h_bytes;
+                    uint32_t v[64];
+                    tmem_ld64(tmem + col_z + lane_base, v);
+                    tmem_ld_wait();
+                    const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll
-                    for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem + col_z + lane_base + c0, v);
-                        tmem_ld_wait();
-                        uint32_t h[8];
+                    for (uint32_t c = 0; c < (uint32_t)kNeurons / 8u; ++c) {
+                        uint32_t h[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const __half2 p = __floats2half2_rn(fmaxf(__uint_as_float(v[2 * i]), 0.f), fmaxf(__uint_as_float(v[2 * i + 1]), 0.f));
+                        for (int i = 0; i < 4; ++i) {
+                            const __half2 p = __hmax2(__floats2half2_rn(__uint_as_float(v[8 * c + 2 * i]), __uint_as_float(v[8 * c + 2 * i + 1])), zero2);
                             h[i]            = *reinterpret_cast<const uint32_t *>(&p);
                         }
-                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons))        = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) = make_uint4(h[4], h[5], h[6], h[7]);
+                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c, kNeurons)) = make_uint4(h[0], h[1], h[2], h[3]);
                     }
                 } else {
                     uint32_t v[16];
@@ -467,25 +506,23 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                 if (layer > 0) {
                     // dZ_{layer-1} = dA . ReLU'(H_{layer-1}) -> fp16, in place over H_{layer-1} (every MMA that read it has completed)
                     uint8_t *h_tile = h_tiles + (uint32_t)(layer - 1) * h_bytes;
+                    uint32_t v[64];
+                    tmem_ld64(tmem + col_z + lane_base, v);
+                    tmem_ld_wait();
+                    const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll
-                    for (uint32_t c0 = 0; c0 < (uint32_t)kNeurons; c0 += 16u) {
-                        uint32_t v[16];
-                        tmem_ld16(tmem + col_z + lane_base + c0, v);
-                        tmem_ld_wait();
-                        uint4 *p0 = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c0 >> 3, kNeurons));
-                        uint4 *p1 = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons));
-                        const uint4 m0 = *p0, m1 = *p1;
-                        const uint32_t mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-                        uint32_t h[8];
+                    for (uint32_t c = 0; c < (uint32_t)kNeurons / 8u; ++c) {
+                        uint4 *pm      = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c, kNeurons));
+                        const uint4 m  = *pm;
+                        const uint32_t mk[4] = {m.x, m.y, m.z, m.w};
+                        uint32_t h[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float a   = (mk[i] & 0x00007FFFu) ? __uint_as_float(v[2 * i]) : 0.f; // stored activation > 0 (fp16 bits)
-                            const float b   = (mk[i] & 0x7FFF0000u) ? __uint_as_float(v[2 * i + 1]) : 0.f;
-                            const __half2 p = __floats2half2_rn(a, b);
-                            h[i]            = *reinterpret_cast<const uint32_t *>(&p);
+                        for (int i = 0; i < 4; ++i) {
+                            // stored activation > 0 (per half: all-ones / zero mask) selects the rounded gradient
+                            const __half2 p = __floats2half2_rn(__uint_as_float(v[8 * c + 2 * i]), __uint_as_float(v[8 * c + 2 * i + 1]));
+                            h[i] = *reinterpret_cast<const uint32_t *>(&p) & __hgt2_mask(*reinterpret_cast<const __half2 *>(&mk[i]), zero2);
                         }
-                        *p0 = make_uint4(h[0], h[1], h[2], h[3]);
-                        *p1 = make_uint4(h[4], h[5], h[6], h[7]);
+                        *pm = make_uint4(h[0], h[1], h[2], h[3]);
                     }
                     fence_proxy_async_smem();
                 } else {
@@ -543,13 +580,28 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                 tmem_ld16(tmem + col + lane_base + c0, v);
                 tmem_ld_wait();
                 if (lane < 16u) {
+                    // hidden/first: D[out = r][in = c0 + i]; last (transposed): D[in = r][out = c0 + i]
+                    if (tp.wgrad_partial) {
+                        float *dst = tp.wgrad_partial + (size_t)blockIdx.x * tp.n_matrix;
+                        if (last) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float g = __uint_as_float(v[i]);
-                        if (g != 0.f) {
-                            // hidden/first: D[out = r][in = c0 + i]; last (transposed): D[in = r][out = c0 + i]
-                            const size_t idx = last ? goff + (size_t)(c0 + i) * kNeurons + r : goff + (size_t)r * kin + c0 + i;
-                            atomicAdd(tp.wgrad + idx, g);
+                            for (int i = 0; i < 16; ++i)
+                                dst[goff + (size_t)(c0 + i) * kNeurons + r] = __uint_as_float(v[i]);
+                        } else {
+                            float4 *d4 = reinterpret_cast<float4 *>(dst + goff + (size_t)r * kin + c0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                    __uint_as_float(v[4 * i + 3]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float g = __uint_as_float(v[i]);
+                            if (g != 0.f) {
+                                const size_t idx = last ? goff + (size_t)(c0 + i) * kNeurons + r : goff + (size_t)r * kin + c0 + i;
+                                atomicAdd(tp.wgrad + idx, g);
+                            }
                         }
                     }
                 }
@@ -564,6 +616,20 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
         tc_fence_after_sync();
         tmem_dealloc(tmem, 512u);
     }
+}
+
+// wgrad[i] = sum over the CTAs of k_train_mlp of their partial sums, in CTA order (deterministic)
+__global__ void __launch_bounds__(256)
+k_reduce_wgrad(const float *__restrict__ partial, uint32_t n_parts, uint32_t n, float *__restrict__ wgrad)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float acc = 0.f;
+#pragma unroll 4
+    for (uint32_t p = 0; p < n_parts; ++p)
+        acc += partial[(size_t)p * n + i];
+    wgrad[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ k_grid_backward
@@ -716,9 +782,13 @@ cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_
     const uint32_t grid    = want < (uint32_t)num_sms ? want : (uint32_t)num_sms;
     const uint32_t smem    = train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u, slots).total;
     if (slots == 2u)
-        k_train_mlp<2><<<grid, 2 * kTileRows + 32, smem, stream>>>(nc, tp);
+        k_train_mlp<2><<<grid, 2 * kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(2), smem, stream>>>(nc, tp);
     else
-        k_train_mlp<1><<<grid, kTileRows + 32, smem, stream>>>(nc, tp);
+        k_train_mlp<1><<<grid, kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(1), smem, stream>>>(nc, tp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !tp.wgrad_partial)
+        return e;
+    k_reduce_wgrad<<<(tp.n_matrix + 255u) / 256u, 256, 0, stream>>>(tp.wgrad_partial, grid, tp.n_matrix, tp.wgrad);
     return cudaGetLastError();
 }
 
@@ -732,12 +802,17 @@ cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint
     while (n_small < nc.n_levels && nc.lv[n_small].size * 16u <= 64u * 1024u)
         ++n_small;
     const uint64_t total = (uint64_t)batch * nc.n_points;
-    if (n_small) {
-        uint32_t bx = (uint32_t)((total + 255u) / 256u);
-        const uint32_t cap = (uint32_t)num_sms; // few, long-lived blocks: one flush of the table per block
+    // one launch per privatised level with exactly its table in shared memory: the small tables leave room for many resident CTAs,
+    // whose warps hide the latency of the shared-memory atomics (one flush of the table per CTA)
+    for (uint32_t l = 0; l < n_small; ++l) {
+        const uint32_t smem = nc.lv[l].size * 16u;
+        uint32_t per_sm     = (200u * 1024u) / (smem + 1024u);
+        per_sm              = per_sm > 8u ? 8u : per_sm < 1u ? 1u : per_sm;
+        uint32_t bx         = (uint32_t)((total + 255u) / 256u);
+        const uint32_t cap  = (uint32_t)num_sms * per_sm;
         if (bx > cap)
             bx = cap;
-        k_grid_backward<<<dim3(bx, n_small), 256, 64 * 1024, stream>>>(nc, in, dfeat, batch, n_in_dims, 0u, 1u, grid_grads);
+        k_grid_backward<<<dim3(bx, 1), 256, smem, stream>>>(nc, in, dfeat, batch, n_in_dims, l, 1u, grid_grads);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return e;

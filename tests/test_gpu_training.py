@@ -204,7 +204,7 @@ def test_long_loss_curve_matches_tcnn():
         ours, ref = np.median(losses[lo:hi]), np.median(runs[:, lo:hi], axis=1)
         print("steps [%d, %d): median loss %.4f, tcnn runs %s" % (lo, hi, ours, np.round(ref, 4)))
         assert 0.90 * ref.min() <= ours <= 1.10 * ref.max(), (lo, hi, ours, ref)
-    assert np.median(losses[-100:]) < 0.3 * losses[0]
+    assert np.median(losses[700:]) < 0.3 * losses[0]  # (a 100-step window can sit on one of the random spikes)
 
 
 def test_library_communicator_with_one_rank_leaves_the_step_unchanged(env):

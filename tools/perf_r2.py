@@ -73,6 +73,9 @@ def main():
     ms8 = timeit(lambda: mod.neural_render_samples(0, 8), iters=5, warmup=2)
     out["frame_8spl"] = {"ms_per_launch": ms8, "ms_per_sample_frame": ms8 / 8}
     print(json.dumps(out), flush=True)
+    if "--frame-only" in sys.argv:
+        mod.close()
+        return
 
     # ---- optimisation: sampler + step kernels
     tl, ti, bl, _ = nbvh_b200.load_scene_arrays(root, with_neural_mesh=True, with_attributes=True)
