@@ -139,6 +139,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
                  : "r"(taddr)
                  : "memory");
 }
+// 32 accumulator columns of this thread's TMEM lane in one instruction
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr)
+                 : "memory");
+}
+// elects one lane of a converged warp (the others skip the predicated instruction stream)
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile("{\n"
+                 ".reg .pred P;\n"
+                 "elect.sync _|P, 0xFFFFFFFF;\n"
+                 "selp.u32 %0, 1, 0, P;\n"
+                 "}"
+                 : "=r"(pred));
+    return pred != 0u;
+}
 // 64 accumulator columns of this thread's TMEM lane in one instruction (the epilogues of the training kernel)
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64])
 {

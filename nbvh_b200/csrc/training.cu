@@ -20,6 +20,7 @@
 
 #include <cuda_fp16.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace nbvh {
 
@@ -144,15 +145,16 @@ __device__ __forceinline__ void loss_and_gradient(float target, float prediction
 }
 
 // pt_composite_loss.cuh:19-123 for output element `e` of one sample; returns loss / n_total, grad = scale*g/n_total
-__device__ __forceinline__ float loss_element(const LossConst &lc, const float *tgt, float prediction, uint32_t e, float n_total,
-                                              float loss_scale, float &grad_out)
+// `target` = tgt[e], `target0` = tgt[0] (the visibility target that masks the other terms).  Division by n_total: when n_total is a
+// power of two (every shipped batch size) the product with its exact reciprocal `inv_n` has the same bits and no division sequence.
+__device__ __forceinline__ float loss_element(const LossConst &lc, float target, float target0, float prediction, uint32_t e, float n_total,
+                                              float inv_n, bool n_pow2, float loss_scale, float &grad_out)
 {
     const uint32_t depth0 = lc.vis_dim, normal0 = depth0 + lc.depth_dim, albedo0 = normal0 + lc.normal_dim,
                    end = albedo0 + lc.albedo_dim;
     float loss = 0.f, grad = 0.f;
     if (e < end) {
-        const float target = tgt[e];
-        const bool ignore  = lc.vis_masking ? (tgt[0] < 0.5f) : false;
+        const bool ignore  = lc.vis_masking ? (target0 < 0.5f) : false;
         if (lc.vis_dim > 0 && e == 0) {
             loss_and_gradient(target, prediction, lc.vis_loss, loss, grad);
             loss *= lc.vis_scale, grad *= lc.vis_scale;
@@ -181,6 +183,10 @@ __device__ __forceinline__ float loss_element(const LossConst &lc, const float *
             }
             loss *= lc.albedo_scale, grad *= lc.albedo_scale;
         }
+    }
+    if (n_pow2) {
+        grad_out = (loss_scale * grad) * inv_n;
+        return loss * inv_n;
     }
     grad_out = loss_scale * grad / n_total;
     return loss / n_total;
@@ -223,34 +229,41 @@ __host__ __device__ inline TrainSmem train_smem_layout(uint32_t wimg_bytes, uint
     s.dzo_off    = s.h_off + n_hidden * kTileRows * kNeurons * 2u;
     s.slot_bytes = s.dzo_off + kTileRows * kOutPadded * 2u;
     s.bar_off    = s.slot_off + slots * s.slot_bytes;
-    s.tmem_off   = s.bar_off + 64u; // mbarriers: weights, then {features, operands ready, MMAs done} per slot
+    s.tmem_off   = s.bar_off + 8u + 32u * slots; // mbarriers: weights, then {features, operands ready, MMAs done, weight-gradient MMAs done} per slot
     s.total      = s.tmem_off + 16u;
     return s;
 }
 
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                 "selp.u32 %0, 1, 0, p;\n"
+                 "}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Warp roles: warps [4 s, 4 s + 4) are the epilogue warps of slot s (thread r of the group owns sample row r = TMEM lane r of the
-// slot's accumulators); the last warp's lane 0 issues every tcgen05.mma of the CTA, alternating between the slots step by step, so
+// Warp roles: warps [8 s, 8 s + 8) are the epilogue warps of slot s -- two groups of four: thread r of either group owns sample row
+// r = TMEM lane r of the slot's accumulators, group g converts columns [32 g, 32 g + 32) (a warp may only read the TMEM lane quarter
+// warp % 4, so the second group halves every epilogue's work per thread instead of its rows); the last warp issues every
+// tcgen05.mma of the CTA -- converged, one elected lane per instruction --, serving whichever slot has its next step ready, so
 // that one slot's epilogue (tcgen05.ld, ReLU / loss / ReLU', fp16 stores) runs under the other slot's MMAs.  Hand-over is by
-// mbarriers: `ready[s]` (128 arrivals: operands of the slot's next step are in shared memory and its TMEM reads are done) and
-// `done[s]` (tcgen05.commit of the step's MMAs).  A tile is 10 steps for the shipped network: 5 forward layers, then per layer,
-// last to first, the weight-gradient MMAs + the data-gradient MMAs.
-#ifdef NBVH_TRAIN_TWO_ISSUERS // A/B variant: one MMA-issuing warp per slot (the weight-gradient accumulators are zeroed up front)
-#define NBVH_TRAIN_ISSUER_WARPS(slots) (slots)
-#else
-#define NBVH_TRAIN_ISSUER_WARPS(slots) 1
-#endif
-__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(0u) : "memory");
-}
-
+// mbarriers: `ready[s]` (256 arrivals: operands of the slot's next step are in shared memory and its TMEM reads are done), `done[s]`
+// (tcgen05.commit of the step's forward / data-gradient MMAs) and `wdone[s]` (commit of its weight-gradient MMAs).  A tile is 10
+// steps for the shipped network: 5 forward layers, then per layer, last to first, the data-gradient + the weight-gradient MMAs.
+constexpr uint32_t kTrainSlotThreads = 2u * kTileRows;
 template <int kSlots>
-__global__ void __launch_bounds__(kSlots *kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(kSlots), 1)
+__global__ void __launch_bounds__(kSlots *kTrainSlotThreads + 32, 1)
 k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainParams tp)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -258,21 +271,24 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     const TrainSmem lay     = train_smem_layout(nc.wimg_bytes, nc.in_k, n_hidden, kSlots);
     const uint32_t tid      = threadIdx.x;
     const uint32_t warp     = tid >> 5, lane = tid & 31u;
-    const bool is_issuer    = warp >= (uint32_t)(kSlots * 4);
-    const uint32_t slot     = is_issuer ? 0u : tid / kTileRows;
+    const bool is_issuer    = warp == (uint32_t)(kSlots * 8);
+    const uint32_t slot     = is_issuer ? 0u : tid / kTrainSlotThreads;
     const uint32_t row      = tid % kTileRows;
+    const uint32_t half     = (tid / kTileRows) & 1u; // column half of the epilogues
     const uint32_t bar0     = smem_u32(smem + lay.bar_off);
     const uint32_t bar_w    = bar0;
-    auto bar_feat  = [&](uint32_t sl) { return bar0 + 8u + 24u * sl; };
-    auto bar_ready = [&](uint32_t sl) { return bar0 + 16u + 24u * sl; };
-    auto bar_done  = [&](uint32_t sl) { return bar0 + 24u + 24u * sl; };
+    auto bar_feat  = [&](uint32_t sl) { return bar0 + 8u + 32u * sl; };
+    auto bar_ready = [&](uint32_t sl) { return bar0 + 16u + 32u * sl; };
+    auto bar_done  = [&](uint32_t sl) { return bar0 + 24u + 32u * sl; };
+    auto bar_wdone = [&](uint32_t sl) { return bar0 + 32u + 32u * sl; };
 
     if (tid == 0) {
         mbar_init(bar_w, 1u);
         for (uint32_t sl = 0; sl < (uint32_t)kSlots; ++sl) {
             mbar_init(bar_feat(sl), 1u);
-            mbar_init(bar_ready(sl), (uint32_t)kTileRows);
+            mbar_init(bar_ready(sl), kTrainSlotThreads);
             mbar_init(bar_done(sl), 1u);
+            mbar_init(bar_wdone(sl), 1u);
         }
         fence_barrier_init();
     }
@@ -300,51 +316,51 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     const uint32_t n_tiles    = (tp.batch + kTileRows - 1u) / kTileRows;
     // tile of (round, slot): blockIdx.x + (round * kSlots + slot) * gridDim.x
     const uint32_t my_tiles   = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
-    const uint32_t n_rounds   = (my_tiles + (uint32_t)kSlots - 1u) / (uint32_t)kSlots;
 
-#ifdef NBVH_TRAIN_TWO_ISSUERS
-    if (!is_issuer && slot == 0u) {
-        const uint32_t total = train_tmem_cols(nc.in_k, nc.n_layers, (uint32_t)kSlots);
-        for (uint32_t c0 = col_dw; c0 < total; c0 += 16u)
-            tmem_st16_zero(tmem + ((row & ~31u) << 16) + c0);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-#endif
     if (is_issuer) {
-        // ================================================================ MMA issuer
-        if (lane == 0) {
-            uint32_t ready_phase[kSlots], feat_phase[kSlots];
+        // ================================================================ MMA issuer (the whole warp runs the loop; one elected lane issues)
+        {
+            // Event-driven: whichever slot has its next step ready is served (the steps are not equally long -- the loss epilogue --, and
+            // strict alternation would make the faster slot wait for the slower one)
+            uint32_t ready_phase[kSlots], feat_phase[kSlots], step_of[kSlots], round_of[kSlots];
+            uint32_t remaining = my_tiles * 2u * nc.n_layers;
             for (int sl = 0; sl < kSlots; ++sl)
-                ready_phase[sl] = feat_phase[sl] = 0u;
+                ready_phase[sl] = feat_phase[sl] = step_of[sl] = round_of[sl] = 0u;
             uint32_t dw_started = 0u; // bit `layer`: the layer's weight-gradient accumulator holds a value
-            for (uint32_t round = 0; round < n_rounds; ++round) {
-                for (uint32_t step = 0; step < 2u * nc.n_layers; ++step) {
+#ifdef NBVH_TRAIN_TIMING
+            long long t_iss = 0, t_all0 = clock64();
+#endif
+            while (remaining) {
+                {
 #pragma unroll
                     for (int sl = 0; sl < kSlots; ++sl) {
-                        if (round * (uint32_t)kSlots + (uint32_t)sl >= my_tiles)
+                        if (round_of[sl] * (uint32_t)kSlots + (uint32_t)sl >= my_tiles)
                             continue;
-#ifdef NBVH_TRAIN_TWO_ISSUERS
-                        if ((uint32_t)sl != warp - (uint32_t)(kSlots * 4))
-                            continue;
+                        const uint32_t step = step_of[sl], round = round_of[sl];
+                        // step 0: the tile's features landed (TMA) and -- after the first tile -- the previous tile's last epilogue
+                        // released the slot's TMEM columns; other steps: the slot's operands are in shared memory
+                        if (step == 0u) {
+                            if (!mbar_test(bar_feat((uint32_t)sl), feat_phase[sl]) || (round > 0u && !mbar_test(bar_ready((uint32_t)sl), ready_phase[sl])))
+                                continue;
+                            feat_phase[sl] ^= 1u;
+                            if (round > 0u)
+                                ready_phase[sl] ^= 1u;
+                        } else {
+                            if (!mbar_test(bar_ready((uint32_t)sl), ready_phase[sl]))
+                                continue;
+                            ready_phase[sl] ^= 1u;
+                        }
+#ifdef NBVH_TRAIN_TIMING
+                        const long long t_i0 = clock64();
 #endif
+                        --remaining;
+                        if (++step_of[sl] == 2u * nc.n_layers)
+                            step_of[sl] = 0u, ++round_of[sl];
                         const uint32_t base    = smem_u32(smem + lay.slot_off + (uint32_t)sl * lay.slot_bytes);
                         const uint32_t a0_addr = base + lay.a0_off, h_addr = base + lay.h_off, dzo_addr = base + lay.dzo_off;
                         const uint32_t col_z   = (uint32_t)sl * slot_cols;
-                        if (step == 0u) {
-                            mbar_wait(bar_feat((uint32_t)sl), feat_phase[sl]); // the tile's features landed (TMA)
-                            feat_phase[sl] ^= 1u;
-                            if (round > 0u) { // the previous tile's last epilogue released the slot's TMEM columns
-                                mbar_wait(bar_ready((uint32_t)sl), ready_phase[sl]);
-                                ready_phase[sl] ^= 1u;
-                            }
-                        } else {
-                            mbar_wait(bar_ready((uint32_t)sl), ready_phase[sl]);
-                            ready_phase[sl] ^= 1u;
-                        }
                         tc_fence_after_sync();
+                        if (elect_one_sync()) {
                         // Descriptors advance by constant increments (16-byte units in the low word), so one MMA costs two 64-bit adds:
                         // this thread's instruction stream paces the whole CTA.
                         if (step < nc.n_layers) {
@@ -372,13 +388,23 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                             const uint32_t dz_rg   = last ? rg_o : rg_h;
                             const uint32_t dz_n    = last ? (uint32_t)kOutPadded : (uint32_t)kNeurons;
                             const uint32_t dw_col  = col_dw + (layer == 0u ? 0u : nc.in_k + (layer - 1u) * kNeurons);
-#ifdef NBVH_TRAIN_TWO_ISSUERS
-                            const uint32_t fresh   = 0u;
-                            (void)dw_started;
-#else
                             const uint32_t fresh   = (dw_started >> layer) & 1u ? 0u : 1u;
                             dw_started |= 1u << layer;
-#endif
+                            // data gradient: D[128 x kin] = dZ (K-major, K = dz_n) . W_layer viewed MN-major (N = kin, K = out)
+                            {
+                                const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
+                                const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
+                                uint64_t ad = umma_desc(dz_addr, kLBO, dz_rg), bd = umma_desc_mn(w_smem + nc.layer_off[layer], w_rg, 128u);
+                                const uint32_t b_inc = w_rg >> 3;
+                                umma_f16(tmem + col_z, ad, bd, idesc, 0u);
+                                for (uint32_t k = 16u; k < dz_n; k += 16u) {
+                                    ad += 16u, bd += b_inc;
+                                    umma_f16(tmem + col_z, ad, bd, idesc, 1u);
+                                }
+                            }
+                            // the epilogue only needs dA: it may load and convert it while the weight-gradient MMAs run; it stores dZ
+                            // (in place over the tile those MMAs read) after their own commit
+                            umma_commit(bar_done((uint32_t)sl));
                             // weight gradient, K = the 128 samples of the tile (8 steps of 16 rows = two row groups), both operands MN-major:
                             //   hidden / first: D[64 (out) x kin] += dZ^T (M = 64) . A_{in} (N = kin)
                             //   last (transposed): D[64 (in) x 16 (out)] += A_{in}^T (M = 64) . dZ_out (N = 16)
@@ -394,23 +420,22 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                                     umma_f16(tmem + dw_col, ad, bd, idesc, 1u);
                                 }
                             }
-                            // data gradient: D[128 x kin] = dZ (K-major, K = dz_n) . W_layer viewed MN-major (N = kin, K = out)
-                            {
-                                const uint32_t idesc = umma_idesc(128u, kin, 0u, 1u);
-                                const uint32_t w_rg  = (kin >> 3) * 128u; // row-group (8 outputs) stride of the forward image
-                                uint64_t ad = umma_desc(dz_addr, kLBO, dz_rg), bd = umma_desc_mn(w_smem + nc.layer_off[layer], w_rg, 128u);
-                                const uint32_t b_inc = w_rg >> 3;
-                                umma_f16(tmem + col_z, ad, bd, idesc, 0u);
-                                for (uint32_t k = 16u; k < dz_n; k += 16u) {
-                                    ad += 16u, bd += b_inc;
-                                    umma_f16(tmem + col_z, ad, bd, idesc, 1u);
-                                }
-                            }
+                            umma_commit(bar_wdone((uint32_t)sl));
                         }
-                        umma_commit(bar_done((uint32_t)sl)); // implies tcgen05.fence::before_thread_sync
+                        if (step < nc.n_layers)
+                            umma_commit(bar_done((uint32_t)sl)); // implies tcgen05.fence::before_thread_sync
+                        }
+                        __syncwarp();
+#ifdef NBVH_TRAIN_TIMING
+                        t_iss += clock64() - t_i0;
+#endif
                     }
                 }
             }
+#ifdef NBVH_TRAIN_TIMING
+            if (blockIdx.x == 0 && lane == 0)
+                printf("[k_train_mlp] issuer: %lld cycles total, %lld issuing (%u tiles)\n", clock64() - t_all0, t_iss, my_tiles);
+#endif
         }
     } else {
         // ================================================================ epilogue warps of slot `slot`
@@ -421,120 +446,165 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
         const uint32_t col_z     = slot * slot_cols;
         const uint32_t lane_base = (row & ~31u) << 16;
         const float n_total_f    = (float)tp.n_total;
-        uint32_t done_phase      = 0u;
+        const bool n_total_pow2  = tp.n_total != 0u && (tp.n_total & (tp.n_total - 1u)) == 0u;
+        const float inv_n_total  = 1.f / n_total_f;
+        uint32_t done_phase      = 0u, wdone_phase = 0u;
+#ifdef NBVH_TRAIN_TIMING
+        long long t_wait = 0, t_wwait = 0, t_loss = 0, t_ld = 0, t_cvt = 0, t_fence = 0, t_e0 = clock64();
+#define TT_BEGIN const long long tt0_ = clock64();
+#define TT_END(acc) acc += clock64() - tt0_;
+#else
+#define TT_BEGIN
+#define TT_END(acc)
+#endif
         float loss_acc           = 0.f;
-        if (row == 0 && slot < my_tiles) { // first tile of the slot
+        const bool lead = row == 0 && half == 0u; // the slot's TMA-issuing thread
+        if (lead && slot < my_tiles) { // first tile of the slot
             mbar_expect_tx(bar_feat(slot), tile_bytes);
             tma_bulk_g2s(smem_u32(a0_tile), tp.feat + (size_t)(blockIdx.x + slot * gridDim.x) * tile_bytes, tile_bytes, bar_feat(slot));
         }
+        const __half2 zero2 = __float2half2_rn(0.f);
+        const uint32_t col_h = 32u * half; // this thread's columns of a 64-wide accumulator: [col_h, col_h + 32) = 16-byte chunks 4 half ..
         for (uint32_t round = 0; round * (uint32_t)kSlots + slot < my_tiles; ++round) {
             const uint32_t tile = blockIdx.x + (round * (uint32_t)kSlots + slot) * gridDim.x;
             const uint32_t s    = tile * kTileRows + row;
             const bool valid    = s < tp.batch;
-            float tgt[8];
+            // the loss epilogue is split by output element: group `half` owns elements [4 half, 4 half + 4) of the row
+            float tgt[4];
+            const float tgt0 = (valid && nc.n_out > 0u) ? __ldg(tp.target + (size_t)s * nc.n_out) : 0.f;
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
-                tgt[j] = (valid && j < nc.n_out) ? __ldg(tp.target + (size_t)s * nc.n_out + j) : 0.f;
+            for (uint32_t j = 0; j < 4; ++j)
+                tgt[j] = (valid && 4u * half + j < nc.n_out) ? __ldg(tp.target + (size_t)s * nc.n_out + 4u * half + j) : 0.f;
             // ================= forward: activations of every layer stay in shared memory
-            float y[8];
             for (uint32_t layer = 0; layer < nc.n_layers; ++layer) {
                 const bool last = layer + 1u == nc.n_layers;
-                mbar_wait(bar_done(slot), done_phase);
+                {
+                    TT_BEGIN
+                    mbar_wait(bar_done(slot), done_phase);
+                    TT_END(t_wait)
+                }
                 done_phase ^= 1u;
                 tc_fence_after_sync();
                 if (!last) {
                     // ReLU after the fp16 rounding (same values: rounding is monotonic and keeps zero), two activations per instruction
                     uint8_t *h_tile = h_tiles + layer * h_bytes;
-                    uint32_t v[64];
-                    tmem_ld64(tmem + col_z + lane_base, v);
-                    tmem_ld_wait();
-                    const __half2 zero2 = __float2half2_rn(0.f);
+                    uint32_t v[32];
+                    {
+                        TT_BEGIN
+                        tmem_ld32(tmem + col_z + lane_base + col_h, v);
+                        tmem_ld_wait();
+                        TT_END(t_ld)
+                    }
+                    TT_BEGIN
 #pragma unroll
-                    for (uint32_t c = 0; c < (uint32_t)kNeurons / 8u; ++c) {
+                    for (uint32_t c = 0; c < 4u; ++c) {
                         uint32_t h[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const __half2 p = __hmax2(__floats2half2_rn(__uint_as_float(v[8 * c + 2 * i]), __uint_as_float(v[8 * c + 2 * i + 1])), zero2);
                             h[i]            = *reinterpret_cast<const uint32_t *>(&p);
                         }
-                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c, kNeurons)) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, 4u * half + c, kNeurons)) = make_uint4(h[0], h[1], h[2], h[3]);
                     }
+                    TT_END(t_cvt)
                 } else {
+                    TT_BEGIN
                     uint32_t v[16];
                     tmem_ld16(tmem + col_z + lane_base, v);
                     tmem_ld_wait();
+                    const uint32_t e0 = 4u * half;
+                    float y[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) // the training forward hands fp16 predictions to the loss (trainer.h:108-131)
-                        y[i] = h2f_round(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[i]))));
+                    for (int i = 0; i < 4; ++i) // the training forward hands fp16 predictions to the loss (trainer.h:108-131)
+                        y[i] = h2f_round(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(half ? v[4 + i] : v[i]))));
                     // ---- loss + output-activation backward -> dZ_out tile (128 x 16 fp16, loss-scaled)
-                    float dz[8];
+                    float dz[4];
                     float lrow = 0.f;
 #pragma unroll
-                    for (uint32_t e = 0; e < 8; ++e) {
-                        float g       = 0.f;
-                        const float l = (valid && e < nc.n_out) ? loss_element(tp.loss, tgt, y[e], e, n_total_f, tp.loss_scale, g) : 0.f;
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        const uint32_t e = e0 + j;
+                        float g          = 0.f;
+                        const float l    = (valid && e < nc.n_out)
+                                               ? loss_element(tp.loss, tgt[j], tgt0, y[j], e, n_total_f, inv_n_total, n_total_pow2, tp.loss_scale, g)
+                                               : 0.f;
                         if (tp.per_sample_loss && valid)
                             tp.per_sample_loss[(size_t)s * kOutPadded + e] = l;
                         lrow += l;
                         g     = valid ? h2f_round(g) : 0.f;
-                        dz[e] = g * (y[e] * (1.f - y[e])); // sigmoid' from the output value
+                        dz[j] = g * (y[j] * (1.f - y[j])); // sigmoid' from the output value
                     }
                     if (tp.per_sample_loss && valid) {
 #pragma unroll
-                        for (uint32_t e = 8; e < (uint32_t)kOutPadded; ++e)
-                            tp.per_sample_loss[(size_t)s * kOutPadded + e] = 0.f;
+                        for (uint32_t j = 0; j < 4; ++j)
+                            tp.per_sample_loss[(size_t)s * kOutPadded + 8u + e0 + j] = 0.f;
                     }
                     loss_acc += lrow;
-                    uint32_t h[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const __half2 p = __floats2half2_rn(dz[2 * i], dz[2 * i + 1]);
-                        h[i]            = *reinterpret_cast<const uint32_t *>(&p);
-                    }
-                    *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 0u, kOutPadded)) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(dzo_tile + tile_chunk_off(row, 1u, kOutPadded)) = make_uint4(0u, 0u, 0u, 0u);
+                    const __half2 p0 = __floats2half2_rn(dz[0], dz[1]), p1 = __floats2half2_rn(dz[2], dz[3]);
+                    *reinterpret_cast<uint2 *>(dzo_tile + tile_chunk_off(row, 0u, kOutPadded) + 8u * half) =
+                        make_uint2(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1));
+                    *reinterpret_cast<uint2 *>(dzo_tile + tile_chunk_off(row, 1u, kOutPadded) + 8u * half) = make_uint2(0u, 0u);
+                    TT_END(t_loss)
                 }
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                mbar_arrive(bar_ready(slot));
+                {
+                    TT_BEGIN
+                    fence_proxy_async_smem();
+                    tc_fence_before_sync();
+                    mbar_arrive(bar_ready(slot));
+                    TT_END(t_fence)
+                }
             }
-            // ================= backward, layer = last .. 0: the issuer ran dW_layer and dA_{layer-1}; here dZ_{layer-1}
+            // ================= backward, layer = last .. 0: the issuer runs dA_{layer-1} (commit: done) and dW_layer (commit: wdone);
+            // here dZ_{layer-1}
             for (int layer = (int)nc.n_layers - 1; layer >= 0; --layer) {
-                mbar_wait(bar_done(slot), done_phase);
+                {
+                    TT_BEGIN
+                    mbar_wait(bar_done(slot), done_phase);
+                    TT_END(t_wait)
+                }
                 done_phase ^= 1u;
                 tc_fence_after_sync();
                 if (layer > 0) {
-                    // dZ_{layer-1} = dA . ReLU'(H_{layer-1}) -> fp16, in place over H_{layer-1} (every MMA that read it has completed)
+                    // dZ_{layer-1} = dA . ReLU'(H_{layer-1}) -> fp16: computed while the weight-gradient MMAs (which read H_{layer-1}) run,
+                    // stored in place over H_{layer-1} once they have completed
                     uint8_t *h_tile = h_tiles + (uint32_t)(layer - 1) * h_bytes;
-                    uint32_t v[64];
-                    tmem_ld64(tmem + col_z + lane_base, v);
+                    uint32_t v[32];
+                    tmem_ld32(tmem + col_z + lane_base + col_h, v);
                     tmem_ld_wait();
-                    const __half2 zero2 = __float2half2_rn(0.f);
+                    uint32_t h[4][4];
 #pragma unroll
-                    for (uint32_t c = 0; c < (uint32_t)kNeurons / 8u; ++c) {
-                        uint4 *pm      = reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, c, kNeurons));
-                        const uint4 m  = *pm;
+                    for (uint32_t c = 0; c < 4u; ++c) {
+                        const uint4 m = *reinterpret_cast<const uint4 *>(h_tile + tile_chunk_off(row, 4u * half + c, kNeurons));
                         const uint32_t mk[4] = {m.x, m.y, m.z, m.w};
-                        uint32_t h[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             // stored activation > 0 (per half: all-ones / zero mask) selects the rounded gradient
                             const __half2 p = __floats2half2_rn(__uint_as_float(v[8 * c + 2 * i]), __uint_as_float(v[8 * c + 2 * i + 1]));
-                            h[i] = *reinterpret_cast<const uint32_t *>(&p) & __hgt2_mask(*reinterpret_cast<const __half2 *>(&mk[i]), zero2);
+                            h[c][i] = *reinterpret_cast<const uint32_t *>(&p) & __hgt2_mask(*reinterpret_cast<const __half2 *>(&mk[i]), zero2);
                         }
-                        *pm = make_uint4(h[0], h[1], h[2], h[3]);
                     }
+                    {
+                        TT_BEGIN
+                        mbar_wait(bar_wdone(slot), wdone_phase);
+                        TT_END(t_wwait)
+                    }
+                    wdone_phase ^= 1u;
+#pragma unroll
+                    for (uint32_t c = 0; c < 4u; ++c)
+                        *reinterpret_cast<uint4 *>(h_tile + tile_chunk_off(row, 4u * half + c, kNeurons)) = make_uint4(h[c][0], h[c][1], h[c][2], h[c][3]);
                     fence_proxy_async_smem();
                 } else {
-                    // the feature tile is free (dW_0 has completed): fetch the slot's next tile under this epilogue
+                    // the feature tile is free once dW_0 has completed: fetch the slot's next tile under this epilogue
                     const uint32_t next_idx = (round + 1u) * (uint32_t)kSlots + slot;
-                    if (row == 0 && next_idx < my_tiles) {
+                    if (lead && next_idx < my_tiles) {
+                        mbar_wait(bar_wdone(slot), wdone_phase);
                         mbar_expect_tx(bar_feat(slot), tile_bytes);
                         tma_bulk_g2s(smem_u32(a0_tile), tp.feat + (size_t)(blockIdx.x + next_idx * gridDim.x) * tile_bytes, tile_bytes, bar_feat(slot));
                     }
-                    // dL/dfeatures -> fp16 -> global, same tile-canonical layout as the features
+                    wdone_phase ^= 1u;
+                    // dL/dfeatures -> fp16 -> global, same tile-canonical layout as the features; the 16-column chunks alternate between
+                    // the two warp groups
                     uint8_t *dst = tp.dfeat + (size_t)tile * tile_bytes;
-                    for (uint32_t c0 = 0; c0 < nc.in_k; c0 += 16u) {
+                    for (uint32_t c0 = 16u * half; c0 < nc.in_k; c0 += 32u) {
                         uint32_t v[16];
                         tmem_ld16(tmem + col_z + lane_base + c0, v);
                         tmem_ld_wait();
@@ -552,6 +622,13 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
                 mbar_arrive(bar_ready(slot));
             }
         }
+        if (my_tiles > slot) // the last tile's weight-gradient MMAs (flushed below)
+            mbar_wait(bar_wdone(slot), wdone_phase ^ 1u);
+#ifdef NBVH_TRAIN_TIMING
+        if (blockIdx.x == 0 && lead)
+            printf("[k_train_mlp] slot %u epilogue: %lld cycles total, %lld waiting for MMAs, %lld for weight-gradient MMAs; forward: tmem ld %lld, cvt+store %lld, loss %lld, fence+arrive %lld\n", slot, clock64() - t_e0,
+                   t_wait, t_wwait, t_ld, t_cvt, t_loss, t_fence);
+#endif
         loss_acc = warp_sum(loss_acc);
         if (lane == 0 && tp.loss_sum && loss_acc != 0.f)
             atomicAdd(tp.loss_sum, loss_acc);
@@ -563,7 +640,7 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
     tc_fence_after_sync();
     if (!is_issuer && my_tiles > 0u) {
         // M = 64 accumulators: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  ->  warp w (mod 4), lanes 0..15 hold rows 16 w .. 16 w + 15;
-        // the 16-column chunks are dealt round-robin to the slots' warp groups
+        // the 16-column chunks are dealt round-robin to the warp groups
         const uint32_t lane_base = (row & ~31u) << 16;
         const uint32_t r         = 16u * (warp & 3u) + lane;
         uint32_t col             = col_dw;
@@ -574,7 +651,7 @@ k_train_mlp(const __grid_constant__ NetConst nc, const __grid_constant__ TrainPa
             const uint32_t kin = layer == 0 ? nc.in_k : (uint32_t)kNeurons;
             const uint32_t nn  = last ? (uint32_t)kOutPadded : kin; // accumulator columns
             for (uint32_t c0 = 0; c0 < nn; c0 += 16u, ++chunk) {
-                if (chunk % (uint32_t)kSlots != slot)
+                if (chunk % (2u * (uint32_t)kSlots) != 2u * slot + half)
                     continue;
                 uint32_t v[16];
                 tmem_ld16(tmem + col + lane_base + c0, v);
@@ -782,9 +859,9 @@ cudaError_t launch_train_mlp(const NetConst &nc, const TrainParams &tp, int num_
     const uint32_t grid    = want < (uint32_t)num_sms ? want : (uint32_t)num_sms;
     const uint32_t smem    = train_smem_layout(nc.wimg_bytes, nc.in_k, nc.n_layers - 1u, slots).total;
     if (slots == 2u)
-        k_train_mlp<2><<<grid, 2 * kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(2), smem, stream>>>(nc, tp);
+        k_train_mlp<2><<<grid, 2 * kTrainSlotThreads + 32, smem, stream>>>(nc, tp);
     else
-        k_train_mlp<1><<<grid, kTileRows + 32 * NBVH_TRAIN_ISSUER_WARPS(1), smem, stream>>>(nc, tp);
+        k_train_mlp<1><<<grid, kTrainSlotThreads + 32, smem, stream>>>(nc, tp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || !tp.wgrad_partial)
         return e;
