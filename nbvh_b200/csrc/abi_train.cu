@@ -46,6 +46,7 @@ int nbvh_optimisation_data_generation(nbvh_ctx *ctx, uint32_t training_step, uin
     sp.nbvh.mint_eps   = bc.learning_mint_epsilon;
     sp.nbvh.maxt_eps   = bc.learning_maxt_epsilon;
     sp.nbvh.predilated = 0u;
+    sp.nbvh.idx_mask   = 0x7FFFFFFFu; // plain stack entries (device_core.cuh)
     sp.blas            = host_blas(ctx, bc.neural_bvh_idx);
     sp.attr.normals       = nb.normals;
     sp.attr.texcoords     = nb.texcoords;

@@ -172,6 +172,18 @@ NbvhConst make_nbvh_const(const nbvh_ctx *ctx, bool inference)
     bc.maxt_eps     = inference ? ctx->bvh_const.inference_maxt_epsilon : ctx->bvh_const.learning_maxt_epsilon;
     bc.dilation     = ctx->bvh_const.fixed_node_dilation;
     bc.predilated   = 1u;
+    // node index bits | truncated entry distance (device_core.cuh, nbvh_pop); at least 9 bits (sign, exponent) must remain for the distance
+    bc.idx_mask = 0x7FFFFFFFu; // bit 31 of a stack entry is the children flag
+    static const bool no_skip = [] { const char *e = getenv("NBVH_NO_STACK_SKIP"); return e && e[0] == '1'; }(); // A/B measurements
+    bc.poke = 0.f;
+    if (ctx->nbvh_poke >= 0.f && !no_skip) {
+        bc.poke = ctx->nbvh_poke;
+        uint32_t bits = 1u;
+        while (bits < 32u && (1u << bits) < ctx->nbvh_nodes)
+            ++bits;
+        if (bits <= 20u)
+            bc.idx_mask = (1u << bits) - 1u;
+    }
     return bc;
 }
 
@@ -203,6 +215,52 @@ int refresh_dilated(nbvh_ctx *ctx)
         CU_TRY(ctx, cudaDeviceSynchronize());
     }
     ctx->dilated_with = ctx->bvh_const.fixed_node_dilation;
+    {
+        // Input of the walk's distance-skipped stack entries (device_core.cuh, nbvh_pop): the largest distance by which a box REACHABLE
+        // below a node sticks out of that node's box (0 for an exactly nested array).  Setup time only: one depth-first pass that
+        // compares every node with all its ancestors.  Malformed arrays (child indices outside the array, cycles, NaN) disable skipping.
+        std::vector<float> h((size_t)ctx->nbvh_nodes * 8u);
+        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->d_nbvh_dilated, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        struct Item { uint32_t node, depth; };
+        std::vector<Item> todo;
+        std::vector<uint32_t> path;
+        todo.push_back({0u, 0u});
+        double poke    = 0.0;
+        bool ok        = ctx->nbvh_nodes > 0;
+        size_t visited = 0;
+        while (ok && !todo.empty()) {
+            const Item it = todo.back();
+            todo.pop_back();
+            if (++visited > (size_t)ctx->nbvh_nodes) { // a cycle: not a tree
+                ok = false;
+                break;
+            }
+            path.resize(it.depth);
+            const float *q = h.data() + (size_t)it.node * 8u;
+            for (uint32_t anc : path) {
+                const float *p = h.data() + (size_t)anc * 8u;
+                for (int k = 0; k < 3; k++) {
+                    const double lo = (double)p[k] - (double)q[k], hi = (double)q[4 + k] - (double)p[4 + k];
+                    if (!(lo == lo) || !(hi == hi))
+                        ok = false;
+                    poke = std::max(poke, std::max(lo, hi));
+                }
+            }
+            uint32_t a, b;
+            memcpy(&a, q + 3, 4);
+            memcpy(&b, q + 7, 4);
+            if (b == 0xFFFFFFFFu || a == 1u) // no neural child / LEAF_FINAL (neural_bvh2.cuh:16,29)
+                continue;
+            if (b >= ctx->nbvh_nodes || b + 1u >= ctx->nbvh_nodes) {
+                ok = false;
+                break;
+            }
+            path.push_back(it.node);
+            todo.push_back({b, it.depth + 1u});
+            todo.push_back({b + 1u, it.depth + 1u});
+        }
+        ctx->nbvh_poke = (ok && std::isfinite(poke)) ? (float)(poke * 1.0001) + 1e-30f : -1.f;
+    }
     return check_nodes(ctx, ctx->d_nbvh_dilated, ctx->nbvh_nodes, ctx->nbvh_safe);
 }
 

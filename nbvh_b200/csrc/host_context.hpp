@@ -12,6 +12,7 @@
 #include "treecut.cuh"
 #include "shading.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -146,6 +147,7 @@ struct nbvh_ctx {
     uint64_t sampler_item_capacity = 0;
     float dilated_with  = -1.f;
     bool nbvh_safe = false;            // node arrays passed k_check_nodes (hoisted IEEE division precondition)
+    float nbvh_poke = -1.f;            // dilated tree-cut: largest overhang of a descendant box over an ancestor's (< 0: walk-stack skipping off)
     std::vector<uint8_t> blas_safe;   // per mesh: its BLAS nodes passed k_check_nodes
     BlasConst *d_blas_ext = nullptr;  // device tables of the BLAS descriptors / shading attributes of scenes with more than kMaxBlas meshes
     BlasAttr *d_attr_ext = nullptr;

@@ -380,8 +380,16 @@ struct TileCtx {
 // Runs all layers on the 128 rows currently in t.a_tile.  All 128 threads of the tile must call it.
 // `row` = thread index within the tile.  On return out[0..n_out) holds the post-sigmoid outputs of this
 // thread's row (fp32).  The caller must have executed fence_proxy_async_smem() after writing the A tile.
-__device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t, uint32_t row, float *out)
+__device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t, uint32_t row, float *out, unsigned long long *mp = nullptr)
 {
+    long long mp_t = mp ? clock64() : 0ll; // development builds: [0] barrier, [1] MMA issue, [2] MMA wait, [3] epilogue
+    auto mp_lap = [&](int i) {
+        if (mp) {
+            const long long now = clock64();
+            mp[i] += (unsigned long long)(now - mp_t);
+            mp_t = now;
+        }
+    };
     const uint32_t a_addr    = smem_u32(t.a_tile);
     const uint32_t lane_base = (row & ~31u) << 16; // TMEM lane quadrant of this warp
     uint32_t k_in            = nc.in_k;
@@ -391,6 +399,7 @@ __device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t,
         // ---- all rows of A are in shared memory and visible to the async proxy
         tc_fence_before_sync();
         named_bar_sync(t.bar_id, kTileRows);
+        mp_lap(layer == 0 ? 0 : 4);
         if (row == 0) {
             tc_fence_after_sync();
             const uint32_t sbo_a = (k_in >> 3) * 128u;
@@ -403,9 +412,11 @@ __device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t,
             }
             umma_commit(t.mma_bar); // implies tcgen05.fence::before_thread_sync
         }
+        mp_lap(1);
         mbar_wait(t.mma_bar, t.phase);
         t.phase ^= 1u;
         tc_fence_after_sync();
+        mp_lap(2);
         // ---- epilogue: this thread's accumulator row -> registers
         if (!last) {
 #ifdef NBVH_EPI_WIDE
@@ -439,7 +450,9 @@ __device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t,
                 *reinterpret_cast<uint4 *>(t.a_tile + tile_chunk_off(row, (c0 >> 3) + 1u, kNeurons)) =
                     make_uint4(h[4], h[5], h[6], h[7]);
             }
+            mp_lap(3);
             fence_proxy_async_smem();
+            mp_lap(5);
             k_in = kNeurons;
         } else {
             uint32_t v[16];

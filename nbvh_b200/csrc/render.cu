@@ -18,6 +18,7 @@
 //
 // Compiled with -fmad=false: see device_core.cuh for the arithmetic contract.
 #include "render_common.cuh"
+#include <cstdio>
 
 namespace nbvh {
 
@@ -39,6 +40,22 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
+#ifndef NBVH_NEURAL_SMEM_STACK
+#define NBVH_NEURAL_SMEM_STACK 0
+#endif
+// k_neural keeps the per-lane N-BVH walk stacks in shared memory (entry i of thread t at word i * kNeuralThreads + t: conflict-free
+// whatever the lanes' stack depths).  As a thread-local array the stack is dynamically indexed local memory, one 128-byte line per
+// stack level and warp, and the hash-grid gathers of every tile iteration evict those lines from L1: each pop of the resumed walk --
+// also each entry skipped as behind the closest hit -- then costs a round trip to L2 on the critical path of the ray's query chain.
+constexpr uint32_t kNeuralStackBytes = NBVH_NEURAL_SMEM_STACK ? (uint32_t)kNeuralThreads * (uint32_t)kNeuralStackSize * 4u : 0u;
+struct LaneStack {
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator[](int i) const { return base[i * kNeuralThreads]; }
+};
+__host__ __device__ inline uint32_t neural_stack_offset(uint32_t wimg_bytes, uint32_t in_k)
+{
+    return (smem_layout(wimg_bytes, in_k, kNeuralTiles).total + 127u) & ~127u;
+}
 constexpr int kLongStack     = NBVH_LONG_STACK;          // pending-stack depth from which a queued ray counts as a long query chain
 constexpr int kWalkRounds    = NBVH_WALK_ROUNDS;         // refill/advance rounds before a tile runs the network
 
@@ -178,6 +195,10 @@ k_primary(const __grid_constant__ RenderParams p)
 }
 
 // ------------------------------------------------------------------------------------------------ k_neural
+#if NBVH_PHASE_TIMING
+__device__ unsigned long long g_probe[24];
+__device__ unsigned int g_probe_done;
+#endif
 struct NeuralLane {
     Ray ray;
     uint32_t pixel;
@@ -232,7 +253,11 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 
     const uint32_t n_front  = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
     const uint32_t n_queued = n_front + (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u);
+#if NBVH_NEURAL_SMEM_STACK
+    const LaneStack nstack{reinterpret_cast<uint32_t *>(smem + neural_stack_offset(nc.wimg_bytes, nc.in_k)) + threadIdx.x};
+#else
     uint32_t nstack[kNeuralStackSize];
+#endif
     NeuralLane s;
     s.have_ray = s.have_query = false;
     s.nss = 0, s.pixel = 0u;
@@ -249,6 +274,8 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_PHASE_TIMING
     unsigned long long ph[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
     uint32_t iters_drain = 0u;
+    unsigned long long mp_s[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull}, mp_d[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+    uint32_t wprobe[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #endif
     for (;;) {
 #if NBVH_PHASE_TIMING
@@ -313,7 +340,11 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
             if (work) {
                 // NeuralBVH2::intersect resumed with ray.maxt = closest t so far (neural_bvh_module_common.cuh:529-545)
                 uint32_t node;
+#if NBVH_PHASE_TIMING
+                if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh, wprobe)) {
+#else
                 if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
+#endif
                     s.have_query = true;
                 } else {
                     finish_lane<kPath>(p, s.pixel, s.ray, s.h);
@@ -360,7 +391,11 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #endif
         // ---------------- MLP on tensor cores (a10), decode + closest-hit update (a11)
         float y[8];
+#if NBVH_PHASE_TIMING
+        mlp_tile_forward(nc, t, row, y, exhausted ? mp_d : mp_s);
+#else
         mlp_tile_forward(nc, t, row, y);
+#endif
         ++cnt_iters;
 #if NBVH_PHASE_TIMING
         {
@@ -392,6 +427,26 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         for (int k = 0; k < 8; ++k)
             atomicAdd(p.counters + CNT_PH_WALK + k, ph[k]);
         atomicAdd(p.counters + CNT_ITERS_DRAIN, (unsigned long long)iters_drain);
+        for (int k = 0; k < 6; ++k)
+            atomicAdd(&g_probe[k], mp_s[k]), atomicAdd(&g_probe[8 + k], mp_d[k]);
+    }
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t v = __reduce_add_sync(0xFFFFFFFFu, wprobe[k]);
+        if (lane == 0)
+            atomicAdd(&g_probe[16 + k], (unsigned long long)v);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_probe_done, 1u) == gridDim.x - 1u) {
+            printf("[k_neural probe] mlp steady: bar0 %llu issue %llu mmawait %llu epi %llu bar %llu fence %llu | drain: bar0 %llu issue %llu mmawait %llu epi %llu bar %llu fence %llu\n",
+                   g_probe[0], g_probe[1], g_probe[2], g_probe[3], g_probe[4], g_probe[5], g_probe[8], g_probe[9], g_probe[10], g_probe[11], g_probe[12], g_probe[13]);
+            printf("[k_neural probe] walk: pops %llu popped-leaf %llu leaf-behind-hit %llu popped-interior %llu (both culled %llu) descent-leaf %llu descent-interior-culled %llu skipped-entries %llu\n",
+                   g_probe[16], g_probe[17], g_probe[18], g_probe[21], g_probe[19], g_probe[20], g_probe[22], g_probe[23]);
+            for (int k = 0; k < 24; ++k)
+                g_probe[k] = 0ull;
+            g_probe_done = 0u;
+        }
     }
 #endif
     __syncthreads();
@@ -415,7 +470,7 @@ cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
 
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream)
 {
-    const uint32_t smem_bytes = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles).total;
+    const uint32_t smem_bytes = neural_stack_offset(nc.wimg_bytes, nc.in_k) + kNeuralStackBytes;
     if (path_mode)
         k_neural<true><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
     else
