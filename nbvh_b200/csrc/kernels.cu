@@ -28,7 +28,7 @@ k_query(const __grid_constant__ NetConst nc, const float *__restrict__ in, float
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
     const uint32_t tmem_base = cta_setup<kTilesPerCta>(nc, smem, lay);
-    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t tile      = __shfl_sync(0xFFFFFFFFu, threadIdx.x / kTileRows, 0); // warp-uniform for ptxas (mlp_tile_forward)
     const uint32_t row       = threadIdx.x % kTileRows;
     TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
 
@@ -239,7 +239,7 @@ k_render(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     __shared__ uint32_t s_flags[kCtaThreads / 32];
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kTilesPerCta);
     const uint32_t tmem_base = cta_setup<kTilesPerCta>(nc, smem, lay);
-    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t tile      = __shfl_sync(0xFFFFFFFFu, threadIdx.x / kTileRows, 0); // warp-uniform for ptxas (mlp_tile_forward)
     const uint32_t row       = threadIdx.x % kTileRows;
     const uint32_t lane      = threadIdx.x & 31u;
     const uint32_t warp      = threadIdx.x >> 5;

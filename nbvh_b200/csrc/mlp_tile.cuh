@@ -400,19 +400,25 @@ __device__ __forceinline__ void mlp_tile_forward(const NetConst &nc, TileCtx &t,
         tc_fence_before_sync();
         named_bar_sync(t.bar_id, kTileRows);
         mp_lap(layer == 0 ? 0 : 4);
-        if (row == 0) {
-            tc_fence_after_sync();
-            const uint32_t sbo_a = (k_in >> 3) * 128u;
-            const uint32_t idesc = umma_idesc_f16_f32(128u, n_out);
-            // one K step = two 128-byte core-matrix columns: both descriptors advance by 256 B = 16 address units; this thread's
-            // instruction stream is on the critical path of the tile (measured: a third of the MLP phase), so nothing else stays in the loop
-            uint64_t ad = umma_desc(a_addr, kLBO, sbo_a), bd = umma_desc(t.w_smem + nc.layer_off[layer], kLBO, sbo_a);
-            umma_f16(t.tmem_acc, ad, bd, idesc, 0u);
-            for (uint32_t k = 16u; k < k_in; k += 16u) {
-                ad += 16u, bd += 16u;
-                umma_f16(t.tmem_acc, ad, bd, idesc, 1u);
+        // The MMAs of the layer are issued by ONE elected lane of the tile's first warp, which enters the block converged: every operand of
+        // the instruction stream (tile index via shuffle in the callers, shared-memory addresses, descriptors) is warp-uniform, so ptxas keeps
+        // the descriptors in uniform registers and emits UTCHMMA back to back (a `row == 0` branch is divergent: ptxas then wraps every MMA
+        // in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY loop, measured 1.1 k cycles per layer on the tile's critical path)
+        if (row < 32u) {
+            if (elect_one_sync()) {
+                tc_fence_after_sync();
+                const uint32_t sbo_a = (k_in >> 3) * 128u;
+                const uint32_t idesc = umma_idesc_f16_f32(128u, n_out);
+                // one K step = two 128-byte core-matrix columns: both descriptors advance by 256 B = 16 address units
+                uint64_t ad = umma_desc(a_addr, kLBO, sbo_a), bd = umma_desc(t.w_smem + nc.layer_off[layer], kLBO, sbo_a);
+                umma_f16(t.tmem_acc, ad, bd, idesc, 0u);
+                for (uint32_t k = 16u; k < k_in; k += 16u) {
+                    ad += 16u, bd += 16u;
+                    umma_f16(t.tmem_acc, ad, bd, idesc, 1u);
+                }
+                umma_commit(t.mma_bar); // implies tcgen05.fence::before_thread_sync
             }
-            umma_commit(t.mma_bar); // implies tcgen05.fence::before_thread_sync
+            __syncwarp();
         }
         mp_lap(1);
         mbar_wait(t.mma_bar, t.phase);

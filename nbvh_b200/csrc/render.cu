@@ -40,6 +40,12 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
+#ifndef NBVH_WALK_BUDGET
+#define NBVH_WALK_BUDGET 0 // > 0: node fetches a lane may spend per walk round before it parks its walk (0 = unbounded)
+#endif
+#ifndef NBVH_TILE_COOP
+#define NBVH_TILE_COOP 0 // 1: the hash-grid gathers of a tile's active rows are dealt to all 128 lanes of the tile (else: per warp)
+#endif
 #ifndef NBVH_NEURAL_SMEM_STACK
 #define NBVH_NEURAL_SMEM_STACK 0
 #endif
@@ -243,9 +249,13 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
+#if NBVH_TILE_COOP
+    __shared__ uint32_t s_qmask[kNeuralThreads / 32];
+    __shared__ float s_ep[kNeuralThreads * 6];
+#endif
     const SmemLayout lay     = smem_layout(nc.wimg_bytes, nc.in_k, kNeuralTiles);
     const uint32_t tmem_base = cta_setup<kNeuralTiles>(nc, smem, lay);
-    const uint32_t tile      = threadIdx.x / kTileRows;
+    const uint32_t tile      = __shfl_sync(0xFFFFFFFFu, threadIdx.x / kTileRows, 0); // warp-uniform for ptxas (mlp_tile_forward)
     const uint32_t row       = threadIdx.x % kTileRows;
     const uint32_t lane      = threadIdx.x & 31u;
     const uint32_t warp      = threadIdx.x >> 5;
@@ -340,12 +350,19 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
             if (work) {
                 // NeuralBVH2::intersect resumed with ray.maxt = closest t so far (neural_bvh_module_common.cuh:529-545)
                 uint32_t node;
-#if NBVH_PHASE_TIMING
+#if NBVH_WALK_BUDGET > 0
+                int budget = NBVH_WALK_BUDGET;
+                if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh, nullptr, &budget)) {
+                    s.have_query = true;
+                } else if (budget < 0) {
+                    // parked mid-walk: the lane keeps its ray and walks on in the next round / after the tile's next network pass
+#elif NBVH_PHASE_TIMING
                 if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh, wprobe)) {
+                    s.have_query = true;
 #else
                 if (s.nss > 0 && nbvh_next_interval(p.nbvh, s.ray, nstack, s.nss, s.h.best_t, s.seg_mint, s.seg_maxt, node, cnt_nbvh)) {
-#endif
                     s.have_query = true;
+#endif
                 } else {
                     finish_lane<kPath>(p, s.pixel, s.ray, s.h);
                     s.have_ray = false;
@@ -359,16 +376,34 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         const long long pt1 = clock64();
 #endif
         // ---------------- tile-wide agreement: anything to infer?  anything left at all?
+#if NBVH_TILE_COOP
+        uint32_t tile_masks[kTileRows / 32];
+#endif
         {
-            const uint32_t q    = __any_sync(0xFFFFFFFFu, s.have_query) ? 1u : 0u;
+            const uint32_t qm   = __ballot_sync(0xFFFFFFFFu, s.have_query);
+            const uint32_t q    = qm ? 1u : 0u;
             const uint32_t live = (__any_sync(0xFFFFFFFFu, s.have_ray) || !exhausted) ? 2u : 0u;
             if (lane == 0)
                 s_flags[warp] = q | live | (exhausted ? 0u : 4u); // bit 2: this warp can still refill from the queue
+#if NBVH_TILE_COOP
+            if (lane == 0)
+                s_qmask[warp] = qm;
+            if (s.have_query) {
+                float eo[3], ei[3];
+                encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
+                float *e = s_ep + 6u * threadIdx.x;
+                e[0] = eo[0], e[1] = eo[1], e[2] = eo[2], e[3] = ei[0], e[4] = ei[1], e[5] = ei[2];
+            }
+#endif
             named_bar_sync(t.bar_id, kTileRows);
             uint32_t f = 0;
 #pragma unroll
             for (int w = 0; w < kTileRows / 32; ++w)
                 f |= s_flags[tile * (kTileRows / 32) + w];
+#if NBVH_TILE_COOP
+            for (int w = 0; w < kTileRows / 32; ++w)
+                tile_masks[w] = s_qmask[tile * (kTileRows / 32) + w];
+#endif
             named_bar_sync(t.bar_id, kTileRows);
             if ((f & 3u) == 0u)
                 break;
@@ -379,12 +414,16 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_PHASE_TIMING
         const long long pt2 = clock64();
 #endif
+#if NBVH_TILE_COOP
+        encode_rows_tile(nc, p.enc, t.a_tile, row, tile_masks, s_ep + 6u * tile * (uint32_t)kTileRows);
+#else
         {
             float eo[3] = {0.f, 0.f, 0.f}, ei[3] = {0.f, 0.f, 0.f};
             if (s.have_query)
                 encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
             encode_rows_coop(nc, p.enc, t.a_tile, row & ~31u, lane, eo, ei, s.have_query);
         }
+#endif
         fence_proxy_async_smem();
 #if NBVH_PHASE_TIMING
         const long long pt3 = clock64();

@@ -2,6 +2,10 @@
 #pragma once
 #include "shading.cuh"
 
+#ifndef NBVH_COOP_JMAJOR
+#define NBVH_COOP_JMAJOR 0
+#endif
+
 namespace nbvh {
 
 // closest hit of the ray in flight (NeuralTraversalResult / HybridIntersectionResult, path_module.h:19-45,104-210)
@@ -85,11 +89,18 @@ __device__ __forceinline__ void encode_rows_coop(const NetConst &nc, const Encod
     const uint32_t pairs  = nc.in_k >> 3;
     const uint32_t items  = (uint32_t)__popc(mask) * pairs;
     const uint32_t my_src = __fns(mask, 0u, lane + 1u); // lane of the (lane+1)-th active row (garbage beyond the count: never used)
+    const uint32_t n_rows = (uint32_t)__popc(mask);
     for (uint32_t base = 0; base < items; base += 32u) {
         const uint32_t it = base + lane;
         const bool on     = it < items;
+#if NBVH_COOP_JMAJOR
+        // chunk-major: neighbouring lanes gather the same (point, level) pairs of different rows (coherent rays share grid cells)
+        const uint32_t j  = on ? it / n_rows : 0u;
+        const uint32_t r  = on ? it - j * n_rows : 0u;
+#else
         const uint32_t r  = on ? it / pairs : 0u;
         const uint32_t j  = it - r * pairs;
+#endif
         const uint32_t src = __shfl_sync(0xFFFFFFFFu, my_src, r) & 31u;
         const float ox = __shfl_sync(0xFFFFFFFFu, eo[0], src), oy = __shfl_sync(0xFFFFFFFFu, eo[1], src),
                     oz = __shfl_sync(0xFFFFFFFFu, eo[2], src);
@@ -104,6 +115,48 @@ __device__ __forceinline__ void encode_rows_coop(const NetConst &nc, const Encod
             const uint2 f1 = grid_level_features(nc.grid, nc.lv[l1], lerp_point(ox, ix, s1), lerp_point(oy, iy, s1), lerp_point(oz, iz, s1));
             *reinterpret_cast<uint4 *>(a_tile + tile_chunk_off(warp_row0 + src, j, nc.in_k)) = make_uint4(f0.x, f0.y, f1.x, f1.y);
         }
+    }
+}
+
+// The same for the whole 128-row tile: the chunks of ALL active rows of the tile are dealt round-robin to its 128 lanes, so the four
+// warps finish together whatever their share of the active rows (per warp, the tile waits for the warp with the most queries: 7 k of
+// the 37 k cycles of a drain iteration).  The segment end points travel through shared memory (`ep`: 6 floats per row, written by the
+// row's owner before the tile barrier); `masks` = the four warps' ballots of rows with a query.  Same arithmetic per chunk, same bits.
+__device__ __forceinline__ void encode_rows_tile(const NetConst &nc, const EncodeConst &ec, uint8_t *a_tile, uint32_t row,
+                                                 const uint32_t masks[4], const float *ep)
+{
+    const uint32_t c0 = (uint32_t)__popc(masks[0]), c1 = (uint32_t)__popc(masks[1]), c2 = (uint32_t)__popc(masks[2]),
+                   c3 = (uint32_t)__popc(masks[3]);
+    const uint32_t n_rows = c0 + c1 + c2 + c3;
+    const uint32_t pairs  = nc.in_k >> 3;
+    const uint32_t items  = n_rows * pairs;
+    for (uint32_t it = row; it < items; it += (uint32_t)kTileRows) {
+#if NBVH_COOP_JMAJOR
+        const uint32_t j = it / n_rows;
+        uint32_t r       = it - j * n_rows;
+#else
+        uint32_t r       = it / pairs;
+        const uint32_t j = it - r * pairs;
+#endif
+        uint32_t w = 0u, m = masks[0];
+        if (r >= c0) {
+            r -= c0, w = 1u, m = masks[1];
+            if (r >= c1) {
+                r -= c1, w = 2u, m = masks[2];
+                if (r >= c2)
+                    r -= c2, w = 3u, m = masks[3];
+            }
+        }
+        const uint32_t src = 32u * w + __fns(m, 0u, r + 1u);
+        const float *e     = ep + 6u * src;
+        const float ox = e[0], oy = e[1], oz = e[2], ix = e[3], iy = e[4], iz = e[5];
+        const uint32_t q0 = 2u * j, q1 = 2u * j + 1u;
+        const uint32_t p0 = q0 / nc.n_levels, l0 = q0 - p0 * nc.n_levels;
+        const uint32_t p1 = q1 / nc.n_levels, l1 = q1 - p1 * nc.n_levels;
+        const float s0 = ec.point_s[p0], s1 = ec.point_s[p1];
+        const uint2 f0 = grid_level_features(nc.grid, nc.lv[l0], lerp_point(ox, ix, s0), lerp_point(oy, iy, s0), lerp_point(oz, iz, s0));
+        const uint2 f1 = grid_level_features(nc.grid, nc.lv[l1], lerp_point(ox, ix, s1), lerp_point(oy, iy, s1), lerp_point(oz, iz, s1));
+        *reinterpret_cast<uint4 *>(a_tile + tile_chunk_off(src, j, nc.in_k)) = make_uint4(f0.x, f0.y, f1.x, f1.y);
     }
 }
 
