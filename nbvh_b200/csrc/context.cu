@@ -55,12 +55,15 @@ std::string layout_error(const nbvh_ctx *ctx)
     return std::string();
 }
 
-int rebuild_layout(nbvh_ctx *ctx)
+int rebuild_layout(nbvh_ctx *ctx, bool keep_parameters_if_unchanged)
 {
     const nbvh_network_desc &d = ctx->net_desc;
     const std::string err      = layout_error(ctx);
     if (!err.empty())
         return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
+    const uint32_t old_in_k = ctx->in_k, old_n_layers = ctx->n_layers, old_wimg_bytes = ctx->wimg_bytes;
+    const uint64_t old_n_params = ctx->n_params;
+    const std::vector<uint32_t> old_level_offsets = ctx->level_offsets, old_layer_off = ctx->layer_off;
     ctx->in_k = ctx->module_const.input_segment_points * d.n_levels * d.n_features_per_level;
     ctx->n_layers = (uint32_t)d.n_hidden_layers + 1u;
 
@@ -93,6 +96,11 @@ int rebuild_layout(nbvh_ctx *ctx)
         bytes += n * k * 2u;
     }
     ctx->wimg_bytes = bytes;
+    // A constant block that leaves the parameter layout as it is (segment distribution, epsilons, ...) keeps the loaded parameters
+    // and the optimisation state: the reference's update of bvh_module_const does not touch the model either
+    if (keep_parameters_if_unchanged && ctx->d_params && ctx->d_wimg && ctx->in_k == old_in_k && ctx->n_layers == old_n_layers && ctx->n_params == old_n_params &&
+        ctx->wimg_bytes == old_wimg_bytes && ctx->level_offsets == old_level_offsets && ctx->layer_off == old_layer_off)
+        return NBVH_OK;
     if (ctx->d_params)
         cudaFree(ctx->d_params);
     if (ctx->d_wimg)
@@ -276,6 +284,7 @@ EncodeConst make_encode_const(const nbvh_ctx *ctx)
     }
     const uint32_t n = ctx->module_const.input_segment_points;
     ec.n_points      = n;
+    ec.uniform       = ctx->module_const.segment_distribution == 2 ? 1u : 0u;
     float delta, offset;
     if (ctx->module_const.segment_distribution == 1) { // EquidistantExterior
         delta  = n == 1 ? 1.f : 1.f / (float)(n - 1);
@@ -303,11 +312,13 @@ DecodeConst make_decode_const(const nbvh_ctx *ctx)
     return dc;
 }
 
-// the wavefront kernels (segment encoding + output decode) implement equidistant segment points and the LocalT / WorldT depth modes
+// the wavefront kernels (segment encoding + output decode) implement every segment distribution and the LocalT / WorldT depth modes
 int check_wavefront_modes(nbvh_ctx *ctx)
 {
-    if (ctx->module_const.segment_distribution == 2)
-        return fail(ctx, NBVH_ERR_UNSUPPORTED, "Uniform segment distribution is not implemented");
+    // SegmentDistribution::Uniform: k_neural<., true> (render.cu) draws the segment parameters from the ray's generator; the single
+    // mega-kernel development mode has no such variant
+    if (ctx->module_const.segment_distribution == 2 && ctx->mega_kernel)
+        return fail(ctx, NBVH_ERR_UNSUPPORTED, "Uniform segment distribution is not available in NBVH_RENDER_MODE=mega");
     // Position / LocalPosition: the training sampler produces their targets (sampler.cu); the inference-side decode is not
     // implemented (the reference's LocalPosition branch prints every query, neural_bvh_module_common.cuh:131-134)
     if (ctx->pt_const.depth_learning_mode > 1)
@@ -355,6 +366,8 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
         ctx->mega_kernel = std::string(m) == "mega";
     if (const char *m = getenv("NBVH_L2_PREFETCH"))
         ctx->l2_prefetch = std::string(m) != "0";
+    if (const char *m = getenv("NBVH_REGION_SPLIT"))
+        ctx->region_split = std::string(m) != "0";
     if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
@@ -384,6 +397,14 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaFree(ctx->ldr);
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
+    cudaFree(ctx->d_region_ctr);
+    if (ctx->region_hi)
+        cudaStreamDestroy(ctx->region_hi);
+    if (ctx->region_lo)
+        cudaStreamDestroy(ctx->region_lo);
+    for (cudaEvent_t e : ctx->region_ev)
+        if (e)
+            cudaEventDestroy(e);
     dp_release(ctx);
     cudaFree(ctx->d_blas_ext), cudaFree(ctx->d_attr_ext);
     cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_counters);
@@ -475,7 +496,7 @@ int nbvh_set_constants(nbvh_ctx *ctx, int which, const void *pod_host, size_t by
             return fail(ctx, NBVH_ERR_UNSUPPORTED, err);
         }
         ctx->walk_version++;
-        return which == NBVH_CONST_PT_OUTPUT ? NBVH_OK : rebuild_layout(ctx);
+        return which == NBVH_CONST_PT_OUTPUT ? NBVH_OK : rebuild_layout(ctx, which == NBVH_CONST_MODULE);
     }
     memcpy(dst, pod_host, bytes);
     ctx->walk_version++; // sampler constants may have changed: walked-ahead items are stale
@@ -611,13 +632,18 @@ int nbvh_host::adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemc
     ctx->tree_cut_ready = false; // a new tree-cut invalidates the learning state (reinitialise_neural_bvh_learning_states)
     CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes, (size_t)n * 32, kind));
     ctx->dilated_with = -1.f, ctx->walk_version++;
-    if (!ctx->scene_bbox_set) {
-        // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
-        // (neural_bvh_renderer_accel.cpp:40,248-251)
+    {
         nbvh_node32 root;
         CU_TRY(ctx, cudaMemcpy(&root, ctx->d_nbvh, 32, cudaMemcpyDeviceToHost));
-        memcpy(ctx->scene_bbox.min, root.aabb_min, 12);
-        memcpy(ctx->scene_bbox.max, root.aabb_max, 12);
+        memcpy(ctx->nbvh_root_min, root.aabb_min, 12);
+        memcpy(ctx->nbvh_root_max, root.aabb_max, 12);
+        ctx->nbvh_root_known = true;
+        if (!ctx->scene_bbox_set) {
+            // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
+            // (neural_bvh_renderer_accel.cpp:40,248-251)
+            memcpy(ctx->scene_bbox.min, root.aabb_min, 12);
+            memcpy(ctx->scene_bbox.max, root.aabb_max, 12);
+        }
     }
     return refresh_dilated(ctx);
 }
@@ -805,7 +831,7 @@ int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
         cudaEventDestroy(e);
     ctx->stage_ev.clear();
     ctx->stage_used = 0;
-    for (uint32_t i = 0; i < 3u * max_frames; i++) {
+    for (uint32_t i = 0; i < 4u * max_frames; i++) { // per frame: start, primary done, frame done, neural pass done
         cudaEvent_t e;
         CU_TRY(ctx, cudaEventCreate(&e));
         ctx->stage_ev.push_back(e);
@@ -820,11 +846,11 @@ int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_m
         return NBVH_ERR_INVALID_ARG;
     float a = 0.f, b = 0.f;
     for (uint32_t i = 0; i < ctx->stage_used; i++) {
-        cudaEvent_t *e = ctx->stage_ev.data() + 3u * i;
+        cudaEvent_t *e = ctx->stage_ev.data() + 4u * i;
         CU_TRY(ctx, cudaEventSynchronize(e[2]));
         float m0 = 0.f, m1 = 0.f;
         CU_TRY(ctx, cudaEventElapsedTime(&m0, e[0], e[1]));
-        CU_TRY(ctx, cudaEventElapsedTime(&m1, e[1], e[2]));
+        CU_TRY(ctx, cudaEventElapsedTime(&m1, e[1], e[3])); // the neural pass itself (a region-split frame ends later: e[2])
         a += m0, b += m1;
     }
     if (primary_ms_total)

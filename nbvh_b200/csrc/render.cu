@@ -41,10 +41,13 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #define NBVH_LONG_STACK 4
 #endif
 #ifndef NBVH_WALK_BUDGET
-#define NBVH_WALK_BUDGET 0 // > 0: node fetches a lane may spend per walk round before it parks its walk (0 = unbounded)
+#define NBVH_WALK_BUDGET 0 // > 0: node fetches a lane may spend per walk round before it parks its walk (0 = unbounded).  Measured on
+                           // B200 (gpurun s31): 4 fetches 0.606 ms, 8 fetches 0.507 ms, unbounded 0.506 ms per 1080p launch -- parked
+                           // rays pay a whole extra network pass; kept as a switch only
 #endif
 #ifndef NBVH_TILE_COOP
-#define NBVH_TILE_COOP 0 // 1: the hash-grid gathers of a tile's active rows are dealt to all 128 lanes of the tile (else: per warp)
+#define NBVH_TILE_COOP 1 // 1: the hash-grid gathers of a tile's active rows are dealt to all 128 lanes of the tile (0: per warp).
+                         // Measured (s31, 1080p launch): per warp 0.506 ms, per tile 0.481 ms, per tile chunk-major 0.465 ms
 #endif
 #ifndef NBVH_NEURAL_SMEM_STACK
 #define NBVH_NEURAL_SMEM_STACK 0
@@ -212,6 +215,7 @@ struct NeuralLane {
     float seg_mint, seg_maxt;
     int nss;
     bool have_ray, have_query;
+    uint32_t rng; // kUniform only: the ray's generator (segment parameters are drawn from it; path mode hands it back to the path state)
 };
 
 // kPath: multi-bounce mode -- the queue entry names a path slot, the ray is read from the path state and the closest
@@ -223,10 +227,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
-template <bool kPath>
-__device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, const Ray &ray, const HitState &h)
+template <bool kPath, bool kUniform>
+__device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, const Ray &ray, const HitState &h, uint32_t rng)
 {
     if constexpr (kPath) {
+        if constexpr (kUniform)
+            p.paths[id].s3.x = rng; // HybridIntersectionResult takes the traversal data's throughput_rng back (path_module.h:111,141)
         PathHit ph;
         ph.h0 = make_float4(h.best_t, __uint_as_float(h.valid_hit), h.n_or_uv[0], h.n_or_uv[1]);
         ph.h1 = make_float4(h.n_or_uv[2], h.alb_or_ids[0], h.alb_or_ids[1], h.alb_or_ids[2]);
@@ -243,12 +249,20 @@ __device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, 
     }
 }
 
-template <bool kPath>
+// kUniform: SegmentDistribution::Uniform (neural_bvh_module_kernels.cu:53-69,292-297) -- every query draws one parameter per segment
+// point from its ray's generator; rows then encode their own points (no shipped configuration uses it: the cooperative gather paths
+// serve the equidistant distributions only)
+template <bool kPath, bool kUniform>
 __global__ void __launch_bounds__(kNeuralThreads, kNeuralCtasPerSm)
 k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetConst nc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
+    // nothing queued (the safety-net launch of launch_render_regions, frames without neural rays): leave before TMEM / weight set-up.
+    // The counts are final: every producer launch precedes this kernel in stream order.
+    if (*reinterpret_cast<const volatile uint32_t *>(p.queue_count) +
+            (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u) == 0u)
+        return;
 #if NBVH_TILE_COOP
     __shared__ uint32_t s_qmask[kNeuralThreads / 32];
     __shared__ float s_ep[kNeuralThreads * 6];
@@ -323,9 +337,13 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                             s.ray.ox = s0.x, s.ray.oy = s0.y, s.ray.oz = s0.z;
                             s.ray.dx = s0.w, s.ray.dy = s1.x, s.ray.dz = s1.y;
                             ray_prepare(s.ray, p.cam.nodes_safe != 0u);
+                            if constexpr (kUniform)
+                                rng = p.paths[a.x].s3.x;
                         } else {
                             s.ray = camera_ray(p.cam, s.pixel, p.sample_idx + (int)c.z, p.sample_offset, rng);
                         }
+                        if constexpr (kUniform)
+                            s.rng = rng;
                         s.h.best_t    = __uint_as_float(a.y);
                         s.h.valid_hit = a.z;
                         s.h.n_or_uv[0] = __uint_as_float(a.w), s.h.n_or_uv[1] = __uint_as_float(b.x), s.h.n_or_uv[2] = 0.f;
@@ -364,7 +382,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                     s.have_query = true;
 #endif
                 } else {
-                    finish_lane<kPath>(p, s.pixel, s.ray, s.h);
+                    finish_lane<kPath, kUniform>(p, s.pixel, s.ray, s.h, s.rng);
                     s.have_ray = false;
                 }
             }
@@ -388,7 +406,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_TILE_COOP
             if (lane == 0)
                 s_qmask[warp] = qm;
-            if (s.have_query) {
+            if (!kUniform && s.have_query) {
                 float eo[3], ei[3];
                 encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
                 float *e = s_ep + 6u * threadIdx.x;
@@ -414,6 +432,18 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_PHASE_TIMING
         const long long pt2 = clock64();
 #endif
+        if constexpr (kUniform) {
+            float pts[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (s.have_query) {
+                float eo[3], ei[3];
+                encode_endpoints(p.enc, s.ray, s.seg_mint, s.seg_maxt, eo, ei);
+                for (uint32_t k = 0; k < p.enc.n_points && k < 4u; ++k) {
+                    const float sk = lcg_randomf(s.rng);
+                    pts[3u * k] = lerp_point(eo[0], ei[0], sk), pts[3u * k + 1u] = lerp_point(eo[1], ei[1], sk), pts[3u * k + 2u] = lerp_point(eo[2], ei[2], sk);
+                }
+            }
+            encode_row_to_tile(nc, t.a_tile, row, pts, s.have_query);
+        } else
 #if NBVH_TILE_COOP
         encode_rows_tile(nc, p.enc, t.a_tile, row, tile_masks, s_ep + 6u * tile * (uint32_t)kTileRows);
 #else
@@ -501,19 +531,29 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k)
 {
     (void)wimg_bytes, (void)in_k;
-    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<false>));
-    if (e != cudaSuccess)
-        return e;
-    return allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<true>));
+    cudaError_t e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<false, false>));
+    if (e == cudaSuccess)
+        e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<true, false>));
+    if (e == cudaSuccess)
+        e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<false, true>));
+    if (e == cudaSuccess)
+        e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_neural<true, true>));
+    return e;
 }
 
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream)
 {
     const uint32_t smem_bytes = neural_stack_offset(nc.wimg_bytes, nc.in_k) + kNeuralStackBytes;
-    if (path_mode)
-        k_neural<true><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
+    const uint32_t grid = (uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm;
+    if (rp.enc.uniform) {
+        if (path_mode)
+            k_neural<true, true><<<grid, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
+        else
+            k_neural<false, true><<<grid, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
+    } else if (path_mode)
+        k_neural<true, false><<<grid, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
     else
-        k_neural<false><<<(uint32_t)num_sms * (uint32_t)kNeuralCtasPerSm, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
+        k_neural<false, false><<<grid, kNeuralThreads, smem_bytes, stream>>>(rp, nc);
     return cudaGetLastError();
 }
 
@@ -538,6 +578,43 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
         k_resolve_ldr<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp, 1.f / (float)(rp.sample_idx + (int)rp.spp_count));
         return cudaGetLastError();
     }
+    return cudaSuccess;
+}
+
+cudaError_t launch_render_regions(const RenderParams &rp_in, const RenderParams &rp_out, const NetConst &nc, int num_sms, cudaStream_t stream,
+                                  const RegionStreams &rs, cudaEvent_t between, cudaEvent_t neural_done)
+{
+    cudaError_t e;
+#define NBVH_TRY(x)                                                                                                                        \
+    if ((e = (x)) != cudaSuccess)                                                                                                          \
+    return e
+    NBVH_TRY(cudaEventRecord(rs.start, stream));
+    NBVH_TRY(cudaStreamWaitEvent(rs.hi, rs.start, 0));
+    NBVH_TRY(cudaStreamWaitEvent(rs.lo, rs.start, 0));
+    // inside region: primary pass, then the persistent neural pass
+    if (rp_in.pixel_count) {
+        k_primary<<<((rp_in.pixel_count >> 5) + 7u) / 8u, 256, 0, rs.hi>>>(rp_in);
+        NBVH_TRY(cudaGetLastError());
+    }
+    if (between)
+        NBVH_TRY(cudaEventRecord(between, rs.hi));
+    if (rp_in.pixel_count)
+        NBVH_TRY(launch_neural(rp_in, nc, num_sms, false, rs.hi));
+    if (neural_done)
+        NBVH_TRY(cudaEventRecord(neural_done, rs.hi));
+    NBVH_TRY(cudaEventRecord(rs.hi_done, rs.hi));
+    // outside region: primary pass only, at low priority
+    if (rp_out.pixel_count) {
+        k_primary<<<((rp_out.pixel_count >> 5) + 7u) / 8u, 256, 0, rs.lo>>>(rp_out);
+        NBVH_TRY(cudaGetLastError());
+    }
+    NBVH_TRY(cudaEventRecord(rs.lo_done, rs.lo));
+    NBVH_TRY(cudaStreamWaitEvent(stream, rs.hi_done, 0));
+    NBVH_TRY(cudaStreamWaitEvent(stream, rs.lo_done, 0));
+    // safety net: rays of the outside region that reached the neural BVH after all
+    if (rp_out.pixel_count)
+        NBVH_TRY(launch_neural(rp_out, nc, num_sms, false, stream));
+#undef NBVH_TRY
     return cudaSuccess;
 }
 

@@ -569,7 +569,16 @@ int onbvh_tlas_intersect_only(const oscene_t *s, const float o[3], const float d
  * PTX: world = fma(t, d, o); dilation = (extent_dil + 1) + fixed_dil; centre = (max+min)*0.5;
  *      enc = (world - centre) / (dilation*(max-min)) + 0.5; p = fma(enc_i, s, enc_o*(1-s)),
  *      s = rcp(float(n-1)) * (float(k) + offset). */
+/* SegmentDistribution::Uniform (neural_bvh_module_kernels.cu:53-69): t = lcg_randomf(rng) per segment point, drawn from the RAY's
+ * generator (encode_bvh_network_input_data :292-297 reads and writes back traversal_data's rng), same blend expression. */
+
 void onbvh_encode_segment(const oconst_t *c, const float o[3], const float d[3], float mint, float maxt, float *out)
+{
+    onbvh_encode_segment_rng(c, o, d, mint, maxt, NULL, out);
+}
+
+void onbvh_encode_segment_rng(const oconst_t *c, const float o[3], const float d[3], float mint, float maxt, uint32_t *rng,
+                              float *out)
 {
     if (mint < 0.f) {
         float t = mint;
@@ -588,6 +597,14 @@ void onbvh_encode_segment(const oconst_t *c, const float o[3], const float d[3],
     }
     const uint32_t n = c->n_segment_points;
     float delta, offset;
+    if (c->segment_distribution == 2u && rng) { /* Uniform */
+        for (uint32_t k = 0; k < n; k++) {
+            float s = onbvh_lcg_randomf(rng);
+            for (int i = 0; i < 3; i++)
+                out[3 * k + i] = fmaf(ei[i], s, eo[i] * (1.0f - s));
+        }
+        return;
+    }
     if (c->segment_distribution == 1u) { /* EquidistantExterior */
         delta  = (n == 1u) ? 1.f : 1.f / (float)(n - 1u);
         offset = 0.f;
@@ -1085,8 +1102,9 @@ void onbvh_generate_batch(const onode_t *nbvh, const oconst_t *c, const osampler
 
 /* ------------------------------------------------------------------ primary-ray pipeline */
 /* closest hit of one ray over the whole TLAS: classical BLAS closest hits + neural leaf queries, in TLAS order */
+/* rng: the ray's generator (Uniform segment points draw from it and leave it advanced for the shading step); NULL = none */
 static void trace_ray(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net, const float o[3],
-                      const float d[3], uint32_t ray_depth, uint32_t lod, int mlp_mode, ohit_t *hit, uint64_t *cnt)
+                      const float d[3], uint32_t ray_depth, uint32_t lod, int mlp_mode, ohit_t *hit, uint64_t *cnt, uint32_t *rng)
 {
     memset(hit, 0, sizeof(*hit));
     hit->t = FLT_MAX;
@@ -1112,7 +1130,7 @@ static void trace_ray(const oscene_t *s, const onode_t *nbvh, const oconst_t *c,
                                             c->fixed_node_dilation, &mint, &maxt, &node, &cnt[1]))
                     break;
                 float pts[64], y[16];
-                onbvh_encode_segment(c, o, d, mint, maxt, pts);
+                onbvh_encode_segment_rng(c, o, d, mint, maxt, rng, pts);
                 query_one(net, pts, n_points, mlp_mode, y);
                 cnt[0]++;
                 float t;
@@ -1154,8 +1172,9 @@ static void render_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c
                        int sample_idx, int rnd_offset, int mlp_mode, ohit_t *hit, uint64_t *cnt)
 {
     float o[3], d[3];
-    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, NULL);
-    trace_ray(s, nbvh, c, net, o, d, 1u, c->rendered_lod, mlp_mode, hit, cnt);
+    uint32_t rng;
+    onbvh_raygen(c, pixel, sample_idx, rnd_offset, o, d, &rng);
+    trace_ray(s, nbvh, c, net, o, d, 1u, c->rendered_lod, mlp_mode, hit, cnt, &rng);
 }
 
 void onbvh_render_primary(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, const onet_t *net,
@@ -1526,7 +1545,7 @@ static void path_one(const oscene_t *s, const onode_t *nbvh, const oconst_t *c, 
     for (uint32_t depth = 1;; depth++) {
         ohit_t hit;
         uint32_t lod = (pc->path_lod_switch && pc->num_lods_learned > 0 && depth > 1) ? pc->lod_switch : c->rendered_lod;
-        trace_ray(s, nbvh, c, net, o, d, depth, lod, mlp_mode, &hit, cnt);
+        trace_ray(s, nbvh, c, net, o, d, depth, lod, mlp_mode, &hit, cnt, &rng);
         cnt[4]++;
         if (depth == 1 && primary)
             *primary = hit;
@@ -1624,7 +1643,7 @@ void onbvh_trace_rays(const oscene_t *s, const onode_t *nbvh, const oconst_t *c,
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : c0, c1, c2, c3)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         uint64_t cnt[4] = {0, 0, 0, 0};
-        trace_ray(s, nbvh, c, net, o + 3 * i, d + 3 * i, ray_depth, lod, mlp_mode, &hits[i], cnt);
+        trace_ray(s, nbvh, c, net, o + 3 * i, d + 3 * i, ray_depth, lod, mlp_mode, &hits[i], cnt, NULL);
         c0 += cnt[0], c1 += cnt[1], c2 += cnt[2], c3 += cnt[3];
     }
     if (counters) {

@@ -64,7 +64,7 @@ typedef struct {
     float depth_epsilon, fixed_depth_epsilon;
     uint32_t ignore_neural_blas;
     uint32_t n_segment_points;      /* 3 */
-    uint32_t segment_distribution;  /* 0 EquidistantInterior 1 EquidistantExterior (2 Uniform unsupported) */
+    uint32_t segment_distribution;  /* 0 EquidistantInterior 1 EquidistantExterior 2 Uniform (camera / path rays: points drawn from the ray's generator) */
     float bbox_min[3], bbox_max[3]; /* neural_scene_bbox */
     /* camera (cuda_backend.cpp:595-611) */
     float cam_origin[3], cam_du[3], cam_dv[3], cam_top_left[3];
@@ -118,6 +118,9 @@ int onbvh_tlas_intersect_only(const oscene_t *s, const float o[3], const float d
 /* a8: leaf interval -> 3x3 encoded points */
 void onbvh_encode_segment(const oconst_t *c, const float o[3], const float d[3], float mint, float maxt,
                           float *out /* 3*n_points */);
+/* the same with the ray's generator: SegmentDistribution::Uniform draws one parameter per point from it (rng may be NULL) */
+void onbvh_encode_segment_rng(const oconst_t *c, const float o[3], const float d[3], float mint, float maxt, uint32_t *rng,
+                              float *out);
 /* a9: hash grid, fp16 arithmetic as tcnn; writes n_points*n_levels*n_features fp16 bit patterns */
 void onbvh_grid_encode(const onet_t *net, const float *points, uint32_t n_points, uint16_t *features);
 /* a10: mode 0 = fp16 in / fp32 accumulate (the B200 kernel's arithmetic), 1 = fp16-accumulate emulation of

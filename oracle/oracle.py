@@ -286,6 +286,33 @@ def encode_segments(const, o, d, mint, maxt):
     return out
 
 
+def raygen_rng(const, pixels, sample_idx=0, rnd_offset=0):
+    """State of each pixel's generator after ray generation (what the wavefront's traversal data carries)."""
+    pixels = np.asarray(pixels, dtype=np.uint32)
+    out = np.zeros(pixels.size, np.uint32)
+    oo, dd, st = (C.c_float * 3)(), (C.c_float * 3)(), C.c_uint32(0)
+    f = lib().onbvh_raygen
+    for i, p in enumerate(pixels):
+        f(C.byref(const), C.c_uint32(int(p)), C.c_int(sample_idx), C.c_int(rnd_offset), oo, dd, C.byref(st))
+        out[i] = st.value
+    return out
+
+
+def encode_segments_rng(const, o, d, mint, maxt, rng_states):
+    """encode_segments with each ray's generator (SegmentDistribution::Uniform); returns (inputs, advanced generator states)."""
+    n = o.shape[0]
+    out = np.zeros((n, 3 * const.n_segment_points), np.float32)
+    states = np.array(rng_states, dtype=np.uint32).copy()
+    f = lib().onbvh_encode_segment_rng
+    for i in range(n):
+        oo = (C.c_float * 3)(*o[i])
+        dd = (C.c_float * 3)(*d[i])
+        st = C.c_uint32(int(states[i]))
+        f(C.byref(const), oo, dd, C.c_float(mint[i]), C.c_float(maxt[i]), C.byref(st), _p(out[i]))
+        states[i] = st.value
+    return out, states
+
+
 def query(net, inputs, mode=0):
     """inputs: (N, 9) float32 rows (== the reference's column-major 9xN matrix in memory)."""
     x = np.ascontiguousarray(inputs, dtype=np.float32)

@@ -208,7 +208,7 @@ def test_gpu_path_matches_oracle_synthetic(syn_path, oracle, torch_cuda, max_dep
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["ignore_neural_blas", "force_constant_material", "dielectric", "anisotropic", "skylike_no_rr"])
+@pytest.mark.parametrize("variant", ["ignore_neural_blas", "force_constant_material", "dielectric", "anisotropic", "skylike_no_rr", "uniform_points"])
 def test_gpu_path_shading_branches_match_oracle(oracle, synthetic, torch_cuda, variant):
     """The remaining branches of the shading kernel against the oracle: the non-neural rendering of the neural mesh
     (ignore_neural_blas: its classical BLAS, unpack_albedo + the module's constant specular parameters), force_constant_material,
@@ -233,6 +233,10 @@ def test_gpu_path_shading_branches_match_oracle(oracle, synthetic, torch_cuda, v
         mats["sheen_tint"][:] = 0.3
         mats["specular_tint"][:] = 0.4
         mats["roughness"][1] = 0.25
+    elif variant == "uniform_points":
+        # SegmentDistribution::Uniform: every query draws its segment parameters from the path's generator, which the shading step
+        # continues from (neural_bvh_module_kernels.cu:53-69,292-297; path_module.h:111,141)
+        cfg["neural_bvh_renderer"]["neural_module"].setdefault("bvh_module_constants", {})["segment_distribution"] = "Uniform"
     elif variant == "skylike_no_rr":
         sc.update(skylike_background=True)
         cfg["neural_bvh_renderer"]["neural_module"]["path_module_constants"]["apply_russian_roulette"] = False
@@ -254,6 +258,12 @@ def test_gpu_path_shading_branches_match_oracle(oracle, synthetic, torch_cuda, v
     assert np.isfinite(img).all() and m >= PIXEL_MATCH
     if variant == "ignore_neural_blas":
         assert (hits["valid_hit"] != 1).all() and (hits["valid_hit"] == 2).sum() > 1000
+    if variant == "uniform_points":
+        assert mod.get_constants(A.CONST_MODULE).segment_distribution == 2
+        cfg0 = json.loads(json.dumps(cfg))
+        cfg0["neural_bvh_renderer"]["neural_module"]["bvh_module_constants"]["segment_distribution"] = "EquidistantInterior"
+        rad0, _, _ = oracle_synthetic(oracle, (cfg0,) + inputs[1:], params, max_depth=3)
+        assert pixel_match(rad0.reshape(H, W, 3), rad) < 0.9  # the option changes the frame: the agreement above is not vacuous
     mod.close()
 
 

@@ -282,6 +282,84 @@ def test_gpu_worldt_depth_mode_matches_reference_wavefront(gold, gpu_env):
     assert (dt < NET_TOL_TCNN * diag).mean() > 0.99
 
 
+G_UNIFORM = os.path.join(HERE, "golden", "ref_chess_uniform_256x144.npz")
+
+
+def uniform_const(oracle, chess_cfg, nbvh):
+    cfg = json.loads(json.dumps(chess_cfg))
+    cfg["neural_bvh_renderer"]["neural_module"].setdefault("bvh_module_constants", {})["segment_distribution"] = "Uniform"
+    return oracle.config_constants(cfg, nbvh)
+
+
+def test_oracle_uniform_segment_points_match_reference_kernel(gold, oracle, cpu_env, chess_cfg):
+    """SegmentDistribution::Uniform on the wavefront path (neural_bvh_module_kernels.cu:53-69,292-297): the reference's first-step
+    network inputs (tools/make_ref_uniform_golden.py) are reproduced BIT FOR BIT from each pixel's generator state after ray
+    generation -- this pins which generator the draws come from, their order and the blend expression; the final hit records pin
+    the draws of the later queries of each chain."""
+    if not os.path.exists(G_UNIFORM):
+        pytest.skip("Uniform golden not generated (tools/make_ref_uniform_golden.py on a GPU box)")
+    g = np.load(G_UNIFORM)
+    const = uniform_const(oracle, chess_cfg, cpu_env["nbvh"])
+    assert const.segment_distribution == 2
+    px = g["s0_px"].astype(np.int64)
+    assert (px == gold["s0_px"]).all()  # the same rays queue a first query
+    o, d = golden_rays(gold)
+    first = gold["first"][px]
+    mint = gold["iv_mint"].view(np.float32)[first]
+    maxt = gold["iv_maxt"].view(np.float32)[first]
+    rng = oracle.raygen_rng(const, px)
+    x, rng1 = oracle.encode_segments_rng(const, o[px], d[px], mint, maxt, rng)
+    assert (rng1 != rng).all()
+    assert (bits(x) == g["s0_in"]).all()
+    assert not (g["s0_in"] == gold["s0_in"]).all()
+    hits, _ = oracle.render_primary(cpu_env["scene"], cpu_env["nbvh"], const, cpu_env["net"], 0, gold["n"])
+    check_uniform_hits(g, hits["valid_hit"].astype(np.uint8), hits["t"], "oracle")
+
+
+def check_uniform_hits(g, kind, t, label):
+    gk, gt = g["hit_kind"], g["hit_t"].view(np.float32)
+    same = kind == gk
+    assert (gk == 1).sum() > 1000
+    assert (~same).sum() <= int(0.02 * len(gk)), "%s: %d hit-kind flips" % (label, int((~same).sum()))
+    cls = same & (gk == 2)
+    assert (bits(t[cls]) == g["hit_t"][cls]).mean() > 0.99
+    neu = same & (gk == 1)
+    dt = np.abs(t[neu] - gt[neu])
+    assert np.median(dt) < 2e-3, "%s: median |dt| %g" % (label, np.median(dt))
+    assert (dt < 5e-2).mean() > 0.98
+
+
+@pytest.mark.gpu
+def test_gpu_uniform_segment_points_match_reference_wavefront(gold, gpu_env, oracle, cpu_env, chess_cfg):
+    """The CUDA path with SegmentDistribution::Uniform (k_neural<., true>) against the reference's wavefront run with the same
+    constant, and -- tighter -- against the oracle, whose first-step inputs are pinned bit for bit by the CPU test above."""
+    import nbvh_b200
+    if not os.path.exists(G_UNIFORM):
+        pytest.skip("Uniform golden not generated (tools/make_ref_uniform_golden.py on a GPU box)")
+    g = np.load(G_UNIFORM)
+    mod, torch = gpu_env["mod"], gpu_env["torch"]
+    saved = mod.get_constants(nbvh_b200.CONST_MODULE)
+    mc = mod.get_constants(nbvh_b200.CONST_MODULE)
+    mc.segment_distribution = 2
+    mod.set_constants(nbvh_b200.CONST_MODULE, mc)
+    try:
+        hits_dev = mod.attach_hit_buffer(gold["n"])
+        mod.neural_render(0, 0)
+        torch.cuda.synchronize()
+        h = hits_dev.cpu().numpy().view(nbvh_b200.HIT_DTYPE).copy()
+    finally:
+        mod.set_constants(nbvh_b200.CONST_MODULE, saved)
+    kind, t = h["valid_hit"].astype(np.uint8), h["t"]
+    assert not (kind == gold["hit_kind"]).all() or not (bits(t) == gold["hit_t"]).all()  # the mode changes the frame
+    check_uniform_hits(g, kind, t, "CUDA")
+    const = uniform_const(oracle, chess_cfg, cpu_env["nbvh"])
+    oh, _ = oracle.render_primary(cpu_env["scene"], cpu_env["nbvh"], const, cpu_env["net"], 0, gold["n"])
+    ok = oh["valid_hit"].astype(np.uint8)
+    assert (kind != ok).sum() <= int(2e-3 * len(ok)), "%d kind flips against the oracle" % int((kind != ok).sum())
+    neu = (kind == ok) & (ok == 1)
+    assert np.median(np.abs(t[neu] - oh["t"][neu])) < 1e-4
+
+
 @pytest.mark.gpu
 def test_gpu_1080p_frame_matches_reference_summaries(chess_root, chess_cfg, gpu_env):
     """Full BASELINE.json size: per-pixel interval counts, per-row checksums of the interval lists, classical-hit row sums
