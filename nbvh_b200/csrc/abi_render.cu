@@ -230,59 +230,6 @@ int nbvh_render_samples(nbvh_ctx *ctx, uint32_t first_spp, uint32_t n_spp, uint3
     return render_impl(ctx, first_spp, sample_offset, 0u, mine * 32u, shard_count, shard_index, stream, n_spp);
 }
 
-// Block rectangle (8x4-pixel blocks) that contains every pixel whose camera ray can meet the tree-cut: the projection of the N-BVH root
-// box (grown by 1 % + the node dilations) through the pinhole camera of camera_ray -- a pixel (px, py) looks along
-// top_left + xf du + yf dv with xf in [px, px + 1) / W --, padded by two pixels.  False when the rectangle cannot be bounded (a corner
-// behind the camera, degenerate camera) or the frame size is not a multiple of the block size.  The rectangle only steers the launch
-// order (launch_render_regions drains neural rays of the outside region too), so it need not be exact for correctness.
-static bool neural_block_rect(const nbvh_ctx *ctx, uint32_t &bx0, uint32_t &by0, uint32_t &bw, uint32_t &bh)
-{
-    if (!ctx->nbvh_root_known || !ctx->cam_set || (ctx->fb_w & 7u) || (ctx->fb_h & 3u))
-        return false;
-    const nbvh_camera_params &c = ctx->camera;
-    const double m[3][3] = {{c.du[0], c.dv[0], c.dir_top_left[0]}, {c.du[1], c.dv[1], c.dir_top_left[1]}, {c.du[2], c.dv[2], c.dir_top_left[2]}};
-    auto det3 = [](const double a[3][3]) {
-        return a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
-               a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
-    };
-    const double det = det3(m);
-    if (!(fabs(det) > 1e-30))
-        return false;
-    const double grow = 0.01 + (double)ctx->bvh_const.fixed_node_dilation + (double)ctx->bvh_const.node_extent_dilation;
-    double xmin = 1e30, xmax = -1e30, ymin = 1e30, ymax = -1e30;
-    for (int k = 0; k < 8; k++) {
-        double rhs[3];
-        for (int a = 0; a < 3; a++) {
-            const double lo = ctx->nbvh_root_min[a], hi = ctx->nbvh_root_max[a], pad = grow * (hi - lo) + 1e-6;
-            rhs[a] = (((k >> a) & 1) ? hi + pad : lo - pad) - (double)c.origin[a];
-        }
-        double sol[3];
-        for (int col = 0; col < 3; col++) {
-            double t[3][3];
-            for (int r = 0; r < 3; r++)
-                for (int q = 0; q < 3; q++)
-                    t[r][q] = q == col ? rhs[r] : m[r][q];
-            sol[col] = det3(t) / det;
-        }
-        if (!(sol[2] > 1e-9))
-            return false; // the corner is not in front of the camera
-        const double xf = sol[0] / sol[2], yf = sol[1] / sol[2];
-        xmin = xf < xmin ? xf : xmin, xmax = xf > xmax ? xf : xmax;
-        ymin = yf < ymin ? yf : ymin, ymax = yf > ymax ? yf : ymax;
-    }
-    const double W = ctx->fb_w, H = ctx->fb_h;
-    double px0 = floor(xmin * W) - 2.0, px1 = ceil(xmax * W) + 2.0, py0 = floor(ymin * H) - 2.0, py1 = ceil(ymax * H) + 2.0;
-    px0 = px0 < 0.0 ? 0.0 : px0, py0 = py0 < 0.0 ? 0.0 : py0;
-    px1 = px1 > W ? W : px1, py1 = py1 > H ? H : py1;
-    if (!(px1 > px0) || !(py1 > py0)) { // the box is off screen: an empty rectangle (every block is "outside")
-        bx0 = by0 = 0u, bw = bh = 0u;
-        return true;
-    }
-    bx0 = (uint32_t)px0 >> 3, by0 = (uint32_t)py0 >> 2;
-    bw  = (((uint32_t)px1 + 7u) >> 3) - bx0, bh = (((uint32_t)py1 + 3u) >> 2) - by0;
-    return true;
-}
-
 static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_offset, uint32_t first_pixel, uint32_t pixel_count,
                        uint32_t chunk_stride, uint32_t chunk_offset, void *stream, uint32_t spp_count)
 {
@@ -428,51 +375,14 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
         CU_TRY(ctx, launch_render_path(rp, pc, nc, nbvh_bounce, ctx->d_paths, ctx->d_path_hits, ctx->d_bounce_counters, ctx->num_sms, st));
     } else if (ctx->mega_kernel) {
         CU_TRY(ctx, launch_render(rp, nc, ctx->num_sms, st));
+    } else if (3u * (ctx->stage_used + 1u) <= ctx->stage_ev.size()) {
+        cudaEvent_t *e = ctx->stage_ev.data() + 3u * ctx->stage_used;
+        CU_TRY(ctx, cudaEventRecord(e[0], st));
+        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st, e[1]));
+        CU_TRY(ctx, cudaEventRecord(e[2], st));
+        ctx->stage_used++;
     } else {
-        cudaEvent_t *e = 4u * (ctx->stage_used + 1u) <= ctx->stage_ev.size() ? ctx->stage_ev.data() + 4u * ctx->stage_used : nullptr;
-        if (e)
-            CU_TRY(ctx, cudaEventRecord(e[0], st));
-        uint32_t bx0 = 0, by0 = 0, bw = 0, bh = 0;
-        const uint32_t bpr = ctx->fb_w >> 3, bpc = ctx->fb_h >> 2;
-        // region split: a whole frame, one sample, default slot, and a rectangle that leaves at least a tenth of the frame outside
-        const bool regions = ctx->region_split && !alt && spp_count <= 1u && chunk_stride <= 1u && first_pixel == 0u && pixel_count == total &&
-                             !ctx->bvh_const.ignore_neural_blas && neural_block_rect(ctx, bx0, by0, bw, bh) &&
-                             (uint64_t)bw * bh * 10u <= (uint64_t)bpr * bpc * 9u;
-        if (regions) {
-            if (!ctx->region_hi) {
-                int least = 0, greatest = 0;
-                CU_TRY(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
-                CU_TRY(ctx, cudaStreamCreateWithPriority(&ctx->region_hi, cudaStreamNonBlocking, greatest));
-                CU_TRY(ctx, cudaStreamCreateWithPriority(&ctx->region_lo, cudaStreamNonBlocking, least));
-                for (cudaEvent_t &ev : ctx->region_ev)
-                    CU_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                CU_TRY(ctx, cudaMalloc(&ctx->d_region_ctr, 8 * sizeof(uint32_t)));
-            }
-            CU_TRY(ctx, cudaMemsetAsync(ctx->d_region_ctr, 0, 4 * sizeof(uint32_t), st));
-            RenderParams rin = rp, rout = rp;
-            rin.rect_mode = 1u, rout.rect_mode = 2u;
-            rin.rect_bx0 = rout.rect_bx0 = bx0, rin.rect_by0 = rout.rect_by0 = by0;
-            rin.rect_bw = rout.rect_bw = bw, rin.rect_bh = rout.rect_bh = bh;
-            rin.first_pixel = rout.first_pixel = 0u;
-            rin.pixel_count  = bw * bh * 32u;
-            rout.pixel_count = total - rin.pixel_count;
-            // the two regions queue into disjoint parts of the array, with their own counters
-            rin.queue_capacity = rin.pixel_count;
-            rout.queue          = rp.queue + rin.pixel_count;
-            rout.queue_capacity = rout.pixel_count;
-            rout.next_chunk = ctx->d_region_ctr, rout.queue_count = ctx->d_region_ctr + 1, rout.queue_cursor = ctx->d_region_ctr + 2;
-            rout.queue_count_back = nullptr;
-            RegionStreams rs{ctx->region_hi, ctx->region_lo, ctx->region_ev[0], ctx->region_ev[1], ctx->region_ev[2]};
-            CU_TRY(ctx, launch_render_regions(rin, rout, nc, ctx->num_sms, st, rs, e ? e[1] : nullptr, e ? e[3] : nullptr));
-        } else {
-            CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st, e ? e[1] : nullptr));
-            if (e)
-                CU_TRY(ctx, cudaEventRecord(e[3], st));
-        }
-        if (e) {
-            CU_TRY(ctx, cudaEventRecord(e[2], st));
-            ctx->stage_used++;
-        }
+        CU_TRY(ctx, launch_render_split(rp, nc, ctx->num_sms, st, nullptr));
     }
     kt.stop();
     return NBVH_OK;

@@ -366,8 +366,6 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
         ctx->mega_kernel = std::string(m) == "mega";
     if (const char *m = getenv("NBVH_L2_PREFETCH"))
         ctx->l2_prefetch = std::string(m) != "0";
-    if (const char *m = getenv("NBVH_REGION_SPLIT"))
-        ctx->region_split = std::string(m) != "0";
     if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
@@ -397,14 +395,6 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaFree(ctx->ldr);
     cudaFree(ctx->own_hits);
     cudaFree(ctx->d_next_chunk);
-    cudaFree(ctx->d_region_ctr);
-    if (ctx->region_hi)
-        cudaStreamDestroy(ctx->region_hi);
-    if (ctx->region_lo)
-        cudaStreamDestroy(ctx->region_lo);
-    for (cudaEvent_t e : ctx->region_ev)
-        if (e)
-            cudaEventDestroy(e);
     dp_release(ctx);
     cudaFree(ctx->d_blas_ext), cudaFree(ctx->d_attr_ext);
     cudaFree(ctx->d_sampler_items), cudaFree(ctx->d_sampler_counters);
@@ -632,18 +622,13 @@ int nbvh_host::adopt_nbvh(nbvh_ctx *ctx, const void *nodes, uint32_t n, cudaMemc
     ctx->tree_cut_ready = false; // a new tree-cut invalidates the learning state (reinitialise_neural_bvh_learning_states)
     CU_TRY(ctx, cudaMemcpy(ctx->d_nbvh, nodes, (size_t)n * 32, kind));
     ctx->dilated_with = -1.f, ctx->walk_version++;
-    {
+    if (!ctx->scene_bbox_set) {
+        // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
+        // (neural_bvh_renderer_accel.cpp:40,248-251)
         nbvh_node32 root;
         CU_TRY(ctx, cudaMemcpy(&root, ctx->d_nbvh, 32, cudaMemcpyDeviceToHost));
-        memcpy(ctx->nbvh_root_min, root.aabb_min, 12);
-        memcpy(ctx->nbvh_root_max, root.aabb_max, 12);
-        ctx->nbvh_root_known = true;
-        if (!ctx->scene_bbox_set) {
-            // load_neural_bvh takes the CPU BLAS root box, which is the box of tree-cut node 0
-            // (neural_bvh_renderer_accel.cpp:40,248-251)
-            memcpy(ctx->scene_bbox.min, root.aabb_min, 12);
-            memcpy(ctx->scene_bbox.max, root.aabb_max, 12);
-        }
+        memcpy(ctx->scene_bbox.min, root.aabb_min, 12);
+        memcpy(ctx->scene_bbox.max, root.aabb_max, 12);
     }
     return refresh_dilated(ctx);
 }
@@ -831,7 +816,7 @@ int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
         cudaEventDestroy(e);
     ctx->stage_ev.clear();
     ctx->stage_used = 0;
-    for (uint32_t i = 0; i < 4u * max_frames; i++) { // per frame: start, primary done, frame done, neural pass done
+    for (uint32_t i = 0; i < 3u * max_frames; i++) {
         cudaEvent_t e;
         CU_TRY(ctx, cudaEventCreate(&e));
         ctx->stage_ev.push_back(e);
@@ -846,11 +831,11 @@ int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_m
         return NBVH_ERR_INVALID_ARG;
     float a = 0.f, b = 0.f;
     for (uint32_t i = 0; i < ctx->stage_used; i++) {
-        cudaEvent_t *e = ctx->stage_ev.data() + 4u * i;
+        cudaEvent_t *e = ctx->stage_ev.data() + 3u * i;
         CU_TRY(ctx, cudaEventSynchronize(e[2]));
         float m0 = 0.f, m1 = 0.f;
         CU_TRY(ctx, cudaEventElapsedTime(&m0, e[0], e[1]));
-        CU_TRY(ctx, cudaEventElapsedTime(&m1, e[1], e[3])); // the neural pass itself (a region-split frame ends later: e[2])
+        CU_TRY(ctx, cudaEventElapsedTime(&m1, e[1], e[2]));
         a += m0, b += m1;
     }
     if (primary_ms_total)

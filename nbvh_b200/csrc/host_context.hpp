@@ -188,14 +188,6 @@ struct nbvh_ctx {
     uint32_t launches = 0;
     // stage timing of the split frame pipeline: event triples (start, between k_primary and k_neural, end) recorded
     // without host synchronisation; read back by nbvh_get_stage_times
-    // region split of depth-1 frames (launch_render_regions): internal high / low priority streams, their events, the counters of
-    // the outside region's queue, and the N-BVH root box the pixel rectangle is projected from
-    bool region_split = true;            // NBVH_REGION_SPLIT=0 switches it off
-    cudaStream_t region_hi = nullptr, region_lo = nullptr;
-    cudaEvent_t region_ev[3] = {nullptr, nullptr, nullptr};
-    uint32_t *d_region_ctr = nullptr;
-    float nbvh_root_min[3] = {0.f, 0.f, 0.f}, nbvh_root_max[3] = {0.f, 0.f, 0.f};
-    bool nbvh_root_known = false;
     std::vector<cudaEvent_t> stage_ev;
     uint32_t stage_used = 0; // frames recorded
     // the same for the optimisation step: per recorded step 7 events (before encode | mlp | grid backward | gradient exchange |

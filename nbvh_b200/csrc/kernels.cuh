@@ -94,9 +94,6 @@ struct RenderParams {
     uint32_t first_pixel, pixel_count; // shard of the frame rendered by this launch
     uint32_t spp_count; // samples per launch (multi-sample path launches: slot = sample * pixel_count + pixel slot; 0/1 = one)
     uint32_t chunk_stride, chunk_offset; // interleaved shard: every chunk_stride-th 32-pixel chunk from chunk_offset (0/1 = contiguous)
-    // region split of a full frame (launch_render_regions): 1 = the launch owns the 8x4-pixel blocks INSIDE the block rectangle
-    // [rect_bx0, rect_bx0 + rect_bw) x [rect_by0, rect_by0 + rect_bh), 2 = the blocks outside it, 0 = off
-    uint32_t rect_mode, rect_bx0, rect_by0, rect_bw, rect_bh;
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
     NeuralQueueEntry *queue;            // neural ray queue filled by k_primary, drained by k_neural
     uint32_t *queue_count, *queue_cursor;
@@ -217,17 +214,6 @@ cudaError_t launch_selftest_division(uint64_t seed, uint32_t blocks, uint32_t it
 cudaError_t launch_predilate(const float4 *src, float4 *dst, uint32_t n, float dilation, cudaStream_t stream);
 cudaError_t launch_render(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream);
 cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int num_sms, cudaStream_t stream, cudaEvent_t between);
-// One depth-1 frame as two pixel regions: the blocks inside `rect` (every pixel whose ray can reach the neural BVH) go
-// through k_primary + k_neural on `hi`, a high-priority stream; the blocks outside it -- classical hits and background only -- run
-// k_primary on the low-priority stream `lo` and fill the SMs that the persistent k_neural CTAs free while the launch drains its
-// dependent query chains.  `rp_out` queues into its own region and counters; a last k_neural launch on `stream` drains whatever the
-// outside region queued after all (nothing when the rectangle is conservative; the launch then exits before its set-up).
-struct RegionStreams {
-    cudaStream_t hi, lo;
-    cudaEvent_t start, hi_done, lo_done;
-};
-cudaError_t launch_render_regions(const RenderParams &rp_in, const RenderParams &rp_out, const NetConst &nc, int num_sms, cudaStream_t stream,
-                                  const RegionStreams &rs, cudaEvent_t between, cudaEvent_t neural_done);
 cudaError_t configure_render(uint32_t wimg_bytes, uint32_t in_k);
 cudaError_t launch_neural(const RenderParams &rp, const NetConst &nc, int num_sms, bool path_mode, cudaStream_t stream);
 cudaError_t configure_kernels(uint32_t wimg_bytes, uint32_t in_k);

@@ -258,7 +258,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
-    // nothing queued (the safety-net launch of launch_render_regions, frames without neural rays): leave before TMEM / weight set-up.
+    // nothing queued (frames without neural rays): leave before TMEM / weight set-up.
     // The counts are final: every producer launch precedes this kernel in stream order.
     if (*reinterpret_cast<const volatile uint32_t *>(p.queue_count) +
             (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u) == 0u)
@@ -578,43 +578,6 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
         k_resolve_ldr<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp, 1.f / (float)(rp.sample_idx + (int)rp.spp_count));
         return cudaGetLastError();
     }
-    return cudaSuccess;
-}
-
-cudaError_t launch_render_regions(const RenderParams &rp_in, const RenderParams &rp_out, const NetConst &nc, int num_sms, cudaStream_t stream,
-                                  const RegionStreams &rs, cudaEvent_t between, cudaEvent_t neural_done)
-{
-    cudaError_t e;
-#define NBVH_TRY(x)                                                                                                                        \
-    if ((e = (x)) != cudaSuccess)                                                                                                          \
-    return e
-    NBVH_TRY(cudaEventRecord(rs.start, stream));
-    NBVH_TRY(cudaStreamWaitEvent(rs.hi, rs.start, 0));
-    NBVH_TRY(cudaStreamWaitEvent(rs.lo, rs.start, 0));
-    // inside region: primary pass, then the persistent neural pass
-    if (rp_in.pixel_count) {
-        k_primary<<<((rp_in.pixel_count >> 5) + 7u) / 8u, 256, 0, rs.hi>>>(rp_in);
-        NBVH_TRY(cudaGetLastError());
-    }
-    if (between)
-        NBVH_TRY(cudaEventRecord(between, rs.hi));
-    if (rp_in.pixel_count)
-        NBVH_TRY(launch_neural(rp_in, nc, num_sms, false, rs.hi));
-    if (neural_done)
-        NBVH_TRY(cudaEventRecord(neural_done, rs.hi));
-    NBVH_TRY(cudaEventRecord(rs.hi_done, rs.hi));
-    // outside region: primary pass only, at low priority
-    if (rp_out.pixel_count) {
-        k_primary<<<((rp_out.pixel_count >> 5) + 7u) / 8u, 256, 0, rs.lo>>>(rp_out);
-        NBVH_TRY(cudaGetLastError());
-    }
-    NBVH_TRY(cudaEventRecord(rs.lo_done, rs.lo));
-    NBVH_TRY(cudaStreamWaitEvent(stream, rs.hi_done, 0));
-    NBVH_TRY(cudaStreamWaitEvent(stream, rs.lo_done, 0));
-    // safety net: rays of the outside region that reached the neural BVH after all
-    if (rp_out.pixel_count)
-        NBVH_TRY(launch_neural(rp_out, nc, num_sms, false, stream));
-#undef NBVH_TRY
     return cudaSuccess;
 }
 

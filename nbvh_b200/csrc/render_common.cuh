@@ -222,29 +222,6 @@ __device__ __forceinline__ void background(const RenderParams &p, const Ray &ray
 // chunk_offset, so its slot s maps to the global slot ((s / 32) * stride + offset) * 32 + s % 32.
 __device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_t s)
 {
-    if (p.rect_mode) {
-        // region launches (launch_render_regions): slot -> 8x4 block inside / outside the block rectangle, row-major in both cases
-        const uint32_t bpr = p.cam.fb_w >> 3;
-        uint32_t c = s >> 5, bx, by;
-        const uint32_t k = s & 31u;
-        if (p.rect_mode == 1u) {
-            by = p.rect_by0 + c / p.rect_bw, bx = p.rect_bx0 + c % p.rect_bw;
-        } else {
-            const uint32_t top = p.rect_by0 * bpr, per_row = bpr - p.rect_bw, mid = p.rect_bh * per_row;
-            if (c < top) {
-                by = c / bpr, bx = c % bpr;
-            } else if (c < top + mid) {
-                c -= top;
-                by = p.rect_by0 + c / per_row;
-                const uint32_t x = c % per_row;
-                bx = x < p.rect_bx0 ? x : x + p.rect_bw;
-            } else {
-                c -= top + mid;
-                by = p.rect_by0 + p.rect_bh + c / bpr, bx = c % bpr;
-            }
-        }
-        return (by * 4u + (k >> 3)) * p.cam.fb_w + bx * 8u + (k & 7u);
-    }
     if (p.chunk_stride > 1u)
         s = (((s - p.first_pixel) >> 5) * p.chunk_stride + p.chunk_offset) * 32u + (s & 31u);
     const uint32_t w = p.cam.fb_w, h = p.cam.fb_h;
