@@ -484,15 +484,49 @@ def main():
         step_no = [0]
         mod.sampler_walk_ahead(walk_ahead, world)  # one walk launch serves 16 steps of this rank (training_step = step * world + rank)
 
+        # second set of sample buffers + a generation stream: the samples of a step depend on the tree-cut and the RNG only (not on the
+        # parameters), so step k + 1 is generated while step k runs forward / backward / gradient exchange / Adam -- the same batches
+        # in the same order as the sequential loop (tools/train_overlap_probe.py); at N > 1 this hides the wait for the NCCL buckets
+        nodes_dev2 = torch.zeros(train_B, dtype=torch.int32, device=dev)
+        tx2 = torch.zeros((train_B, in_dims), dtype=torch.float32, device=dev)
+        tt2 = torch.zeros((train_B, out_dims), dtype=torch.float32, device=dev)
+        gen_stream = torch.cuda.Stream(device=dev)
+        buf_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        buf_free = [torch.cuda.Event(), torch.cuda.Event()]
+
         def run_steps(B_local, B_global, n, what="step"):
-            sx, st_, sn = tx[:B_local], tt[:B_local], nodes_dev[:B_local]
-            for _ in range(n):
+            bufs = [(tx[:B_local], tt[:B_local], nodes_dev[:B_local]), (tx2[:B_local], tt2[:B_local], nodes_dev2[:B_local])]
+            if what != "step":  # "generate": sample generation alone; "sequential": one stream (per-kernel stage timing, kernels alone)
+                sx, st_, sn = bufs[0]
+                for _ in range(n):
+                    mod.optimisation_data_generation(step_no[0] * world + rank, B_local, 0, sn, 1.0, cut_dev, sx, st_, stream=stream.cuda_stream)
+                    step_no[0] += 1
+                    if what == "sequential":
+                        mod.training_forward_backward(sx, st_, global_batch=B_global, stream=stream.cuda_stream)
+                        mod.optimizer_step(stream=stream.cuda_stream)
+                return
+            gen_stream.wait_stream(stream)
+            for b in range(2):
+                buf_free[b].record(stream)
+
+            def generate(k):
                 # rank r samples its own slots of the global batch: the RNG is keyed by training_step * batch + slot
-                mod.optimisation_data_generation(step_no[0] * world + rank, B_local, 0, sn, 1.0, cut_dev, sx, st_, stream=stream.cuda_stream)
-                step_no[0] += 1
-                if what == "step":
-                    mod.training_forward_backward(sx, st_, global_batch=B_global, stream=stream.cuda_stream)
-                    mod.optimizer_step(stream=stream.cuda_stream)
+                sx, st_, sn = bufs[k & 1]
+                gen_stream.wait_event(buf_free[k & 1])
+                mod.optimisation_data_generation((step_no[0] + k) * world + rank, B_local, 0, sn, 1.0, cut_dev, sx, st_,
+                                                 stream=gen_stream.cuda_stream)
+                buf_ready[k & 1].record(gen_stream)
+
+            generate(0)
+            for k in range(n):
+                if k + 1 < n:
+                    generate(k + 1)
+                sx, st_, sn = bufs[k & 1]
+                stream.wait_event(buf_ready[k & 1])
+                mod.training_forward_backward(sx, st_, global_batch=B_global, stream=stream.cuda_stream)
+                mod.optimizer_step(stream=stream.cuda_stream)
+                buf_free[k & 1].record(stream)
+            step_no[0] += n
 
         def time_steps(B_local, B_global, what="step"):
             run_steps(B_local, B_global, (walk_ahead - step_no[0] % walk_ahead) % walk_ahead + walk_ahead, what)  # warm-up to a group boundary
@@ -505,8 +539,9 @@ def main():
             return te0.elapsed_time(te1) / train_steps
 
         train_ms = time_steps(train_B, train_B * world)
+        seq_ms = time_steps(train_B, train_B * world, what="sequential")
         mod.enable_training_stage_timing(train_steps)
-        run_steps(train_B, train_B * world, train_steps)
+        run_steps(train_B, train_B * world, train_steps, what="sequential")
         torch.cuda.synchronize()
         stage, stage_n = mod.training_stage_times()
         mod.enable_training_stage_timing(0)
@@ -516,14 +551,14 @@ def main():
         if world > 1:
             strong_ms = time_steps(train_B // world, train_B)
             mod.enable_training_stage_timing(train_steps)
-            run_steps(train_B // world, train_B, train_steps)
+            run_steps(train_B // world, train_B, train_steps, what="sequential")
             torch.cuda.synchronize()
             strong_stage, sn_ = mod.training_stage_times()
             mod.enable_training_stage_timing(0)
             strong_stage = {k: v / max(sn_, 1) for k, v in strong_stage.items()}
             strong_gen = time_steps(train_B // world, train_B, what="generate")
             strong_stage["sample_generation"] = strong_gen
-        train = dict(train_B=train_B, train_ms=train_ms, gen_ms=gen_ms, strong_ms=strong_ms, strong_stage=strong_stage,
+        train = dict(train_B=train_B, train_ms=train_ms, seq_ms=seq_ms, gen_ms=gen_ms, strong_ms=strong_ms, strong_stage=strong_stage,
                      stage={k: v / max(stage_n, 1) for k, v in stage.items()}, steps=train_steps)
 
     # ---------------- hybrid neural path tracing (BASELINE configs[1] at the shipped max_depth = "2b", and configs[3]):
@@ -719,10 +754,10 @@ def main():
                     v_["frac"] = v_["achieved"] / v_["peak"]
             line["train"] = {"metric": "train samples/s", "value": world * B / (train_ms * 1e-3), "unit": "samples/s",
                              "ms_per_step": train_ms, "batch_per_gpu": B, "steps": train["steps"], "scaling": "weak",
-                             "sample_generation_ms": train["gen_ms"], "roofline": kern,
+                             "sample_generation_ms": train["gen_ms"], "ms_per_step_one_stream": train["seq_ms"], "roofline": kern,
                              "strong_scaling": {"global_batch": B, "ms_per_step": strong_train_ms, "samples_s": B / (strong_train_ms * 1e-3),
                                                 "per_kernel_ms": train["strong_stage"]},
-                             "what": "per step: sample generation on the Chess tree-cut + neural-mesh BLAS (K10, procedural materials), "
+                             "what": "per step: sample generation on the Chess tree-cut + neural-mesh BLAS (K10, procedural materials; generated for step k + 1 on a second stream while step k trains: same batches, same order), "
                                      "hash-grid encode + fused tcgen05 MLP forward/loss/backward + grid backward + Adam" +
                                      ("; gradient exchange inside the library (NCCL, two buckets)" if world > 1 else "")}
             config["train_samples_s"] = world * B / (train_ms * 1e-3)
