@@ -297,8 +297,35 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
         CU_TRY(ctx, cudaMalloc(&queue, slots * sizeof(NeuralQueueEntry)));
         queue_capacity = slots;
     }
+    // drain order by expected chain length (kernels.cuh: class_lists): a 16-word header (render counters [0..3], class counts
+    // [4..8]) followed by kChainClasses index lists of queue_capacity entries; primary-ray pipeline only
+    uint32_t memset_words = 4;
+    if (ctx->long_chain_thr != 0u && ctx->max_depth == 1 && !ctx->mega_kernel) {
+        uint32_t *&lists   = ctx->d_class_lists[alt ? ai + 1 : 0];
+        size_t &lists_cap  = ctx->class_lists_capacity[alt ? ai + 1 : 0];
+        if (lists_cap != queue_capacity) {
+            CU_TRY(ctx, cudaDeviceSynchronize());
+            cudaFree(lists);
+            lists = nullptr, lists_cap = 0;
+            CU_TRY(ctx, cudaMalloc(&lists, (16 + (size_t)kChainClasses * queue_capacity) * sizeof(uint32_t)));
+            lists_cap = queue_capacity;
+        }
+        if (ctx->chain_hist_pixels != (size_t)total) {
+            CU_TRY(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->d_chain_hist);
+            ctx->d_chain_hist = nullptr, ctx->chain_hist_pixels = 0;
+            CU_TRY(ctx, cudaMalloc(&ctx->d_chain_hist, (size_t)total));
+            CU_TRY(ctx, cudaMemset(ctx->d_chain_hist, 0, (size_t)total));
+            ctx->chain_hist_pixels = (size_t)total;
+        }
+        chunk_ctr      = lists;
+        rp.next_chunk  = chunk_ctr;
+        rp.class_count = lists + 4, rp.class_lists = lists + 16;
+        rp.chain_hist  = ctx->d_chain_hist;
+        rp.chain_thr   = ctx->long_chain_thr, rp.chain_flags = ctx->chain_pred;
+        memset_words   = 4 + kChainClasses;
+    }
     rp.queue = queue, rp.queue_count = chunk_ctr + 1, rp.queue_cursor = chunk_ctr + 2;
-    rp.queue_count_back = chunk_ctr + 3; // zeroed with the other counters below
     rp.queue_capacity   = (uint32_t)queue_capacity;
     rp.sample_idx    = (int)accumulated_spp;
     rp.sample_offset = (int)sample_offset;
@@ -307,7 +334,7 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
     rp.ema_weight     = ctx->scene_const.ema_weight;
     rp.counters       = ctx->d_counters;
     const NetConst nc = make_net_const(ctx);
-    CU_TRY(ctx, cudaMemsetAsync(chunk_ctr, 0, 4 * sizeof(uint32_t), st));
+    CU_TRY(ctx, cudaMemsetAsync(chunk_ctr, 0, memset_words * sizeof(uint32_t), st));
     KernelTimer kt(ctx, st);
     if (ctx->l2_prefetch) {
         // warm L2 with the tables the scattered gathers of this frame touch (see k_prefetch_l2)

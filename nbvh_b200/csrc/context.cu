@@ -366,6 +366,13 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
         ctx->mega_kernel = std::string(m) == "mega";
     if (const char *m = getenv("NBVH_L2_PREFETCH"))
         ctx->l2_prefetch = std::string(m) != "0";
+    if (const char *m = getenv("NBVH_CHAIN_CLASSES")) { // A/B measurements: "t0,t1,t2,t3" (descending), "0" = arrival order
+        unsigned t[4] = {0u, 0u, 0u, 0u};
+        const int n = sscanf(m, "%u,%u,%u,%u", &t[0], &t[1], &t[2], &t[3]);
+        ctx->long_chain_thr = n <= 0 ? 0u : ((t[0] & 255u) << 24) | ((t[1] & 255u) << 16) | ((t[2] & 255u) << 8) | (t[3] & 255u);
+    }
+    if (const char *m = getenv("NBVH_CHAIN_PRED"))
+        ctx->chain_pred = (uint32_t)atoi(m) & 3u;
     if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;
@@ -402,6 +409,9 @@ void nbvh_destroy(nbvh_ctx *ctx)
         cudaEventDestroy(ctx->ahead_done);
     cudaFree(ctx->d_node_keep);
     cudaFree(ctx->d_queue);
+    cudaFree(ctx->d_chain_hist);
+    for (int k = 0; k < kPipeSlots; k++)
+        cudaFree(ctx->d_class_lists[k]);
     for (int k = 0; k < 2; k++)
         cudaFree(ctx->d_paths[k]), cudaFree(ctx->d_path_hits[k]);
     cudaFree(ctx->d_build_ws);

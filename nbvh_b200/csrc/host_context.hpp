@@ -177,6 +177,15 @@ struct nbvh_ctx {
     uint32_t *d_next_chunk = nullptr; // [0] chunk counter (mega kernel), [1] queue count, [2] queue cursor, [3] node-check flag, [4] sampler slot counter, [5] image-error sum, [6] BLAS depth, [7] sampler item count
     NeuralQueueEntry *d_queue = nullptr;
     size_t queue_capacity = 0;
+    // Drain order of the neural ray queue by expected query-chain length (kernels.cuh: RenderParams::class_lists).  d_chain_hist:
+    // per-pixel chain length of the last frame (k_neural writes it, k_primary reads it); one header + index-list block per frame
+    // slot.  Scheduling only: results never depend on it.  NBVH_CHAIN_CLASSES="t0,t1,t2,t3" sets the class limits ("0" disables
+    // the ordering: arrival order), NBVH_CHAIN_PRED the predictor flags (bit 0: 3x3 maximum, bit 1: decaying maximum)
+    uint8_t *d_chain_hist = nullptr;
+    size_t chain_hist_pixels = 0;
+    uint32_t *d_class_lists[kPipeSlots] = {};
+    size_t class_lists_capacity[kPipeSlots] = {};
+    uint32_t long_chain_thr = (6u << 24) | (4u << 16) | (3u << 8) | 2u, chain_pred = 1;
     bool l2_prefetch = false; // NBVH_L2_PREFETCH=1 enables a per-frame L2 warm-up of the gather tables (A/B: no effect measured)
     bool mega_kernel = false; // NBVH_RENDER_MODE=mega: the single persistent kernel of the first design (kept for A/B timing)
     unsigned long long *d_counters = nullptr;

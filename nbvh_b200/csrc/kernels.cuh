@@ -81,6 +81,8 @@ struct BackgroundConst {
     cudaTextureObject_t envmap; // RGBA32F lat-long map, linear filter, clamp; 0 = white (the reference's fallback image)
 };
 
+constexpr int kChainClasses = 5;
+
 struct RenderParams {
     CameraConst cam;
     NbvhConst nbvh;
@@ -97,8 +99,15 @@ struct RenderParams {
     uint32_t *next_chunk;               // global work counter (32-pixel chunks)
     NeuralQueueEntry *queue;            // neural ray queue filled by k_primary, drained by k_neural
     uint32_t *queue_count, *queue_cursor;
-    uint32_t *queue_count_back; // rays expected to need few queries are queued from the END of the array (drained last); may be null
     uint32_t queue_capacity;
+    // Drain order of the queue (scheduling only -- results never depend on it).  class_lists != null: k_primary files every queued
+    // ray under one of kChainClasses classes by the query-chain length it is EXPECTED to need, k_neural drains class 0 (longest)
+    // first.  class_lists[k * queue_capacity + i] = queue slot of the i-th ray of class k; class_count[k] = rays in class k.
+    // The expectation is the chain the pixel's camera ray needed in the last frame: chain_hist[pixel] (0 = unknown), written by
+    // k_neural; chain_thr packs the class limits t0 >= t1 >= t2 >= t3 (one byte each, t0 in the top byte).
+    uint32_t *class_lists, *class_count;
+    uint8_t *chain_hist;
+    uint32_t chain_thr, chain_flags; // flags: bit 0 = predict from the 3x3 neighbourhood's maximum, bit 1 = decaying maximum
     int sample_idx, sample_offset;
     // outputs
     float4 *accum;          // RGBA32F accumulation buffer (linear memory replaces the GL surface)

@@ -291,6 +291,7 @@ cudaError_t launch_trace_rays(const RenderParams &rp_in, const NetConst &nc, con
     rp.first_pixel  = 0;
     rp.chunk_stride = 1, rp.chunk_offset = 0;
     rp.queue_count = counters, rp.queue_cursor = counters + 1;
+    rp.class_lists = nullptr, rp.class_count = nullptr, rp.chain_hist = nullptr; // arrival order (no per-pixel history of a ray batch)
     rp.ray_depth = ray_depth;
     rp.paths = paths, rp.path_hits = hits;
     rp.hits = nullptr;
@@ -371,6 +372,7 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
     if (rp_in.pixel_count == 0)
         return cudaSuccess;
     RenderParams rp       = rp_in;
+    rp.class_lists = nullptr, rp.class_count = nullptr, rp.chain_hist = nullptr;
     const uint32_t slots  = rp.pixel_count * (rp.spp_count > 1u ? rp.spp_count : 1u);
     const uint32_t blocks = ((slots + 31u) / 32u + 7u) / 8u;
     cudaError_t e;

@@ -40,6 +40,9 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
+#ifndef NBVH_CHAIN_STATS
+#define NBVH_CHAIN_STATS 0 // development builds: histogram of (predicted chain, actual chain) of every queued ray, printed per launch
+#endif
 #ifndef NBVH_WALK_BUDGET
 #define NBVH_WALK_BUDGET 0 // > 0: node fetches a lane may spend per walk round before it parks its walk (0 = unbounded).  Measured on
                            // B200 (gpurun s31): 4 fetches 0.606 ms, 8 fetches 0.507 ms, unbounded 0.506 ms per 1080p launch -- parked
@@ -111,6 +114,24 @@ k_clear_accum(const __grid_constant__ RenderParams p)
         p.accum[swizzle_pixel(p, p.first_pixel + i)] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+#if NBVH_CHAIN_STATS
+__device__ unsigned long long g_chain_stats[16 * 16];
+__device__ unsigned int g_chain_done;
+__device__ __forceinline__ uint32_t g_pred_dbg(const RenderParams &p, uint32_t pixel)
+{
+    uint32_t pred = 0u;
+    if (!p.chain_hist)
+        return 0u;
+    const uint32_t w = p.cam.fb_w, hgt = p.cam.fb_h;
+    const uint32_t px = pixel % w, py = pixel / w;
+    const uint32_t x0 = px > 0u ? px - 1u : 0u, x1 = px + 1u < w ? px + 1u : px;
+    const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
+    for (uint32_t y = y0; y <= y1; ++y)
+        for (uint32_t x = x0; x <= x1; ++x)
+            pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
+    return pred < 15u ? pred : 15u;
+}
+#endif
 // ------------------------------------------------------------------------------------------------ k_primary
 // 64 registers -> four CTAs per SM (measured: 0.386 -> 0.367 ms at 1080p; the kernel is issue-bound and takes the extra warps)
 __global__ void __launch_bounds__(256, 4)
@@ -167,32 +188,67 @@ k_primary(const __grid_constant__ RenderParams p)
             neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
         }
     }
-    // ---- queue compaction: one atomic per warp and class.  Longest-processing-time-first: rays whose pending N-BVH stack is deep
-    // (many leaves still ahead) are queued from the front and drained first, the others from the back of the array -- the
-    // persistent kernel's tail then consists of short query chains (k_neural header)
-    const bool is_long    = nss >= kLongStack || p.queue_count_back == nullptr;
-    const uint32_t qlong  = __ballot_sync(0xFFFFFFFFu, active && neural && is_long);
-    const uint32_t qshort = __ballot_sync(0xFFFFFFFFu, active && neural && !is_long);
-    uint32_t base_l = 0, base_s = 0;
-    if (qlong) {
-        if (lane == (uint32_t)(__ffs(qlong) - 1))
-            base_l = atomicAdd(p.queue_count, (uint32_t)__popc(qlong));
-        base_l = __shfl_sync(0xFFFFFFFFu, base_l, __ffs(qlong) - 1);
+    // ---- queue compaction: one atomic per warp for the slot, one per class present in the warp for the drain order.
+    // Longest-processing-time-first: k_neural drains the classes in order, so the rays expected to need the longest query chains
+    // start first and the persistent kernel's tail consists of short chains (k_neural header).  The chain length
+    // is uncorrelated with anything known about the ray at queue time, but strongly correlated from sample to sample of one pixel.
+    uint32_t cls = 0u;
+    if (p.class_lists && active && neural) {
+        uint32_t pred = 0u;
+        if (p.chain_hist) {
+            if (p.chain_flags & 1u) { // the jittered ray may fall anywhere in the pixel: the longest chain of the 3x3 neighbourhood
+                const uint32_t w = p.cam.fb_w, hgt = p.cam.fb_h;
+                const uint32_t px = pixel % w, py = pixel / w;
+                const uint32_t x0 = px > 0u ? px - 1u : 0u, x1 = px + 1u < w ? px + 1u : px;
+                const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
+                for (uint32_t y = y0; y <= y1; ++y)
+                    for (uint32_t x = x0; x <= x1; ++x)
+                        pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
+            } else
+                pred = p.chain_hist[pixel];
+        }
+        if (pred == 0u) // no history (first frame, or the neighbourhood queued nothing): pending-stack depth
+            cls = nss >= kLongStack ? 2u : 3u;
+        else
+            cls = (pred < (p.chain_thr >> 24) ? 1u : 0u) + (pred < ((p.chain_thr >> 16) & 255u) ? 1u : 0u) +
+                  (pred < ((p.chain_thr >> 8) & 255u) ? 1u : 0u) + (pred < (p.chain_thr & 255u) ? 1u : 0u);
     }
-    if (qshort) {
-        if (lane == (uint32_t)(__ffs(qshort) - 1))
-            base_s = atomicAdd(p.queue_count_back, (uint32_t)__popc(qshort));
-        base_s = __shfl_sync(0xFFFFFFFFu, base_s, __ffs(qshort) - 1);
-    }
-    if (active && neural) {
+    const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
+    if (qmask) {
         const uint32_t below = (1u << lane) - 1u;
-        const uint32_t slot  = is_long ? base_l + __popc(qlong & below) : p.queue_capacity - 1u - (base_s + __popc(qshort & below));
-        NeuralQueueEntry *q = p.queue + slot;
-        q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
-        q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
-        q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), smp, 0u); // c.z: sample of a multi-sample launch
-        for (int i = 0; i < nss; i += 4)
-            q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
+        const int leader     = __ffs(qmask) - 1;
+        uint32_t base = 0;
+        if (lane == (uint32_t)leader)
+            base = atomicAdd(p.queue_count, (uint32_t)__popc(qmask));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        const uint32_t slot = base + __popc(qmask & below);
+        if (active && neural) {
+            NeuralQueueEntry *q = p.queue + slot;
+            q->a = make_uint4(pixel, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
+            q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
+#if NBVH_CHAIN_STATS
+            q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), smp, g_pred_dbg(p, pixel) | (cls << 8));
+#else
+            q->c = make_uint4(__float_as_uint(seg_mint), __float_as_uint(seg_maxt), smp, 0u); // c.z: sample of a multi-sample launch
+#endif
+            for (int i = 0; i < nss; i += 4)
+                q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
+        }
+        if (p.class_lists) {
+            uint32_t rem = qmask; // warp-uniform
+            while (rem) {
+                const int l0     = __ffs(rem) - 1;
+                const uint32_t k = __shfl_sync(0xFFFFFFFFu, cls, l0);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((qmask >> lane) & 1u) && cls == k);
+                uint32_t cb = 0;
+                if (lane == (uint32_t)l0)
+                    cb = atomicAdd(p.class_count + k, (uint32_t)__popc(m));
+                cb = __shfl_sync(0xFFFFFFFFu, cb, l0);
+                if ((m >> lane) & 1u)
+                    p.class_lists[(size_t)k * p.queue_capacity + cb + __popc(m & below)] = slot;
+                rem &= ~m;
+            }
+        }
     }
     if (active && !neural)
         finish_pixel(p, pixel, ray, h);
@@ -215,6 +271,7 @@ struct NeuralLane {
     float seg_mint, seg_maxt;
     int nss;
     bool have_ray, have_query;
+    uint32_t nq;  // queries this ray has been through (chain-length history)
     uint32_t rng; // kUniform only: the ray's generator (segment parameters are drawn from it; path mode hands it back to the path state)
 };
 
@@ -228,8 +285,22 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 
 template <bool kPath, bool kUniform>
-__device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, const Ray &ray, const HitState &h, uint32_t rng)
+__device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, const Ray &ray, const HitState &h, uint32_t rng, uint32_t nq)
 {
+    if constexpr (!kPath) {
+#if NBVH_CHAIN_STATS
+        atomicAdd(&g_chain_stats[(nq >> 16) * 16u + min(nq & 0xFFFFu, 15u)], 1ull);
+        nq &= 0xFFFFu;
+#endif
+        if (p.chain_hist) {
+            uint32_t v = nq < 255u ? nq : 255u;
+            if (p.chain_flags & 2u) { // slow decay: a pixel that needed a long chain recently stays suspicious for a few frames
+                const uint32_t old = p.chain_hist[id];
+                v = max(v, old > 0u ? old - 1u : 0u);
+            }
+            p.chain_hist[id] = (uint8_t)v;
+        }
+    }
     if constexpr (kPath) {
         if constexpr (kUniform)
             p.paths[id].s3.x = rng; // HybridIntersectionResult takes the traversal data's throughput_rng back (path_module.h:111,141)
@@ -260,9 +331,18 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     __shared__ uint32_t s_flags[kNeuralThreads / 32];
     // nothing queued (frames without neural rays): leave before TMEM / weight set-up.
     // The counts are final: every producer launch precedes this kernel in stream order.
-    if (*reinterpret_cast<const volatile uint32_t *>(p.queue_count) +
-            (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u) == 0u)
+    if (*reinterpret_cast<const volatile uint32_t *>(p.queue_count) == 0u)
         return;
+    __shared__ uint32_t s_cum[kChainClasses + 1]; // class k of the drain order = queue positions [s_cum[k], s_cum[k + 1])
+    if (threadIdx.x == 0) {
+        uint32_t cum = 0u;
+        for (int k = 0; k < kChainClasses; ++k) {
+            s_cum[k] = cum;
+            if (p.class_lists)
+                cum += reinterpret_cast<const volatile uint32_t *>(p.class_count)[k];
+        }
+        s_cum[kChainClasses] = cum;
+    }
 #if NBVH_TILE_COOP
     __shared__ uint32_t s_qmask[kNeuralThreads / 32];
     __shared__ float s_ep[kNeuralThreads * 6];
@@ -275,8 +355,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     const uint32_t warp      = threadIdx.x >> 5;
     TileCtx t                = make_tile(smem, lay, nc, tile, tmem_base);
 
-    const uint32_t n_front  = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
-    const uint32_t n_queued = n_front + (p.queue_count_back ? *reinterpret_cast<const volatile uint32_t *>(p.queue_count_back) : 0u);
+    const uint32_t n_queued = *reinterpret_cast<const volatile uint32_t *>(p.queue_count);
 #if NBVH_NEURAL_SMEM_STACK
     const LaneStack nstack{reinterpret_cast<uint32_t *>(smem + neural_stack_offset(nc.wimg_bytes, nc.in_k)) + threadIdx.x};
 #else
@@ -284,7 +363,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #endif
     NeuralLane s;
     s.have_ray = s.have_query = false;
-    s.nss = 0, s.pixel = 0u;
+    s.nss = 0, s.pixel = 0u, s.nq = 0u;
 
     uint32_t chunk_base = 0u, chunk_used = 32u;
     bool exhausted = false;
@@ -328,7 +407,14 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                 if (!s.have_ray && rank < avail) {
                     const uint32_t qi = chunk_base + chunk_used + rank;
                     if (qi < n_queued) {
-                        const NeuralQueueEntry *q = p.queue + (qi < n_front ? qi : p.queue_capacity - 1u - (qi - n_front));
+                        uint32_t ei = qi;
+                        if (p.class_lists) { // position in the drain order -> class list -> queue slot
+                            int k = 0;
+                            while (k < kChainClasses - 1 && qi >= s_cum[k + 1])
+                                ++k;
+                            ei = p.class_lists[(size_t)k * p.queue_capacity + (qi - s_cum[k])];
+                        }
+                        const NeuralQueueEntry *q = p.queue + ei;
                         const uint4 a = q->a, b = q->b, c = q->c;
                         uint32_t rng;
                         s.pixel       = a.x;
@@ -356,6 +442,10 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                         }
                         s.have_ray   = true;
                         s.have_query = true;
+                        s.nq         = 0u;
+#if NBVH_CHAIN_STATS
+                        s.nq = (c.w & 15u) << 16; // predicted chain rides in the upper half
+#endif
                     }
                 }
                 const uint32_t want = __popc(need_mask);
@@ -382,7 +472,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
                     s.have_query = true;
 #endif
                 } else {
-                    finish_lane<kPath, kUniform>(p, s.pixel, s.ray, s.h, s.rng);
+                    finish_lane<kPath, kUniform>(p, s.pixel, s.ray, s.h, s.rng, s.nq);
                     s.have_ray = false;
                 }
             }
@@ -476,6 +566,7 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #endif
         if (s.have_query) {
             ++cnt_q;
+            ++s.nq;
             float t_hit;
             if (decode_hit(p.dec, s.ray, y[0], y[1], s.seg_mint, s.seg_maxt, kPath ? p.ray_depth : 1u, t_hit) && t_hit < s.h.best_t) {
                 s.h.best_t    = t_hit;
@@ -524,6 +615,21 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         atomicMax(p.counters + CNT_T_END, t1);
         atomicAdd(p.counters + CNT_T_CTA_SUM, t1 - t_cta0);
     }
+#if NBVH_CHAIN_STATS
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_chain_done, 1u) == gridDim.x - 1u) {
+            for (int a = 0; a < 16; ++a) {
+                printf("[chain stats] pred %2d:", a);
+                for (int b = 0; b < 16; ++b)
+                    printf(" %llu", g_chain_stats[a * 16 + b]), g_chain_stats[a * 16 + b] = 0ull;
+                printf("\n");
+            }
+            g_chain_done = 0u;
+        }
+    }
+#endif
     cta_teardown<kNeuralTiles>(tmem_base);
 }
 
