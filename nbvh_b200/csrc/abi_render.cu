@@ -298,9 +298,9 @@ static int render_impl(nbvh_ctx *ctx, uint32_t accumulated_spp, uint32_t sample_
         queue_capacity = slots;
     }
     // drain order by expected chain length (kernels.cuh: class_lists): a 16-word header (render counters [0..3], class counts
-    // [4..8]) followed by kChainClasses index lists of queue_capacity entries; primary-ray pipeline only
+    // [4..8]) followed by kChainClasses index lists of queue_capacity entries; camera rays only (bounce rays have no per-pixel history)
     uint32_t memset_words = 4;
-    if (ctx->long_chain_thr != 0u && ctx->max_depth == 1 && !ctx->mega_kernel) {
+    if (ctx->long_chain_thr != 0u && !ctx->mega_kernel) {
         uint32_t *&lists   = ctx->d_class_lists[alt ? ai + 1 : 0];
         size_t &lists_cap  = ctx->class_lists_capacity[alt ? ai + 1 : 0];
         if (lists_cap != queue_capacity) {

@@ -185,7 +185,7 @@ struct nbvh_ctx {
     size_t chain_hist_pixels = 0;
     uint32_t *d_class_lists[kPipeSlots] = {};
     size_t class_lists_capacity[kPipeSlots] = {};
-    uint32_t long_chain_thr = (6u << 24) | (4u << 16) | (3u << 8) | 2u, chain_pred = 1;
+    uint32_t long_chain_thr = (4u << 24) | (3u << 16) | (2u << 8) | 2u, chain_pred = 1; // classes: >= 4, 3, 2, -, 1 (s45 sweep)
     bool l2_prefetch = false; // NBVH_L2_PREFETCH=1 enables a per-frame L2 warm-up of the gather tables (A/B: no effect measured)
     bool mega_kernel = false; // NBVH_RENDER_MODE=mega: the single persistent kernel of the first design (kept for A/B timing)
     unsigned long long *d_counters = nullptr;

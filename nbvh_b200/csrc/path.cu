@@ -211,14 +211,23 @@ k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
             neural = nbvh_next_interval(p.nbvh, ray, nstack, nss, h.best_t, seg_mint, seg_maxt, node, cnt_nbvh);
         }
     }
+    uint32_t cls = 0u;
+    if constexpr (kFirst) {
+        if (p.class_lists && active && neural)
+            cls = chain_class(p, pixel, nss);
+    }
     const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
     if (qmask) {
         uint32_t base = 0;
         if (lane == (uint32_t)(__ffs(qmask) - 1))
             base = atomicAdd(p.queue_count, (uint32_t)__popc(qmask));
         base = __shfl_sync(0xFFFFFFFFu, base, __ffs(qmask) - 1);
+        const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
+        if constexpr (kFirst) {
+            if (p.class_lists)
+                file_in_class(p, qmask, cls, slot, lane);
+        }
         if (active && neural) {
-            const uint32_t slot = base + __popc(qmask & ((1u << lane) - 1u));
             NeuralQueueEntry *q = p.queue + slot;
             q->a = make_uint4(sidx, __float_as_uint(h.best_t), h.valid_hit, __float_as_uint(h.n_or_uv[0]));
             q->b = make_uint4(__float_as_uint(h.n_or_uv[1]), __float_as_uint(h.alb_or_ids[0]), __float_as_uint(h.alb_or_ids[1]), (uint32_t)nss);
@@ -372,7 +381,6 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
     if (rp_in.pixel_count == 0)
         return cudaSuccess;
     RenderParams rp       = rp_in;
-    rp.class_lists = nullptr, rp.class_count = nullptr, rp.chain_hist = nullptr;
     const uint32_t slots  = rp.pixel_count * (rp.spp_count > 1u ? rp.spp_count : 1u);
     const uint32_t blocks = ((slots + 31u) / 32u + 7u) / 8u;
     cudaError_t e;
@@ -392,6 +400,7 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
         if (depth == 1u) {
             k_path_trace<true><<<blocks, 256, 0, stream>>>(rp, io);
         } else {
+            rp.class_lists = nullptr, rp.class_count = nullptr, rp.chain_hist = nullptr; // bounce rays: arrival order
             rp.nbvh = nbvh_bounce; // path_lod_switch: bounce rays may walk a coarser LoD (neural_bvh_module_common.cuh:333-335)
             k_path_trace<false><<<blocks, 256, 0, stream>>>(rp, io);
         }

@@ -68,7 +68,6 @@ __host__ __device__ inline uint32_t neural_stack_offset(uint32_t wimg_bytes, uin
 {
     return (smem_layout(wimg_bytes, in_k, kNeuralTiles).total + 127u) & ~127u;
 }
-constexpr int kLongStack     = NBVH_LONG_STACK;          // pending-stack depth from which a queued ray counts as a long query chain
 constexpr int kWalkRounds    = NBVH_WALK_ROUNDS;         // refill/advance rounds before a tile runs the network
 
 // ------------------------------------------------------------------------------------------------ shared helpers
@@ -192,27 +191,7 @@ k_primary(const __grid_constant__ RenderParams p)
     // Longest-processing-time-first: k_neural drains the classes in order, so the rays expected to need the longest query chains
     // start first and the persistent kernel's tail consists of short chains (k_neural header).  The chain length
     // is uncorrelated with anything known about the ray at queue time, but strongly correlated from sample to sample of one pixel.
-    uint32_t cls = 0u;
-    if (p.class_lists && active && neural) {
-        uint32_t pred = 0u;
-        if (p.chain_hist) {
-            if (p.chain_flags & 1u) { // the jittered ray may fall anywhere in the pixel: the longest chain of the 3x3 neighbourhood
-                const uint32_t w = p.cam.fb_w, hgt = p.cam.fb_h;
-                const uint32_t px = pixel % w, py = pixel / w;
-                const uint32_t x0 = px > 0u ? px - 1u : 0u, x1 = px + 1u < w ? px + 1u : px;
-                const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
-                for (uint32_t y = y0; y <= y1; ++y)
-                    for (uint32_t x = x0; x <= x1; ++x)
-                        pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
-            } else
-                pred = p.chain_hist[pixel];
-        }
-        if (pred == 0u) // no history (first frame, or the neighbourhood queued nothing): pending-stack depth
-            cls = nss >= kLongStack ? 2u : 3u;
-        else
-            cls = (pred < (p.chain_thr >> 24) ? 1u : 0u) + (pred < ((p.chain_thr >> 16) & 255u) ? 1u : 0u) +
-                  (pred < ((p.chain_thr >> 8) & 255u) ? 1u : 0u) + (pred < (p.chain_thr & 255u) ? 1u : 0u);
-    }
+    const uint32_t cls = (p.class_lists && active && neural) ? chain_class(p, pixel, nss) : 0u;
     const uint32_t qmask = __ballot_sync(0xFFFFFFFFu, active && neural);
     if (qmask) {
         const uint32_t below = (1u << lane) - 1u;
@@ -234,21 +213,8 @@ k_primary(const __grid_constant__ RenderParams p)
             for (int i = 0; i < nss; i += 4)
                 q->st[i >> 2] = make_uint4(nstack[i], nstack[i + 1], nstack[i + 2], nstack[i + 3]);
         }
-        if (p.class_lists) {
-            uint32_t rem = qmask; // warp-uniform
-            while (rem) {
-                const int l0     = __ffs(rem) - 1;
-                const uint32_t k = __shfl_sync(0xFFFFFFFFu, cls, l0);
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((qmask >> lane) & 1u) && cls == k);
-                uint32_t cb = 0;
-                if (lane == (uint32_t)l0)
-                    cb = atomicAdd(p.class_count + k, (uint32_t)__popc(m));
-                cb = __shfl_sync(0xFFFFFFFFu, cb, l0);
-                if ((m >> lane) & 1u)
-                    p.class_lists[(size_t)k * p.queue_capacity + cb + __popc(m & below)] = slot;
-                rem &= ~m;
-            }
-        }
+        if (p.class_lists)
+            file_in_class(p, qmask, cls, slot, lane);
     }
     if (active && !neural)
         finish_pixel(p, pixel, ray, h);
@@ -302,6 +268,8 @@ __device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, 
         }
     }
     if constexpr (kPath) {
+        if (p.chain_hist && p.ray_depth == 1u) // camera rays of the multi-bounce pipeline keep the same per-pixel history
+            p.chain_hist[p.paths[id].s3.z] = (uint8_t)(nq < 255u ? nq : 255u);
         if constexpr (kUniform)
             p.paths[id].s3.x = rng; // HybridIntersectionResult takes the traversal data's throughput_rng back (path_module.h:111,141)
         PathHit ph;

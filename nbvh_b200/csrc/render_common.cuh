@@ -233,6 +233,56 @@ __device__ __forceinline__ uint32_t swizzle_pixel(const RenderParams &p, uint32_
     return (by * 4u + (k >> 3)) * w + bx * 8u + (k & 7u);
 }
 
+#ifndef NBVH_LONG_STACK
+#define NBVH_LONG_STACK 4
+#endif
+constexpr int kLongStack = NBVH_LONG_STACK; // pending-stack depth from which a queued ray without history counts as a long query chain
+
+// ---- drain order of the neural ray queue (RenderParams::class_lists; k_primary / k_path_trace<first> file, k_neural drains).
+// Longest-processing-time-first: the rays expected to need the longest query chains start first, so that the tail of the persistent
+// kernel consists of short chains.  The chain length is uncorrelated with anything known about the ray at queue time (DESIGN
+// section 4), but the longest chain among the last frame's camera rays of the 3x3 pixel neighbourhood bounds it: measured on Chess
+// at 1080p, 99.2 % of the rays predicted 1 need 1 query and 0.03 % need more than 2 (profiles/r2_s46_chain_stats.txt).
+__device__ __forceinline__ uint32_t chain_class(const RenderParams &p, uint32_t pixel, int nss)
+{
+    uint32_t pred = 0u;
+    if (p.chain_hist) {
+        if (p.chain_flags & 1u) { // the jittered ray may fall anywhere in the pixel: the longest chain of the 3x3 neighbourhood
+            const uint32_t w = p.cam.fb_w, hgt = p.cam.fb_h;
+            const uint32_t px = pixel % w, py = pixel / w;
+            const uint32_t x0 = px > 0u ? px - 1u : 0u, x1 = px + 1u < w ? px + 1u : px;
+            const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
+            for (uint32_t y = y0; y <= y1; ++y)
+                for (uint32_t x = x0; x <= x1; ++x)
+                    pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
+        } else
+            pred = p.chain_hist[pixel];
+    }
+    if (pred == 0u) // no history (first frame, or the neighbourhood queued nothing): pending-stack depth
+        return nss >= kLongStack ? 2u : 3u;
+    return (pred < (p.chain_thr >> 24) ? 1u : 0u) + (pred < ((p.chain_thr >> 16) & 255u) ? 1u : 0u) +
+           (pred < ((p.chain_thr >> 8) & 255u) ? 1u : 0u) + (pred < (p.chain_thr & 255u) ? 1u : 0u);
+}
+
+// one atomic per class present in the warp; qmask = lanes that queued a ray (warp-uniform), slot = this lane's queue slot
+__device__ __forceinline__ void file_in_class(const RenderParams &p, uint32_t qmask, uint32_t cls, uint32_t slot, uint32_t lane)
+{
+    const uint32_t below = (1u << lane) - 1u;
+    uint32_t rem = qmask;
+    while (rem) {
+        const int l0     = __ffs(rem) - 1;
+        const uint32_t k = __shfl_sync(0xFFFFFFFFu, cls, l0);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, ((qmask >> lane) & 1u) && cls == k);
+        uint32_t cb = 0;
+        if (lane == (uint32_t)l0)
+            cb = atomicAdd(p.class_count + k, (uint32_t)__popc(m));
+        cb = __shfl_sync(0xFFFFFFFFu, cb, l0);
+        if ((m >> lane) & 1u)
+            p.class_lists[(size_t)k * p.queue_capacity + cb + __popc(m & below)] = slot;
+        rem &= ~m;
+    }
+}
+
 // multi-sample launches (render.cu): clear / resolve the shard's pixels
 __global__ void k_clear_accum(const __grid_constant__ RenderParams p);
 __global__ void k_resolve_ldr(const __grid_constant__ RenderParams p, float inv_samples);
