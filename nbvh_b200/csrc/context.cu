@@ -372,7 +372,7 @@ int nbvh_create(int device, const char *config_json, nbvh_ctx **out)
         ctx->long_chain_thr = n <= 0 ? 0u : ((t[0] & 255u) << 24) | ((t[1] & 255u) << 16) | ((t[2] & 255u) << 8) | (t[3] & 255u);
     }
     if (const char *m = getenv("NBVH_CHAIN_PRED"))
-        ctx->chain_pred = (uint32_t)atoi(m) & 3u;
+        ctx->chain_pred = (uint32_t)atoi(m) & 7u;
     if (cudaMalloc(&ctx->d_next_chunk, 8 * sizeof(uint32_t)) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * (CNT_COUNT + 1)) != cudaSuccess) {
         delete ctx;

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t g_pred_dbg(const RenderParams &p, uint32_t p
     const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
     for (uint32_t y = y0; y <= y1; ++y)
         for (uint32_t x = x0; x <= x1; ++x)
-            pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
+            pred = max(pred, chain_hist_value(p, p.chain_hist[y * w + x]));
     return pred < 15u ? pred : 15u;
 }
 #endif
@@ -258,18 +258,12 @@ __device__ __forceinline__ void finish_lane(const RenderParams &p, uint32_t id, 
         atomicAdd(&g_chain_stats[(nq >> 16) * 16u + min(nq & 0xFFFFu, 15u)], 1ull);
         nq &= 0xFFFFu;
 #endif
-        if (p.chain_hist) {
-            uint32_t v = nq < 255u ? nq : 255u;
-            if (p.chain_flags & 2u) { // slow decay: a pixel that needed a long chain recently stays suspicious for a few frames
-                const uint32_t old = p.chain_hist[id];
-                v = max(v, old > 0u ? old - 1u : 0u);
-            }
-            p.chain_hist[id] = (uint8_t)v;
-        }
+        if (p.chain_hist)
+            chain_hist_store(p, id, nq);
     }
     if constexpr (kPath) {
         if (p.chain_hist && p.ray_depth == 1u) // camera rays of the multi-bounce pipeline keep the same per-pixel history
-            p.chain_hist[p.paths[id].s3.z] = (uint8_t)(nq < 255u ? nq : 255u);
+            chain_hist_store(p, p.paths[id].s3.z, nq);
         if constexpr (kUniform)
             p.paths[id].s3.x = rng; // HybridIntersectionResult takes the traversal data's throughput_rng back (path_module.h:111,141)
         PathHit ph;

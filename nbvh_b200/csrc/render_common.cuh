@@ -243,6 +243,26 @@ constexpr int kLongStack = NBVH_LONG_STACK; // pending-stack depth from which a 
 // kernel consists of short chains.  The chain length is uncorrelated with anything known about the ray at queue time (DESIGN
 // section 4), but the longest chain among the last frame's camera rays of the 3x3 pixel neighbourhood bounds it: measured on Chess
 // at 1080p, 99.2 % of the rays predicted 1 need 1 query and 0.03 % need more than 2 (profiles/r2_s46_chain_stats.txt).
+// History byte: the chain length of the last frame; with chain_flags bit 2 two nibbles, the last frame's (low) and the one before
+// (high), and the prediction is their maximum -- halves the mispredicted long chains among the rays drained last.
+__device__ __forceinline__ uint32_t chain_hist_value(const RenderParams &p, uint8_t v)
+{
+    return (p.chain_flags & 4u) ? max((uint32_t)v & 15u, (uint32_t)v >> 4) : (uint32_t)v;
+}
+__device__ __forceinline__ void chain_hist_store(const RenderParams &p, uint32_t pixel, uint32_t nq)
+{
+    if (p.chain_flags & 4u) {
+        const uint32_t old = p.chain_hist[pixel];
+        p.chain_hist[pixel] = (uint8_t)(((old & 15u) << 4) | (nq < 15u ? nq : 15u));
+        return;
+    }
+    uint32_t v = nq < 255u ? nq : 255u;
+    if (p.chain_flags & 2u) { // slow decay: a pixel that needed a long chain recently stays suspicious for a few frames
+        const uint32_t old = p.chain_hist[pixel];
+        v = max(v, old > 0u ? old - 1u : 0u);
+    }
+    p.chain_hist[pixel] = (uint8_t)v;
+}
 __device__ __forceinline__ uint32_t chain_class(const RenderParams &p, uint32_t pixel, int nss)
 {
     uint32_t pred = 0u;
@@ -254,9 +274,9 @@ __device__ __forceinline__ uint32_t chain_class(const RenderParams &p, uint32_t 
             const uint32_t y0 = py > 0u ? py - 1u : 0u, y1 = py + 1u < hgt ? py + 1u : py;
             for (uint32_t y = y0; y <= y1; ++y)
                 for (uint32_t x = x0; x <= x1; ++x)
-                    pred = max(pred, (uint32_t)p.chain_hist[y * w + x]);
+                    pred = max(pred, chain_hist_value(p, p.chain_hist[y * w + x]));
         } else
-            pred = p.chain_hist[pixel];
+            pred = chain_hist_value(p, p.chain_hist[pixel]);
     }
     if (pred == 0u) // no history (first frame, or the neighbourhood queued nothing): pending-stack depth
         return nss >= kLongStack ? 2u : 3u;
