@@ -392,6 +392,14 @@ int nbvh_enable_kernel_timing(nbvh_ctx *ctx, int enable);
  * launching stream; nbvh_get_stage_times synchronises on them, returns the two summed durations and re-arms. */
 int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames);
 int nbvh_get_stage_times(nbvh_ctx *ctx, float *primary_ms_total, float *neural_ms_total, uint32_t *frames);
+/* Drain order of the neural ray queue (scheduling only: frames, hit records and counters do not depend on it).  The reference's
+ * wavefront compaction keeps arrival order (path_module.cu:109-137); here the persistent tile kernel pulls the queued camera rays
+ * in the order of their EXPECTED query-chain length, longest first: the expectation is the longest chain the camera rays of the
+ * pixel's 3x3 neighbourhood needed in the last frame (a one-byte-per-pixel history the kernel maintains), and rays are filed
+ * under five classes with the limits t0 >= t1 >= t2 >= t3 (class = number of limits the expectation stays below; default
+ * 4, 3, 2, 2).  All limits 0: arrival order.  flags: bit 0 = 3x3 neighbourhood maximum (default), bit 1 = decaying maximum,
+ * bit 2 = maximum over the last two frames. */
+int nbvh_set_queue_order(nbvh_ctx *ctx, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t flags);
 /* the same for the optimisation step: the next `max_steps` nbvh_training_forward_backward + nbvh_optimizer_step pairs record events
  * between their kernels; nbvh_get_training_stage_times returns the summed milliseconds of
  * {k_encode_features, k_train_mlp, k_grid_backward (both launches), wait for the gradient exchange, k_adam} and re-arms. */

@@ -159,6 +159,7 @@ SYMBOLS = {
     "nbvh_get_kernel_time": (_i, [_vp, C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_enable_kernel_timing": (_i, [_vp, _i]),
     "nbvh_enable_stage_timing": (_i, [_vp, _u32]),
+    "nbvh_set_queue_order": (_i, [_vp, _u32, _u32, _u32, _u32, _u32]),
     "nbvh_get_stage_times": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_u32)]),
     "nbvh_training_step": (_i, [_vp, _vp, _vp, _u32, _vp, C.POINTER(_f), _vp]),
     "nbvh_training_forward_backward": (_i, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp]),

@@ -817,6 +817,17 @@ int nbvh_get_kernel_time(nbvh_ctx *ctx, float *total_ms, uint32_t *launches)
     return NBVH_OK;
 }
 
+int nbvh_set_queue_order(nbvh_ctx *ctx, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t flags)
+{
+    if (!ctx)
+        return NBVH_ERR_INVALID_ARG;
+    if (t0 > 255u || t0 < t1 || t1 < t2 || t2 < t3)
+        return fail(ctx, NBVH_ERR_INVALID_ARG, "nbvh_set_queue_order: class limits must be descending and below 256");
+    ctx->long_chain_thr = (t0 << 24) | (t1 << 16) | (t2 << 8) | t3;
+    ctx->chain_pred     = flags & 7u;
+    return NBVH_OK;
+}
+
 int nbvh_enable_stage_timing(nbvh_ctx *ctx, uint32_t max_frames)
 {
     DeviceGuard device_guard(ctx);

@@ -612,6 +612,11 @@ class NeuralPathModule:
         self._check(self._lib.nbvh_get_kernel_time(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def set_queue_order(self, limits=(4, 3, 2, 2), flags=1):
+        """Drain order of the neural ray queue by expected query-chain length (scheduling only; limits (0, 0, 0, 0) = arrival order)."""
+        t = [int(x) for x in limits]
+        self._check(self._lib.nbvh_set_queue_order(self._h, t[0], t[1], t[2], t[3], int(flags)))
+
     def enable_stage_timing(self, max_frames):
         """Event triples around k_primary / k_neural for the next `max_frames` frames (no host synchronisation)."""
         self._check(self._lib.nbvh_enable_stage_timing(self._h, int(max_frames)))

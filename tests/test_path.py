@@ -318,6 +318,36 @@ def test_gpu_interleaved_tile_shards_reproduce_full_frame(syn_path, torch_cuda, 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("max_depth", [1, 3])
+def test_gpu_queue_drain_order_does_not_change_results(syn_path, torch_cuda, max_depth):
+    """nbvh_set_queue_order: draining the neural ray queue by expected chain length (per-pixel history of the last frame) is
+    scheduling only -- accumulation buffer, sRGB8 frame, hit records and the work counters are bit-identical to arrival order,
+    for every class layout / predictor, on a cold history (first frame) and on a warm one."""
+    mod, W, H = syn_path["mod"], syn_path["W"], syn_path["H"]
+    mod.max_depth = max_depth
+    results = []
+    try:
+        for limits, flags in (((0, 0, 0, 0), 0), ((4, 3, 2, 2), 1), ((2, 2, 2, 2), 0), ((6, 4, 3, 2), 3), ((5, 4, 3, 2), 5)):
+            mod.set_queue_order(limits, flags)
+            hits = mod.attach_hit_buffer(W * H)
+            mod.reset_counters()
+            acc, ldr = gpu_render(mod, torch_cuda, W, H, spp=4)
+            c = mod.counters()
+            results.append((acc.copy(), ldr.copy(), hits.cpu().numpy().copy(), {k: c[k] for k in ("rays", "queries", "nbvh_steps", "queued_rays")}))
+    finally:
+        mod.set_queue_order()
+        mod.attach_hit_buffer(0)
+    assert results[0][3]["queued_rays"] > 0
+    for acc, ldr, hits, cnt in results[1:]:
+        assert (acc.view(np.uint32) == results[0][0].view(np.uint32)).all()
+        assert (ldr == results[0][1]).all()
+        assert (hits == results[0][2]).all()
+        assert cnt == results[0][3]
+    with pytest.raises(Exception):
+        mod.set_queue_order((2, 3, 2, 2), 1)  # limits must be descending
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_depth", [1, 3])
 def test_gpu_multi_sample_launch_equals_sample_by_sample(syn_path, torch_cuda, max_depth):
     """nbvh_render_samples: 5 samples per pixel in one launch sequence (and 3 + 2 over two shards) == five nbvh_render calls, up
     to the fp32 order of the per-pixel sum (16-byte reductions instead of read-modify-write); max_depth 1 exercises the
