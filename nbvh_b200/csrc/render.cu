@@ -37,6 +37,9 @@ constexpr int kNeuralCtasPerSm = NBVH_NEURAL_CTAS_PER_SM;
 #ifndef NBVH_PHASE_TIMING
 #define NBVH_PHASE_TIMING 0 // development builds: per-phase SM-cycle sums of k_neural (tools/perf_r2.py prints them)
 #endif
+#ifndef NBVH_PHASE_SPARSE
+#define NBVH_PHASE_SPARSE 0
+#endif
 #ifndef NBVH_LONG_STACK
 #define NBVH_LONG_STACK 4
 #endif
@@ -345,7 +348,9 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
     for (;;) {
 #if NBVH_PHASE_TIMING
         const long long pt0 = clock64();
+#if !NBVH_PHASE_SPARSE
         const uint32_t pdr  = exhausted ? 4u : 0u;
+#endif
 #endif
         // ---------------- walk phase: every lane works until it owns a pending interval (or the queue is drained)
         for (int round = 0; round < kWalkRounds; ++round) {
@@ -513,7 +518,12 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
         // ---------------- MLP on tensor cores (a10), decode + closest-hit update (a11)
         float y[8];
 #if NBVH_PHASE_TIMING
+#if NBVH_PHASE_SPARSE // second category = sparse iterations (at most NBVH_PHASE_SPARSE active rows in the tile) instead of "queue exhausted"
+        const bool ph_sparse = __popc(tile_masks[0]) + __popc(tile_masks[1]) + __popc(tile_masks[2]) + __popc(tile_masks[3]) <= NBVH_PHASE_SPARSE;
+        mlp_tile_forward(nc, t, row, y, ph_sparse ? mp_d : mp_s);
+#else
         mlp_tile_forward(nc, t, row, y, exhausted ? mp_d : mp_s);
+#endif
 #else
         mlp_tile_forward(nc, t, row, y);
 #endif
@@ -521,6 +531,9 @@ k_neural(const __grid_constant__ RenderParams p, const __grid_constant__ NetCons
 #if NBVH_PHASE_TIMING
         {
             const long long pt4 = clock64();
+#if NBVH_PHASE_SPARSE
+            const uint32_t pdr = ph_sparse ? 4u : 0u;
+#endif
             ph[pdr + 0] += (unsigned long long)(pt1 - pt0), ph[pdr + 1] += (unsigned long long)(pt2 - pt1);
             ph[pdr + 2] += (unsigned long long)(pt3 - pt2), ph[pdr + 3] += (unsigned long long)(pt4 - pt3);
             iters_drain += pdr ? 1u : 0u;
