@@ -775,6 +775,88 @@ k_grid_backward(const __grid_constant__ NetConst nc, const float *__restrict__ i
     }
 }
 
+// The privatised (dense, coarse) levels with one thread per SAMPLE: the points of a segment mostly fall into the same cell of a coarse
+// level (cell edge 1/8 or 1/16 of the scene box against a leaf-sized segment), so their 8 x 4 corner contributions are summed in
+// registers and flushed once per distinct cell -- up to n_points times fewer shared-memory float atomics, which are compare-and-swap
+// loops on sm_100 (ATOMS.CAST.SPIN) and bound these launches (85 % L1TEX, profiles/r2_s59_full_ncu.txt).
+__global__ void __launch_bounds__(256)
+k_grid_backward_merge(const __grid_constant__ NetConst nc, const float *__restrict__ in, const uint8_t *__restrict__ dfeat, uint32_t batch,
+                      uint32_t n_in_dims, uint32_t first_level, uint32_t use_smem, float *__restrict__ grid_grads)
+{
+    extern __shared__ float sg[];
+    const uint32_t level = first_level + blockIdx.y;
+    const GridLevel &L   = nc.lv[level];
+    float *gbase         = grid_grads + 4u * (size_t)L.offset;
+    if (use_smem) {
+        for (uint32_t i = threadIdx.x; i < L.size * 4u; i += blockDim.x)
+            sg[i] = 0.f;
+        __syncthreads();
+    }
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < batch; s += gridDim.x * blockDim.x) {
+        float acc[8][4];
+        uint32_t idx[8];
+        bool have = false;
+        auto flush = [&]() {
+            if (use_smem) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float *dst = sg + 4u * idx[c];
+                    atomicAdd(dst + 0, acc[c][0]);
+                    atomicAdd(dst + 1, acc[c][1]);
+                    atomicAdd(dst + 2, acc[c][2]);
+                    atomicAdd(dst + 3, acc[c][3]);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    red_add_v4(gbase + 4u * (size_t)idx[c], acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+            }
+        };
+        for (uint32_t p = 0; p < nc.n_points; ++p) {
+            const uint32_t j = p * nc.n_levels + level;
+            const uint2 raw  = __ldg(reinterpret_cast<const uint2 *>(dfeat + feat_slot_offset(s, j, nc.in_k)));
+            if ((raw.x | raw.y) == 0u)
+                continue; // masked sample (target not visible) or dead ReLU path: nothing to scatter
+            const float2 g01 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+            const float2 g23 = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+            const float *x   = in + (size_t)s * n_in_dims + 3u * p;
+            GridCorner gc;
+            grid_corners(L, __ldg(x), __ldg(x + 1), __ldg(x + 2), gc);
+            bool same = have;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                same = same && gc.index[c] == idx[c];
+            if (!same) {
+                if (have)
+                    flush();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    idx[c]    = gc.index[c];
+                    acc[c][0] = gc.weight[c] * g01.x, acc[c][1] = gc.weight[c] * g01.y;
+                    acc[c][2] = gc.weight[c] * g23.x, acc[c][3] = gc.weight[c] * g23.y;
+                }
+                have = true;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    acc[c][0] += gc.weight[c] * g01.x, acc[c][1] += gc.weight[c] * g01.y;
+                    acc[c][2] += gc.weight[c] * g23.x, acc[c][3] += gc.weight[c] * g23.y;
+                }
+            }
+        }
+        if (have)
+            flush();
+    }
+    if (!use_smem)
+        return;
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < L.size; e += blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4 *>(sg + 4u * e);
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+            red_add_v4(gbase + 4u * (size_t)e, v.x, v.y, v.z, v.w);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k_adam
 // optimizers/adam.h:48-123 (relative/absolute decay 0, no clipping, AdaBound off).  lr already carries the
 // ExponentialDecay factor.  Also writes the fp16 parameter and, for matrix weights, its slot in the packed weight image.
@@ -833,7 +915,9 @@ cudaError_t configure_training(uint32_t wimg_bytes, uint32_t in_k, uint32_t n_la
         return e;
     if ((e = allow_max_dynamic_smem(reinterpret_cast<const void *>(k_train_mlp<2>))) != cudaSuccess)
         return e;
-    return cudaFuncSetAttribute(k_grid_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if ((e = cudaFuncSetAttribute(k_grid_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)) != cudaSuccess)
+        return e;
+    return cudaFuncSetAttribute(k_grid_backward_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }
 
 cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t batch, uint32_t n_in_dims, uint8_t *feat, int num_sms,
@@ -885,6 +969,7 @@ cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint
 {
     if (batch == 0)
         return cudaSuccess;
+    static const bool per_point_all = [] { const char *e = getenv("NBVH_GRID_BACKWARD_PER_POINT"); return e && e[0] == '1'; }(); // A/B measurements
     // leading levels small enough for a 64 KB shared-memory table
     uint32_t n_small = 0;
     while (n_small < nc.n_levels && nc.lv[n_small].size * 16u <= 64u * 1024u)
@@ -896,14 +981,39 @@ cudaError_t launch_grid_backward(const NetConst &nc, const float *in, const uint
         const uint32_t smem = nc.lv[l].size * 16u;
         uint32_t per_sm     = (200u * 1024u) / (smem + 1024u);
         per_sm              = per_sm > 8u ? 8u : per_sm < 1u ? 1u : per_sm;
-        uint32_t bx         = (uint32_t)((total + 255u) / 256u);
         const uint32_t cap  = (uint32_t)num_sms * per_sm;
+        if (!per_point_all) {
+            uint32_t bx = (batch + 255u) / 256u;
+            if (bx > cap)
+                bx = cap;
+            k_grid_backward_merge<<<bx, 256, smem, stream>>>(nc, in, dfeat, batch, n_in_dims, l, 1u, grid_grads);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                return e;
+            continue;
+        }
+        uint32_t bx         = (uint32_t)((total + 255u) / 256u);
         if (bx > cap)
             bx = cap;
         k_grid_backward<<<dim3(bx, 1), 256, smem, stream>>>(nc, in, dfeat, batch, n_in_dims, l, 1u, grid_grads);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess)
             return e;
+    }
+    // the other levels: the same per-sample kernel with 16-byte reductions to L2 (measured at 2^18 on B200, profiles/r2_s63: all six
+    // levels through it 0.247 ms for the whole backward pass, none 0.287 ms -- merging still pays on levels 2 and 3, and on the hashed
+    // levels one thread per sample issues its three points' reductions back to back); NBVH_GRID_BACKWARD_PER_POINT=1 = the old mapping
+    if (!per_point_all && n_small < nc.n_levels) {
+        const uint32_t k = nc.n_levels - n_small;
+        uint32_t bx = (batch + 255u) / 256u;
+        const uint32_t cap = (uint32_t)num_sms * 8u;
+        if (bx > cap)
+            bx = cap;
+        k_grid_backward_merge<<<dim3(bx, k), 256, 0, stream>>>(nc, in, dfeat, batch, n_in_dims, n_small, 0u, grid_grads);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+        n_small += k;
     }
     if (n_small < nc.n_levels) {
         uint32_t bx = (uint32_t)((total + 255u) / 256u);
