@@ -103,6 +103,36 @@ k_encode_features(const __grid_constant__ NetConst nc, const float *__restrict__
     }
 }
 
+// One thread per (sample, level): the points of a segment that fall into the same cell of the level share ONE gather of its eight
+// corner entries (coarse levels: mostly all of them), blended per point with grid_level_features' arithmetic in its order -- same bits,
+// fewer lookups for a kernel that runs at 93 % of the L1TEX peak.  Consecutive lanes = consecutive samples of one level.
+__global__ void __launch_bounds__(256)
+k_encode_features_merge(const __grid_constant__ NetConst nc, const float *__restrict__ in, uint32_t batch, uint32_t padded_batch,
+                        uint32_t n_in_dims, uint8_t *__restrict__ feat)
+{
+    const uint64_t total = (uint64_t)padded_batch * nc.n_levels;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t l = (uint32_t)(i / padded_batch), s = (uint32_t)(i % padded_batch);
+        if (s >= batch) {
+            for (uint32_t p = 0; p < nc.n_points; ++p)
+                *reinterpret_cast<uint2 *>(feat + feat_slot_offset(s, p * nc.n_levels + l, nc.in_k)) = make_uint2(0u, 0u);
+            continue;
+        }
+        const GridLevel &L = nc.lv[l];
+        GridCell prev;
+        prev.gx = prev.gy = prev.gz = 0u, prev.px = prev.py = prev.pz = 0.f;
+        uint2 g[8];
+        for (uint32_t p = 0; p < nc.n_points; ++p) {
+            const float *x   = in + (size_t)s * n_in_dims + 3u * p;
+            const GridCell c = grid_cell(L, __ldg(x), __ldg(x + 1), __ldg(x + 2));
+            if (p == 0u || c.gx != prev.gx || c.gy != prev.gy || c.gz != prev.gz)
+                grid_gather_cell(nc.grid, L, c, g);
+            prev = c;
+            *reinterpret_cast<uint2 *>(feat + feat_slot_offset(s, p * nc.n_levels + l, nc.in_k)) = grid_blend_cell(c, g);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ composite loss (a18)
 __device__ __forceinline__ void loss_and_gradient(float target, float prediction, uint32_t type, float &loss, float &grad)
 {
@@ -926,9 +956,18 @@ cudaError_t launch_encode_features(const NetConst &nc, const float *in, uint32_t
     if (batch == 0)
         return cudaSuccess;
     const uint32_t padded = (batch + kTileRows - 1u) / kTileRows * kTileRows;
+    const uint64_t cap    = (uint64_t)num_sms * 32u;
+    // measured at 2^18 on B200 (profiles/r2_s65): 0.106 -> 0.101 ms; NBVH_ENCODE_MERGE=0 = one thread per (sample, point, level)
+    static const bool merge = [] { const char *e = getenv("NBVH_ENCODE_MERGE"); return !(e && e[0] == '0'); }();
+    if (merge && (nc.in_k >> 2) == nc.n_points * nc.n_levels) {
+        uint64_t blocks = ((uint64_t)padded * nc.n_levels + 255u) / 256u;
+        if (blocks > cap)
+            blocks = cap;
+        k_encode_features_merge<<<(uint32_t)blocks, 256, 0, stream>>>(nc, in, batch, padded, n_in_dims, feat);
+        return cudaGetLastError();
+    }
     const uint64_t total  = (uint64_t)padded * (nc.in_k >> 2);
     uint64_t blocks       = (total + 255u) / 256u;
-    const uint64_t cap    = (uint64_t)num_sms * 32u;
     if (blocks > cap)
         blocks = cap;
     k_encode_features<<<(uint32_t)blocks, 256, 0, stream>>>(nc, in, batch, padded, n_in_dims, feat);
