@@ -83,6 +83,11 @@ public:
     {
         check(nbvh_render_samples(m_ctx, first_spp, n_spp, sample_offset, shard, n_shards, stream));
     }
+    // drain order of the neural ray queue by expected query-chain length (scheduling only; all limits 0 = arrival order)
+    void set_queue_order(uint32_t t0 = 4, uint32_t t1 = 3, uint32_t t2 = 2, uint32_t t3 = 2, uint32_t flags = 1)
+    {
+        check(nbvh_set_queue_order(m_ctx, t0, t1, t2, t3, flags));
+    }
     void neural_render_host(uint32_t accumulated_spp, uint32_t sample_offset, uint8_t *ldr_host, const nbvh_camera_params *camera = nullptr)
     {
         check(nbvh_render_host(m_ctx, accumulated_spp, sample_offset, camera, ldr_host, nullptr));
