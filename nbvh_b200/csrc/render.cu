@@ -135,8 +135,11 @@ __device__ __forceinline__ uint32_t g_pred_dbg(const RenderParams &p, uint32_t p
 }
 #endif
 // ------------------------------------------------------------------------------------------------ k_primary
-// 64 registers -> four CTAs per SM (measured: 0.386 -> 0.367 ms at 1080p; the kernel is issue-bound and takes the extra warps)
-__global__ void __launch_bounds__(256, 4)
+// 64 registers -> 32 resident warps per SM (measured: 0.386 -> 0.367 ms at 1080p against 80 registers; the kernel is issue-bound and takes the extra warps)
+#ifndef NBVH_PRIMARY_THREADS
+#define NBVH_PRIMARY_THREADS 128 // measured on B200 (gpurun s69): 64 / 128 / 256 / 512 threads -> 0.347 / 0.342 / 0.346 / 0.377 ms per 1080p launch
+#endif
+__global__ void __launch_bounds__(NBVH_PRIMARY_THREADS, 1024 / NBVH_PRIMARY_THREADS)
 k_primary(const __grid_constant__ RenderParams p)
 {
     const uint32_t lane  = threadIdx.x & 31u;
@@ -646,7 +649,8 @@ cudaError_t launch_render_split(const RenderParams &rp, const NetConst &nc, int 
     const uint32_t n_chunks = (slots + 31u) >> 5;
     if (rp.spp_count > 1u && rp.sample_idx == 0) // sample 0 overwrites the accumulation; here: clear, then 16-byte reductions
         k_clear_accum<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp);
-    k_primary<<<(n_chunks + 7u) / 8u, 256, 0, stream>>>(rp);
+    constexpr uint32_t kWarpsPerBlock = NBVH_PRIMARY_THREADS / 32;
+    k_primary<<<(n_chunks + kWarpsPerBlock - 1u) / kWarpsPerBlock, NBVH_PRIMARY_THREADS, 0, stream>>>(rp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return e;
