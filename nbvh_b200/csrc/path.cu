@@ -99,7 +99,10 @@ __device__ __forceinline__ bool shade_and_scatter(const RenderParams &p, const P
 // One thread per path of the current (compacted) list: shades the closest hit, splats finished paths, and appends the
 // survivors -- with their bounce ray -- to the next list (warp ballot/prefix-sum compaction, one atomic per warp), so
 // that the following trace and network kernels run on dense warps.
-__global__ void __launch_bounds__(256)
+#ifndef NBVH_SHADE_THREADS
+#define NBVH_SHADE_THREADS 256
+#endif
+__global__ void __launch_bounds__(NBVH_SHADE_THREADS)
 k_path_shade(const __grid_constant__ RenderParams p, const __grid_constant__ PathConst pc, const __grid_constant__ PathIo io)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -140,8 +143,11 @@ k_path_shade(const __grid_constant__ RenderParams p, const __grid_constant__ Pat
 // One thread per path of the list (kFirst: per pixel, camera rays): TLAS walk + classical BLAS closest hits + first
 // N-BVH interval, exactly like k_primary; rays with a pending interval go to the neural ray queue (entry id = list index),
 // all others leave their closest hit in path_hits.
+#ifndef NBVH_TRACE_THREADS
+#define NBVH_TRACE_THREADS 64 // measured on B200 (gpurun s71), config 2b frame: 256 / 128 / 64 threads -> 2.406 / 2.343 / 2.325 ms (72 registers: 24 -> 28 resident warps)
+#endif
 template <bool kFirst>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(NBVH_TRACE_THREADS)
 k_path_trace(const __grid_constant__ RenderParams p, const __grid_constant__ PathIo io)
 {
     const uint32_t lane  = threadIdx.x & 31u;
@@ -311,7 +317,7 @@ cudaError_t launch_trace_rays(const RenderParams &rp_in, const NetConst &nc, con
         return e;
     const uint32_t blocks = (n + 255u) / 256u;
     k_rays_to_paths<<<blocks, 256, 0, stream>>>(o, d, n, ray_depth, paths, counters);
-    k_path_trace<false><<<blocks, 256, 0, stream>>>(rp, io);
+    k_path_trace<false><<<(n + NBVH_TRACE_THREADS - 1u) / NBVH_TRACE_THREADS, NBVH_TRACE_THREADS, 0, stream>>>(rp, io);
     if ((e = cudaGetLastError()) != cudaSuccess)
         return e;
     if ((e = launch_neural(rp, nc, num_sms, true, stream)) != cudaSuccess)
@@ -383,6 +389,7 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
     RenderParams rp       = rp_in;
     const uint32_t slots  = rp.pixel_count * (rp.spp_count > 1u ? rp.spp_count : 1u);
     const uint32_t blocks = ((slots + 31u) / 32u + 7u) / 8u;
+    const uint32_t tblocks = (slots + NBVH_TRACE_THREADS - 1u) / NBVH_TRACE_THREADS;
     cudaError_t e;
     if (rp.spp_count > 1u && rp.sample_idx == 0) // sample 0 overwrites the accumulation (accumulate_pixel_value); here: clear, then reduce
         k_clear_accum<<<(rp.pixel_count + 255u) / 256u, 256, 0, stream>>>(rp);
@@ -398,17 +405,17 @@ cudaError_t launch_render_path(const RenderParams &rp_in, const PathConst &pc, c
         io.count_in  = depth == 1u ? nullptr : c + 2; // list length written by the previous shade pass
         io.count_out = c + kPathCountersPerDepth + 2;
         if (depth == 1u) {
-            k_path_trace<true><<<blocks, 256, 0, stream>>>(rp, io);
+            k_path_trace<true><<<tblocks, NBVH_TRACE_THREADS, 0, stream>>>(rp, io);
         } else {
             rp.class_lists = nullptr, rp.class_count = nullptr, rp.chain_hist = nullptr; // bounce rays: arrival order
             rp.nbvh = nbvh_bounce; // path_lod_switch: bounce rays may walk a coarser LoD (neural_bvh_module_common.cuh:333-335)
-            k_path_trace<false><<<blocks, 256, 0, stream>>>(rp, io);
+            k_path_trace<false><<<tblocks, NBVH_TRACE_THREADS, 0, stream>>>(rp, io);
         }
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
         if ((e = launch_neural(rp, nc, num_sms, true, stream)) != cudaSuccess)
             return e;
-        k_path_shade<<<blocks, 256, 0, stream>>>(rp, pc, io);
+        k_path_shade<<<(slots + NBVH_SHADE_THREADS - 1u) / NBVH_SHADE_THREADS, NBVH_SHADE_THREADS, 0, stream>>>(rp, pc, io);
         if ((e = cudaGetLastError()) != cudaSuccess)
             return e;
     }
